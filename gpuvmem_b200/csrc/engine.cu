@@ -1,0 +1,328 @@
+// engine.cu — the C-ABI (include/gvm_b200.h): lifecycle, uploads, and the host
+// drivers of the hot path. The kernels live in forward.cu, grad_simt.cu,
+// grad_umma.cu, priors.cu, vecops.cu and weights_grid.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "gvm_internal.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void gvm_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void gvm_ev_begin(gvm_engine* e) {
+  if (e->ev_used + 2 > (int)e->ev.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    e->ev.push_back(a);
+    e->ev.push_back(b);
+  }
+  cudaEventRecord(e->ev[e->ev_used], e->stream);
+}
+void gvm_ev_end(gvm_engine* e) {
+  cudaEventRecord(e->ev[e->ev_used + 1], e->stream);
+  e->ev_used += 2;
+}
+
+extern "C" {
+
+const char* gvm_last_error(void) { return g_err; }
+int gvm_version(void) { return 100; }
+
+int gvm_create(const gvm_config* cfg, gvm_engine** out) {
+  if (!cfg || !out) { gvm_set_error("gvm_create: null argument"); return 1; }
+  if (cfg->M != cfg->N || cfg->N <= 0) {
+    gvm_set_error("gvm_create: M == N > 0 required (got %ld x %ld); the reference kernels assume it",
+                  (long)cfg->M, (long)cfg->N);
+    return 1;
+  }
+  if (cfg->N > 65536) { gvm_set_error("gvm_create: N > 65536 unsupported"); return 1; }
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev < 1) {
+    gvm_set_error("gvm_create: no CUDA device (%s); this engine has no CPU fallback",
+                  cudaGetErrorString(err));
+    return 1;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { gvm_set_error("gvm_create: bad device %d", cfg->device); return 1; }
+  GVM_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  GVM_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    gvm_set_error("gvm_create: built for sm_100a only, device is sm_%d%d", prop.major, prop.minor);
+    return 1;
+  }
+  gvm_engine* e = new gvm_engine();
+  e->cfg = *cfg;
+  e->sm_count = prop.multiProcessorCount;
+  GVM_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  e->own_stream = true;
+  const size_t MN = (size_t)cfg->M * cfg->N;
+  GVM_CUDA(cudaMalloc(&e->I_nu, MN * sizeof(float2)));
+  GVM_CUDA(cudaMalloc(&e->V, MN * sizeof(float2)));
+  GVM_CUDA(cudaMalloc(&e->noise, MN * sizeof(float)));
+  GVM_CUDA(cudaMemset(e->noise, 0, MN * sizeof(float)));
+  GVM_CUDA(cudaMalloc(&e->dchi2, MN * sizeof(float)));
+  GVM_CUDA(cudaMalloc(&e->pixtab, 2 * (size_t)cfg->N * sizeof(float)));
+  GVM_CUDA(cudaMemset(e->pixtab, 0, 2 * (size_t)cfg->N * sizeof(float)));
+  GVM_CUDA(cudaMalloc(&e->I_stage, 2 * MN * sizeof(float)));
+  GVM_CUDA(cudaMalloc(&e->grad_stage, 2 * MN * sizeof(float)));
+  e->red_blocks = e->sm_count * 8;
+  e->red_slots = 1024;
+  const size_t rp = (size_t)e->red_slots * e->red_blocks;
+  GVM_CUDA(cudaMalloc(&e->red_partials, rp * (sizeof(double) + sizeof(float))));
+  GVM_CUDA(cudaMalloc(&e->red_counter, e->red_slots * sizeof(unsigned int)));
+  GVM_CUDA(cudaMemset(e->red_counter, 0, e->red_slots * sizeof(unsigned int)));
+  GVM_CUDA(cudaMalloc(&e->red_sum, e->red_slots * sizeof(double)));
+  GVM_CUDA(cudaMemset(e->red_sum, 0, e->red_slots * sizeof(double)));
+  GVM_CUDA(cudaMalloc(&e->red_Z, e->red_slots * sizeof(long)));
+  GVM_CUDA(cudaMemset(e->red_Z, 0, e->red_slots * sizeof(long)));
+  GVM_CUDA(cudaMalloc(&e->red_max, 3 * e->red_slots * sizeof(float)));
+  GVM_CUDA(cudaMemset(e->red_max, 0, 3 * e->red_slots * sizeof(float)));
+  GVM_CUDA(cudaMalloc(&e->red_out, 8 * sizeof(double)));
+  GVM_CUDA(cudaMemset(e->red_out, 0, 8 * sizeof(double)));
+  GVM_CUDA(cudaMallocHost(&e->h_red, 8 * sizeof(double)));
+  GVM_CUDA(cudaMalloc(&e->tile_counter, 16 * sizeof(unsigned int)));
+  GVM_CUDA(cudaMemset(e->tile_counter, 0, 16 * sizeof(unsigned int)));
+  // cufftPlan2d(N, M, C2C): src/functions.cu:2149
+  if (cufftPlan2d(&e->plan, (int)cfg->N, (int)cfg->M, CUFFT_C2C) != CUFFT_SUCCESS) {
+    gvm_set_error("gvm_create: cufftPlan2d failed");
+    return 1;
+  }
+  e->have_plan = true;
+  cufftSetStream(e->plan, e->stream);
+  *out = e;
+  return 0;
+}
+
+static void free_channel(GvmChannel& c) {
+  cudaFree(c.uvw_l); cudaFree(c.cell); cudaFree(c.frac); cudaFree(c.Vo); cudaFree(c.w);
+  cudaFree(c.Vr); cudaFree(c.Vm); cudaFree(c.du64); cudaFree(c.dv64); cudaFree(c.wz);
+}
+
+int gvm_destroy(gvm_engine* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& c : e->chans) free_channel(c);
+  if (e->have_plan) cufftDestroy(e->plan);
+  cudaFree(e->I_nu); cudaFree(e->V); cudaFree(e->noise); cudaFree(e->gcf); cudaFree(e->dchi2);
+  cudaFree(e->grad_scratch); cudaFree(e->pixtab); cudaFree(e->I_stage); cudaFree(e->grad_stage);
+  cudaFree(e->red_partials); cudaFree(e->red_counter); cudaFree(e->red_sum); cudaFree(e->red_Z);
+  cudaFree(e->red_max); cudaFree(e->red_out); cudaFreeHost(e->h_red); cudaFree(e->tile_counter);
+  for (auto ev : e->ev) cudaEventDestroy(ev);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return 0;
+}
+
+int gvm_set_stream(gvm_engine* e, void* s) {
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  e->own_stream = false;
+  e->stream = (cudaStream_t)s;
+  if (e->have_plan) cufftSetStream(e->plan, e->stream);
+  return 0;
+}
+void* gvm_get_stream(gvm_engine* e) { return (void*)e->stream; }
+int gvm_synchronize(gvm_engine* e) {
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int gvm_set_scalars(gvm_engine* e, float fg_scale, float noise_cut, float threshold) {
+  e->cfg.fg_scale = fg_scale;
+  e->cfg.noise_cut = noise_cut;
+  e->cfg.threshold = threshold;
+  return 0;
+}
+int gvm_set_grad_mode(gvm_engine* e, int m) { e->cfg.grad_mode = m; return 0; }
+int gvm_set_flag_opt(gvm_engine* e, int f) { e->flag_opt = f; return 0; }
+
+int gvm_set_noise_image(gvm_engine* e, const float* noise, int src_is_device) {
+  const size_t MN = (size_t)e->cfg.M * e->cfg.N;
+  GVM_CUDA(cudaMemcpyAsync(e->noise, noise, MN * sizeof(float),
+                           src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int gvm_get_noise_image(gvm_engine* e, float* out) {
+  const size_t MN = (size_t)e->cfg.M * e->cfg.N;
+  GVM_CUDA(cudaMemcpyAsync(out, e->noise, MN * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+int gvm_set_gcf(gvm_engine* e, const float* gcf_host) {
+  const size_t MN = (size_t)e->cfg.M * e->cfg.N;
+  if (!gcf_host) { cudaFree(e->gcf); e->gcf = nullptr; return 0; }
+  if (!e->gcf) GVM_CUDA(cudaMalloc(&e->gcf, MN * sizeof(float)));
+  GVM_CUDA(cudaMemcpyAsync(e->gcf, gcf_host, MN * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int gvm_add_channel(gvm_engine* e, const gvm_channel_desc* desc, int64_t Z, const double* uvw_m,
+                    const float* Vo, const float* w, int* chan_out) {
+  if (!e || !desc || Z < 0) { gvm_set_error("gvm_add_channel: bad argument"); return 1; }
+  if ((int)e->chans.size() >= e->red_slots - 2) { gvm_set_error("gvm_add_channel: too many blocks"); return 1; }
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  GvmChannel c;
+  c.d = *desc;
+  c.Z = Z;
+  const size_t z = (size_t)(Z > 0 ? Z : 1);
+  GVM_CUDA(cudaMalloc(&c.uvw_l, z * 3 * sizeof(double)));
+  GVM_CUDA(cudaMalloc(&c.cell, z * sizeof(uint32_t)));
+  GVM_CUDA(cudaMalloc(&c.frac, z * sizeof(float2)));
+  GVM_CUDA(cudaMalloc(&c.Vo, z * sizeof(float2)));
+  GVM_CUDA(cudaMalloc(&c.w, z * sizeof(float)));
+  GVM_CUDA(cudaMalloc(&c.Vr, z * sizeof(float2)));
+  GVM_CUDA(cudaMemset(c.Vr, 0, z * sizeof(float2)));
+  if (e->cfg.keep_vm) {
+    GVM_CUDA(cudaMalloc(&c.Vm, z * sizeof(float2)));
+    GVM_CUDA(cudaMemset(c.Vm, 0, z * sizeof(float2)));
+  }
+  GVM_CUDA(cudaMalloc(&c.du64, z * sizeof(uint64_t)));
+  GVM_CUDA(cudaMalloc(&c.dv64, z * sizeof(uint64_t)));
+  GVM_CUDA(cudaMalloc(&c.wz, z * sizeof(float)));
+  if (Z > 0) {
+    double* d_uvw = nullptr; float2* d_vo = nullptr; float* d_w = nullptr;
+    GVM_CUDA(cudaMalloc(&d_uvw, z * 3 * sizeof(double)));
+    GVM_CUDA(cudaMalloc(&d_vo, z * sizeof(float2)));
+    GVM_CUDA(cudaMalloc(&d_w, z * sizeof(float)));
+    GVM_CUDA(cudaMemcpyAsync(d_uvw, uvw_m, z * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    GVM_CUDA(cudaMemcpyAsync(d_vo, Vo, z * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+    GVM_CUDA(cudaMemcpyAsync(d_w, w, z * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    int rc = gvm_launch_prep_channel(e, c, d_uvw, d_vo, d_w);
+    cudaFree(d_uvw); cudaFree(d_vo); cudaFree(d_w);
+    if (rc) return rc;
+  }
+  const int slot = (int)e->chans.size();
+  long zl = (long)Z;
+  GVM_CUDA(cudaMemcpy(e->red_Z + slot, &zl, sizeof(long), cudaMemcpyHostToDevice));
+  e->chans.push_back(c);
+  if (chan_out) *chan_out = slot;
+  return 0;
+}
+
+int gvm_num_channels(gvm_engine* e) { return (int)e->chans.size(); }
+int64_t gvm_channel_nvis(gvm_engine* e, int chan) {
+  if (chan < 0 || chan >= (int)e->chans.size()) return -1;
+  return e->chans[chan].Z;
+}
+
+int gvm_get_vis(gvm_engine* e, int chan, double* uvw_lambda, int32_t* cell, float* Vo, float* Vm,
+                float* Vr, float* w) {
+  if (chan < 0 || chan >= (int)e->chans.size()) { gvm_set_error("gvm_get_vis: bad channel"); return 1; }
+  GvmChannel& c = e->chans[chan];
+  const size_t Z = (size_t)c.Z;
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  if (uvw_lambda) GVM_CUDA(cudaMemcpy(uvw_lambda, c.uvw_l, Z * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (Vo) GVM_CUDA(cudaMemcpy(Vo, c.Vo, Z * sizeof(float2), cudaMemcpyDeviceToHost));
+  if (Vr) GVM_CUDA(cudaMemcpy(Vr, c.Vr, Z * sizeof(float2), cudaMemcpyDeviceToHost));
+  if (w) GVM_CUDA(cudaMemcpy(w, c.w, Z * sizeof(float), cudaMemcpyDeviceToHost));
+  if (Vm) {
+    if (!c.Vm) { gvm_set_error("gvm_get_vis: Vm not kept (cfg.keep_vm = 0)"); return 1; }
+    GVM_CUDA(cudaMemcpy(Vm, c.Vm, Z * sizeof(float2), cudaMemcpyDeviceToHost));
+  }
+  if (cell) {
+    std::vector<uint32_t> packed(Z);
+    GVM_CUDA(cudaMemcpy(packed.data(), c.cell, Z * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < Z; k++) {
+      if (packed[k] == GVM_CELL_INVALID) { cell[2 * k] = -1; cell[2 * k + 1] = -1; }
+      else { cell[2 * k] = (int32_t)(packed[k] & 0xFFFFu); cell[2 * k + 1] = (int32_t)(packed[k] >> 16); }
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ hot path
+int gvm_chi2_async(gvm_engine* e, float* I_dev, int normalize, double* chi2_dev) {
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  if (e->chans.empty()) { gvm_set_error("gvm_chi2: no visibility blocks uploaded"); return 1; }
+  bool first = true;
+  for (size_t s = 0; s < e->chans.size(); s++) {
+    GvmChannel& c = e->chans[s];
+    // the reference skips empty blocks (src/functions.cu:4382) but still clips once per call
+    if (c.Z <= 0 && !(first && s + 1 == e->chans.size())) continue;
+    if (gvm_forward_channel(e, c, I_dev, first, e->flag_opt, (int)s)) return 1;
+    first = false;
+  }
+  return gvm_reduce_finish(e, (int)e->chans.size(), normalize, chi2_dev ? chi2_dev : e->red_out);
+}
+
+int gvm_chi2(gvm_engine* e, float* I_dev, int normalize, float* chi2_out) {
+  if (gvm_chi2_async(e, I_dev, normalize, e->red_out)) return 1;
+  GVM_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  if (chi2_out) *chi2_out = (float)e->h_red[0];
+  return 0;
+}
+
+static int pick_grad_mode(gvm_engine* e, GvmChannel& c) {
+  int mode = e->cfg.grad_mode;
+  if (mode == GVM_GRAD_SIMT_EXACT || mode == GVM_GRAD_SIMT) return mode;
+  const bool sep_ok = gvm_wterm_cross_bound(e, c) <= 2e-6;  // turns; DESIGN.md §3.4
+  if (mode == GVM_GRAD_UMMA) return GVM_GRAD_UMMA;
+  if (!sep_ok) return GVM_GRAD_SIMT_EXACT;
+  return gvm_grad_umma_supported(e, c) ? GVM_GRAD_UMMA : GVM_GRAD_SIMT;
+}
+
+int gvm_dchi2(gvm_engine* e, const float* I_dev, int flag_opt, int normalize,
+              float* result_dchi2_dev) {
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  e->flag_opt = flag_opt;
+  e->ev_used = 0;
+  for (size_t s = 0; s < e->chans.size(); s++) {
+    GvmChannel& c = e->chans[s];
+    if (c.Z <= 0) continue;
+    if (c.slot < 0) { gvm_set_error("gvm_dchi2: call gvm_chi2 first (Vr comes from the forward pass)"); return 1; }
+    const int mode = pick_grad_mode(e, c);
+    int ksplit = 1;
+    int rc;
+    if (mode == GVM_GRAD_UMMA) rc = gvm_grad_umma(e, c, &ksplit);
+    else rc = gvm_grad_simt(e, c, mode == GVM_GRAD_SIMT_EXACT, &ksplit);
+    if (rc) return rc;
+    e->last_grad_mode = mode;
+    if (gvm_grad_finish(e, c, I_dev, ksplit, flag_opt, normalize, result_dchi2_dev)) return 1;
+  }
+  return 0;
+}
+
+int gvm_eval_host(gvm_engine* e, const float* I_host, int flag_opt, int normalize, float* chi2_out,
+                  float* grad_host) {
+  const size_t MN = (size_t)e->cfg.M * e->cfg.N;
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  e->flag_opt = flag_opt;
+  GVM_CUDA(cudaMemcpyAsync(e->I_stage, I_host, 2 * MN * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  if (gvm_chi2_async(e, e->I_stage, normalize, e->red_out)) return 1;
+  GVM_CUDA(cudaMemsetAsync(e->grad_stage, 0, 2 * MN * sizeof(float), e->stream));  // Chi2::restartDGi
+  if (gvm_dchi2(e, e->I_stage, flag_opt, normalize, e->grad_stage)) return 1;
+  GVM_CUDA(cudaMemcpyAsync(grad_host, e->grad_stage, 2 * MN * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  GVM_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  if (chi2_out) *chi2_out = (float)e->h_red[0];
+  return 0;
+}
+
+int64_t gvm_launch_count(gvm_engine* e) { return e->launches; }
+int gvm_last_grad_mode(gvm_engine* e) { return e->last_grad_mode; }
+int gvm_last_grad_kernel_ms(gvm_engine* e, float* ms, int* launches) {
+  float total = 0.f;
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  for (int i = 0; i + 1 < e->ev_used; i += 2) {
+    float t = 0.f;
+    GVM_CUDA(cudaEventElapsedTime(&t, e->ev[i], e->ev[i + 1]));
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (launches) *launches = e->ev_used / 2;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,312 @@
+// forward.cu — image -> visibility forward model and the chi2 reduction.
+//
+// Reference path: clip2IWNoise, calculateInu, apply_beam2I,
+// apply_GCF, cufftExecC2C(INVERSE), phase_rotate, vis_mod, residual, chi2Vector,
+// deviceReduce (src/functions.cu:4323-4454).  Here:
+//   k_prep_channel   once per upload: hermitianSymmetry + metres->lambda + the
+//                    static part of vis_mod (cell index, fractions, OOB weights)
+//                    + fixed-point phase increments for the gradient
+//   k_image_prep     clip (first channel only) + I_nu + beam + GCF -> complex grid
+//   cuFFT            dense 2-D inverse C2C (the one library call the spec allows)
+//   k_phase_rotate   post-FFT modulation
+//   k_degrid_chi2    gather 4 taps + bilinear + residual + w|Vr|^2, block partials,
+//                    last block finishes the sum in fp64 in a fixed order
+// All streaming kernels are HBM-bound: 24 B read + 8 B written per visibility,
+// grid sized in multiples of the SM count, 128-bit loads where the layout allows.
+#include "gvm_internal.cuh"
+
+namespace {
+
+constexpr int kVisThreads = 256;
+constexpr int kVisPerThread = 4;
+
+// ---------------------------------------------------------------------------
+// Upload-time preprocessing. One thread per visibility.
+// hermitianSymmetry: src/functions.cu:2256-2273 (w is NOT negated there).
+// vis_mod static part: src/functions.cu:2569-2586, 2607.
+__global__ void __launch_bounds__(256) k_prep_channel(
+    const double* __restrict__ uvw_m, const float2* __restrict__ Vo_in,
+    const float* __restrict__ w_in, float freq, double deltau, double deltav, double dx_turn,
+    double dy_turn, long N, long Z, double* __restrict__ uvw_l, uint32_t* __restrict__ cell,
+    float2* __restrict__ frac, float2* __restrict__ Vo, float* __restrict__ w,
+    uint64_t* __restrict__ du64, uint64_t* __restrict__ dv64, float* __restrict__ wz,
+    float* __restrict__ max_abs_wz) {
+  long k = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  float my_wz = 0.f;
+  if (k < Z) {
+    double um = uvw_m[3 * k], vm = uvw_m[3 * k + 1], wm = uvw_m[3 * k + 2];
+    float2 vo = Vo_in[k];
+    if (um > 0.0) {
+      um *= -1.0;
+      vm *= -1.0;
+      vo.y *= -1.0f;
+    }
+    double u = gvm_metres_to_lambda(um, freq);
+    double v = gvm_metres_to_lambda(vm, freq);
+    double wl = gvm_metres_to_lambda(wm, freq);
+    uvw_l[3 * k] = u;
+    uvw_l[3 * k + 1] = v;
+    uvw_l[3 * k + 2] = wl;
+    Vo[k] = vo;
+
+    double uv_x = u / deltau;
+    double uv_y = v / deltav;
+    if (uv_x < 0.0) uv_x += N;
+    if (uv_y < 0.0) uv_y += N;
+    const int i1 = __double2int_rd(uv_x);
+    const int j1 = __double2int_rd(uv_y);
+    const double du = uv_x - i1;
+    const double dv = uv_y - j1;
+    float wk = w_in[k];
+    if (i1 >= 0 && i1 < N && j1 >= 0 && j1 < N) {
+      cell[k] = (uint32_t)i1 | ((uint32_t)j1 << 16);
+      frac[k] = make_float2((float)du, (float)dv);
+    } else {
+      cell[k] = GVM_CELL_INVALID;
+      frac[k] = make_float2(0.f, 0.f);
+      wk = 0.0f;  // vis_mod: weight[i] = 0 for samples that fall off the grid
+    }
+    w[k] = wk;
+
+    // phase increment per pixel step, as a 0.64 fixed-point fraction of a turn
+    double tu = u * dx_turn;
+    double tv = v * dy_turn;
+    tu -= floor(tu);
+    tv -= floor(tv);
+    du64[k] = __double2ull_rd(tu * 18446744073709551616.0);
+    dv64[k] = __double2ull_rd(tv * 18446744073709551616.0);
+    wz[k] = (float)wl;
+    my_wz = fabsf((float)wl);
+  }
+  my_wz = gvm_warp_max(my_wz);
+  if ((threadIdx.x & 31) == 0 && my_wz > 0.f)
+    atomicMax(reinterpret_cast<int*>(max_abs_wz), __float_as_int(my_wz));  // non-negative floats order as ints
+}
+
+// ---------------------------------------------------------------------------
+// clip2IWNoise (src/functions.cu:2694-2719) fused with calculateInu (:3939-3966),
+// apply_beam2I (:2424-2444) and apply_GCF (:2468-2476). One thread per pixel.
+template <bool kClip>
+__global__ void __launch_bounds__(256) k_image_prep(
+    float* __restrict__ I, const float* __restrict__ noise, const float* __restrict__ gcf,
+    float2* __restrict__ I_nu, long N, long M, float noise_cut, float minpix, float eta,
+    float threshold, int schedule, float nu, float nu_0, float fg_scale, float D, float pb_factor,
+    float pb_cutoff, float xobs, float yobs, double DELTAX, double DELTAY, int primary_beam) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int i = (int)(idx / N), j = (int)(idx % N);
+  float I0 = I[idx];
+  float alpha = I[M * N + idx];
+  if (kClip) {
+    if (noise[idx] > noise_cut) {
+      I0 = (eta > 0.0f) ? 0.0f : -1.0f * eta * minpix;
+      alpha = 0.0f;
+      I[idx] = I0;
+      I[M * N + idx] = alpha;
+    } else if (I0 < threshold && schedule > 0) {
+      alpha = 0.0f;
+      I[M * N + idx] = alpha;
+    }
+  }
+  const float nudiv = nu / nu_0;
+  float v = I0 * powf(nudiv, alpha);
+  const float floor_v = -1.0f * eta * minpix;
+  if (v < floor_v) v = floor_v;
+  const float atten = gvm_attenuation(i, j, D, pb_factor, pb_cutoff, nu, xobs, yobs, DELTAX,
+                                      DELTAY, primary_beam);
+  v = v * atten * fg_scale;
+  if (gcf != nullptr) v = v * gcf[idx];
+  I_nu[idx] = make_float2(v, 0.0f);
+}
+
+// phase_rotate: src/functions.cu:2483-2518.
+__global__ void __launch_bounds__(256) k_phase_rotate(float2* __restrict__ data, long M, long N,
+                                                     double xphs, double yphs) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int i = (int)(idx / N), j = (int)(idx % N);
+  const double upix = xphs / (double)M;
+  const double vpix = yphs / (double)N;
+  float u, v;
+  if (j < M / 2) u = upix * j; else u = upix * (j - M);
+  if (i < N / 2) v = vpix * i; else v = vpix * (i - N);
+  const float phase = -2.0f * (u + v);
+  float s, c;
+  sincospif(phase, &s, &c);
+  const float2 d = data[idx];
+  data[idx] = make_float2(d.x * c - d.y * s, d.x * s + d.y * c);  // cuCmulf
+}
+
+// ---------------------------------------------------------------------------
+// vis_mod (dynamic part, src/functions.cu:2588-2606) + residual (:2663) +
+// chi2Vector (:2867) + first reduction level. Each thread handles kVisPerThread
+// consecutive-by-stride samples so that every load is coalesced.
+template <bool kKeepVm>
+__global__ void __launch_bounds__(kVisThreads) k_degrid_chi2(
+    const float2* __restrict__ V, const uint32_t* __restrict__ cell,
+    const float2* __restrict__ frac, const float2* __restrict__ Vo, const float* __restrict__ w,
+    float2* __restrict__ Vr, float2* __restrict__ Vm, long Z, int N,
+    double* __restrict__ partials, float* __restrict__ partial_max,
+    unsigned int* __restrict__ counter, double* __restrict__ out_sum, float* __restrict__ out_max) {
+  __shared__ float s_sum[kVisThreads / 32];
+  __shared__ float s_max[kVisThreads / 32];
+  __shared__ bool s_last;
+  float acc = 0.f, mx = 0.f;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long k = blockIdx.x * (long)blockDim.x + threadIdx.x; k < Z; k += stride) {
+    const uint32_t c = __ldg(&cell[k]);
+    const float2 f = __ldg(&frac[k]);
+    const float2 vo = __ldg(&Vo[k]);
+    const float wk = __ldg(&w[k]);
+    float2 vm = make_float2(0.f, 0.f);
+    if (c != GVM_CELL_INVALID) {
+      const int i1 = (int)(c & 0xFFFFu), j1 = (int)(c >> 16);
+      const int i2 = (i1 + 1 == N) ? 0 : i1 + 1;
+      const int j2 = (j1 + 1 == N) ? 0 : j1 + 1;
+      const float2 v11 = __ldg(&V[(long)N * j1 + i1]);
+      const float2 v12 = __ldg(&V[(long)N * j2 + i1]);
+      const float2 v21 = __ldg(&V[(long)N * j1 + i2]);
+      const float2 v22 = __ldg(&V[(long)N * j2 + i2]);
+      const float du = f.x, dv = f.y;
+      const float w11 = (1.0f - du) * (1.0f - dv);
+      const float w12 = (1.0f - du) * dv;
+      const float w21 = du * (1.0f - dv);
+      const float w22 = du * dv;
+      vm.x = w11 * v11.x + w12 * v12.x + w21 * v21.x + w22 * v22.x;
+      vm.y = w11 * v11.y + w12 * v12.y + w21 * v21.y + w22 * v22.y;
+    }
+    const float2 vr = make_float2(vo.x - vm.x, vo.y - vm.y);
+    Vr[k] = vr;
+    if (kKeepVm) Vm[k] = vm;
+    acc += wk * (vr.x * vr.x + vr.y * vr.y);
+    mx = fmaxf(mx, wk * fmaxf(fabsf(vr.x), fabsf(vr.y)));
+  }
+  acc = gvm_warp_sum(acc);
+  mx = gvm_warp_max(mx);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_sum[warp] = acc; s_max[warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    float a = (lane < kVisThreads / 32) ? s_sum[lane] : 0.f;
+    float m = (lane < kVisThreads / 32) ? s_max[lane] : 0.f;
+    a = gvm_warp_sum(a);
+    m = gvm_warp_max(m);
+    if (lane == 0) {
+      partials[blockIdx.x] = (double)a;
+      partial_max[blockIdx.x] = m;
+      __threadfence();
+      const unsigned int done = atomicAdd(counter, 1u);
+      s_last = (done == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (s_last && warp == 0) {
+    // fixed-order fp64 finish: deterministic for a given grid size
+    __threadfence();
+    double t = 0.0;
+    float m = 0.f;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) {
+      t += partials[b];
+      m = fmaxf(m, partial_max[b]);
+    }
+    t = gvm_warp_sum_d(t);
+    m = gvm_warp_max(m);
+    if (lane == 0) {
+      *out_sum = t;
+      *out_max = m;
+      *counter = 0u;
+    }
+  }
+}
+
+// Combines the per-block sums the way chi2() does on the host
+// (src/functions.cu:4439-4453): float accumulation, optional /Z, 0.5f * total.
+__global__ void k_chi2_combine(const double* __restrict__ sums, const long* __restrict__ Zs,
+                               int nslots, int normalize, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float reduced = 0.0f;
+    for (int s = 0; s < nslots; s++) {
+      if (Zs[s] <= 0) continue;
+      float r = (float)sums[s];
+      if (normalize) r /= (float)Zs[s];
+      reduced += r;
+    }
+    out[0] = (double)(0.5f * reduced);
+  }
+}
+
+}  // namespace
+
+int gvm_launch_prep_channel(gvm_engine* e, GvmChannel& c, const double* uvw_m_dev,
+                            const float2* Vo_dev, const float* w_dev) {
+  const gvm_config& g = e->cfg;
+  const double deltax = GVM_RPDEG_D * g.DELTAX, deltay = GVM_RPDEG_D * g.DELTAY;  // src/mfs.cu:493-496
+  const double deltau = 1.0 / (g.M * deltax), deltav = 1.0 / (g.N * deltay);
+  float* d_max = nullptr;
+  GVM_CUDA(cudaMalloc(&d_max, sizeof(float)));
+  GVM_CUDA(cudaMemsetAsync(d_max, 0, sizeof(float), e->stream));
+  const int blocks = (int)((c.Z + 255) / 256);
+  k_prep_channel<<<blocks, 256, 0, e->stream>>>(uvw_m_dev, Vo_dev, w_dev, c.d.freq, deltau, deltav,
+                                                 g.DELTAX * GVM_RPDEG_D, g.DELTAY * GVM_RPDEG_D,
+                                                 g.N, c.Z, c.uvw_l, c.cell, c.frac, c.Vo, c.w,
+                                                 c.du64, c.dv64, c.wz, d_max);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  GVM_CUDA(cudaMemcpyAsync(&c.max_abs_wz, d_max, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(d_max);
+  return 0;
+}
+
+int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, int flag_opt,
+                        int slot) {
+  const gvm_config& g = e->cfg;
+  const long MN = g.M * g.N;
+  const int pix_blocks = (int)((MN + 255) / 256);
+  if (first)
+    k_image_prep<true><<<pix_blocks, 256, 0, e->stream>>>(
+        I_dev, e->noise, e->gcf, e->I_nu, g.N, g.M, g.noise_cut, g.minpix, g.eta, g.threshold,
+        flag_opt, c.d.freq, g.nu_0, g.fg_scale, c.d.antenna_diameter, c.d.pb_factor, c.d.pb_cutoff,
+        c.d.ref_xobs_pix, c.d.ref_yobs_pix, g.DELTAX, g.DELTAY, c.d.primary_beam);
+  else
+    k_image_prep<false><<<pix_blocks, 256, 0, e->stream>>>(
+        I_dev, e->noise, e->gcf, e->I_nu, g.N, g.M, g.noise_cut, g.minpix, g.eta, g.threshold,
+        flag_opt, c.d.freq, g.nu_0, g.fg_scale, c.d.antenna_diameter, c.d.pb_factor, c.d.pb_cutoff,
+        c.d.ref_xobs_pix, c.d.ref_yobs_pix, g.DELTAX, g.DELTAY, c.d.primary_beam);
+  GVM_LAUNCH(e);
+  if (cufftExecC2C(e->plan, reinterpret_cast<cufftComplex*>(e->I_nu),
+                   reinterpret_cast<cufftComplex*>(e->V), CUFFT_INVERSE) != CUFFT_SUCCESS) {
+    gvm_set_error("cufftExecC2C failed");
+    return 1;
+  }
+  GVM_LAUNCH(e);
+  k_phase_rotate<<<pix_blocks, 256, 0, e->stream>>>(e->V, g.M, g.N, (double)c.d.phs_xobs_pix,
+                                                     (double)c.d.phs_yobs_pix);
+  GVM_LAUNCH(e);
+  long want = (c.Z + (long)kVisThreads * kVisPerThread - 1) / ((long)kVisThreads * kVisPerThread);
+  int blocks = (int)(want < 1 ? 1 : (want > e->red_blocks ? e->red_blocks : want));
+  double* partials = e->red_partials + (size_t)slot * e->red_blocks;
+  float* pmax = reinterpret_cast<float*>(e->red_partials + (size_t)e->red_slots * e->red_blocks) +
+                (size_t)slot * e->red_blocks;
+  if (c.Z > 0) {
+    if (g.keep_vm)
+      k_degrid_chi2<true><<<blocks, kVisThreads, 0, e->stream>>>(
+          e->V, c.cell, c.frac, c.Vo, c.w, c.Vr, c.Vm, c.Z, (int)g.N, partials, pmax,
+          e->red_counter + slot, e->red_sum + slot, e->red_max + slot);
+    else
+      k_degrid_chi2<false><<<blocks, kVisThreads, 0, e->stream>>>(
+          e->V, c.cell, c.frac, c.Vo, c.w, c.Vr, nullptr, c.Z, (int)g.N, partials, pmax,
+          e->red_counter + slot, e->red_sum + slot, e->red_max + slot);
+    GVM_LAUNCH(e);
+  }
+  c.slot = slot;
+  GVM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gvm_reduce_finish(gvm_engine* e, int nslots, int normalize, double* out_dev) {
+  k_chi2_combine<<<1, 32, 0, e->stream>>>(e->red_sum, e->red_Z, nslots, normalize, out_dev);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,163 @@
+// gvm_internal.cuh — engine state and device helpers shared by the kernels.
+// B200 (sm_100a) only. See DESIGN.md for the data layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gvm_b200.h"
+
+#define GVM_PI_F CUDART_PI_F
+#define GVM_PI_D CUDART_PI
+#define GVM_RPDEG_D (CUDART_PI / 180.0)          // include/functions.cuh:18
+#define GVM_LIGHTSPEED 2.99792458E8f             // include/MSFITSIO.cuh:54
+#define GVM_RZ 1.2196698912665045f               // include/functions.cuh:23 (stored as float)
+#define GVM_CELL_INVALID 0xFFFFFFFFu
+
+void gvm_set_error(const char* fmt, ...);
+
+#define GVM_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (call);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      gvm_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return 1;                                                                     \
+    }                                                                               \
+  } while (0)
+
+struct GvmChannel {
+  gvm_channel_desc d;
+  int64_t Z = 0;
+  // SoA, device
+  double* uvw_l = nullptr;     // [Z][3] wavelengths after the Hermitian fold (kept for readback / exact checks)
+  uint32_t* cell = nullptr;    // i1 | j1 << 16, GVM_CELL_INVALID when outside the grid
+  float2* frac = nullptr;      // (du, dv) bilinear fractions
+  float2* Vo = nullptr;
+  float* w = nullptr;
+  float2* Vr = nullptr;
+  float2* Vm = nullptr;        // only when cfg.keep_vm
+  // gradient inputs (static per block): phase increments per pixel step as
+  // 0.64 fixed-point fractions of a turn, and the w coordinate in wavelengths
+  uint64_t* du64 = nullptr;    // frac(u_lambda * DELTAX * pi/180) * 2^64
+  uint64_t* dv64 = nullptr;    // frac(v_lambda * DELTAY * pi/180) * 2^64
+  float* wz = nullptr;
+  float max_abs_wz = 0.f;      // max |w| (wavelengths)
+  int slot = -1;               // reduction slot of the last forward pass
+};
+
+struct gvm_engine {
+  gvm_config cfg;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cufftHandle plan = 0;
+  bool have_plan = false;
+  int sm_count = 148;
+  // image-sized scratch
+  float2* I_nu = nullptr;   // [MN] complex
+  float2* V = nullptr;      // [MN] complex
+  float* noise = nullptr;   // [MN]
+  float* gcf = nullptr;     // [MN] or null
+  float* dchi2 = nullptr;   // [MN] per-channel gradient before the chain rule
+  float* grad_scratch = nullptr;  // [ksplit][MN] partial sums
+  size_t grad_scratch_floats = 0;
+  float* pixtab = nullptr;  // [2][N] gA(x_j), gB(y_i) tables (w-term), rebuilt per channel
+  // reductions
+  double* red_partials = nullptr;  // per-block partials
+  unsigned int* red_counter = nullptr;
+  double* red_sum = nullptr;       // [slot] sum_k w|Vr|^2 of the last forward pass
+  float* red_max = nullptr;        // [slot] max_k w*max(|Vr.re|,|Vr.im|)  (fp16 scaling of the UMMA path)
+  double* red_out = nullptr;       // [0] = 0.5*chi2 of the last gvm_chi2
+  double* h_red = nullptr;         // pinned host mirror of red_out
+  long* red_Z = nullptr;           // [slot] visibilities per block (device)
+  int red_blocks = 0;
+  int red_slots = 0;
+  int flag_opt = 0;                // optimizer schedule flag (src/frprmn.cu:46), read by the clip
+  // staging
+  float* I_stage = nullptr;     // [2][MN] device image for gvm_eval_host
+  float* grad_stage = nullptr;  // [2][MN]
+  std::vector<GvmChannel> chans;
+  int64_t launches = 0;
+  // telemetry
+  std::vector<cudaEvent_t> ev;
+  int ev_used = 0;
+  int last_grad_mode = 0;
+  unsigned int* tile_counter = nullptr;
+};
+
+#define GVM_LAUNCH(e) ((e)->launches++)
+
+// ---------------------------------------------------------------- device helpers
+// Restates src/MSFITSIO.cu:36-45 (fp32 wavelength, fp64 division).
+__host__ __device__ inline float gvm_freq_to_wavelength(float freq) { return GVM_LIGHTSPEED / freq; }
+__host__ __device__ inline double gvm_metres_to_lambda(double m, float freq) {
+  float lambda = gvm_freq_to_wavelength(freq);
+  return m / lambda;
+}
+
+// attenuation(): src/functions.cu:2304-2333 with AiryDiskBeam (:2275) / GaussianBeam (:2293).
+__device__ inline float gvm_attenuation(int i, int j, float D, float pb_factor, float pb_cutoff,
+                                        float freq, float xobs, float yobs, double DELTAX,
+                                        double DELTAY, int primary_beam) {
+  int x0 = (int)xobs;
+  int y0 = (int)yobs;
+  float x = (float)((j - x0) * DELTAX * GVM_RPDEG_D);
+  float y = (float)((i - y0) * DELTAY * GVM_RPDEG_D);
+  float arc = sqrtf(x * x + y * y);
+  float lambda = gvm_freq_to_wavelength(freq);
+  float atten;
+  if (primary_beam == GVM_BEAM_AIRYDISK) {
+    atten = 1.0f;
+    if (arc != 0.0f) {
+      float arg = GVM_PI_F * arc * D / lambda * (GVM_RZ / pb_factor);
+      float b = j1f(arg);
+      atten = 4.0f * (b / arg) * (b / arg);
+    }
+  } else {
+    float fwhm = pb_factor * lambda / D;
+    float c = 4.0f * logf(2.0f);
+    float r = arc / fwhm;
+    atten = expf(-c * r * r);
+  }
+  return (arc <= pb_cutoff) ? atten : 0.0f;
+}
+
+__device__ inline float gvm_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ inline double gvm_warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ inline float gvm_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------ kernel launchers
+// forward.cu
+int gvm_launch_prep_channel(gvm_engine* e, GvmChannel& c, const double* uvw_m_dev,
+                            const float2* Vo_dev, const float* w_dev);
+int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, int flag_opt,
+                        int slot);
+int gvm_reduce_finish(gvm_engine* e, int nslots, int normalize, double* out_dev);
+// grad_simt.cu
+int gvm_grad_simt(gvm_engine* e, GvmChannel& c, bool exact, int* ksplit_out);
+// grad_umma.cu
+int gvm_grad_umma(gvm_engine* e, GvmChannel& c, int* ksplit_out);
+bool gvm_grad_umma_supported(const gvm_engine* e, const GvmChannel& c);
+// shared by gradient paths
+int gvm_grad_finish(gvm_engine* e, GvmChannel& c, const float* I_dev, int ksplit, int flag_opt,
+                    int normalize, float* result_dev);
+int gvm_ensure_grad_scratch(gvm_engine* e, size_t floats);
+int gvm_build_pixtab(gvm_engine* e, const GvmChannel& c);
+double gvm_wterm_cross_bound(const gvm_engine* e, const GvmChannel& c);
+void gvm_ev_begin(gvm_engine* e);
+void gvm_ev_end(gvm_engine* e);

@@ -1,0 +1,553 @@
+// priors.cu — regularisation terms (values and gradients), the noise image, and
+// the image-sized vector kernels the optimizers use.
+//
+// Reference: one kernel writing a per-pixel term into a
+// scratch image + deviceReduce (cudaMalloc/D2H/free per call) for every value,
+// one kernel per gradient, one kernel per image for every optimizer update
+// (src/functions.cu:2878-3545 device, :4633-4964 hosts, :2721-2865, :3556-3687).
+// Here every value is ONE launch: the term is computed and reduced in the same
+// pass (warp shuffles -> block partial -> last block finishes in fp64 in a fixed
+// order), nothing is allocated, and the per-image loops are folded into the grid.
+// All of these are HBM-bound streaming passes over 4*M*N bytes per operand.
+#include <cmath>
+#include "gvm_internal.cuh"
+
+namespace {
+
+constexpr int kT = 256;
+
+// ---- per-pixel terms, formulas and edge rules copied in meaning (not text) from
+// calculateS/DS (:3036/:3057), calculateL1norm/DNormL1 (:2882/:2915),
+// calculateTV/DTV (:3238/:3283), calculateTSV/DTSV (:3353/:3397),
+// calculateL/DL (:3443/:3490, incl. the "-8(d - r - u - l)" sign slip),
+// calculateQP/DQ (:3146/:3189, incl. "4c - d + u + r + l"),
+// calculateGL1norm/DGNormL1 (:2954/:2990), SGVector/DSG (:3114/:3130).
+struct PriorArgs {
+  const float* I;      // image `index` base: I + N*M*index
+  const float* noise;
+  const float* prior_image;
+  float noise_cut, G, eta, eps, eps_b, lambda;
+  int N;
+};
+
+__device__ __forceinline__ float approx_abs(float v, float eps) { return sqrtf(v * v + eps); }
+
+template <int KIND>
+__device__ __forceinline__ float prior_value_at(const PriorArgs& a, int i, int j) {
+  const int N = a.N;
+  const long idx = (long)N * i + j;
+  const float* I = a.I;
+  if (!(a.noise[idx] < a.noise_cut)) return 0.0f;
+  const float c = I[idx];
+  if (KIND == GVM_PRIOR_ENTROPY) return c * logf((c / a.G) + (a.eta + 1.0f));
+  if (KIND == GVM_PRIOR_GENTROPY) return c * logf((c / a.prior_image[idx]) + (a.eta + 1.0f));
+  if (KIND == GVM_PRIOR_L1) return approx_abs(c, a.eps);
+  if (KIND == GVM_PRIOR_GL1)
+    return approx_abs(c, a.eps) / (approx_abs(a.prior_image[idx], a.eps) + a.eps_b);
+  if (KIND == GVM_PRIOR_TV) {
+    if (i < N - 1 && j < N - 1) {
+      const float r = I[idx + 1], d = I[idx + N];
+      const float dxy0 = (r - c) * (r - c), dxy1 = (d - c) * (d - c);
+      return sqrtf(dxy0 + dxy1 + a.eps);
+    }
+    return c;
+  }
+  if (KIND == GVM_PRIOR_TSV) {
+    if (i < N - 1 && j < N - 1) {
+      const float r = I[idx + 1], d = I[idx + N];
+      const float dx = c - r, dy = c - d;
+      return dx * dx + dy * dy;
+    }
+    return c;
+  }
+  if (KIND == GVM_PRIOR_LAPLACIAN) {
+    if ((i > 0 && i < N - 1) && (j > 0 && j < N - 1)) {
+      const float l = I[idx - 1], r = I[idx + 1], d = I[idx + N], u = I[idx - N];
+      const float Dx = l - 2.0f * c + r, Dy = u - 2.0f * c + d;
+      return 0.5f * (Dx + Dy) * (Dx + Dy);
+    }
+    return c;
+  }
+  if (KIND == GVM_PRIOR_QUADRATIC) {
+    if ((i > 0 && i < N - 1) && (j > 0 && j < N - 1)) {
+      const float l = I[idx - 1], r = I[idx + 1], d = I[idx + N], u = I[idx - N];
+      float qp = (c - l) * (c - l) + (c - r) * (c - r) + (c - u) * (c - u) + (c - d) * (c - d);
+      return qp / 2.0f;
+    }
+    return c;
+  }
+  return 0.0f;
+}
+
+template <int KIND>
+__device__ __forceinline__ float prior_grad_at(const PriorArgs& a, int i, int j) {
+  const int N = a.N;
+  const long idx = (long)N * i + j;
+  const float* I = a.I;
+  float g = 0.0f;
+  if (a.noise[idx] < a.noise_cut) {
+    const float c = I[idx];
+    if (KIND == GVM_PRIOR_ENTROPY) {
+      const float G = a.G;
+      g = logf((c / G) + (a.eta + 1.0f)) + 1.0f / (1.0f + (((a.eta + 1.0f) * G) / c));
+    } else if (KIND == GVM_PRIOR_GENTROPY) {
+      const float G = a.prior_image[idx];
+      g = logf((c / G) + (a.eta + 1.0f)) + 1.0f / (1.0f + (((a.eta + 1.0f) * G) / c));
+    } else if (KIND == GVM_PRIOR_L1) {
+      g = c / approx_abs(c, a.eps);
+    } else if (KIND == GVM_PRIOR_GL1) {
+      g = c / (approx_abs(c, a.eps) * (approx_abs(a.prior_image[idx], a.eps) + a.eps_b));
+    } else if (KIND == GVM_PRIOR_TV) {
+      if ((i > 0 && i < N - 1) && (j > 0 && j < N - 1)) {
+        const float d = I[idx + N], u = I[idx - N], r = I[idx + 1], l = I[idx - 1];
+        const float dl = I[idx + N - 1], ru = I[idx - N + 1];
+        const float num0 = 2.0f * c - r - d, num1 = c - l, num2 = c - u;
+        const float a0 = (c - r) * (c - r) + (c - d) * (c - d) + a.eps;
+        const float a1 = (l - c) * (l - c) + (l - dl) * (l - dl) + a.eps;
+        const float a2 = (u - ru) * (u - ru) + (u - c) * (u - c) + a.eps;
+        g = num0 / sqrtf(a0) + num1 / sqrtf(a1) + num2 / sqrtf(a2);
+      } else {
+        g = c;
+      }
+    } else if (KIND == GVM_PRIOR_TSV) {
+      if ((i > 0 && i < N - 1) && (j > 0 && j < N - 1)) {
+        const float d = I[idx + N], u = I[idx - N], r = I[idx + 1], l = I[idx - 1];
+        g = 8.0f * c - 2.0f * (u + l + d + r);
+      } else {
+        g = c;
+      }
+    } else if (KIND == GVM_PRIOR_LAPLACIAN) {
+      if ((i > 1 && i < N - 2) && (j > 1 && j < N - 2)) {
+        const float d = I[idx + N], u = I[idx - N], r = I[idx + 1], l = I[idx - 1];
+        const float dl = I[idx + N - 1], dr = I[idx + N + 1], lu = I[idx - N - 1], ru = I[idx - N + 1];
+        const float d2 = I[idx + 2 * (long)N], u2 = I[idx - 2 * (long)N], l2 = I[idx - 2], r2 = I[idx + 2];
+        g = 20.0f * c - 8.0f * (d - r - u - l) + 2.0f * (dl + dr + lu + ru) + d2 + r2 + u2 + l2;
+      } else {
+        g = 0.0f;
+      }
+    } else if (KIND == GVM_PRIOR_QUADRATIC) {
+      if ((i > 0 && i < N - 1) && (j > 0 && j < N - 1)) {
+        const float d = I[idx + N], u = I[idx - N], r = I[idx + 1], l = I[idx - 1];
+        g = 2.0f * (4.0f * c - d + u + r + l);
+      } else {
+        g = c;
+      }
+    }
+  }
+  return g * a.lambda;
+}
+
+// Block-level finish shared by every reducing kernel in this file: up to two
+// sums and one max per block; the last block to arrive adds the partials in
+// index order in fp64.
+__device__ __forceinline__ void block_reduce_finish(float s0, float s1, float mx,
+                                                    double* __restrict__ partials,
+                                                    float* __restrict__ pmax,
+                                                    unsigned int* __restrict__ counter,
+                                                    double* __restrict__ out) {
+  __shared__ float sh0[kT / 32], sh1[kT / 32], shm[kT / 32];
+  __shared__ bool last;
+  s0 = gvm_warp_sum(s0);
+  s1 = gvm_warp_sum(s1);
+  mx = gvm_warp_max(mx);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh0[warp] = s0; sh1[warp] = s1; shm[warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    float a = lane < kT / 32 ? sh0[lane] : 0.f, b = lane < kT / 32 ? sh1[lane] : 0.f;
+    float m = lane < kT / 32 ? shm[lane] : 0.f;
+    a = gvm_warp_sum(a); b = gvm_warp_sum(b); m = gvm_warp_max(m);
+    if (lane == 0) {
+      partials[2 * blockIdx.x] = (double)a;
+      partials[2 * blockIdx.x + 1] = (double)b;
+      pmax[blockIdx.x] = m;
+      __threadfence();
+      last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (last && warp == 0) {
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    float m = 0.f;
+    for (unsigned int k = lane; k < gridDim.x; k += 32) {
+      a += partials[2 * k];
+      b += partials[2 * k + 1];
+      m = fmaxf(m, pmax[k]);
+    }
+    a = gvm_warp_sum_d(a); b = gvm_warp_sum_d(b); m = gvm_warp_max(m);
+    if (lane == 0) { out[0] = a; out[1] = b; out[2] = (double)m; *counter = 0u; }
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kT) k_prior_value(PriorArgs a, double* partials, float* pmax,
+                                                    unsigned int* counter, double* out) {
+  const long MN = (long)a.N * a.N;
+  float s = 0.f;
+  for (long idx = blockIdx.x * (long)kT + threadIdx.x; idx < MN; idx += (long)gridDim.x * kT)
+    s += prior_value_at<KIND>(a, (int)(idx / a.N), (int)(idx % a.N));
+  block_reduce_finish(s, 0.f, 0.f, partials, pmax, counter, out);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kT) k_prior_grad(PriorArgs a, float* __restrict__ dgi) {
+  const long MN = (long)a.N * a.N;
+  const long idx = blockIdx.x * (long)kT + threadIdx.x;
+  if (idx < MN) dgi[idx] = prior_grad_at<KIND>(a, (int)(idx / a.N), (int)(idx % a.N));
+}
+
+__global__ void __launch_bounds__(kT) k_add_to_dphi(float* __restrict__ dphi,
+                                                    const float* __restrict__ dgi, long MN) {
+  const long idx = blockIdx.x * (long)kT + threadIdx.x;
+  if (idx < MN) dphi[idx] += dgi[idx];
+}
+
+// ------------------------------------------------------------- noise image --
+// total_attenuation (:2349) -> weight_image (:2401) accumulated per field.
+__global__ void __launch_bounds__(kT) k_weight_accum(float* __restrict__ weight, long N, long M,
+                                                     float D, float pbf, float pbc, float nu0,
+                                                     float xobs, float yobs, double DELTAX,
+                                                     double DELTAY, int pb) {
+  const long idx = blockIdx.x * (long)kT + threadIdx.x;
+  if (idx >= M * N) return;
+  const float at = gvm_attenuation((int)(idx / N), (int)(idx % N), D, pbf, pbc, nu0, xobs, yobs,
+                                   DELTAX, DELTAY, pb);
+  weight[idx] += at * at;
+}
+__global__ void __launch_bounds__(kT) k_max_reduce(const float* __restrict__ v, long n,
+                                                   double* partials, float* pmax,
+                                                   unsigned int* counter, double* out) {
+  float m = 0.f;
+  for (long idx = blockIdx.x * (long)kT + threadIdx.x; idx < n; idx += (long)gridDim.x * kT)
+    m = fmaxf(m, v[idx]);
+  block_reduce_finish(0.f, 0.f, m, partials, pmax, counter, out);
+}
+// noise_image (:2409-2422); the min is taken as max of -noise... noise > 0 so we
+// reduce 1/noise with max and invert on the host instead.
+__global__ void __launch_bounds__(kT) k_noise_image(float* __restrict__ noise,
+                                                    const float* __restrict__ weight, long n,
+                                                    float max_weight, float noise_jypix) {
+  const long idx = blockIdx.x * (long)kT + threadIdx.x;
+  if (idx >= n) return;
+  const float nsq = noise_jypix * noise_jypix;
+  const float nw = (weight[idx] / max_weight) / nsq;
+  noise[idx] = sqrtf(1.0f / nw);
+}
+__global__ void __launch_bounds__(kT) k_min_reduce(const float* __restrict__ v, long n,
+                                                   float* __restrict__ out_bits) {
+  float m = CUDART_INF_F;
+  for (long idx = blockIdx.x * (long)kT + threadIdx.x; idx < n; idx += (long)gridDim.x * kT)
+    m = fminf(m, v[idx]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  // positive floats (and +inf) order like their bit patterns
+  if ((threadIdx.x & 31) == 0) atomicMin(reinterpret_cast<int*>(out_bits), __float_as_int(m));
+}
+
+// ---------------------------------------------------------------- vector ops --
+__global__ void __launch_bounds__(kT) k_evaluate_xt(float* __restrict__ xt,
+                                                    const float* __restrict__ pcom,
+                                                    const float* __restrict__ xicom, float x,
+                                                    long MN, int image_count, float floor0,
+                                                    int nopositivity) {
+  const long idx = blockIdx.x * (long)kT + threadIdx.x;
+  if (idx >= MN * image_count) return;
+  const float v = pcom[idx] + x * xicom[idx];
+  if (idx < MN && !nopositivity) xt[idx] = (v > floor0) ? v : floor0;
+  else xt[idx] = v;
+}
+__global__ void __launch_bounds__(kT) k_new_p(float* __restrict__ p, float* __restrict__ xi,
+                                              float xmin, long MN, int image_count, float floor0,
+                                              int nopositivity) {
+  const long idx = blockIdx.x * (long)kT + threadIdx.x;
+  if (idx >= MN * image_count) return;
+  float x = xi[idx] * xmin;
+  const float pv = p[idx];
+  if (idx < MN && !nopositivity) {
+    if (pv + x > floor0) { p[idx] = pv + x; }
+    else { p[idx] = floor0; x = 0.0f; }
+  } else {
+    p[idx] = pv + x;
+  }
+  xi[idx] = x;
+}
+__global__ void __launch_bounds__(kT) k_dot(const float* __restrict__ a, const float* __restrict__ b,
+                                            long n, double* partials, float* pmax,
+                                            unsigned int* counter, double* out) {
+  float s = 0.f;
+  for (long idx = blockIdx.x * (long)kT + threadIdx.x; idx < n; idx += (long)gridDim.x * kT)
+    s += a[idx] * b[idx];
+  block_reduce_finish(s, 0.f, 0.f, partials, pmax, counter, out);
+}
+__global__ void __launch_bounds__(kT) k_gg_dgg(const float* __restrict__ xi,
+                                               const float* __restrict__ g, long n,
+                                               double* partials, float* pmax,
+                                               unsigned int* counter, double* out) {
+  float s0 = 0.f, s1 = 0.f;
+  for (long idx = blockIdx.x * (long)kT + threadIdx.x; idx < n; idx += (long)gridDim.x * kT) {
+    const float gv = g[idx], xv = xi[idx];
+    s0 += gv * gv;
+    s1 += (xv + gv) * xv;
+  }
+  block_reduce_finish(s0, s1, 0.f, partials, pmax, counter, out);
+}
+__global__ void __launch_bounds__(kT) k_grad_condition(const float* __restrict__ xi,
+                                                       const float* __restrict__ p, float den,
+                                                       long n, double* partials, float* pmax,
+                                                       unsigned int* counter, double* out) {
+  float m = 0.f;
+  for (long idx = blockIdx.x * (long)kT + threadIdx.x; idx < n; idx += (long)gridDim.x * kT)
+    m = fmaxf(m, fabsf(xi[idx]) * fmaxf(fabsf(p[idx]), 1.0f) / den);
+  block_reduce_finish(0.f, 0.f, m, partials, pmax, counter, out);
+}
+__global__ void __launch_bounds__(kT) k_new_xi(float* __restrict__ g, float* __restrict__ xi,
+                                               float* __restrict__ h, float gam, long n) {
+  const long idx = blockIdx.x * (long)kT + threadIdx.x;
+  if (idx >= n) return;
+  const float gv = -xi[idx];
+  g[idx] = gv;
+  const float hv = (gam == 0.0f) ? gv : gv + gam * h[idx];
+  h[idx] = hv;
+  xi[idx] = hv;
+}
+__global__ void __launch_bounds__(kT) k_axpby(float a, const float* __restrict__ x, float b,
+                                              float* __restrict__ y, long n) {
+  const long idx = blockIdx.x * (long)kT + threadIdx.x;
+  if (idx >= n) return;
+  y[idx] = (b == 0.0f) ? a * x[idx] : a * x[idx] + b * y[idx];
+}
+
+struct RedBuf {
+  double* partials; float* pmax; unsigned int* counter; double* out;
+};
+RedBuf aux_red(gvm_engine* e) {
+  // the last reduction slot is reserved for image-sized reductions
+  const int slot = e->red_slots - 1;
+  RedBuf r;
+  r.partials = e->red_partials + (size_t)slot * e->red_blocks - e->red_blocks;  // 2 doubles per block: use two slots
+  r.pmax = reinterpret_cast<float*>(e->red_partials + (size_t)e->red_slots * e->red_blocks) +
+           (size_t)slot * e->red_blocks;
+  r.counter = e->red_counter + slot;
+  r.out = e->red_out + 4;
+  return r;
+}
+int red_grid(gvm_engine* e, long n) {
+  long b = (n + (long)kT * 4 - 1) / ((long)kT * 4);
+  if (b < 1) b = 1;
+  if (b > e->red_blocks) b = e->red_blocks;
+  return (int)b;
+}
+int fetch_red(gvm_engine* e, double* v3) {
+  GVM_CUDA(cudaMemcpyAsync(e->h_red + 4, e->red_out + 4, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  v3[0] = e->h_red[4]; v3[1] = e->h_red[5]; v3[2] = e->h_red[6];
+  return 0;
+}
+
+template <int KIND>
+int launch_value(gvm_engine* e, const PriorArgs& a) {
+  RedBuf r = aux_red(e);
+  k_prior_value<KIND><<<red_grid(e, (long)a.N * a.N), kT, 0, e->stream>>>(a, r.partials, r.pmax, r.counter, r.out);
+  return 0;
+}
+template <int KIND>
+int launch_grad(gvm_engine* e, const PriorArgs& a, float* dgi) {
+  const long MN = (long)a.N * a.N;
+  k_prior_grad<KIND><<<(int)((MN + kT - 1) / kT), kT, 0, e->stream>>>(a, dgi);
+  return 0;
+}
+
+int make_args(gvm_engine* e, int kind, const float* I_dev, int image_index,
+              const gvm_prior_params* p, float lambda, PriorArgs* a) {
+  if (image_index < 0 || image_index > 1) { gvm_set_error("prior: image index %d out of range", image_index); return 1; }
+  const long MN = (long)e->cfg.M * e->cfg.N;
+  a->I = I_dev + MN * image_index;
+  a->noise = e->noise;
+  a->prior_image = p ? p->prior_image_dev : nullptr;
+  a->noise_cut = e->cfg.noise_cut;
+  a->G = p ? p->prior_value : 1.0f;
+  a->eta = p ? p->eta : e->cfg.eta;
+  a->eps = p ? p->epsilon : 0.0f;
+  a->eps_b = p ? p->epsilon_b : 0.0f;
+  a->lambda = lambda;
+  a->N = (int)e->cfg.N;
+  if ((kind == GVM_PRIOR_GENTROPY || kind == GVM_PRIOR_GL1) && !a->prior_image) {
+    gvm_set_error("prior kind %d needs prior_image_dev", kind);
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gvm_prior_value(gvm_engine* e, int kind, const float* I_dev, int image_index,
+                    const gvm_prior_params* p, float* value_out) {
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  PriorArgs a;
+  if (make_args(e, kind, I_dev, image_index, p, 1.0f, &a)) return 1;
+  switch (kind) {
+    case GVM_PRIOR_ENTROPY: launch_value<GVM_PRIOR_ENTROPY>(e, a); break;
+    case GVM_PRIOR_L1: launch_value<GVM_PRIOR_L1>(e, a); break;
+    case GVM_PRIOR_TV: launch_value<GVM_PRIOR_TV>(e, a); break;
+    case GVM_PRIOR_TSV: launch_value<GVM_PRIOR_TSV>(e, a); break;
+    case GVM_PRIOR_LAPLACIAN: launch_value<GVM_PRIOR_LAPLACIAN>(e, a); break;
+    case GVM_PRIOR_QUADRATIC: launch_value<GVM_PRIOR_QUADRATIC>(e, a); break;
+    case GVM_PRIOR_GENTROPY: launch_value<GVM_PRIOR_GENTROPY>(e, a); break;
+    case GVM_PRIOR_GL1: launch_value<GVM_PRIOR_GL1>(e, a); break;
+    default: gvm_set_error("gvm_prior_value: unknown kind %d", kind); return 1;
+  }
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  double v[3];
+  if (fetch_red(e, v)) return 1;
+  *value_out = (float)v[0];
+  return 0;
+}
+
+int gvm_prior_grad(gvm_engine* e, int kind, const float* I_dev, int image_index,
+                   const gvm_prior_params* p, float lambda, float* dgi_dev) {
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  PriorArgs a;
+  if (make_args(e, kind, I_dev, image_index, p, lambda, &a)) return 1;
+  switch (kind) {
+    case GVM_PRIOR_ENTROPY: launch_grad<GVM_PRIOR_ENTROPY>(e, a, dgi_dev); break;
+    case GVM_PRIOR_L1: launch_grad<GVM_PRIOR_L1>(e, a, dgi_dev); break;
+    case GVM_PRIOR_TV: launch_grad<GVM_PRIOR_TV>(e, a, dgi_dev); break;
+    case GVM_PRIOR_TSV: launch_grad<GVM_PRIOR_TSV>(e, a, dgi_dev); break;
+    case GVM_PRIOR_LAPLACIAN: launch_grad<GVM_PRIOR_LAPLACIAN>(e, a, dgi_dev); break;
+    case GVM_PRIOR_QUADRATIC: launch_grad<GVM_PRIOR_QUADRATIC>(e, a, dgi_dev); break;
+    case GVM_PRIOR_GENTROPY: launch_grad<GVM_PRIOR_GENTROPY>(e, a, dgi_dev); break;
+    case GVM_PRIOR_GL1: launch_grad<GVM_PRIOR_GL1>(e, a, dgi_dev); break;
+    default: gvm_set_error("gvm_prior_grad: unknown kind %d", kind); return 1;
+  }
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gvm_add_to_dphi(gvm_engine* e, float* dphi_dev, const float* dgi_dev, int index) {
+  const long MN = (long)e->cfg.M * e->cfg.N;
+  k_add_to_dphi<<<(int)((MN + kT - 1) / kT), kT, 0, e->stream>>>(dphi_dev + MN * index, dgi_dev, MN);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gvm_build_noise_image(gvm_engine* e, float noise_jypix, float* fg_scale_out) {
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  const gvm_config& g = e->cfg;
+  const long MN = g.M * g.N;
+  const int blocks = (int)((MN + kT - 1) / kT);
+  if (e->chans.empty()) { gvm_set_error("gvm_build_noise_image: add the visibility blocks first"); return 1; }
+  float* weight = nullptr;
+  GVM_CUDA(cudaMalloc(&weight, MN * sizeof(float)));
+  GVM_CUDA(cudaMemsetAsync(weight, 0, MN * sizeof(float), e->stream));
+  // one attenuation pattern per distinct field (pointing centre + beam model), at nu_0
+  std::vector<gvm_channel_desc> fields;
+  for (auto& c : e->chans) {
+    bool seen = false;
+    for (auto& f : fields)
+      if (f.ref_xobs_pix == c.d.ref_xobs_pix && f.ref_yobs_pix == c.d.ref_yobs_pix &&
+          f.antenna_diameter == c.d.antenna_diameter && f.pb_factor == c.d.pb_factor &&
+          f.pb_cutoff == c.d.pb_cutoff && f.primary_beam == c.d.primary_beam) seen = true;
+    if (!seen) fields.push_back(c.d);
+  }
+  for (auto& f : fields) {
+    k_weight_accum<<<blocks, kT, 0, e->stream>>>(weight, g.N, g.M, f.antenna_diameter, f.pb_factor,
+                                                 f.pb_cutoff, g.nu_0, f.ref_xobs_pix, f.ref_yobs_pix,
+                                                 g.DELTAX, g.DELTAY, f.primary_beam);
+    GVM_LAUNCH(e);
+  }
+  RedBuf r = aux_red(e);
+  k_max_reduce<<<red_grid(e, MN), kT, 0, e->stream>>>(weight, MN, r.partials, r.pmax, r.counter, r.out);
+  GVM_LAUNCH(e);
+  double v[3];
+  if (fetch_red(e, v)) { cudaFree(weight); return 1; }
+  const float max_weight = (float)v[2];
+  k_noise_image<<<blocks, kT, 0, e->stream>>>(e->noise, weight, MN, max_weight, noise_jypix);
+  GVM_LAUNCH(e);
+  float* d_min = nullptr;
+  GVM_CUDA(cudaMalloc(&d_min, sizeof(float)));
+  const float inf = INFINITY;
+  GVM_CUDA(cudaMemcpyAsync(d_min, &inf, sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  k_min_reduce<<<red_grid(e, MN), kT, 0, e->stream>>>(e->noise, MN, d_min);
+  GVM_LAUNCH(e);
+  float mn = 0.f;
+  GVM_CUDA(cudaMemcpyAsync(&mn, d_min, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(weight);
+  cudaFree(d_min);
+  if (fg_scale_out) *fg_scale_out = mn;
+  return 0;
+}
+
+int gvm_vec_evaluate_xt(gvm_engine* e, float* xt, const float* pcom, const float* xicom, float x,
+                        int image_count, int nopositivity) {
+  const long MN = (long)e->cfg.M * e->cfg.N;
+  const long n = MN * image_count;
+  k_evaluate_xt<<<(int)((n + kT - 1) / kT), kT, 0, e->stream>>>(
+      xt, pcom, xicom, x, MN, image_count, -1.0f * e->cfg.eta * e->cfg.minpix, nopositivity);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  return 0;
+}
+int gvm_vec_new_p(gvm_engine* e, float* p, float* xi, float xmin, int image_count, int nopositivity) {
+  const long MN = (long)e->cfg.M * e->cfg.N;
+  const long n = MN * image_count;
+  k_new_p<<<(int)((n + kT - 1) / kT), kT, 0, e->stream>>>(p, xi, xmin, MN, image_count,
+                                                         -1.0f * e->cfg.eta * e->cfg.minpix, nopositivity);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  return 0;
+}
+int gvm_vec_dot(gvm_engine* e, const float* a, const float* b, int64_t n, float* out) {
+  RedBuf r = aux_red(e);
+  k_dot<<<red_grid(e, n), kT, 0, e->stream>>>(a, b, n, r.partials, r.pmax, r.counter, r.out);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  double v[3];
+  if (fetch_red(e, v)) return 1;
+  *out = (float)v[0];
+  return 0;
+}
+int gvm_vec_gg_dgg(gvm_engine* e, const float* xi, const float* g, int image_count, float* gg, float* dgg) {
+  const long n = (long)e->cfg.M * e->cfg.N * image_count;
+  RedBuf r = aux_red(e);
+  k_gg_dgg<<<red_grid(e, n), kT, 0, e->stream>>>(xi, g, n, r.partials, r.pmax, r.counter, r.out);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  double v[3];
+  if (fetch_red(e, v)) return 1;
+  *gg = (float)v[0];
+  *dgg = (float)v[1];
+  return 0;
+}
+int gvm_vec_grad_condition(gvm_engine* e, const float* xi, const float* p, float den, int image_count, float* gmax) {
+  const long n = (long)e->cfg.M * e->cfg.N * image_count;
+  RedBuf r = aux_red(e);
+  k_grad_condition<<<red_grid(e, n), kT, 0, e->stream>>>(xi, p, den, n, r.partials, r.pmax, r.counter, r.out);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  double v[3];
+  if (fetch_red(e, v)) return 1;
+  *gmax = (float)v[2];
+  return 0;
+}
+int gvm_vec_new_xi(gvm_engine* e, float* g, float* xi, float* h, float gam, int image_count) {
+  const long n = (long)e->cfg.M * e->cfg.N * image_count;
+  k_new_xi<<<(int)((n + kT - 1) / kT), kT, 0, e->stream>>>(g, xi, h, gam, n);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  return 0;
+}
+int gvm_vec_axpby(gvm_engine* e, float a, const float* x, float b, float* y, int64_t n) {
+  k_axpby<<<(int)((n + kT - 1) / kT), kT, 0, e->stream>>>(a, x, b, y, n);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

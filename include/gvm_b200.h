@@ -1,0 +1,239 @@
+/* gvm_b200.h — C-ABI of the B200-native objective/gradient engine.
+ *
+ * gpuvmem has no FFI: its plugin surface is C++ abstract classes compiled into
+ * one executable. This header is the boundary a maintainer
+ * would bind those classes to; every entry point names the reference interface
+ * it replaces (paths relative to the reference tree). The C++ adapters that
+ * reproduce the reference's class surface on top of it live in
+ * gpuvmem_b200/csrc/host/ (see INTEGRATION.md).
+ *
+ * Conventions kept from the reference: images are row-major fp32
+ * I[image][i*N + j] with i = row (y), j = column (x), image 0 = I_nu0 (in units
+ * of fg_scale), image 1 = alpha; M = NAXIS1, N = NAXIS2 and M == N is required
+ * (the reference assumes it, src/functions.cu:2574-2588). All `*_dev` pointers
+ * are device pointers on the engine's GPU; everything else is host memory.
+ * Every function returns 0 on success, non-zero on error (gvm_last_error()).
+ * There is no CPU fallback: without a CUDA device gvm_create fails.
+ */
+#ifndef GVM_B200_H
+#define GVM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gvm_engine gvm_engine;
+
+enum { GVM_BEAM_AIRYDISK = 0, GVM_BEAM_GAUSSIAN = 1 }; /* include/MSFITSIO.cuh:56 */
+
+/* Which gradient kernel gvm_dchi2 runs. AUTO picks UMMA when the separable
+ * w-term bound holds, else SIMT_EXACT. */
+enum {
+  GVM_GRAD_AUTO = 0,
+  GVM_GRAD_UMMA = 1,       /* tcgen05 / TMEM, fp16x3 error-compensated split */
+  GVM_GRAD_SIMT = 2,       /* separable outer-product on CUDA cores, fp32 */
+  GVM_GRAD_SIMT_EXACT = 3  /* per-pair phase incl. the full w-term (reference formula) */
+};
+
+/* Globals of the reference that the hot path reads (src/functions.cu:37-71,
+ * defined src/mfs.cu:4-45). */
+typedef struct gvm_config {
+  int64_t M, N;          /* image size; M == N */
+  double DELTAX, DELTAY; /* CDELT1, CDELT2 in degrees (DELTAX < 0 for RA) */
+  float nu_0;            /* reference frequency (Hz), -F */
+  float eta;             /* -e, default -1 */
+  float minpix;          /* initial_values[0] = -eta * (-z value)  (src/mfs.cu:169) */
+  float noise_cut;       /* ALREADY scaled by min(noise) as src/mfs.cu:916 does */
+  float threshold;       /* -T * 5 (src/mfs.cu:107) */
+  float fg_scale;        /* min(noise image) (src/mfs.cu:912) or 1 if normalize */
+  int device;            /* CUDA device ordinal ("firstgpu") */
+  int grad_mode;         /* GVM_GRAD_* */
+  int keep_vm;           /* also store model visibilities Vm (residual write-back) */
+} gvm_config;
+
+/* One (field, channel, stokes) block of visibilities, i.e. one entry of
+ * fields[f].visibilities[i][s] (include/MSFITSIO.cuh:82-121) plus the antenna
+ * beam model of datasets[d].antennas[0] (include/MSFITSIO.cuh:123-131). */
+typedef struct gvm_channel_desc {
+  float freq;            /* fields[f].nu[i] (float, as the reference stores it) */
+  float antenna_diameter, pb_factor, pb_cutoff;
+  int primary_beam;      /* GVM_BEAM_* */
+  float ref_xobs_pix, ref_yobs_pix; /* pointing centre (attenuation) */
+  float phs_xobs_pix, phs_yobs_pix; /* phase centre (phase_rotate, DChi2) */
+} gvm_channel_desc;
+
+const char* gvm_last_error(void);
+int gvm_version(void);
+
+/* ------------------------------------------------------------- lifecycle -- */
+/* Replaces the device-side part of MFS::setDevice (src/mfs.cu:530-916): per-GPU
+ * scratch (varsPerGPU, include/framework.cuh:49-55), cuFFT plan (initFFT,
+ * src/functions.cu:2142). */
+int gvm_create(const gvm_config* cfg, gvm_engine** out);
+int gvm_destroy(gvm_engine* e);
+/* Use the caller's CUDA stream (cudaStream_t as void*) for all engine work. */
+int gvm_set_stream(gvm_engine* e, void* cuda_stream);
+void* gvm_get_stream(gvm_engine* e);
+int gvm_synchronize(gvm_engine* e);
+/* Update scalars that the reference mutates between runs (fg_scale:
+ * Chi2::setFgScale src/chi2.cu:74; noise_cut; threshold). */
+int gvm_set_scalars(gvm_engine* e, float fg_scale, float noise_cut, float threshold);
+int gvm_set_grad_mode(gvm_engine* e, int grad_mode);
+/* The optimizers' schedule flag `flag_opt` (src/frprmn.cu:46, set from
+ * Optimizer::setFlag): read by the clip in gvm_chi2; gvm_dchi2 also sets it. */
+int gvm_set_flag_opt(gvm_engine* e, int flag_opt);
+
+/* device_noise_image (src/mfs.cu:28; built src/mfs.cu:850-916). M*N floats. */
+int gvm_set_noise_image(gvm_engine* e, const float* noise, int src_is_device);
+/* Builds the noise image on the GPU the way MFS::setDevice does
+ * (total_attenuation -> weight_image -> noise_image, src/functions.cu:2382-2422,
+ * src/mfs.cu:850-916) from the channels already added; returns min(noise) =
+ * fg_scale. Does NOT rescale noise_cut (the caller does, as src/mfs.cu:916). */
+int gvm_build_noise_image(gvm_engine* e, float noise_jypix, float* fg_scale_out);
+int gvm_get_noise_image(gvm_engine* e, float* noise_host);
+/* Gridding-correction image (CKernel::getGCFGPU, include/classes/ckernel.cuh:57);
+ * NULL disables it (ip->getCKernel() == NULL, src/functions.cu:4358). */
+int gvm_set_gcf(gvm_engine* e, const float* gcf_host);
+
+/* Upload one visibility block: raw uvw in METRES as [Z][3] doubles, Vo as [Z][2]
+ * floats, weights [Z]. Performs on the GPU what MFS::setDevice + the
+ * hermitianSymmetry kernel do (src/mfs.cu:555-617, src/functions.cu:2256-2273):
+ * u>0 -> (u,v) negated, Vo conjugated (w untouched), metres -> lambda with the
+ * fp32 wavelength (src/MSFITSIO.cu:36-45); and precomputes the vis_mod cell
+ * index / fractions (src/functions.cu:2569-2586), zeroing the weight of
+ * out-of-grid samples as vis_mod does (:2607). Returns the channel slot. */
+int gvm_add_channel(gvm_engine* e, const gvm_channel_desc* desc, int64_t Z,
+                    const double* uvw_m, const float* Vo, const float* w,
+                    int* chan_out);
+int gvm_num_channels(gvm_engine* e);
+int64_t gvm_channel_nvis(gvm_engine* e, int chan);
+/* Device-side state of a block after upload / a forward pass; any pointer may be
+ * NULL. uvw_lambda [Z][3] doubles, cell [Z][2] int32 (i1, j1), Vo/Vm/Vr [Z][2]. */
+int gvm_get_vis(gvm_engine* e, int chan, double* uvw_lambda, int32_t* cell,
+                float* Vo, float* Vm, float* Vr, float* w);
+
+/* -------------------------------------------------------------- hot path -- */
+/* chi2() (src/functions.cu:4323-4454) incl. ip->clipWNoise (clip2IWNoise, :2694 —
+ * MUTATES I_dev like the reference), calculateInu (:3939), apply_beam2I (:2424),
+ * apply_GCF (:2468), cuFFT inverse C2C (:2165), phase_rotate (:2483), vis_mod
+ * (:2557), residual (:2663), chi2Vector (:2867), deviceReduce (:605).
+ * I_dev: [2][M][N]. Leaves Vr per block for gvm_dchi2. chi2_out = 0.5*sum. */
+int gvm_chi2(gvm_engine* e, float* I_dev, int normalize, float* chi2_out);
+/* Same, but the result stays on the device (no host sync); for graphs. */
+int gvm_chi2_async(gvm_engine* e, float* I_dev, int normalize, double* chi2_dev);
+
+/* dchi2() (src/functions.cu:4456-4558): per block DChi2 (:3698 / :3793 with GCF)
+ * then DChi2_total_I_nu_0 (:4000, flag_opt even) or DChi2_total_alpha (:3968,
+ * flag_opt odd) ACCUMULATED (+=) into result_dchi2_dev [2][M][N], as the
+ * reference does (Chi2::restartDGi zeroes it first, src/chi2.cu:55). */
+int gvm_dchi2(gvm_engine* e, const float* I_dev, int flag_opt, int normalize,
+              float* result_dchi2_dev);
+
+/* End-to-end convenience used by bench.py's e2e leg and the smoke test: host
+ * image in (pinned or pageable), H2D, gvm_chi2, zero + gvm_dchi2, D2H of the
+ * gradient [2][M][N] and chi2. */
+int gvm_eval_host(gvm_engine* e, const float* I_host, int flag_opt, int normalize,
+                  float* chi2_out, float* grad_host);
+
+/* --------------------------------------------------------------- priors --- */
+enum {
+  GVM_PRIOR_ENTROPY = 0,   /* SEntropy/DEntropy  src/functions.cu:4722/4744 */
+  GVM_PRIOR_L1 = 1,        /* L1Norm/DL1Norm     :4633/4655 */
+  GVM_PRIOR_TV = 2,        /* totalvariation/DTVariation :4886/4907 */
+  GVM_PRIOR_TSV = 3,       /* TotalSquaredVariation/DTSVariation :4927/4947 */
+  GVM_PRIOR_LAPLACIAN = 4, /* laplacian/DLaplacian :4808/4828 */
+  GVM_PRIOR_QUADRATIC = 5, /* quadraticP/DQuadraticP :4847/4867 */
+  GVM_PRIOR_GENTROPY = 6,  /* SGEntropy/DGEntropy :4765/4787 (prior image) */
+  GVM_PRIOR_GL1 = 7        /* GL1NormK/DGL1Norm :4675/4700 (prior image) */
+};
+typedef struct gvm_prior_params {
+  float prior_value;  /* Entropy G (Fi::setPrior(float)) */
+  float eta;          /* Entropy eta */
+  float epsilon;      /* L1 (1e-12, src/l1norm.cu:10) / TV epsilon / GL1 epsilon_a */
+  float epsilon_b;    /* GL1 */
+  const float* prior_image_dev; /* GEntropy / GL1Norm prior image, M*N, device */
+} gvm_prior_params;
+
+/* The value host functions: sum over the image of the per-pixel term, masked by
+ * noise < noise_cut. The reference gates on (iter > 0 && lambda != 0)
+ * (e.g. :4643); the gate is the caller's (Fi adapter) business here. */
+int gvm_prior_value(gvm_engine* e, int kind, const float* I_dev, int image_index,
+                    const gvm_prior_params* p, float* value_out);
+/* The gradient host functions: dgi_dev[M*N] = lambda * d(term)/dI, written (not
+ * accumulated), like DS/DL1NormK/... write device_DS. */
+int gvm_prior_grad(gvm_engine* e, int kind, const float* I_dev, int image_index,
+                   const gvm_prior_params* p, float lambda, float* dgi_dev);
+/* linkAddToDPhi / AddToDPhi (src/functions.cu:4560/3890): dphi[index] += dgi. */
+int gvm_add_to_dphi(gvm_engine* e, float* dphi_dev, const float* dgi_dev, int index);
+
+/* ------------------------------------------------- optimizer vector ops ---
+ * Image-sized kernels the optimizers launch (src/functions.cu:2721-2865,
+ * 3556-3687), one fused launch each, reductions finished on the device. */
+/* evaluateXt / evaluateXtNoPositivity (:2832/:2853) for all images:
+ * xt = pcom + x*xicom, image 0 floored at -eta*minpix unless nopositivity. */
+int gvm_vec_evaluate_xt(gvm_engine* e, float* xt, const float* pcom,
+                        const float* xicom, float x, int image_count, int nopositivity);
+/* newP / newPNoPositivity (:2779/:2801): xi *= xmin; p += xi with projection
+ * (xi zeroed where clipped). */
+int gvm_vec_new_p(gvm_engine* e, float* p, float* xi, float xmin, int image_count,
+                  int nopositivity);
+/* sum(a*b) over n floats, fp32 pairwise -> fp64 final. */
+int gvm_vec_dot(gvm_engine* e, const float* a, const float* b, int64_t n, float* out);
+/* getGGandDGG + two deviceReduce (src/frprmn.cu:157-170): gg = sum g*g,
+ * dgg = sum (xi+g)*xi over all images. */
+int gvm_vec_gg_dgg(gvm_engine* e, const float* xi, const float* g, int image_count,
+                   float* gg, float* dgg);
+/* CGGradCondition + deviceMaxReduce (src/frprmn.cu:139-148):
+ * max |xi|*max(|p|,1)/den. */
+int gvm_vec_grad_condition(gvm_engine* e, const float* xi, const float* p, float den,
+                           int image_count, float* gmax);
+/* searchDirection (:3655): g = -xi; xi = h = g.  newXi (:3678): g = -xi;
+ * xi = h = g + gam*h. (gam = 0 and first = 1 give searchDirection.) */
+int gvm_vec_new_xi(gvm_engine* e, float* g, float* xi, float* h, float gam,
+                   int image_count);
+/* y = a*x + b*y over n floats (L-BFGS pieces, :3564-3653). */
+int gvm_vec_axpby(gvm_engine* e, float a, const float* x, float b, float* y, int64_t n);
+
+/* ------------------------------------------------- weights and gridding ---
+ * WeightingScheme::apply (src/{natural,uniform,briggs,radial}weightingscheme.cu)
+ * for ONE dataset of `nblocks` (field,channel,stokes) blocks in the reference's
+ * loop order. uvw_m[b] -> [Z[b]][3] doubles in metres, w[b] updated in place.
+ * All host pointers; the arithmetic runs on the GPU. */
+enum { GVM_W_NATURAL = 0, GVM_W_UNIFORM = 1, GVM_W_BRIGGS = 2, GVM_W_RADIAL = 3 };
+typedef struct gvm_taper {           /* UVTaper::getValue, include/classes/uvtaper.cuh:100 */
+  int enabled;
+  float sigma_maj, sigma_min, bpa, amplitude;
+  double u_0, v_0;
+} gvm_taper;
+int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N,
+                double deltau, double deltav, int nblocks, const int64_t* Z,
+                const double* const* uvw_m, const float* freqs, float* const* w,
+                const gvm_taper* taper);
+
+/* do_gridding (src/functions.cu:1339-1653) for one block: convolutional
+ * gridding of the Hermitian-doubled samples with an m x n CKernel table, then
+ * w_eff = gw^2/gw2, V = gV/gw, row-major compaction of cells with w > 0.
+ * Outputs are written to caller-provided host arrays sized M*N (upper bound);
+ * *nout = number of gridded samples. uvw_out in METRES (cell centres), w = 0. */
+int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double deltav,
+                   float freq, int64_t Z, const double* uvw_m, const float* Vo,
+                   const float* w, const float* ckernel, int ck_m, int ck_n,
+                   int support_x, int support_y, double* uvw_out, float* Vo_out,
+                   float* w_out, int64_t* nout);
+
+/* ------------------------------------------------------------- telemetry -- */
+/* Number of kernels (ours + cuFFT) launched by the engine since creation. */
+int64_t gvm_launch_count(gvm_engine* e);
+/* Device time (ms, CUDA events on the engine stream) of the dominant gradient
+ * kernel over the last gvm_dchi2 call, and how many launches it comprised. */
+int gvm_last_grad_kernel_ms(gvm_engine* e, float* ms, int* launches);
+/* Which kernel the last gvm_dchi2 used (GVM_GRAD_*). */
+int gvm_last_grad_mode(gvm_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVM_B200_H */
