@@ -1,0 +1,184 @@
+"""GPU parity against the REFERENCE ITSELF: gpuvmem's own sources compiled unmodified
+for sm_100a (oracle/_ref/libgvref.so, built by oracle/Makefile from /root/reference
+in the build container; the .so travels to the GPU box, the sources do not).
+
+Everything the reference derives or computes on this path is compared on identical
+synthetic input: the setup scalars and noise image (MFS::configure/setDevice), the
+folded uvw in wavelengths (bit-exact), 0.5*chi2 (rel 1e-5), residuals, the chi2
+gradient for both optimisation flags (rel-L2 1e-4), every prior value/gradient that
+main.cu wires, and the assembled objective/gradient with priors active.
+
+The reference library keeps its state in process globals, so ONE problem is
+initialised per test process (module-scoped fixture)."""
+import os
+
+import numpy as np
+import pytest
+
+from gpuvmem_b200 import Engine, synth
+from gpuvmem_b200.engine import GRAD_AUTO, GRAD_SIMT
+
+pytestmark = pytest.mark.gpu
+
+LAMBDAS = [0.01, 0.005, 0.002, 0.001]  # -Z: Entropy, L1-Norm, TSV, Laplacian (src/main.cu:193-197)
+ARGS = "-X 16 -Y 16 -V 256 -z 0.001 -Z " + ",".join(map(str, LAMBDAS)) + " -t 3 -i synth.ms -o out.ms -m hdr.fits"
+
+
+def _image(e, seed=3):
+    rng = np.random.default_rng(seed)
+    N = e.N
+    yy, xx = np.mgrid[0:N, 0:N]
+    I = e.initial_image()
+    blob = np.exp(-((xx - N * 0.55) ** 2 + (yy - N * 0.45) ** 2) / (2 * (N / 16) ** 2))
+    I[0] = (e.meta["minpix"] * (1.0 + 40.0 * blob + 0.2 * rng.random((N, N)))).astype(np.float32)
+    I[1] = (0.3 * blob + 0.05 * rng.standard_normal((N, N))).astype(np.float32)
+    return I
+
+
+@pytest.fixture(scope="module")
+def setup(gvref):
+    import torch
+    p = synth.make_problem(N=256, nvis=40000, nchan=2, freq0=2.3e11, bandwidth=4e9, seed=21, grid_fill=1.03)
+    gvref.set_problem(p)
+    gvref.init(ARGS)
+    e = Engine.from_problem(p, keep_vm=True, grad_mode=GRAD_AUTO)
+    yield p, e, gvref, torch
+    e.close()
+
+
+def test_setup_scalars_match_reference(setup):
+    p, e, ref, _ = setup
+    s = ref.scalars()
+    m = e.meta
+    assert s["deltau"] == m["deltau"] and s["deltav"] == m["deltav"]
+    assert s["xpix"] == m["xpix"] and s["ypix"] == m["ypix"]
+    assert np.float32(s["nu_0"]) == np.float32(m["nu_0"])
+    assert np.float32(s["pb_cutoff"]) == np.float32(m["pb_cutoff"])
+    assert np.float32(s["pb_factor"]) == np.float32(m["pb_factor"])
+    assert abs(s["vis_noise"] - m["vis_noise"]) <= 1e-6 * s["vis_noise"]
+    assert abs(s["noise_jypix"] - m["noise_jypix"]) <= 1e-5 * s["noise_jypix"]
+    assert abs(s["fg_scale"] - m["fg_scale"]) <= 1e-5 * s["fg_scale"]
+    assert abs(s["noise_cut"] - m["noise_cut"]) <= 1e-5 * s["noise_cut"]
+
+
+def test_noise_image_matches_reference(setup):
+    p, e, ref, _ = setup
+    a, b = e.get_noise_image(), ref.noise_image()
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin)
+    np.testing.assert_allclose(a[fin], b[fin], rtol=2e-5)
+    # same mask
+    s = ref.scalars()
+    assert np.array_equal(a < e.meta["noise_cut"], b < s["noise_cut"])
+
+
+def test_uploaded_visibilities_bit_exact(setup):
+    p, e, ref, _ = setup
+    for c in range(p.nchan):
+        r = ref.get_vis(c)
+        g = e.get_vis(c, want=("uvw", "Vo"))
+        assert np.array_equal(g["uvw"].view(np.uint64), r["uvw"].view(np.uint64)), "hermitianSymmetry + metres->lambda"
+        assert np.array_equal(g["Vo"].view(np.uint32), r["Vo"].view(np.uint32))
+
+
+def test_chi2_and_residuals_match_reference(setup):
+    p, e, ref, torch = setup
+    I = _image(e)
+    ref.set_image(I)
+    want, fi = ref.calc_function(iteration=0)   # priors gated off at iteration 0 -> 0.5*chi2
+    I_dev = torch.from_numpy(I).cuda()
+    got = e.chi2(I_dev)
+    assert abs(got - want) <= 1e-5 * abs(want), (got, want)
+    assert abs(fi[0] - want) <= 1e-6 * abs(want)
+    assert np.array_equal(ref.get_image().view(np.uint32), I_dev.cpu().numpy().view(np.uint32)), "clip2IWNoise"
+    for c in range(p.nchan):
+        r = ref.get_vis(c)
+        g = e.get_vis(c, want=("Vm", "Vr", "w"))
+        assert np.array_equal(g["w"].view(np.uint32), r["w"].view(np.uint32)), "vis_mod zeroes off-grid weights"
+        scale = np.abs(r["Vm"]).max()
+        on = r["w"] > 0
+        assert np.abs(g["Vm"][on] - r["Vm"][on]).max() <= 2e-5 * scale
+        assert np.abs(g["Vr"][on] - r["Vr"][on]).max() <= 2e-5 * max(scale, np.abs(r["Vr"]).max())
+
+
+@pytest.mark.parametrize("flag", [0, 1])
+def test_chi2_gradient_matches_reference(setup, flag):
+    p, e, ref, torch = setup
+    I = _image(e)
+    ref.set_image(I)
+    ref.calc_function(iteration=0)
+    want = ref.calc_gradient(iteration=0, flag=flag)   # priors gated -> pure chi2 gradient
+    I_dev = torch.from_numpy(I).cuda()
+    e.set_flag_opt(flag)
+    e.chi2(I_dev)
+    g = torch.zeros_like(I_dev)
+    e.dchi2(I_dev, g, flag_opt=flag)
+    got = g.cpu().numpy()
+    err = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert err <= 1e-4, (flag, err, e.last_grad_mode())
+    assert np.array_equal(got == 0, want == 0) or np.count_nonzero((got == 0) != (want == 0)) < 4
+
+
+def test_priors_match_reference(setup):
+    p, e, ref, torch = setup
+    I = _image(e)
+    ref.set_image(I)
+    total, fi = ref.calc_function(iteration=1)   # priors active
+    I_dev = torch.from_numpy(I).cuda()
+    chi2 = e.chi2(I_dev)
+    vals = [e.prior_value("Entropy", I_dev, 0, prior_value=0.001, eta=-1.0),
+            e.prior_value("L1-Norm", I_dev, 0, epsilon=1e-12),
+            e.prior_value("TotalSquaredVariation", I_dev, 0),
+            e.prior_value("Laplacian", I_dev, 0)]
+    for k, v in enumerate(vals):
+        assert abs(v - fi[k + 1]) <= 2e-5 * abs(fi[k + 1]), (k, v, fi[k + 1])
+    mine = chi2 + sum(l * v for l, v in zip(LAMBDAS, vals))
+    assert abs(mine - total) <= 2e-5 * abs(total)
+
+
+def test_full_gradient_with_priors_matches_reference(setup):
+    p, e, ref, torch = setup
+    I = _image(e)
+    ref.set_image(I)
+    ref.calc_function(iteration=1)
+    want = ref.calc_gradient(iteration=1, flag=0)
+    I_dev = torch.from_numpy(I).cuda()
+    e.chi2(I_dev)
+    dphi = torch.zeros_like(I_dev)
+    e.dchi2(I_dev, dphi, flag_opt=0)               # Chi2::addToDphi overwrites dphi with result_dchi2
+    dgi = torch.empty(p.N, p.N, device="cuda")
+    for kind, lam, kw in [("Entropy", LAMBDAS[0], dict(prior_value=0.001, eta=-1.0)),
+                          ("L1-Norm", LAMBDAS[1], dict(epsilon=1e-12)),
+                          ("TotalSquaredVariation", LAMBDAS[2], {}), ("Laplacian", LAMBDAS[3], {})]:
+        e.prior_grad(kind, I_dev, dgi, lam, 0, **kw)
+        e.add_to_dphi(dphi, dgi, 0)
+    got = dphi.cpu().numpy()
+    err = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert err <= 1e-4, err
+
+
+def test_reference_distance_to_fp64_truth(setup, oracle):
+    """Reports (and bounds) how far the reference's own fp32 gradient is from the fp64
+    oracle next to how far the engine is: the engine must be at least as close."""
+    p, e, ref, torch = setup
+    from test_parity_gpu import _grad_oracle_sample
+    I = _image(e)
+    ref.set_image(I)
+    ref.calc_function(iteration=0)
+    gref = ref.calc_gradient(iteration=0, flag=0)[0].reshape(-1)
+    I_dev = torch.from_numpy(I).cuda()
+    e.chi2(I_dev)
+    g = torch.zeros_like(I_dev)
+    e.dchi2(I_dev, g, flag_opt=0)
+    gmine = g.cpu().numpy()[0].reshape(-1)
+    pix = np.arange(0, p.N * p.N, 97)
+    truth = _grad_oracle_sample(oracle, p, e, I_dev.cpu().numpy(), pix, 0)
+    err_ref = np.linalg.norm(gref[pix] - truth) / np.linalg.norm(truth)
+    err_mine = np.linalg.norm(gmine[pix] - truth) / np.linalg.norm(truth)
+    print(f"\n[parity] rel-L2 to fp64 oracle: reference={err_ref:.3e} engine={err_mine:.3e}")
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_distances.txt"), "a") as f:
+        f.write(f"N={p.N} Z={p.total_vis()} mode={e.last_grad_mode()} ref_vs_fp64={err_ref:.4e} engine_vs_fp64={err_mine:.4e}\n")
+    assert err_ref <= 1e-4
+    assert err_mine <= max(2e-5, err_ref)
