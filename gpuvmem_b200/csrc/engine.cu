@@ -62,7 +62,9 @@ int gvm_create(const gvm_config* cfg, gvm_engine** out) {
   gvm_engine* e = new gvm_engine();
   e->cfg = *cfg;
   e->sm_count = prop.multiProcessorCount;
-  GVM_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  // a BLOCKING stream: it orders itself against the legacy default stream, which is what the
+  // reference's host code (and torch, by default) launches on — safe drop-in semantics
+  GVM_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamDefault));
   e->own_stream = true;
   const size_t MN = (size_t)cfg->M * cfg->N;
   GVM_CUDA(cudaMalloc(&e->I_nu, MN * sizeof(float2)));

@@ -106,7 +106,8 @@ __device__ inline float gvm_attenuation(int i, int j, float D, float pb_factor, 
   int y0 = (int)yobs;
   float x = (float)((j - x0) * DELTAX * GVM_RPDEG_D);
   float y = (float)((i - y0) * DELTAY * GVM_RPDEG_D);
-  float arc = sqrtf(x * x + y * y);
+  // distance(): src/MSFITSIO.cu:47-51; nvcc contracts it as fma(x, x, y*y) (checked in the reference's SASS)
+  float arc = sqrtf(fmaf(x, x, __fmul_rn(y, y)));
   float lambda = gvm_freq_to_wavelength(freq);
   float atten;
   if (primary_beam == GVM_BEAM_AIRYDISK) {
