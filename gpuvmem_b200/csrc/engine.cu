@@ -107,6 +107,7 @@ int gvm_create(const gvm_config* cfg, gvm_engine** out) {
 static void free_channel(GvmChannel& c) {
   cudaFree(c.uvw_l); cudaFree(c.cell); cudaFree(c.frac); cudaFree(c.Vo); cudaFree(c.w);
   cudaFree(c.Vr); cudaFree(c.Vm); cudaFree(c.du64); cudaFree(c.dv64); cudaFree(c.wz);
+  cudaFree(c.amp); cudaFree(c.gam);
 }
 
 int gvm_destroy(gvm_engine* e) {

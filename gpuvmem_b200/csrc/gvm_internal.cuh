@@ -45,6 +45,9 @@ struct GvmChannel {
   uint64_t* du64 = nullptr;    // frac(u_lambda * DELTAX * pi/180) * 2^64
   uint64_t* dv64 = nullptr;    // frac(v_lambda * DELTAY * pi/180) * 2^64
   float* wz = nullptr;
+  // per-evaluation gradient coefficients of the tensor-core path (grad_umma.cu)
+  float* amp = nullptr;        // w_k |Vr_k| * 2^e
+  uint32_t* gam = nullptr;     // arg(Vr_k) as a 0.32 fixed-point turn
   float max_abs_wz = 0.f;      // max |w| (wavelengths)
   int slot = -1;               // reduction slot of the last forward pass
 };

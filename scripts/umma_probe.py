@@ -1,0 +1,40 @@
+"""Probe of the tensor-core gradient kernel: accuracy vs the CUDA-core separable kernel and
+kernel time, for several TMEM chunk lengths (env GVM_UMMA_CHUNK). Run on the GPU box."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gpuvmem_b200 import Engine, synth  # noqa: E402
+from gpuvmem_b200.engine import GRAD_SIMT, GRAD_UMMA  # noqa: E402
+
+N = int(os.environ.get("PROBE_N", "2048"))
+Z = int(os.environ.get("PROBE_Z", "1000000"))
+chunks = [int(x) for x in os.environ.get("PROBE_CHUNKS", "512,2048,8192,32768").split(",")]
+p = synth.make_problem(N=N, nvis=Z, nchan=1, seed=3)
+e = Engine.from_problem(p, grad_mode=GRAD_SIMT)
+e.use_torch_stream()
+I_dev = torch.from_numpy(e.initial_image()).cuda()
+I_dev[0] *= 1.0 + torch.rand(N, N, device="cuda")
+chi2 = e.chi2(I_dev)
+ref = torch.zeros_like(I_dev)
+e.dchi2(I_dev, ref, 0)
+torch.cuda.synchronize()
+ms_simt, _ = e.last_grad_kernel_ms()
+print(f"N={N} Z={Z} chi2={chi2:.6e} SIMT kernel {ms_simt:.2f} ms "
+      f"({4.0*N*N*Z/ms_simt/1e9:.1f} TFLOP/s algorithmic)", flush=True)
+e.set_grad_mode(GRAD_UMMA)
+for ch in chunks:
+    os.environ["GVM_UMMA_CHUNK"] = str(ch)
+    for rep in range(2):
+        g = torch.zeros_like(I_dev)
+        e.dchi2(I_dev, g, 0)
+        torch.cuda.synchronize()
+    ms, n = e.last_grad_kernel_ms()
+    err = float((g[0] - ref[0]).norm() / ref[0].norm())
+    print(f"chunk={ch:6d}: UMMA kernel {ms:.3f} ms ({4.0*N*N*Z/ms/1e9:.1f} TFLOP/s algorithmic, "
+          f"{ms*1e-3*148*1.9e9/(Z*(N/128)*(N/256)):.1f} SM-clk@1.9GHz per vis-tile) rel-L2 vs SIMT {err:.3e}", flush=True)
+e.close()
