@@ -462,6 +462,9 @@ int gvm_grad_umma(gvm_engine* e, GvmChannel& c, int* ksplit_out) {
   if (chunk < KV) chunk = KV;
   chunk = (chunk / KV) * KV;
 
+  if (const char* s = getenv("GVM_UMMA_KERNEL"))
+    if (atoi(s) == 2) return gvm_grad_umma2_launch(e, c, use_w, chunk, ksplit_out);
+
   const int tiles = ((N + TJ - 1) / TJ) * ((N + TI - 1) / TI);
   // split K so that tiles*ksplit fills whole waves of one-CTA-per-SM, slices >= 2048 samples
   long max_ks = c.Z / 2048;

@@ -1,0 +1,422 @@
+// grad_umma2.cu — the chi2 gradient contraction on CTA pairs (tcgen05 cta_group::2).
+//
+// Same mathematics as grad_umma.cu (see its header): d[i,j] = sum_k Q_k(i) . B_k(j) as a real
+// GEMM with K' = 2Z, operands generated on the fly, fp16x3 error-compensated split, fp32
+// accumulation in TMEM. What changes is the tile: a CTA PAIR (two SMs of one TPC) owns a
+// 256 (i) x 512 (j) output tile as two UMMA 256 x 256 x 16 accumulators (all 512 TMEM
+// columns of both SMs). Per visibility each SM generates 128 A rows + 2 x 128 B rows
+// (384 phasors) for 256 x 512 / 2 outputs — half the generation work and half the
+// shared-memory operand reads per output of the single-CTA kernel, which is what it
+// takes to keep the tensor pipe busy when every operand byte is computed, not loaded:
+//   per SM and visibility:  tensor  2 x 3 x 256x256x2 / (2 x 4096 MAC/clk) = 96 clk
+//                           generation ~ 384 rows x ~17 instr / 128 lanes   ~ 50 clk
+//                           smem: operand reads 48 + stores 24 + records 12 wavefronts
+//
+// Warp roles per CTA (576 threads): 0-11 operand generators (one row per thread: A,
+// B block 0, B block 1), 12-15 epilogue (tcgen05.ld -> red.global.add into the split-K
+// scratch slice), 16 record producer, 17 MMA issuer (leader CTA only) + TMEM owner.
+// Cross-CTA protocol: every generator warp of BOTH CTAs arrives (cluster scope) on the
+// LEADER's operand-full barrier; the leader's tcgen05.commit multicasts the stage-free
+// and accumulator-full arrivals to both CTAs; both epilogues arrive on the leader's
+// accumulator-empty barrier.
+#include <cstdlib>
+
+#include <cuda_fp16.h>
+
+#include "gvm_internal.cuh"
+
+namespace {
+
+constexpr int KV = 32;                      // visibilities per operand stage (64 fp16 = one 128 B row)
+constexpr int NSTAGE = 2;
+constexpr int NVS = 4;
+constexpr int BLK_BYTES = 128 * 128;        // one 128-row operand block, K-major SWIZZLE_128B
+constexpr int STAGE_BYTES = 6 * BLK_BYTES;  // A_hi | A_lo | B0_hi | B0_lo | B1_hi | B1_lo
+constexpr int TILE_I = 256, TILE_J = 512;   // output tile of a CTA pair
+constexpr int REC_BYTES = NVS * KV * 16;
+constexpr int OFF_RECA = NSTAGE * STAGE_BYTES;
+constexpr int OFF_RECB = OFF_RECA + REC_BYTES;
+constexpr int OFF_BAR = OFF_RECB + REC_BYTES;
+constexpr int NBAR = 2 * NSTAGE + 2 * NVS + 2;
+constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+constexpr int GEN_WARPS = 12;
+constexpr int NTHREADS = 18 * 32;
+constexpr uint32_t TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on a barrier that lives in another CTA of the cluster (address from mapa)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+// wait with cluster-scope acquire: the arrivals come from both CTAs of the pair
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// arrive (once the MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void st_global_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// fire-and-forget fp32 add in L2: no load latency in the epilogue; each address is only ever
+// touched by one thread of one CTA, so the result does not depend on scheduling
+__device__ __forceinline__ void red_global_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// K-major SWIZZLE_128B matrix descriptor (see grad_umma.cu)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// kind::f16, D fp32, A/B fp16 K-major, N = 256, M = 256 (cta_group::2)
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+// fractional turn (top 23 bits of a 0.32 fixed-point phase) -> angle - pi, radians; one SHF + one FFMA
+__device__ __forceinline__ float phase_to_angle(uint32_t ph) {
+  const float f = __uint_as_float(__funnelshift_r(ph, 0x7Fu, 9));   // 0x3F800000 | (ph >> 9) = 1 + frac
+  return fmaf(f, 6.283185307179586f, -9.42477796076938f);
+}
+__device__ __forceinline__ void split2(float c, float s, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(c, s);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(c - hf.x, s - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <bool kUseW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_umma2(
+    const uint64_t* __restrict__ du64, const uint64_t* __restrict__ dv64,
+    const float* __restrict__ wz, const float* __restrict__ amp, const uint32_t* __restrict__ gam,
+    const float* __restrict__ gA, const float* __restrict__ gB, long Z, int N, int x0, int y0,
+    long klen, int chunk_stages, float* __restrict__ scratch) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar0 = sbase + OFF_BAR;
+  auto BAR_OP_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto BAR_OP_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+  auto BAR_VIS_FULL = [&](int s) { return bar0 + 8u * (2 * NSTAGE + s); };
+  auto BAR_VIS_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + NVS + s); };
+  const uint32_t BAR_ACC_FULL = bar0 + 8u * (2 * NSTAGE + 2 * NVS);
+  const uint32_t BAR_ACC_EMPTY = BAR_ACC_FULL + 8u;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1;
+  const int tiles_j = (N + TILE_J - 1) / TILE_J;
+  const int tj = pair % tiles_j, ti = pair / tiles_j;
+  const int i0 = ti * TILE_I + 128 * (int)rank;     // this CTA's 128 rows of the 256-row tile
+  const int j0 = tj * TILE_J;
+  const int jb = j0 + 128 * (int)rank;              // this CTA's half of each 256-column B block
+  const int ks = blockIdx.y;
+  const long kbeg = ks * klen;
+  const long kend = (kbeg + klen < Z) ? kbeg + klen : Z;
+  const int nst = (int)((kend - kbeg + KV - 1) / KV);
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; s++) {
+      mbar_init(BAR_OP_FULL(s), 2 * GEN_WARPS);   // generator warps of both CTAs (used in the leader)
+      mbar_init(BAR_OP_EMPTY(s), 1);
+    }
+    for (int s = 0; s < NVS; s++) {
+      mbar_init(BAR_VIS_FULL(s), 32);
+      mbar_init(BAR_VIS_EMPTY(s), GEN_WARPS);
+    }
+    mbar_init(BAR_ACC_FULL, 1);
+    mbar_init(BAR_ACC_EMPTY, 8);                  // 4 epilogue warps x 2 CTAs (used in the leader)
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     sbase + OFF_TMEM), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < GEN_WARPS) {
+    // ================================================= operand generators (one row per thread)
+    const int grp = warp >> 2;               // 0: A rows, 1: B block 0, 2: B block 1
+    const int r = tid & 127;
+    const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+    const uint32_t swz = (uint32_t)(r & 7);
+    // rows are addressed as (record centre) + dr: A centre i0+64; B centre jb+192 (between the blocks)
+    const int dr = (grp == 0) ? r - 64 : (r - 192 + 256 * (grp - 1));
+    float g2 = 0.f;                          // 2 pi * g(row): w-term slope per wavelength of w
+    if (kUseW) {
+      if (grp == 0) g2 = 6.283185307179586f * gB[min(i0 + r, N - 1)];
+      else g2 = 6.283185307179586f * gA[min(jb + 256 * (grp - 1) + r, N - 1)];
+    }
+    const uint32_t rec0 = sbase + (grp == 0 ? OFF_RECA : OFF_RECB);
+    const uint32_t blk_hi = (uint32_t)(2 * grp) * BLK_BYTES + rowoff;
+    const uint32_t full_remote0 = mapa_rank(BAR_OP_FULL(0), 0);   // the leader's barriers
+    for (int it = 0; it < nst; it++) {
+      const int s = it % NSTAGE, vs = it % NVS;
+      mbar_wait(BAR_VIS_FULL(vs), (uint32_t)((it / NVS) & 1));
+      mbar_wait(BAR_OP_EMPTY(s), (uint32_t)(((it / NSTAGE) & 1) ^ 1));
+      const uint32_t hi_row = sbase + (uint32_t)s * STAGE_BYTES + blk_hi, lo_row = hi_row + BLK_BYTES;
+      const uint32_t recs = rec0 + (uint32_t)vs * (KV * 16);
+#pragma unroll 2
+      for (int kq = 0; kq < KV / 4; kq++) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          const uint4 rec = ld_shared_v4(recs + (uint32_t)(kq * 4 + kk) * 16);
+          float a = phase_to_angle(rec.x + (uint32_t)dr * rec.y);
+          if (kUseW) a = fmaf(__uint_as_float(rec.w), g2, a);
+          const float am = __uint_as_float(rec.z);          // 1 for A rows
+          split2(am * __cosf(a), am * __sinf(a), hi[kk], lo[kk]);
+        }
+        const uint32_t off = ((uint32_t)kq ^ swz) << 4;
+        st_shared_v4(hi_row + off, hi[0], hi[1], hi[2], hi[3]);
+        st_shared_v4(lo_row + off, lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_remote(full_remote0 + 8u * s);
+        mbar_arrive(BAR_VIS_EMPTY(vs));
+      }
+    }
+  } else if (warp < 16) {
+    // ================================================= epilogue: TMEM -> split-K scratch slice
+    const int q = warp - 12;
+    const int nchunks = (nst + chunk_stages - 1) / chunk_stages;
+    const int gi = i0 + 32 * q + lane;
+    float* orow = scratch + (size_t)ks * N * N + (size_t)gi * N + j0;
+    const uint32_t acc_empty_remote = mapa_rank(BAR_ACC_EMPTY, 0);
+    for (int c = 0; c < nchunks; c++) {
+      mbar_wait(BAR_ACC_FULL, (uint32_t)(c & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < TILE_J / 32; cb++) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cb * 32), v);
+        tc_wait_ld();
+        if (gi < N) {
+#pragma unroll
+          for (int g = 0; g < 8; g++) {
+            const int j = j0 + cb * 32 + g * 4;
+            if (j < N) {   // N % 4 == 0 (checked on the host)
+              float* p = orow + cb * 32 + g * 4;
+              const float a0 = __uint_as_float(v[4 * g]), a1 = __uint_as_float(v[4 * g + 1]),
+                          a2 = __uint_as_float(v[4 * g + 2]), a3 = __uint_as_float(v[4 * g + 3]);
+              if (c == 0) st_global_v4(p, a0, a1, a2, a3);
+              else red_global_v4(p, a0, a1, a2, a3);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(acc_empty_remote);
+    }
+  } else if (warp == 16) {
+    // ================================================= record producer (lane = visibility)
+    const int ic = i0 + 64, jc = jb + 192;
+    for (int it = 0; it < nst; it++) {
+      const int vs = it % NVS;
+      mbar_wait(BAR_VIS_EMPTY(vs), (uint32_t)(((it / NVS) & 1) ^ 1));
+      const long k = kbeg + (long)it * KV + lane;
+      uint4 ra = make_uint4(0u, 0u, 0x3F800000u, 0u), rb = make_uint4(0u, 0u, 0u, 0u);
+      if (k < kend) {
+        const uint64_t du = __ldg(&du64[k]), dv = __ldg(&dv64[k]);
+        const float wzk = kUseW ? __ldg(&wz[k]) : 0.f;
+        // A: +phase of v_k y_i ; B: arg(Vr_k) - phase of u_k x_j (and -w for the w-term).
+        // The per-row increment is ROUNDED to 32 bits: |dr| <= 192 rows => <= 2.3e-8 turns.
+        ra.x = (uint32_t)((dv * (uint64_t)(int64_t)(ic - y0)) >> 32);
+        ra.y = (uint32_t)((dv + 0x80000000ull) >> 32);
+        ra.w = __float_as_uint(wzk);
+        const uint32_t pu = (uint32_t)((du * (uint64_t)(int64_t)(jc - x0)) >> 32);
+        rb.x = __ldg(&gam[k]) - pu;
+        rb.y = 0u - (uint32_t)((du + 0x80000000ull) >> 32);
+        rb.z = __float_as_uint(__ldg(&amp[k]));
+        rb.w = __float_as_uint(-wzk);
+      }
+      *reinterpret_cast<uint4*>(sgen + OFF_RECA + (vs * KV + lane) * 16) = ra;
+      *reinterpret_cast<uint4*>(sgen + OFF_RECB + (vs * KV + lane) * 16) = rb;
+      mbar_arrive(BAR_VIS_FULL(vs));
+    }
+  } else if (rank == 0 && lane == 0) {
+    // ================================================= MMA issuer (one thread of the leader CTA)
+    for (int it = 0; it < nst; it++) {
+      const int s = it % NSTAGE;
+      const int cpos = it % chunk_stages;
+      if (cpos == 0) {
+        mbar_wait_cluster(BAR_ACC_EMPTY, (uint32_t)(((it / chunk_stages) & 1) ^ 1));
+        tc_fence_after();
+      }
+      mbar_wait_cluster(BAR_OP_FULL(s), (uint32_t)((it / NSTAGE) & 1));
+      tc_fence_after();
+      const uint32_t st0 = sbase + (uint32_t)s * STAGE_BYTES;
+      const uint32_t a_hi = st0, a_lo = st0 + BLK_BYTES;
+#pragma unroll
+      for (int nb = 0; nb < 2; nb++) {
+        const uint32_t b_hi = st0 + (uint32_t)(2 + 2 * nb) * BLK_BYTES, b_lo = b_hi + BLK_BYTES;
+        const uint32_t d = tmem_base + (uint32_t)(nb * 256);
+#pragma unroll
+        for (int kstep = 0; kstep < 4; kstep++) {   // 4 x (K = 16 fp16 = 32 B) inside the 128 B row
+          const uint32_t ko = (uint32_t)kstep * 32;
+          tc_mma_pair_f16(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), kIdesc,
+                          (cpos > 0 || kstep > 0) ? 1u : 0u);
+          tc_mma_pair_f16(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), kIdesc, 1u);
+          tc_mma_pair_f16(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), kIdesc, 1u);
+        }
+      }
+      tc_commit_pair(BAR_OP_EMPTY(s));                 // stage reusable (both CTAs) once retired
+      if (cpos == chunk_stages - 1 || it == nst - 1) tc_commit_pair(BAR_ACC_FULL);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's TMEM / smem / barriers stay alive until both are done
+  if (warp == 17) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+}  // namespace
+
+int gvm_grad_umma2_launch(gvm_engine* e, GvmChannel& c, bool use_w, long chunk, int* ksplit_out) {
+  const int N = (int)e->cfg.N;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GVM_CUDA(cudaFuncSetAttribute(k_grad_umma2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GVM_CUDA(cudaFuncSetAttribute(k_grad_umma2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  chunk = (chunk / KV) * KV;
+  if (chunk < KV) chunk = KV;
+  const int tiles = ((N + TILE_J - 1) / TILE_J) * ((N + TILE_I - 1) / TILE_I);   // CTA pairs per K slice
+  const int pairs_per_wave = e->sm_count / 2;
+  long max_ks = c.Z / 2048;
+  if (max_ks < 1) max_ks = 1;
+  while (max_ks > 1 && (size_t)max_ks * N * N * sizeof(float) > ((size_t)2 << 30)) max_ks--;
+  if (max_ks > 4096) max_ks = 4096;
+  int best = 1;
+  double best_eff = -1.0;
+  for (long ks = 1; ks <= max_ks; ks++) {
+    const long ctas = (long)tiles * ks;
+    const long waves = (ctas + pairs_per_wave - 1) / pairs_per_wave;
+    double eff = (double)ctas / (double)(waves * pairs_per_wave);
+    if (waves < 2 && ks < max_ks) eff *= 0.5 + 0.25 * waves;
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = (int)ks; }
+    if (ctas >= 8L * pairs_per_wave && eff > 0.97) break;
+  }
+  long klen = (c.Z + best - 1) / best;
+  klen = ((klen + KV - 1) / KV) * KV;
+  int ksplit = (int)((c.Z + klen - 1) / klen);
+  if (ksplit < 1) ksplit = 1;
+  if (gvm_ensure_grad_scratch(e, (size_t)ksplit * N * N)) return 1;
+  const int x0 = (int)c.d.phs_xobs_pix, y0 = (int)c.d.phs_yobs_pix;
+  dim3 grid(2 * tiles, ksplit);
+  gvm_ev_begin(e);
+  if (use_w)
+    k_grad_umma2<true><<<grid, NTHREADS, SMEM_BYTES, e->stream>>>(
+        c.du64, c.dv64, c.wz, c.amp, c.gam, e->pixtab, e->pixtab + N, c.Z, N, x0, y0, klen,
+        (int)(chunk / KV), e->grad_scratch);
+  else
+    k_grad_umma2<false><<<grid, NTHREADS, SMEM_BYTES, e->stream>>>(
+        c.du64, c.dv64, c.wz, c.amp, c.gam, e->pixtab, e->pixtab + N, c.Z, N, x0, y0, klen,
+        (int)(chunk / KV), e->grad_scratch);
+  gvm_ev_end(e);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  *ksplit_out = ksplit;
+  return 0;
+}

@@ -157,6 +157,8 @@ int gvm_grad_simt(gvm_engine* e, GvmChannel& c, bool exact, int* ksplit_out);
 // grad_umma.cu
 int gvm_grad_umma(gvm_engine* e, GvmChannel& c, int* ksplit_out);
 bool gvm_grad_umma_supported(const gvm_engine* e, const GvmChannel& c);
+// grad_umma2.cu (CTA-pair kernel)
+int gvm_grad_umma2_launch(gvm_engine* e, GvmChannel& c, bool use_w, long chunk, int* ksplit_out);
 // shared by gradient paths
 int gvm_grad_finish(gvm_engine* e, GvmChannel& c, const float* I_dev, int ksplit, int flag_opt,
                     int normalize, float* result_dev);

@@ -26,6 +26,23 @@ torch.cuda.synchronize()
 ms_simt, _ = e.last_grad_kernel_ms()
 print(f"N={N} Z={Z} chi2={chi2:.6e} SIMT kernel {ms_simt:.2f} ms "
       f"({4.0*N*N*Z/ms_simt/1e9:.1f} TFLOP/s algorithmic)", flush=True)
+# fp64 truth at sampled pixels (CPU oracle; test infrastructure)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from _checkers import Oracle  # noqa: E402
+o = Oracle()
+cfg = dict(D=p.antenna_diameter, DELTAX=p.DELTAX, DELTAY=p.DELTAY, eta=-1.0)
+npix = int(os.environ.get("PROBE_NPIX", "400"))
+pix = np.linspace(0, N * N - 1, npix).astype(np.int64)
+v = e.get_vis(0, want=("uvw", "Vr", "w"))
+Ic = I_dev.cpu().numpy()
+t0 = time.time()
+truth = o.dchi2(pix, N, v["uvw"], v["Vr"], v["w"], e.get_noise_image(), None, float(p.freqs[0]), e.meta, cfg)
+truth = truth * o.chain(Ic, pix, float(p.freqs[0]), e.meta, e.cfg.threshold, 0)
+print(f"oracle: {npix} pixels in {time.time()-t0:.1f} s", flush=True)
+def err64(g):
+    got = g[0].reshape(-1)[torch.from_numpy(pix).cuda()].double().cpu().numpy()
+    return float(np.linalg.norm(got - truth) / np.linalg.norm(truth))
+print(f"SIMT rel-L2 vs fp64 oracle: {err64(ref):.3e}", flush=True)
 e.set_grad_mode(GRAD_UMMA)
 for ch in chunks:
     os.environ["GVM_UMMA_CHUNK"] = str(ch)
@@ -36,5 +53,5 @@ for ch in chunks:
     ms, n = e.last_grad_kernel_ms()
     err = float((g[0] - ref[0]).norm() / ref[0].norm())
     print(f"chunk={ch:6d}: UMMA kernel {ms:.3f} ms ({4.0*N*N*Z/ms/1e9:.1f} TFLOP/s algorithmic, "
-          f"{ms*1e-3*148*1.9e9/(Z*(N/128)*(N/256)):.1f} SM-clk@1.9GHz per vis-tile) rel-L2 vs SIMT {err:.3e}", flush=True)
+          f"{ms*1e-3*148*1.9e9/(Z*(N/128)*(N/256)):.1f} SM-clk@1.9GHz per vis-tile) rel-L2 vs SIMT {err:.3e} vs fp64 {err64(g):.3e}", flush=True)
 e.close()
