@@ -285,14 +285,19 @@ def main():
         pk = peaks()
         mode = e.last_grad_mode()
         Zloc = sum(e.nvis(c) for c in range(e.num_channels()))
-        flops = 4.0 * MN * Zloc                      # algorithmic: 2 FMA per (pixel, visibility) pair
+        ntiles, npx = e.grad_plan()
+        if mode != 1:
+            npx = MN
+        flops = 4.0 * npx * Zloc                     # algorithmic: 2 FMA per (computed pixel, visibility) pair
         ach = flops / (kern_ms / 1e3) / 1e12 if kern_ms > 0 else None
         peak = pk["tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": {1: "k_grad_umma (tcgen05 fp16x3)", 2: "k_grad_sep (CUDA cores fp32)",
+        roof = {"bound": "tensor", "kernel": {1: "k_grad_umma (tcgen05 cta_group::2, fp16x3)", 2: "k_grad_sep (CUDA cores fp32)",
                                               3: "k_grad_exact (CUDA cores)"}.get(mode, str(mode)),
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
                 "traffic": None,
-                "note": f"algorithmic flops 4*M*N*Z per launch = {flops:.3e}; {kern_n} launch(es) per step, "
+                "plan": {"tiles": ntiles, "pixels_computed": npx, "pixels_image": MN},
+                "note": f"algorithmic flops 4*P*Z per launch = {flops:.3e}, P = pixels of the tiles that cover the unmasked "
+                        f"part of the image (masked pixels are skipped, as DChi2 does); {kern_n} launch(es) per step, "
                         f"{kern_ms:.2f} ms; peak = bf16/fp16 dense ({pk['source']}, sustained); the fp16x3 split issues "
                         "3 MMAs per useful product, so frac <= 1/3 by construction"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -120,6 +120,7 @@ int gvm_destroy(gvm_engine* e) {
   cudaFree(e->grad_scratch); cudaFree(e->pixtab); cudaFree(e->I_stage); cudaFree(e->grad_stage);
   cudaFree(e->red_partials); cudaFree(e->red_counter); cudaFree(e->red_sum); cudaFree(e->red_Z);
   cudaFree(e->red_max); cudaFree(e->red_out); cudaFreeHost(e->h_red); cudaFree(e->tile_counter);
+  cudaFree(e->row_ext); cudaFree(e->tile_list); cudaFree(e->band_tab);
   for (auto ev : e->ev) cudaEventDestroy(ev);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -143,6 +144,7 @@ int gvm_set_scalars(gvm_engine* e, float fg_scale, float noise_cut, float thresh
   e->cfg.fg_scale = fg_scale;
   e->cfg.noise_cut = noise_cut;
   e->cfg.threshold = threshold;
+  e->plan_dirty = true;
   return 0;
 }
 int gvm_set_grad_mode(gvm_engine* e, int m) { e->cfg.grad_mode = m; return 0; }
@@ -150,6 +152,7 @@ int gvm_set_flag_opt(gvm_engine* e, int f) { e->flag_opt = f; return 0; }
 
 int gvm_set_noise_image(gvm_engine* e, const float* noise, int src_is_device) {
   const size_t MN = (size_t)e->cfg.M * e->cfg.N;
+  e->plan_dirty = true;
   GVM_CUDA(cudaMemcpyAsync(e->noise, noise, MN * sizeof(float),
                            src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
   GVM_CUDA(cudaStreamSynchronize(e->stream));
@@ -286,13 +289,14 @@ int gvm_dchi2(gvm_engine* e, const float* I_dev, int flag_opt, int normalize,
     if (c.Z <= 0) continue;
     if (c.slot < 0) { gvm_set_error("gvm_dchi2: call gvm_chi2 first (Vr comes from the forward pass)"); return 1; }
     const int mode = pick_grad_mode(e, c);
-    int ksplit = 1;
-    int rc;
-    if (mode == GVM_GRAD_UMMA) rc = gvm_grad_umma(e, c, &ksplit);
-    else rc = gvm_grad_simt(e, c, mode == GVM_GRAD_SIMT_EXACT, &ksplit);
-    if (rc) return rc;
     e->last_grad_mode = mode;
-    if (gvm_grad_finish(e, c, I_dev, ksplit, flag_opt, normalize, result_dchi2_dev)) return 1;
+    if (mode == GVM_GRAD_UMMA) {
+      if (gvm_grad_umma(e, c, I_dev, flag_opt, normalize, result_dchi2_dev)) return 1;
+    } else {
+      int ksplit = 1;
+      if (gvm_grad_simt(e, c, mode == GVM_GRAD_SIMT_EXACT, &ksplit)) return 1;
+      if (gvm_grad_finish(e, c, I_dev, ksplit, flag_opt, normalize, result_dchi2_dev)) return 1;
+    }
   }
   return 0;
 }
@@ -315,6 +319,11 @@ int gvm_eval_host(gvm_engine* e, const float* I_host, int flag_opt, int normaliz
 
 int64_t gvm_launch_count(gvm_engine* e) { return e->launches; }
 int gvm_last_grad_mode(gvm_engine* e) { return e->last_grad_mode; }
+int gvm_grad_plan(gvm_engine* e, int* ntiles, int64_t* pixels) {
+  if (ntiles) *ntiles = e->plan_ntiles;
+  if (pixels) *pixels = e->plan_pixels;
+  return 0;
+}
 int gvm_last_grad_kernel_ms(gvm_engine* e, float* ms, int* launches) {
   float total = 0.f;
   GVM_CUDA(cudaStreamSynchronize(e->stream));

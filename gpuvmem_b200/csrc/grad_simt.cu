@@ -222,45 +222,20 @@ __global__ void k_pixtab(float* __restrict__ tab, int N, int x0, int y0, double 
   tab[N + n] = (float)(-(y * y) / (1.0 + sqrt(1.0 - y * y)));
 }
 
-// Sum the split-K slices in order, then what DChi2 does after its loop
-// (src/functions.cu:3779-3790) and the chain rule of DChi2_total_I_nu_0 /
-// DChi2_total_alpha (:4000-4024 / :3968-3998), accumulated into result.
-__global__ void __launch_bounds__(256) k_grad_finish(
-    const float* __restrict__ scratch, int ksplit, const float* __restrict__ inv_scale,
-    const float* __restrict__ noise, const float* __restrict__ gcf, const float* __restrict__ I,
-    float* __restrict__ result, float* __restrict__ dchi2_out, long N, long M, float noise_cut,
-    float fg_scale, float D, float pb_factor, float pb_cutoff, float freq, float xobs, float yobs,
-    double DELTAX, double DELTAY, int primary_beam, float nu_0, float threshold, int flag_opt,
-    int normalize, long Z) {
+// Sum the split-K slices in a fixed order, then gvm_finish_pixel (scale, chain rule, +=).
+__global__ void __launch_bounds__(256) k_grad_finish(const float* __restrict__ scratch, int ksplit,
+                                                     const float* __restrict__ noise,
+                                                     float noise_cut, GvmFinishParams p) {
   const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  const long MN = M * N;
+  const long MN = p.M * p.N;
   if (idx >= MN) return;
   if (noise[idx] >= noise_cut) {  // DChi2 returns early; device_dchi2 was memset to 0
-    if (dchi2_out) dchi2_out[idx] = 0.0f;
+    if (p.dchi2_out) p.dchi2_out[idx] = 0.0f;
     return;
   }
-  const int i = (int)(idx / N), j = (int)(idx % N);
   float d = 0.0f;
   for (int s = 0; s < ksplit; s++) d += scratch[(size_t)s * MN + idx];
-  if (inv_scale) d *= *inv_scale;
-  const float atten = gvm_attenuation(i, j, D, pb_factor, pb_cutoff, freq, xobs, yobs, DELTAX,
-                                      DELTAY, primary_beam);
-  float scale_factor = fg_scale * atten;
-  if (gcf) scale_factor = scale_factor * gcf[idx];
-  d *= scale_factor;
-  if (normalize) d /= Z;
-  const float dchi2 = -d;
-  if (dchi2_out) dchi2_out[idx] = dchi2;
-  const float I0 = I[idx];
-  const float alpha = I[MN + idx];
-  const float nudiv = freq / nu_0;
-  const float dI = powf(nudiv, alpha);
-  if (flag_opt % 2 == 0) {
-    result[idx] += dchi2 * dI;
-  } else {
-    const float dalpha = I0 * dI * fg_scale * logf(nudiv);
-    if (I0 > threshold) result[MN + idx] += dchi2 * dalpha;
-  }
+  gvm_finish_pixel(p, d, idx, (int)(idx / p.N), (int)(idx % p.N));
 }
 
 }  // namespace
@@ -357,17 +332,25 @@ int gvm_grad_simt(gvm_engine* e, GvmChannel& c, bool exact, int* ksplit_out) {
   return 0;
 }
 
+GvmFinishParams gvm_finish_params(gvm_engine* e, const GvmChannel& c, const float* I_dev, int flag_opt,
+                                  int normalize, float* result_dev) {
+  const gvm_config& g = e->cfg;
+  GvmFinishParams p;
+  p.gcf = e->gcf; p.I = I_dev; p.result = result_dev; p.dchi2_out = e->dchi2;
+  p.N = g.N; p.M = g.M; p.Z = (long)c.Z;
+  p.fg_scale = g.fg_scale; p.D = c.d.antenna_diameter; p.pb_factor = c.d.pb_factor;
+  p.pb_cutoff = c.d.pb_cutoff; p.freq = c.d.freq; p.xobs = c.d.ref_xobs_pix; p.yobs = c.d.ref_yobs_pix;
+  p.nu_0 = g.nu_0; p.threshold = g.threshold; p.DELTAX = g.DELTAX; p.DELTAY = g.DELTAY;
+  p.primary_beam = c.d.primary_beam; p.flag_opt = flag_opt; p.normalize = normalize;
+  return p;
+}
+
 int gvm_grad_finish(gvm_engine* e, GvmChannel& c, const float* I_dev, int ksplit, int flag_opt,
                     int normalize, float* result_dev) {
-  const gvm_config& g = e->cfg;
-  const long MN = g.M * g.N;
-  const float* inv_scale = (e->last_grad_mode == GVM_GRAD_UMMA) ? (e->red_max + e->red_slots + c.slot)
-                                                                 : nullptr;
+  const long MN = e->cfg.M * e->cfg.N;
   k_grad_finish<<<(int)((MN + 255) / 256), 256, 0, e->stream>>>(
-      e->grad_scratch, ksplit, inv_scale, e->noise, e->gcf, I_dev, result_dev, e->dchi2, g.N, g.M,
-      g.noise_cut, g.fg_scale, c.d.antenna_diameter, c.d.pb_factor, c.d.pb_cutoff, c.d.freq,
-      c.d.ref_xobs_pix, c.d.ref_yobs_pix, g.DELTAX, g.DELTAY, c.d.primary_beam, g.nu_0,
-      g.threshold, flag_opt, normalize, (long)c.Z);
+      e->grad_scratch, ksplit, e->noise, e->cfg.noise_cut,
+      gvm_finish_params(e, c, I_dev, flag_opt, normalize, result_dev));
   GVM_LAUNCH(e);
   GVM_CUDA(cudaGetLastError());
   return 0;

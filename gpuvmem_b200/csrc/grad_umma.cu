@@ -1,4 +1,4 @@
-// grad_umma.cu — the chi2 gradient as a tensor-core contraction (tcgen05 / TMEM).
+// grad_umma.cu — the chi2 gradient as a tensor-core contraction (tcgen05 / TMEM, CTA pairs).
 //
 // Reference: DChi2 (src/functions.cu:3698-3791) computes, per unmasked pixel (i,j),
 //   d[i,j] = sum_k w_k (Vr_k.re cos 2 pi phi + Vr_k.im sin 2 pi phi),
@@ -17,16 +17,32 @@
 // the tensor rate and half the shared-memory bytes; the exponent range is handled by
 // an exact power-of-two scale of B taken from max_k w|Vr| (reduced in the forward pass).
 //
-// Kernel layout (one CTA per SM, 448 threads, cta_group::1, UMMA 128 x 256 x 16):
-//   warps 0-3   generate A rows (1 row / thread)        \  st.shared into the canonical
-//   warps 4-7   generate B rows (2 rows / thread)       /  K-major SWIZZLE_128B layout
-//   warps 8-11  epilogue: tcgen05.ld TMEM -> registers -> += split-K scratch slice
-//   warp  12    record producer: coalesced loads of the visibility arrays, per-tile
-//               phase bases -> 16-byte records in shared memory (broadcast to the rows)
-//   warp  13    one thread issues tcgen05.mma / tcgen05.commit; owns TMEM alloc/dealloc
-// Pipelines: records (4 stages), operands (2 stages x 96 KB), accumulator (1 x 256
-// TMEM columns, drained every `chunk` visibilities so that no fp32 TMEM accumulation
-// runs longer than 2*chunk*3 products).
+// Tile plan. DChi2 returns early for masked pixels (noise >= noise_cut, :3723-3726), so
+// only the unmasked part of the image is covered: 256-row bands starting at the first
+// unmasked row, each band cut into tiles of two UMMA column blocks whose width (a
+// multiple of 16, <= 256) is fitted to the band's unmasked column extent. A CTA PAIR
+// (two SMs of one TPC, cta_group::2) owns one 256 x (2 x nbw) tile for one K slice:
+// two UMMA 256 x nbw x 16 accumulators in TMEM. Per visibility each SM generates
+// 128 A rows + 2 x nbw/2 B rows for 256 x 2nbw / 2 outputs — half the generation work and
+// half the shared-memory operand reads per output of a single-CTA 128 x 256 kernel, which
+// is what keeps the tensor pipe busy when every operand byte is computed, not loaded
+// (per SM and visibility at nbw = 256: tensor 96 clk, generation ~50 clk of issue slots,
+// shared memory 48 + 24 + 12 wavefronts).
+//
+// Warp roles per CTA (576 threads): 0-11 operand generators (one row per thread: A,
+// B block 0, B block 1), 12-15 epilogue (tcgen05.ld -> st/red.global into the split-K
+// scratch slice of this tile), 16 record producer (coalesced loads of the visibility
+// arrays, per-tile phase bases -> 16-byte records broadcast to the rows), 17 MMA issuer
+// (leader CTA only) + TMEM owner.
+// Cross-CTA protocol: every generator warp of BOTH CTAs arrives (cluster scope) on the
+// LEADER's operand-full barrier; the leader's tcgen05.commit multicasts the stage-free
+// and accumulator-full arrivals to both CTAs; both epilogues arrive on the leader's
+// accumulator-empty barrier. The accumulator is drained every `chunk` visibilities:
+// TMEM accumulation is fp32 with round-toward-zero per instruction (measured,
+// scripts/diag/umma_arith.cu), so the bias grows linearly with the chunk length
+// (6e-9 relative per visibility): 2048 keeps the gradient at ~1e-5 of the fp64 truth.
+#include <climits>
+#include <algorithm>
 #include <cstdlib>
 
 #include <cuda_fp16.h>
@@ -35,28 +51,38 @@
 
 namespace {
 
-constexpr int TI = 128;                    // UMMA M  (image rows)
-constexpr int TJ = 256;                    // UMMA N  (image columns)
-constexpr int KV = 32;                     // visibilities per operand stage = 64 fp16 = 128 B rows
+constexpr int KV = 32;                      // visibilities per operand stage (64 fp16 = one 128 B row)
 constexpr int NSTAGE = 2;
 constexpr int NVS = 4;
-constexpr int A_BYTES = TI * 128;
-constexpr int B_BYTES = TJ * 128;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A_hi | A_lo | B_hi | B_lo
+constexpr int BLK_BYTES = 128 * 128;        // one 128-row operand block, K-major SWIZZLE_128B
+constexpr int STAGE_BYTES = 6 * BLK_BYTES;  // A_hi | A_lo | B0_hi | B0_lo | B1_hi | B1_lo
+constexpr int TILE_I = 256, TILE_J = 512;   // output tile of a CTA pair
 constexpr int REC_BYTES = NVS * KV * 16;
 constexpr int OFF_RECA = NSTAGE * STAGE_BYTES;
 constexpr int OFF_RECB = OFF_RECA + REC_BYTES;
 constexpr int OFF_BAR = OFF_RECB + REC_BYTES;
 constexpr int NBAR = 2 * NSTAGE + 2 * NVS + 2;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;           // + alignment slack
-constexpr int NTHREADS = 448;
-constexpr int GEN_THREADS = 256;
-constexpr uint32_t TMEM_COLS = 256;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+constexpr int GEN_WARPS = 12;
+constexpr int NTHREADS = 18 * 32;
+constexpr uint32_t TMEM_COLS = 512;
 
-// ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -64,19 +90,29 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
+// arrive on a barrier that lives in another CTA of the cluster (address from mapa)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+// wait with cluster-scope acquire: the arrivals come from both CTAs of the pair
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   }
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -88,19 +124,19 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
+// arrive (once the MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 (fp16 inputs, fp32 accumulate)
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                           uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_pair_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -112,8 +148,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
         "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
         "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
+      : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -126,9 +161,16 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 r;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "r"(addr));
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
+}
+__device__ __forceinline__ void st_global_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// fire-and-forget fp32 add in L2: no load latency in the epilogue; each address is only ever
+// touched by one thread of one CTA, so the result does not depend on scheduling
+__device__ __forceinline__ void red_global_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
@@ -139,16 +181,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) |
          (1ull << 46) | (2ull << 61);
 }
-// Instruction descriptor, kind::f16: D fp32 (bit 4), A/B fp16 (0), both K-major,
-// N>>3 at [17,23), M>>4 at [24,29).
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TJ >> 3) << 17) | ((uint32_t)(TI >> 4) << 24);
+// Instruction descriptor (built per tile): kind::f16, D fp32 (bit 4), A/B fp16 K-major,
+// N>>3 at [17,23), M>>4 at [24,29) with M = 256 for cta_group::2.
 
-// fractional turn (top 23 bits of a 0.32 fixed-point phase) -> angle - pi, in radians
+// fractional turn (top 23 bits of a 0.32 fixed-point phase) -> angle - pi, radians; one SHF + one FFMA
 __device__ __forceinline__ float phase_to_angle(uint32_t ph) {
-  const float f = __uint_as_float(0x3F800000u | (ph >> 9));   // 1 + frac  in [1, 2)
-  return fmaf(f, 6.283185307179586f, -9.42477796076938f);     // 2 pi frac - pi
+  const float f = __uint_as_float(__funnelshift_r(ph, 0x7Fu, 9));   // 0x3F800000 | (ph >> 9) = 1 + frac
+  return fmaf(f, 6.283185307179586f, -9.42477796076938f);
 }
-// error-compensated fp16 split of (c, s): hi = rn(x), lo = rn(x - hi); packed (c | s << 16)
 __device__ __forceinline__ void split2(float c, float s, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(c, s);
   const float2 hf = __half22float2(h);
@@ -183,11 +223,12 @@ __global__ void __launch_bounds__(256) k_grad_coeff(const float2* __restrict__ V
 
 // ---------------------------------------------------------------------------
 template <bool kUseW>
-__global__ void __launch_bounds__(NTHREADS, 1) k_grad_umma(
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_umma(
     const uint64_t* __restrict__ du64, const uint64_t* __restrict__ dv64,
     const float* __restrict__ wz, const float* __restrict__ amp, const uint32_t* __restrict__ gam,
-    const float* __restrict__ gA, const float* __restrict__ gB, long Z, int N, int x0, int y0,
-    long klen, int chunk_stages, float* __restrict__ scratch) {
+    const float* __restrict__ gA, const float* __restrict__ gB, const int4* __restrict__ tile_list,
+    int ntiles, long Z, int N, int x0, int y0, long klen, int chunk_stages,
+    float* __restrict__ scratch) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -201,9 +242,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_grad_umma(
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tiles_j = (N + TJ - 1) / TJ;
-  const int tj = blockIdx.x % tiles_j, ti = blockIdx.x / tiles_j;
-  const int i0 = ti * TI, j0 = tj * TJ;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
+  const int tile = blockIdx.x >> 1;
+  const int4 tl = tile_list[tile];                  // (i0, j0, column-block width, -)
+  const int i0 = tl.x + 128 * (int)rank;            // this CTA's 128 rows of the 256-row tile
+  const int nbw = tl.z;                             // UMMA N: multiple of 16, <= 256
+  const int hb = nbw >> 1;                          // B rows each CTA supplies per column block
+  const int jb = tl.y + hb * (int)rank;             // first column of this CTA's share of block 0
+  const int span = nbw + hb;                        // this CTA's B columns lie in [jb, jb + span)
   const int ks = blockIdx.y;
   const long kbeg = ks * klen;
   const long kend = (kbeg + klen < Z) ? kbeg + klen : Z;
@@ -211,155 +257,125 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_grad_umma(
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; s++) {
-      mbar_init(BAR_OP_FULL(s), GEN_THREADS);
+      mbar_init(BAR_OP_FULL(s), 2 * GEN_WARPS);   // generator warps of both CTAs (used in the leader)
       mbar_init(BAR_OP_EMPTY(s), 1);
     }
     for (int s = 0; s < NVS; s++) {
       mbar_init(BAR_VIS_FULL(s), 32);
-      mbar_init(BAR_VIS_EMPTY(s), GEN_THREADS);
+      mbar_init(BAR_VIS_EMPTY(s), GEN_WARPS);
     }
     mbar_init(BAR_ACC_FULL, 1);
-    mbar_init(BAR_ACC_EMPTY, 128);
+    mbar_init(BAR_ACC_EMPTY, 8);                  // 4 epilogue warps x 2 CTAs (used in the leader)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 13) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     sbase + OFF_TMEM),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     sbase + OFF_TMEM), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 8) {
-    // ================================================= operand generators
-    const bool isA = warp < 4;
-    const int r = tid & 127;                 // row within the 128-row group
-    const int dr = r - 64;
+  if (warp < GEN_WARPS) {
+    // ================================================= operand generators (one row per thread)
+    const int grp = warp >> 2;               // 0: A rows, 1: B block 0, 2: B block 1
+    const int r = tid & 127;
     const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
     const uint32_t swz = (uint32_t)(r & 7);
-    float g2a = 0.f, g2b = 0.f;              // 2 pi * g(row): w-term slope per wavelength of w
+    // rows are addressed as (record centre) + dr: A centre i0+64; B centre jb+span/2
+    const int dr = (grp == 0) ? r - 64 : (r + nbw * (grp - 1) - (span >> 1));
+    const bool active = (grp == 0) || (r < hb);   // narrow column blocks leave B rows idle
+    float g2 = 0.f;                          // 2 pi * g(row): w-term slope per wavelength of w
     if (kUseW) {
-      if (isA) {
-        const int gi = min(i0 + r, N - 1);
-        g2a = 6.283185307179586f * gB[gi];
-      } else {
-        const int gj1 = min(j0 + r, N - 1), gj2 = min(j0 + r + 128, N - 1);
-        g2a = 6.283185307179586f * gA[gj1];
-        g2b = 6.283185307179586f * gA[gj2];
-      }
+      if (grp == 0) g2 = 6.283185307179586f * gB[max(0, min(i0 + r, N - 1))];
+      else g2 = 6.283185307179586f * gA[max(0, min(jb + nbw * (grp - 1) + r, N - 1))];
     }
-    const uint32_t rec0 = sbase + (isA ? OFF_RECA : OFF_RECB);
+    const uint32_t rec0 = sbase + (grp == 0 ? OFF_RECA : OFF_RECB);
+    const uint32_t blk_hi = (uint32_t)(2 * grp) * BLK_BYTES + rowoff;
+    const uint32_t full_remote0 = mapa_rank(BAR_OP_FULL(0), 0);   // the leader's barriers
     for (int it = 0; it < nst; it++) {
       const int s = it % NSTAGE, vs = it % NVS;
       mbar_wait(BAR_VIS_FULL(vs), (uint32_t)((it / NVS) & 1));
       mbar_wait(BAR_OP_EMPTY(s), (uint32_t)(((it / NSTAGE) & 1) ^ 1));
-      const uint32_t st0 = sbase + (uint32_t)s * STAGE_BYTES;
+      const uint32_t hi_row = sbase + (uint32_t)s * STAGE_BYTES + blk_hi, lo_row = hi_row + BLK_BYTES;
       const uint32_t recs = rec0 + (uint32_t)vs * (KV * 16);
-      if (isA) {
-        const uint32_t hi_row = st0 + rowoff, lo_row = st0 + A_BYTES + rowoff;
 #pragma unroll 2
-        for (int kq = 0; kq < KV / 4; kq++) {
-          uint32_t hi[4], lo[4];
+      for (int kq = 0; kq < (active ? KV / 4 : 0); kq++) {
+        uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int kk = 0; kk < 4; kk++) {
-            const uint4 rec = ld_shared_v4(recs + (uint32_t)(kq * 4 + kk) * 16);
-            const uint32_t ph = rec.x + (uint32_t)dr * rec.y;
-            float a = phase_to_angle(ph);
-            if (kUseW) a = fmaf(__uint_as_float(rec.z), g2a, a);
-            split2(__cosf(a), __sinf(a), hi[kk], lo[kk]);
-          }
-          const uint32_t off = ((uint32_t)kq ^ swz) << 4;
-          st_shared_v4(hi_row + off, hi[0], hi[1], hi[2], hi[3]);
-          st_shared_v4(lo_row + off, lo[0], lo[1], lo[2], lo[3]);
+        for (int kk = 0; kk < 4; kk++) {
+          const uint4 rec = ld_shared_v4(recs + (uint32_t)(kq * 4 + kk) * 16);
+          float a = phase_to_angle(rec.x + (uint32_t)dr * rec.y);
+          if (kUseW) a = fmaf(__uint_as_float(rec.w), g2, a);
+          const float am = __uint_as_float(rec.z);          // 1 for A rows
+          split2(am * __cosf(a), am * __sinf(a), hi[kk], lo[kk]);
         }
-      } else {
-        const uint32_t hi_row = st0 + 2 * A_BYTES + rowoff;
-        const uint32_t lo_row = hi_row + B_BYTES;
-#pragma unroll 2
-        for (int kq = 0; kq < KV / 4; kq++) {
-          uint32_t hi1[4], lo1[4], hi2[4], lo2[4];
-#pragma unroll
-          for (int kk = 0; kk < 4; kk++) {
-            const uint4 rec = ld_shared_v4(recs + (uint32_t)(kq * 4 + kk) * 16);
-            const uint32_t ph1 = rec.x + (uint32_t)dr * rec.y;
-            const uint32_t ph2 = ph1 + (rec.y << 7);
-            const float am = __uint_as_float(rec.z);
-            float a1 = phase_to_angle(ph1), a2 = phase_to_angle(ph2);
-            if (kUseW) {
-              const float wn = __uint_as_float(rec.w);
-              a1 = fmaf(wn, g2a, a1);
-              a2 = fmaf(wn, g2b, a2);
-            }
-            split2(am * __cosf(a1), am * __sinf(a1), hi1[kk], lo1[kk]);
-            split2(am * __cosf(a2), am * __sinf(a2), hi2[kk], lo2[kk]);
-          }
-          const uint32_t off = ((uint32_t)kq ^ swz) << 4;
-          st_shared_v4(hi_row + off, hi1[0], hi1[1], hi1[2], hi1[3]);
-          st_shared_v4(lo_row + off, lo1[0], lo1[1], lo1[2], lo1[3]);
-          st_shared_v4(hi_row + 16 * 1024 + off, hi2[0], hi2[1], hi2[2], hi2[3]);   // row + 128
-          st_shared_v4(lo_row + 16 * 1024 + off, lo2[0], lo2[1], lo2[2], lo2[3]);
-        }
+        const uint32_t off = ((uint32_t)kq ^ swz) << 4;
+        st_shared_v4(hi_row + off, hi[0], hi[1], hi[2], hi[3]);
+        st_shared_v4(lo_row + off, lo[0], lo[1], lo[2], lo[3]);
       }
       fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(BAR_OP_FULL(s));
-      mbar_arrive(BAR_VIS_EMPTY(vs));
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_remote(full_remote0 + 8u * s);
+        mbar_arrive(BAR_VIS_EMPTY(vs));
+      }
     }
-  } else if (warp < 12) {
-    // ================================================= epilogue: TMEM -> scratch slice (+=)
-    const int q = warp - 8;
+  } else if (warp < 16) {
+    // ================================================= epilogue: TMEM -> split-K scratch slice
+    const int q = warp - 12;
     const int nchunks = (nst + chunk_stages - 1) / chunk_stages;
-    const int gi = i0 + 32 * q + lane;
-    float* orow = scratch + (size_t)ks * N * N + (size_t)gi * N + j0;
+    // compact scratch: [K slice][tile][256 rows][2 x 256 columns]
+    float* orow = scratch + (((size_t)ks * ntiles + tile) * TILE_I + (128 * rank + 32 * q + lane)) * TILE_J;
+    const int ncb = (nbw + 31) >> 5;
+    const uint32_t acc_empty_remote = mapa_rank(BAR_ACC_EMPTY, 0);
     for (int c = 0; c < nchunks; c++) {
       mbar_wait(BAR_ACC_FULL, (uint32_t)(c & 1));
       tc_fence_after();
 #pragma unroll 1
-      for (int cb = 0; cb < TJ / 32; cb++) {
+      for (int cbi = 0; cbi < 2 * ncb; cbi++) {
+        const int nb = cbi >= ncb, cb = cbi - nb * ncb;
+        const int col = nb * 256 + cb * 32;
         uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cb * 32), v);
+        tc_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)col, v);
         tc_wait_ld();
-        if (gi < N) {
 #pragma unroll
-          for (int g = 0; g < 8; g++) {
-            const int j = j0 + cb * 32 + g * 4;
-            if (j < N) {   // N % 4 == 0 (checked on the host)
-              float4* p = reinterpret_cast<float4*>(orow + cb * 32 + g * 4);
-              float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                                     __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-              if (c > 0) {
-                const float4 prev = *p;
-                o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
-              }
-              *p = o;
-            }
+        for (int g = 0; g < 8; g++) {
+          if (cb * 32 + g * 4 < nbw) {   // nbw % 4 == 0
+            float* p = orow + col + g * 4;
+            const float a0 = __uint_as_float(v[4 * g]), a1 = __uint_as_float(v[4 * g + 1]),
+                        a2 = __uint_as_float(v[4 * g + 2]), a3 = __uint_as_float(v[4 * g + 3]);
+            if (c == 0) st_global_v4(p, a0, a1, a2, a3);
+            else red_global_v4(p, a0, a1, a2, a3);
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(BAR_ACC_EMPTY);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(acc_empty_remote);
     }
-  } else if (warp == 12) {
+  } else if (warp == 16) {
     // ================================================= record producer (lane = visibility)
-    const int ic = i0 + 64, jc = j0 + 64;   // rows are addressed as centre + dr, |dr| <= 64 (+128)
+    const int ic = i0 + 64, jc = jb + (span >> 1);
     for (int it = 0; it < nst; it++) {
       const int vs = it % NVS;
       mbar_wait(BAR_VIS_EMPTY(vs), (uint32_t)(((it / NVS) & 1) ^ 1));
       const long k = kbeg + (long)it * KV + lane;
-      uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = make_uint4(0u, 0u, 0u, 0u);
+      uint4 ra = make_uint4(0u, 0u, 0x3F800000u, 0u), rb = make_uint4(0u, 0u, 0u, 0u);
       if (k < kend) {
         const uint64_t du = __ldg(&du64[k]), dv = __ldg(&dv64[k]);
         const float wzk = kUseW ? __ldg(&wz[k]) : 0.f;
-        // A: +phase of v_k y_i ; B: arg(Vr_k) - phase of u_k x_j (and -w for the w-term)
+        // A: +phase of v_k y_i ; B: arg(Vr_k) - phase of u_k x_j (and -w for the w-term).
+        // The per-row increment is ROUNDED to 32 bits: |dr| <= 192 rows => <= 2.3e-8 turns.
         ra.x = (uint32_t)((dv * (uint64_t)(int64_t)(ic - y0)) >> 32);
-        ra.y = (uint32_t)(dv >> 32);
-        ra.z = __float_as_uint(wzk);
+        ra.y = (uint32_t)((dv + 0x80000000ull) >> 32);
+        ra.w = __float_as_uint(wzk);
         const uint32_t pu = (uint32_t)((du * (uint64_t)(int64_t)(jc - x0)) >> 32);
         rb.x = __ldg(&gam[k]) - pu;
-        rb.y = 0u - (uint32_t)(du >> 32);
+        rb.y = 0u - (uint32_t)((du + 0x80000000ull) >> 32);
         rb.z = __float_as_uint(__ldg(&amp[k]));
         rb.w = __float_as_uint(-wzk);
       }
@@ -367,42 +383,100 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_grad_umma(
       *reinterpret_cast<uint4*>(sgen + OFF_RECB + (vs * KV + lane) * 16) = rb;
       mbar_arrive(BAR_VIS_FULL(vs));
     }
-  } else if (lane == 0) {
-    // ================================================= MMA issuer (one thread)
+  } else if (rank == 0 && lane == 0) {
+    // ================================================= MMA issuer (one thread of the leader CTA)
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(nbw >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
     for (int it = 0; it < nst; it++) {
       const int s = it % NSTAGE;
       const int cpos = it % chunk_stages;
       if (cpos == 0) {
-        mbar_wait(BAR_ACC_EMPTY, (uint32_t)(((it / chunk_stages) & 1) ^ 1));
+        mbar_wait_cluster(BAR_ACC_EMPTY, (uint32_t)(((it / chunk_stages) & 1) ^ 1));
         tc_fence_after();
       }
-      mbar_wait(BAR_OP_FULL(s), (uint32_t)((it / NSTAGE) & 1));
+      mbar_wait_cluster(BAR_OP_FULL(s), (uint32_t)((it / NSTAGE) & 1));
       tc_fence_after();
       const uint32_t st0 = sbase + (uint32_t)s * STAGE_BYTES;
-      const uint32_t a_hi = st0, a_lo = st0 + A_BYTES, b_hi = st0 + 2 * A_BYTES,
-                     b_lo = st0 + 2 * A_BYTES + B_BYTES;
+      const uint32_t a_hi = st0, a_lo = st0 + BLK_BYTES;
 #pragma unroll
-      for (int kstep = 0; kstep < 4; kstep++) {   // 4 x K=16 fp16 = 32 B steps inside the 128 B row
-        const uint32_t ko = (uint32_t)kstep * 32;
-        tc_mma_f16(tmem_base, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), kIdesc,
-                   (cpos > 0 || kstep > 0) ? 1u : 0u);
-        tc_mma_f16(tmem_base, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), kIdesc, 1u);
-        tc_mma_f16(tmem_base, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), kIdesc, 1u);
+      for (int nb = 0; nb < 2; nb++) {
+        const uint32_t b_hi = st0 + (uint32_t)(2 + 2 * nb) * BLK_BYTES, b_lo = b_hi + BLK_BYTES;
+        const uint32_t d = tmem_base + (uint32_t)(nb * 256);
+#pragma unroll
+        for (int kstep = 0; kstep < 4; kstep++) {   // 4 x (K = 16 fp16 = 32 B) inside the 128 B row
+          const uint32_t ko = (uint32_t)kstep * 32;
+          tc_mma_pair_f16(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), idesc,
+                          (cpos > 0 || kstep > 0) ? 1u : 0u);
+          tc_mma_pair_f16(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), idesc, 1u);
+          tc_mma_pair_f16(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), idesc, 1u);
+        }
       }
-      tc_commit(BAR_OP_EMPTY(s));                  // smem stage reusable once these MMAs retire
-      if (cpos == chunk_stages - 1 || it == nst - 1) tc_commit(BAR_ACC_FULL);
+      tc_commit_pair(BAR_OP_EMPTY(s));                 // stage reusable (both CTAs) once retired
+      if (cpos == chunk_stages - 1 || it == nst - 1) tc_commit_pair(BAR_ACC_FULL);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  cluster_sync_all();          // the peer's TMEM / smem / barriers stay alive until both are done
+  if (warp == 17) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(TMEM_COLS)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                  : "memory");
   }
+}
+
+
+// ---------------------------------------------------------------------------
+// First / last unmasked column of every image row (one block per row).
+__global__ void __launch_bounds__(128) k_row_extent(const float* __restrict__ noise, float noise_cut,
+                                                    int N, int2* __restrict__ row_ext) {
+  __shared__ int s_min[4], s_max[4];
+  const int i = blockIdx.x;
+  int lo = INT_MAX, hi = -1;
+  for (int j = threadIdx.x; j < N; j += blockDim.x)
+    if (noise[(size_t)i * N + j] < noise_cut) {
+      lo = min(lo, j);
+      hi = max(hi, j);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lo; s_max[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    row_ext[i] = make_int2(min(min(s_min[0], s_min[1]), min(s_min[2], s_min[3])),
+                           max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3])));
+}
+
+// Sum the K slices of the compact tile scratch in a fixed order, undo the fp16 scale, then the
+// shared finishing math (scale, chain rule, += result).
+__global__ void __launch_bounds__(256) k_grad_finish_tiled(
+    const float* __restrict__ scratch, int ksplit, int ntiles, const float* __restrict__ inv_scale,
+    const float* __restrict__ noise, float noise_cut, const int4* __restrict__ band_tab, int imin,
+    GvmFinishParams p) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long MN = p.M * p.N;
+  if (idx >= MN) return;
+  if (noise[idx] >= noise_cut) {  // DChi2 returns early; device_dchi2 was memset to 0
+    if (p.dchi2_out) p.dchi2_out[idx] = 0.0f;
+    return;
+  }
+  const int i = (int)(idx / p.N), j = (int)(idx % p.N);
+  const int b = (i - imin) / TILE_I;
+  const int4 bt = band_tab[b];                       // (jmin, first tile, tiles, tile width)
+  const int lj = j - bt.x;
+  const int t = lj / bt.w, within = lj - t * bt.w;
+  const int nbw = bt.w >> 1;
+  const int nb = within >= nbw, c = within - nb * nbw;
+  const size_t off = ((size_t)(bt.y + t) * TILE_I + (i - imin - b * TILE_I)) * TILE_J + nb * 256 + c;
+  const size_t stride = (size_t)ntiles * TILE_I * TILE_J;
+  float d = 0.0f;
+  for (int s = 0; s < ksplit; s++) d += scratch[(size_t)s * stride + off];
+  d *= *inv_scale;
+  gvm_finish_pixel(p, d, idx, i, j);
 }
 
 }  // namespace
@@ -426,15 +500,60 @@ static double wterm_turns(const gvm_engine* e, const GvmChannel& c) {
 }
 
 bool gvm_grad_umma_supported(const gvm_engine* e, const GvmChannel& c) {
-  if (e->cfg.N % 4 != 0) return false;
-  if (wterm_turns(e, c) > 4.0) return false;
-  return true;
+  return wterm_turns(e, c) <= 4.0;
 }
 
-int gvm_grad_umma(gvm_engine* e, GvmChannel& c, int* ksplit_out) {
+// (Re)build the tile plan from the noise mask: bands of 256 rows from the first unmasked row,
+// tiles of two column blocks fitted to each band's unmasked extent.
+static int build_plan(gvm_engine* e) {
+  const int N = (int)e->cfg.N;
+  if (!e->row_ext) GVM_CUDA(cudaMalloc(&e->row_ext, (size_t)N * sizeof(int2)));
+  k_row_extent<<<N, 128, 0, e->stream>>>(e->noise, e->cfg.noise_cut, N, e->row_ext);
+  GVM_LAUNCH(e);
+  std::vector<int2> ext(N);
+  GVM_CUDA(cudaMemcpyAsync(ext.data(), e->row_ext, (size_t)N * sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  int imin = -1, imax = -1;
+  for (int i = 0; i < N; i++)
+    if (ext[i].y >= ext[i].x) { if (imin < 0) imin = i; imax = i; }
+  std::vector<int4> tiles, bands;
+  long pixels = 0;
+  if (imin >= 0) {
+    for (int i0 = imin; i0 <= imax; i0 += TILE_I) {
+      int jmin = INT_MAX, jmax = -1;
+      for (int i = i0; i < i0 + TILE_I && i < N; i++)
+        if (ext[i].y >= ext[i].x) { jmin = std::min(jmin, ext[i].x); jmax = std::max(jmax, ext[i].y); }
+      if (jmax < jmin) { bands.push_back(make_int4(0, (int)tiles.size(), 0, 32)); continue; }
+      const int w = jmax - jmin + 1;
+      const int nt = (w + TILE_J - 1) / TILE_J;
+      int tw = (w + nt - 1) / nt;
+      tw = ((tw + 31) / 32) * 32;                     // two column blocks, each a multiple of 16
+      bands.push_back(make_int4(jmin, (int)tiles.size(), nt, tw));
+      for (int t = 0; t < nt; t++) tiles.push_back(make_int4(i0, jmin + t * tw, tw / 2, 0));
+      pixels += (long)nt * TILE_I * tw;
+    }
+  }
+  cudaFree(e->tile_list); cudaFree(e->band_tab);
+  e->tile_list = nullptr; e->band_tab = nullptr;
+  if (!tiles.empty()) {
+    GVM_CUDA(cudaMalloc(&e->tile_list, tiles.size() * sizeof(int4)));
+    GVM_CUDA(cudaMalloc(&e->band_tab, bands.size() * sizeof(int4)));
+    GVM_CUDA(cudaMemcpy(e->tile_list, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    GVM_CUDA(cudaMemcpy(e->band_tab, bands.data(), bands.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  }
+  e->plan_ntiles = (int)tiles.size();
+  e->plan_nbands = (int)bands.size();
+  e->plan_imin = imin < 0 ? 0 : imin;
+  e->plan_pixels = pixels;
+  e->plan_dirty = false;
+  return 0;
+}
+
+int gvm_grad_umma(gvm_engine* e, GvmChannel& c, const float* I_dev, int flag_opt, int normalize,
+                  float* result_dev) {
   const int N = (int)e->cfg.N;
   if (!gvm_grad_umma_supported(e, c)) {
-    gvm_set_error("gvm_grad_umma: unsupported problem (N %% 4 != 0 or w-term beyond 4 turns)");
+    gvm_set_error("gvm_grad_umma: the w-term exceeds 4 turns across the image; use the SIMT kernels");
     return 1;
   }
   static bool attr_set = false;
@@ -443,6 +562,10 @@ int gvm_grad_umma(gvm_engine* e, GvmChannel& c, int* ksplit_out) {
     GVM_CUDA(cudaFuncSetAttribute(k_grad_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
+  if (e->plan_dirty)
+    if (build_plan(e)) return 1;
+  const int ntiles = e->plan_ntiles;
+  if (ntiles == 0) return 0;      // every pixel is masked: the gradient is exactly zero
   if (!c.amp) {
     const size_t z = (size_t)(c.Z > 0 ? c.Z : 1);
     GVM_CUDA(cudaMalloc(&c.amp, z * sizeof(float)));
@@ -456,50 +579,53 @@ int gvm_grad_umma(gvm_engine* e, GvmChannel& c, int* ksplit_out) {
   if (use_w)
     if (gvm_build_pixtab(e, c)) return 1;
 
-  // visibilities per TMEM accumulation chunk (fp32 accumulation length control)
-  long chunk = 8192;
+  // visibilities per TMEM accumulation chunk (bounds the round-toward-zero bias, see header)
+  long chunk = 2048;
   if (const char* s = getenv("GVM_UMMA_CHUNK")) chunk = atol(s);
-  if (chunk < KV) chunk = KV;
   chunk = (chunk / KV) * KV;
+  if (chunk < KV) chunk = KV;
 
-  if (const char* s = getenv("GVM_UMMA_KERNEL"))
-    if (atoi(s) == 2) return gvm_grad_umma2_launch(e, c, use_w, chunk, ksplit_out);
-
-  const int tiles = ((N + TJ - 1) / TJ) * ((N + TI - 1) / TI);
-  // split K so that tiles*ksplit fills whole waves of one-CTA-per-SM, slices >= 2048 samples
+  // split K so that tiles * ksplit fills whole waves of CTA pairs; slices >= 2048 samples
+  const size_t tile_floats = (size_t)TILE_I * TILE_J;
+  const int pairs_per_wave = e->sm_count / 2;
   long max_ks = c.Z / 2048;
   if (max_ks < 1) max_ks = 1;
-  while (max_ks > 1 && (size_t)max_ks * N * N * sizeof(float) > ((size_t)2 << 30)) max_ks--;
-  if (max_ks > 4096) max_ks = 4096;
+  while (max_ks > 1 && (size_t)max_ks * ntiles * tile_floats * sizeof(float) > ((size_t)2 << 30)) max_ks--;
+  if (max_ks > 1024) max_ks = 1024;
   int best = 1;
   double best_eff = -1.0;
   for (long ks = 1; ks <= max_ks; ks++) {
-    const long ctas = (long)tiles * ks;
-    const long waves = (ctas + e->sm_count - 1) / e->sm_count;
-    double eff = (double)ctas / (double)(waves * e->sm_count);
+    const long ctas = (long)ntiles * ks;
+    const long waves = (ctas + pairs_per_wave - 1) / pairs_per_wave;
+    double eff = (double)ctas / (double)(waves * pairs_per_wave);
     if (waves < 2 && ks < max_ks) eff *= 0.5 + 0.25 * waves;   // prefer >= 2 waves when possible
     if (eff > best_eff + 1e-9) { best_eff = eff; best = (int)ks; }
-    if (ctas >= 8L * e->sm_count && eff > 0.97) break;
+    if (ctas >= 8L * pairs_per_wave && eff > 0.97) break;
   }
   long klen = (c.Z + best - 1) / best;
   klen = ((klen + KV - 1) / KV) * KV;
   int ksplit = (int)((c.Z + klen - 1) / klen);
   if (ksplit < 1) ksplit = 1;
-  if (gvm_ensure_grad_scratch(e, (size_t)ksplit * N * N)) return 1;
+  if (gvm_ensure_grad_scratch(e, (size_t)ksplit * ntiles * tile_floats)) return 1;
   const int x0 = (int)c.d.phs_xobs_pix, y0 = (int)c.d.phs_yobs_pix;
-  dim3 grid(tiles, ksplit);
+  dim3 grid(2 * ntiles, ksplit);
   gvm_ev_begin(e);
   if (use_w)
     k_grad_umma<true><<<grid, NTHREADS, SMEM_BYTES, e->stream>>>(
-        c.du64, c.dv64, c.wz, c.amp, c.gam, e->pixtab, e->pixtab + N, c.Z, N, x0, y0, klen,
-        (int)(chunk / KV), e->grad_scratch);
+        c.du64, c.dv64, c.wz, c.amp, c.gam, e->pixtab, e->pixtab + N, e->tile_list, ntiles, c.Z, N,
+        x0, y0, klen, (int)(chunk / KV), e->grad_scratch);
   else
     k_grad_umma<false><<<grid, NTHREADS, SMEM_BYTES, e->stream>>>(
-        c.du64, c.dv64, c.wz, c.amp, c.gam, e->pixtab, e->pixtab + N, c.Z, N, x0, y0, klen,
-        (int)(chunk / KV), e->grad_scratch);
+        c.du64, c.dv64, c.wz, c.amp, c.gam, e->pixtab, e->pixtab + N, e->tile_list, ntiles, c.Z, N,
+        x0, y0, klen, (int)(chunk / KV), e->grad_scratch);
   gvm_ev_end(e);
   GVM_LAUNCH(e);
   GVM_CUDA(cudaGetLastError());
-  *ksplit_out = ksplit;
+  const long MN = e->cfg.M * e->cfg.N;
+  k_grad_finish_tiled<<<(int)((MN + 255) / 256), 256, 0, e->stream>>>(
+      e->grad_scratch, ksplit, ntiles, inv_scale, e->noise, e->cfg.noise_cut, e->band_tab, e->plan_imin,
+      gvm_finish_params(e, c, I_dev, flag_opt, normalize, result_dev));
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
   return 0;
 }

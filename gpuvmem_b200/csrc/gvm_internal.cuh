@@ -89,6 +89,13 @@ struct gvm_engine {
   int ev_used = 0;
   int last_grad_mode = 0;
   unsigned int* tile_counter = nullptr;
+  // tensor-core gradient: tile plan over the unmasked part of the image (grad_umma.cu)
+  bool plan_dirty = true;          // noise image / noise_cut changed since the last plan
+  int2* row_ext = nullptr;         // [N] (first, last) unmasked column of every row (device)
+  int4* tile_list = nullptr;       // [ntiles] (i0, j0, block width, 0)   (device)
+  int4* band_tab = nullptr;        // [nbands] (jmin, first tile, tiles, tile width) (device)
+  int plan_ntiles = 0, plan_nbands = 0, plan_imin = 0;
+  long plan_pixels = 0;            // output pixels the plan computes (algorithmic flops = 4 * this * Z)
 };
 
 #define GVM_LAUNCH(e) ((e)->launches++)
@@ -145,6 +152,43 @@ __device__ inline float gvm_warp_max(float v) {
   return v;
 }
 
+// What DChi2 does after its visibility loop (src/functions.cu:3779-3790) followed by the chain
+// rule of DChi2_total_I_nu_0 (:4000-4024, flag_opt even) / DChi2_total_alpha (:3968-3998, odd),
+// accumulated into result. `d` is the raw sum over visibilities for an UNMASKED pixel.
+struct GvmFinishParams {
+  const float* gcf;
+  const float* I;
+  float* result;
+  float* dchi2_out;
+  long N, M, Z;
+  float fg_scale, D, pb_factor, pb_cutoff, freq, xobs, yobs, nu_0, threshold;
+  double DELTAX, DELTAY;
+  int primary_beam, flag_opt, normalize;
+};
+__device__ inline void gvm_finish_pixel(const GvmFinishParams& p, float d, long idx, int i, int j) {
+  const long MN = p.M * p.N;
+  const float atten = gvm_attenuation(i, j, p.D, p.pb_factor, p.pb_cutoff, p.freq, p.xobs, p.yobs,
+                                      p.DELTAX, p.DELTAY, p.primary_beam);
+  float scale_factor = p.fg_scale * atten;
+  if (p.gcf) scale_factor = scale_factor * p.gcf[idx];
+  d *= scale_factor;
+  if (p.normalize) d /= p.Z;
+  const float dchi2 = -d;
+  if (p.dchi2_out) p.dchi2_out[idx] = dchi2;
+  const float I0 = p.I[idx];
+  const float alpha = p.I[MN + idx];
+  const float nudiv = p.freq / p.nu_0;
+  const float dI = powf(nudiv, alpha);
+  if (p.flag_opt % 2 == 0) {
+    p.result[idx] += dchi2 * dI;
+  } else {
+    const float dalpha = I0 * dI * p.fg_scale * logf(nudiv);
+    if (I0 > p.threshold) p.result[MN + idx] += dchi2 * dalpha;
+  }
+}
+GvmFinishParams gvm_finish_params(gvm_engine* e, const GvmChannel& c, const float* I_dev, int flag_opt,
+                                  int normalize, float* result_dev);
+
 // ------------------------------------------------------------ kernel launchers
 // forward.cu
 int gvm_launch_prep_channel(gvm_engine* e, GvmChannel& c, const double* uvw_m_dev,
@@ -155,10 +199,10 @@ int gvm_reduce_finish(gvm_engine* e, int nslots, int normalize, double* out_dev)
 // grad_simt.cu
 int gvm_grad_simt(gvm_engine* e, GvmChannel& c, bool exact, int* ksplit_out);
 // grad_umma.cu
-int gvm_grad_umma(gvm_engine* e, GvmChannel& c, int* ksplit_out);
+// grad_umma.cu: tensor-core gradient incl. its own finishing pass (accumulates into result_dev)
+int gvm_grad_umma(gvm_engine* e, GvmChannel& c, const float* I_dev, int flag_opt, int normalize,
+                  float* result_dev);
 bool gvm_grad_umma_supported(const gvm_engine* e, const GvmChannel& c);
-// grad_umma2.cu (CTA-pair kernel)
-int gvm_grad_umma2_launch(gvm_engine* e, GvmChannel& c, bool use_w, long chunk, int* ksplit_out);
 // shared by gradient paths
 int gvm_grad_finish(gvm_engine* e, GvmChannel& c, const float* I_dev, int ksplit, int flag_opt,
                     int normalize, float* result_dev);

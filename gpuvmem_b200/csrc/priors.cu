@@ -467,6 +467,7 @@ int gvm_build_noise_image(gvm_engine* e, float noise_jypix, float* fg_scale_out)
   double v[3];
   if (fetch_red(e, v)) { cudaFree(weight); return 1; }
   const float max_weight = (float)v[2];
+  e->plan_dirty = true;
   k_noise_image<<<blocks, kT, 0, e->stream>>>(e->noise, weight, MN, max_weight, noise_jypix);
   GVM_LAUNCH(e);
   float* d_min = nullptr;

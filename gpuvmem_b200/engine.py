@@ -275,6 +275,12 @@ class Engine:
     def last_grad_mode(self):
         return self.lib.gvm_last_grad_mode(self.h)
 
+    def grad_plan(self):
+        """(tiles, output pixels) of the tensor-core gradient's plan over the unmasked pixels."""
+        nt, px = C.c_int(), C.c_int64()
+        self._ck(self.lib.gvm_grad_plan(self.h, C.byref(nt), C.byref(px)))
+        return nt.value, px.value
+
     # -- MFS::configure / setDevice on the host --------------------------------
     @classmethod
     def from_problem(cls, p, device=0, z0=0.001, alpha0=0.0, eta=-1.0, noise_cut=10.0,

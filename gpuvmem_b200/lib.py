@@ -77,6 +77,7 @@ SIGNATURES = {
     "gvm_launch_count": (C.c_int64, [_P]),
     "gvm_last_grad_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "gvm_last_grad_mode": (C.c_int, [_P]),
+    "gvm_grad_plan": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
 }
 
 

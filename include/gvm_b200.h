@@ -230,6 +230,10 @@ int64_t gvm_launch_count(gvm_engine* e);
 /* Device time (ms, CUDA events on the engine stream) of the dominant gradient
  * kernel over the last gvm_dchi2 call, and how many launches it comprised. */
 int gvm_last_grad_kernel_ms(gvm_engine* e, float* ms, int* launches);
+/* Tile plan of the tensor-core gradient after the last gvm_dchi2: number of 256-row tiles that
+ * cover the unmasked pixels (DChi2 skips masked pixels, src/functions.cu:3723-3726) and the
+ * number of output pixels they contain (algorithmic flops of one launch = 4 * pixels * Z). */
+int gvm_grad_plan(gvm_engine* e, int* ntiles, int64_t* pixels);
 /* Which kernel the last gvm_dchi2 used (GVM_GRAD_*). */
 int gvm_last_grad_mode(gvm_engine* e);
 

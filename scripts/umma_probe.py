@@ -15,7 +15,7 @@ N = int(os.environ.get("PROBE_N", "2048"))
 Z = int(os.environ.get("PROBE_Z", "1000000"))
 chunks = [int(x) for x in os.environ.get("PROBE_CHUNKS", "512,2048,8192,32768").split(",")]
 p = synth.make_problem(N=N, nvis=Z, nchan=1, seed=3)
-e = Engine.from_problem(p, grad_mode=GRAD_SIMT)
+e = Engine.from_problem(p, grad_mode=GRAD_SIMT, noise_cut=float(os.environ.get("PROBE_NOISE_CUT", "10")))
 e.use_torch_stream()
 I_dev = torch.from_numpy(e.initial_image()).cuda()
 I_dev[0] *= 1.0 + torch.rand(N, N, device="cuda")
@@ -52,6 +52,8 @@ for ch in chunks:
         torch.cuda.synchronize()
     ms, n = e.last_grad_kernel_ms()
     err = float((g[0] - ref[0]).norm() / ref[0].norm())
-    print(f"chunk={ch:6d}: UMMA kernel {ms:.3f} ms ({4.0*N*N*Z/ms/1e9:.1f} TFLOP/s algorithmic, "
-          f"{ms*1e-3*148*1.9e9/(Z*(N/128)*(N/256)):.1f} SM-clk@1.9GHz per vis-tile) rel-L2 vs SIMT {err:.3e} vs fp64 {err64(g):.3e}", flush=True)
+    nt, px = e.grad_plan()
+    print(f"chunk={ch:6d}: UMMA kernel {ms:.3f} ms, plan {nt} tiles / {px} px of {N*N} "
+          f"({4.0*px*Z/ms/1e9:.1f} TFLOP/s algorithmic on computed pixels; {N*N*Z/ms/1e9:.2f} Mvis*Mpix/s whole image) "
+          f"rel-L2 vs SIMT {err:.3e} vs fp64 {err64(g):.3e}", flush=True)
 e.close()
