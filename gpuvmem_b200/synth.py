@@ -144,12 +144,12 @@ def config_c1(scale=1.0, **kw):
 
 
 def config_c2(scale=1.0, **kw):
-    # 5 km baselines (an extended ALMA configuration): the 2048-pixel field is then about twice the
-    # 12 m primary-beam FWHM, so the default noise mask (noise < 10 min) leaves most of the image
-    # unmasked — the reference's DChi2 and this engine both skip masked pixels, and a compact array
-    # (1 km) would leave only ~2 % of the pixels to compute.
-    kw.setdefault("bmax", 5000.0)
-    kw.setdefault("bmin", 50.0)
+    # Baselines out to ~14 km (ALMA's most extended configurations): the 2048-pixel field is then
+    # about 1.5x the 12 m primary-beam FWHM, so the default noise mask (noise < 10 min) leaves
+    # nearly the whole image unmasked and "Mpix" means computed pixels. The reference's DChi2 and
+    # this engine both skip masked pixels; a compact array (1 km) would leave ~2 % of them.
+    kw.setdefault("bmax", 14000.0)
+    kw.setdefault("bmin", 150.0)
     return make_problem(N=2048, nvis=int(10_000_000 * scale), nchan=1, freq0=2.3e11,
                         name="C2-alma-2048-10M", **kw)
 

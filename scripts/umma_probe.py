@@ -14,7 +14,8 @@ from gpuvmem_b200.engine import GRAD_SIMT, GRAD_UMMA  # noqa: E402
 N = int(os.environ.get("PROBE_N", "2048"))
 Z = int(os.environ.get("PROBE_Z", "1000000"))
 chunks = [int(x) for x in os.environ.get("PROBE_CHUNKS", "512,2048,8192,32768").split(",")]
-p = synth.make_problem(N=N, nvis=Z, nchan=1, seed=3)
+p = synth.make_problem(N=N, nvis=Z, nchan=1, seed=3, bmax=float(os.environ.get("PROBE_BMAX", "1000")),
+                       bmin=float(os.environ.get("PROBE_BMIN", "15")))
 e = Engine.from_problem(p, grad_mode=GRAD_SIMT, noise_cut=float(os.environ.get("PROBE_NOISE_CUT", "10")))
 e.use_torch_stream()
 I_dev = torch.from_numpy(e.initial_image()).cuda()

@@ -1,0 +1,65 @@
+"""Generates tests/golden/ref_small.npz: outputs of the REFERENCE ITSELF (gpuvmem's own sources,
+compiled unmodified for sm_100a into oracle/_ref/libgvref.so) on a small seeded synthetic problem.
+Run on the GPU box (the reference's objective/gradient only exists as CUDA kernels):
+
+    gpurun -- 'python tests/golden/make_golden.py'      # writes gpurun_out/golden/ref_small.npz
+    cp gpurun_out/golden/ref_small.npz tests/golden/
+
+The inputs are NOT stored: tests rebuild them from the same seed with gpuvmem_b200.synth.
+tests/test_oracle_golden.py (CPU, no GPU needed) checks the C oracle against these vectors."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from _checkers import GvRef  # noqa: E402
+from gpuvmem_b200 import synth  # noqa: E402
+
+PROBLEM = dict(N=128, nvis=3000, nchan=2, freq0=2.3e11, bandwidth=4e9, seed=101, grid_fill=1.02)
+LAMBDAS = [0.01, 0.005, 0.002, 0.001]   # -Z: Entropy, L1-Norm, TSV, Laplacian (src/main.cu:193-197)
+ARGS = "-X 16 -Y 16 -V 256 -z 0.001 -Z " + ",".join(map(str, LAMBDAS)) + " -t 3 -i synth.ms -o out.ms -m hdr.fits"
+
+
+def golden_image(N, minpix, seed=3):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:N, 0:N]
+    blob = np.exp(-((xx - N * 0.55) ** 2 + (yy - N * 0.45) ** 2) / (2 * (N / 16) ** 2))
+    I = np.empty((2, N, N), np.float32)
+    I[0] = (minpix * (1.0 + 40.0 * blob + 0.2 * rng.random((N, N)))).astype(np.float32)
+    I[1] = (0.3 * blob + 0.05 * rng.standard_normal((N, N))).astype(np.float32)
+    return I
+
+
+def main():
+    p = synth.make_problem(**PROBLEM)
+    ref = GvRef()
+    ref.set_problem(p)
+    ref.init(ARGS)
+    s = ref.scalars()
+    out = {"scalars_keys": np.array(sorted(s)), "scalars": np.array([s[k] for k in sorted(s)]),
+           "noise": ref.noise_image(), "lambdas": np.array(LAMBDAS)}
+    I = golden_image(p.N, np.float32(0.001))
+    ref.set_image(I)
+    v0, fi0 = ref.calc_function(iteration=0)          # priors gated off: 0.5*chi2
+    out["half_chi2"] = np.float32(v0)
+    out["image_after_clip"] = ref.get_image()
+    for c in range(p.nchan):
+        r = ref.get_vis(c)
+        out[f"uvw_{c}"] = r["uvw"]; out[f"Vm_{c}"] = r["Vm"]; out[f"Vr_{c}"] = r["Vr"]; out[f"w_{c}"] = r["w"]
+    out["grad_flag0"] = ref.calc_gradient(iteration=0, flag=0)
+    out["grad_flag1"] = ref.calc_gradient(iteration=0, flag=1)
+    v1, fi1 = ref.calc_function(iteration=1)          # priors active
+    out["objective_it1"] = np.float32(v1)
+    out["fi_it1"] = fi1
+    out["grad_it1_flag0"] = ref.calc_gradient(iteration=1, flag=0)
+    d = os.path.join(ROOT, "gpurun_out", "golden")
+    os.makedirs(d, exist_ok=True)
+    np.savez_compressed(os.path.join(d, "ref_small.npz"), **out)
+    print("wrote", os.path.join(d, "ref_small.npz"), {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,129 @@
+"""Pins the CPU oracle against GOLDEN VECTORS produced by the reference itself: gpuvmem's own
+CUDA kernels (compiled unmodified for sm_100a) run on a B200 by tests/golden/make_golden.py.
+No GPU needed here: the inputs are rebuilt from the fixture's seed, the oracle (fp64 where the
+reference is fp32) must land within the north_star tolerances of what the reference computed:
+uv folding bit-exact, mask/clip bit-exact, 0.5*chi2 rel 1e-5, residuals, chi2 gradient rel-L2
+1e-4 for both optimisation flags, every prior value main.cu wires, the assembled gradient."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from gpuvmem_b200 import synth
+from gpuvmem_b200.engine import RPDEG_D, beam_model
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden import LAMBDAS, PROBLEM, golden_image  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(HERE, "golden", "ref_small.npz"))
+
+
+@pytest.fixture(scope="module")
+def ctx(gold):
+    p = synth.make_problem(**PROBLEM)
+    s = dict(zip([str(k) for k in gold["scalars_keys"]], gold["scalars"].tolist()))
+    pbf, pbc, pb = beam_model(p.telescope, p.antenna_diameter, float(p.freqs.min()))
+    meta = dict(nu_0=s["nu_0"], pb_factor=pbf, pb_cutoff=pbc, primary_beam=pb, xpix=s["xpix"], ypix=s["ypix"],
+                fg_scale=s["fg_scale"], noise_cut=s["noise_cut"], noise_jypix=s["noise_jypix"], minpix=0.001,
+                deltau=1.0 / (p.M * RPDEG_D * p.DELTAX), deltav=1.0 / (p.N * RPDEG_D * p.DELTAY))
+    cfg = dict(D=p.antenna_diameter, DELTAX=p.DELTAX, DELTAY=p.DELTAY, eta=-1.0)
+    return p, s, meta, cfg
+
+
+def test_setup_scalars(gold, ctx):
+    p, s, meta, cfg = ctx
+    assert s["deltau"] == meta["deltau"] and s["deltav"] == meta["deltav"]
+    assert np.float32(s["pb_factor"]) == np.float32(meta["pb_factor"])
+    assert np.float32(s["pb_cutoff"]) == np.float32(meta["pb_cutoff"])
+    assert s["xpix"] == p.N / 2 and s["ypix"] == p.N / 2
+
+
+def test_noise_image_and_mask(gold, ctx, oracle):
+    p, s, meta, cfg = ctx
+    mn, noise = oracle.noise_image(p.N, cfg, meta)
+    ref = gold["noise"]
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(noise), fin)
+    np.testing.assert_allclose(noise[fin], ref[fin], rtol=2e-6)
+    assert abs(mn - s["fg_scale"]) <= 2e-6 * mn
+    assert np.array_equal(noise < s["noise_cut"], ref < s["noise_cut"])
+
+
+def test_fold_and_lambda_bit_exact(gold, ctx, oracle):
+    p, s, meta, cfg = ctx
+    for c in range(p.nchan):
+        prep = oracle.prep(p.uvw[c], p.Vo[c], p.w[c], float(p.freqs[c]), meta["deltau"], meta["deltav"], p.N)
+        assert np.array_equal(prep["uvw"].view(np.uint64), gold[f"uvw_{c}"].view(np.uint64))
+        assert np.array_equal(prep["w"].view(np.uint32), gold[f"w_{c}"].view(np.uint32))
+
+
+def _forward(oracle, p, meta, cfg, gold):
+    I = golden_image(p.N, np.float32(0.001))
+    oracle.clip(I, gold["noise"], meta["noise_cut"], meta["minpix"], -1.0, 0.0, 0)
+    total = np.float32(0.0)
+    per = []
+    for c in range(p.nchan):
+        prep = oracle.prep(p.uvw[c], p.Vo[c], p.w[c], float(p.freqs[c]), meta["deltau"], meta["deltav"], p.N)
+        Vre, Vim = oracle.model_grid(I, None, float(p.freqs[c]), meta, cfg)
+        sm, Vm, Vr = oracle.degrid_chi2(Vre, Vim, prep, p.N)
+        total = np.float32(total + np.float32(sm))
+        per.append((prep, Vm, Vr))
+    return I, 0.5 * float(total), per
+
+
+def test_chi2_and_residuals(gold, ctx, oracle):
+    p, s, meta, cfg = ctx
+    I, half, per = _forward(oracle, p, meta, cfg, gold)
+    assert np.array_equal(I.view(np.uint32), gold["image_after_clip"].view(np.uint32)), "clip2IWNoise"
+    want = float(gold["half_chi2"])
+    assert abs(half - want) <= 1e-5 * abs(want), (half, want)
+    for c in range(p.nchan):
+        prep, Vm, Vr = per[c]
+        scale = np.abs(gold[f"Vm_{c}"]).max()
+        on = gold[f"w_{c}"] > 0
+        assert np.abs(Vm[on] - gold[f"Vm_{c}"][on]).max() <= 2e-5 * scale
+        assert np.abs(Vr[on] - gold[f"Vr_{c}"][on]).max() <= 2e-5 * max(scale, np.abs(Vr).max())
+
+
+@pytest.mark.parametrize("flag", [0, 1])
+def test_chi2_gradient(gold, ctx, oracle, flag):
+    p, s, meta, cfg = ctx
+    I, half, per = _forward(oracle, p, meta, cfg, gold)
+    pix = np.arange(p.N * p.N)
+    tot = np.zeros(len(pix))
+    for c in range(p.nchan):
+        prep, Vm, Vr = per[c]
+        # the gradient consumes the residuals of the forward pass; use the reference's own Vr
+        d = oracle.dchi2(pix, p.N, gold[f"uvw_{c}"], gold[f"Vr_{c}"], gold[f"w_{c}"], gold["noise"], None,
+                         float(p.freqs[c]), meta, cfg)
+        tot += d * oracle.chain(I, pix, float(p.freqs[c]), meta, 0.0, flag)
+    want = gold[f"grad_flag{flag}"]
+    got = tot.reshape(p.N, p.N)
+    err = np.linalg.norm(got - want[flag % 2]) / np.linalg.norm(want[flag % 2])
+    assert err <= 1e-4, err
+    assert not want[1 - flag % 2].any()
+    masked = gold["noise"] >= meta["noise_cut"]
+    assert not got[masked].any() and not want[flag % 2][masked].any()
+
+
+def test_priors_and_objective(gold, ctx, oracle):
+    p, s, meta, cfg = ctx
+    I, half, per = _forward(oracle, p, meta, cfg, gold)
+    fi = gold["fi_it1"]
+    kinds = [0, 1, 3, 4]   # Entropy, L1-Norm, TSV, Laplacian
+    vals = [oracle.prior_value(k, I[0], gold["noise"], meta["noise_cut"], G=0.001, eta=-1.0, eps=1e-12) for k in kinds]
+    for k, v in enumerate(vals):
+        assert abs(v - fi[k + 1]) <= 2e-5 * abs(fi[k + 1]), (k, v, fi[k + 1])
+    total = half + sum(l * v for l, v in zip(LAMBDAS, vals))
+    assert abs(total - float(gold["objective_it1"])) <= 2e-5 * abs(total)
+    # assembled gradient: chi2 gradient (from the golden pure-chi2 vector) + lambda * prior gradients
+    g = gold["grad_flag0"][0].astype(np.float64)
+    for k, lam in zip(kinds, LAMBDAS):
+        g = g + oracle.prior_grad(k, I[0], gold["noise"], meta["noise_cut"], lam, G=0.001, eta=-1.0, eps=1e-12)
+    want = gold["grad_it1_flag0"][0]
+    assert np.linalg.norm(g - want) / np.linalg.norm(want) <= 1e-5
