@@ -1,16 +1,440 @@
-// weights_grid.cu — imaging weights and convolutional gridding (placeholder for the
-// first GPU bring-up; replaced by the GPU implementation).
+// weights_grid.cu — imaging weights (natural / uniform / Briggs / radial) and convolutional
+// gridding on the GPU, bit-exact with the reference's host code run with ONE thread.
+//
+// Reference: WeightingScheme::apply (src/{natural,uniform,briggs,radial}weightingscheme.cu)
+// and do_gridding (src/functions.cu:1339-1653). Both accumulate fp32 sums sample by sample
+// (under `omp critical` / `omp atomic`), so the result depends on the order; the only
+// deterministic reference order is the single-thread one (ascending sample index). It is
+// reproduced exactly: samples are STABLY radix-sorted by grid cell (cub) and every cell is summed
+// sequentially in ascending sample order by one thread; all fp32 arithmetic uses explicit
+// round-to-nearest intrinsics so that nvcc cannot contract what gcc does not (the reference's
+// host code is compiled for baseline x86-64: separate multiply and add). Cell indices use the
+// reference's mixed fp32/fp64 arithmetic verbatim.
+// The two order-dependent SCALARS of Briggs (sum of weights, sum of squared grid weights over
+// the half plane; src/briggsweightingscheme.cu:46-110) are sequential fp32 sums over host /
+// downloaded data in the reference's loop order. UVTaper (include/classes/uvtaper.cuh:100) is
+// evaluated on the host: it calls libm's exp/cosf/sinf, which no device routine matches bit for bit.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include <cub/cub.cuh>
+
 #include "gvm_internal.cuh"
+
+namespace {
+
+#define WG_CUDA(call)                                                                \
+  do {                                                                               \
+    cudaError_t _e = (call);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      gvm_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return 1;                                                                      \
+    }                                                                                \
+  } while (0)
+
+constexpr uint32_t kNoCell = 0xFFFFFFFFu;
+
+// src/uniformweightingscheme.cu:36-49 / src/briggsweightingscheme.cu:75-88
+__global__ void __launch_bounds__(256) k_weight_cells(const double* __restrict__ uvw_m, long Z, float freq,
+                                                      double adu, double adv, long M, long N,
+                                                      uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const long z = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (z >= Z) return;
+  double u = gvm_metres_to_lambda(uvw_m[3 * z], freq);
+  double v = gvm_metres_to_lambda(uvw_m[3 * z + 1], freq);
+  if (u < 0.0) { u *= -1.0; v *= -1.0; }
+  const double gx = u / adu, gy = v / adv;
+  const int x = (int)(gx + (double)(int)(N / 2) + 0.5);
+  const int y = (int)(gy + (double)(int)(M / 2) + 0.5);
+  keys[z] = (x >= 0 && y >= 0 && x < N && y < M) ? (uint32_t)(N * y + x) : kNoCell;
+  vals[z] = (uint32_t)z;
+}
+
+// One thread per segment head of the sorted (cell, sample) list: sequential fp32 sum of the
+// cell's samples in ascending sample order, starting from what the grid already holds.
+__global__ void __launch_bounds__(256) k_cell_accumulate(const uint32_t* __restrict__ keys,
+                                                         const uint32_t* __restrict__ vals, long n,
+                                                         const float* __restrict__ w, float* __restrict__ grid) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t c = keys[t];
+  if (c == kNoCell || (t > 0 && keys[t - 1] == c)) return;
+  float g = grid[c];
+  for (long s = t; s < n && keys[s] == c; s++) g = __fadd_rn(g, w[vals[s]]);
+  grid[c] = g;
+}
+
+// uniform: w /= g (src/uniformweightingscheme.cu:82-86); Briggs: w /= (1.0 + g * f2) in double
+// (src/briggsweightingscheme.cu:172-173); off-grid samples get weight 0.
+__global__ void __launch_bounds__(256) k_weight_apply(const uint32_t* __restrict__ keys,
+                                                      const uint32_t* __restrict__ vals, long n,
+                                                      const float* __restrict__ grid, int briggs, float f2,
+                                                      float* __restrict__ w) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t c = keys[t], z = vals[t];
+  if (c == kNoCell) { w[z] = 0.0f; return; }
+  const float g = grid[c];
+  if (briggs) w[z] = (float)((double)w[z] / (1.0 + (double)__fmul_rn(g, f2)));
+  else w[z] = __fdiv_rn(w[z], g);
+}
+
+__global__ void __launch_bounds__(256) k_clear_cells(const uint32_t* __restrict__ keys, long n,
+                                                     float* __restrict__ grid) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t < n && keys[t] != kNoCell) grid[keys[t]] = 0.0f;
+}
+
+// src/radialweightingscheme.cu: w *= distance((float)u, (float)v, 0, 0), no Hermitian fold
+__global__ void __launch_bounds__(256) k_radial(const double* __restrict__ uvw_m, long Z, float freq,
+                                                float* __restrict__ w) {
+  const long z = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (z >= Z) return;
+  const float u = (float)gvm_metres_to_lambda(uvw_m[3 * z], freq);
+  const float v = (float)gvm_metres_to_lambda(uvw_m[3 * z + 1], freq);
+  const float d = sqrtf(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)));
+  w[z] = __fmul_rn(w[z], d);
+}
+
+// ------------------------------------------------------------------ gridding
+// Centre cell of every Hermitian-doubled sample on the grid EXTENDED by the kernel support
+// (src/functions.cu:1432-1461); samples whose taps cannot reach the grid are dropped.
+__global__ void __launch_bounds__(256) k_grid_centres(const double* __restrict__ uvw_m, long Z, float freq,
+                                                      double deltau, double deltav, long M, long N, int sx,
+                                                      int sy, uint32_t* __restrict__ keys,
+                                                      uint32_t* __restrict__ vals) {
+  const long z = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (z >= 2 * Z) return;
+  const long vi = (z < Z) ? z : z - Z;
+  double u = uvw_m[3 * vi], v = uvw_m[3 * vi + 1];
+  if (z >= Z) { u *= -1.0; v *= -1.0; }
+  u = gvm_metres_to_lambda(u, freq);
+  v = gvm_metres_to_lambda(v, freq);
+  const double gx = u / deltau, gy = v / deltav;
+  const double j_fp = gx + floor(N / 2.0) + 0.5, k_fp = gy + floor(M / 2.0) + 0.5;
+  const int j = (int)j_fp, k = (int)k_fp;
+  const long EW = N + 2L * sx;
+  const bool ok = (j >= -sx && j < N + sx && k >= -sy && k < M + sy);
+  keys[z] = ok ? (uint32_t)((long)(k + sy) * EW + (j + sx)) : kNoCell;
+  vals[z] = (uint32_t)z;
+}
+
+__device__ __forceinline__ long lower_bound_u32(const uint32_t* __restrict__ a, long n, uint32_t key) {
+  long lo = 0, hi = n;
+  while (lo < hi) {
+    const long mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+constexpr int kMaxTaps = 17 * 17;
+
+// One thread per output cell: merge the (<= taps) sorted sample lists of the centre cells whose
+// kernel footprint covers this cell, in ascending sample order, and accumulate exactly like the
+// reference's sequential loop (src/functions.cu:1466-1505), then normalise (:1537-1558).
+__global__ void __launch_bounds__(128) k_grid_accumulate(
+    const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long n, long Z,
+    const float2* __restrict__ Vo, const float* __restrict__ w, const float* __restrict__ kernel, int ck_m,
+    int ck_n, int sx, int sy, long M, long N, float* __restrict__ out_w, float2* __restrict__ out_V) {
+  const long cell = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (cell >= M * N) return;
+  const int gk = (int)(cell / N), gj = (int)(cell % N);
+  const long EW = N + 2L * sx;
+  int head[kMaxTaps], tail[kMaxTaps];
+  float ckv[kMaxTaps];
+  int nl = 0;
+  for (int m = -sy; m <= sy; m++)
+    for (int nn = -sx; nn <= sx; nn++) {
+      const int ki = m + sy, kj = nn + sx;
+      if (ki < 0 || ki >= ck_m || kj < 0 || kj >= ck_n) continue;
+      // centre (k, j) with k + m == gk, j + nn == gj
+      const long ek = (long)(gk - m + sy), ej = (long)(gj - nn + sx);
+      const uint32_t key = (uint32_t)(ek * EW + ej);
+      const long b = lower_bound_u32(keys, n, key);
+      if (b < n && keys[b] == key) {
+        const long e = lower_bound_u32(keys, n, key + 1);
+        head[nl] = (int)b; tail[nl] = (int)e; ckv[nl] = kernel[ck_n * ki + kj];
+        nl++;
+      }
+    }
+  float gw = 0.f, gw2 = 0.f, gvr = 0.f, gvi = 0.f;
+  while (true) {
+    uint32_t best = kNoCell; int bl = -1;
+    for (int l = 0; l < nl; l++)
+      if (head[l] < tail[l]) {
+        const uint32_t z = vals[head[l]];
+        if (z < best) { best = z; bl = l; }
+      }
+    if (bl < 0) break;
+    head[bl]++;
+    const long vi = (best < (uint32_t)Z) ? (long)best : (long)best - Z;
+    const float wt = w[vi];
+    float2 vo = Vo[vi];
+    if (best >= (uint32_t)Z) vo.y *= -1.0f;
+    const float ck = ckv[bl];
+    const float ck2 = __fmul_rn(ck, ck);
+    gw = __fadd_rn(gw, __fmul_rn(wt, ck));
+    gw2 = __fadd_rn(gw2, __fmul_rn(wt, ck2));
+    gvr = __fadd_rn(gvr, __fmul_rn(__fmul_rn(wt, vo.x), ck));
+    gvi = __fadd_rn(gvi, __fmul_rn(__fmul_rn(wt, vo.y), ck));
+  }
+  float weight = 0.f, orr = 0.f, oi = 0.f;
+  if (gw2 != 0.0f && gw != 0.0f) {
+    weight = __fdiv_rn(__fmul_rn(gw, gw), gw2);
+    orr = __fdiv_rn(gvr, gw);
+    oi = __fdiv_rn(gvi, gw);
+  }
+  out_w[cell] = weight;
+  out_V[cell] = make_float2(orr, oi);
+}
+
+__global__ void __launch_bounds__(256) k_grid_flags(const float* __restrict__ wgt, long MN,
+                                                    int* __restrict__ flags) {
+  const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (c < MN) flags[c] = wgt[c] > 0.0f ? 1 : 0;
+}
+
+// Row-major compaction (src/functions.cu:1591-1612) with the cell-centre coordinates in metres
+// (:1524-1532): u = (j - floor(N/2)) * deltau * lambda.
+__global__ void __launch_bounds__(256) k_grid_compact(const float* __restrict__ wgt,
+                                                      const float2* __restrict__ V,
+                                                      const int* __restrict__ pos, long M, long N,
+                                                      double deltau, double deltav, float lambda,
+                                                      double* __restrict__ uvw_out, float2* __restrict__ Vo_out,
+                                                      float* __restrict__ w_out) {
+  const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (c >= M * N) return;
+  const float weight = wgt[c];
+  if (!(weight > 0.0f)) return;
+  const long gk = c / N, gj = c % N;
+  const int o = pos[c];
+  const double ul = __dmul_rn((double)gj - floor(N / 2.0), deltau);
+  const double vl = __dmul_rn((double)gk - floor(M / 2.0), deltav);
+  uvw_out[3 * o] = __dmul_rn(ul, (double)lambda);
+  uvw_out[3 * o + 1] = __dmul_rn(vl, (double)lambda);
+  uvw_out[3 * o + 2] = 0.0;
+  Vo_out[o] = V[c];
+  w_out[o] = weight;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { cudaFree(p); }
+  int ensure(size_t n) {
+    if (n <= bytes) return 0;
+    cudaFree(p); p = nullptr; bytes = 0;
+    if (cudaMalloc(&p, n) != cudaSuccess) { gvm_set_error("weights_grid: cudaMalloc(%zu) failed", n); return 1; }
+    bytes = n;
+    return 0;
+  }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+int sort_pairs(DevBuf& tmp, uint32_t* k_in, uint32_t* k_out, uint32_t* v_in, uint32_t* v_out, long n,
+               int end_bit) {
+  size_t bytes = 0;
+  WG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit));
+  if (tmp.ensure(bytes)) return 1;
+  WG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit));
+  return 0;
+}
+
+// UVTaper::getValue (include/classes/uvtaper.cuh:100-118), host libm, folded coordinates
+void apply_taper_host(const gvm_taper* t, int scheme, long Z, const double* uvw_m, float freq, float* w) {
+  const float cb = cosf(t->bpa), sb = sinf(t->bpa), s2 = sinf(2.0f * t->bpa);
+  const float a = (cb * cb) / (2.0f * t->sigma_maj * t->sigma_maj) + (sb * sb) / (2.0f * t->sigma_min * t->sigma_min);
+  const float b = s2 / (2.0f * t->sigma_maj * t->sigma_maj) - s2 / (2.0f * t->sigma_min * t->sigma_min);
+  const float c = (sb * sb) / (2.0f * t->sigma_maj * t->sigma_maj) + (cb * cb) / (2.0f * t->sigma_min * t->sigma_min);
+  for (long z = 0; z < Z; z++) {
+    double u = gvm_metres_to_lambda(uvw_m[3 * z], freq), v = gvm_metres_to_lambda(uvw_m[3 * z + 1], freq);
+    if (scheme != GVM_W_RADIAL && u < 0.0) { u *= -1.0; v *= -1.0; }
+    const double x = u - t->u_0, y = v - t->v_0;
+    w[z] *= (float)(t->amplitude * exp(-a * x * x - b * x * y - c * y * y));
+  }
+}
+
+}  // namespace
+
 extern "C" {
-int gvm_weights(int, int, float, int64_t, int64_t, double, double, int, const int64_t*,
-                const double* const*, const float*, float* const*, const gvm_taper*) {
-  gvm_set_error("gvm_weights: not built yet");
-  return 1;
+
+int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, double deltau, double deltav,
+                int nblocks, const int64_t* Z, const double* const* uvw_m, const float* freqs,
+                float* const* w, const gvm_taper* taper) {
+  if (scheme < GVM_W_NATURAL || scheme > GVM_W_RADIAL) { gvm_set_error("gvm_weights: unknown scheme %d", scheme); return 1; }
+  if (scheme == GVM_W_BRIGGS && (robust < -2.0f || robust > 2.0f)) {
+    gvm_set_error("gvm_weights: Briggs robust must be in [-2, 2] (src/briggsweightingscheme.cu:13-21)");
+    return 1;
+  }
+  if (M * N >= (int64_t)kNoCell) { gvm_set_error("gvm_weights: grid too large"); return 1; }
+  const bool use_taper = taper && taper->enabled;
+  if (scheme != GVM_W_NATURAL) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+      gvm_set_error("gvm_weights: no CUDA device %d (no CPU fallback)", device);
+      return 1;
+    }
+    WG_CUDA(cudaSetDevice(device));
+  }
+  if (scheme == GVM_W_NATURAL || scheme == GVM_W_RADIAL) {
+    DevBuf d_uvw, d_w;
+    for (int b = 0; b < nblocks; b++) {
+      const long z = (long)Z[b];
+      if (scheme == GVM_W_RADIAL && z > 0) {
+        if (d_uvw.ensure((size_t)z * 24) || d_w.ensure((size_t)z * 4)) return 1;
+        WG_CUDA(cudaMemcpy(d_uvw.p, uvw_m[b], (size_t)z * 24, cudaMemcpyHostToDevice));
+        WG_CUDA(cudaMemcpy(d_w.p, w[b], (size_t)z * 4, cudaMemcpyHostToDevice));
+        k_radial<<<(int)((z + 255) / 256), 256>>>(d_uvw.as<double>(), z, freqs[b], d_w.as<float>());
+        WG_CUDA(cudaGetLastError());
+        WG_CUDA(cudaMemcpy(w[b], d_w.p, (size_t)z * 4, cudaMemcpyDeviceToHost));
+      }
+      if (use_taper) apply_taper_host(taper, scheme, z, uvw_m[b], freqs[b], w[b]);
+    }
+    return 0;
+  }
+
+  const size_t MN = (size_t)(M * N);
+  const double adu = fabs(deltau), adv = fabs(deltav);
+  int end_bit = 1;
+  while (end_bit < 32 && (1ull << end_bit) <= MN) end_bit++;
+  end_bit = 32;  // the off-grid sentinel is all ones: sort on all 32 bits
+  DevBuf d_grid, d_uvw, d_w, d_k0, d_k1, d_v0, d_v1, d_tmp;
+  if (d_grid.ensure(MN * 4)) return 1;
+  WG_CUDA(cudaMemset(d_grid.p, 0, MN * 4));
+  long zmax = 1;
+  for (int b = 0; b < nblocks; b++) zmax = Z[b] > zmax ? (long)Z[b] : zmax;
+  if (zmax >= (long)0x7FFFFFFF) { gvm_set_error("gvm_weights: block too large"); return 1; }
+  if (d_uvw.ensure((size_t)zmax * 24) || d_w.ensure((size_t)zmax * 4) || d_k0.ensure((size_t)zmax * 4) ||
+      d_k1.ensure((size_t)zmax * 4) || d_v0.ensure((size_t)zmax * 4) || d_v1.ensure((size_t)zmax * 4))
+    return 1;
+
+  auto load_and_sort = [&](int b) -> int {
+    const long z = (long)Z[b];
+    WG_CUDA(cudaMemcpy(d_uvw.p, uvw_m[b], (size_t)z * 24, cudaMemcpyHostToDevice));
+    WG_CUDA(cudaMemcpy(d_w.p, w[b], (size_t)z * 4, cudaMemcpyHostToDevice));
+    k_weight_cells<<<(int)((z + 255) / 256), 256>>>(d_uvw.as<double>(), z, freqs[b], adu, adv, M, N,
+                                                    d_k0.as<uint32_t>(), d_v0.as<uint32_t>());
+    WG_CUDA(cudaGetLastError());
+    return sort_pairs(d_tmp, d_k0.as<uint32_t>(), d_k1.as<uint32_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(), z,
+                      end_bit);
+  };
+
+  float f_squared = 0.0f;
+  if (scheme == GVM_W_BRIGGS) {
+    float sum_w = 0.0f, sum_g2 = 0.0f;
+    for (int b = 0; b < nblocks; b++) {
+      float acc = 0.0f;
+      for (long z = 0; z < (long)Z[b]; z++) acc += w[b][z];   // std::accumulate(..., 0.0f)
+      sum_w += acc;
+    }
+    std::vector<float> hgrid(MN);
+    for (int b = 0; b < nblocks; b++) {
+      const long z = (long)Z[b];
+      if (z > 0) {
+        if (load_and_sort(b)) return 1;
+        k_cell_accumulate<<<(int)((z + 255) / 256), 256>>>(d_k1.as<uint32_t>(), d_v1.as<uint32_t>(), z,
+                                                           d_w.as<float>(), d_grid.as<float>());
+        WG_CUDA(cudaGetLastError());
+      }
+      // the first-pass grid is never cleared between blocks and the half-plane sum of squares is
+      // taken after each one (src/briggsweightingscheme.cu:59-106)
+      WG_CUDA(cudaMemcpy(hgrid.data(), d_grid.p, MN * 4, cudaMemcpyDeviceToHost));
+      for (long m = 0; m < M; m++)
+        for (long n = N / 2; n < N; n++) sum_g2 += hgrid[N * m + n] * hgrid[N * m + n];
+    }
+    const float avg = sum_g2 / sum_w;
+    f_squared = (5.0f * powf(10.0f, -robust)) * (5.0f * powf(10.0f, -robust)) / avg;
+    WG_CUDA(cudaMemset(d_grid.p, 0, MN * 4));
+  }
+  for (int b = 0; b < nblocks; b++) {
+    const long z = (long)Z[b];
+    if (z > 0) {
+      if (load_and_sort(b)) return 1;
+      const int blocks = (int)((z + 255) / 256);
+      k_cell_accumulate<<<blocks, 256>>>(d_k1.as<uint32_t>(), d_v1.as<uint32_t>(), z, d_w.as<float>(),
+                                         d_grid.as<float>());
+      k_weight_apply<<<blocks, 256>>>(d_k1.as<uint32_t>(), d_v1.as<uint32_t>(), z, d_grid.as<float>(),
+                                      scheme == GVM_W_BRIGGS, f_squared, d_w.as<float>());
+      k_clear_cells<<<blocks, 256>>>(d_k1.as<uint32_t>(), z, d_grid.as<float>());
+      WG_CUDA(cudaGetLastError());
+      WG_CUDA(cudaMemcpy(w[b], d_w.p, (size_t)z * 4, cudaMemcpyDeviceToHost));
+    }
+    if (use_taper) apply_taper_host(taper, scheme, z, uvw_m[b], freqs[b], w[b]);
+  }
+  return 0;
 }
-int gvm_grid_block(int, int64_t, int64_t, double, double, float, int64_t, const double*,
-                   const float*, const float*, const float*, int, int, int, int, double*, float*,
-                   float*, int64_t*) {
-  gvm_set_error("gvm_grid_block: not built yet");
-  return 1;
+
+int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double deltav, float freq, int64_t Z,
+                   const double* uvw_m, const float* Vo, const float* w, const float* ckernel, int ck_m,
+                   int ck_n, int support_x, int support_y, double* uvw_out, float* Vo_out, float* w_out,
+                   int64_t* nout) {
+  if (!nout || Z < 0 || ck_m < 1 || ck_n < 1 || support_x < 0 || support_y < 0) {
+    gvm_set_error("gvm_grid_block: bad argument");
+    return 1;
+  }
+  if ((2 * support_x + 1) * (2 * support_y + 1) > kMaxTaps) {
+    gvm_set_error("gvm_grid_block: kernel support %d x %d exceeds %d taps", support_x, support_y, kMaxTaps);
+    return 1;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    gvm_set_error("gvm_grid_block: no CUDA device %d (no CPU fallback)", device);
+    return 1;
+  }
+  WG_CUDA(cudaSetDevice(device));
+  const size_t MN = (size_t)(M * N);
+  const long n2 = 2 * (long)Z;
+  const size_t ext = (size_t)(M + 2 * support_y) * (size_t)(N + 2 * support_x);
+  if (ext >= (size_t)kNoCell || n2 >= (long)0x7FFFFFFF) { gvm_set_error("gvm_grid_block: problem too large"); return 1; }
+  *nout = 0;
+  DevBuf d_uvw, d_Vo, d_w, d_ck, d_k0, d_k1, d_v0, d_v1, d_tmp, d_gw, d_gV, d_flags, d_pos, d_uo, d_Vout, d_wo;
+  const size_t zz = (size_t)(Z > 0 ? Z : 1);
+  if (d_uvw.ensure(zz * 24) || d_Vo.ensure(zz * 8) || d_w.ensure(zz * 4) || d_ck.ensure((size_t)ck_m * ck_n * 4) ||
+      d_k0.ensure(2 * zz * 4) || d_k1.ensure(2 * zz * 4) || d_v0.ensure(2 * zz * 4) || d_v1.ensure(2 * zz * 4) ||
+      d_gw.ensure(MN * 4) || d_gV.ensure(MN * 8) || d_flags.ensure(MN * 4) || d_pos.ensure(MN * 4))
+    return 1;
+  if (Z > 0) {
+    WG_CUDA(cudaMemcpy(d_uvw.p, uvw_m, zz * 24, cudaMemcpyHostToDevice));
+    WG_CUDA(cudaMemcpy(d_Vo.p, Vo, zz * 8, cudaMemcpyHostToDevice));
+    WG_CUDA(cudaMemcpy(d_w.p, w, zz * 4, cudaMemcpyHostToDevice));
+  }
+  WG_CUDA(cudaMemcpy(d_ck.p, ckernel, (size_t)ck_m * ck_n * 4, cudaMemcpyHostToDevice));
+  if (n2 > 0) {
+    k_grid_centres<<<(int)((n2 + 255) / 256), 256>>>(d_uvw.as<double>(), (long)Z, freq, deltau, deltav, M, N,
+                                                     support_x, support_y, d_k0.as<uint32_t>(),
+                                                     d_v0.as<uint32_t>());
+    WG_CUDA(cudaGetLastError());
+    if (sort_pairs(d_tmp, d_k0.as<uint32_t>(), d_k1.as<uint32_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(), n2, 32))
+      return 1;
+  }
+  k_grid_accumulate<<<(int)((MN + 127) / 128), 128>>>(d_k1.as<uint32_t>(), d_v1.as<uint32_t>(), n2, (long)Z,
+                                                      d_Vo.as<float2>(), d_w.as<float>(), d_ck.as<float>(), ck_m,
+                                                      ck_n, support_x, support_y, M, N, d_gw.as<float>(),
+                                                      d_gV.as<float2>());
+  WG_CUDA(cudaGetLastError());
+  k_grid_flags<<<(int)((MN + 255) / 256), 256>>>(d_gw.as<float>(), (long)MN, d_flags.as<int>());
+  size_t bytes = 0;
+  WG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, d_flags.as<int>(), d_pos.as<int>(), (int)MN));
+  if (d_tmp.ensure(bytes)) return 1;
+  WG_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, bytes, d_flags.as<int>(), d_pos.as<int>(), (int)MN));
+  int last_pos = 0, last_flag = 0;
+  WG_CUDA(cudaMemcpy(&last_pos, d_pos.as<int>() + (MN - 1), 4, cudaMemcpyDeviceToHost));
+  WG_CUDA(cudaMemcpy(&last_flag, d_flags.as<int>() + (MN - 1), 4, cudaMemcpyDeviceToHost));
+  const long count = (long)last_pos + last_flag;
+  if (count > 0) {
+    if (d_uo.ensure((size_t)count * 24) || d_Vout.ensure((size_t)count * 8) || d_wo.ensure((size_t)count * 4)) return 1;
+    k_grid_compact<<<(int)((MN + 255) / 256), 256>>>(d_gw.as<float>(), d_gV.as<float2>(), d_pos.as<int>(), M, N,
+                                                     deltau, deltav, gvm_freq_to_wavelength(freq),
+                                                     d_uo.as<double>(), d_Vout.as<float2>(), d_wo.as<float>());
+    WG_CUDA(cudaGetLastError());
+    WG_CUDA(cudaMemcpy(uvw_out, d_uo.p, (size_t)count * 24, cudaMemcpyDeviceToHost));
+    WG_CUDA(cudaMemcpy(Vo_out, d_Vout.p, (size_t)count * 8, cudaMemcpyDeviceToHost));
+    WG_CUDA(cudaMemcpy(w_out, d_wo.p, (size_t)count * 4, cudaMemcpyDeviceToHost));
+  }
+  *nout = count;
+  return 0;
 }
-}
+
+}  // extern "C"

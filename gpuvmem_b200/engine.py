@@ -328,3 +328,47 @@ class Engine:
         I[0] = self.meta["minpix"]
         I[1] = self.meta["alpha0"]
         return I
+
+
+# -- weights and gridding (stateless entry points of the C-ABI) ------------------------------
+def weights(scheme, robust, M, N, deltau, deltav, uvw_list, freqs, w_list, device=0, taper=None):
+    """WeightingScheme::apply for one dataset (reference src/*weightingscheme.cu). ``uvw_list[b]``:
+    [Z_b][3] float64 metres; ``w_list[b]``: float32 weights, returned as NEW arrays."""
+    lib = _lib.load_library()
+    nb = len(w_list)
+    uvw = [np.ascontiguousarray(u, dtype=np.float64) for u in uvw_list]
+    w = [np.array(x, dtype=np.float32, copy=True) for x in w_list]
+    Z = (C.c_int64 * nb)(*[len(x) for x in w])
+    up = (C.c_void_p * nb)(*[u.ctypes.data for u in uvw])
+    wp = (C.c_void_p * nb)(*[x.ctypes.data for x in w])
+    fr = np.ascontiguousarray(freqs, dtype=np.float32)
+    tp = None
+    if taper is not None:
+        tp = C.byref(_lib.gvm_taper(1, *taper))
+    rc = lib.gvm_weights(device, WEIGHTING.get(scheme, scheme), robust, M, N, deltau, deltav, nb,
+                         C.cast(Z, C.c_void_p), C.cast(up, C.c_void_p), fr.ctypes.data,
+                         C.cast(wp, C.c_void_p), tp)
+    if rc != 0:
+        raise EngineError(lib.gvm_last_error().decode())
+    return w
+
+
+def grid_block(M, N, deltau, deltav, freq, uvw_m, Vo, w, table, support, device=0):
+    """do_gridding for one (field, channel, stokes) block (reference src/functions.cu:1339-1653).
+    Returns (uvw_out [n][3] metres, Vo_out [n][2], w_out [n]) in the reference's row-major order."""
+    lib = _lib.load_library()
+    uvw_m = np.ascontiguousarray(uvw_m, dtype=np.float64)
+    Vo = np.ascontiguousarray(Vo, dtype=np.float32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    table = np.ascontiguousarray(table, dtype=np.float32)
+    uo = np.empty((M * N, 3), np.float64)
+    vo = np.empty((M * N, 2), np.float32)
+    wo = np.empty(M * N, np.float32)
+    n = C.c_int64()
+    rc = lib.gvm_grid_block(device, M, N, deltau, deltav, freq, len(w), uvw_m.ctypes.data, Vo.ctypes.data,
+                            w.ctypes.data, table.ctypes.data, table.shape[0], table.shape[1],
+                            support[0], support[1], uo.ctypes.data, vo.ctypes.data, wo.ctypes.data, C.byref(n))
+    if rc != 0:
+        raise EngineError(lib.gvm_last_error().decode())
+    k = n.value
+    return uo[:k].copy(), vo[:k].copy(), wo[:k].copy()

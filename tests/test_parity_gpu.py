@@ -292,3 +292,64 @@ def test_umma_multitile_vs_simt_and_oracle(oracle, wterm):
     print(f"\n[umma] wterm={wterm} rel-L2 vs SIMT={err:.3e} vs fp64 oracle={err64:.3e}")
     assert err64 <= 4e-5, err64
     e.close()
+
+
+# ---------------------------------------------------------------- weights and gridding (bit-exact)
+@pytest.fixture(scope="module")
+def wprob():
+    # 2 channels (Briggs' never-cleared first-pass grid), samples off the grid (weight -> 0)
+    return synth.make_problem(N=128, nvis=6000, nchan=2, freq0=1.0e11, bandwidth=8e9, seed=7, grid_fill=1.15)
+
+
+def _deltas(p):
+    return 1.0 / (p.M * RPDEG_D * p.DELTAX), 1.0 / (p.N * RPDEG_D * p.DELTAY)
+
+
+@pytest.mark.parametrize("scheme,robust,taper", [("Natural", 0.0, None), ("Uniform", 0.0, None), ("Briggs", 0.0, None),
+                                                 ("Briggs", -2.0, None), ("Briggs", 2.0, None), ("Radial", 0.0, None),
+                                                 ("Uniform", 0.0, (4.0e4, 2.0e4, 0.3, 1.0, 0.0, 0.0)),
+                                                 ("Natural", 0.0, (4.0e4, 2.0e4, 0.3, 1.0, 0.0, 0.0))])
+def test_weights_bit_exact_on_gpu(oracle, wprob, scheme, robust, taper):
+    from gpuvmem_b200.engine import WEIGHTING, weights
+    p = wprob
+    du, dv = _deltas(p)
+    want = oracle.weights(WEIGHTING[scheme], robust, p.M, p.N, du, dv, p.uvw, p.freqs, p.w,
+                          taper=None if taper is None else taper[:4])
+    got = weights(scheme, robust, p.M, p.N, du, dv, p.uvw, p.freqs, p.w, taper=taper)
+    for c in range(p.nchan):
+        assert np.array_equal(got[c].view(np.uint32), want[c].view(np.uint32)), (scheme, c)
+    if scheme in ("Uniform", "Briggs"):
+        assert any((g == 0).any() for g in got), "off-grid edge case not exercised"
+
+
+@pytest.mark.parametrize("name,m,n", [("PillBox2D", 1, 1), ("Gaussian2D", 7, 7), ("GaussianSinc2D", 7, 7),
+                                      ("PSWF", 9, 9)])
+def test_gridding_bit_exact_on_gpu(oracle, wprob, name, m, n):
+    from gpuvmem_b200.engine import grid_block
+    p = wprob
+    du, dv = _deltas(p)
+    table = oracle.ckernel(name, m, n, np.float32(abs(du)), np.float32(abs(dv)))
+    support = (m // 2, m // 2)   # support_y is computed from m too (include/classes/ckernel.cuh:508-511)
+    for c in range(p.nchan):
+        u, v, w = oracle.gridding(p.M, p.N, du, dv, float(p.freqs[c]), p.uvw[c], p.Vo[c], p.w[c], table, support)
+        gu, gv, gw = grid_block(p.M, p.N, du, dv, float(p.freqs[c]), p.uvw[c], p.Vo[c], p.w[c], table, support)
+        assert len(gw) == len(w) > 0
+        assert np.array_equal(gu.view(np.uint64), u.view(np.uint64))
+        assert np.array_equal(gv.view(np.uint32), v.view(np.uint32))
+        assert np.array_equal(gw.view(np.uint32), w.view(np.uint32))
+
+
+def test_gridding_empty_and_single(oracle):
+    from gpuvmem_b200.engine import grid_block
+    N = 64
+    du = dv = 100.0
+    table = np.ones((1, 1), np.float32)
+    u, v, w = grid_block(N, N, -du, dv, 1e11, np.zeros((0, 3)), np.zeros((0, 2), np.float32), np.zeros(0, np.float32),
+                         table, (0, 0))
+    assert len(w) == 0
+    lam = float(np.float32(2.99792458e8) / np.float32(1e11))
+    uvw = np.array([[3.2 * du * lam, -5.1 * dv * lam, 0.0]])
+    u, v, w = grid_block(N, N, -du, dv, 1e11, uvw, np.array([[1.0, 2.0]], np.float32), np.array([2.0], np.float32),
+                         table, (0, 0))
+    assert len(w) == 2, "a sample and its Hermitian twin"
+    assert np.allclose(v[:, 0], 1.0) and sorted(v[:, 1].tolist()) == [-2.0, 2.0] and np.allclose(w, 2.0)
