@@ -1,0 +1,116 @@
+// dist_nccl.cu — multi-GPU plumbing of the engine: one process per GPU, one NCCL
+// communicator over NVLink/NVSwitch, sum all-reduces issued on the engine stream.
+//
+// What is reduced: the chi2 scalar of every objective
+// evaluation (fp64, 1 element) and the image-sized gradient [2][M][N] fp32 of every
+// gradient evaluation. The reference instead accumulates per-GPU gradients into GPU 0
+// through peer-to-peer loads under an OpenMP critical section
+// (src/functions.cu:4534-4549) and sums chi2 on the host (:4437-4446).
+//
+// NCCL is bound at run time with dlopen("libnccl.so.2") so that a process that already
+// carries a NCCL (torch's bundled one) shares it, and single-GPU users need no NCCL.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+
+#include "gvm_internal.cuh"
+
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+  if (g_nccl.handle) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { gvm_set_error("gvm_dist: cannot load libnccl.so.2 (%s)", dlerror()); return 1; }
+#define GVM_SYM(field, name)                                                        \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                                        \
+  if (!g_nccl.field) { gvm_set_error("gvm_dist: libnccl lacks %s", name); return 1; }
+  GVM_SYM(GetUniqueId, "ncclGetUniqueId")
+  GVM_SYM(CommInitRank, "ncclCommInitRank")
+  GVM_SYM(AllReduce, "ncclAllReduce")
+  GVM_SYM(CommDestroy, "ncclCommDestroy")
+  GVM_SYM(GetErrorString, "ncclGetErrorString")
+  GVM_SYM(GetVersion, "ncclGetVersion")
+#undef GVM_SYM
+  g_nccl.handle = h;
+  return 0;
+}
+
+#define GVM_NCCL(call)                                                              \
+  do {                                                                              \
+    ncclResult_t _r = (call);                                                       \
+    if (_r != ncclSuccess) {                                                        \
+      gvm_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(_r)); \
+      return 1;                                                                     \
+    }                                                                               \
+  } while (0)
+}  // namespace
+
+int gvm_dist_allreduce_f32(gvm_engine* e, float* buf, size_t n) {
+  if (e->world <= 1) return 0;
+  GVM_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat, ncclSum, (ncclComm_t)e->nccl_comm, e->stream));
+  e->collectives++;
+  return 0;
+}
+int gvm_dist_allreduce_f64(gvm_engine* e, double* buf, size_t n) {
+  if (e->world <= 1) return 0;
+  GVM_NCCL(g_nccl.AllReduce(buf, buf, n, ncclDouble, ncclSum, (ncclComm_t)e->nccl_comm, e->stream));
+  e->collectives++;
+  return 0;
+}
+void gvm_dist_release(gvm_engine* e) {
+  if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)e->nccl_comm);
+  e->nccl_comm = nullptr;
+  e->world = 1;
+  e->rank = 0;
+}
+
+extern "C" {
+
+int gvm_dist_unique_id(char* id_out, size_t bytes) {
+  if (!id_out || bytes < sizeof(ncclUniqueId)) { gvm_set_error("gvm_dist_unique_id: need %zu bytes", sizeof(ncclUniqueId)); return 1; }
+  if (load_nccl()) return 1;
+  ncclUniqueId id;
+  GVM_NCCL(g_nccl.GetUniqueId(&id));
+  std::memcpy(id_out, &id, sizeof(id));
+  return 0;
+}
+
+int gvm_dist_init(gvm_engine* e, int rank, int world, const char* id, size_t bytes) {
+  if (!e || world < 1 || rank < 0 || rank >= world) { gvm_set_error("gvm_dist_init: bad rank/world %d/%d", rank, world); return 1; }
+  if (world == 1) { e->rank = 0; e->world = 1; return 0; }
+  if (!id || bytes < sizeof(ncclUniqueId)) { gvm_set_error("gvm_dist_init: need the %zu-byte id of gvm_dist_unique_id", sizeof(ncclUniqueId)); return 1; }
+  if (load_nccl()) return 1;
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  ncclComm_t comm = nullptr;
+  GVM_NCCL(g_nccl.CommInitRank(&comm, world, uid, rank));
+  e->nccl_comm = comm;
+  e->rank = rank;
+  e->world = world;
+  return 0;
+}
+
+int gvm_dist_rank(gvm_engine* e) { return e->rank; }
+int gvm_dist_world(gvm_engine* e) { return e->world; }
+int64_t gvm_dist_collectives(gvm_engine* e) { return e->collectives; }
+
+/* In-place sum all-reduce of n floats on the engine stream (optimizer-level use). */
+int gvm_dist_allreduce(gvm_engine* e, float* buf_dev, int64_t n) {
+  return gvm_dist_allreduce_f32(e, buf_dev, (size_t)n);
+}
+
+}  // extern "C"

@@ -121,6 +121,8 @@ int gvm_destroy(gvm_engine* e) {
   cudaFree(e->red_partials); cudaFree(e->red_counter); cudaFree(e->red_sum); cudaFree(e->red_Z);
   cudaFree(e->red_max); cudaFree(e->red_out); cudaFreeHost(e->h_red); cudaFree(e->tile_counter);
   cudaFree(e->row_ext); cudaFree(e->tile_list); cudaFree(e->band_tab);
+  gvm_dist_release(e);
+  cudaFree(e->dist_grad);
   for (auto ev : e->ev) cudaEventDestroy(ev);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -141,10 +143,11 @@ int gvm_synchronize(gvm_engine* e) {
 }
 
 int gvm_set_scalars(gvm_engine* e, float fg_scale, float noise_cut, float threshold) {
+  // the gradient's tile plan depends on the mask (noise < noise_cut) only
+  if (e->cfg.noise_cut != noise_cut) e->plan_dirty = true;
   e->cfg.fg_scale = fg_scale;
   e->cfg.noise_cut = noise_cut;
   e->cfg.threshold = threshold;
-  e->plan_dirty = true;
   return 0;
 }
 int gvm_set_grad_mode(gvm_engine* e, int m) { e->cfg.grad_mode = m; return 0; }
@@ -216,6 +219,14 @@ int gvm_add_channel(gvm_engine* e, const gvm_channel_desc* desc, int64_t Z, cons
   return 0;
 }
 
+int gvm_clear_channels(gvm_engine* e) {
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  for (auto& c : e->chans) free_channel(c);
+  e->chans.clear();
+  return 0;
+}
+
 int gvm_num_channels(gvm_engine* e) { return (int)e->chans.size(); }
 int64_t gvm_channel_nvis(gvm_engine* e, int chan) {
   if (chan < 0 || chan >= (int)e->chans.size()) return -1;
@@ -259,7 +270,10 @@ int gvm_chi2_async(gvm_engine* e, float* I_dev, int normalize, double* chi2_dev)
     if (gvm_forward_channel(e, c, I_dev, first, e->flag_opt, (int)s)) return 1;
     first = false;
   }
-  return gvm_reduce_finish(e, (int)e->chans.size(), normalize, chi2_dev ? chi2_dev : e->red_out);
+  double* out = chi2_dev ? chi2_dev : e->red_out;
+  if (gvm_reduce_finish(e, (int)e->chans.size(), normalize, out)) return 1;
+  // multi-GPU: chi2 is a plain sum over the visibility shards
+  return gvm_dist_allreduce_f64(e, out, 1);
 }
 
 int gvm_chi2(gvm_engine* e, float* I_dev, int normalize, float* chi2_out) {
@@ -279,11 +293,25 @@ static int pick_grad_mode(gvm_engine* e, GvmChannel& c) {
   return gvm_grad_umma_supported(e, c) ? GVM_GRAD_UMMA : GVM_GRAD_SIMT;
 }
 
+static __global__ void k_add_inplace(float* __restrict__ dst, const float* __restrict__ src, long n) {
+  const long idx = blockIdx.x * 256L + threadIdx.x;
+  if (idx < n) dst[idx] += src[idx];
+}
+
 int gvm_dchi2(gvm_engine* e, const float* I_dev, int flag_opt, int normalize,
               float* result_dchi2_dev) {
   GVM_CUDA(cudaSetDevice(e->cfg.device));
   e->flag_opt = flag_opt;
   e->ev_used = 0;
+  float* const caller_result = result_dchi2_dev;
+  const size_t MN2 = 2 * (size_t)e->cfg.M * e->cfg.N;
+  if (e->world > 1) {
+    // this rank's shard accumulates into a private buffer; ONE all-reduce of the image-sized
+    // gradient replaces the reference's serialised peer-to-peer accumulate (src/functions.cu:4534-4549)
+    if (!e->dist_grad) GVM_CUDA(cudaMalloc(&e->dist_grad, MN2 * sizeof(float)));
+    GVM_CUDA(cudaMemsetAsync(e->dist_grad, 0, MN2 * sizeof(float), e->stream));
+    result_dchi2_dev = e->dist_grad;
+  }
   for (size_t s = 0; s < e->chans.size(); s++) {
     GvmChannel& c = e->chans[s];
     if (c.Z <= 0) continue;
@@ -297,6 +325,12 @@ int gvm_dchi2(gvm_engine* e, const float* I_dev, int flag_opt, int normalize,
       if (gvm_grad_simt(e, c, mode == GVM_GRAD_SIMT_EXACT, &ksplit)) return 1;
       if (gvm_grad_finish(e, c, I_dev, ksplit, flag_opt, normalize, result_dchi2_dev)) return 1;
     }
+  }
+  if (e->world > 1) {
+    if (gvm_dist_allreduce_f32(e, e->dist_grad, MN2)) return 1;
+    k_add_inplace<<<(int)((MN2 + 255) / 256), 256, 0, e->stream>>>(caller_result, e->dist_grad, (long)MN2);
+    GVM_LAUNCH(e);
+    GVM_CUDA(cudaGetLastError());
   }
   return 0;
 }
@@ -314,6 +348,35 @@ int gvm_eval_host(gvm_engine* e, const float* I_host, int flag_opt, int normaliz
   GVM_CUDA(cudaMemcpyAsync(e->h_red, e->red_out, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   GVM_CUDA(cudaStreamSynchronize(e->stream));
   if (chi2_out) *chi2_out = (float)e->h_red[0];
+  return 0;
+}
+
+// ------------------------------------------------------------ device memory
+int gvm_dev_alloc(gvm_engine* e, size_t bytes, void** out) {
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  void* p = nullptr;
+  GVM_CUDA(cudaMalloc(&p, bytes ? bytes : 4));
+  GVM_CUDA(cudaMemsetAsync(p, 0, bytes ? bytes : 4, e->stream));
+  *out = p;
+  return 0;
+}
+int gvm_dev_free(gvm_engine* e, void* p) {
+  if (!p) return 0;
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  GVM_CUDA(cudaFree(p));
+  return 0;
+}
+int gvm_dev_memset(gvm_engine* e, void* p, int value, size_t bytes) {
+  GVM_CUDA(cudaMemsetAsync(p, value, bytes, e->stream));
+  return 0;
+}
+int gvm_dev_copy(gvm_engine* e, void* dst, const void* src, size_t bytes, int kind) {
+  const cudaMemcpyKind k = kind == GVM_COPY_H2D ? cudaMemcpyHostToDevice
+                           : kind == GVM_COPY_D2H ? cudaMemcpyDeviceToHost
+                                                  : cudaMemcpyDeviceToDevice;
+  GVM_CUDA(cudaMemcpyAsync(dst, src, bytes, k, e->stream));
+  if (kind != GVM_COPY_D2D) GVM_CUDA(cudaStreamSynchronize(e->stream));
   return 0;
 }
 

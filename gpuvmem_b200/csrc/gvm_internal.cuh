@@ -96,6 +96,11 @@ struct gvm_engine {
   int4* band_tab = nullptr;        // [nbands] (jmin, first tile, tiles, tile width) (device)
   int plan_ntiles = 0, plan_nbands = 0, plan_imin = 0;
   long plan_pixels = 0;            // output pixels the plan computes (algorithmic flops = 4 * this * Z)
+  // multi-GPU (dist_nccl.cu): one process per GPU, NCCL communicator over NVLink
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+  float* dist_grad = nullptr;      // [2][MN] this rank's gradient contribution before the all-reduce
+  int64_t collectives = 0;
 };
 
 #define GVM_LAUNCH(e) ((e)->launches++)
@@ -209,5 +214,9 @@ int gvm_grad_finish(gvm_engine* e, GvmChannel& c, const float* I_dev, int ksplit
 int gvm_ensure_grad_scratch(gvm_engine* e, size_t floats);
 int gvm_build_pixtab(gvm_engine* e, const GvmChannel& c);
 double gvm_wterm_cross_bound(const gvm_engine* e, const GvmChannel& c);
+// dist_nccl.cu: in-place sum all-reduce on the engine stream (no-op when world == 1)
+int gvm_dist_allreduce_f32(gvm_engine* e, float* buf, size_t n);
+int gvm_dist_allreduce_f64(gvm_engine* e, double* buf, size_t n);
+void gvm_dist_release(gvm_engine* e);
 void gvm_ev_begin(gvm_engine* e);
 void gvm_ev_end(gvm_engine* e);

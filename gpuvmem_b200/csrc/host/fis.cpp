@@ -1,0 +1,179 @@
+// fis.cpp — Fi adapters over the C ABI (see fi.hpp).
+#include <cstdio>
+#include <cstdlib>
+
+#include "fi.hpp"
+
+namespace gpuvmem {
+
+Fi::~Fi() {
+  if (G().engine) {
+    devFree(device_S);
+    devFree(device_DS);
+  }
+}
+
+void Fi::configure(int penalizatorIndex, int imageIndex_, int imageToAdd_, bool normalize_) {
+  Globals& g = G();
+  imageIndex = imageIndex_;
+  imageToAdd = imageToAdd_;
+  normalize = normalize_;
+  if (imageIndex > g.image_count - 1 || imageToAdd > g.image_count - 1) {
+    std::printf("There is no image for the provided index %s\n", name.c_str());
+    std::exit(-1);
+  }
+  if (penalizatorIndex != -1) {
+    if (penalizatorIndex < 0) {
+      std::printf("invalid index for penalizator (%s)\n", name.c_str());
+      std::exit(-1);
+    } else if (penalizatorIndex > g.nPenalizators - 1) {
+      penalization_factor = 0.0f;
+    } else {
+      penalization_factor = g.penalizators[penalizatorIndex];
+    }
+  }
+  if (!device_DS) device_DS = devAllocFloats((size_t)g.M * g.N);
+}
+
+void Fi::restartDGi() {
+  if (device_DS) devZero(device_DS, (size_t)G().M * G().N);
+}
+void Fi::addToDphi(float* device_dphi) {
+  GVM_CHECK(gvm_add_to_dphi(G().engine, device_dphi, device_DS, imageToAdd));  // linkAddToDPhi
+}
+void Fi::setS(float* S) { devFree(device_S); device_S = S; }
+void Fi::setDS(float* DS) { devFree(device_DS); device_DS = DS; }
+
+float Fi::priorValue(int kind, float* p, const gvm_prior_params& pp) {
+  float v = 0.0f;
+  if (iteration > 0 && penalization_factor)
+    GVM_CHECK(gvm_prior_value(G().engine, kind, p, imageIndex, &pp, &v));
+  set_fivalue(v);
+  return penalization_factor * v;
+}
+void Fi::priorGrad(int kind, float* p, const gvm_prior_params& pp) {
+  if (iteration > 0 && penalization_factor && G().flag_opt % 2 == imageIndex)
+    GVM_CHECK(gvm_prior_grad(G().engine, kind, p, imageIndex, &pp, penalization_factor, device_DS));
+}
+
+// ------------------------------------------------------------------ Chi2 --
+Chi2::~Chi2() {
+  if (G().engine) devFree(result_dchi2);
+}
+void Chi2::configure(int penalizatorIndex, int imageIndex_, int, bool normalize_) {
+  Globals& g = G();
+  imageIndex = imageIndex_;
+  normalize = normalize_;
+  if (penalizatorIndex != -1) {
+    if (penalizatorIndex > g.nPenalizators - 1 || penalizatorIndex < 0) {
+      std::printf("invalid index for penalizator (%s)\n", name.c_str());
+      std::exit(-1);
+    }
+    penalization_factor = g.penalizators[penalizatorIndex];
+  }
+  if (!result_dchi2) result_dchi2 = devAllocFloats((size_t)g.M * g.N * g.image_count);
+}
+float Chi2::calcFi(float* p) {
+  Globals& g = G();
+  float v = 0.0f;
+  GVM_CHECK(gvm_set_scalars(g.engine, fg_scale, g.noise_cut, g.threshold));
+  GVM_CHECK(gvm_set_flag_opt(g.engine, g.flag_opt));
+  GVM_CHECK(gvm_chi2(g.engine, p, normalize ? 1 : 0, &v));
+  set_fivalue(v);
+  return penalization_factor * v;
+}
+void Chi2::calcGi(float* p, float*) {
+  Globals& g = G();
+  GVM_CHECK(gvm_dchi2(g.engine, p, g.flag_opt, normalize ? 1 : 0, result_dchi2));
+}
+void Chi2::restartDGi() { devZero(result_dchi2, (size_t)G().M * G().N * G().image_count); }
+// src/chi2.cu:60-70: with two images the chi2 gradient REPLACES dphi (priors are added after it)
+void Chi2::addToDphi(float* device_dphi) {
+  Globals& g = G();
+  if (g.image_count == 1) GVM_CHECK(gvm_add_to_dphi(g.engine, device_dphi, result_dchi2, 0));
+  if (g.image_count > 1) devCopyD2D(device_dphi, result_dchi2, (size_t)g.M * g.N * g.image_count);
+}
+void Chi2::setCKernel(CKernel* ck) {
+  ckernel = ck;
+  GVM_CHECK(gvm_set_gcf(G().engine, ck && ck->getGCF() ? ck->getGCFCPUPointer() : nullptr));
+}
+
+// ---------------------------------------------------------------- priors --
+namespace {
+gvm_prior_params params(float prior_value, float eta, float eps_a, float eps_b, const float* prior_image) {
+  gvm_prior_params pp;
+  pp.prior_value = prior_value; pp.eta = eta; pp.epsilon = eps_a; pp.epsilon_b = eps_b;
+  pp.prior_image_dev = prior_image;
+  return pp;
+}
+}  // namespace
+
+float Entropy::calcFi(float* p) { return priorValue(GVM_PRIOR_ENTROPY, p, params(prior_value, eta, 0, 0, nullptr)); }
+void Entropy::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_ENTROPY, p, params(prior_value, eta, 0, 0, nullptr)); }
+
+float L1norm::calcFi(float* p) { return priorValue(GVM_PRIOR_L1, p, params(0, 0, epsilon, 0, nullptr)); }
+void L1norm::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_L1, p, params(0, 0, epsilon, 0, nullptr)); }
+
+float TVariation::calcFi(float* p) { return priorValue(GVM_PRIOR_TV, p, params(0, 0, epsilon, 0, nullptr)); }
+void TVariation::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_TV, p, params(0, 0, epsilon, 0, nullptr)); }
+void TVariation::addToDphi(float* device_dphi) { GVM_CHECK(gvm_add_to_dphi(G().engine, device_dphi, device_DS, 0)); }
+
+float TSqVariation::calcFi(float* p) { return priorValue(GVM_PRIOR_TSV, p, params(0, 0, 0, 0, nullptr)); }
+void TSqVariation::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_TSV, p, params(0, 0, 0, 0, nullptr)); }
+
+float Laplacian::calcFi(float* p) { return priorValue(GVM_PRIOR_LAPLACIAN, p, params(0, 0, 0, 0, nullptr)); }
+void Laplacian::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_LAPLACIAN, p, params(0, 0, 0, 0, nullptr)); }
+
+float QuadraticP::calcFi(float* p) { return priorValue(GVM_PRIOR_QUADRATIC, p, params(0, 0, 0, 0, nullptr)); }
+void QuadraticP::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_QUADRATIC, p, params(0, 0, 0, 0, nullptr)); }
+
+namespace {
+float* uploadImage(const std::vector<float>& host) {
+  float* d = devAllocFloats(host.size());
+  devUpload(d, host.data(), host.size());
+  return d;
+}
+void scaleImage(float* img, float factor) {  // normalizeImage, src/functions.cu:4626
+  GVM_CHECK(gvm_vec_scale(G().engine, img, 1.0f / factor, (int64_t)G().M * G().N));
+}
+}  // namespace
+
+GEntropy::GEntropy(const std::vector<float>& prior_host) : prior(uploadImage(prior_host)) { name = "GEntropy"; }
+GEntropy::~GEntropy() { if (G().engine) devFree(prior); }
+void GEntropy::setPrior(float* p) { devFree(prior); prior = p; }
+void GEntropy::normalizePrior() { scaleImage(prior, normalization_factor); }
+float GEntropy::calcFi(float* p) { return priorValue(GVM_PRIOR_GENTROPY, p, params(0, eta, 0, 0, prior)); }
+void GEntropy::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_GENTROPY, p, params(0, eta, 0, 0, prior)); }
+
+GL1Norm::GL1Norm(const std::vector<float>& prior_host) : prior(uploadImage(prior_host)) { name = "G L1-Norm"; }
+GL1Norm::~GL1Norm() { if (G().engine) devFree(prior); }
+void GL1Norm::setPrior(float* p) { devFree(prior); prior = p; }
+void GL1Norm::normalizePrior() { scaleImage(prior, normalization_factor); }
+float GL1Norm::calcFi(float* p) { return priorValue(GVM_PRIOR_GL1, p, params(0, 0, epsilon_a, epsilon_b, prior)); }
+void GL1Norm::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_GL1, p, params(0, 0, epsilon_a, epsilon_b, prior)); }
+
+namespace {
+Fi* makeChi2() { return new Chi2; }
+Fi* makeEntropy() { return new Entropy; }
+Fi* makeL1() { return new L1norm; }
+Fi* makeTV() { return new TVariation; }
+Fi* makeTSV() { return new TSqVariation; }
+Fi* makeLaplacian() { return new Laplacian; }
+Fi* makeQuadratic() { return new QuadraticP; }
+Fi* makeGEntropy() { return new GEntropy; }
+Fi* makeGL1() { return new GL1Norm; }
+const bool kRegistered[] = {
+    registerCreationFunction<Fi, std::string>("Chi2", makeChi2),
+    registerCreationFunction<Fi, std::string>("Entropy", makeEntropy),
+    registerCreationFunction<Fi, int>(0, makeEntropy),  // src/entropy.cu:78-79
+    registerCreationFunction<Fi, std::string>("L1-Norm", makeL1),
+    registerCreationFunction<Fi, std::string>("TotalVariation", makeTV),
+    registerCreationFunction<Fi, std::string>("TotalSquaredVariation", makeTSV),
+    registerCreationFunction<Fi, std::string>("Laplacian", makeLaplacian),
+    registerCreationFunction<Fi, std::string>("Quadratic", makeQuadratic),
+    registerCreationFunction<Fi, std::string>("GEntropy", makeGEntropy),
+    registerCreationFunction<Fi, std::string>("GL1Norm", makeGL1),
+};
+}  // namespace
+
+}  // namespace gpuvmem

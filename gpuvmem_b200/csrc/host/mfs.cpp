@@ -1,0 +1,696 @@
+// mfs.cpp — MFS synthesizer: the host flow of src/mfs.cu (configure :79-528, setDevice
+// :530-943, clearRun :945-976, run :978-1074, writeImages :1076-1113, writeResiduals
+// :1115-1155, unSetDevice :1157-1248) driving the B200 engine through the C ABI.
+// One process per GPU; multi-GPU jobs run one MFS per rank over a NCCL communicator.
+#include <getopt.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <sstream>
+
+#include "synthesizer.hpp"
+
+namespace gpuvmem {
+
+namespace {
+const double RPDEG_D = 3.14159265358979323846 / 180.0;  // include/functions.cuh:18
+const double RPARCSEC = RPDEG_D / 3600.0;
+const double PI_D = 3.14159265358979323846;
+
+double wallSeconds() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+bool usedCorrelation(int c) { return c == LL || c == RR || c == XX || c == YY; }  // src/functions.cu:4378-4381
+
+// src/directioncosines.cu:40-59
+void direccos(double ra, double dec, double ra0, double dec0, double* l, double* m) {
+  const double dra = ra - ra0;
+  *l = std::cos(dec) * std::sin(dra);
+  *m = std::sin(dec) * std::cos(dec0) - std::cos(dec) * std::sin(dec0) * std::cos(dra);
+}
+
+struct FlagSpec { char key; const char* name; bool takes_value; const char* help; };
+const FlagSpec kFlags[] = {
+    {'i', "input", true, "Name of the input visibility file/s (separated by a comma)"},
+    {'o', "output", true, "Name of the output visibility file/s (separated by a comma)"},
+    {'O', "output_image", true, "Name of the output image"},
+    {'m', "model_input", true, "File including a complete header for astrometry"},
+    {'n', "noise", true, "Noise factor parameter"},
+    {'e', "eta", true, "Variable that controls the minimum image value in the entropy prior"},
+    {'N', "noise_cut", true, "Noise-cut Parameter"},
+    {'F', "ref_frequency", true, "Reference frequency in Hz (if alpha is not zero)"},
+    {'T', "threshold", true, "Threshold to calculate the spectral index image above a number of sigmas in I_nu_0"},
+    {'p', "path", true, "Path to save images. With last trail / included"},
+    {'G', "gpus", true, "Index of the GPU/s you are going to use separated by a comma"},
+    {'r', "random_sampling", true, "Percentage of data used when random sampling"},
+    {'R', "robust_parameter", true, "Robust weighting parameter when gridding (-2 uniform, 2 natural)"},
+    {'f', "output_file", true, "Output file where final objective function values are saved"},
+    {'X', "blockSizeX", true, "GPU block X Size for image/Fourier plane (accepted, unused by this engine)"},
+    {'Y', "blockSizeY", true, "GPU block Y Size for image/Fourier plane (accepted, unused by this engine)"},
+    {'V', "blockSizeV", true, "GPU block V Size for visibilities (accepted, unused by this engine)"},
+    {'t', "iterations", true, "Number of iterations for optimization"},
+    {'g', "gridding", true, "Use gridded visibilities (any value > 0; gridding runs on the GPU)"},
+    {'z', "initial_values", true, "Initial values for image/s"},
+    {'Z', "regularization_factors", true, "Regularization factors for each regularization (separated by a comma)"},
+    {'U', "user-mask", true, "Use a user created mask instead of using the noise mask"},
+    {'K', "grad-mode", true, "Gradient kernel: 0 auto, 1 tensor-core, 2 CUDA-core separable, 3 CUDA-core exact (engine extension)"},
+    {'v', "verbose", false, "Shows information through all the execution"},
+    {'x', "nopositivity", false, "Runs with no positivity restrictions on the images"},
+    {'a', "apply-noise", false, "Applies random gaussian noise to visibilities (not supported)"},
+    {'P', "print-images", false, "Prints images per iteration"},
+    {'E', "print-errors", false, "Prints final error maps (not supported)"},
+    {'s', "save_modelcolumn", false, "Saves the model visibilities"},
+    {'M', "use-radius-mask", false, "Use a mask based on a radius instead of the noise estimation (not supported)"},
+    {'W', "modify-weights", false, "Modify the WEIGHT column with the computed weights"},
+    {'h', "help", false, "Shows this help"},
+    {'w', "warranty", false, "Shows warranty details"},
+    {'c', "copyright", false, "Shows copyright conditions"},
+};
+}  // namespace
+
+void print_help() {
+  std::printf("gpuvmem_b200 options:\n");
+  for (const FlagSpec& f : kFlags)
+    std::printf("  -%c, --%-24s %s\n", f.key, f.name, f.help);
+}
+
+bool getOptions(int argc, char** argv, Vars* v) {
+  Globals& g = G();
+  std::string shortopts;
+  std::vector<option> longopts;
+  for (const FlagSpec& f : kFlags) {
+    shortopts += f.key;
+    if (f.takes_value) shortopts += ':';
+    longopts.push_back({f.name, f.takes_value ? required_argument : no_argument, nullptr, f.key});
+  }
+  longopts.push_back({nullptr, 0, nullptr, 0});
+  bool help = false;
+  optind = 1;
+  opterr = 0;
+  int c;
+  while ((c = getopt_long(argc, argv, shortopts.c_str(), longopts.data(), nullptr)) != -1) {
+    switch (c) {
+      case 'i': v->input = optarg; break;
+      case 'o': v->output = optarg; break;
+      case 'O': v->output_image = optarg; break;
+      case 'm': v->modin = optarg; break;
+      case 'n': v->noise = std::stof(optarg); break;
+      case 'e': v->eta = std::stof(optarg); break;
+      case 'N': v->noise_cut = std::stof(optarg); break;
+      case 'F': v->nu_0 = std::stof(optarg); break;
+      case 'T': v->threshold = std::stof(optarg); break;
+      case 'p': v->path = optarg; break;
+      case 'G': v->gpus = optarg; break;
+      case 'r': v->randoms = std::stof(optarg); break;
+      case 'R': v->robust_param = std::stof(optarg); break;
+      case 'f': v->ofile = optarg; break;
+      case 'X': v->blockSizeX = std::stoi(optarg); break;
+      case 'Y': v->blockSizeY = std::stoi(optarg); break;
+      case 'V': v->blockSizeV = std::stoi(optarg); break;
+      case 't': v->it_max = std::stoi(optarg); break;
+      case 'g': v->gridding = std::stoi(optarg); break;
+      case 'z': v->initial_values = optarg; break;
+      case 'Z': v->penalization_factors = optarg; break;
+      case 'U': v->user_mask = optarg; break;
+      case 'K': v->grad_mode = std::stoi(optarg); break;
+      case 'v': g.verbose_flag = 1; break;
+      case 'x': g.nopositivity = true; break;
+      case 'a': g.apply_noise = true; break;
+      case 'P': g.print_images = true; break;
+      case 'E': g.print_errors = true; break;
+      case 's': g.save_model_input = true; break;
+      case 'M': g.radius_mask = true; break;
+      case 'W': g.modify_weights = true; break;
+      case 'h': case 'w': case 'c': help = true; break;
+      default: help = true; break;  // unknown flag: the reference prints the help and exits
+    }
+  }
+  if (help) { print_help(); return false; }
+  if (v->randoms > 1.0 || v->randoms < 0.0 || v->gridding < 0) { print_help(); return false; }
+  if (v->user_mask != "NULL") v->noise_cut = 1.0f;  // src/functions.cu:296-298
+  return true;
+}
+
+std::vector<std::string> MFS::countAndSeparateStrings(std::string long_str, std::string sep) {
+  std::vector<std::string> out;
+  size_t start = 0;
+  while (start <= long_str.size()) {
+    const size_t hit = long_str.find_first_of(sep, start);
+    const size_t end = hit == std::string::npos ? long_str.size() : hit;
+    out.push_back(long_str.substr(start, end - start));
+    if (hit == std::string::npos) break;
+    start = hit + 1;
+  }
+  return out;
+}
+
+MFS::~MFS() {}
+
+void MFS::adoptDatasets(std::vector<MSDataset>&& ds, const headerValues& h) {
+  datasets = std::move(ds);
+  header = h;
+  adopted = true;
+}
+
+void MFS::setDistributed(int rank, int world, const std::string& id) {
+  G().rank = rank;
+  G().world = world;
+  G().quiet = rank != 0;
+  nccl_id = id;
+}
+
+void MFS::configure(int argc, char** argv) {
+  Globals& g = G();
+  t_start = wallSeconds();
+  if (!ioImageHandler) ioImageHandler = createObject<Io, std::string>("IoFITS");
+  if (!ioVisibilitiesHandler) ioVisibilitiesHandler = createObject<Io, std::string>("IoMS");
+  if (!getOptions(argc, argv, &variables)) std::exit(EXIT_SUCCESS);
+
+  msinput = variables.input;
+  msoutput = variables.output;
+  modinput = variables.modin;
+  out_image = variables.output_image;
+  ioImageHandler->setInput(modinput);
+  ioImageHandler->setOutput(out_image);
+  ioImageHandler->setPath(variables.path);
+  optimizer->setTotalIterations(variables.it_max);
+  setVisNoise(variables.noise);
+  g.noise_cut = variables.noise_cut;
+  g.random_probability = variables.randoms;
+  g.eta = variables.eta;
+  setGriddingThreads(variables.gridding);
+  g.nu_0 = variables.nu_0;
+  g.robust_param = variables.robust_param;
+  g.threshold = variables.threshold * 5.0;
+  ioImageHandler->setPrintImages(g.print_images);
+  if (g.apply_noise || g.print_errors || g.radius_mask || variables.user_mask != "NULL" || variables.randoms < 1.0f) {
+    std::printf("ERROR: -a, -E, -M, -U and -r < 1 are outside this engine's scope (DESIGN.md §7)\n");
+    std::exit(-1);
+  }
+
+  if (!adopted) {
+    if (msinput == "NULL") {
+      std::printf("Datasets files were not provided\n");
+      print_help();
+      std::exit(-1);
+    }
+    if (msoutput == "NULL") {
+      std::printf("Output/s was/were not provided\n");
+      print_help();
+      std::exit(-1);
+    }
+    const std::vector<std::string> ins = countAndSeparateStrings(msinput, ",");
+    const std::vector<std::string> outs = countAndSeparateStrings(msoutput, ",");
+    if (ins.size() != outs.size()) {
+      std::printf("Number of input datasets should be equal to the number of output datasets\n");
+      std::exit(-1);
+    }
+    datasets.assign(ins.size(), MSDataset());
+    for (size_t i = 0; i < ins.size(); i++) {
+      datasets[i].name = ins[i];
+      datasets[i].oname = outs[i];
+    }
+  }
+  g.nMeasurementSets = (int)datasets.size();
+  if (g.verbose_flag && !g.quiet) std::printf("Number of input datasets %d\n", g.nMeasurementSets);
+
+  if (variables.initial_values == "NULL") {
+    std::printf("Initial values for image/s were not provided\n");
+    print_help();
+    std::exit(-1);
+  }
+  const std::vector<std::string> init = countAndSeparateStrings(variables.initial_values, ",");
+  g.image_count = (int)init.size();
+  g.initial_values.clear();
+  for (int i = 0; i < g.image_count; i++)
+    g.initial_values.push_back(i == 0 ? std::stof(init[i]) * -1.0f * g.eta : std::stof(init[i]));
+  g.imagesChanged = 0;
+  if (g.image_count == 1) {  // src/mfs.cu:176-180: a second (alpha) image is always carried
+    g.initial_values.push_back(0.0f);
+    g.image_count++;
+    g.imagesChanged = 1;
+  }
+
+  if (!adopted) header = ioImageHandler->readHeader(modinput);
+  g.M = header.M;
+  g.N = header.N;
+  g.DELTAX = header.DELTAX;
+  g.DELTAY = header.DELTAY;
+  g.ra = header.ra;
+  g.dec = header.dec;
+  g.crpix1 = header.crpix1;
+  g.crpix2 = header.crpix2;
+  ioImageHandler->setMN(g.M, g.N);
+  ioImageHandler->setRADec(g.ra, g.dec);
+  ioImageHandler->setFrame(header.radesys);
+  ioImageHandler->setEquinox(header.equinox);
+  if (header.beam_noise > 0.0f) setVisNoise(header.beam_noise);
+  if (ckernel) ckernel->setIoImageHandler(ioImageHandler);
+
+  if (!adopted)
+    for (MSDataset& ds : datasets)
+      ioVisibilitiesHandler->read(ds.name, ds.antennas, ds.fields, &ds.data);
+
+  float max_freq = 0, min_freq = 0, max_blength = 0;
+  double max_uvmax = 0;
+  for (size_t d = 0; d < datasets.size(); d++) {
+    const MSData& md = datasets[d].data;
+    if (d == 0) { max_freq = md.max_freq; min_freq = md.min_freq; }
+    max_freq = std::max(max_freq, md.max_freq);
+    min_freq = std::min(min_freq, md.min_freq);
+    max_blength = std::max(max_blength, md.max_blength);
+    max_uvmax = std::max(max_uvmax, md.uvmax_wavelength);
+    if (!g.quiet)
+      std::printf("Dataset %zu: %s - Antenna diameter: %.3f metres\n", d, datasets[d].name.c_str(),
+                  datasets[d].antennas[0].antenna_diameter);
+  }
+  max_uvmax += 1E-5;
+  if (!g.quiet) {
+    const float resolution_arcsec = (freq_to_wavelength(max_freq) / max_blength) / RPARCSEC;
+    std::printf("The maximum u,v in wavelength units is: %e\n", max_uvmax);
+    std::printf("The maximum theoretical resolution of this/these dataset/s is ~%f arcsec\n", resolution_arcsec);
+  }
+  if (g.nu_0 < 0.0) {
+    if (!g.quiet)
+      std::printf("WARNING: Reference frequency not provided. It will be calculated as the middle of the frequency range.\n");
+    g.nu_0 = 0.5f * (max_freq + min_freq);
+  }
+  if (!g.quiet) {
+    std::printf("Reference frequency: %e Hz\n", g.nu_0);
+    const double deltau_theo = 2.0 * max_uvmax / (g.M - 1);
+    std::printf("The pixel size has to be less or equal to %lf arcsec\n", 1.0 / (g.M * deltau_theo) / RPARCSEC);
+    std::printf("Actual pixel size is %lf arcsec\n", std::fabs(g.DELTAX) * 3600.0);
+  }
+
+  // -G: with one process per GPU the list names the devices of the job; this rank drives entry
+  // `rank` of it (LOCAL_RANK order). The reference's single-process multi-GPU mode does not exist.
+  const std::vector<std::string> gpu_list = countAndSeparateStrings(variables.gpus, ",");
+  g.firstgpu = 0;
+  if (!gpu_list.empty() && !gpu_list[0].empty()) {
+    const size_t pick = (size_t)g.rank < gpu_list.size() ? (size_t)g.rank : 0;
+    g.firstgpu = std::stoi(gpu_list[pick]);
+    if (g.world == 1 && gpu_list.size() > 1 && !g.quiet)
+      std::printf("NOTE: %zu GPUs listed but this is a single process; launch one process per GPU "
+                  "(RANK/WORLD_SIZE/LOCAL_RANK) for multi-GPU. Using GPU %d.\n", gpu_list.size(), g.firstgpu);
+  }
+  g.num_gpus = g.world;
+  g.multigpu = g.world > 1 ? g.world : 0;
+  if (ckernel) ckernel->setGPUID(g.firstgpu);
+
+  g.penalizators.clear();
+  if (variables.penalization_factors != "NULL") {
+    for (const std::string& s : countAndSeparateStrings(variables.penalization_factors, ","))
+      g.penalizators.push_back(std::stof(s));
+  } else if (!g.quiet) {
+    std::printf("No regularization factors provided\n");
+  }
+  g.nPenalizators = (int)g.penalizators.size();
+
+  const double deltax = RPDEG_D * g.DELTAX, deltay = RPDEG_D * g.DELTAY;  // radians
+  g.deltau = 1.0 / (g.M * deltax);
+  g.deltav = 1.0 / (g.N * deltay);
+  der.deltau = g.deltau;
+  der.deltav = g.deltav;
+
+  if (!scheme) scheme = createObject<WeightingScheme, std::string>("Natural");
+  if (gridding) scheme->setThreads(griddingThreads);
+  scheme->configure(&g.robust_param);
+  scheme->setModifyWeights(g.modify_weights);
+  double t0 = wallSeconds();
+  scheme->apply(datasets);
+  der.weighting_seconds = wallSeconds() - t0;
+
+  if (gridding) {
+    if (!ckernel) ckernel = new PillBox2D();
+    if (!g.quiet) std::cout << "Doing gridding" << std::endl;
+    ckernel->setSigmas(std::fabs(g.deltau), std::fabs(g.deltav));
+    ckernel->buildKernel();
+    ckernel->initializeGCF(g.M, g.N, std::fabs(deltax), std::fabs(deltay));
+    if (!g.quiet)
+      std::printf("Using an antialiasing kernel %s of size (%d, %d) and support (%d, %d)\n",
+                  ckernel->getName().c_str(), ckernel->getm(), ckernel->getn(), ckernel->getSupportX(),
+                  ckernel->getSupportY());
+    t0 = wallSeconds();
+    doGridding();
+    der.gridding_seconds = wallSeconds() - t0;
+  }
+}
+
+// do_gridding (src/functions.cu:1339-1653) for every dataset/field/channel/stokes through
+// gvm_grid_block; the originals are kept for the residual write-back.
+void MFS::doGridding() {
+  Globals& g = G();
+  ungridded = datasets;
+  const size_t MN = (size_t)g.M * g.N;
+  std::vector<double> uvw_out(3 * MN);
+  std::vector<float> vo_out(2 * MN), w_out(MN);
+  for (MSDataset& ds : datasets) {
+    int max = 0;
+    for (Field& f : ds.fields)
+      for (size_t i = 0; i < f.visibilities.size(); i++) {
+        long per_freq = 0;
+        for (size_t s = 0; s < f.visibilities[i].size(); s++) {
+          HVis& v = f.visibilities[i][s];
+          int64_t nout = 0;
+          GVM_CHECK(gvm_grid_block(g.firstgpu, g.M, g.N, g.deltau, g.deltav, f.nu[i], (int64_t)v.size(),
+                                   v.uvw.data(), v.Vo.data(), v.weight.data(), ckernel->getKernelPointer(),
+                                   ckernel->getm(), ckernel->getn(), ckernel->getSupportX(),
+                                   ckernel->getSupportY(), uvw_out.data(), vo_out.data(), w_out.data(), &nout));
+          v.uvw.assign(uvw_out.begin(), uvw_out.begin() + 3 * nout);
+          v.Vo.assign(vo_out.begin(), vo_out.begin() + 2 * nout);
+          v.weight.assign(w_out.begin(), w_out.begin() + nout);
+          v.Vm.assign(2 * nout, 0.0f);
+          v.Vr.assign(2 * nout, 0.0f);
+          f.numVisibilitiesPerFreqPerStoke[i][s] = (long)nout;
+          per_freq += (long)nout;
+          max = std::max<long>(max, (long)nout);
+        }
+        f.numVisibilitiesPerFreq[i] = per_freq;
+      }
+    ds.data.max_number_visibilities_in_channel_and_stokes = max;
+  }
+}
+
+// Which part of every (dataset, field, channel, stokes) block lives on this rank, then the
+// uploads. Whole channels go to rank (i % world) as in the reference (src/mfs.cu:568,
+// src/functions.cu:4341) when there are at least `world` channels; otherwise every block is cut
+// into `world` contiguous visibility chunks (chi2 and its gradient are sums over visibilities).
+void MFS::shardAndUpload() {
+  Globals& g = G();
+  int max_nfreq = 1;
+  for (MSDataset& ds : datasets) max_nfreq = std::max(max_nfreq, ds.data.total_frequencies);
+  const bool by_channel = g.world > 1 && max_nfreq >= g.world;
+  for (MSDataset& ds : datasets)
+    for (Field& f : ds.fields) {
+      f.engine_slot.assign(f.visibilities.size(), std::vector<int>(ds.data.nstokes, -1));
+      for (size_t i = 0; i < f.visibilities.size(); i++)
+        for (int s = 0; s < ds.data.nstokes; s++) {
+          if (!usedCorrelation(ds.data.corr_type[s])) continue;
+          HVis& v = f.visibilities[i][s];
+          size_t lo = 0, hi = v.size();
+          if (g.world > 1) {
+            if (by_channel) {
+              if ((int)(i % g.world) != g.rank) continue;
+            } else {
+              lo = v.size() * (size_t)g.rank / g.world;
+              hi = v.size() * (size_t)(g.rank + 1) / g.world;
+            }
+          }
+          gvm_channel_desc cd;
+          cd.freq = f.nu[i];
+          cd.antenna_diameter = ds.antennas[0].antenna_diameter;
+          cd.pb_factor = ds.antennas[0].pb_factor;
+          cd.pb_cutoff = ds.antennas[0].pb_cutoff;
+          cd.primary_beam = ds.antennas[0].primary_beam;
+          cd.ref_xobs_pix = f.ref_xobs_pix; cd.ref_yobs_pix = f.ref_yobs_pix;
+          cd.phs_xobs_pix = f.phs_xobs_pix; cd.phs_yobs_pix = f.phs_yobs_pix;
+          int slot = -1;
+          GVM_CHECK(gvm_add_channel(g.engine, &cd, (int64_t)(hi - lo), v.uvw.data() + 3 * lo, v.Vo.data() + 2 * lo,
+                                    v.weight.data() + lo, &slot));
+          f.engine_slot[i][s] = slot;
+        }
+    }
+}
+
+void MFS::setDevice() {
+  Globals& g = G();
+  const double deltax = RPDEG_D * g.DELTAX, deltay = RPDEG_D * g.DELTAY;
+  g.deltau = 1.0 / (g.M * deltax);
+  g.deltav = 1.0 / (g.N * deltay);
+
+  // calculateNoiseAndBeam (src/functions.cu:1700-1813): weighted second moments of the uv
+  // coverage in fp64, sum of weights as a running fp32 sum per block (reduceCPU, :354-367)
+  double s_uu = 0.0, s_vv = 0.0, s_uv = 0.0;
+  sum_weights = 0.0f;
+  total_visibilities = 0;
+  for (MSDataset& ds : datasets)
+    for (Field& f : ds.fields)
+      for (size_t i = 0; i < f.visibilities.size(); i++)
+        for (int s = 0; s < ds.data.nstokes; s++) {
+          if (!usedCorrelation(ds.data.corr_type[s])) continue;
+          const HVis& v = f.visibilities[i][s];
+          const size_t Z = v.size();
+          if (Z == 0) continue;
+          double uu = 0.0, vv = 0.0, uv = 0.0;
+          for (size_t k = 0; k < Z; k++) {
+            const double ul = metres_to_lambda(v.uvw[3 * k], f.nu[i]);
+            const double vl = metres_to_lambda(v.uvw[3 * k + 1], f.nu[i]);
+            uu += ul * ul * v.weight[k];
+            vv += vl * vl * v.weight[k];
+            uv += ul * vl * v.weight[k];
+          }
+          s_uu += uu; s_vv += vv; s_uv += uv;
+          float block = v.weight[0];
+          for (size_t k = 1; k < Z; k++) block = block + v.weight[k];
+          sum_weights += block;
+          total_visibilities += (int)Z;
+        }
+  if (!(sum_weights > 0.0f)) {
+    std::printf("Error: The sum of the visibility weights cannot be zero\n");
+    std::exit(-1);
+  }
+  s_uu /= sum_weights; s_vv /= sum_weights; s_uv /= sum_weights;
+  const float variance = 1.0f / sum_weights;
+  {  // calc_beamSize (:1685-1698)
+    const double diff = s_uu - s_vv, sum = s_uu + s_vv;
+    const double root = std::sqrt(diff * diff + 4.0 * (s_uv * s_uv));
+    g.beam_bmaj = 1.0 / std::sqrt(2.0) / PI_D / std::sqrt(sum - root) / RPDEG_D;
+    g.beam_bmin = 1.0 / std::sqrt(2.0) / PI_D / std::sqrt(sum + root) / RPDEG_D;
+    g.beam_bpa = -0.5 * std::atan2(2.0 * s_uv, diff) / RPDEG_D;
+  }
+  if (vis_noise <= 0.0) vis_noise = 0.5f * sqrtf(variance);
+  der.beam_bmaj_deg = g.beam_bmaj; der.beam_bmin_deg = g.beam_bmin; der.beam_bpa_deg = g.beam_bpa;
+  der.sum_weights = sum_weights; der.vis_noise = vis_noise; der.total_visibilities = total_visibilities;
+
+  g.max_number_vis = 0;
+  for (MSDataset& ds : datasets)
+    g.max_number_vis = std::max(g.max_number_vis, ds.data.max_number_visibilities_in_channel_and_stokes);
+  if (g.max_number_vis == 0) {
+    std::printf("Max number of visibilities cannot be zero for image synthesis\n");
+    std::exit(-1);
+  }
+  if (!g.quiet)
+    std::printf("Estimated beam size: %e x %e (arcsec) / %lf (degrees)\n", g.beam_bmaj * 3600.0,
+                g.beam_bmin * 3600.0, g.beam_bpa);
+  g.beam_bmaj = g.beam_bmaj / std::fabs(g.DELTAX);  // to pixels
+  g.beam_bmin = g.beam_bmin / std::fabs(g.DELTAX);
+  g.noise_jypix = vis_noise / (PI_D * g.beam_bmaj * g.beam_bmin / (4.0 * logf(2.0)));
+  der.noise_jypix = g.noise_jypix;
+
+  // phase / pointing centres in pixels (src/mfs.cu:660-691; both are set from the PHASE centre)
+  const double raimage = g.ra * RPDEG_D, decimage = g.dec * RPDEG_D;
+  for (MSDataset& ds : datasets)
+    for (Field& f : ds.fields) {
+      double lphs, mphs;
+      direccos(f.phs_ra, f.phs_dec, raimage, decimage, &lphs, &mphs);
+      const double lpix = lphs / deltax, mpix = mphs / deltay;
+      f.ref_xobs_pix = f.phs_xobs_pix = lpix + (g.crpix1 - 1.0f);
+      f.ref_yobs_pix = f.phs_yobs_pix = mpix + (g.crpix2 - 1.0f);
+      der.xobs_pix = f.phs_xobs_pix; der.yobs_pix = f.phs_yobs_pix;
+      if (f.ref_xobs_pix < 0 || f.ref_xobs_pix >= g.M || f.ref_yobs_pix < 0 || f.ref_yobs_pix >= g.N) {
+        std::printf("Dataset: %s\nPointing reference center (%f,%f) is outside the range of the image\n",
+                    ds.name.c_str(), f.ref_xobs_pix, f.ref_yobs_pix);
+        std::exit(0);  // goToError()
+      }
+    }
+
+  // the engine: per-GPU scratch, cuFFT plan, visibility blocks (varsPerGPU + device_visibilities)
+  gvm_config cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.M = g.M; cfg.N = g.N; cfg.DELTAX = g.DELTAX; cfg.DELTAY = g.DELTAY;
+  cfg.nu_0 = g.nu_0; cfg.eta = g.eta; cfg.minpix = g.initial_values[0];
+  cfg.noise_cut = 1e30f; cfg.threshold = g.threshold; cfg.fg_scale = 1.0f;
+  cfg.device = g.firstgpu; cfg.grad_mode = variables.grad_mode;
+  cfg.keep_vm = 1;  // -o is mandatory in the reference: the model visibilities are always written back
+  if (gvm_create(&cfg, &g.engine) != 0) {
+    std::printf("ERROR: %s\n", gvm_last_error());
+    std::exit(-1);
+  }
+  if (g.world > 1) GVM_CHECK(gvm_dist_init(g.engine, g.rank, g.world, nccl_id.data(), nccl_id.size()));
+  shardAndUpload();
+
+  // starting image (src/mfs.cu:742-750) and the Image object with its update rules (:798-811)
+  const size_t MN = (size_t)g.M * g.N;
+  host_I.assign(MN * g.image_count, 0.0f);
+  for (int k = 0; k < g.image_count; k++) std::fill_n(host_I.begin() + MN * k, MN, g.initial_values[k]);
+  device_Image = devAllocFloats(MN * g.image_count);
+  devUpload(device_Image, host_I.data(), MN * g.image_count);
+  image = new Image(device_Image, g.image_count);
+  functionPtr = new imageMap[g.image_count];
+  for (int i = 0; i < g.image_count; i++) {
+    const bool positive = !g.nopositivity && i == 0;
+    functionPtr[i].evaluateXt = positive ? particularEvaluateXt : defaultEvaluateXt;
+    functionPtr[i].newP = positive ? particularNewP : defaultNewP;
+  }
+  image->setFunctionMapping(functionPtr);
+
+  // noise image -> fg_scale, noise_cut (src/mfs.cu:850-916)
+  if (gvm_num_channels(g.engine) == 0) {
+    std::printf("ERROR: rank %d holds no visibility block\n", g.rank);
+    std::exit(-1);
+  }
+  float noise_min = 0.0f;
+  GVM_CHECK(gvm_build_noise_image(g.engine, g.noise_jypix, &noise_min));
+  fg_scale = noise_min;
+  g.noise_cut = g.noise_cut * noise_min;
+  GVM_CHECK(gvm_set_scalars(g.engine, fg_scale, g.noise_cut, g.threshold));
+  if (gridding && ckernel) GVM_CHECK(gvm_set_gcf(g.engine, ckernel->getGCFCPUPointer()));
+  der.fg_scale = fg_scale; der.noise_cut = g.noise_cut; der.nu_0 = g.nu_0;
+  if (g.verbose_flag && !g.quiet) {
+    std::printf("fg_scale = %e\n", fg_scale);
+    std::printf("noise (Jy/pix) = %e\n", g.noise_jypix);
+  }
+  der.setup_seconds = wallSeconds() - t_start;
+}
+
+void MFS::clearRun() {
+  Globals& g = G();
+  devUpload(device_Image, host_I.data(), (size_t)g.M * g.N * g.image_count);
+}
+
+void MFS::run() {
+  Globals& g = G();
+  ObjectiveFunction* of = optimizer->getObjectiveFunction();
+  of->setIo(ioImageHandler);
+  Fi* chi2 = of->getFiByName("Chi2");
+  if (chi2 && chi2->getNormalize()) fg_scale = 1.0f;
+  if (chi2) chi2->setFgScale(fg_scale);
+  if (gridding && chi2) chi2->setCKernel(ckernel);
+
+  if (!g.quiet) std::printf("\n\nStarting optimizer\n");
+  const double t0 = wallSeconds();
+  if (!Order) {
+    if (g.imagesChanged) {
+      optimizer->setImage(image);
+      optimizer->optimize();
+    } else if (g.image_count == 2) {
+      optimizer->setImage(image);
+      for (int flag = 0; flag < 4; flag++) {
+        optimizer->setFlag(flag);
+        optimizer->optimize();
+      }
+    }
+  } else {
+    Order(optimizer, image);
+  }
+  GVM_CHECK(gvm_synchronize(g.engine));
+  der.run_seconds = wallSeconds() - t0;
+
+  const float chi2_final = chi2 ? chi2->get_fivalue() : 0.0f;
+  Fi* entropy = of->getFiByName("Entropy");
+  const float final_S = entropy ? entropy->get_fivalue() : 0.0f;
+  const float lambda_S = entropy ? entropy->getPenalizationFactor() : 0.0f;
+  auto report = [&](std::FILE* out) {
+    std::fprintf(out, "Iterations: %d\n", optimizer->getCurrentIteration());
+    std::fprintf(out, "chi2: %f\n", 2.0f * chi2_final);
+    std::fprintf(out, "0.5*chi2: %f\n", chi2_final);
+    std::fprintf(out, "Total visibilities: %d\n", total_visibilities);
+    std::fprintf(out, "Reduced-chi2 (Num visibilities): %f\n", chi2_final / total_visibilities);
+    std::fprintf(out, "Reduced-chi2 (Weights sum): %f\n", chi2_final / sum_weights);
+    std::fprintf(out, "S: %f\n", final_S);
+    std::fprintf(out, "Normalized S: %f\n", final_S / (g.M * g.N));
+    std::fprintf(out, "lambda*S: %f\n", lambda_S * final_S);
+    std::fprintf(out, "Wall time: %lf\n", der.run_seconds);
+  };
+  if (!g.quiet) {
+    std::printf("Minimization ended successfully\n\n");
+    report(stdout);
+    std::printf("Objective evaluations: %ld, gradient evaluations: %ld\n\n", of->functionEvaluations(),
+                of->gradientEvaluations());
+  }
+  if (variables.ofile != "NULL" && g.rank == 0) {
+    std::FILE* out = std::fopen(variables.ofile.c_str(), "w");
+    if (!out) {
+      std::printf("Error opening output file!\n");
+      std::exit(0);
+    }
+    report(out);
+    std::fclose(out);
+  }
+}
+
+void MFS::writeImages() {
+  Globals& g = G();
+  if (g.rank != 0) return;
+  std::printf("Saving final image to disk\n");
+  if (IoOrderEnd) {
+    IoOrderEnd(image->getImage(), ioImageHandler);
+    return;
+  }
+  ioImageHandler->printImage(image->getImage(), out_image, "JY/PIXEL", optimizer->getCurrentIteration(), 0,
+                             fg_scale, g.M, g.N, true);
+  if (g.print_images)
+    ioImageHandler->printNotNormalizedImage(image->getImage(), "alpha.fits", "", optimizer->getCurrentIteration(), 1, true);
+}
+
+// Residual / model write-back (src/mfs.cu:1115-1155): weights restored, and in gridded mode the
+// model is re-sampled at the ORIGINAL (u,v) with the bilinear degridder (what
+// getOriginalVisibilitiesBack + chi2 do, src/functions.cu:1844-2010).
+void MFS::writeResiduals() {
+  Globals& g = G();
+  if (!g.quiet) std::printf("Transferring residuals to host memory\n");
+  Fi* chi2 = optimizer->getObjectiveFunction()->getFiByName("Chi2");
+  if (gridding) {
+    datasets = ungridded;
+    scheme->restoreWeights(datasets);
+    GVM_CHECK(gvm_clear_channels(g.engine));
+    GVM_CHECK(gvm_set_gcf(g.engine, nullptr));
+    shardAndUpload();
+    if (chi2) {
+      const float res = chi2->calcFi(image->getImage());
+      if (!g.quiet) std::printf("Non-gridded chi2 after de-gridding using bilinear interpolation %f\n", res);
+    }
+  } else {
+    scheme->restoreWeights(datasets);
+  }
+  // modelToHost (src/MSFITSIO.cu:1114-1138): Vm, Vr of the blocks this rank holds
+  for (MSDataset& ds : datasets)
+    for (Field& f : ds.fields)
+      for (size_t i = 0; i < f.visibilities.size(); i++)
+        for (size_t s = 0; s < f.visibilities[i].size(); s++) {
+          const int slot = f.engine_slot.empty() ? -1 : f.engine_slot[i][s];
+          if (slot < 0) continue;
+          HVis& v = f.visibilities[i][s];
+          const size_t Z = (size_t)gvm_channel_nvis(g.engine, slot);
+          size_t lo = 0;
+          if (g.world > 1 && Z != v.size()) lo = v.size() * (size_t)g.rank / g.world;
+          v.Vm.assign(2 * v.size(), 0.0f);
+          v.Vr.assign(2 * v.size(), 0.0f);
+          GVM_CHECK(gvm_get_vis(g.engine, slot, nullptr, nullptr, nullptr, v.Vm.data() + 2 * lo, v.Vr.data() + 2 * lo, nullptr));
+        }
+  if (msoutput != "NULL") {
+    const std::vector<std::string> outs = countAndSeparateStrings(msoutput, ",");
+    for (size_t d = 0; d < datasets.size() && d < outs.size(); d++) {
+      const std::string file = g.world > 1 ? outs[d] + ".rank" + std::to_string(g.rank) : outs[d];
+      ioVisibilitiesHandler->writeModelVisibilities(file, datasets[d].fields, datasets[d].data);
+    }
+    if (!g.quiet) std::printf("Residuals and model visibilities saved.\n");
+  }
+}
+
+void MFS::unSetDevice() {
+  Globals& g = G();
+  if (!g.quiet) std::printf("Freeing device memory\n");
+  if (g.engine) {
+    devFree(device_Image);
+    device_Image = nullptr;
+    GVM_CHECK(gvm_destroy(g.engine));
+    g.engine = nullptr;
+  }
+  delete image;
+  image = nullptr;
+  delete[] functionPtr;
+  functionPtr = nullptr;
+}
+
+namespace {
+Synthesizer* makeMFS() { return new MFS; }
+const bool kRegistered = registerCreationFunction<Synthesizer, std::string>("MFS", makeMFS);
+}  // namespace
+
+}  // namespace gpuvmem

@@ -1,0 +1,74 @@
+#include "objectivefunction.hpp"
+
+namespace gpuvmem {
+
+ObjectiveFunction::~ObjectiveFunction() {
+  if (G().engine) devFree(dphi);
+}
+
+void ObjectiveFunction::addFi(Fi* fi) {
+  if (fi->getPenalizationFactor()) {
+    fis.push_back(fi);
+    fi_values.push_back(0.0f);
+  }
+}
+
+float ObjectiveFunction::calcFunction(float* p) {
+  float value = 0.0f;
+  size_t k = 0;
+  for (Fi* fi : fis) {
+    const float term = fi->calcFi(p);
+    fi_values[k++] = fi->get_fivalue();
+    value += term;
+  }
+  n_function++;
+  return value;
+}
+
+void ObjectiveFunction::calcGradient(float* p, float* xi, int iter) {
+  if (io && io->getPrintImages()) {
+    if (IoOrderIterations) {
+      IoOrderIterations(p, io);
+    } else {
+      io->printImageIteration(p, "I_nu_0", "JY/PIXEL", iter, 0, true);
+      io->printImageIteration(p, "alpha", "JY/PIXEL", iter, 1, true);
+    }
+  }
+  restartDPhi();
+  for (Fi* fi : fis) {
+    fi->setIteration(iter);
+    fi->calcGi(p, xi);
+    fi->addToDphi(dphi);
+  }
+  copyDphiToXi(xi);
+  n_gradient++;
+}
+
+void ObjectiveFunction::restartDPhi() {
+  for (Fi* fi : fis) fi->restartDGi();
+  devZero(dphi, (size_t)M * N * image_count);
+}
+
+void ObjectiveFunction::copyDphiToXi(float* xi) { devCopyD2D(xi, dphi, (size_t)M * N * image_count); }
+
+Fi* ObjectiveFunction::getFiByName(const std::string& fi_name) {
+  for (Fi* fi : fis)
+    if (fi->getName() == fi_name) return fi;
+  return nullptr;
+}
+
+void ObjectiveFunction::configure(long N_, long M_, int I) {
+  setN(N_);
+  setM(M_);
+  setImageCount(I);
+  if (dphi) devFree(dphi);
+  dphi = devAllocFloats((size_t)M * N * I);
+}
+
+namespace {
+ObjectiveFunction* makeObjectiveFunction() { return new ObjectiveFunction; }
+const bool kRegistered =
+    registerCreationFunction<ObjectiveFunction, std::string>("ObjectiveFunction", makeObjectiveFunction);
+}  // namespace
+
+}  // namespace gpuvmem

@@ -1,0 +1,48 @@
+// objectivefunction.hpp — Phi(I) = sum_i lambda_i f_i(I) and its gradient. Surface of the
+// reference's include/classes/objectivefunction.cuh:6-112 (factory key "ObjectiveFunction").
+#pragma once
+#include <string>
+#include <vector>
+
+#include "factory.hpp"
+#include "fi.hpp"
+#include "io.hpp"
+
+namespace gpuvmem {
+
+class ObjectiveFunction {
+ public:
+  ObjectiveFunction() = default;
+  ~ObjectiveFunction();
+  // terms with a zero factor are dropped (objectivefunction.cuh:9-14)
+  void addFi(Fi* fi);
+  float calcFunction(float* p);
+  // restartDPhi, then per term setIteration/calcGi/addToDphi, then dphi -> xi (:28-45)
+  void calcGradient(float* p, float* xi, int iter);
+  void restartDPhi();
+  void copyDphiToXi(float* xi);
+  std::vector<Fi*> getFi() { return fis; }
+  Fi* getFiByName(const std::string& fi_name);
+  void setN(long n) { N = n; }
+  void setM(long m) { M = m; }
+  void setImageCount(int I) { image_count = I; }
+  void setIo(Io* i) { io = i; }
+  void setIoOrderIterations(void (*func)(float* I, Io* io)) { IoOrderIterations = func; }
+  void configure(long N, long M, int I);
+  std::vector<float> get_fi_values() { return fi_values; }
+  // evaluation counters (bench / statistics block)
+  long functionEvaluations() const { return n_function; }
+  long gradientEvaluations() const { return n_gradient; }
+
+ private:
+  std::vector<Fi*> fis;
+  std::vector<float> fi_values;
+  Io* io = nullptr;
+  float* dphi = nullptr;
+  long N = 0, M = 0;
+  void (*IoOrderIterations)(float* I, Io* io) = nullptr;
+  int image_count = 1;
+  long n_function = 0, n_gradient = 0;
+};
+
+}  // namespace gpuvmem

@@ -1,0 +1,78 @@
+#include "weightingscheme.hpp"
+
+#include "globals.hpp"
+
+namespace gpuvmem {
+
+void WeightingScheme::restoreWeights(std::vector<MSDataset>& d) {
+  for (auto& ds : d)
+    for (auto& f : ds.fields)
+      for (size_t i = 0; i < f.visibilities.size(); i++)
+        for (size_t s = 0; s < f.visibilities[i].size(); s++)
+          if (i < f.backup_visibilities.size() && s < f.backup_visibilities[i].size())
+            f.visibilities[i][s].weight = f.backup_visibilities[i][s].weight;
+}
+
+void WeightingScheme::applyOnGpu(int scheme, float robust, std::vector<MSDataset>& d, const char* label) {
+  Globals& g = G();
+  if (!g.quiet) std::cout << "Running " << label << " weighting scheme on GPU " << g.firstgpu << std::endl;
+  std::vector<int64_t> Z;
+  std::vector<const double*> uvw;
+  std::vector<float> freqs;
+  std::vector<float*> w;
+  std::vector<std::vector<float>> before;
+  for (auto& ds : d)
+    for (auto& f : ds.fields) {
+      f.backup_visibilities.resize(f.visibilities.size());
+      for (size_t i = 0; i < f.visibilities.size(); i++) {
+        f.backup_visibilities[i].resize(f.visibilities[i].size());
+        for (size_t s = 0; s < f.visibilities[i].size(); s++) {
+          HVis& v = f.visibilities[i][s];
+          Z.push_back((int64_t)v.size());
+          uvw.push_back(v.uvw.data());
+          freqs.push_back(f.nu[i]);
+          w.push_back(v.weight.data());
+          before.push_back(v.weight);
+        }
+      }
+    }
+  gvm_taper taper;
+  if (uvtaper) taper = uvtaper->abi();
+  GVM_CHECK(gvm_weights(g.firstgpu, scheme, robust, g.M, g.N, g.deltau, g.deltav, (int)Z.size(), Z.data(),
+                        uvw.data(), freqs.data(), w.data(), uvtaper ? &taper : nullptr));
+  // backup_visibilities: the weights before the scheme, or the new ones with -W (modify_weights)
+  size_t b = 0;
+  for (auto& ds : d)
+    for (auto& f : ds.fields)
+      for (size_t i = 0; i < f.visibilities.size(); i++)
+        for (size_t s = 0; s < f.visibilities[i].size(); s++, b++)
+          f.backup_visibilities[i][s].weight = modify_weights ? f.visibilities[i][s].weight : before[b];
+}
+
+void BriggsWeightingScheme::setRobustParam(float r) {
+  if (r >= -2.0f && r <= 2.0f) {
+    robust_param = r;
+  } else {
+    std::cout << "Error. Robust parameter must have values between -2.0 and 2.0" << std::endl;
+    std::exit(-1);
+  }
+}
+void BriggsWeightingScheme::configure(void* params) {
+  setRobustParam(*static_cast<float*>(params));
+  if (!G().quiet) std::cout << "Using robust " << robust_param << " for Briggs weighting" << std::endl;
+}
+
+namespace {
+WeightingScheme* makeNatural() { return new NaturalWeightingScheme; }
+WeightingScheme* makeUniform() { return new UniformWeightingScheme; }
+WeightingScheme* makeBriggs() { return new BriggsWeightingScheme; }
+WeightingScheme* makeRadial() { return new RadialWeightingScheme; }
+const bool kRegistered[] = {
+    registerCreationFunction<WeightingScheme, std::string>("Natural", makeNatural),
+    registerCreationFunction<WeightingScheme, std::string>("Uniform", makeUniform),
+    registerCreationFunction<WeightingScheme, std::string>("Briggs", makeBriggs),
+    registerCreationFunction<WeightingScheme, std::string>("Radial", makeRadial),
+};
+}  // namespace
+
+}  // namespace gpuvmem

@@ -318,6 +318,28 @@ __global__ void __launch_bounds__(kT) k_axpby(float a, const float* __restrict__
   y[idx] = (b == 0.0f) ? a * x[idx] : a * x[idx] + b * y[idx];
 }
 
+__global__ void __launch_bounds__(kT) k_absmax(const float* __restrict__ v, long n, double* partials,
+                                               float* pmax, unsigned int* counter, double* out) {
+  float m = 0.f;
+  for (long idx = blockIdx.x * (long)kT + threadIdx.x; idx < n; idx += (long)gridDim.x * kT)
+    m = fmaxf(m, fabsf(v[idx]));
+  block_reduce_finish(0.f, 0.f, m, partials, pmax, counter, out);
+}
+__global__ void __launch_bounds__(kT) k_scale(float* v, float s, long n) {
+  const long idx = blockIdx.x * (long)kT + threadIdx.x;
+  if (idx < n) v[idx] *= s;
+}
+// r = y + s (in place on y's copy): y_out = a + b, s_out = c - d (calculateSandY, src/functions.cu:3636-3653)
+__global__ void __launch_bounds__(kT) k_lbfgs_sy(float* __restrict__ y_out, float* __restrict__ s_out,
+                                                 const float* __restrict__ xi, const float* __restrict__ xi_old,
+                                                 const float* __restrict__ p, const float* __restrict__ p_old,
+                                                 long n) {
+  const long idx = blockIdx.x * (long)kT + threadIdx.x;
+  if (idx >= n) return;
+  y_out[idx] = xi[idx] - (-1.0f * xi_old[idx]);
+  s_out[idx] = p[idx] - p_old[idx];
+}
+
 struct RedBuf {
   double* partials; float* pmax; unsigned int* counter; double* out;
 };
@@ -546,6 +568,33 @@ int gvm_vec_new_xi(gvm_engine* e, float* g, float* xi, float* h, float gam, int 
 }
 int gvm_vec_axpby(gvm_engine* e, float a, const float* x, float b, float* y, int64_t n) {
   k_axpby<<<(int)((n + kT - 1) / kT), kT, 0, e->stream>>>(a, x, b, y, n);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+/* normArray + deviceMaxReduce (src/lbfgs.cu:151-160): max |v| over n floats. */
+int gvm_vec_absmax(gvm_engine* e, const float* v, int64_t n, float* out) {
+  RedBuf r = aux_red(e);
+  k_absmax<<<red_grid(e, n), kT, 0, e->stream>>>(v, n, r.partials, r.pmax, r.counter, r.out);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  double v3[3];
+  if (fetch_red(e, v3)) return 1;
+  *out = (float)v3[2];
+  return 0;
+}
+/* searchDirection_LBFGS (src/functions.cu:3564): v *= s. */
+int gvm_vec_scale(gvm_engine* e, float* v, float s, int64_t n) {
+  k_scale<<<(int)((n + kT - 1) / kT), kT, 0, e->stream>>>(v, s, n);
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
+  return 0;
+}
+/* calculateSandY (src/functions.cu:3636): y = xi - (-xi_old), s = p - p_old over n floats. */
+int gvm_vec_lbfgs_sy(gvm_engine* e, float* y_out, float* s_out, const float* xi, const float* xi_old,
+                     const float* p, const float* p_old, int64_t n) {
+  k_lbfgs_sy<<<(int)((n + kT - 1) / kT), kT, 0, e->stream>>>(y_out, s_out, xi, xi_old, p, p_old, n);
   GVM_LAUNCH(e);
   GVM_CUDA(cudaGetLastError());
   return 0;

@@ -52,6 +52,7 @@ SIGNATURES = {
     "gvm_get_noise_image": (C.c_int, [_P, _P]),
     "gvm_set_gcf": (C.c_int, [_P, _P]),
     "gvm_add_channel": (C.c_int, [_P, C.POINTER(gvm_channel_desc), C.c_int64, _P, _P, _P, C.POINTER(C.c_int)]),
+    "gvm_clear_channels": (C.c_int, [_P]),
     "gvm_num_channels": (C.c_int, [_P]),
     "gvm_channel_nvis": (C.c_int64, [_P, C.c_int]),
     "gvm_get_vis": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P]),
@@ -69,6 +70,19 @@ SIGNATURES = {
     "gvm_vec_grad_condition": (C.c_int, [_P, _P, _P, C.c_float, C.c_int, C.POINTER(C.c_float)]),
     "gvm_vec_new_xi": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int]),
     "gvm_vec_axpby": (C.c_int, [_P, C.c_float, _P, C.c_float, _P, C.c_int64]),
+    "gvm_vec_absmax": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_float)]),
+    "gvm_vec_scale": (C.c_int, [_P, _P, C.c_float, C.c_int64]),
+    "gvm_vec_lbfgs_sy": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64]),
+    "gvm_dev_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "gvm_dev_free": (C.c_int, [_P, _P]),
+    "gvm_dev_memset": (C.c_int, [_P, _P, C.c_int, C.c_size_t]),
+    "gvm_dev_copy": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int]),
+    "gvm_dist_unique_id": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "gvm_dist_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
+    "gvm_dist_rank": (C.c_int, [_P]),
+    "gvm_dist_world": (C.c_int, [_P]),
+    "gvm_dist_allreduce": (C.c_int, [_P, _P, C.c_int64]),
+    "gvm_dist_collectives": (C.c_int64, [_P]),
     "gvm_weights": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_int64, C.c_int64, C.c_double, C.c_double,
                               C.c_int, _P, _P, _P, _P, C.POINTER(gvm_taper)]),
     "gvm_grid_block": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_float,

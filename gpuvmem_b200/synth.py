@@ -137,6 +137,28 @@ def make_problem(N=512, nvis=1 << 20, nchan=1, freq0=2.3e11, bandwidth=0.0, seed
     return p
 
 
+def write_gvms(p: Problem, path):
+    """Write the GVMS container the C++ host layer reads (``csrc/host/msdata.hpp``): the values
+    ``readMS`` + ``readFITSHeader`` would deliver, one field, one correlation (XX = 9)."""
+    import struct
+    with open(path, "wb") as f:
+        f.write(b"GVMS0001")
+        f.write(struct.pack("<qq", p.M, p.N))
+        f.write(struct.pack("<6d", p.DELTAX, p.DELTAY, p.ra, p.dec, p.crpix1, p.crpix2))
+        f.write(struct.pack("<ff", -1.0, p.antenna_diameter))
+        f.write(p.telescope.encode()[:31].ljust(32, b"\0"))
+        f.write(struct.pack("<iii", 1, p.nchan, 1))
+        f.write(struct.pack("<i", 9))
+        ra, dec = np.deg2rad(p.ra), np.deg2rad(p.dec)
+        f.write(struct.pack("<4d", ra, dec, ra, dec))
+        f.write(np.asarray(p.freqs, dtype="<f4").tobytes())
+        for c in range(p.nchan):
+            f.write(struct.pack("<q", len(p.w[c])))
+            f.write(np.ascontiguousarray(p.uvw[c], dtype="<f8").tobytes())
+            f.write(np.ascontiguousarray(p.Vo[c], dtype="<f4").tobytes())
+            f.write(np.ascontiguousarray(p.w[c], dtype="<f4").tobytes())
+
+
 # BASELINE.json configs (SURVEY.md §8d). Sizes can be scaled down for tests.
 def config_c1(scale=1.0, **kw):
     return make_problem(N=512, nvis=int((1 << 20) * scale), nchan=1, freq0=6.9147e11,

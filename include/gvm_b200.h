@@ -108,6 +108,9 @@ int gvm_set_gcf(gvm_engine* e, const float* gcf_host);
 int gvm_add_channel(gvm_engine* e, const gvm_channel_desc* desc, int64_t Z,
                     const double* uvw_m, const float* Vo, const float* w,
                     int* chan_out);
+/* Drop every uploaded block (MFS::writeResiduals re-uploads the ungridded samples after a
+ * gridded run, src/mfs.cu:1118-1139). */
+int gvm_clear_channels(gvm_engine* e);
 int gvm_num_channels(gvm_engine* e);
 int64_t gvm_channel_nvis(gvm_engine* e, int chan);
 /* Device-side state of a block after upload / a forward pass; any pointer may be
@@ -194,8 +197,43 @@ int gvm_vec_grad_condition(gvm_engine* e, const float* xi, const float* p, float
  * xi = h = g + gam*h. (gam = 0 and first = 1 give searchDirection.) */
 int gvm_vec_new_xi(gvm_engine* e, float* g, float* xi, float* h, float gam,
                    int image_count);
-/* y = a*x + b*y over n floats (L-BFGS pieces, :3564-3653). */
+/* y = a*x + b*y over n floats (L-BFGS pieces: updateQ :3613, getR :3625). */
 int gvm_vec_axpby(gvm_engine* e, float a, const float* x, float b, float* y, int64_t n);
+/* normArray + deviceMaxReduce (src/lbfgs.cu:151-160; kernel :3590): max |v|. */
+int gvm_vec_absmax(gvm_engine* e, const float* v, int64_t n, float* out);
+/* searchDirection_LBFGS (:3564): v *= s. */
+int gvm_vec_scale(gvm_engine* e, float* v, float s, int64_t n);
+/* calculateSandY (:3636): y_out = xi - (-1*xi_old), s_out = p - p_old over n floats. */
+int gvm_vec_lbfgs_sy(gvm_engine* e, float* y_out, float* s_out, const float* xi,
+                     const float* xi_old, const float* p, const float* p_old, int64_t n);
+
+/* ------------------------------------------------------- device memory -----
+ * The engine owns device memory for its callers (the reference's classes call
+ * cudaMalloc/cudaMemset/cudaMemcpy directly: include/classes/fi.cuh:84-88,
+ * src/frprmn.cpp allocateMemoryGpu, objectivefunction.cuh:80-85). Allocations are
+ * zero-filled like the reference's malloc+memset pairs. Copies are ordered on
+ * the engine stream; H2D/D2H return after completion. */
+enum { GVM_COPY_H2D = 0, GVM_COPY_D2H = 1, GVM_COPY_D2D = 2 };
+int gvm_dev_alloc(gvm_engine* e, size_t bytes, void** out);
+int gvm_dev_free(gvm_engine* e, void* p);
+int gvm_dev_memset(gvm_engine* e, void* p, int value, size_t bytes);
+int gvm_dev_copy(gvm_engine* e, void* dst, const void* src, size_t bytes, int kind);
+
+/* ------------------------------------------------------------ multi-GPU ----
+ * One process per GPU. Every rank holds a shard of the visibility blocks
+ * (whole channels, as the reference's `i % num_gpus` rule, src/functions.cu:4341,
+ * or contiguous visibility chunks of a channel) and a replica of the image.
+ * After gvm_dist_init, gvm_chi2 all-reduces the chi2 scalar and gvm_dchi2
+ * all-reduces the [2][M][N] gradient (NCCL, sum) before adding it to
+ * result_dchi2_dev — replacing the reference's serialised peer-to-peer
+ * accumulate (:4534-4549). Rank 0 creates the id, the launcher distributes it. */
+#define GVM_DIST_ID_BYTES 128
+int gvm_dist_unique_id(char* id_out, size_t bytes);
+int gvm_dist_init(gvm_engine* e, int rank, int world, const char* id, size_t bytes);
+int gvm_dist_rank(gvm_engine* e);
+int gvm_dist_world(gvm_engine* e);
+int gvm_dist_allreduce(gvm_engine* e, float* buf_dev, int64_t n);
+int64_t gvm_dist_collectives(gvm_engine* e);
 
 /* ------------------------------------------------- weights and gridding ---
  * WeightingScheme::apply (src/{natural,uniform,briggs,radial}weightingscheme.cu)

@@ -1,0 +1,110 @@
+/* gvm_host.h — C entry points of the C++ host layer (gpuvmem_b200/libgvmhost.so).
+ *
+ * The host layer restates gpuvmem's plugin surface in C++ (headers under gpuvmem_b200/csrc/host:
+ * Synthesizer "MFS", Optimizer "CG-FRPRMN"/"CG-LBFGS", ObjectiveFunction, the Fi terms,
+ * CKernel and WeightingScheme families, the string-keyed factories and the reference's
+ * command line) on top of the engine's C ABI (gvm_b200.h). A C++ program uses the classes
+ * directly (gpuvmem_b200/csrc/host/main.cpp is the reference's src/main.cu:100-229 on this
+ * layer); these functions expose the same flows to non-C++ callers (tests, bench.py).
+ * Every function returns 0 on success; errors that the reference turns into print+exit
+ * do the same here.
+ */
+#ifndef GVM_HOST_H
+#define GVM_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "gvm_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gvmh_session gvmh_session;
+
+/* What readMS + readFITSHeader hand to MFS::configure (src/MSFITSIO.cu:398-754,
+ * include/MSFITSIO.cuh:140-150): one dataset, one field, one correlation (XX). */
+typedef struct gvmh_problem {
+  int64_t M, N;
+  double DELTAX, DELTAY;   /* CDELT1, CDELT2 (deg) */
+  double ra, dec;          /* CRVAL1, CRVAL2 (deg) = phase centre */
+  double crpix1, crpix2;
+  const char* telescope;   /* "ALMA", "EVLA", other */
+  float antenna_diameter;
+  float beam_noise;        /* NOISE header keyword, <= 0: estimate */
+  int nchan;
+  const float* freqs;      /* [nchan] */
+  const int64_t* Z;        /* [nchan] */
+  const double* const* uvw_m; /* [nchan] -> [Z][3] metres */
+  const float* const* Vo;     /* [nchan] -> [Z][2] */
+  const float* const* w;      /* [nchan] -> [Z] */
+} gvmh_problem;
+
+/* Everything src/main.cu:147-212 does up to (not including) sy->run():
+ * factories -> MFS::configure(args) -> setDevice -> Fi terms -> ObjectiveFunction.
+ *   args      the reference's command line as one string, e.g.
+ *             "-z 0.001 -Z 0.01,0.0,1e-4 -t 50 -R 0.0 -g 0 -v"
+ *   optimizer "CG-FRPRMN" | "CG-LBFGS"; scheme "Natural"|"Uniform"|"Briggs"|"Radial";
+ *   ckernel   "PillBox2D"|"Gaussian2D"|"Sinc2D"|"GaussianSinc2D"|"PSWF" with size ck_m x ck_n
+ *   fi_spec   comma list of name:penalizatorIndex:imageIndex:imageToAdd, NULL = main.cu's
+ *             "Chi2:-1:0:0,Entropy:0:0:0,L1-Norm:1:0:0,TotalSquaredVariation:2:0:0,Laplacian:3:0:0"
+ *   rank/world/nccl_id  one process per GPU; nccl_id from gvm_dist_unique_id on rank 0 */
+int gvmh_create(const gvmh_problem* p, const char* args, const char* optimizer, const char* scheme,
+                const char* ckernel, int ck_m, int ck_n, const char* fi_spec, int rank, int world,
+                const char* nccl_id, gvmh_session** out);
+int gvmh_destroy(gvmh_session* s);
+
+/* Synthesizer::run (+ the default optimisation order of main.cu: flag 0 only). image_out
+ * [2][M][N] host, optional. */
+int gvmh_run(gvmh_session* s, float* image_out, double* optimize_seconds);
+int gvmh_clear_run(gvmh_session* s);
+int gvmh_set_lbfgs_k(gvmh_session* s, int k);
+int gvmh_write_outputs(gvmh_session* s);   /* writeImages + writeResiduals */
+
+/* ObjectiveFunction::calcFunction / calcGradient on the session's device image. */
+int gvmh_set_image(gvmh_session* s, const float* I_host);
+int gvmh_get_image(gvmh_session* s, float* I_host);
+int gvmh_set_iteration(gvmh_session* s, int iteration);  /* Fi::setIteration on every term */
+int gvmh_set_flag(gvmh_session* s, int flag_opt);
+int gvmh_calc_function(gvmh_session* s, float* value, float* fi_values, int nfi);
+int gvmh_calc_gradient(gvmh_session* s, int iteration, float* grad_host /* [2][M][N] or NULL */);
+/* One objective + gradient evaluation, device resident (bench `value`) ... */
+int gvmh_eval_device(gvmh_session* s, int iteration, float* value);
+/* ... and end to end: pinned/pageable host image in, gradient + value out (bench `e2e`). */
+int gvmh_eval_host(gvmh_session* s, const float* I_host, int iteration, float* value, float* grad_host);
+
+gvm_engine* gvmh_engine(gvmh_session* s);
+/* out[16]: fg_scale, noise_cut, noise_jypix, nu_0, vis_noise, sum_weights, bmaj_deg, bmin_deg,
+ * bpa_deg, deltau, deltav, xobs_pix, yobs_pix, total_visibilities, iterations_done, n_fi */
+int gvmh_scalars(gvmh_session* s, double* out);
+/* timings of the last create/run: setup, weighting, gridding, optimize (seconds); evaluation
+ * counters: function evaluations, gradient evaluations */
+int gvmh_stats(gvmh_session* s, double* seconds4, int64_t* counts2);
+/* the visibilities as the hot path sees them after weighting (+ gridding): per channel */
+int64_t gvmh_nvis(gvmh_session* s, int chan);
+int gvmh_get_host_vis(gvmh_session* s, int chan, double* uvw_m, float* Vo, float* w);
+const char* gvmh_exit_reason(gvmh_session* s);
+int gvmh_history(gvmh_session* s, float* out, int cap);
+
+/* --- stateless pieces (no GPU needed) ---------------------------------------------- */
+/* CKernel::buildKernel table (m x n) with sigmas (sx, sy); w <= 0 keeps the family default. */
+int gvmh_ckernel_table(const char* name, int m, int n, float sx, float sy, float w, float* table,
+                       int* support_x, int* support_y);
+/* CKernel::initializeGCF(M, N, dx, dy) image (M x N). */
+int gvmh_ckernel_gcf(const char* name, int m, int n, int M, int N, float dx, float dy, float* gcf);
+/* 1 if `name` is registered in the factory of `kind` ("Fi", "Optimizer", "CKernel",
+ * "WeightingScheme", "Synthesizer", "Io", "ObjectiveFunction"). */
+int gvmh_factory_has(const char* kind, const char* name);
+/* getOptions on a command-line string; writes a JSON object of the parsed Vars. */
+int gvmh_parse_args(const char* args, char* json_out, size_t cap);
+/* linmin's bracketing + Brent search on a caller-supplied 1-D function (host logic test). */
+typedef float (*gvmh_fn1d)(float x, void* user);
+int gvmh_linmin_1d(gvmh_fn1d f, void* user, float* xmin, float* fmin, int* probes);
+/* readGVMS summary: out[8] = M, N, nchan, total visibilities, min_freq, max_freq, max_blength, uvmax_wavelength */
+int gvmh_read_gvms(const char* path, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVM_HOST_H */

@@ -712,3 +712,105 @@ void gvo_ckernel(int kind, int m, int n, float sx, float sy, float w, int gcf, f
       table[n * i + j] = ck_eval(kind, x, y, sx, sy, w, m, n, gcf);
     }
 }
+
+/* ------------------------------------------------------------ line search --
+ * Restates linmin's 1-D search (src/linmin.cu:78-84: ax = 0, xx = 1, mnbrak then
+ * brent with TOL 1e-7) with mnbrak (src/mnbrak.cu:44-98) and brent
+ * (src/brent.cu:43-125) and the macros of include/nrutil.h:27-29,55. The reference is
+ * C++: fabs() on a float is the float overload, literals without suffix are double. */
+typedef float (*gvo_fn1d)(float, void*);
+static float lm_sign(float a, float b) { return b >= 0.0 ? fabsf(a) : -fabsf(a); }
+static float lm_fmax(float a, float b) { return a > b ? a : b; }
+int gvo_linmin_1d(gvo_fn1d func, void* user, float* xmin_out, float* fmin_out, int* probes_out) {
+  int probes = 0;
+#define F(x) (probes++, func((x), user))
+  float ax = 0.0f, bx = 1.0f, cx, fa, fb, fc;
+  { /* mnbrak */
+    const double GOLD = 1.618034, GLIMIT = 100.0;
+    const float TINY = (float)1.0e-20;
+    float ulim, u, r, q, fu, dum;
+    fa = F(ax);
+    fb = F(bx);
+    if (fb > fa) { dum = ax; ax = bx; bx = dum; dum = fb; fb = fa; fa = dum; }
+    cx = (float)(bx + GOLD * (bx - ax));
+    fc = F(cx);
+    while (fb > fc) {
+      r = (bx - ax) * (fb - fc);
+      q = (bx - cx) * (fb - fa);
+      u = (float)(bx - ((bx - cx) * q - (bx - ax) * r) / (2.0 * lm_sign(lm_fmax(fabsf(q - r), TINY), q - r)));
+      ulim = (float)(bx + GLIMIT * (cx - bx));
+      if ((bx - u) * (u - cx) > 0.0) {
+        fu = F(u);
+        if (fu < fc) { ax = bx; bx = u; fa = fb; fb = fu; break; }
+        else if (fu > fb) { cx = u; fc = fu; break; }
+        u = (float)(cx + GOLD * (cx - bx));
+        fu = F(u);
+      } else if ((cx - u) * (u - ulim) > 0.0) {
+        fu = F(u);
+        if (fu < fc) {
+          bx = cx; cx = u; u = (float)(cx + GOLD * (cx - bx));
+          fb = fc; fc = fu; fu = F(u);
+        }
+      } else if ((u - ulim) * (ulim - cx) >= 0.0) {
+        u = ulim;
+        fu = F(u);
+      } else {
+        u = (float)(cx + GOLD * (cx - bx));
+        fu = F(u);
+      }
+      ax = bx; bx = cx; cx = u;
+      fa = fb; fb = fc; fc = fu;
+    }
+  }
+  { /* brent */
+    const double CGOLD = 0.3819660, ZEPS = 1.0e-10;
+    const float tol = (float)1.0e-7;
+    float a, b, d = 0.0f, etemp, fu, fv, fw, fx, p, q, r, tol1, tol2, u, v, w, x, xm;
+    float e = 0.0f;
+    int iter;
+    a = (ax < cx ? ax : cx);
+    b = (ax > cx ? ax : cx);
+    x = w = v = bx;
+    fw = fv = fx = F(x);
+    for (iter = 1; iter <= 500; iter++) {
+      xm = (float)(0.5 * (a + b));
+      tol2 = (float)(2.0 * (tol1 = (float)(tol * fabsf(x) + ZEPS)));
+      if (fabsf(x - xm) <= (tol2 - 0.5 * (b - a))) break;
+      if (fabsf(e) > tol1) {
+        r = (x - w) * (fx - fv);
+        q = (x - v) * (fx - fw);
+        p = (x - v) * q - (x - w) * r;
+        q = (float)(2.0 * (q - r));
+        if (q > 0.0) p = -p;
+        q = fabsf(q);
+        etemp = e;
+        e = d;
+        if (fabsf(p) >= fabs(0.5 * q * etemp) || p <= q * (a - x) || p >= q * (b - x))
+          d = (float)(CGOLD * (e = (x >= xm ? a - x : b - x)));
+        else {
+          d = p / q;
+          u = x + d;
+          if (u - a < tol2 || b - u < tol2) d = lm_sign(tol1, xm - x);
+        }
+      } else {
+        d = (float)(CGOLD * (e = (x >= xm ? a - x : b - x)));
+      }
+      u = (fabsf(d) >= tol1 ? x + d : x + lm_sign(tol1, d));
+      fu = F(u);
+      if (fu <= fx) {
+        if (u >= x) a = x; else b = x;
+        v = w; w = x; x = u;
+        fv = fw; fw = fx; fx = fu;
+      } else {
+        if (u < x) a = u; else b = u;
+        if (fu <= fw || w == x) { v = w; w = u; fv = fw; fw = fu; }
+        else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
+      }
+    }
+    *xmin_out = x;
+    *fmin_out = fx;
+  }
+#undef F
+  if (probes_out) *probes_out = probes;
+  return 0;
+}

@@ -1,0 +1,25 @@
+"""Reconstruction scenarios shared by the reference runner (tests/_ref_runner.py, one fresh
+process per scenario because the reference keeps its state in process globals) and the host
+layer's GPU parity tests (tests/test_host_gpu.py)."""
+from gpuvmem_b200 import synth
+
+LAMBDAS = "0.01,0.005,0.002,0.001"   # -Z: Entropy, L1-Norm, TSV, Laplacian (src/main.cu:193-197)
+
+SCENARIOS = {
+    # name: (problem kwargs, reference command line, optimizer, scheme, ckernel, (m, n), lbfgs K)
+    "cg_natural": (dict(N=128, nvis=20000, nchan=1, freq0=2.3e11, seed=31, grid_fill=0.9),
+                   f"-z 0.001 -Z {LAMBDAS} -t 6", "CG-FRPRMN", "Natural", "PillBox2D", (1, 1), 0),
+    "lbfgs_natural": (dict(N=128, nvis=20000, nchan=1, freq0=2.3e11, seed=32, grid_fill=0.9),
+                      f"-z 0.001 -Z {LAMBDAS} -t 6", "CG-LBFGS", "Natural", "PillBox2D", (1, 1), 4),
+    "cg_mfs_briggs": (dict(N=128, nvis=12000, nchan=3, freq0=1.0e11, bandwidth=6e9, seed=33, grid_fill=0.9),
+                      "-z 0.001,0.2 -Z 0.01,0.0,0.002 -R 0.5 -t 4", "CG-FRPRMN", "Briggs", "PillBox2D", (1, 1), 0),
+    "cg_gridded_gaussian": (dict(N=128, nvis=20000, nchan=1, freq0=2.3e11, seed=34, grid_fill=0.9),
+                            f"-z 0.001 -Z {LAMBDAS} -g 1 -R 0.0 -t 4", "CG-FRPRMN", "Briggs", "Gaussian2D", (7, 7), 0),
+    "cg_gridded_pswf": (dict(N=128, nvis=20000, nchan=1, freq0=2.3e11, seed=35, grid_fill=0.9),
+                        "-z 0.001 -Z 0.01 -g 1 -t 3", "CG-FRPRMN", "Uniform", "PSWF", (9, 9), 0),
+}
+REF_EXTRA = " -X 16 -Y 16 -V 256 -i synth.ms -o out.ms -m hdr.fits"
+
+
+def problem(name):
+    return synth.make_problem(**SCENARIOS[name][0])

@@ -1,0 +1,104 @@
+"""GPU parity of the C++ host layer against the REFERENCE ITSELF, scenario by scenario:
+MFS::configure/setDevice scalars, the weighted (and gridded) visibilities (bit-exact),
+ObjectiveFunction::calcFunction / calcGradient at a probe image, and the image after the
+optimizer has run N iterations (north-star tolerance: chi2 rel 1e-5, gradient rel-L2 1e-4;
+final image: stated per scenario below, it inherits the amplification of the line search).
+
+The reference runs in its own process per scenario (tests/_ref_runner.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from _ref_runner import probe_image
+from _scenarios import SCENARIOS, problem
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# rel-L2 tolerance on the final image (unmasked pixels) after the scenario's iterations
+FINAL_TOL = {"cg_natural": 2e-3, "lbfgs_natural": 2e-3, "cg_mfs_briggs": 2e-3, "cg_gridded_gaussian": 2e-3,
+             "cg_gridded_pswf": 2e-3}
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def refdir(tmp_path_factory):
+    from _checkers import GVREF_SO
+    if not os.path.exists(GVREF_SO):
+        pytest.skip("oracle/_ref/libgvref.so not built")
+    return tmp_path_factory.mktemp("ref")
+
+
+def _reference(name, refdir):
+    out = os.path.join(str(refdir), name + ".npz")
+    if not os.path.exists(out):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_ref_runner.py"), name, out],
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return np.load(out)
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_scenario_matches_reference(name, refdir):
+    from gpuvmem_b200 import host
+    ref = _reference(name, refdir)
+    kw, args, optimizer, scheme, ck, ck_size, K = SCENARIOS[name]
+    p = problem(name)
+    s = host.Session(p, args=args, optimizer=optimizer, scheme=scheme, ckernel=ck, ck_size=ck_size)
+    try:
+        if K:
+            s.set_lbfgs_k(K)
+        sc = s.scalars()
+        # -- MFS::configure / setDevice ----------------------------------------------------
+        assert sc["deltau"] == ref["s_deltau"] and sc["deltav"] == ref["s_deltav"]
+        assert np.float32(sc["xobs_pix"]) == np.float32(ref["s_xpix"]) and np.float32(sc["yobs_pix"]) == np.float32(ref["s_ypix"])
+        assert np.float32(sc["nu_0"]) == np.float32(ref["s_nu_0"])
+        for mine, theirs, tol in (("vis_noise", "s_vis_noise", 1e-6), ("noise_jypix", "s_noise_jypix", 1e-5),
+                                  ("fg_scale", "s_fg_scale", 1e-5), ("noise_cut", "s_noise_cut", 1e-5)):
+            assert abs(sc[mine] - float(ref[theirs])) <= tol * abs(float(ref[theirs])), (mine, sc[mine], float(ref[theirs]))
+        # -- weights (+ gridding): bit-exact -----------------------------------------------
+        for c in range(p.nchan):
+            uvw, Vo, w = s.host_vis(c)
+            assert len(w) == len(ref[f"w{c}"]), (c, len(w), len(ref[f"w{c}"]))
+            assert np.array_equal(w.view(np.uint32), ref[f"w{c}"].view(np.uint32)), f"weights, channel {c}"
+            assert np.array_equal(uvw.view(np.uint64), ref[f"uvw{c}"].view(np.uint64)), f"uvw, channel {c}"
+            assert np.array_equal(Vo.view(np.uint32), ref[f"Vo{c}"].view(np.uint32)), f"Vo, channel {c}"
+        assert np.array_equal(s.get_image(), ref["I_start"])
+        # -- objective + gradient at a probe image -----------------------------------------
+        z = [float(t) for t in args.split("-z")[1].split()[0].split(",")]
+        probe = probe_image(p.N, np.float32(z[0]), z[1] if len(z) > 1 else 0.0)
+        s.set_image(probe)
+        s.set_iteration(1)
+        v, fi = s.calc_function()
+        rfi = ref["probe_fi"][:len(fi)]
+        assert abs(fi[0] - rfi[0]) <= 1e-5 * abs(rfi[0]), ("chi2", fi[0], rfi[0])
+        assert np.allclose(fi[1:], rfi[1:], rtol=2e-5, atol=0), (fi, rfi)
+        assert abs(v - float(ref["probe_value"])) <= 1e-5 * abs(float(ref["probe_value"]))
+        g = s.calc_gradient(1)
+        assert np.array_equal(s.get_image(), ref["probe_image_after"]), "clip2IWNoise side effect"
+        assert _rel(g[0], ref["probe_grad"][0]) <= 1e-4, _rel(g[0], ref["probe_grad"][0])
+        assert np.array_equal(g[0] == 0, ref["probe_grad"][0] == 0), "masked pixels must be exactly 0"
+        # -- the optimizer: image after N iterations ---------------------------------------
+        s.set_image(ref["I_start"])
+        s.set_iteration(0)
+        img, seconds = s.run()
+        it = int(s.scalars()["iterations_done"])
+        assert it == int(ref["iterations"]), (it, int(ref["iterations"]), s.exit_reason())
+        err0 = _rel(img[0], ref["final_image"][0])
+        print(f"\n[{name}] iterations={it} final-image rel-L2={err0:.3e} reference {float(ref['run_ms']):.0f} ms, "
+              f"here {seconds * 1e3:.0f} ms, exit={s.exit_reason()}")
+        assert err0 <= FINAL_TOL[name], err0
+        if len(z) > 1:
+            m = ref["final_image"][1] != np.float32(z[1])
+            assert _rel(img[1][m], ref["final_image"][1][m]) <= 10 * FINAL_TOL[name]
+        v2, fi2 = s.calc_function()
+        assert abs(v2 - float(ref["final_value"])) <= 1e-3 * abs(float(ref["final_value"]))
+    finally:
+        s.close()
