@@ -61,7 +61,23 @@ int gvmh_create(const gvmh_problem* p, const char* args, const char* optimizer, 
                 const char* ckernel, int ck_m, int ck_n, const char* fi_spec, int rank, int world,
                 const char* nccl_id, gvmh_session** out) {
   if (!p || !out) return 1;
+  {  // library callers get an error code instead of the reference's print + exit when no B200 is present
+    gvm_config probe;
+    std::memset(&probe, 0, sizeof(probe));
+    probe.M = probe.N = 16; probe.DELTAX = -1e-5; probe.DELTAY = 1e-5; probe.nu_0 = 1e11f; probe.eta = -1.0f;
+    probe.fg_scale = 1.0f; probe.noise_cut = 1e30f;
+    int dev = 0;
+    if (args) {
+      const char* gflag = std::strstr(args, "-G ");
+      if (gflag) dev = std::atoi(gflag + 3);
+    }
+    probe.device = dev;
+    gvm_engine* e = nullptr;
+    if (gvm_create(&probe, &e) != 0) return 2;
+    gvm_destroy(e);
+  }
   G() = Globals();
+
   gvmh_session* s = new gvmh_session();
   s->sy = createObject<Synthesizer, std::string>("MFS");
   s->mfs = static_cast<MFS*>(s->sy);

@@ -120,7 +120,7 @@ class Session:
                                 ck_size[0], ck_size[1], (fi_spec or DEFAULT_FI_SPEC).encode(), rank, world,
                                 nccl_id, C.byref(s))
         if rc != 0:
-            raise RuntimeError("gvmh_create failed")
+            raise RuntimeError("gvmh_create failed: " + _lib.load_library().gvm_last_error().decode())
         self.s = s
         self.M, self.N = p.M, p.N
         self.eng = _lib.load_library()

@@ -188,3 +188,22 @@ def test_line_search_matches_the_reference_binary(gvref, k):
     assert n == len(seen_r)
     assert np.array_equal(np.array(seen_r).view(np.uint32), np.array(seen_h).view(np.uint32))
     assert np.float32(xm) == np.float32(xmin.value) and np.float32(fm) == np.float32(fret)
+
+
+def test_session_fails_loudly_without_a_gpu(prob):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback|no CUDA device"):
+        host.Session(prob, args="-z 0.001 -Z 0.01 -t 2")
+
+
+def test_libraries_do_not_leak_runtime_symbols():
+    """Both libraries export only their own API: a second copy of C++ runtime symbols in the
+    process (some toolchains link libstdc++ statically) breaks iostream in the host program."""
+    import subprocess
+    from gpuvmem_b200 import lib
+    for path, allowed in ((lib.lib_path(), ("gvm_",)), (host.host_lib_path(), ("gvmh_", "gpuvmem::"))):
+        out = subprocess.run(["nm", "-DC", "--defined-only", path], capture_output=True, text=True).stdout
+        leaked = [l for l in out.splitlines() if l and not any(a in l for a in allowed)]
+        assert not leaked, leaked[:5]
