@@ -4,9 +4,10 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's engine
     python bench.py --impl reference --gpus N --steps K ...   # the reference arm
 
-One *step* = one regularised-ML evaluation of the chi2 term: gvm_chi2 (forward model,
-residuals, chi2) + gvm_dchi2 (DFT gradient, chain rule) over the whole visibility set,
-followed for N > 1 by one NCCL all-reduce of [gradient | chi2]. The workload is
+One *step* = one objective + gradient evaluation through the C++ host layer
+(ObjectiveFunction::calcFunction + calcGradient with the Fi terms BASELINE.json names for the
+config: Chi2 + L1 + TSV for configs[1]) over the whole visibility set; for N > 1 the engine
+all-reduces the chi2 scalar and the [2][M][N] gradient over NCCL inside those calls. The workload is
 BASELINE.json configs[1] (ALMA-like 2048^2 image x 10 M visibilities, 1 channel) on
 synthetic data; at N > 1 the visibilities are sharded by contiguous chunk (strong
 scaling). `value` is whole-job Mvis*Mpix/s = (Z/1e6)*(M*N/1e6)*evals/s, which is
@@ -80,6 +81,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class NativeStdoutToStderr:
+    """Native code (the reference prints its progress with printf) must not write into the
+    stream that carries the ONE JSON line: fd 1 points at stderr inside the block."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def make_workload(args):
     from gpuvmem_b200 import synth
     if args.config == "c2":
@@ -88,7 +106,19 @@ def make_workload(args):
         return synth.config_c1(scale=args.scale), "BASELINE.json configs[0]: co65-shaped 512x512, 2^20 visibilities, 1 channel"
     if args.config == "c3":
         return synth.config_c3(scale=args.scale), "BASELINE.json configs[2]: MFS 64 channels x 1M visibilities, 2048x2048"
+    if args.config == "c4":
+        return synth.config_c4(scale=args.scale), "BASELINE.json configs[3]: VLBI-like 4096x4096, 50M visibilities"
     raise SystemExit(f"unknown --config {args.config}")
+
+
+# per workload: the reference command line (initial values, -Z factors with main.cu's index map:
+# Entropy 0, L1-Norm 1, TSV 2, Laplacian 3), the Fi terms BASELINE.json names, the optimizer
+WORKLOAD_SETUP = {
+    "c1": ("-z 0.001 -Z 0.01", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN"),
+    "c2": ("-z 0.001 -Z 0.0,0.005,0.002", "Chi2:-1:0:0,L1-Norm:1:0:0,TotalSquaredVariation:2:0:0", "CG-LBFGS"),
+    "c3": ("-z 0.001,0.0 -Z 0.01", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN"),
+    "c4": ("-z 0.001 -Z 0.01", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN"),
+}
 
 
 def cpu_baseline(problem, engine_meta, seconds_target=15.0):
@@ -146,23 +176,29 @@ def run_reference(args):
     except Exception:
         pass
     if have_gpu and os.path.exists(GVREF_SO):
-        ref = GvRef()
-        ref.set_problem(sub)
-        ref.init("-X 16 -Y 16 -V 256 -z 0.001 -Z 0.0 -t 1 -i synth.ms -o out.ms -m hdr.fits")
-        sampler = ClockSampler(0)
-        for _ in range(max(args.warmup, 1)):
-            ref.time_evals(1)
-        sampler.start()
-        ms = ref.time_evals(args.steps)
-        clocks = sampler.stop()
-        value = (Zs / 1e6) * (N * N / 1e6) / (ms / 1e3)
-        line.update({"value": value, "ms_per_step": ms, "clocks": clocks, "gpu_launches": None,
-                     "evals_per_s_extrapolated_to_workload": value / ((problem.total_vis() / 1e6) * (N * N / 1e6)),
-                     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
-                                      "sample": f"reference CUDA build (unmodified src/*.cu, sm_100a) chi2()+dchi2() on "
-                                                f"{Zs} of {problem.total_vis()} visibilities, full {N}x{N} image, 1 GPU; "
-                                                "gpuvmem has no CPU implementation of this path"}})
+        with NativeStdoutToStderr():
+            ref = GvRef()
+            ref.set_problem(sub)
+            cli, fi_spec, optimizer = WORKLOAD_SETUP[args.config]
+            ref.lib.gvref_set_verbose(0)
+            ref.init(f"-X 16 -Y 16 -V 256 {cli} -t {max(args.recon_iters, 1)} -i synth.ms -o out.ms -m hdr.fits",
+                     optimizer=optimizer)
+            line["config"]["terms"] = fi_spec
+            line["config"]["cli"] = cli
+            sampler = ClockSampler(0)
+            for _ in range(max(args.warmup, 1)):
+                ref.time_evals(1, iteration=1)
+            sampler.start()
+            ms = ref.time_evals(args.steps, iteration=1)
+            clocks = sampler.stop()
+            value = (Zs / 1e6) * (N * N / 1e6) / (ms / 1e3)
+            line.update({"value": value, "ms_per_step": ms, "clocks": clocks, "gpu_launches": None,
+                         "evals_per_s_extrapolated_to_workload": value / ((problem.total_vis() / 1e6) * (N * N / 1e6)),
+                         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                                          "sample": f"reference CUDA build (unmodified src/*.cu, sm_100a) chi2()+dchi2() on "
+                                                    f"{Zs} of {problem.total_vis()} visibilities, full {N}x{N} image, 1 GPU; "
+                                                    "gpuvmem has no CPU implementation of this path"}})
     else:
         from gpuvmem_b200.engine import beam_model
         pbf, pbc, pb = beam_model(problem.telescope, problem.antenna_diameter, float(problem.freqs.min()))
@@ -187,6 +223,8 @@ def main():
     ap.add_argument("--grad-mode", type=int, default=0)
     ap.add_argument("--ref-sample", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--recon-iters", type=int, default=10, help="optimizer iterations of the full-reconstruction leg (0: skip)")
+    ap.add_argument("--lbfgs-k", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -195,50 +233,49 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from gpuvmem_b200 import Engine
     from gpuvmem_b200 import dist as gdist
+    from gpuvmem_b200 import host
 
     rank, world, local = gdist.init_from_env(args.gpus)
     torch.cuda.set_device(local)
     problem, wl = make_workload(args)
     M, N = problem.M, problem.N
     Ztot = problem.total_vis()
-    shard = gdist.shard_plan(problem.nchan, [len(w) for w in problem.w], world)
-    e = Engine.from_problem(problem, device=local, grad_mode=args.grad_mode, **shard[rank])
-    e.use_torch_stream()
     MN = M * N
-    I_host = torch.from_numpy(e.initial_image()).pin_memory()
-    I_dev = I_host.cuda()
-    # [gradient 2*M*N | chi2 as fp32 pair] in one buffer -> one collective per evaluation
-    buf = torch.zeros(2 * MN + 2, device="cuda", dtype=torch.float32)
-    chi2_dev = torch.zeros(1, device="cuda", dtype=torch.float64)
-    grad_host = torch.empty(2 * MN + 2).pin_memory()
+    cli, fi_spec, optimizer = WORKLOAD_SETUP[args.config]
+    # rank 0 creates the NCCL id; torch.distributed (the launcher's rendezvous) carries it
+    nccl_id = None
+    if world > 1:
+        box = [host.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+    # The public API: the C++ host layer (reference plugin surface) over the C ABI. Every rank
+    # builds the same Session; MFS::setDevice uploads this rank's shard (host.shard_plan).
+    host.set_quiet(True)   # stdout carries the JSON line only
+    s = host.Session(problem, args=f"{cli} -t {args.recon_iters} -G {local} -K {args.grad_mode}", optimizer=optimizer,
+                     fi_spec=fi_spec, rank=rank, world=world, nccl_id=nccl_id)
+    if optimizer == "CG-LBFGS":
+        s.set_lbfgs_k(args.lbfgs_k)
+    stream = torch.cuda.ExternalStream(s.eng.gvm_get_stream(s.engine_handle()), device=local)
+    I_host = torch.from_numpy(s.get_image()).pin_memory()
+    grad_host = torch.empty(2 * MN).pin_memory()
+    s.set_iteration(1)   # priors are gated off at iteration 0 in the reference (src/functions.cu:4643)
 
-    def step():
-        e.chi2_async(I_dev, False, chi2_dev)
-        buf.zero_()
-        e.dchi2(I_dev, buf, 0, False)
-        if world > 1:
-            buf[2 * MN:] = gdist.split_f64(chi2_dev)
-            dist.all_reduce(buf)
+    def step():          # ObjectiveFunction::calcFunction + calcGradient, image resident in HBM
+        s.eval_device(1)
 
-    def step_e2e():
-        if world == 1:
-            return e.eval_host(I_host, grad_host)
-        I_dev.copy_(I_host, non_blocking=True)
-        step()
-        grad_host.copy_(buf, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def step_e2e():      # host image in, objective value + gradient out
+        s.eval_host(I_host.data_ptr(), grad_host.data_ptr(), 1)
 
     def timed(fn, k):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        a.record(stream)
         for _ in range(k):
             fn()
-        b.record()
+        b.record(stream)
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
         if world > 1:
@@ -252,26 +289,13 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = e.launch_count()
-    kern_ms, kern_n = 0.0, 0
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.steps):
-        step()
-    b.record()
-    torch.cuda.synchronize()
-    ms_total = a.elapsed_time(b)
-    # dominant-kernel time of the LAST timed step, from CUDA events recorded on the same stream
-    # around each gradient-kernel launch inside the timed region
-    kern_ms, kern_n = e.last_grad_kernel_ms()
-    if world > 1:
-        t = torch.tensor([ms_total], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    launches = e.launch_count() - l0 + (args.steps if world > 1 else 0)
+    l0, c0 = s.launch_count(), s.collectives()
+    ms_total = timed(step, args.steps)
+    # dominant-kernel time of the LAST timed step: CUDA events recorded by the engine on its own
+    # stream around each gradient-kernel launch inside the timed region
+    kern_ms, kern_n = s.last_grad_kernel_ms()
+    launches = s.launch_count() - l0
+    collectives = s.collectives() - c0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     unit_work = (Ztot / 1e6) * (MN / 1e6)
@@ -281,13 +305,31 @@ def main():
     ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_value = unit_work / (ms_e2e / 1e3)
 
+    # full reconstruction (the second half of the BASELINE metric): optimizer from the flat
+    # starting image, setup/H2D excluded, wall time of Synthesizer::run
+    recon = None
+    if args.recon_iters > 0:
+        s.clear_run()
+        s.set_iteration(0)
+        _, sec = s.run()
+        st = s.stats()
+        if world > 1:
+            t = torch.tensor([sec], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        recon = {"optimizer": optimizer, "iterations": int(s.scalars()["iterations_done"]), "seconds": sec,
+                 "function_evals": st["function_evals"], "gradient_evals": st["gradient_evals"],
+                 "exit": s.exit_reason(), "lbfgs_k": args.lbfgs_k if optimizer == "CG-LBFGS" else None,
+                 "setup_seconds": st["setup_s"]}
+
     if rank == 0:
         pk = peaks()
-        mode = e.last_grad_mode()
-        Zloc = sum(e.nvis(c) for c in range(e.num_channels()))
-        ntiles, npx = e.grad_plan()
+        mode = s.last_grad_mode()
+        Zloc = s.local_nvis()
+        ntiles, npx = s.grad_plan()
         if mode != 1:
             npx = MN
+        nchan_local = max(1, kern_n)
         flops = 4.0 * npx * Zloc                     # algorithmic: 2 FMA per (computed pixel, visibility) pair
         ach = flops / (kern_ms / 1e3) / 1e12 if kern_ms > 0 else None
         peak = pk["tflops_sustained"]
@@ -296,25 +338,33 @@ def main():
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
                 "traffic": None,
                 "plan": {"tiles": ntiles, "pixels_computed": npx, "pixels_image": MN},
-                "note": f"algorithmic flops 4*P*Z per launch = {flops:.3e}, P = pixels of the tiles that cover the unmasked "
-                        f"part of the image (masked pixels are skipped, as DChi2 does); {kern_n} launch(es) per step, "
-                        f"{kern_ms:.2f} ms; peak = bf16/fp16 dense ({pk['source']}, sustained); the fp16x3 split issues "
-                        "3 MMAs per useful product, so frac <= 1/3 by construction"}
+                "note": f"algorithmic flops 4*P*Z per step on this rank = {flops:.3e}, P = pixels of the tiles that cover the "
+                        f"unmasked part of the image (masked pixels are skipped, as DChi2 does); {kern_n} launch(es) per step "
+                        f"(one per channel), {kern_ms:.2f} ms in total; peak = bf16/fp16 dense ({pk['source']}, sustained); the "
+                        "fp16x3 split issues 3 MMAs per useful product, so frac <= 1/3 by construction"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "evals_per_s": 1e3 / ms_step,
-                "config": {"workload": wl, "image": f"{M}x{N}", "visibilities": Ztot,
-                           "sharding": f"visibility chunks over {world} rank(s)" if problem.nchan == 1 else f"channels over {world} rank(s)",
+                "config": {"workload": wl, "image": f"{M}x{N}", "visibilities": Ztot, "terms": fi_spec, "cli": cli,
+                           "api": "C++ host layer (ObjectiveFunction::calcFunction + calcGradient) over the C ABI",
+                           "sharding": (f"visibility chunks over {world} rank(s)" if problem.nchan < world or world == 1
+                                        else f"channels over {world} rank(s) (i % world)"),
                            "l2": "inputs (>= 52 B/vis x Z) exceed the 126 MB L2; no flush needed",
                            "grad_mode": mode},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
-                        "h2d_bytes_per_step": 2 * MN * 4, "d2h_bytes_per_step": 2 * MN * 4 + 8},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+                        "h2d_bytes_per_step": 2 * MN * 4, "d2h_bytes_per_step": 2 * MN * 4 + 4},
+                "gpu_launches": int(launches), "collectives": int(collectives), "clocks": clocks, "roofline": roof,
+                "recon": recon}
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(problem, e.meta)
+            sc = s.scalars()
+            from gpuvmem_b200.engine import beam_model
+            pbf, pbc, pb = beam_model(problem.telescope, problem.antenna_diameter, float(problem.freqs.min()))
+            meta = dict(deltau=sc["deltau"], deltav=sc["deltav"], fg_scale=sc["fg_scale"], pb_factor=pbf, pb_cutoff=pbc,
+                        primary_beam=pb, xpix=sc["xobs_pix"], ypix=sc["yobs_pix"], nu_0=sc["nu_0"], noise_cut=sc["noise_cut"])
+            line["cpu_baseline"] = cpu_baseline(problem, meta)
         print(json.dumps(line), flush=True)
-    e.close()
+    s.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

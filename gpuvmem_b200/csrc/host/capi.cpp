@@ -24,6 +24,7 @@ struct gvmh_session {
 };
 
 namespace {
+bool g_quiet_all = false;  // gvmh_set_quiet: library callers that own stdout (bench.py prints ONE JSON line)
 std::vector<std::string> splitArgs(const std::string& s) {
   std::vector<std::string> out;
   std::istringstream is(s);
@@ -98,6 +99,7 @@ int gvmh_create(const gvmh_problem* p, const char* args, const char* optimizer, 
   h.crpix1 = p->crpix1; h.crpix2 = p->crpix2; h.beam_noise = p->beam_noise;
   s->mfs->adoptDatasets(std::move(ds), h);
   s->mfs->setDistributed(rank, world, nccl_id ? std::string(nccl_id, GVM_DIST_ID_BYTES) : std::string());
+  if (g_quiet_all) G().quiet = true;
 
   s->sy->setIoVisibilitiesHandler(ioms);
   s->sy->setIoImageHandler(iofits);
@@ -136,6 +138,12 @@ int gvmh_create(const gvmh_problem* p, const char* args, const char* optimizer, 
   }
   s->xi = devAllocFloats(imageFloats());
   *out = s;
+  return 0;
+}
+
+int gvmh_set_quiet(int quiet) {
+  g_quiet_all = quiet != 0;
+  G().quiet = G().quiet || g_quiet_all;
   return 0;
 }
 
@@ -327,6 +335,14 @@ int gvmh_linmin_1d(gvmh_fn1d f, void* user, float* xmin, float* fmin, int* probe
   if (xmin) *xmin = xm;
   if (fmin) *fmin = fm;
   if (probes) *probes = (int)ls.probes;
+  return 0;
+}
+int gvmh_shard_plan(int nchan, const int64_t* Z, int world, int rank, int64_t* lo, int64_t* hi) {
+  for (int c = 0; c < nchan; c++) {
+    size_t a = 0, b = 0;
+    if (shardRange(nchan, c, (size_t)Z[c], rank, world, &a, &b)) { lo[c] = (int64_t)a; hi[c] = (int64_t)b; }
+    else { lo[c] = hi[c] = 0; }
+  }
   return 0;
 }
 int gvmh_read_gvms(const char* path, double* out) {

@@ -376,6 +376,16 @@ void MFS::doGridding() {
   }
 }
 
+bool shardRange(int max_nfreq, int chan, size_t Z, int rank, int world, size_t* lo, size_t* hi) {
+  *lo = 0;
+  *hi = Z;
+  if (world <= 1) return true;
+  if (max_nfreq >= world) return chan % world == rank;  // whole channels, the reference's rule
+  *lo = Z * (size_t)rank / world;                         // contiguous visibility chunks
+  *hi = Z * (size_t)(rank + 1) / world;
+  return true;
+}
+
 // Which part of every (dataset, field, channel, stokes) block lives on this rank, then the
 // uploads. Whole channels go to rank (i % world) as in the reference (src/mfs.cu:568,
 // src/functions.cu:4341) when there are at least `world` channels; otherwise every block is cut
@@ -384,7 +394,6 @@ void MFS::shardAndUpload() {
   Globals& g = G();
   int max_nfreq = 1;
   for (MSDataset& ds : datasets) max_nfreq = std::max(max_nfreq, ds.data.total_frequencies);
-  const bool by_channel = g.world > 1 && max_nfreq >= g.world;
   for (MSDataset& ds : datasets)
     for (Field& f : ds.fields) {
       f.engine_slot.assign(f.visibilities.size(), std::vector<int>(ds.data.nstokes, -1));
@@ -392,15 +401,8 @@ void MFS::shardAndUpload() {
         for (int s = 0; s < ds.data.nstokes; s++) {
           if (!usedCorrelation(ds.data.corr_type[s])) continue;
           HVis& v = f.visibilities[i][s];
-          size_t lo = 0, hi = v.size();
-          if (g.world > 1) {
-            if (by_channel) {
-              if ((int)(i % g.world) != g.rank) continue;
-            } else {
-              lo = v.size() * (size_t)g.rank / g.world;
-              hi = v.size() * (size_t)(g.rank + 1) / g.world;
-            }
-          }
+          size_t lo = 0, hi = 0;
+          if (!shardRange(max_nfreq, (int)i, v.size(), g.rank, g.world, &lo, &hi)) continue;
           gvm_channel_desc cd;
           cd.freq = f.nu[i];
           cd.antenna_diameter = ds.antennas[0].antenna_diameter;

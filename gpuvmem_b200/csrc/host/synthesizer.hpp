@@ -31,6 +31,12 @@ struct Vars {
 bool getOptions(int argc, char** argv, Vars* out);
 void print_help();
 
+// The part [lo, hi) of a block of Z visibilities in channel `chan` that rank `rank` of `world`
+// holds; false when the block lives elsewhere. Whole channels go to rank chan % world (the
+// reference's rule, src/functions.cu:4341) when the job has at least `world` channels; otherwise
+// every block is cut into `world` contiguous chunks.
+bool shardRange(int max_nfreq, int chan, size_t Z, int rank, int world, size_t* lo, size_t* hi);
+
 class Synthesizer {
  public:
   virtual ~Synthesizer() = default;

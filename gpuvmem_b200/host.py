@@ -39,6 +39,7 @@ SIGNATURES = {
     "gvmh_create": (C.c_int, [C.POINTER(gvmh_problem), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int,
                               C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(_P)]),
     "gvmh_destroy": (C.c_int, [_P]),
+    "gvmh_set_quiet": (C.c_int, [C.c_int]),
     "gvmh_run": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     "gvmh_clear_run": (C.c_int, [_P]),
     "gvmh_set_lbfgs_k": (C.c_int, [_P, C.c_int]),
@@ -65,6 +66,7 @@ SIGNATURES = {
     "gvmh_parse_args": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t]),
     "gvmh_linmin_1d": (C.c_int, [FN1D, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "gvmh_read_gvms": (C.c_int, [C.c_char_p, _P]),
+    "gvmh_shard_plan": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, _P, _P]),
 }
 
 
@@ -288,6 +290,18 @@ def read_gvms(path):
         raise RuntimeError(f"cannot read {path}")
     return dict(M=int(out[0]), N=int(out[1]), nchan=int(out[2]), total_vis=int(out[3]), min_freq=out[4],
                 max_freq=out[5], max_blength=out[6], uvmax_wavelength=out[7])
+
+
+def set_quiet(quiet=True):
+    load_host_library().gvmh_set_quiet(1 if quiet else 0)
+
+
+def shard_plan(Z, world, rank):
+    """[(lo, hi)] per channel: what MFS::setDevice uploads on ``rank`` of ``world``."""
+    Z = np.ascontiguousarray(Z, dtype=np.int64)
+    lo, hi = np.zeros_like(Z), np.zeros_like(Z)
+    load_host_library().gvmh_shard_plan(len(Z), Z.ctypes.data, world, rank, lo.ctypes.data, hi.ctypes.data)
+    return list(zip(lo.tolist(), hi.tolist()))
 
 
 def nccl_unique_id():

@@ -54,6 +54,9 @@ int gvmh_create(const gvmh_problem* p, const char* args, const char* optimizer, 
                 const char* ckernel, int ck_m, int ck_n, const char* fi_spec, int rank, int world,
                 const char* nccl_id, gvmh_session** out);
 int gvmh_destroy(gvmh_session* s);
+/* 1: the host layer prints nothing to stdout (the reference's progress text), for callers that
+ * own stdout. Applies to sessions created afterwards and to the current one. */
+int gvmh_set_quiet(int quiet);
 
 /* Synthesizer::run (+ the default optimisation order of main.cu: flag 0 only). image_out
  * [2][M][N] host, optional. */
@@ -101,6 +104,9 @@ int gvmh_parse_args(const char* args, char* json_out, size_t cap);
 /* linmin's bracketing + Brent search on a caller-supplied 1-D function (host logic test). */
 typedef float (*gvmh_fn1d)(float x, void* user);
 int gvmh_linmin_1d(gvmh_fn1d f, void* user, float* xmin, float* fmin, int* probes);
+/* Multi-GPU sharding rule of MFS::setDevice: the part [lo[c], hi[c]) of channel c's Z[c]
+ * visibilities that `rank` of `world` holds (lo == hi: none). */
+int gvmh_shard_plan(int nchan, const int64_t* Z, int world, int rank, int64_t* lo, int64_t* hi);
 /* readGVMS summary: out[8] = M, N, nchan, total visibilities, min_freq, max_freq, max_blength, uvmax_wavelength */
 int gvmh_read_gvms(const char* path, double* out);
 

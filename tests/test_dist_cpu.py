@@ -68,3 +68,37 @@ def test_two_rank_gloo_exchange(tmp_path):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+_WORKER_HOST = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from gpuvmem_b200 import dist as gdist
+from gpuvmem_b200 import host
+rank, world, local = gdist.init_from_env(2)
+assert world == 2 and dist.get_backend() == "gloo"
+# what bench.py / a launcher does before creating the per-rank Session: rank 0 makes the NCCL id,
+# the launcher's rendezvous carries it, every rank derives its shard of the visibilities
+box = [host.nccl_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(box, src=0)
+assert isinstance(box[0], bytes) and len(box[0]) == 128
+ids = [None, None]
+dist.all_gather_object(ids, box[0])
+assert ids[0] == ids[1]
+for Z in ([1001], [700, 900, 1100]):          # visibility chunks / whole channels
+    mine = sum(hi - lo for lo, hi in host.shard_plan(Z, world, rank))
+    n = torch.tensor([mine]); dist.all_reduce(n); assert int(n) == sum(Z), (Z, int(n))
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_host_layer_rendezvous(tmp_path):
+    script = tmp_path / "worker_host.py"
+    script.write_text(_WORKER_HOST)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29534", str(script), ROOT]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

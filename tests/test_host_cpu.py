@@ -207,3 +207,25 @@ def test_libraries_do_not_leak_runtime_symbols():
         out = subprocess.run(["nm", "-DC", "--defined-only", path], capture_output=True, text=True).stdout
         leaked = [l for l in out.splitlines() if l and not any(a in l for a in allowed)]
         assert not leaked, leaked[:5]
+
+
+def test_shard_plan_covers_every_visibility_exactly_once():
+    # >= world channels: whole channels, rank = chan % world (the reference's rule)
+    Z = [1000 + 7 * c for c in range(64)]
+    for world in (2, 4, 8):
+        owners = np.zeros(64, int)
+        for r in range(world):
+            for c, (lo, hi) in enumerate(host.shard_plan(Z, world, r)):
+                if hi > lo:
+                    assert (lo, hi) == (0, Z[c]) and c % world == r
+                    owners[c] += 1
+        assert (owners == 1).all()
+    # fewer channels than ranks: contiguous visibility chunks
+    for Zs, world in [([10_000_000], 8), ([1_048_576, 999_999], 4), ([7], 2), ([5], 8)]:
+        for c, z in enumerate(Zs):
+            covered = np.zeros(z, int)
+            for r in range(world):
+                lo, hi = host.shard_plan(Zs, world, r)[c]
+                covered[lo:hi] += 1
+            assert (covered == 1).all()
+    assert host.shard_plan([5, 6], 1, 0) == [(0, 5), (0, 6)]

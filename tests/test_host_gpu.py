@@ -39,8 +39,11 @@ def refdir(tmp_path_factory):
 def _reference(name, refdir):
     out = os.path.join(str(refdir), name + ".npz")
     if not os.path.exists(out):
+        # one OpenMP thread: the reference's Briggs/uniform grids are fp32 sums whose order follows
+        # the thread interleaving (omp critical); only the 1-thread order is deterministic
+        env = dict(os.environ, OMP_THREAD_LIMIT="1", OMP_NUM_THREADS="1")
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_ref_runner.py"), name, out],
-                           capture_output=True, text=True, timeout=900)
+                           capture_output=True, text=True, timeout=900, env=env)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return np.load(out)
 
