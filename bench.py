@@ -346,6 +346,9 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "evals_per_s": 1e3 / ms_step,
+                # the metric counts image pixels; masked pixels (noise >= noise_cut) are skipped by the
+                # reference's DChi2 and by this engine alike — the same figure over the computed pixels only:
+                "value_computed_pixels": value * (npx / MN),
                 "config": {"workload": wl, "image": f"{M}x{N}", "visibilities": Ztot, "terms": fi_spec, "cli": cli,
                            "api": "C++ host layer (ObjectiveFunction::calcFunction + calcGradient) over the C ABI",
                            "sharding": (f"visibility chunks over {world} rank(s)" if problem.nchan < world or world == 1
