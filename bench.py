@@ -108,16 +108,22 @@ def make_workload(args):
         return synth.config_c3(scale=args.scale), "BASELINE.json configs[2]: MFS 64 channels x 1M visibilities, 2048x2048"
     if args.config == "c4":
         return synth.config_c4(scale=args.scale), "BASELINE.json configs[3]: VLBI-like 4096x4096, 50M visibilities"
+    if args.config == "c5":
+        return synth.config_c5(scale=args.scale), "BASELINE.json configs[4]: gridded mode, Briggs R=0, 8192x8192 grid, 200M visibilities"
     raise SystemExit(f"unknown --config {args.config}")
 
 
 # per workload: the reference command line (initial values, -Z factors with main.cu's index map:
 # Entropy 0, L1-Norm 1, TSV 2, Laplacian 3), the Fi terms BASELINE.json names, the optimizer
 WORKLOAD_SETUP = {
-    "c1": ("-z 0.001 -Z 0.01", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN"),
-    "c2": ("-z 0.001 -Z 0.0,0.005,0.002", "Chi2:-1:0:0,L1-Norm:1:0:0,TotalSquaredVariation:2:0:0", "CG-LBFGS"),
-    "c3": ("-z 0.001,0.0 -Z 0.01", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN"),
-    "c4": ("-z 0.001 -Z 0.01", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN"),
+    "c1": ("-z 0.001 -Z 0.01", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN", "Natural", "PillBox2D", (0, 0)),
+    "c2": ("-z 0.001 -Z 0.0,0.005,0.002", "Chi2:-1:0:0,L1-Norm:1:0:0,TotalSquaredVariation:2:0:0", "CG-LBFGS",
+           "Natural", "PillBox2D", (0, 0)),
+    "c3": ("-z 0.001,0.0 -Z 0.01", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN", "Natural", "PillBox2D", (0, 0)),
+    # PSWF_12D is a GRIDDING kernel in the reference (it only acts under -g; degriddingGPU is dead code)
+    "c4": ("-z 0.001 -Z 0.01 -g 1", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN", "Natural", "PSWF", (9, 9)),
+    # gridded mode: Briggs R = 0 weights, convolutional gridding (-g), then the objective on the gridded samples
+    "c5": ("-z 0.001 -Z 0.01 -g 1 -R 0.0", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN", "Briggs", "Gaussian2D", (7, 7)),
 }
 
 
@@ -179,10 +185,10 @@ def run_reference(args):
         with NativeStdoutToStderr():
             ref = GvRef()
             ref.set_problem(sub)
-            cli, fi_spec, optimizer = WORKLOAD_SETUP[args.config]
+            cli, fi_spec, optimizer, scheme, ckernel, ck_size = WORKLOAD_SETUP[args.config]
             ref.lib.gvref_set_verbose(0)
             ref.init(f"-X 16 -Y 16 -V 256 {cli} -t {max(args.recon_iters, 1)} -i synth.ms -o out.ms -m hdr.fits",
-                     optimizer=optimizer)
+                     optimizer=optimizer, scheme=scheme, ckernel=ckernel, ck_m=max(ck_size[0], 1), ck_n=max(ck_size[1], 1))
             line["config"]["terms"] = fi_spec
             line["config"]["cli"] = cli
             sampler = ClockSampler(0)
@@ -242,7 +248,7 @@ def main():
     M, N = problem.M, problem.N
     Ztot = problem.total_vis()
     MN = M * N
-    cli, fi_spec, optimizer = WORKLOAD_SETUP[args.config]
+    cli, fi_spec, optimizer, scheme, ckernel, ck_size = WORKLOAD_SETUP[args.config]
     # rank 0 creates the NCCL id; torch.distributed (the launcher's rendezvous) carries it
     nccl_id = None
     if world > 1:
@@ -253,7 +259,8 @@ def main():
     # builds the same Session; MFS::setDevice uploads this rank's shard (host.shard_plan).
     host.set_quiet(True)   # stdout carries the JSON line only
     s = host.Session(problem, args=f"{cli} -t {args.recon_iters} -G {local} -K {args.grad_mode}", optimizer=optimizer,
-                     fi_spec=fi_spec, rank=rank, world=world, nccl_id=nccl_id)
+                     scheme=scheme, ckernel=ckernel, ck_size=ck_size, fi_spec=fi_spec, rank=rank, world=world,
+                     nccl_id=nccl_id)
     if optimizer == "CG-LBFGS":
         s.set_lbfgs_k(args.lbfgs_k)
     stream = torch.cuda.ExternalStream(s.eng.gvm_get_stream(s.engine_handle()), device=local)
@@ -298,7 +305,9 @@ def main():
     collectives = s.collectives() - c0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
-    unit_work = (Ztot / 1e6) * (MN / 1e6)
+    # gridded mode: the objective runs over the gridded samples, not the raw visibilities
+    Zwork = sum(s.h.gvmh_nvis(s.s, c) for c in range(problem.nchan)) if "-g" in cli else Ztot
+    unit_work = (Zwork / 1e6) * (MN / 1e6)
     value = unit_work / (ms_step / 1e3)
 
     step_e2e()
@@ -311,6 +320,7 @@ def main():
     if args.recon_iters > 0:
         s.clear_run()
         s.set_iteration(0)
+        st0 = s.stats()
         _, sec = s.run()
         st = s.stats()
         if world > 1:
@@ -318,7 +328,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sec = float(t.item())
         recon = {"optimizer": optimizer, "iterations": int(s.scalars()["iterations_done"]), "seconds": sec,
-                 "function_evals": st["function_evals"], "gradient_evals": st["gradient_evals"],
+                 "function_evals": st["function_evals"] - st0["function_evals"],
+                 "gradient_evals": st["gradient_evals"] - st0["gradient_evals"],
+                 "seconds_in_function_evals": st["function_s"] - st0["function_s"],
+                 "seconds_in_gradient_evals": st["gradient_s"] - st0["gradient_s"],
                  "exit": s.exit_reason(), "lbfgs_k": args.lbfgs_k if optimizer == "CG-LBFGS" else None,
                  "setup_seconds": st["setup_s"]}
 
@@ -333,6 +346,7 @@ def main():
         flops = 4.0 * npx * Zloc                     # algorithmic: 2 FMA per (computed pixel, visibility) pair
         ach = flops / (kern_ms / 1e3) / 1e12 if kern_ms > 0 else None
         peak = pk["tflops_sustained"]
+        st_all = s.stats()
         roof = {"bound": "tensor", "kernel": {1: "k_grad_umma (tcgen05 cta_group::2, fp16x3)", 2: "k_grad_sep (CUDA cores fp32)",
                                               3: "k_grad_exact (CUDA cores)"}.get(mode, str(mode)),
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
@@ -342,6 +356,26 @@ def main():
                         f"unmasked part of the image (masked pixels are skipped, as DChi2 does); {kern_n} launch(es) per step "
                         f"(one per channel), {kern_ms:.2f} ms in total; peak = bf16/fp16 dense ({pk['source']}, sustained); the "
                         "fp16x3 split issues 3 MMAs per useful product, so frac <= 1/3 by construction"}
+        if mode == 4:
+            # gridded samples: scatter (28 B/sample in + 8 B RMW) + memset (8 B/px) + cuFFT (two passes,
+            # 16 B r/w each) + real part (8 B in, 4 B out) — HBM-bound
+            gbytes = 36.0 * Zloc + (8.0 + 32.0 + 12.0) * MN
+            ach = gbytes / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else None
+            roof = {"bound": "hbm", "kernel": "k_gridfft_scatter + cuFFT C2C + k_gridfft_real (gridded samples: the DFT is an FFT)",
+                    "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": (ach / pk["hbm_gbs"]) if ach else None,
+                    "traffic": None,
+                    "note": f"algorithmic bytes 36*Z + 52*M*N = {gbytes:.3e} per gradient on this rank, {kern_ms:.3f} ms; "
+                            f"peak = measured HBM copy bandwidth ({pk['source']})"}
+        if mode == 1 and args.config == "c2" and args.scale == 1.0 and world == 1:
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this exact workload,
+            # from the committed ncu --set full capture (profiles/r1b_traffic.json)
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
+                roof["traffic"] = next(iter(tr.values()))["dram_bytes_total"]
+                roof["traffic_note"] = ("bytes per launch (ncu); algorithmic minimum 28 B x Z per tile pass x 32 tiles, "
+                                        "served from L2: the kernel is tensor-bound, DRAM at 0.02 % of peak")
+            except Exception:
+                pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -349,7 +383,7 @@ def main():
                 # the metric counts image pixels; masked pixels (noise >= noise_cut) are skipped by the
                 # reference's DChi2 and by this engine alike — the same figure over the computed pixels only:
                 "value_computed_pixels": value * (npx / MN),
-                "config": {"workload": wl, "image": f"{M}x{N}", "visibilities": Ztot, "terms": fi_spec, "cli": cli,
+                "config": {"workload": wl, "image": f"{M}x{N}", "visibilities": Ztot, "samples_in_objective": Zwork, "terms": fi_spec, "cli": cli,
                            "api": "C++ host layer (ObjectiveFunction::calcFunction + calcGradient) over the C ABI",
                            "sharding": (f"visibility chunks over {world} rank(s)" if problem.nchan < world or world == 1
                                         else f"channels over {world} rank(s) (i % world)"),
@@ -358,7 +392,12 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": 2 * MN * 4, "d2h_bytes_per_step": 2 * MN * 4 + 4},
                 "gpu_launches": int(launches), "collectives": int(collectives), "clocks": clocks, "roofline": roof,
-                "recon": recon}
+                "recon": recon,
+                "preprocessing": {"raw_visibilities": Ztot, "samples_after_gridding": int(Zloc) if "-g" in cli else None,
+                                  "weighting_seconds": st_all["weighting_s"], "gridding_seconds": st_all["gridding_s"],
+                                  "scheme": scheme, "ckernel": f"{ckernel} {ck_size[0]}x{ck_size[1]}" if "-g" in cli else None,
+                                  "gridding_Mvis_per_s": (Ztot / 1e6 / (st_all["weighting_s"] + st_all["gridding_s"]))
+                                  if "-g" in cli and st_all["gridding_s"] > 0 else None}}
         if not args.no_cpu_baseline:
             sc = s.scalars()
             from gpuvmem_b200.engine import beam_model

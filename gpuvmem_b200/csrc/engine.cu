@@ -123,6 +123,8 @@ int gvm_destroy(gvm_engine* e) {
   cudaFree(e->row_ext); cudaFree(e->tile_list); cudaFree(e->band_tab);
   gvm_dist_release(e);
   cudaFree(e->dist_grad);
+  for (auto& kv : e->pool_free) cudaFree(kv.second);
+  for (auto& kv : e->pool_live) cudaFree(kv.first);
   for (auto ev : e->ev) cudaEventDestroy(ev);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -287,6 +289,10 @@ int gvm_chi2(gvm_engine* e, float* I_dev, int normalize, float* chi2_out) {
 static int pick_grad_mode(gvm_engine* e, GvmChannel& c) {
   int mode = e->cfg.grad_mode;
   if (mode == GVM_GRAD_SIMT_EXACT || mode == GVM_GRAD_SIMT) return mode;
+  if (mode == GVM_GRAD_GRIDFFT || (mode == GVM_GRAD_AUTO && c.offgrid == 0)) {
+    if (c.offgrid == 0) return GVM_GRAD_GRIDFFT;
+    mode = GVM_GRAD_AUTO;  // not applicable to these samples
+  }
   const bool sep_ok = gvm_wterm_cross_bound(e, c) <= 2e-6;  // turns; DESIGN.md §3.4
   if (mode == GVM_GRAD_UMMA) return GVM_GRAD_UMMA;
   if (!sep_ok) return GVM_GRAD_SIMT_EXACT;
@@ -320,6 +326,9 @@ int gvm_dchi2(gvm_engine* e, const float* I_dev, int flag_opt, int normalize,
     e->last_grad_mode = mode;
     if (mode == GVM_GRAD_UMMA) {
       if (gvm_grad_umma(e, c, I_dev, flag_opt, normalize, result_dchi2_dev)) return 1;
+    } else if (mode == GVM_GRAD_GRIDFFT) {
+      if (gvm_grad_gridfft(e, c)) return 1;
+      if (gvm_grad_finish(e, c, I_dev, 1, flag_opt, normalize, result_dchi2_dev)) return 1;
     } else {
       int ksplit = 1;
       if (gvm_grad_simt(e, c, mode == GVM_GRAD_SIMT_EXACT, &ksplit)) return 1;
@@ -354,17 +363,28 @@ int gvm_eval_host(gvm_engine* e, const float* I_host, int flag_opt, int normaliz
 // ------------------------------------------------------------ device memory
 int gvm_dev_alloc(gvm_engine* e, size_t bytes, void** out) {
   GVM_CUDA(cudaSetDevice(e->cfg.device));
+  const size_t want = bytes ? bytes : 4;
   void* p = nullptr;
-  GVM_CUDA(cudaMalloc(&p, bytes ? bytes : 4));
-  GVM_CUDA(cudaMemsetAsync(p, 0, bytes ? bytes : 4, e->stream));
+  auto hit = e->pool_free.find(want);       // exact-size reuse: the callers' sizes repeat
+  if (hit != e->pool_free.end()) {
+    p = hit->second;
+    e->pool_free.erase(hit);
+  } else {
+    GVM_CUDA(cudaMalloc(&p, want));
+  }
+  e->pool_live[p] = want;
+  GVM_CUDA(cudaMemsetAsync(p, 0, want, e->stream));
   *out = p;
   return 0;
 }
 int gvm_dev_free(gvm_engine* e, void* p) {
   if (!p) return 0;
-  GVM_CUDA(cudaSetDevice(e->cfg.device));
-  GVM_CUDA(cudaStreamSynchronize(e->stream));
-  GVM_CUDA(cudaFree(p));
+  auto it = e->pool_live.find(p);
+  if (it == e->pool_live.end()) { gvm_set_error("gvm_dev_free: %p was not allocated by gvm_dev_alloc", p); return 1; }
+  // stream-ordered reuse: every user of the block works on the engine stream, so a later
+  // gvm_dev_alloc may hand it out again without a device synchronisation
+  e->pool_free.emplace(it->second, p);
+  e->pool_live.erase(it);
   return 0;
 }
 int gvm_dev_memset(gvm_engine* e, void* p, int value, size_t bytes) {

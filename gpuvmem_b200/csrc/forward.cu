@@ -30,9 +30,10 @@ __global__ void __launch_bounds__(256) k_prep_channel(
     double dy_turn, long N, long Z, double* __restrict__ uvw_l, uint32_t* __restrict__ cell,
     float2* __restrict__ frac, float2* __restrict__ Vo, float* __restrict__ w,
     uint64_t* __restrict__ du64, uint64_t* __restrict__ dv64, float* __restrict__ wz,
-    float* __restrict__ max_abs_wz) {
+    float* __restrict__ max_abs_wz, unsigned long long* __restrict__ offgrid) {
   long k = blockIdx.x * (long)blockDim.x + threadIdx.x;
   float my_wz = 0.f;
+  bool off = false;
   if (k < Z) {
     double um = uvw_m[3 * k], vm = uvw_m[3 * k + 1], wm = uvw_m[3 * k + 2];
     float2 vo = Vo_in[k];
@@ -77,7 +78,13 @@ __global__ void __launch_bounds__(256) k_prep_channel(
     dv64[k] = __double2ull_rd(tv * 18446744073709551616.0);
     wz[k] = (float)wl;
     my_wz = fabsf((float)wl);
+    // Is the sample the centre of a uv cell with w = 0 (output of do_gridding)? Then its phase
+    // step per pixel is an integer multiple of 1/N turns and the DFT gradient is an FFT.
+    const double gu = tu * (double)N, gv = tv * (double)N;
+    off = fabs(gu - rint(gu)) > 1e-6 || fabs(gv - rint(gv)) > 1e-6 || wl != 0.0;
   }
+  const unsigned any_off = __ballot_sync(0xffffffffu, off);
+  if ((threadIdx.x & 31) == 0 && any_off) atomicAdd(offgrid, (unsigned long long)__popc(any_off));
   my_wz = gvm_warp_max(my_wz);
   if ((threadIdx.x & 31) == 0 && my_wz > 0.f)
     atomicMax(reinterpret_cast<int*>(max_abs_wz), __float_as_int(my_wz));  // non-negative floats order as ints
@@ -243,17 +250,21 @@ int gvm_launch_prep_channel(gvm_engine* e, GvmChannel& c, const double* uvw_m_de
   const double deltax = GVM_RPDEG_D * g.DELTAX, deltay = GVM_RPDEG_D * g.DELTAY;  // src/mfs.cu:493-496
   const double deltau = 1.0 / (g.M * deltax), deltav = 1.0 / (g.N * deltay);
   float* d_max = nullptr;
-  GVM_CUDA(cudaMalloc(&d_max, sizeof(float)));
-  GVM_CUDA(cudaMemsetAsync(d_max, 0, sizeof(float), e->stream));
+  GVM_CUDA(cudaMalloc(&d_max, 16));
+  GVM_CUDA(cudaMemsetAsync(d_max, 0, 16, e->stream));
+  unsigned long long* d_off = reinterpret_cast<unsigned long long*>(d_max) + 1;
   const int blocks = (int)((c.Z + 255) / 256);
   k_prep_channel<<<blocks, 256, 0, e->stream>>>(uvw_m_dev, Vo_dev, w_dev, c.d.freq, deltau, deltav,
                                                  g.DELTAX * GVM_RPDEG_D, g.DELTAY * GVM_RPDEG_D,
                                                  g.N, c.Z, c.uvw_l, c.cell, c.frac, c.Vo, c.w,
-                                                 c.du64, c.dv64, c.wz, d_max);
+                                                 c.du64, c.dv64, c.wz, d_max, d_off);
   GVM_LAUNCH(e);
   GVM_CUDA(cudaGetLastError());
+  unsigned long long h_off = 0;
+  GVM_CUDA(cudaMemcpyAsync(&h_off, d_off, sizeof(h_off), cudaMemcpyDeviceToHost, e->stream));
   GVM_CUDA(cudaMemcpyAsync(&c.max_abs_wz, d_max, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   GVM_CUDA(cudaStreamSynchronize(e->stream));
+  c.offgrid = (long)h_off;
   cudaFree(d_max);
   return 0;
 }

@@ -6,6 +6,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -49,6 +50,7 @@ struct GvmChannel {
   float* amp = nullptr;        // w_k |Vr_k| * 2^e
   uint32_t* gam = nullptr;     // arg(Vr_k) as a 0.32 fixed-point turn
   float max_abs_wz = 0.f;      // max |w| (wavelengths)
+  long offgrid = -1;           // samples that are NOT the centre of a uv cell with w = 0 (0: gridded data)
   int slot = -1;               // reduction slot of the last forward pass
 };
 
@@ -101,6 +103,10 @@ struct gvm_engine {
   int rank = 0, world = 1;
   float* dist_grad = nullptr;      // [2][MN] this rank's gradient contribution before the all-reduce
   int64_t collectives = 0;
+  // caller-visible device memory (gvm_dev_alloc/free): a caching pool — cudaMalloc/cudaFree cost
+  // 15-45 ms each on a loaded context, and the optimizers allocate work buffers per optimize() call
+  std::map<void*, size_t> pool_live;          // pointer -> bytes of every block handed out
+  std::multimap<size_t, void*> pool_free;     // bytes -> cached free blocks
 };
 
 #define GVM_LAUNCH(e) ((e)->launches++)
@@ -208,6 +214,8 @@ int gvm_grad_simt(gvm_engine* e, GvmChannel& c, bool exact, int* ksplit_out);
 int gvm_grad_umma(gvm_engine* e, GvmChannel& c, const float* I_dev, int flag_opt, int normalize,
                   float* result_dev);
 bool gvm_grad_umma_supported(const gvm_engine* e, const GvmChannel& c);
+// grad_gridfft.cu: gradient of gridded samples (cell centres, w = 0) as ONE inverse FFT
+int gvm_grad_gridfft(gvm_engine* e, GvmChannel& c);
 // shared by gradient paths
 int gvm_grad_finish(gvm_engine* e, GvmChannel& c, const float* I_dev, int ksplit, int flag_opt,
                     int normalize, float* result_dev);

@@ -244,9 +244,12 @@ int gvmh_scalars(gvmh_session* s, double* out) {
   out[13] = d.total_visibilities; out[14] = s->opt->getCurrentIteration(); out[15] = (double)s->of->getFi().size();
   return 0;
 }
-int gvmh_stats(gvmh_session* s, double* sec, int64_t* counts) {
+int gvmh_stats(gvmh_session* s, double* sec /* [6] */, int64_t* counts /* [2] */) {
   const MFS::Derived& d = s->mfs->derived();
-  if (sec) { sec[0] = d.setup_seconds; sec[1] = d.weighting_seconds; sec[2] = d.gridding_seconds; sec[3] = d.run_seconds; }
+  if (sec) {
+    sec[0] = d.setup_seconds; sec[1] = d.weighting_seconds; sec[2] = d.gridding_seconds; sec[3] = d.run_seconds;
+    sec[4] = s->of->functionSeconds(); sec[5] = s->of->gradientSeconds();
+  }
   if (counts) { counts[0] = s->of->functionEvaluations(); counts[1] = s->of->gradientEvaluations(); }
   return 0;
 }

@@ -40,7 +40,23 @@ Globals& G();
 // checkCudaErrors convention of the reference (print + exit), applied to the C ABI's
 // int status + gvm_last_error().
 void gvmCheck(int rc, const char* what, const char* file, int line);
-#define GVM_CHECK(call) ::gpuvmem::gvmCheck((call), #call, __FILE__, __LINE__)
+// GVM_PROFILE_HOST=1 in the environment: wall time and call count per C-ABI call site, printed to
+// stderr by hostProfileReport() (MFS::unSetDevice) — a host-side profile without external tools.
+bool hostProfileOn();
+double hostProfileNow();
+void hostProfileAdd(const char* what, double seconds);
+void hostProfileReport();
+#define GVM_CHECK(call)                                                           \
+  do {                                                                            \
+    if (::gpuvmem::hostProfileOn()) {                                             \
+      const double _t0 = ::gpuvmem::hostProfileNow();                             \
+      const int _rc = (call);                                                     \
+      ::gpuvmem::hostProfileAdd(#call, ::gpuvmem::hostProfileNow() - _t0);        \
+      ::gpuvmem::gvmCheck(_rc, #call, __FILE__, __LINE__);                        \
+    } else {                                                                      \
+      ::gpuvmem::gvmCheck((call), #call, __FILE__, __LINE__);                     \
+    }                                                                             \
+  } while (0)
 
 // Device buffers of n floats, zero-filled (cudaMalloc + cudaMemset pairs of the reference).
 float* devAllocFloats(size_t n);

@@ -346,9 +346,6 @@ void MFS::configure(int argc, char** argv) {
 void MFS::doGridding() {
   Globals& g = G();
   ungridded = datasets;
-  const size_t MN = (size_t)g.M * g.N;
-  std::vector<double> uvw_out(3 * MN);
-  std::vector<float> vo_out(2 * MN), w_out(MN);
   for (MSDataset& ds : datasets) {
     int max = 0;
     for (Field& f : ds.fields)
@@ -360,10 +357,12 @@ void MFS::doGridding() {
           GVM_CHECK(gvm_grid_block(g.firstgpu, g.M, g.N, g.deltau, g.deltav, f.nu[i], (int64_t)v.size(),
                                    v.uvw.data(), v.Vo.data(), v.weight.data(), ckernel->getKernelPointer(),
                                    ckernel->getm(), ckernel->getn(), ckernel->getSupportX(),
-                                   ckernel->getSupportY(), uvw_out.data(), vo_out.data(), w_out.data(), &nout));
-          v.uvw.assign(uvw_out.begin(), uvw_out.begin() + 3 * nout);
-          v.Vo.assign(vo_out.begin(), vo_out.begin() + 2 * nout);
-          v.weight.assign(w_out.begin(), w_out.begin() + nout);
+                                   ckernel->getSupportY(), nullptr, nullptr, nullptr, &nout));
+          // the gridded samples replace the block in place (do_gridding, src/functions.cu:1577-1612)
+          v.uvw.resize(3 * nout);
+          v.Vo.resize(2 * nout);
+          v.weight.resize(nout);
+          GVM_CHECK(gvm_grid_fetch(v.uvw.data(), v.Vo.data(), v.weight.data()));
           v.Vm.assign(2 * nout, 0.0f);
           v.Vr.assign(2 * nout, 0.0f);
           f.numVisibilitiesPerFreqPerStoke[i][s] = (long)nout;
@@ -677,6 +676,7 @@ void MFS::writeResiduals() {
 
 void MFS::unSetDevice() {
   Globals& g = G();
+  hostProfileReport();
   if (!g.quiet) std::printf("Freeing device memory\n");
   if (g.engine) {
     devFree(device_Image);

@@ -1,6 +1,12 @@
 #include "objectivefunction.hpp"
 
+#include <chrono>
+
 namespace gpuvmem {
+
+namespace {
+double nowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
 
 ObjectiveFunction::~ObjectiveFunction() {
   if (G().engine) devFree(dphi);
@@ -14,6 +20,7 @@ void ObjectiveFunction::addFi(Fi* fi) {
 }
 
 float ObjectiveFunction::calcFunction(float* p) {
+  const double t0 = nowS();
   float value = 0.0f;
   size_t k = 0;
   for (Fi* fi : fis) {
@@ -22,10 +29,12 @@ float ObjectiveFunction::calcFunction(float* p) {
     value += term;
   }
   n_function++;
+  t_function += nowS() - t0;
   return value;
 }
 
 void ObjectiveFunction::calcGradient(float* p, float* xi, int iter) {
+  const double t0 = nowS();
   if (io && io->getPrintImages()) {
     if (IoOrderIterations) {
       IoOrderIterations(p, io);
@@ -41,7 +50,9 @@ void ObjectiveFunction::calcGradient(float* p, float* xi, int iter) {
     fi->addToDphi(dphi);
   }
   copyDphiToXi(xi);
+  GVM_CHECK(gvm_synchronize(G().engine));
   n_gradient++;
+  t_gradient += nowS() - t0;
 }
 
 void ObjectiveFunction::restartDPhi() {

@@ -33,6 +33,9 @@ class ObjectiveFunction {
   // evaluation counters (bench / statistics block)
   long functionEvaluations() const { return n_function; }
   long gradientEvaluations() const { return n_gradient; }
+  // host wall time spent inside calcFunction / calcGradient (the calls return after the GPU work)
+  double functionSeconds() const { return t_function; }
+  double gradientSeconds() const { return t_gradient; }
 
  private:
   std::vector<Fi*> fis;
@@ -43,6 +46,7 @@ class ObjectiveFunction {
   void (*IoOrderIterations)(float* I, Io* io) = nullptr;
   int image_count = 1;
   long n_function = 0, n_gradient = 0;
+  double t_function = 0.0, t_gradient = 0.0;
 };
 
 }  // namespace gpuvmem

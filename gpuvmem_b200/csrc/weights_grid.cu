@@ -134,8 +134,16 @@ constexpr int kMaxTaps = 17 * 17;
 // One thread per output cell: merge the (<= taps) sorted sample lists of the centre cells whose
 // kernel footprint covers this cell, in ascending sample order, and accumulate exactly like the
 // reference's sequential loop (src/functions.cu:1466-1505), then normalise (:1537-1558).
+// occupancy of the extended grid: count[key]++ for every (sample, twin) centre; an exclusive scan
+// turns it into start[key] = first position of that centre cell in the sorted list
+__global__ void __launch_bounds__(256) k_cell_count(const uint32_t* __restrict__ keys, long n,
+                                                    int* __restrict__ count) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < n && keys[i] != kNoCell) atomicAdd(count + keys[i], 1);
+}
+
 __global__ void __launch_bounds__(128) k_grid_accumulate(
-    const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, long n, long Z,
+    const int* __restrict__ start, const uint32_t* __restrict__ vals, long n, long Z,
     const float2* __restrict__ Vo, const float* __restrict__ w, const float* __restrict__ kernel, int ck_m,
     int ck_n, int sx, int sy, long M, long N, float* __restrict__ out_w, float2* __restrict__ out_V) {
   const long cell = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -145,20 +153,24 @@ __global__ void __launch_bounds__(128) k_grid_accumulate(
   int head[kMaxTaps], tail[kMaxTaps];
   float ckv[kMaxTaps];
   int nl = 0;
-  for (int m = -sy; m <= sy; m++)
+  for (int m = -sy; m <= sy; m++) {
+    // the centres of one footprint row are consecutive keys: one look-up tells whether the row is empty
+    // (most of the uv plane is, so most cells leave after 2 * (2 sy + 1) loads)
+    const long row0 = (long)(gk - m + sy) * EW + gj;   // nn = +sx ... -sx  <->  ej = gj ... gj + 2 sx
+    if (start[row0 + 2L * sx + 1] == start[row0]) continue;
     for (int nn = -sx; nn <= sx; nn++) {
       const int ki = m + sy, kj = nn + sx;
       if (ki < 0 || ki >= ck_m || kj < 0 || kj >= ck_n) continue;
       // centre (k, j) with k + m == gk, j + nn == gj
       const long ek = (long)(gk - m + sy), ej = (long)(gj - nn + sx);
       const uint32_t key = (uint32_t)(ek * EW + ej);
-      const long b = lower_bound_u32(keys, n, key);
-      if (b < n && keys[b] == key) {
-        const long e = lower_bound_u32(keys, n, key + 1);
-        head[nl] = (int)b; tail[nl] = (int)e; ckv[nl] = kernel[ck_n * ki + kj];
+      const int b = start[key], e = start[key + 1];
+      if (e > b) {
+        head[nl] = b; tail[nl] = e; ckv[nl] = kernel[ck_n * ki + kj];
         nl++;
       }
     }
+  }
   float gw = 0.f, gw2 = 0.f, gvr = 0.f, gvi = 0.f;
   while (true) {
     uint32_t best = kNoCell; int bl = -1;
@@ -232,6 +244,13 @@ struct DevBuf {
   }
   template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
+
+// result of the last gvm_grid_block of this thread (device resident until fetched)
+struct GridResult {
+  DevBuf uvw, Vo, w;
+  long count = 0;
+};
+thread_local GridResult g_grid_result;
 
 int sort_pairs(DevBuf& tmp, uint32_t* k_in, uint32_t* k_out, uint32_t* v_in, uint32_t* v_out, long n,
                int end_bit) {
@@ -389,7 +408,10 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
   const size_t ext = (size_t)(M + 2 * support_y) * (size_t)(N + 2 * support_x);
   if (ext >= (size_t)kNoCell || n2 >= (long)0x7FFFFFFF) { gvm_set_error("gvm_grid_block: problem too large"); return 1; }
   *nout = 0;
-  DevBuf d_uvw, d_Vo, d_w, d_ck, d_k0, d_k1, d_v0, d_v1, d_tmp, d_gw, d_gV, d_flags, d_pos, d_uo, d_Vout, d_wo;
+  DevBuf d_uvw, d_Vo, d_w, d_ck, d_k0, d_k1, d_v0, d_v1, d_tmp, d_gw, d_gV, d_flags, d_pos, d_start;
+  GridResult& res = g_grid_result;   // compacted output stays on the device until it is fetched
+  DevBuf &d_uo = res.uvw, &d_Vout = res.Vo, &d_wo = res.w;
+  res.count = 0;
   const size_t zz = (size_t)(Z > 0 ? Z : 1);
   if (d_uvw.ensure(zz * 24) || d_Vo.ensure(zz * 8) || d_w.ensure(zz * 4) || d_ck.ensure((size_t)ck_m * ck_n * 4) ||
       d_k0.ensure(2 * zz * 4) || d_k1.ensure(2 * zz * 4) || d_v0.ensure(2 * zz * 4) || d_v1.ensure(2 * zz * 4) ||
@@ -409,7 +431,20 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
     if (sort_pairs(d_tmp, d_k0.as<uint32_t>(), d_k1.as<uint32_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(), n2, 32))
       return 1;
   }
-  k_grid_accumulate<<<(int)((MN + 127) / 128), 128>>>(d_k1.as<uint32_t>(), d_v1.as<uint32_t>(), n2, (long)Z,
+  // start table over the extended grid (ext + 1 entries): histogram of the centre cells + exclusive scan
+  if (d_start.ensure((ext + 2) * 4)) return 1;
+  WG_CUDA(cudaMemset(d_start.p, 0, (ext + 2) * 4));
+  if (n2 > 0) {
+    k_cell_count<<<(int)((n2 + 255) / 256), 256>>>(d_k1.as<uint32_t>(), n2, d_start.as<int>());
+    WG_CUDA(cudaGetLastError());
+  }
+  {
+    size_t sb = 0;
+    WG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, d_start.as<int>(), d_start.as<int>(), (int)(ext + 1)));
+    if (d_tmp.ensure(sb)) return 1;
+    WG_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, sb, d_start.as<int>(), d_start.as<int>(), (int)(ext + 1)));
+  }
+  k_grid_accumulate<<<(int)((MN + 127) / 128), 128>>>(d_start.as<int>(), d_v1.as<uint32_t>(), n2, (long)Z,
                                                       d_Vo.as<float2>(), d_w.as<float>(), d_ck.as<float>(), ck_m,
                                                       ck_n, support_x, support_y, M, N, d_gw.as<float>(),
                                                       d_gV.as<float2>());
@@ -429,11 +464,23 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
                                                      deltau, deltav, gvm_freq_to_wavelength(freq),
                                                      d_uo.as<double>(), d_Vout.as<float2>(), d_wo.as<float>());
     WG_CUDA(cudaGetLastError());
-    WG_CUDA(cudaMemcpy(uvw_out, d_uo.p, (size_t)count * 24, cudaMemcpyDeviceToHost));
-    WG_CUDA(cudaMemcpy(Vo_out, d_Vout.p, (size_t)count * 8, cudaMemcpyDeviceToHost));
-    WG_CUDA(cudaMemcpy(w_out, d_wo.p, (size_t)count * 4, cudaMemcpyDeviceToHost));
+    WG_CUDA(cudaDeviceSynchronize());
   }
+  res.count = count;
   *nout = count;
+  // outputs may be omitted: the caller sizes its arrays from *nout and calls gvm_grid_fetch
+  if (uvw_out || Vo_out || w_out) return gvm_grid_fetch(uvw_out, Vo_out, w_out);
+  return 0;
+}
+
+int gvm_grid_fetch(double* uvw_out, float* Vo_out, float* w_out) {
+  GridResult& res = g_grid_result;
+  const size_t count = (size_t)res.count;
+  if (count > 0) {
+    if (uvw_out) WG_CUDA(cudaMemcpy(uvw_out, res.uvw.p, count * 24, cudaMemcpyDeviceToHost));
+    if (Vo_out) WG_CUDA(cudaMemcpy(Vo_out, res.Vo.p, count * 8, cudaMemcpyDeviceToHost));
+    if (w_out) WG_CUDA(cudaMemcpy(w_out, res.w.p, count * 4, cudaMemcpyDeviceToHost));
+  }
   return 0;
 }
 

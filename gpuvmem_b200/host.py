@@ -203,11 +203,11 @@ class Session:
         return dict(zip(SCALAR_NAMES, out.tolist()))
 
     def stats(self):
-        sec = np.zeros(4, np.float64)
+        sec = np.zeros(6, np.float64)
         cnt = np.zeros(2, np.int64)
         self.h.gvmh_stats(self.s, sec.ctypes.data, cnt.ctypes.data)
         return dict(setup_s=sec[0], weighting_s=sec[1], gridding_s=sec[2], optimize_s=sec[3],
-                    function_evals=int(cnt[0]), gradient_evals=int(cnt[1]))
+                    function_s=sec[4], gradient_s=sec[5], function_evals=int(cnt[0]), gradient_evals=int(cnt[1]))
 
     def host_vis(self, chan=0):
         n = self.h.gvmh_nvis(self.s, chan)

@@ -190,3 +190,13 @@ def config_c4(scale=1.0, **kw):
     return make_problem(N=4096, nvis=int(50_000_000 * scale), nchan=1, freq0=2.3e11, nant=8,
                         bmin=1.0e6, bmax=1.0e7, telescope="EHT", antenna_diameter=12.0,
                         name="C4-m87-style-vlbi", **kw)
+
+
+def config_c5(scale=1.0, **kw):
+    # gridded-visibility mode: 8192 x 8192 uv grid, 200 M raw visibilities (Briggs R = 0 weighting and the
+    # convolutional gridding happen inside MFS::configure, -g); extended array as in C2 so the field is unmasked
+    kw.setdefault("bmax", 14000.0)
+    kw.setdefault("bmin", 150.0)
+    kw.setdefault("nant", 64)
+    return make_problem(N=8192, nvis=int(200_000_000 * scale), nchan=1, freq0=2.3e11,
+                        name="C5-gridded-8192-200M", **kw)

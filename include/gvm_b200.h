@@ -35,7 +35,9 @@ enum {
   GVM_GRAD_AUTO = 0,
   GVM_GRAD_UMMA = 1,       /* tcgen05 / TMEM, fp16x3 error-compensated split */
   GVM_GRAD_SIMT = 2,       /* separable outer-product on CUDA cores, fp32 */
-  GVM_GRAD_SIMT_EXACT = 3  /* per-pair phase incl. the full w-term (reference formula) */
+  GVM_GRAD_SIMT_EXACT = 3, /* per-pair phase incl. the full w-term (reference formula) */
+  GVM_GRAD_GRIDFFT = 4     /* samples on uv-cell centres with w = 0 (gridded mode, -g): the DFT
+                              is evaluated exactly as one inverse FFT; AUTO picks it when it applies */
 };
 
 /* Globals of the reference that the hot path reads (src/functions.cu:37-71,
@@ -261,6 +263,9 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
                    const float* w, const float* ckernel, int ck_m, int ck_n,
                    int support_x, int support_y, double* uvw_out, float* Vo_out,
                    float* w_out, int64_t* nout);
+/* Two-phase use for large grids: call gvm_grid_block with the three output pointers NULL to get
+ * *nout, size the host arrays, then fetch the gridded samples of that last call (same thread). */
+int gvm_grid_fetch(double* uvw_out, float* Vo_out, float* w_out);
 
 /* ------------------------------------------------------------- telemetry -- */
 /* Number of kernels (ours + cuFFT) launched by the engine since creation. */

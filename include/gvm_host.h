@@ -81,9 +81,9 @@ gvm_engine* gvmh_engine(gvmh_session* s);
 /* out[16]: fg_scale, noise_cut, noise_jypix, nu_0, vis_noise, sum_weights, bmaj_deg, bmin_deg,
  * bpa_deg, deltau, deltav, xobs_pix, yobs_pix, total_visibilities, iterations_done, n_fi */
 int gvmh_scalars(gvmh_session* s, double* out);
-/* timings of the last create/run: setup, weighting, gridding, optimize (seconds); evaluation
- * counters: function evaluations, gradient evaluations */
-int gvmh_stats(gvmh_session* s, double* seconds4, int64_t* counts2);
+/* seconds6: setup, weighting, gridding, optimize (last run), time inside calcFunction, time inside
+ * calcGradient (both cumulative); counts2: function evaluations, gradient evaluations */
+int gvmh_stats(gvmh_session* s, double* seconds6, int64_t* counts2);
 /* the visibilities as the hot path sees them after weighting (+ gridding): per channel */
 int64_t gvmh_nvis(gvmh_session* s, int chan);
 int gvmh_get_host_vis(gvmh_session* s, int chan, double* uvw_m, float* Vo, float* w);

@@ -353,3 +353,96 @@ def test_gridding_empty_and_single(oracle):
                          table, (0, 0))
     assert len(w) == 2, "a sample and its Hermitian twin"
     assert np.allclose(v[:, 0], 1.0) and sorted(v[:, 1].tolist()) == [-2.0, 2.0] and np.allclose(w, 2.0)
+
+
+def test_gridded_gradient_as_fft_vs_direct_sum_and_oracle(oracle):
+    """Gridded samples (do_gridding output: uv-cell centres, w = 0) make the DFT gradient an exact
+    inverse FFT (GVM_GRAD_GRIDFFT, picked automatically). Checked against the direct CUDA-core
+    sum over the same samples and against the fp64 oracle; ungridded data must NOT take it."""
+    torch = _torch()
+    from gpuvmem_b200 import host
+    from gpuvmem_b200.engine import grid_block
+    p = synth.make_problem(N=256, nvis=60000, nchan=1, freq0=2.3e11, seed=17, grid_fill=0.9)
+    du, dv = 1.0 / (p.M * RPDEG_D * p.DELTAX), 1.0 / (p.N * RPDEG_D * p.DELTAY)
+    table, support = host.ckernel_table("Gaussian2D", 7, 7, np.float32(abs(du)), np.float32(abs(dv)))
+    uo, vo, wo = grid_block(p.M, p.N, du, dv, float(p.freqs[0]), p.uvw[0], p.Vo[0], p.w[0], table, support)
+    assert 1000 < len(wo) < p.M * p.N
+    raw_uvw, raw_Vo, raw_w = p.uvw[0], p.Vo[0], p.w[0]
+    p.uvw[0], p.Vo[0], p.w[0] = uo, vo, wo
+    e = Engine.from_problem(p, grad_mode=0)
+    try:
+        I = _test_image(e)
+        I_dev = torch.from_numpy(I).cuda()
+        e.chi2(I_dev)
+        g_fft = torch.zeros_like(I_dev)
+        e.dchi2(I_dev, g_fft, flag_opt=0)
+        assert e.last_grad_mode() == 4, "AUTO must pick the FFT path for gridded samples"
+        e.set_grad_mode(GRAD_SIMT)
+        g_sum = torch.zeros_like(I_dev)
+        e.dchi2(I_dev, g_sum, flag_opt=0)
+        assert e.last_grad_mode() == GRAD_SIMT
+        a, b = g_fft[0].cpu().numpy().astype(np.float64), g_sum[0].cpu().numpy().astype(np.float64)
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) <= 2e-5
+        assert np.array_equal(a == 0, b == 0)
+        rng = np.random.default_rng(6)
+        pix = np.unique(rng.integers(0, p.N * p.N, 500))
+        want = _grad_oracle_sample(oracle, p, e, I_dev.cpu().numpy(), pix, 0)
+        got = g_fft[0].cpu().numpy().reshape(-1)[pix]
+        err = np.linalg.norm(got - want) / np.linalg.norm(want)
+        print(f"\ngridded gradient: FFT vs fp64 oracle {err:.2e}, FFT vs direct fp32 sum "
+              f"{np.linalg.norm(a - b) / np.linalg.norm(b):.2e}, {len(wo)} cells")
+        assert err <= 1e-5, err
+    finally:
+        e.close()
+    # the raw (ungridded) samples are not on cell centres: AUTO keeps the contraction kernels
+    p.uvw[0], p.Vo[0], p.w[0] = raw_uvw, raw_Vo, raw_w
+    e = Engine.from_problem(p, grad_mode=0)
+    try:
+        I_dev = torch.from_numpy(_test_image(e)).cuda()
+        e.chi2(I_dev)
+        g = torch.zeros_like(I_dev)
+        e.dchi2(I_dev, g, flag_opt=0)
+        assert e.last_grad_mode() in (1, 2, 3)
+        e.set_grad_mode(4)                      # forcing it on unsuitable data falls back, never approximates
+        g2 = torch.zeros_like(I_dev)
+        e.dchi2(I_dev, g2, flag_opt=0)
+        assert e.last_grad_mode() in (1, 2, 3)
+    finally:
+        e.close()
+
+
+def test_lbfgs_vector_ops_and_device_pool(small):
+    """The L-BFGS pieces of the C ABI (normArray+max, searchDirection_LBFGS, calculateSandY:
+    src/functions.cu:3564-3653) and the caching device allocator behind gvm_dev_alloc/free."""
+    import ctypes as C
+    torch = _torch()
+    p, e = small
+    L, h = e.lib, e.h
+    n = 2 * p.N * p.N
+    g = torch.Generator(device="cuda").manual_seed(2)
+    xi, xo, pp, po = (torch.randn(n, device="cuda", generator=g) for _ in range(4))
+    out = C.c_float()
+    assert L.gvm_vec_absmax(h, xi.data_ptr(), n, C.byref(out)) == 0
+    assert out.value == float(xi.abs().max())
+    y, s = torch.empty_like(xi), torch.empty_like(xi)
+    assert L.gvm_vec_lbfgs_sy(h, y.data_ptr(), s.data_ptr(), xi.data_ptr(), xo.data_ptr(), pp.data_ptr(), po.data_ptr(), n) == 0
+    e.synchronize()
+    assert torch.equal(y, xi + xo) and torch.equal(s, pp - po)
+    v = xi.clone()
+    assert L.gvm_vec_scale(h, v.data_ptr(), -1.0, n) == 0
+    e.synchronize()
+    assert torch.equal(v, -xi)
+    # pool: a freed block of the same size comes back, zero-filled; foreign pointers are rejected
+    a, b = C.c_void_p(), C.c_void_p()
+    assert L.gvm_dev_alloc(h, 4096, C.byref(a)) == 0
+    host = (C.c_float * 1024)(*([1.5] * 1024))
+    assert L.gvm_dev_copy(h, a, host, 4096, 0) == 0
+    assert L.gvm_dev_free(h, a) == 0
+    assert L.gvm_dev_alloc(h, 4096, C.byref(b)) == 0
+    assert b.value == a.value
+    back = (C.c_float * 1024)()
+    assert L.gvm_dev_copy(h, back, b, 4096, 1) == 0
+    assert not any(back)
+    assert L.gvm_dev_free(h, b) == 0
+    assert L.gvm_dev_free(h, C.c_void_p(xi.data_ptr())) != 0
+    assert b"not allocated" in L.gvm_last_error()
