@@ -286,7 +286,8 @@ int gvm_chi2(gvm_engine* e, float* I_dev, int normalize, float* chi2_out) {
   return 0;
 }
 
-static int pick_grad_mode(gvm_engine* e, GvmChannel& c) {
+}  // extern "C"
+int gvm_pick_grad_mode(gvm_engine* e, GvmChannel& c) {
   int mode = e->cfg.grad_mode;
   if (mode == GVM_GRAD_SIMT_EXACT || mode == GVM_GRAD_SIMT) return mode;
   if (mode == GVM_GRAD_GRIDFFT || (mode == GVM_GRAD_AUTO && c.offgrid == 0)) {
@@ -298,6 +299,7 @@ static int pick_grad_mode(gvm_engine* e, GvmChannel& c) {
   if (!sep_ok) return GVM_GRAD_SIMT_EXACT;
   return gvm_grad_umma_supported(e, c) ? GVM_GRAD_UMMA : GVM_GRAD_SIMT;
 }
+extern "C" {
 
 static __global__ void k_add_inplace(float* __restrict__ dst, const float* __restrict__ src, long n) {
   const long idx = blockIdx.x * 256L + threadIdx.x;
@@ -322,7 +324,7 @@ int gvm_dchi2(gvm_engine* e, const float* I_dev, int flag_opt, int normalize,
     GvmChannel& c = e->chans[s];
     if (c.Z <= 0) continue;
     if (c.slot < 0) { gvm_set_error("gvm_dchi2: call gvm_chi2 first (Vr comes from the forward pass)"); return 1; }
-    const int mode = pick_grad_mode(e, c);
+    const int mode = gvm_pick_grad_mode(e, c);
     e->last_grad_mode = mode;
     if (mode == GVM_GRAD_UMMA) {
       if (gvm_grad_umma(e, c, I_dev, flag_opt, normalize, result_dchi2_dev)) return 1;

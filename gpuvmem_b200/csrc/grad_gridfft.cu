@@ -18,7 +18,7 @@ namespace {
 // one thread per sample: 20 B in (du64, dv64 top words, Vr, w), one 8-byte atomic out
 __global__ void __launch_bounds__(256) k_gridfft_scatter(
     const uint64_t* __restrict__ du64, const uint64_t* __restrict__ dv64, const float2* __restrict__ Vr,
-    const float* __restrict__ w, long Z, int N, int x0, int y0, float2* __restrict__ C) {
+    const float* __restrict__ w, long Z, int N, int x0, int y0, float im_sign, float2* __restrict__ C) {
   const long k = blockIdx.x * 256L + threadIdx.x;
   if (k >= Z) return;
   const float wk = w[k];
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) k_gridfft_scatter(
   float s, c;
   sincospif(-2.0f * (float)r / (float)N, &s, &c);
   const float2 v = Vr[k];
-  const float ar = wk * v.x, ai = -wk * v.y;  // w conj(Vr)
+  const float ar = wk * v.x, ai = -im_sign * wk * v.y;  // w conj(Vr); im_sign = -1 (error maps): w Vr
   float* cell = reinterpret_cast<float*>(C + ((size_t)n * N + m));
   atomicAdd(cell, ar * c - ai * s);
   atomicAdd(cell + 1, ar * s + ai * c);
@@ -55,7 +55,8 @@ int gvm_grad_gridfft(gvm_engine* e, GvmChannel& c) {
   GVM_CUDA(cudaMemsetAsync(e->I_nu, 0, (size_t)MN * sizeof(float2), e->stream));
   gvm_ev_begin(e);
   k_gridfft_scatter<<<(int)((c.Z + 255) / 256), 256, 0, e->stream>>>(
-      c.du64, c.dv64, c.Vr, c.w, c.Z, N, (int)c.d.phs_xobs_pix, (int)c.d.phs_yobs_pix, e->I_nu);
+      c.du64, c.dv64, c.Vr, c.w, c.Z, N, (int)c.d.phs_xobs_pix, (int)c.d.phs_yobs_pix,
+      e->err_variant ? -1.0f : 1.0f, e->I_nu);
   GVM_LAUNCH(e);
   GVM_CUDA(cudaGetLastError());
   if (cufftExecC2C(e->plan, reinterpret_cast<cufftComplex*>(e->I_nu), reinterpret_cast<cufftComplex*>(e->V),

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) k_grad_sep(
     const uint64_t* __restrict__ du64, const uint64_t* __restrict__ dv64,
     const float* __restrict__ wz, const float2* __restrict__ Vr, const float* __restrict__ w,
     const float* __restrict__ gA, const float* __restrict__ gB, long Z, int N, int x0, int y0,
-    long klen, float* __restrict__ scratch) {
+    long klen, float im_sign, float* __restrict__ scratch) {
   __shared__ __align__(16) float2 sP[KC][TJ];
   __shared__ __align__(16) float2 sQ[KC][TI];
   const int tiles_j = (N + TJ - 1) / TJ;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) k_grad_sep(
       if (k < kend) {
         const float wk = __ldg(&w[k]);
         const float2 vr = __ldg(&Vr[k]);
-        const float cr = wk * vr.x, ci = -wk * vr.y;
+        const float cr = wk * vr.x, ci = -im_sign * wk * vr.y;   // im_sign = -1: w Vr (error maps)
         float tu = turns_from_fixed(__ldg(&du64[k]), jg - x0);
         float tv = turns_from_fixed(__ldg(&dv64[k]), ig - y0);
         if (kUseW) {
@@ -308,7 +308,9 @@ int gvm_grad_simt(gvm_engine* e, GvmChannel& c, bool exact, int* ksplit_out) {
   if (gvm_ensure_grad_scratch(e, (size_t)ksplit * N * N)) return 1;
   const int x0 = (int)c.d.phs_xobs_pix, y0 = (int)c.d.phs_yobs_pix;
   dim3 grid(tiles, ksplit);
-  const bool use_w = c.max_abs_wz > 0.f;
+  const bool use_w = c.max_abs_wz > 0.f && !e->err_variant;
+  if (e->err_variant) exact = false;   // no w-term: the separable form is the formula itself
+  const float im_sign = e->err_variant ? -1.0f : 1.0f;
   if (!exact && use_w)
     if (gvm_build_pixtab(e, c)) return 1;
   gvm_ev_begin(e);
@@ -319,11 +321,11 @@ int gvm_grad_simt(gvm_engine* e, GvmChannel& c, bool exact, int* ksplit_out) {
   } else if (use_w) {
     k_grad_sep<true><<<grid, 256, 0, e->stream>>>(c.du64, c.dv64, c.wz, c.Vr, c.w, e->pixtab,
                                                   e->pixtab + N, c.Z, N, x0, y0, klen,
-                                                  e->grad_scratch);
+                                                  im_sign, e->grad_scratch);
   } else {
     k_grad_sep<false><<<grid, 256, 0, e->stream>>>(c.du64, c.dv64, c.wz, c.Vr, c.w, e->pixtab,
                                                    e->pixtab + N, c.Z, N, x0, y0, klen,
-                                                   e->grad_scratch);
+                                                   im_sign, e->grad_scratch);
   }
   gvm_ev_end(e);
   GVM_LAUNCH(e);
@@ -342,6 +344,7 @@ GvmFinishParams gvm_finish_params(gvm_engine* e, const GvmChannel& c, const floa
   p.pb_cutoff = c.d.pb_cutoff; p.freq = c.d.freq; p.xobs = c.d.ref_xobs_pix; p.yobs = c.d.ref_yobs_pix;
   p.nu_0 = g.nu_0; p.threshold = g.threshold; p.DELTAX = g.DELTAX; p.DELTAY = g.DELTAY;
   p.primary_beam = c.d.primary_beam; p.flag_opt = flag_opt; p.normalize = normalize;
+  p.raw = e->err_variant;
   return p;
 }
 

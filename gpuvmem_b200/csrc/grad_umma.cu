@@ -202,7 +202,7 @@ __device__ __forceinline__ void split2(float c, float s, uint32_t& hi, uint32_t&
 // power of two so that the largest amplitude sits near 2^14 (fp16 max is 65504).
 __global__ void __launch_bounds__(256) k_grad_coeff(const float2* __restrict__ Vr,
                                                     const float* __restrict__ w, long Z,
-                                                    const float* __restrict__ max_in,
+                                                    const float* __restrict__ max_in, float im_sign,
                                                     float* __restrict__ inv_scale_out,
                                                     float* __restrict__ amp,
                                                     uint32_t* __restrict__ gam) {
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) k_grad_coeff(const float2* __restrict__ V
   if (k >= Z) return;
   const float wk = w[k];
   const float2 vr = Vr[k];
-  const float re = wk * vr.x, im = wk * vr.y;
+  const float re = wk * vr.x, im = im_sign * wk * vr.y;   // im_sign = -1: error maps
   amp[k] = sqrtf(re * re + im * im) * scale;
   const float t = atan2f(im, re) * 0.15915494309189535f;       // turns in [-0.5, 0.5]
   gam[k] = (uint32_t)(int32_t)__float2int_rn(t * 2147483648.0f) << 1;
@@ -552,7 +552,7 @@ static int build_plan(gvm_engine* e) {
 int gvm_grad_umma(gvm_engine* e, GvmChannel& c, const float* I_dev, int flag_opt, int normalize,
                   float* result_dev) {
   const int N = (int)e->cfg.N;
-  if (!gvm_grad_umma_supported(e, c)) {
+  if (!e->err_variant && !gvm_grad_umma_supported(e, c)) {
     gvm_set_error("gvm_grad_umma: the w-term exceeds 4 turns across the image; use the SIMT kernels");
     return 1;
   }
@@ -573,9 +573,9 @@ int gvm_grad_umma(gvm_engine* e, GvmChannel& c, const float* I_dev, int flag_opt
   }
   float* inv_scale = e->red_max + e->red_slots + c.slot;
   k_grad_coeff<<<(int)((c.Z + 255) / 256), 256, 0, e->stream>>>(c.Vr, c.w, c.Z, e->red_max + c.slot,
-                                                                 inv_scale, c.amp, c.gam);
+                                                                 e->err_variant ? -1.0f : 1.0f, inv_scale, c.amp, c.gam);
   GVM_LAUNCH(e);
-  const bool use_w = c.max_abs_wz > 0.f;
+  const bool use_w = c.max_abs_wz > 0.f && !e->err_variant;
   if (use_w)
     if (gvm_build_pixtab(e, c)) return 1;
 

@@ -103,6 +103,10 @@ struct gvm_engine {
   int rank = 0, world = 1;
   float* dist_grad = nullptr;      // [2][MN] this rank's gradient contribution before the all-reduce
   int64_t collectives = 0;
+  // error maps (errormaps.cu): while set, the gradient contraction runs on w_k Vr_k instead of
+  // w_k conj(Vr_k), without the w-term, and the finishing pass stores the raw sum in `dchi2`
+  // (alpha_Noise, src/functions.cu:4113-4177, is the same direct DFT as DChi2)
+  int err_variant = 0;
   // caller-visible device memory (gvm_dev_alloc/free): a caching pool — cudaMalloc/cudaFree cost
   // 15-45 ms each on a loaded context, and the optimizers allocate work buffers per optimize() call
   std::map<void*, size_t> pool_live;          // pointer -> bytes of every block handed out
@@ -175,9 +179,11 @@ struct GvmFinishParams {
   float fg_scale, D, pb_factor, pb_cutoff, freq, xobs, yobs, nu_0, threshold;
   double DELTAX, DELTAY;
   int primary_beam, flag_opt, normalize;
+  int raw;   // error maps: dchi2_out = raw sum over visibilities, nothing else
 };
 __device__ inline void gvm_finish_pixel(const GvmFinishParams& p, float d, long idx, int i, int j) {
   const long MN = p.M * p.N;
+  if (p.raw) { p.dchi2_out[idx] = d; return; }
   const float atten = gvm_attenuation(i, j, p.D, p.pb_factor, p.pb_cutoff, p.freq, p.xobs, p.yobs,
                                       p.DELTAX, p.DELTAY, p.primary_beam);
   float scale_factor = p.fg_scale * atten;
@@ -226,5 +232,7 @@ double gvm_wterm_cross_bound(const gvm_engine* e, const GvmChannel& c);
 int gvm_dist_allreduce_f32(gvm_engine* e, float* buf, size_t n);
 int gvm_dist_allreduce_f64(gvm_engine* e, double* buf, size_t n);
 void gvm_dist_release(gvm_engine* e);
+// errormaps.cu needs the mode rule of gvm_dchi2
+int gvm_pick_grad_mode(gvm_engine* e, GvmChannel& c);
 void gvm_ev_begin(gvm_engine* e);
 void gvm_ev_end(gvm_engine* e);

@@ -181,6 +181,15 @@ int gvmh_write_outputs(gvmh_session* s) {
   return 0;
 }
 
+int gvmh_error_image(gvmh_session* s, float* errors_host) {
+  Error* est = createObject<Error, std::string>("SecondDerivateError");
+  Image* img = s->sy->getImage();
+  est->calculateErrorImage(img, nullptr);
+  devDownload(errors_host, img->getErrorImage(), imageFloats());
+  delete est;
+  return 0;
+}
+
 int gvmh_set_image(gvmh_session* s, const float* I_host) {
   devUpload(s->sy->getImage()->getImage(), I_host, imageFloats());
   return 0;
@@ -302,6 +311,7 @@ int gvmh_factory_has(const char* kind, const char* name) {
   if (k == "CKernel") return Singleton<Factory<CKernel, std::string>>::Instance().Has(id);
   if (k == "WeightingScheme") return Singleton<Factory<WeightingScheme, std::string>>::Instance().Has(id);
   if (k == "Synthesizer") return Singleton<Factory<Synthesizer, std::string>>::Instance().Has(id);
+  if (k == "Error") return Singleton<Factory<Error, std::string>>::Instance().Has(id);
   if (k == "Io") return Singleton<Factory<Io, std::string>>::Instance().Has(id);
   if (k == "ObjectiveFunction") return Singleton<Factory<ObjectiveFunction, std::string>>::Instance().Has(id);
   return 0;

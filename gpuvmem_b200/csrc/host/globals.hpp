@@ -33,6 +33,7 @@ struct Globals {
   int max_number_vis = 0;
   // one process per GPU: this process's place in the job
   int rank = 0, world = 1;
+  int dist_kind = 0;              // GVM_DIST_*: what this rank's blocks are (set by MFS::shardAndUpload)
   bool quiet = false;             // ranks > 0 stay silent
 };
 Globals& G();

@@ -393,6 +393,7 @@ void MFS::shardAndUpload() {
   Globals& g = G();
   int max_nfreq = 1;
   for (MSDataset& ds : datasets) max_nfreq = std::max(max_nfreq, ds.data.total_frequencies);
+  g.dist_kind = g.world <= 1 ? GVM_DIST_NONE : (max_nfreq >= g.world ? GVM_DIST_BLOCKS : GVM_DIST_CHUNKS);
   for (MSDataset& ds : datasets)
     for (Field& f : ds.fields) {
       f.engine_slot.assign(f.visibilities.size(), std::vector<int>(ds.data.nstokes, -1));
@@ -617,16 +618,40 @@ void MFS::run() {
 
 void MFS::writeImages() {
   Globals& g = G();
-  if (g.rank != 0) return;
-  std::printf("Saving final image to disk\n");
-  if (IoOrderEnd) {
-    IoOrderEnd(image->getImage(), ioImageHandler);
-    return;
+  if (g.rank == 0) {
+    std::printf("Saving final image to disk\n");
+    if (IoOrderEnd) {
+      IoOrderEnd(image->getImage(), ioImageHandler);
+    } else {
+      ioImageHandler->printImage(image->getImage(), out_image, "JY/PIXEL", optimizer->getCurrentIteration(), 0,
+                                 fg_scale, g.M, g.N, true);
+      if (g.print_images)
+        ioImageHandler->printNotNormalizedImage(image->getImage(), "alpha.fits", "", optimizer->getCurrentIteration(), 1, true);
+    }
   }
-  ioImageHandler->printImage(image->getImage(), out_image, "JY/PIXEL", optimizer->getCurrentIteration(), 0,
-                             fg_scale, g.M, g.N, true);
-  if (g.print_images)
-    ioImageHandler->printNotNormalizedImage(image->getImage(), "alpha.fits", "", optimizer->getCurrentIteration(), 1, true);
+  // -E: error images (src/mfs.cu:1090-1113). Every rank takes part: the sums run over its shard.
+  if (g.print_errors) {
+    if (!error) error = createObject<Error, std::string>("SecondDerivateError");
+    if (!g.quiet) std::printf("Calculating Error Images\n");
+    error->calculateErrorImage(image, nullptr);
+    if (g.rank != 0) return;
+    if (IoOrderError) {
+      IoOrderError(image->getErrorImage(), ioImageHandler);
+    } else if (g.print_images) {
+      ioImageHandler->printNotNormalizedImage(image->getErrorImage(), "error_Inu_0.fits", "JY/PIXEL",
+                                              optimizer->getCurrentIteration(), 0, true);
+      ioImageHandler->printNotNormalizedImage(image->getErrorImage(), "error_alpha_0.fits", "",
+                                              optimizer->getCurrentIteration(), 1, true);
+    }
+  }
+}
+
+// calculateErrors (src/functions.cu:4966-5040) uses the residuals Vr the last chi2() left on the
+// device; the error image is allocated here and owned by the Image, as in the reference.
+void SecondDerivateError::calculateErrorImage(Image* I, Visibilities*) {
+  Globals& g = G();
+  if (!I->getErrorImage()) I->setErrorImage(devAllocFloats((size_t)I->getImageCount() * g.M * g.N));
+  GVM_CHECK(gvm_error_maps(g.engine, I->getImage(), g.dist_kind, I->getErrorImage()));
 }
 
 // Residual / model write-back (src/mfs.cu:1115-1155): weights restored, and in gridded mode the
@@ -681,6 +706,7 @@ void MFS::unSetDevice() {
   if (g.engine) {
     devFree(device_Image);
     device_Image = nullptr;
+    if (image && image->getErrorImage()) { devFree(image->getErrorImage()); image->setErrorImage(nullptr); }
     GVM_CHECK(gvm_destroy(g.engine));
     g.engine = nullptr;
   }
@@ -693,6 +719,8 @@ void MFS::unSetDevice() {
 namespace {
 Synthesizer* makeMFS() { return new MFS; }
 const bool kRegistered = registerCreationFunction<Synthesizer, std::string>("MFS", makeMFS);
+Error* makeSecondDerivateError() { return new SecondDerivateError; }
+const bool kRegisteredError = registerCreationFunction<Error, std::string>("SecondDerivateError", makeSecondDerivateError);
 }  // namespace
 
 }  // namespace gpuvmem

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "ckernel.hpp"
+#include "error.hpp"
 #include "factory.hpp"
 #include "image.hpp"
 #include "io.hpp"
@@ -50,6 +51,7 @@ class Synthesizer {
   virtual void clearRun() = 0;
   virtual void writeResiduals() = 0;
 
+  void setError(Error* e) { error = e; }
   void setOptimizator(Optimizer* min) { optimizer = min; }
   void setIoImageHandler(Io* h) { ioImageHandler = h; }
   void setIoVisibilitiesHandler(Io* h) { ioVisibilitiesHandler = h; }
@@ -78,6 +80,7 @@ class Synthesizer {
   Image* image = nullptr;
   Optimizer* optimizer = nullptr;
   CKernel* ckernel = nullptr;
+  Error* error = nullptr;
   Io* ioImageHandler = nullptr;
   Io* ioVisibilitiesHandler = nullptr;
   WeightingScheme* scheme = nullptr;

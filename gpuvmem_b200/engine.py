@@ -209,6 +209,10 @@ class Engine:
     def dchi2(self, I_dev, result_dev, flag_opt=0, normalize=False):
         self._ck(self.lib.gvm_dchi2(self.h, _ptr(I_dev), flag_opt, int(normalize), _ptr(result_dev)))
 
+    def error_maps(self, I_dev, errors_dev, dist_mode=0):
+        """calculateErrors (src/functions.cu:4966-5040): errors_dev [2][M][N] <- (sigma I_nu0, sigma alpha)."""
+        self._ck(self.lib.gvm_error_maps(self.h, _ptr(I_dev), dist_mode, _ptr(errors_dev)))
+
     def eval_host(self, I_host, grad_host, flag_opt=0, normalize=False):
         out = C.c_float()
         self._ck(self.lib.gvm_eval_host(self.h, _ptr(I_host), flag_opt, int(normalize), C.byref(out),

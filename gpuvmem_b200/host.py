@@ -44,6 +44,7 @@ SIGNATURES = {
     "gvmh_clear_run": (C.c_int, [_P]),
     "gvmh_set_lbfgs_k": (C.c_int, [_P, C.c_int]),
     "gvmh_write_outputs": (C.c_int, [_P]),
+    "gvmh_error_image": (C.c_int, [_P, _P]),
     "gvmh_set_image": (C.c_int, [_P, _P]),
     "gvmh_get_image": (C.c_int, [_P, _P]),
     "gvmh_set_iteration": (C.c_int, [_P, C.c_int]),
@@ -154,6 +155,12 @@ class Session:
 
     def write_outputs(self):
         self.h.gvmh_write_outputs(self.s)
+
+    def error_image(self):
+        """Error "SecondDerivateError": (sigma I_nu0, sigma alpha) as [2][M][N]."""
+        out = np.empty((2, self.M, self.N), np.float32)
+        self.h.gvmh_error_image(self.s, out.ctypes.data)
+        return out
 
     # -- objective function ---------------------------------------------------------------
     def set_image(self, I):

@@ -59,6 +59,7 @@ SIGNATURES = {
     "gvm_chi2": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_float)]),
     "gvm_chi2_async": (C.c_int, [_P, _P, C.c_int, _P]),
     "gvm_dchi2": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "gvm_error_maps": (C.c_int, [_P, _P, C.c_int, _P]),
     "gvm_eval_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(C.c_float), _P]),
     "gvm_prior_value": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(gvm_prior_params), C.POINTER(C.c_float)]),
     "gvm_prior_grad": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(gvm_prior_params), C.c_float, _P]),

@@ -143,6 +143,18 @@ int gvm_dchi2(gvm_engine* e, const float* I_dev, int flag_opt, int normalize,
 int gvm_eval_host(gvm_engine* e, const float* I_host, int flag_opt, int normalize,
                   float* chi2_out, float* grad_host);
 
+/* calculateErrors() (src/functions.cu:4966-5040; Error "SecondDerivateError",
+ * src/secondderivateerror.cu:6-10, run by MFS::writeImages under -E,
+ * src/mfs.cu:1090-1113): per block I_nu_0_Noise (:4076) and alpha_Noise (:4113,
+ * a direct DFT over the residuals Vr of the last gvm_chi2 — evaluated on the same
+ * contraction kernels as gvm_dchi2), then noise_reduction (:4179).
+ * errors_dev: [2][M][N], overwritten. dist_mode says what the blocks of a
+ * multi-rank engine are: slices of the same blocks on every rank (sums are
+ * completed per block, every rank gets the full result) or disjoint blocks (one
+ * all-reduce of the accumulated maps). Ignored when world == 1. */
+enum { GVM_DIST_NONE = 0, GVM_DIST_CHUNKS = 1, GVM_DIST_BLOCKS = 2 };
+int gvm_error_maps(gvm_engine* e, const float* I_dev, int dist_mode, float* errors_dev);
+
 /* --------------------------------------------------------------- priors --- */
 enum {
   GVM_PRIOR_ENTROPY = 0,   /* SEntropy/DEntropy  src/functions.cu:4722/4744 */

@@ -64,6 +64,10 @@ int gvmh_run(gvmh_session* s, float* image_out, double* optimize_seconds);
 int gvmh_clear_run(gvmh_session* s);
 int gvmh_set_lbfgs_k(gvmh_session* s, int k);
 int gvmh_write_outputs(gvmh_session* s);   /* writeImages + writeResiduals */
+/* Error "SecondDerivateError" (src/secondderivateerror.cu:6-10 -> calculateErrors,
+ * src/functions.cu:4966-5040) on the session's image and the residuals of the last objective
+ * evaluation; errors_host [2][M][N]: sigma(I_nu0), sigma(alpha). */
+int gvmh_error_image(gvmh_session* s, float* errors_host);
 
 /* ObjectiveFunction::calcFunction / calcGradient on the session's device image. */
 int gvmh_set_image(gvmh_session* s, const float* I_host);

@@ -263,6 +263,56 @@ void gvo_dchi2(long npix, const long* pix, long N, long Z, const double* uvw_l, 
   }
 }
 
+/* One block's contribution to the error maps BEFORE noise_reduction, at the pixels pix[npix]:
+ * I_nu_0_Noise (src/functions.cu:4076-4111) -> acc0[p] += atten^2 * sum_w * (nu/nu0)^(2 alpha)
+ * alpha_Noise  (src/functions.cu:4113-4177) -> acc1[p] += ln^2(nu/nu0) * atten * I_nu * s  if s > 0,
+ *   s = sum_k w_k (atten I_nu + Vr.re cos(2 pi phi) - Vr.im sin(2 pi phi)), phi = x u + y v (no w-term).
+ * Continuous sums in fp64; masked pixels (noise >= noise_cut) are SET to 0 as both kernels do.
+ * fp32_xy != 0 reproduces the reference's `float x, y` and float products Ukv, Vkv (:4133-4160).
+ * calculateErrors (:4966-5040) calls this per (field, channel, stokes) and then noise_reduction
+ * (:4179-4193): e = e > 0 ? 1/sqrt(e) : 0 — see gvo_error_reduce. */
+void gvo_error_accumulate(long npix, const long* pix, long N, long Z, const double* uvw_l, const float* Vr,
+                          const float* w, const float* noise, const float* I, float noise_cut, float D,
+                          float pb_factor, float pb_cutoff, float freq, float nu_0, float ref_xobs,
+                          float ref_yobs, double DELTAX, double DELTAY, int primary_beam, int fp32_xy,
+                          double* acc0, double* acc1) {
+  const long MN = N * N;
+  double sum_w = 0.0;
+  for (long k = 0; k < Z; k++) sum_w += (double)w[k];
+#pragma omp parallel for schedule(dynamic, 4)
+  for (long p = 0; p < npix; p++) {
+    long idx = pix[p];
+    int i = (int)(idx / N), j = (int)(idx % N);
+    if (!(noise[idx] < noise_cut)) { acc0[p] = 0.0; acc1[p] = 0.0; continue; }
+    int x0 = (int)ref_xobs, y0 = (int)ref_yobs;
+    double x = (j - x0) * DELTAX * GVO_RPDEG_D;
+    double y = (i - y0) * DELTAY * GVO_RPDEG_D;
+    if (fp32_xy) { x = (double)(float)x; y = (double)(float)y; }
+    float atten = gvo_attenuation(i, j, D, pb_factor, pb_cutoff, freq, ref_xobs, ref_yobs, DELTAX,
+                                  DELTAY, primary_beam);
+    float nudiv = freq / nu_0;
+    double alpha = (double)I[MN + idx], I0 = (double)I[idx];
+    double I_nu = I0 * pow((double)nudiv, alpha);
+    double log_nu = log((double)nudiv);
+    acc0[p] += (double)atten * (double)atten * sum_w * pow((double)nudiv, 2.0 * alpha);
+    double d = 0.0;
+    for (long k = 0; k < Z; k++) {
+      double ukv = x * uvw_l[3 * k], vkv = y * uvw_l[3 * k + 1];
+      if (fp32_xy) { ukv = (double)(float)ukv; vkv = (double)(float)vkv; }
+      double phase = 2.0 * (ukv + vkv);
+      if (fp32_xy) phase = (double)(float)phase;
+      phase -= 2.0 * floor(phase * 0.5);
+      double c = cos(GVO_PI_D * phase), sn = sin(GVO_PI_D * phase);
+      d += (double)w[k] * ((double)Vr[2 * k] * c - (double)Vr[2 * k + 1] * sn);
+    }
+    double s = (double)atten * I_nu * sum_w + d;
+    if (s > 0.0) acc1[p] += log_nu * log_nu * (double)atten * I_nu * s;
+  }
+}
+void gvo_error_reduce(long n, double* acc) {
+  for (long p = 0; p < n; p++) acc[p] = acc[p] > 0.0 ? 1.0 / sqrt(acc[p]) : 0.0;
+}
+
 /* DChi2_total_I_nu_0 (:4000) / DChi2_total_alpha (:3968): multiplier applied to
  * dchi2 at pixel idx for image (flag_opt % 2). */
 double gvo_chain(const float* I, long MN, long idx, float nu, float nu_0, float fg_scale,

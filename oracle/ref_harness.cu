@@ -556,6 +556,17 @@ int gvref_run(float* image_out, float* wall_ms) {
   return g_opt->getCurrentIteration();
 }
 
+/* calculateErrors (src/functions.cu:4966-5040) on the current device image and the residuals
+ * of the last chi2(); out: image_count*M*N floats (error_Inu_0, error_alpha). */
+int gvref_error_image(float* out) {
+  Image* img = g_sy->getImage();
+  calculateErrors(img);
+  cudaMemcpy(out, img->getErrorImage(), sizeof(float) * M * N * image_count, cudaMemcpyDeviceToHost);
+  cudaFree(img->getErrorImage());
+  img->setErrorImage(nullptr);
+  return 0;
+}
+
 int gvref_set_lbfgs_k(int k) { g_opt->setK(k); return 0; }
 void gvref_set_verbose(int v) { verbose_flag = v != 0; }
 

@@ -48,6 +48,9 @@ class Oracle:
         L.gvo_degrid_chi2.restype = C.c_double
         L.gvo_dchi2.argtypes = [C.c_long, i64p, C.c_long, C.c_long, f64p, f32p, f32p, f32p, _V] + \
                                [C.c_float] * 10 + [C.c_double] * 2 + [C.c_int] * 3 + [f64p]
+        L.gvo_error_accumulate.argtypes = [C.c_long, i64p, C.c_long, C.c_long, f64p, f32p, f32p, f32p, f32p] + \
+                                          [C.c_float] * 8 + [C.c_double] * 2 + [C.c_int] * 2 + [f64p, f64p]
+        L.gvo_error_reduce.argtypes = [C.c_long, f64p]
         L.gvo_chain.argtypes = [f32p, C.c_long, C.c_long, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]
         L.gvo_chain.restype = C.c_double
         L.gvo_prior_value.argtypes = [C.c_int, f32p, f32p, _V, C.c_long] + [C.c_float] * 5
@@ -112,6 +115,20 @@ class Oracle:
                            nu, meta["xpix"], meta["ypix"], meta["xpix"], meta["ypix"],
                            cfg["DELTAX"], cfg["DELTAY"], meta["primary_beam"], normalize, fp32_phase, out)
         return out
+
+    def error_maps(self, pix, N, blocks, noise, I, meta, cfg, fp32_xy=0):
+        """calculateErrors at the pixels `pix`: blocks = [(uvw_lambda, Vr, w, nu), ...]; returns (err_I, err_alpha)."""
+        pix = np.ascontiguousarray(pix, np.int64)
+        a0, a1 = np.zeros(len(pix)), np.zeros(len(pix))
+        for uvw_l, Vr, w, nu in blocks:
+            self.lib.gvo_error_accumulate(len(pix), pix, N, len(w), np.ascontiguousarray(uvw_l), np.ascontiguousarray(Vr),
+                                          np.ascontiguousarray(w), np.ascontiguousarray(noise.reshape(-1), np.float32),
+                                          np.ascontiguousarray(I.reshape(-1), np.float32), meta["noise_cut"], cfg["D"],
+                                          meta["pb_factor"], meta["pb_cutoff"], nu, meta["nu_0"], meta["xpix"], meta["ypix"],
+                                          cfg["DELTAX"], cfg["DELTAY"], int(meta["primary_beam"]), fp32_xy, a0, a1)
+        self.lib.gvo_error_reduce(len(pix), a0)
+        self.lib.gvo_error_reduce(len(pix), a1)
+        return a0, a1
 
     def chain(self, I, idx, nu, meta, threshold, flag_opt):
         MN = I.shape[1] * I.shape[2]
@@ -204,6 +221,8 @@ class GvRef:
         L.gvref_time_evals.argtypes = [C.c_int, C.c_int, C.c_int]
         L.gvref_run.argtypes = [_V, C.POINTER(C.c_float)]
         L.gvref_set_lbfgs_k.argtypes = [C.c_int]
+        if hasattr(L, "gvref_error_image"):
+            L.gvref_error_image.argtypes = [f32p]
         L.gvref_set_verbose.argtypes = [C.c_int]
         self.problem = None
 
@@ -298,6 +317,12 @@ class GvRef:
         p = self.problem
         out = np.empty(2 * p.M * p.N, np.float32)
         self.lib.gvref_calc_gradient(iteration, flag, out)
+        return out.reshape(2, p.M, p.N)
+
+    def error_image(self):
+        p = self.problem
+        out = np.empty(2 * p.M * p.N, np.float32)
+        self.lib.gvref_error_image(out)
         return out.reshape(2, p.M, p.N)
 
     def time_evals(self, n, iteration=0, flag=0):

@@ -36,11 +36,12 @@ def main():
     s.set_iteration(1)
     v, fi = s.calc_function()
     g = s.calc_gradient(1)
+    err = s.error_image()      # SecondDerivateError on the residuals of that evaluation
     s.set_image(start)
     s.set_iteration(0)
     img, sec = s.run()
     if rank == 0:
-        np.savez(out, value=v, fi=fi, grad=g, image=img, local_nvis=s.local_nvis(), collectives=s.collectives(),
+        np.savez(out, value=v, fi=fi, grad=g, image=img, err=err, local_nvis=s.local_nvis(), collectives=s.collectives(),
                  world=world)
     s.close()
     if world > 1:

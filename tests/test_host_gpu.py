@@ -88,6 +88,17 @@ def test_scenario_matches_reference(name, refdir):
         assert np.array_equal(s.get_image(), ref["probe_image_after"]), "clip2IWNoise side effect"
         assert _rel(g[0], ref["probe_grad"][0]) <= 1e-4, _rel(g[0], ref["probe_grad"][0])
         assert np.array_equal(g[0] == 0, ref["probe_grad"][0] == 0), "masked pixels must be exactly 0"
+        # -- Error "SecondDerivateError" (calculateErrors) on the same residuals ------------
+        if "probe_err" in ref.files:
+            err, rerr = s.error_image(), ref["probe_err"]
+            assert np.array_equal(err[0] == 0, rerr[0] == 0)
+            assert _rel(err[0], rerr[0]) <= 2e-5, _rel(err[0], rerr[0])
+            both = (err[1] > 0) & (rerr[1] > 0)
+            assert np.count_nonzero((err[1] > 0) != (rerr[1] > 0)) <= 0.02 * max(both.sum(), 50)
+            if both.any():   # single-channel scenarios have ln(nu/nu0) = 0: sigma(alpha) is 0 everywhere
+                med = float(np.median(np.abs(err[1][both] - rerr[1][both]) / rerr[1][both]))
+                print(f"\n[{name}] error maps: sigma(I) rel-L2 {_rel(err[0], rerr[0]):.2e}, sigma(alpha) median rel {med:.2e}")
+                assert med <= 1e-3, med
         # -- the optimizer: image after N iterations ---------------------------------------
         s.set_image(ref["I_start"])
         s.set_iteration(0)

@@ -50,5 +50,14 @@ def test_sharded_run_matches_single_gpu(tmp_path, nchan):
     assert _rel(two["grad"][0], one["grad"][0]) <= 1e-4
     assert np.array_equal(two["grad"][1] == 0, one["grad"][1] == 0)        # flag_opt 0: no alpha gradient
     assert _rel(two["image"][0], one["image"][0]) <= 2e-3
+    # error maps (calculateErrors): chunks complete the per-block sums first, channels all-reduce the maps
+    assert np.array_equal(two["err"][0] == 0, one["err"][0] == 0)
+    assert _rel(two["err"][0], one["err"][0]) <= 1e-5
+    both = (two["err"][1] > 0) & (one["err"][1] > 0)
+    if nchan > 1:
+        assert both.sum() > 100
+    assert np.count_nonzero((two["err"][1] > 0) != (one["err"][1] > 0)) <= 0.02 * max(both.sum(), 50)
+    if both.any():
+        assert np.median(np.abs(two["err"][1][both] - one["err"][1][both]) / one["err"][1][both]) <= 1e-4
     print(f"\n[nchan={nchan}] grad rel-L2 {_rel(two['grad'][0], one['grad'][0]):.2e}, final image rel-L2 "
           f"{_rel(two['image'][0], one['image'][0]):.2e}, collectives {int(two['collectives'])}")

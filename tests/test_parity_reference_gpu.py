@@ -182,3 +182,41 @@ def test_reference_distance_to_fp64_truth(setup, oracle):
         f.write(f"N={p.N} Z={p.total_vis()} mode={e.last_grad_mode()} ref_vs_fp64={err_ref:.4e} engine_vs_fp64={err_mine:.4e}\n")
     assert err_ref <= 1e-4
     assert err_mine <= max(2e-5, err_ref)
+
+
+def test_error_maps_match_reference(setup, oracle):
+    """calculateErrors of the reference build (src/functions.cu:4966-5040) on the same image and
+    residuals. sigma(I_nu0) is image-sized fp32 arithmetic (rel 2e-5). In alpha_Noise the reference
+    rounds x, y and the products x*u, y*v to FLOAT (:4133-4160; ~1e-5 turns at |x u| ~ 100), and sums
+    Z terms sequentially in fp32, so it is compared at the level its own rounding allows and both
+    are placed against the fp64 oracle (which can mimic those float roundings)."""
+    p, e, ref, torch = setup
+    if not hasattr(ref.lib, "gvref_error_image"):
+        pytest.skip("oracle/_ref/libgvref.so predates gvref_error_image")
+    I = _image(e)
+    ref.set_image(I)
+    ref.calc_function(iteration=0)
+    want = ref.error_image().reshape(2, -1)
+    I_dev = torch.from_numpy(I).cuda()
+    e.chi2(I_dev)
+    err = torch.empty_like(I_dev)
+    e.error_maps(I_dev, err)
+    got = err.cpu().numpy().reshape(2, -1)
+    assert np.array_equal(got[0] == 0, want[0] == 0)
+    nz = want[0] > 0
+    np.testing.assert_allclose(got[0][nz], want[0][nz], rtol=2e-5)
+    both = (got[1] > 0) & (want[1] > 0)
+    assert both.sum() > 0.5 * max((want[1] > 0).sum(), 1)
+    assert np.count_nonzero((got[1] > 0) != (want[1] > 0)) <= 0.02 * both.sum()
+    rel = np.abs(got[1][both] - want[1][both]) / want[1][both]
+    from test_parity_gpu import _cfg, _error_blocks
+    pix = np.flatnonzero(both)[::53]
+    Ic = I_dev.cpu().numpy()
+    t0, t1 = oracle.error_maps(pix, p.N, _error_blocks(p, e), e.get_noise_image(), Ic, e.meta, _cfg(p))
+    ok = t1 > 0
+    r_ref = np.abs(want[1][pix][ok] - t1[ok]) / t1[ok]
+    r_me = np.abs(got[1][pix][ok] - t1[ok]) / t1[ok]
+    print(f"\n[error maps] sigma(alpha) median rel. distance: engine-reference {np.median(rel):.2e}, "
+          f"reference-fp64 {np.median(r_ref):.2e}, engine-fp64 {np.median(r_me):.2e}")
+    assert np.median(rel) <= 1e-3
+    assert np.median(r_me) <= max(2e-5, np.median(r_ref))
