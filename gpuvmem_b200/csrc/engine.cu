@@ -117,6 +117,7 @@ int gvm_destroy(gvm_engine* e) {
   for (auto& c : e->chans) free_channel(c);
   if (e->have_plan) cufftDestroy(e->plan);
   cudaFree(e->I_nu); cudaFree(e->V); cudaFree(e->noise); cudaFree(e->gcf); cudaFree(e->dchi2);
+  cudaFree(e->degrid_table);
   cudaFree(e->grad_scratch); cudaFree(e->pixtab); cudaFree(e->I_stage); cudaFree(e->grad_stage);
   cudaFree(e->red_partials); cudaFree(e->red_counter); cudaFree(e->red_sum); cudaFree(e->red_Z);
   cudaFree(e->red_max); cudaFree(e->red_out); cudaFreeHost(e->h_red); cudaFree(e->tile_counter);
@@ -174,6 +175,32 @@ int gvm_set_gcf(gvm_engine* e, const float* gcf_host) {
   if (!gcf_host) { cudaFree(e->gcf); e->gcf = nullptr; return 0; }
   if (!e->gcf) GVM_CUDA(cudaMalloc(&e->gcf, MN * sizeof(float)));
   GVM_CUDA(cudaMemcpyAsync(e->gcf, gcf_host, MN * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int gvm_set_degrid_kernel(gvm_engine* e, const float* table_host, int m, int n, int support_x, int support_y) {
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(e->degrid_table);
+  e->degrid_table = nullptr;
+  if (!table_host) return 0;                      // back to the bilinear vis_mod
+  if (m < 1 || n < 1 || m * n > GVM_MAX_CKERNEL || support_x < 0 || support_y < 0 ||
+      2 * support_y + 1 > m || 2 * support_x + 1 > n) {
+    gvm_set_error("gvm_set_degrid_kernel: table %dx%d with supports (%d, %d) is not usable (max %d entries)", m, n,
+                  support_x, support_y, GVM_MAX_CKERNEL);
+    return 1;
+  }
+  GVM_CUDA(cudaMalloc(&e->degrid_table, (size_t)m * n * sizeof(float)));
+  GVM_CUDA(cudaMemcpy(e->degrid_table, table_host, (size_t)m * n * sizeof(float), cudaMemcpyHostToDevice));
+  e->degrid_m = m; e->degrid_n = n; e->degrid_sx = support_x; e->degrid_sy = support_y;
+  return 0;
+}
+
+int gvm_get_model_grid(gvm_engine* e, float* V_host) {
+  const size_t MN = (size_t)e->cfg.M * e->cfg.N;
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  GVM_CUDA(cudaMemcpyAsync(V_host, e->V, MN * sizeof(float2), cudaMemcpyDeviceToHost, e->stream));
   GVM_CUDA(cudaStreamSynchronize(e->stream));
   return 0;
 }

@@ -102,6 +102,7 @@ extern "C" int gvm_error_maps(gvm_engine* e, const float* I_dev, int dist_mode, 
     e->err_variant = 1;
     int rc = 0;
     const int mode = gvm_pick_grad_mode(e, c);
+    e->last_grad_mode = mode;
     if (mode == GVM_GRAD_GRIDFFT) {
       rc = gvm_grad_gridfft(e, c) || gvm_grad_finish(e, c, I_dev, 1, 0, 0, nullptr);
     } else if (mode == GVM_GRAD_SIMT || mode == GVM_GRAD_SIMT_EXACT) {

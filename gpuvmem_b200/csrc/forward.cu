@@ -148,16 +148,38 @@ __global__ void __launch_bounds__(256) k_phase_rotate(float2* __restrict__ data,
 // vis_mod (dynamic part, src/functions.cu:2588-2606) + residual (:2663) +
 // chi2Vector (:2867) + first reduction level. Each thread handles kVisPerThread
 // consecutive-by-stride samples so that every load is coalesced.
-template <bool kKeepVm>
+//
+// kConv: the model visibility is a convolutional-kernel degridding of the same grid instead of
+// the bilinear vis_mod — the forward-model option the reference sketches in degriddingGPU
+// (src/functions.cu:2205-2254, never launched): nearest cell j = int(u/deltau + N/2 + 0.5),
+// k likewise (:2222-2223), Vm = sum over taps [-sy, sy] x [-sx, sx] of kernel[kn*(m+sy) + (n+sx)] *
+// V_g[cell + tap], taps outside the centred grid skipped (:2231-2232). degriddingGPU reads a
+// CENTRED grid and folds its left half through the Hermitian twin (:2235-2243); the engine's
+// grid is the full plane with DC at [0,0] (cuFFT output, no shift), so the same cell is read
+// directly at ((j - N/2) mod N, (k - M/2) mod N) — identical for the Hermitian grid of a real image.
+struct GvmConvDegrid {
+  const double* uvw_l;   // [Z][3] wavelengths (after the fold)
+  const float* table;    // [km][kn] kernel, device
+  double deltau, deltav;
+  int km, kn, sx, sy;
+};
+
+template <bool kKeepVm, bool kConv>
 __global__ void __launch_bounds__(kVisThreads) k_degrid_chi2(
     const float2* __restrict__ V, const uint32_t* __restrict__ cell,
     const float2* __restrict__ frac, const float2* __restrict__ Vo, const float* __restrict__ w,
     float2* __restrict__ Vr, float2* __restrict__ Vm, long Z, int N,
     double* __restrict__ partials, float* __restrict__ partial_max,
-    unsigned int* __restrict__ counter, double* __restrict__ out_sum, float* __restrict__ out_max) {
+    unsigned int* __restrict__ counter, double* __restrict__ out_sum, float* __restrict__ out_max,
+    GvmConvDegrid cv) {
   __shared__ float s_sum[kVisThreads / 32];
   __shared__ float s_max[kVisThreads / 32];
   __shared__ bool s_last;
+  __shared__ float s_tab[kConv ? GVM_MAX_CKERNEL : 1];
+  if (kConv) {
+    for (int t = threadIdx.x; t < cv.km * cv.kn; t += blockDim.x) s_tab[t] = cv.table[t];
+    __syncthreads();
+  }
   float acc = 0.f, mx = 0.f;
   const long stride = (long)gridDim.x * blockDim.x;
   for (long k = blockIdx.x * (long)blockDim.x + threadIdx.x; k < Z; k += stride) {
@@ -166,7 +188,25 @@ __global__ void __launch_bounds__(kVisThreads) k_degrid_chi2(
     const float2 vo = __ldg(&Vo[k]);
     const float wk = __ldg(&w[k]);
     float2 vm = make_float2(0.f, 0.f);
-    if (c != GVM_CELL_INVALID) {
+    if (kConv) {
+      const int half = N / 2;
+      const int jc = (int)(cv.uvw_l[3 * k] / cv.deltau + (double)half + 0.5);
+      const int kc = (int)(cv.uvw_l[3 * k + 1] / cv.deltav + (double)half + 0.5);
+      for (int m = -cv.sy; m <= cv.sy; m++) {
+        const int sk = kc + m;
+        if (sk < 0 || sk >= N) continue;
+        const int row = sk >= half ? sk - half : sk + N - half;      // (sk - N/2) mod N
+        for (int n = -cv.sx; n <= cv.sx; n++) {
+          const int sj = jc + n;
+          if (sj < 0 || sj >= N) continue;
+          const int col = sj >= half ? sj - half : sj + N - half;
+          const float kv = s_tab[cv.kn * (m + cv.sy) + (n + cv.sx)];
+          const float2 g = __ldg(&V[(long)N * row + col]);
+          vm.x += kv * g.x;
+          vm.y += kv * g.y;
+        }
+      }
+    } else if (c != GVM_CELL_INVALID) {
       const int i1 = (int)(c & 0xFFFFu), j1 = (int)(c >> 16);
       const int i2 = (i1 + 1 == N) ? 0 : i1 + 1;
       const int j2 = (j1 + 1 == N) ? 0 : j1 + 1;
@@ -300,14 +340,20 @@ int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, 
   float* pmax = reinterpret_cast<float*>(e->red_partials + (size_t)e->red_slots * e->red_blocks) +
                 (size_t)slot * e->red_blocks;
   if (c.Z > 0) {
-    if (g.keep_vm)
-      k_degrid_chi2<true><<<blocks, kVisThreads, 0, e->stream>>>(
-          e->V, c.cell, c.frac, c.Vo, c.w, c.Vr, c.Vm, c.Z, (int)g.N, partials, pmax,
-          e->red_counter + slot, e->red_sum + slot, e->red_max + slot);
-    else
-      k_degrid_chi2<false><<<blocks, kVisThreads, 0, e->stream>>>(
-          e->V, c.cell, c.frac, c.Vo, c.w, c.Vr, nullptr, c.Z, (int)g.N, partials, pmax,
-          e->red_counter + slot, e->red_sum + slot, e->red_max + slot);
+    GvmConvDegrid cv = {};
+    if (e->degrid_table) {
+      const double deltax = GVM_RPDEG_D * g.DELTAX, deltay = GVM_RPDEG_D * g.DELTAY;
+      cv.uvw_l = c.uvw_l; cv.table = e->degrid_table;
+      cv.deltau = 1.0 / (g.M * deltax); cv.deltav = 1.0 / (g.N * deltay);
+      cv.km = e->degrid_m; cv.kn = e->degrid_n; cv.sx = e->degrid_sx; cv.sy = e->degrid_sy;
+    }
+#define GVM_DEGRID(KEEP, CONV)                                                                     \
+  k_degrid_chi2<KEEP, CONV><<<blocks, kVisThreads, 0, e->stream>>>(                                \
+      e->V, c.cell, c.frac, c.Vo, c.w, c.Vr, KEEP ? c.Vm : nullptr, c.Z, (int)g.N, partials, pmax, \
+      e->red_counter + slot, e->red_sum + slot, e->red_max + slot, cv)
+    if (e->degrid_table) { if (g.keep_vm) GVM_DEGRID(true, true); else GVM_DEGRID(false, true); }
+    else                 { if (g.keep_vm) GVM_DEGRID(true, false); else GVM_DEGRID(false, false); }
+#undef GVM_DEGRID
     GVM_LAUNCH(e);
   }
   c.slot = slot;

@@ -18,6 +18,7 @@
 #define GVM_LIGHTSPEED 2.99792458E8f             // include/MSFITSIO.cuh:54
 #define GVM_RZ 1.2196698912665045f               // include/functions.cuh:23 (stored as float)
 #define GVM_CELL_INVALID 0xFFFFFFFFu
+#define GVM_MAX_CKERNEL 1024                     // floats of a convolution-kernel table kept in shared memory
 
 void gvm_set_error(const char* fmt, ...);
 
@@ -66,6 +67,9 @@ struct gvm_engine {
   float2* V = nullptr;      // [MN] complex
   float* noise = nullptr;   // [MN]
   float* gcf = nullptr;     // [MN] or null
+  // optional convolutional degridding in the forward model (gvm_set_degrid_kernel); null = bilinear vis_mod
+  float* degrid_table = nullptr;
+  int degrid_m = 0, degrid_n = 0, degrid_sx = 0, degrid_sy = 0;
   float* dchi2 = nullptr;   // [MN] per-channel gradient before the chain rule
   float* grad_scratch = nullptr;  // [ksplit][MN] partial sums
   size_t grad_scratch_floats = 0;

@@ -345,20 +345,37 @@ void MFS::configure(int argc, char** argv) {
 // gvm_grid_block; the originals are kept for the residual write-back.
 void MFS::doGridding() {
   Globals& g = G();
-  ungridded = datasets;
-  for (MSDataset& ds : datasets) {
+  // The originals move aside (no copy: they can be gigabytes); the gridded samples go into shells
+  // that carry the same metadata (do_gridding replaces the block, src/functions.cu:1577-1612).
+  ungridded = std::move(datasets);
+  datasets.clear();
+  for (MSDataset& src : ungridded) {
+    datasets.emplace_back();
+    MSDataset& ds = datasets.back();
+    ds.name = src.name; ds.oname = src.oname; ds.antennas = src.antennas; ds.data = src.data;
     int max = 0;
-    for (Field& f : ds.fields)
-      for (size_t i = 0; i < f.visibilities.size(); i++) {
+    for (Field& sf : src.fields) {
+      ds.fields.emplace_back();
+      Field& f = ds.fields.back();
+      f.id = sf.id; f.valid_frequencies = sf.valid_frequencies;
+      f.ref_ra = sf.ref_ra; f.ref_dec = sf.ref_dec; f.phs_ra = sf.phs_ra; f.phs_dec = sf.phs_dec;
+      f.ref_xobs_pix = sf.ref_xobs_pix; f.ref_yobs_pix = sf.ref_yobs_pix;
+      f.phs_xobs_pix = sf.phs_xobs_pix; f.phs_yobs_pix = sf.phs_yobs_pix;
+      f.nu = sf.nu;
+      f.numVisibilitiesPerFreqPerStoke = sf.numVisibilitiesPerFreqPerStoke;
+      f.numVisibilitiesPerFreq = sf.numVisibilitiesPerFreq;
+      f.visibilities.resize(sf.visibilities.size());
+      for (size_t i = 0; i < sf.visibilities.size(); i++) {
         long per_freq = 0;
-        for (size_t s = 0; s < f.visibilities[i].size(); s++) {
+        f.visibilities[i].resize(sf.visibilities[i].size());
+        for (size_t s = 0; s < sf.visibilities[i].size(); s++) {
+          const HVis& in = sf.visibilities[i][s];
           HVis& v = f.visibilities[i][s];
           int64_t nout = 0;
-          GVM_CHECK(gvm_grid_block(g.firstgpu, g.M, g.N, g.deltau, g.deltav, f.nu[i], (int64_t)v.size(),
-                                   v.uvw.data(), v.Vo.data(), v.weight.data(), ckernel->getKernelPointer(),
+          GVM_CHECK(gvm_grid_block(g.firstgpu, g.M, g.N, g.deltau, g.deltav, f.nu[i], (int64_t)in.size(),
+                                   in.uvw.data(), in.Vo.data(), in.weight.data(), ckernel->getKernelPointer(),
                                    ckernel->getm(), ckernel->getn(), ckernel->getSupportX(),
                                    ckernel->getSupportY(), nullptr, nullptr, nullptr, &nout));
-          // the gridded samples replace the block in place (do_gridding, src/functions.cu:1577-1612)
           v.uvw.resize(3 * nout);
           v.Vo.resize(2 * nout);
           v.weight.resize(nout);
@@ -371,8 +388,10 @@ void MFS::doGridding() {
         }
         f.numVisibilitiesPerFreq[i] = per_freq;
       }
+    }
     ds.data.max_number_visibilities_in_channel_and_stokes = max;
   }
+  GVM_CHECK(gvm_grid_release());   // the gridding work buffers (several GB at C5) go back before the engine uploads
 }
 
 bool shardRange(int max_nfreq, int chan, size_t Z, int rank, int world, size_t* lo, size_t* hi) {
@@ -661,8 +680,9 @@ void MFS::writeResiduals() {
   Globals& g = G();
   if (!g.quiet) std::printf("Transferring residuals to host memory\n");
   Fi* chi2 = optimizer->getObjectiveFunction()->getFiByName("Chi2");
-  if (gridding) {
-    datasets = ungridded;
+  if (gridding && !ungridded.empty()) {
+    datasets = std::move(ungridded);   // the originals come back (no copy); a second call finds them in place
+    ungridded.clear();
     scheme->restoreWeights(datasets);
     GVM_CHECK(gvm_clear_channels(g.engine));
     GVM_CHECK(gvm_set_gcf(g.engine, nullptr));

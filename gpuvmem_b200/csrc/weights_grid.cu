@@ -150,7 +150,11 @@ __global__ void __launch_bounds__(128) k_grid_accumulate(
   if (cell >= M * N) return;
   const int gk = (int)(cell / N), gj = (int)(cell % N);
   const long EW = N + 2L * sx;
+  // per-thread lists live in local memory, indexed identically across the warp while scanning
+  // (coalesced); hz caches the sample index at the head of every list so that one merge step
+  // costs nl local loads + ONE global load instead of nl scattered global loads
   int head[kMaxTaps], tail[kMaxTaps];
+  uint32_t hz[kMaxTaps];
   float ckv[kMaxTaps];
   int nl = 0;
   for (int m = -sy; m <= sy; m++) {
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(128) k_grid_accumulate(
       const uint32_t key = (uint32_t)(ek * EW + ej);
       const int b = start[key], e = start[key + 1];
       if (e > b) {
-        head[nl] = b; tail[nl] = e; ckv[nl] = kernel[ck_n * ki + kj];
+        head[nl] = b; tail[nl] = e; ckv[nl] = kernel[ck_n * ki + kj]; hz[nl] = vals[b];
         nl++;
       }
     }
@@ -174,13 +178,13 @@ __global__ void __launch_bounds__(128) k_grid_accumulate(
   float gw = 0.f, gw2 = 0.f, gvr = 0.f, gvi = 0.f;
   while (true) {
     uint32_t best = kNoCell; int bl = -1;
-    for (int l = 0; l < nl; l++)
-      if (head[l] < tail[l]) {
-        const uint32_t z = vals[head[l]];
-        if (z < best) { best = z; bl = l; }
-      }
+    for (int l = 0; l < nl; l++) {
+      const uint32_t z = hz[l];
+      if (z < best) { best = z; bl = l; }
+    }
     if (bl < 0) break;
-    head[bl]++;
+    const int nh = ++head[bl];
+    hz[bl] = nh < tail[bl] ? vals[nh] : kNoCell;
     const long vi = (best < (uint32_t)Z) ? (long)best : (long)best - Z;
     const float wt = w[vi];
     float2 vo = Vo[vi];
@@ -235,6 +239,13 @@ struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
   ~DevBuf() { cudaFree(p); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { cudaFree(p); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    return *this;
+  }
   int ensure(size_t n) {
     if (n <= bytes) return 0;
     cudaFree(p); p = nullptr; bytes = 0;
@@ -251,6 +262,12 @@ struct GridResult {
   long count = 0;
 };
 thread_local GridResult g_grid_result;
+// work buffers of gvm_grid_block, kept between calls (a cudaMalloc/cudaFree pair of several GB per
+// block costs more than the kernels); gvm_grid_release() returns them
+struct GridWork {
+  DevBuf uvw, Vo, w, ck, k0, k1, v0, v1, tmp, gw, gV, flags, pos, start;
+};
+thread_local GridWork g_grid_work;
 
 int sort_pairs(DevBuf& tmp, uint32_t* k_in, uint32_t* k_out, uint32_t* v_in, uint32_t* v_out, long n,
                int end_bit) {
@@ -408,7 +425,10 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
   const size_t ext = (size_t)(M + 2 * support_y) * (size_t)(N + 2 * support_x);
   if (ext >= (size_t)kNoCell || n2 >= (long)0x7FFFFFFF) { gvm_set_error("gvm_grid_block: problem too large"); return 1; }
   *nout = 0;
-  DevBuf d_uvw, d_Vo, d_w, d_ck, d_k0, d_k1, d_v0, d_v1, d_tmp, d_gw, d_gV, d_flags, d_pos, d_start;
+  GridWork& wk = g_grid_work;
+  DevBuf &d_uvw = wk.uvw, &d_Vo = wk.Vo, &d_w = wk.w, &d_ck = wk.ck, &d_k0 = wk.k0, &d_k1 = wk.k1, &d_v0 = wk.v0,
+         &d_v1 = wk.v1, &d_tmp = wk.tmp, &d_gw = wk.gw, &d_gV = wk.gV, &d_flags = wk.flags, &d_pos = wk.pos,
+         &d_start = wk.start;
   GridResult& res = g_grid_result;   // compacted output stays on the device until it is fetched
   DevBuf &d_uo = res.uvw, &d_Vout = res.Vo, &d_wo = res.w;
   res.count = 0;
@@ -470,6 +490,11 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
   *nout = count;
   // outputs may be omitted: the caller sizes its arrays from *nout and calls gvm_grid_fetch
   if (uvw_out || Vo_out || w_out) return gvm_grid_fetch(uvw_out, Vo_out, w_out);
+  return 0;
+}
+
+int gvm_grid_release(void) {
+  g_grid_work = GridWork();
   return 0;
 }
 

@@ -167,6 +167,22 @@ class Engine:
             gcf = np.ascontiguousarray(gcf, dtype=np.float32)
             self._ck(self.lib.gvm_set_gcf(self.h, gcf.ctypes.data))
 
+    def set_degrid_kernel(self, table, support=None):
+        """Convolutional degridding in the forward model (degriddingGPU, src/functions.cu:2205-2254);
+        ``table`` [m][n] CKernel table, ``support`` (sx, sy); None restores the bilinear vis_mod."""
+        if table is None:
+            self._ck(self.lib.gvm_set_degrid_kernel(self.h, None, 0, 0, 0, 0))
+            return
+        table = np.ascontiguousarray(table, dtype=np.float32)
+        m, n = table.shape
+        sx, sy = support if support is not None else (n // 2, m // 2)
+        self._ck(self.lib.gvm_set_degrid_kernel(self.h, table.ctypes.data, m, n, int(sx), int(sy)))
+
+    def get_model_grid(self):
+        out = np.empty((self.N, self.N, 2), np.float32)
+        self._ck(self.lib.gvm_get_model_grid(self.h, out.ctypes.data))
+        return out[..., 0] + 1j * out[..., 1]
+
     def add_channel(self, freq, uvw_m, Vo, w, antenna_diameter, pb_factor, pb_cutoff,
                     primary_beam, ref_pix, phs_pix):
         d = _lib.gvm_channel_desc(freq, antenna_diameter, pb_factor, pb_cutoff, primary_beam,

@@ -51,6 +51,8 @@ SIGNATURES = {
     "gvm_build_noise_image": (C.c_int, [_P, C.c_float, C.POINTER(C.c_float)]),
     "gvm_get_noise_image": (C.c_int, [_P, _P]),
     "gvm_set_gcf": (C.c_int, [_P, _P]),
+    "gvm_set_degrid_kernel": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gvm_get_model_grid": (C.c_int, [_P, _P]),
     "gvm_add_channel": (C.c_int, [_P, C.POINTER(gvm_channel_desc), C.c_int64, _P, _P, _P, C.POINTER(C.c_int)]),
     "gvm_clear_channels": (C.c_int, [_P]),
     "gvm_num_channels": (C.c_int, [_P]),
@@ -90,6 +92,7 @@ SIGNATURES = {
                                  C.c_int64, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                  _P, _P, _P, C.POINTER(C.c_int64)]),
     "gvm_grid_fetch": (C.c_int, [_P, _P, _P]),
+    "gvm_grid_release": (C.c_int, []),
     "gvm_launch_count": (C.c_int64, [_P]),
     "gvm_last_grad_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "gvm_last_grad_mode": (C.c_int, [_P]),

@@ -100,6 +100,23 @@ int gvm_get_noise_image(gvm_engine* e, float* noise_host);
  * NULL disables it (ip->getCKernel() == NULL, src/functions.cu:4358). */
 int gvm_set_gcf(gvm_engine* e, const float* gcf_host);
 
+/* Forward-model option: convolutional-kernel degridding instead of the bilinear
+ * vis_mod. This is what the reference sketches in degriddingGPU
+ * (src/functions.cu:2205-2254; defined, never launched — its call site is
+ * commented out at :2127): nearest uv cell by the gridding index rule
+ * (:2222-2223), then the sum over the (2*support_y+1) x (2*support_x+1) taps of
+ * the CKernel table (CKernel::getGPUKernel / getm / getn / getSupportX/Y,
+ * include/classes/ckernel.cuh) times the model grid; with gvm_set_gcf holding the
+ * kernel's GCF image (apply_GCF, :2468) the pair is a gridding-corrected degridder.
+ * table_host [m][n]; NULL restores the reference's bilinear interpolation. The
+ * gradient stays the exact DFT of the residuals (DChi2), as in the reference. */
+int gvm_set_degrid_kernel(gvm_engine* e, const float* table_host, int m, int n,
+                          int support_x, int support_y);
+/* The model grid of the LAST channel evaluated by gvm_chi2 (after phase_rotate):
+ * [M][N] complex as interleaved floats, DC at [0,0] — device_V of varsPerGPU
+ * (include/framework.cuh:49-55). For tests and diagnostics. */
+int gvm_get_model_grid(gvm_engine* e, float* V_host);
+
 /* Upload one visibility block: raw uvw in METRES as [Z][3] doubles, Vo as [Z][2]
  * floats, weights [Z]. Performs on the GPU what MFS::setDevice + the
  * hermitianSymmetry kernel do (src/mfs.cu:555-617, src/functions.cu:2256-2273):
@@ -278,6 +295,8 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
 /* Two-phase use for large grids: call gvm_grid_block with the three output pointers NULL to get
  * *nout, size the host arrays, then fetch the gridded samples of that last call (same thread). */
 int gvm_grid_fetch(double* uvw_out, float* Vo_out, float* w_out);
+/* gvm_grid_block keeps its device work buffers between calls (this thread); this returns them. */
+int gvm_grid_release(void);
 
 /* ------------------------------------------------------------- telemetry -- */
 /* Number of kernels (ours + cuFFT) launched by the engine since creation. */

@@ -225,6 +225,41 @@ double gvo_degrid_chi2(long Z, long N, const double* Vre, const double* Vim, con
   return sum;
 }
 
+/* degriddingGPU (src/functions.cu:2205-2254; defined but never launched by the reference):
+ * convolutional-kernel degridding of a CENTRED model grid Vg [M][N] (interleaved re, im) at
+ * (u, v) in wavelengths. j = int(u/deltau + int(floorf(N/2)) + 0.5), k likewise with M (:2222-2223);
+ * taps outside the grid are skipped (:2231-2232); cells with shifted_j < N/2 are read through
+ * their Hermitian twin [M - k][N - j], conjugated (:2238-2243). The twin index reaches M (or N)
+ * when shifted_k (shifted_j) is 0, which the reference would read out of bounds: such taps are
+ * skipped here and the parity tests keep samples away from row/column 0. fp32 accumulation in
+ * the kernel's tap order. */
+void gvo_degrid_conv(long Z, const double* uvw_l, const float* Vg, const float* table, double deltau,
+                     double deltav, int M, int N, int kn, int sx, int sy, float* Vm) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < Z; i++) {
+    int j = (int)(uvw_l[3 * i] / deltau + (int)floorf((float)(N / 2)) + 0.5);
+    int k = (int)(uvw_l[3 * i + 1] / deltav + (int)floorf((float)(M / 2)) + 0.5);
+    float re = 0.0f, im = 0.0f;
+    for (int m = -sy; m <= sy; m++)
+      for (int n = -sx; n <= sx; n++) {
+        int sj = j + n, sk = k + m;
+        if (sk < 0 || sk >= M || sj < 0 || sj >= N) continue;
+        float kv = table[kn * (m + sy) + (n + sx)];
+        if (sj >= N / 2) {
+          re += kv * Vg[2 * ((long)N * sk + sj)];
+          im += kv * Vg[2 * ((long)N * sk + sj) + 1];
+        } else {
+          int hj = N - sj, hk = M - sk;
+          if (hj >= N || hk >= M) continue;
+          re += kv * Vg[2 * ((long)N * hk + hj)];
+          im -= kv * Vg[2 * ((long)N * hk + hj) + 1];
+        }
+      }
+    Vm[2 * i] = re;
+    Vm[2 * i + 1] = im;
+  }
+}
+
 /* DChi2 (src/functions.cu:3698-3791 / 3793-3888) in fp64 at the pixels listed in
  * pix[npix] (flat indices N*i + j). Vr, w as floats (what the forward pass left).
  * out[p] = dChi2 value (incl. -1, fg_scale, atten, gcf, /Z); masked pixels -> 0.

@@ -567,6 +567,27 @@ int gvref_error_image(float* out) {
   return 0;
 }
 
+/* The reference's degriddingGPU kernel (src/functions.cu:2205-2254; never launched by the
+ * reference itself) on caller-supplied arrays: uvw in wavelengths [Z][3], a CENTRED model grid
+ * Vg [M][N] complex, a kernel table [km][kn]. Vm_out [Z][2]. */
+int gvref_degridding(long Z, const double* uvw_lambda, const float* Vg, const float* table,
+                     double du, double dv, int m_img, int n_img, int km, int kn, int sx, int sy,
+                     float* Vm_out) {
+  double3* d_uvw; cufftComplex *d_vm, *d_vg; float* d_k;
+  cudaMalloc(&d_uvw, sizeof(double3) * Z);
+  cudaMalloc(&d_vm, sizeof(cufftComplex) * Z);
+  cudaMalloc(&d_vg, sizeof(cufftComplex) * m_img * n_img);
+  cudaMalloc(&d_k, sizeof(float) * km * kn);
+  cudaMemcpy(d_uvw, uvw_lambda, sizeof(double3) * Z, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_vg, Vg, sizeof(cufftComplex) * m_img * n_img, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_k, table, sizeof(float) * km * kn, cudaMemcpyHostToDevice);
+  degriddingGPU<<<(int)((Z + 255) / 256), 256>>>(d_uvw, d_vm, d_vg, d_k, du, dv, (int)Z, m_img, n_img, km, kn, sx, sy);
+  cudaError_t err = cudaDeviceSynchronize();
+  cudaMemcpy(Vm_out, d_vm, sizeof(cufftComplex) * Z, cudaMemcpyDeviceToHost);
+  cudaFree(d_uvw); cudaFree(d_vm); cudaFree(d_vg); cudaFree(d_k);
+  return (int)err;
+}
+
 int gvref_set_lbfgs_k(int k) { g_opt->setK(k); return 0; }
 void gvref_set_verbose(int v) { verbose_flag = v != 0; }
 

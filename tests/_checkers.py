@@ -51,6 +51,7 @@ class Oracle:
         L.gvo_error_accumulate.argtypes = [C.c_long, i64p, C.c_long, C.c_long, f64p, f32p, f32p, f32p, f32p] + \
                                           [C.c_float] * 8 + [C.c_double] * 2 + [C.c_int] * 2 + [f64p, f64p]
         L.gvo_error_reduce.argtypes = [C.c_long, f64p]
+        L.gvo_degrid_conv.argtypes = [C.c_long, f64p, f32p, f32p, C.c_double, C.c_double] + [C.c_int] * 5 + [f32p]
         L.gvo_chain.argtypes = [f32p, C.c_long, C.c_long, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]
         L.gvo_chain.restype = C.c_double
         L.gvo_prior_value.argtypes = [C.c_int, f32p, f32p, _V, C.c_long] + [C.c_float] * 5
@@ -115,6 +116,16 @@ class Oracle:
                            nu, meta["xpix"], meta["ypix"], meta["xpix"], meta["ypix"],
                            cfg["DELTAX"], cfg["DELTAY"], meta["primary_beam"], normalize, fp32_phase, out)
         return out
+
+    def degrid_conv(self, uvw_lambda, Vg_centred, table, du, dv, sx, sy):
+        """degriddingGPU (src/functions.cu:2205-2254) on a centred complex grid [M][N]."""
+        M, N = Vg_centred.shape
+        g = np.ascontiguousarray(np.stack([Vg_centred.real, Vg_centred.imag], -1), np.float32).reshape(-1)
+        t = np.ascontiguousarray(table, np.float32)
+        out = np.zeros(2 * len(uvw_lambda), np.float32)
+        self.lib.gvo_degrid_conv(len(uvw_lambda), np.ascontiguousarray(uvw_lambda, np.float64), g, t.reshape(-1), du, dv,
+                                 M, N, t.shape[1], sx, sy, out)
+        return out.reshape(-1, 2)
 
     def error_maps(self, pix, N, blocks, noise, I, meta, cfg, fp32_xy=0):
         """calculateErrors at the pixels `pix`: blocks = [(uvw_lambda, Vr, w, nu), ...]; returns (err_I, err_alpha)."""
@@ -221,6 +232,8 @@ class GvRef:
         L.gvref_time_evals.argtypes = [C.c_int, C.c_int, C.c_int]
         L.gvref_run.argtypes = [_V, C.POINTER(C.c_float)]
         L.gvref_set_lbfgs_k.argtypes = [C.c_int]
+        if hasattr(L, "gvref_degridding"):
+            L.gvref_degridding.argtypes = [C.c_long, f64p, _V, f32p, C.c_double, C.c_double] + [C.c_int] * 6 + [_V]
         if hasattr(L, "gvref_error_image"):
             L.gvref_error_image.argtypes = [f32p]
         L.gvref_set_verbose.argtypes = [C.c_int]
@@ -318,6 +331,18 @@ class GvRef:
         out = np.empty(2 * p.M * p.N, np.float32)
         self.lib.gvref_calc_gradient(iteration, flag, out)
         return out.reshape(2, p.M, p.N)
+
+    def degridding(self, uvw_lambda, Vg_centred, table, du, dv, sx, sy):
+        """degriddingGPU (src/functions.cu:2205-2254) on a centred complex grid."""
+        Z = len(uvw_lambda)
+        M, N = Vg_centred.shape
+        g = np.ascontiguousarray(np.stack([Vg_centred.real, Vg_centred.imag], -1), np.float32)
+        out = np.zeros((Z, 2), np.float32)
+        t = np.ascontiguousarray(table, np.float32)
+        rc = self.lib.gvref_degridding(Z, np.ascontiguousarray(uvw_lambda, np.float64), g.ctypes.data, t.reshape(-1),
+                                       du, dv, M, N, t.shape[0], t.shape[1], sx, sy, out.ctypes.data)
+        assert rc == 0, rc
+        return out
 
     def error_image(self):
         p = self.problem

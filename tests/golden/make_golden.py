@@ -4,6 +4,7 @@ Run on the GPU box (the reference's objective/gradient only exists as CUDA kerne
 
     gpurun -- 'python tests/golden/make_golden.py'      # writes gpurun_out/golden/ref_small.npz
     cp gpurun_out/golden/ref_small.npz tests/golden/
+    gpurun -- 'python tests/golden/make_golden.py ext'  # ref_small_ext.npz: error maps + degriddingGPU
 
 The inputs are NOT stored: tests rebuild them from the same seed with gpuvmem_b200.synth.
 tests/test_oracle_golden.py (CPU, no GPU needed) checks the C oracle against these vectors."""
@@ -31,6 +32,44 @@ def golden_image(N, minpix, seed=3):
     I[0] = (minpix * (1.0 + 40.0 * blob + 0.2 * rng.random((N, N)))).astype(np.float32)
     I[1] = (0.3 * blob + 0.05 * rng.standard_normal((N, N))).astype(np.float32)
     return I
+
+
+def golden_grid(N, du, dv):
+    """A closed-form Hermitian model grid, CENTRED (DC at [N/2][N/2]): the visibility function of three
+    Gaussian components, G(u,v) = sum_s a_s exp(-(u^2+v^2)/(2 s_s^2)) exp(-2 pi i (u x_s + v y_s))."""
+    k = np.arange(N) - N // 2
+    u, v = np.meshgrid(k * abs(du), k * abs(dv))
+    comps = [(1.0, 0.35, 0.0, 0.0), (0.6, 0.2, 0.21, -0.13), (0.3, 0.5, -0.4, 0.33)]   # (amp, width, x, y) in grid units
+    g = np.zeros((N, N), np.complex128)
+    umax = (N // 2) * abs(du)
+    for a, wdt, x, y in comps:
+        g += a * np.exp(-(u * u + v * v) / (2 * (wdt * umax) ** 2)) * np.exp(-2j * np.pi * (u * x + v * y) / abs(du) / N * 8)
+    return g.astype(np.complex64)
+
+
+def main_ext():
+    """Second fixture (ref_small_ext.npz): calculateErrors and the degriddingGPU kernel of the reference."""
+    p = synth.make_problem(**PROBLEM)
+    ref = GvRef()
+    ref.set_problem(p)
+    ref.init(ARGS)
+    s = ref.scalars()
+    I = golden_image(p.N, np.float32(0.001))
+    ref.set_image(I)
+    ref.calc_function(iteration=0)
+    out = {"err_image": ref.error_image()}
+    r = ref.get_vis(0)                                  # before cpu_ckernel: that call rebuilds the host datasets
+    grid = golden_grid(p.N, s["deltau"], s["deltav"])
+    # PSWF 9x9: the reference's Gaussian2D 7x7 table with its default w = 1 is a delta (src/gaussian2D.cu:27)
+    table, support, _ = ref.cpu_ckernel("PSWF", 9, 9)
+    out["degrid_table"] = table
+    out["degrid_support"] = np.array(support)
+    out["degrid_uvw"] = r["uvw"]
+    out["degrid_Vm"] = ref.degridding(r["uvw"], grid, table, s["deltau"], s["deltav"], support[0], support[1])
+    d = os.path.join(ROOT, "gpurun_out", "golden")
+    os.makedirs(d, exist_ok=True)
+    np.savez_compressed(os.path.join(d, "ref_small_ext.npz"), **out)
+    print("wrote", os.path.join(d, "ref_small_ext.npz"), {k: v.shape for k, v in out.items()})
 
 
 def main():
@@ -62,4 +101,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main_ext() if len(sys.argv) > 1 and sys.argv[1] == "ext" else main()

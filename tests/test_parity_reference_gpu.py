@@ -220,3 +220,51 @@ def test_error_maps_match_reference(setup, oracle):
           f"reference-fp64 {np.median(r_ref):.2e}, engine-fp64 {np.median(r_me):.2e}")
     assert np.median(rel) <= 1e-3
     assert np.median(r_me) <= max(2e-5, np.median(r_ref))
+
+
+def test_conv_degridding_matches_reference_kernel(setup, oracle):
+    """Forward-model option gvm_set_degrid_kernel against the reference's degriddingGPU kernel
+    (src/functions.cu:2205-2254, launched by the harness on the engine's own model grid, centred
+    with fftshift) and the C oracle. The reference reads the left half of the grid through the
+    Hermitian twin, the engine reads the cell itself: equal up to the fp32 asymmetry of the FFT."""
+    p, e, ref, torch = setup
+    if not hasattr(ref.lib, "gvref_degridding"):
+        pytest.skip("oracle/_ref/libgvref.so predates gvref_degridding")
+    from gpuvmem_b200 import host
+    du, dv = e.meta["deltau"], e.meta["deltav"]
+    for name, m, n in (("Gaussian2D", 7, 7), ("PSWF", 9, 9), ("PillBox2D", 1, 1)):
+        table, (sx, sy) = host.ckernel_table(name, m, n, np.float32(abs(du)), np.float32(abs(dv)))
+        e.set_degrid_kernel(table, (sx, sy))
+        try:
+            I_dev = torch.from_numpy(_image(e)).cuda()
+            chi2 = e.chi2(I_dev)
+            c = p.nchan - 1                                  # the model grid left behind is the last channel's
+            V = e.get_model_grid()
+            g = e.get_vis(c, want=("uvw", "Vo", "Vm", "Vr", "w"))
+            Vc = np.fft.fftshift(V)
+            want_ref = ref.degridding(g["uvw"], Vc, table, du, dv, sx, sy)
+            want_orc = oracle.degrid_conv(g["uvw"], Vc, table, du, dv, sx, sy)
+            N = p.N
+            j = (g["uvw"][:, 0] / du + N // 2 + 0.5).astype(np.int64)
+            k = (g["uvw"][:, 1] / dv + N // 2 + 0.5).astype(np.int64)
+            inner = (j - sx > 0) & (j + sx < N) & (k - sy > 0) & (k + sy < N)   # no tap on row/column 0 (reference OOB)
+            assert inner.sum() > 0.9 * len(j)
+            scale = np.abs(want_ref[inner]).max()
+            assert np.abs(want_orc[inner] - want_ref[inner]).max() <= 1e-6 * scale, name
+            assert np.abs(g["Vm"][inner] - want_ref[inner]).max() <= 2e-5 * scale, name
+            assert np.allclose(g["Vr"], g["Vo"] - g["Vm"], atol=1e-6 * scale)
+            half = 0.5 * float(np.sum(g["w"].astype(np.float64) * (g["Vr"].astype(np.float64) ** 2).sum(1)))
+            tot = 0.0
+            for cc in range(p.nchan):
+                gg = e.get_vis(cc, want=("Vr", "w"))
+                tot += 0.5 * float(np.sum(gg["w"].astype(np.float64) * (gg["Vr"].astype(np.float64) ** 2).sum(1)))
+            assert abs(chi2 - tot) <= 1e-5 * tot
+        finally:
+            e.set_degrid_kernel(None)
+    # PillBox 1x1 = nearest-cell sampling of the grid
+    assert sx == 0 and sy == 0
+    # and the bilinear model is back
+    I_dev = torch.from_numpy(_image(e)).cuda()
+    ref.set_image(_image(e))
+    want, _ = ref.calc_function(iteration=0)
+    assert abs(e.chi2(I_dev) - want) <= 1e-5 * abs(want)
