@@ -188,8 +188,8 @@ void MFS::configure(int argc, char** argv) {
   g.robust_param = variables.robust_param;
   g.threshold = variables.threshold * 5.0;
   ioImageHandler->setPrintImages(g.print_images);
-  if (g.apply_noise || g.print_errors || g.radius_mask || variables.user_mask != "NULL" || variables.randoms < 1.0f) {
-    std::printf("ERROR: -a, -E, -M, -U and -r < 1 are outside this engine's scope (DESIGN.md §7)\n");
+  if (g.apply_noise || g.radius_mask || variables.user_mask != "NULL" || variables.randoms < 1.0f) {
+    std::printf("ERROR: -a, -M, -U and -r < 1 are outside this engine's scope (DESIGN.md §7)\n");
     std::exit(-1);
   }
 
