@@ -130,6 +130,7 @@ __device__ __forceinline__ long lower_bound_u32(const uint32_t* __restrict__ a, 
 }
 
 constexpr int kMaxTaps = 17 * 17;
+constexpr int kTapBits = 9;               // tap index (< 512) in the low bits of the per-list meta word
 
 // One thread per output cell: merge the (<= taps) sorted sample lists of the centre cells whose
 // kernel footprint covers this cell, in ascending sample order, and accumulate exactly like the
@@ -142,20 +143,23 @@ __global__ void __launch_bounds__(256) k_cell_count(const uint32_t* __restrict__
   if (i < n && keys[i] != kNoCell) atomicAdd(count + keys[i], 1);
 }
 
-__global__ void __launch_bounds__(128) k_grid_accumulate(
+// Per-thread merge state lives in SHARED memory, one column per thread (conflict-free): the head
+// sample index of every non-empty list (hz), its position (head) and remaining-count | tap index
+// (meta). With thread-local arrays the same state spilled to DRAM: 322 GB of traffic for ~1 GB of
+// algorithmic bytes (ncu, profiles/r1c_k_grid_accumulate_*): the kernel was HBM-bound on its own spills.
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) k_grid_accumulate(
     const int* __restrict__ start, const uint32_t* __restrict__ vals, long n, long Z,
     const float2* __restrict__ Vo, const float* __restrict__ w, const float* __restrict__ kernel, int ck_m,
-    int ck_n, int sx, int sy, long M, long N, float* __restrict__ out_w, float2* __restrict__ out_V) {
-  const long cell = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    int ck_n, int sx, int sy, long M, long N, int taps, float* __restrict__ out_w, float2* __restrict__ out_V) {
+  extern __shared__ uint32_t s_state[];
+  uint32_t* const s_hz = s_state + threadIdx.x;                          // [taps][kThreads]
+  uint32_t* const s_head = s_state + (size_t)taps * kThreads + threadIdx.x;
+  uint32_t* const s_meta = s_state + 2 * (size_t)taps * kThreads + threadIdx.x;
+  const long cell = blockIdx.x * (long)kThreads + threadIdx.x;
   if (cell >= M * N) return;
   const int gk = (int)(cell / N), gj = (int)(cell % N);
   const long EW = N + 2L * sx;
-  // per-thread lists live in local memory, indexed identically across the warp while scanning
-  // (coalesced); hz caches the sample index at the head of every list so that one merge step
-  // costs nl local loads + ONE global load instead of nl scattered global loads
-  int head[kMaxTaps], tail[kMaxTaps];
-  uint32_t hz[kMaxTaps];
-  float ckv[kMaxTaps];
   int nl = 0;
   for (int m = -sy; m <= sy; m++) {
     // the centres of one footprint row are consecutive keys: one look-up tells whether the row is empty
@@ -170,7 +174,9 @@ __global__ void __launch_bounds__(128) k_grid_accumulate(
       const uint32_t key = (uint32_t)(ek * EW + ej);
       const int b = start[key], e = start[key + 1];
       if (e > b) {
-        head[nl] = b; tail[nl] = e; ckv[nl] = kernel[ck_n * ki + kj]; hz[nl] = vals[b];
+        s_hz[nl * kThreads] = vals[b];
+        s_head[nl * kThreads] = (uint32_t)b;
+        s_meta[nl * kThreads] = ((uint32_t)(e - b) << kTapBits) | (uint32_t)(ck_n * ki + kj);
         nl++;
       }
     }
@@ -179,17 +185,20 @@ __global__ void __launch_bounds__(128) k_grid_accumulate(
   while (true) {
     uint32_t best = kNoCell; int bl = -1;
     for (int l = 0; l < nl; l++) {
-      const uint32_t z = hz[l];
+      const uint32_t z = s_hz[l * kThreads];
       if (z < best) { best = z; bl = l; }
     }
     if (bl < 0) break;
-    const int nh = ++head[bl];
-    hz[bl] = nh < tail[bl] ? vals[nh] : kNoCell;
+    const uint32_t meta = s_meta[bl * kThreads] - (1u << kTapBits);   // one sample fewer in this list
+    const uint32_t nh = s_head[bl * kThreads] + 1u;
+    s_meta[bl * kThreads] = meta;
+    s_head[bl * kThreads] = nh;
+    s_hz[bl * kThreads] = (meta >> kTapBits) ? vals[nh] : kNoCell;
     const long vi = (best < (uint32_t)Z) ? (long)best : (long)best - Z;
     const float wt = w[vi];
     float2 vo = Vo[vi];
     if (best >= (uint32_t)Z) vo.y *= -1.0f;
-    const float ck = ckv[bl];
+    const float ck = __ldg(&kernel[meta & ((1u << kTapBits) - 1u)]);
     const float ck2 = __fmul_rn(ck, ck);
     gw = __fadd_rn(gw, __fmul_rn(wt, ck));
     gw2 = __fadd_rn(gw2, __fmul_rn(wt, ck2));
@@ -459,15 +468,41 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
     WG_CUDA(cudaGetLastError());
   }
   {
+    // the merge kernel packs a list's remaining count into 32 - kTapBits bits
+    size_t mb = 0;
+    int* d_maxc = d_flags.as<int>();     // free until k_grid_flags
+    WG_CUDA(cub::DeviceReduce::Max(nullptr, mb, d_start.as<int>(), d_maxc, (int)(ext + 1)));
+    if (d_tmp.ensure(mb)) return 1;
+    WG_CUDA(cub::DeviceReduce::Max(d_tmp.p, mb, d_start.as<int>(), d_maxc, (int)(ext + 1)));
+    int maxc = 0;
+    WG_CUDA(cudaMemcpy(&maxc, d_maxc, 4, cudaMemcpyDeviceToHost));
+    if (maxc >= (1 << (32 - kTapBits))) {
+      gvm_set_error("gvm_grid_block: %d samples fall into one uv cell (limit %d)", maxc, (1 << (32 - kTapBits)) - 1);
+      return 1;
+    }
+  }
+  {
     size_t sb = 0;
     WG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, d_start.as<int>(), d_start.as<int>(), (int)(ext + 1)));
     if (d_tmp.ensure(sb)) return 1;
     WG_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, sb, d_start.as<int>(), d_start.as<int>(), (int)(ext + 1)));
   }
-  k_grid_accumulate<<<(int)((MN + 127) / 128), 128>>>(d_start.as<int>(), d_v1.as<uint32_t>(), n2, (long)Z,
-                                                      d_Vo.as<float2>(), d_w.as<float>(), d_ck.as<float>(), ck_m,
-                                                      ck_n, support_x, support_y, M, N, d_gw.as<float>(),
-                                                      d_gV.as<float2>());
+  {
+    // threads per CTA from the tap count: 12 bytes of shared state per (thread, tap)
+    const int taps = (2 * support_x + 1) * (2 * support_y + 1);
+#define GVM_GRID_ACC(T)                                                                                      \
+  do {                                                                                                       \
+    const size_t smem = (size_t)taps * (T) * 3 * sizeof(uint32_t);                                           \
+    WG_CUDA(cudaFuncSetAttribute(k_grid_accumulate<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_grid_accumulate<T><<<(int)((MN + (T) - 1) / (T)), (T), smem>>>(                                        \
+        d_start.as<int>(), d_v1.as<uint32_t>(), n2, (long)Z, d_Vo.as<float2>(), d_w.as<float>(),             \
+        d_ck.as<float>(), ck_m, ck_n, support_x, support_y, M, N, taps, d_gw.as<float>(), d_gV.as<float2>()); \
+  } while (0)
+    if (taps <= 49) GVM_GRID_ACC(128);
+    else if (taps <= 121) GVM_GRID_ACC(64);
+    else GVM_GRID_ACC(32);
+#undef GVM_GRID_ACC
+  }
   WG_CUDA(cudaGetLastError());
   k_grid_flags<<<(int)((MN + 255) / 256), 256>>>(d_gw.as<float>(), (long)MN, d_flags.as<int>());
   size_t bytes = 0;
