@@ -155,6 +155,48 @@ def cpu_baseline(problem, engine_meta, seconds_target=15.0):
             "sample": f"oracle/gvm_oracle.c gvo_dchi2 (fp64, OpenMP): {npix} of {N*N} pixels x {Zs} visibilities in {dt:.1f} s"}
 
 
+def cpu_gridding_baseline(problem, ckernel, ck_size, scheme, nvis=200000):
+    """The reference's OpenMP CPU gridding path (-g: WeightingScheme::apply + do_gridding, host code of
+    the unmodified reference inside oracle/_ref/libgvref.so) on a bounded sample of the workload's first
+    channel and the workload's own grid, with 1 thread and with every host core; and this engine's
+    gvm_weights + gvm_grid_block on the same sample. A reported baseline, not the target."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _checkers import GVREF_SO, GvRef
+    if not os.path.exists(GVREF_SO):
+        return None
+    from gpuvmem_b200 import host
+    from gpuvmem_b200.engine import RPDEG_D, grid_block, weights
+    sub = problem.subset(nvis)
+    for c in range(sub.nchan - 1, 0, -1):       # first channel only
+        del sub.uvw[c], sub.Vo[c], sub.w[c]
+    sub.freqs = sub.freqs[:1].copy()
+    Zs = len(sub.w[0])
+    ck, (m, n) = (ckernel, ck_size) if ck_size[0] > 1 else ("Gaussian2D", (7, 7))
+    sch = scheme if scheme != "Natural" else ""
+    ref = GvRef()
+    ref.set_problem(sub)
+    cores = os.cpu_count() or 1
+    out = {"unit": "Mvis/s", "sample": f"{Zs} visibilities of channel 0 onto the {problem.M}x{problem.N} grid, {ck} {m}x{n}"
+                                       f"{', ' + sch + ' R=0 weights' if sch else ''}", "kind": "reference", "cores": cores}
+    with NativeStdoutToStderr():
+        for label, th in (("threads_1", 1), ("threads_all", cores)):
+            ref.cpu_gridding(ck, m, n, scheme=sch, robust=0.0, threads=th)
+            tw, tg = ref.cpu_last_seconds()
+            out[label] = {"Mvis_per_s": Zs / 1e6 / (tw + tg), "weighting_s": tw, "gridding_s": tg, "threads": th}
+    du, dv = 1.0 / (sub.M * RPDEG_D * sub.DELTAX), 1.0 / (sub.N * RPDEG_D * sub.DELTAY)
+    table, support = host.ckernel_table(ck, m, n, np.float32(abs(du)), np.float32(abs(dv)))
+    for rep in range(2):                         # second pass: buffers allocated, context warm
+        t0 = time.perf_counter()
+        w = sub.w[0].copy()
+        if sch:
+            w = weights(sch, sub.M, sub.N, du, dv, [sub.uvw[0]], [float(sub.freqs[0])], [w], robust=0.0)[0]
+        grid_block(sub.M, sub.N, du, dv, float(sub.freqs[0]), sub.uvw[0], sub.Vo[0], w, table, support)
+        dt = time.perf_counter() - t0
+    out["value"] = out["threads_all"]["Mvis_per_s"]
+    out["this_engine_Mvis_per_s_same_sample"] = Zs / 1e6 / dt
+    return out
+
+
 def run_reference(args):
     """Reference arm: gpuvmem's own CUDA implementation of the path (its only
     implementation — the reference has no CPU objective/gradient), compiled unmodified for
@@ -405,6 +447,10 @@ def main():
             meta = dict(deltau=sc["deltau"], deltav=sc["deltav"], fg_scale=sc["fg_scale"], pb_factor=pbf, pb_cutoff=pbc,
                         primary_beam=pb, xpix=sc["xobs_pix"], ypix=sc["yobs_pix"], nu_0=sc["nu_0"], noise_cut=sc["noise_cut"])
             line["cpu_baseline"] = cpu_baseline(problem, meta)
+            try:
+                line["cpu_gridding"] = cpu_gridding_baseline(problem, ckernel, ck_size, scheme)
+            except Exception as exc:      # a reported baseline must not take the bench line down
+                line["cpu_gridding"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
     s.close()
     if world > 1:

@@ -17,6 +17,7 @@
  * Nothing here is copied from the reference; the reference sources are compiled
  * where they lie.
  */
+#include <omp.h>
 #include <cstdarg>
 #include <sstream>
 
@@ -326,23 +327,31 @@ int gvref_cpu_ckernel(const char* name, int m, int n, float* table, float* gcf,
 
 /* Optional weighting, then do_gridding (src/functions.cu:1339). Results stay in
  * `datasets`; fetch with gvref_cpu_gridded_count / gvref_cpu_gridded_fetch. */
+static double g_cpu_seconds[2] = {0.0, 0.0};   /* WeightingScheme::apply, do_gridding of the last call */
 int gvref_cpu_gridding(const char* scheme, float robust, const char* ckname,
                        int m, int n, int threads) {
   cpu_prepare(1);
+  g_cpu_seconds[0] = g_cpu_seconds[1] = 0.0;
   if (scheme && scheme[0]) {
     WeightingScheme* s = createObject<WeightingScheme, std::string>(scheme);
     s->setThreads(threads);
     s->configure(&robust);
+    double t0 = omp_get_wtime();
     s->apply(datasets);
+    g_cpu_seconds[0] = omp_get_wtime() - t0;
     delete s;
   }
   CKernel* ck = make_ckernel(ckname, m, n);
   if (!ck) return -1;
   ck->setSigmas(fabs(deltau), fabs(deltav));
   ck->buildKernel();
+  double t0 = omp_get_wtime();
   do_gridding(datasets[0].fields, &datasets[0].data, deltau, deltav, M, N, ck, threads);
+  g_cpu_seconds[1] = omp_get_wtime() - t0;
   return 0;
 }
+/* wall seconds of the two reference host calls inside the last gvref_cpu_gridding */
+int gvref_cpu_last_seconds(double* out2) { out2[0] = g_cpu_seconds[0]; out2[1] = g_cpu_seconds[1]; return 0; }
 long gvref_cpu_gridded_count(int chan) {
   return datasets[0].fields[0].numVisibilitiesPerFreqPerStoke[chan][0];
 }

@@ -232,6 +232,8 @@ class GvRef:
         L.gvref_time_evals.argtypes = [C.c_int, C.c_int, C.c_int]
         L.gvref_run.argtypes = [_V, C.POINTER(C.c_float)]
         L.gvref_set_lbfgs_k.argtypes = [C.c_int]
+        if hasattr(L, "gvref_cpu_last_seconds"):
+            L.gvref_cpu_last_seconds.argtypes = [f64p]
         if hasattr(L, "gvref_degridding"):
             L.gvref_degridding.argtypes = [C.c_long, f64p, _V, f32p, C.c_double, C.c_double] + [C.c_int] * 6 + [_V]
         if hasattr(L, "gvref_error_image"):
@@ -279,6 +281,12 @@ class GvRef:
             self.lib.gvref_cpu_gridded_fetch(c, u, v, w)
             out.append((u, v, w))
         return out
+
+    def cpu_last_seconds(self):
+        """(WeightingScheme::apply, do_gridding) wall seconds of the last cpu_gridding call."""
+        out = np.zeros(2)
+        self.lib.gvref_cpu_last_seconds(out)
+        return float(out[0]), float(out[1])
 
     # CUDA reference path (GPU box only)
     def init(self, args, optimizer="CG-FRPRMN", scheme="Natural", ckernel="PillBox2D", ck_m=1, ck_n=1, with_tv=0):
