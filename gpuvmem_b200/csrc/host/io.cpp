@@ -59,6 +59,16 @@ class IoGVMS : public Io {
       std::fclose(js);
     }
   }
+  std::vector<float> read_data_float_FITS(const std::string& file) override {
+    std::vector<float> img((size_t)M * N);
+    std::FILE* fp = std::fopen(file.c_str(), "rb");
+    if (!fp || std::fread(img.data(), sizeof(float), img.size(), fp) != img.size()) {
+      std::printf("ERROR: cannot read %ld x %ld fp32 values from %s\n", M, N, file.c_str());
+      std::exit(-1);
+    }
+    std::fclose(fp);
+    return img;
+  }
   void writeModelVisibilities(const std::string& out, std::vector<Field>& fields, MSData& data) override {
     // residuals + model per block: int64 Z; float Vm[Z][2]; float Vr[Z][2]; float weight[Z]
     std::FILE* fp = std::fopen(out.c_str(), "wb");

@@ -30,6 +30,9 @@ class Io {
     printImage(I_dev, name + "_" + std::to_string(iteration), units, iteration, index, 1.0f, M, N, false);
   }
   virtual void writeModelVisibilities(const std::string& path, std::vector<Field>& fields, MSData& data) = 0;
+  // an image-sized float plane from a file (reference: IoFITS::read_data_float_FITS, src/iofits.cu:98-129;
+  // used for the -U user mask): raw little-endian fp32, M*N values
+  virtual std::vector<float> read_data_float_FITS(const std::string& file) = 0;
 
   void setInput(const std::string& s) { input = s; }
   void setOutput(const std::string& s) { output = s; }

@@ -188,8 +188,8 @@ void MFS::configure(int argc, char** argv) {
   g.robust_param = variables.robust_param;
   g.threshold = variables.threshold * 5.0;
   ioImageHandler->setPrintImages(g.print_images);
-  if (g.apply_noise || g.radius_mask || variables.user_mask != "NULL" || variables.randoms < 1.0f) {
-    std::printf("ERROR: -a, -M, -U and -r < 1 are outside this engine's scope (DESIGN.md §7)\n");
+  if (g.apply_noise || variables.randoms < 1.0f) {
+    std::printf("ERROR: -a and -r < 1 are outside this engine's scope (DESIGN.md §7)\n");
     std::exit(-1);
   }
 
@@ -560,6 +560,25 @@ void MFS::setDevice() {
   fg_scale = noise_min;
   g.noise_cut = g.noise_cut * noise_min;
   GVM_CHECK(gvm_set_scalars(g.engine, fg_scale, g.noise_cut, g.threshold));
+  // -U / -M: the mask plane REPLACES the noise image after fg_scale and noise_cut were derived from it
+  // (src/mfs.cu:922-931). -U: user plane, noise_cut was forced to 1 (x min noise) by getOptions;
+  // -M: distance_image (src/functions.cu:2360-2380) of the last field: 1 everywhere, 0 within 4.5e-5
+  // arcsec of the pointing-centre pixel.
+  if (variables.user_mask != "NULL") {
+    ioImageHandler->setMN(g.M, g.N);
+    const std::vector<float> u_mask = ioImageHandler->read_data_float_FITS(variables.user_mask);
+    GVM_CHECK(gvm_set_noise_image(g.engine, u_mask.data(), 0));
+  } else if (g.radius_mask) {
+    std::vector<float> dist_img(MN, 1.0f);
+    const Field& lf = datasets.back().fields.back();
+    const int x0 = (int)lf.ref_xobs_pix, y0 = (int)lf.ref_yobs_pix;
+    for (long i = 0; i < g.N; i++)
+      for (long j = 0; j < g.M; j++) {
+        const float x = (float)((j - x0) * g.DELTAX * 3600.0), y = (float)((i - y0) * g.DELTAY * 3600.0);
+        if (std::sqrt(x * x + y * y) < 4.5e-05f) dist_img[g.N * i + j] = 0.0f;
+      }
+    GVM_CHECK(gvm_set_noise_image(g.engine, dist_img.data(), 0));
+  }
   if (gridding && ckernel) GVM_CHECK(gvm_set_gcf(g.engine, ckernel->getGCFCPUPointer()));
   der.fg_scale = fg_scale; der.noise_cut = g.noise_cut; der.nu_0 = g.nu_0;
   if (g.verbose_flag && !g.quiet) {

@@ -52,3 +52,48 @@ def test_command_line_reconstruction_with_error_maps(tmp_path):
         assert (e0 > 0).any() and (e1 > 0).any()
     finally:
         s.close()
+
+
+def _noise_of(s):
+    out = np.empty((s.M, s.N), np.float32)
+    assert s.eng.gvm_get_noise_image(s.engine_handle(), out.ctypes.data) == 0
+    return out
+
+
+def test_user_mask_and_radius_mask(tmp_path):
+    """-U file: the plane replaces the noise image after fg_scale / noise_cut were derived, noise_cut = 1 x min
+    noise (src/functions.cu:296-298, src/mfs.cu:916-927); -M: distance_image (src/functions.cu:2360-2380)."""
+    p = synth.make_problem(N=128, nvis=8000, nchan=1, seed=78, grid_fill=0.9)
+    N = p.N
+    host.set_quiet(True)
+    base = host.Session(p, args="-z 0.001 -Z 0.01 -t 3")
+    sc0 = base.scalars()
+    base.close()
+    mask = np.full((N, N), 1e30, np.float32)
+    mask[40:90, 30:100] = 0.0
+    path = str(tmp_path / "mask.f32")
+    mask.tofile(path)
+    s = host.Session(p, args=f"-z 0.001 -Z 0.01 -t 3 -U {path}")
+    try:
+        sc = s.scalars()
+        assert np.array_equal(_noise_of(s), mask)
+        assert abs(sc["fg_scale"] - sc0["fg_scale"]) <= 1e-6 * sc0["fg_scale"]
+        assert abs(sc["noise_cut"] - sc["fg_scale"]) <= 1e-6 * sc["fg_scale"]      # 1 x min(noise)
+        s.set_iteration(1)
+        s.calc_function()
+        g = s.calc_gradient(1)
+        assert not g[0][mask > 0].any()
+        assert np.count_nonzero(g[0][mask == 0]) > 0.99 * np.count_nonzero(mask == 0)
+        img = s.get_image()                       # clip2IWNoise: masked pixels pinned at -eta*MINPIX, alpha 0
+        assert (img[0][mask > 0] == np.float32(0.001)).all() and not img[1][mask > 0].any()
+    finally:
+        s.close()
+    s = host.Session(p, args="-z 0.001 -Z 0.01 -t 3 -M")
+    try:
+        d = _noise_of(s)
+        x0, y0 = int(s.scalars()["xobs_pix"]), int(s.scalars()["yobs_pix"])
+        want = np.ones((N, N), np.float32)
+        want[y0, x0] = 0.0
+        assert np.array_equal(d, want)
+    finally:
+        s.close()
