@@ -90,7 +90,7 @@ bool getOptions(int argc, char** argv, Vars* v) {
   }
   longopts.push_back({nullptr, 0, nullptr, 0});
   bool help = false;
-  optind = 1;
+  optind = 0;   // glibc: 0 = full re-initialisation (1 would keep `nextchar` pointing into the previous argv)
   opterr = 0;
   int c;
   while ((c = getopt_long(argc, argv, shortopts.c_str(), longopts.data(), nullptr)) != -1) {

@@ -48,6 +48,8 @@ def main():
     res["probe_value"], res["probe_fi"] = v, fi
     res["probe_grad"] = ref.calc_gradient(iteration=1, flag=0)
     res["probe_image_after"] = ref.get_image()   # the clip mutates the image
+    if len(z) > 1:                               # spectral-index gradient (flag_opt odd, DChi2_total_alpha + threshold)
+        res["probe_grad_flag1"] = ref.calc_gradient(iteration=1, flag=1)
     if hasattr(ref.lib, "gvref_error_image"):
         res["probe_err"] = ref.error_image()     # calculateErrors on the probe image's residuals
     ref.set_image(I0)

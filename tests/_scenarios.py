@@ -17,6 +17,13 @@ SCENARIOS = {
                             f"-z 0.001 -Z {LAMBDAS} -g 1 -R 0.0 -t 4", "CG-FRPRMN", "Briggs", "Gaussian2D", (7, 7), 0),
     "cg_gridded_pswf": (dict(N=128, nvis=20000, nchan=1, freq0=2.3e11, seed=35, grid_fill=0.9),
                         "-z 0.001 -Z 0.01 -g 1 -t 3", "CG-FRPRMN", "Uniform", "PSWF", (9, 9), 0),
+    # -x: no positivity projection (so no entropy term: ln of a negative pixel is NaN in the reference too);
+    # eta != -1 (MINPIX = -eta * z, the value masked pixels are pinned to); a tighter mask (-N 5)
+    "cg_nopositivity_eta": (dict(N=128, nvis=16000, nchan=1, freq0=2.3e11, seed=36, grid_fill=0.9),
+                            "-z 0.002 -Z 0.0,0.005,0.002,0.001 -x -e -0.5 -N 5 -t 4", "CG-FRPRMN", "Natural", "PillBox2D", (1, 1), 0),
+    # MFS with a spectral-index threshold (-T sigma: alpha frozen where I0 < 5 T) and radial weighting, L-BFGS
+    "lbfgs_mfs_threshold_radial": (dict(N=128, nvis=12000, nchan=3, freq0=1.0e11, bandwidth=6e9, seed=37, grid_fill=0.9),
+                                   "-z 0.001,0.1 -Z 0.01,0.0,0.002 -T 0.001 -t 4", "CG-LBFGS", "Radial", "PillBox2D", (1, 1), 3),
 }
 REF_EXTRA = " -X 16 -Y 16 -V 256 -i synth.ms -o out.ms -m hdr.fits"
 

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # rel-L2 tolerance on the final image (unmasked pixels) after the scenario's iterations
 FINAL_TOL = {"cg_natural": 2e-3, "lbfgs_natural": 2e-3, "cg_mfs_briggs": 2e-3, "cg_gridded_gaussian": 2e-3,
-             "cg_gridded_pswf": 2e-3}
+             "cg_gridded_pswf": 2e-3, "cg_nopositivity_eta": 2e-3, "lbfgs_mfs_threshold_radial": 2e-3}
 
 
 def _rel(a, b):
@@ -88,6 +88,14 @@ def test_scenario_matches_reference(name, refdir):
         assert np.array_equal(s.get_image(), ref["probe_image_after"]), "clip2IWNoise side effect"
         assert _rel(g[0], ref["probe_grad"][0]) <= 1e-4, _rel(g[0], ref["probe_grad"][0])
         assert np.array_equal(g[0] == 0, ref["probe_grad"][0] == 0), "masked pixels must be exactly 0"
+        if "probe_grad_flag1" in ref.files:
+            s.set_flag(1)
+            g1 = s.calc_gradient(1)
+            s.set_flag(0)
+            r1 = ref["probe_grad_flag1"]
+            assert _rel(g1[1], r1[1]) <= 1e-4, _rel(g1[1], r1[1])
+            assert np.array_equal(g1[1] == 0, r1[1] == 0), "alpha gradient: masked / below-threshold pixels exactly 0"
+            assert np.array_equal(g1[0] == 0, r1[0] == 0)
         # -- Error "SecondDerivateError" (calculateErrors) on the same residuals ------------
         if "probe_err" in ref.files:
             err, rerr = s.error_image(), ref["probe_err"]

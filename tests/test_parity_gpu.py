@@ -523,3 +523,32 @@ def test_error_maps_gridded_fft_equals_direct_sum():
             assert np.median(np.abs(a[1][both] - b[1][both]) / b[1][both]) <= 2e-5
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("mode", [GRAD_SIMT, GRAD_UMMA])
+def test_normalize_divides_by_the_block_size(small, oracle, mode):
+    """Fi::configure(..., normalize = true): chi2 sums sum_k/Z per block (src/functions.cu:4439-4453) and
+    DChi2 divides by Z (:3786-3788)."""
+    torch = _torch()
+    p, e = small
+    e.set_grad_mode(mode)
+    I_dev = torch.from_numpy(_test_image(e)).cuda()
+    got = e.chi2(I_dev, normalize=True)
+    want = 0.0
+    for c in range(p.nchan):
+        v = e.get_vis(c, want=("Vr", "w"))
+        want += float(np.sum(v["w"].astype(np.float64) * (v["Vr"].astype(np.float64) ** 2).sum(1))) / len(v["w"])
+    assert abs(got - 0.5 * want) <= 1e-5 * 0.5 * want
+    g = torch.zeros_like(I_dev)
+    e.dchi2(I_dev, g, flag_opt=0, normalize=True)
+    Ic = I_dev.cpu().numpy()
+    pix = np.arange(0, p.N * p.N, 19)
+    tot = np.zeros(len(pix))
+    noise = e.get_noise_image()
+    for c in range(p.nchan):
+        v = e.get_vis(c, want=("uvw", "Vr", "w"))
+        d = oracle.dchi2(pix, p.N, v["uvw"], v["Vr"], v["w"], noise, None, float(p.freqs[c]), e.meta, _cfg(p), normalize=1)
+        tot += d * oracle.chain(Ic, pix, float(p.freqs[c]), e.meta, e.cfg.threshold, 0)
+    gg = g[0].cpu().numpy().reshape(-1)[pix]
+    assert np.linalg.norm(gg - tot) / np.linalg.norm(tot) <= 2e-5
+    e.chi2(I_dev)        # leave the shared engine in its default state
