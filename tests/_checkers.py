@@ -88,13 +88,17 @@ class Oracle:
         M, N = I.shape[1], I.shape[2]
         self.lib.gvo_clip(I.reshape(-1), noise.reshape(-1), M, N, noise_cut, minpix, eta, threshold, schedule)
 
-    def model_grid(self, I, gcf, nu, meta, cfg):
+    def model_grid(self, I, gcf, nu, meta, cfg, ref_pix=None, phs_pix=None):
+        """ref_pix / phs_pix: (x, y) pointing-centre and phase-centre pixels of the block (mosaics:
+        Field::ref_xobs_pix / phs_xobs_pix, include/MSFITSIO.cuh:102-121); default: the image's."""
         N = I.shape[2]
+        rx, ry = ref_pix if ref_pix is not None else (meta["xpix"], meta["ypix"])
+        px, py = phs_pix if phs_pix is not None else (meta["xpix"], meta["ypix"])
         Vre = np.empty(N * N); Vim = np.empty(N * N)
         g = None if gcf is None else np.ascontiguousarray(gcf, np.float32).ctypes.data
         rc = self.lib.gvo_model_grid(np.ascontiguousarray(I.reshape(-1)), g, N, nu, meta["nu_0"], meta["minpix"],
                                      cfg["eta"], meta["fg_scale"], cfg["D"], meta["pb_factor"], meta["pb_cutoff"],
-                                     meta["xpix"], meta["ypix"], float(meta["xpix"]), float(meta["ypix"]),
+                                     rx, ry, float(np.float32(px)), float(np.float32(py)),
                                      cfg["DELTAX"], cfg["DELTAY"], meta["primary_beam"], Vre, Vim)
         assert rc == 0, "oracle FFT needs a power-of-two image"
         return Vre, Vim
@@ -106,14 +110,17 @@ class Oracle:
                                      Vm.ctypes.data, Vr.ctypes.data)
         return s, Vm, Vr
 
-    def dchi2(self, pix, N, uvw_l, Vr, w, noise, gcf, nu, meta, cfg, normalize=0, fp32_phase=0):
+    def dchi2(self, pix, N, uvw_l, Vr, w, noise, gcf, nu, meta, cfg, normalize=0, fp32_phase=0, ref_pix=None,
+              phs_pix=None):
+        rx, ry = ref_pix if ref_pix is not None else (meta["xpix"], meta["ypix"])
+        px, py = phs_pix if phs_pix is not None else (meta["xpix"], meta["ypix"])
         pix = np.ascontiguousarray(pix, np.int64)
         out = np.empty(len(pix))
         g = None if gcf is None else np.ascontiguousarray(gcf, np.float32).ctypes.data
         self.lib.gvo_dchi2(len(pix), pix, N, len(w), np.ascontiguousarray(uvw_l), np.ascontiguousarray(Vr),
                            np.ascontiguousarray(w), np.ascontiguousarray(noise.reshape(-1)), g,
                            meta["noise_cut"], meta["fg_scale"], cfg["D"], meta["pb_factor"], meta["pb_cutoff"],
-                           nu, meta["xpix"], meta["ypix"], meta["xpix"], meta["ypix"],
+                           nu, rx, ry, px, py,
                            cfg["DELTAX"], cfg["DELTAY"], meta["primary_beam"], normalize, fp32_phase, out)
         return out
 
