@@ -399,14 +399,14 @@ def main():
                         f"(one per channel), {kern_ms:.2f} ms in total; peak = bf16/fp16 dense ({pk['source']}, sustained); the "
                         "fp16x3 split issues 3 MMAs per useful product, so frac <= 1/3 by construction"}
         if mode == 4:
-            # gridded samples: scatter (28 B/sample in + 8 B RMW) + memset (8 B/px) + cuFFT (two passes,
-            # 16 B r/w each) + real part (8 B in, 4 B out) — HBM-bound
-            gbytes = 36.0 * Zloc + (8.0 + 32.0 + 12.0) * MN
+            # gridded samples: scatter (28 B/sample in + 8 B RMW) + memset of the half plane (4 B/px) + cuFFT C2R
+            # (two passes: 4 B/px in + ~8 B/px intermediate r/w + 4 B/px real out) — HBM-bound
+            gbytes = 36.0 * Zloc + (4.0 + 16.0) * MN
             ach = gbytes / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else None
-            roof = {"bound": "hbm", "kernel": "k_gridfft_scatter + cuFFT C2C + k_gridfft_real (gridded samples: the DFT is an FFT)",
+            roof = {"bound": "hbm", "kernel": "k_gridfft_scatter + cuFFT C2R (gridded samples: the DFT is an FFT of the Hermitian half plane)",
                     "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": (ach / pk["hbm_gbs"]) if ach else None,
                     "traffic": None,
-                    "note": f"algorithmic bytes 36*Z + 52*M*N = {gbytes:.3e} per gradient on this rank, {kern_ms:.3f} ms; "
+                    "note": f"algorithmic bytes 36*Z + 20*M*N = {gbytes:.3e} per gradient on this rank, {kern_ms:.3f} ms; "
                             f"peak = measured HBM copy bandwidth ({pk['source']})"}
         if mode == 1 and args.config == "c2" and args.scale == 1.0 and world == 1:
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this exact workload,

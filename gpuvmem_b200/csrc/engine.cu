@@ -116,6 +116,8 @@ int gvm_destroy(gvm_engine* e) {
   cudaDeviceSynchronize();
   for (auto& c : e->chans) free_channel(c);
   if (e->have_plan) cufftDestroy(e->plan);
+  if (e->have_plan_r2c) cufftDestroy(e->plan_r2c);
+  if (e->have_plan_c2r) cufftDestroy(e->plan_c2r);
   cudaFree(e->I_nu); cudaFree(e->V); cudaFree(e->noise); cudaFree(e->gcf); cudaFree(e->dchi2);
   cudaFree(e->degrid_table);
   cudaFree(e->grad_scratch); cudaFree(e->pixtab); cudaFree(e->I_stage); cudaFree(e->grad_stage);
@@ -137,6 +139,8 @@ int gvm_set_stream(gvm_engine* e, void* s) {
   e->own_stream = false;
   e->stream = (cudaStream_t)s;
   if (e->have_plan) cufftSetStream(e->plan, e->stream);
+  if (e->have_plan_r2c) cufftSetStream(e->plan_r2c, e->stream);
+  if (e->have_plan_c2r) cufftSetStream(e->plan_c2r, e->stream);
   return 0;
 }
 void* gvm_get_stream(gvm_engine* e) { return (void*)e->stream; }
@@ -197,7 +201,15 @@ int gvm_set_degrid_kernel(gvm_engine* e, const float* table_host, int m, int n, 
   return 0;
 }
 
+int gvm_set_forward_mode(gvm_engine* e, int mode) {
+  if (mode < GVM_FORWARD_AUTO || mode > GVM_FORWARD_HALF) { gvm_set_error("gvm_set_forward_mode: unknown mode %d", mode); return 1; }
+  e->forward_mode = mode;
+  return 0;
+}
+int gvm_last_forward_mode(gvm_engine* e) { return e->last_forward_half ? GVM_FORWARD_HALF : GVM_FORWARD_FULL; }
+
 int gvm_get_model_grid(gvm_engine* e, float* V_host) {
+  if (e->last_forward_half) { gvm_set_error("gvm_get_model_grid: the last forward pass used the half-plane model (gvm_set_forward_mode)"); return 1; }
   const size_t MN = (size_t)e->cfg.M * e->cfg.N;
   GVM_CUDA(cudaSetDevice(e->cfg.device));
   GVM_CUDA(cudaMemcpyAsync(V_host, e->V, MN * sizeof(float2), cudaMemcpyDeviceToHost, e->stream));

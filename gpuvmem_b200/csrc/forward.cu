@@ -93,10 +93,11 @@ __global__ void __launch_bounds__(256) k_prep_channel(
 // ---------------------------------------------------------------------------
 // clip2IWNoise (src/functions.cu:2694-2719) fused with calculateInu (:3939-3966),
 // apply_beam2I (:2424-2444) and apply_GCF (:2468-2476). One thread per pixel.
-template <bool kClip>
+// kReal: the pre-FFT image is written as a real plane (half-plane forward model, see k_degrid_chi2).
+template <bool kClip, bool kReal>
 __global__ void __launch_bounds__(256) k_image_prep(
     float* __restrict__ I, const float* __restrict__ noise, const float* __restrict__ gcf,
-    float2* __restrict__ I_nu, long N, long M, float noise_cut, float minpix, float eta,
+    void* __restrict__ I_nu_out, long N, long M, float noise_cut, float minpix, float eta,
     float threshold, int schedule, float nu, float nu_0, float fg_scale, float D, float pb_factor,
     float pb_cutoff, float xobs, float yobs, double DELTAX, double DELTAY, int primary_beam) {
   const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -123,7 +124,8 @@ __global__ void __launch_bounds__(256) k_image_prep(
                                       DELTAY, primary_beam);
   v = v * atten * fg_scale;
   if (gcf != nullptr) v = v * gcf[idx];
-  I_nu[idx] = make_float2(v, 0.0f);
+  if (kReal) reinterpret_cast<float*>(I_nu_out)[idx] = v;
+  else reinterpret_cast<float2*>(I_nu_out)[idx] = make_float2(v, 0.0f);
 }
 
 // phase_rotate: src/functions.cu:2483-2518.
@@ -162,9 +164,38 @@ struct GvmConvDegrid {
   const float* table;    // [km][kn] kernel, device
   double deltau, deltav;
   int km, kn, sx, sy;
+  double upix, vpix;     // half-plane mode: xphs / M, yphs / N of phase_rotate
 };
 
-template <bool kKeepVm, bool kConv>
+enum { kGridFull = 0, kGridConv = 1, kGridHalf = 2 };
+
+// kGridHalf — half-plane forward model for blocks with few samples per pixel (gridded data, 4 Z <= M N):
+// the pre-FFT image is REAL (calculateInu writes imag = 0, src/functions.cu:3963), so its unnormalised
+// inverse DFT is the conjugate of a real-to-complex forward transform, known on the half plane
+// Vh[N][N/2+1]: V[r][c] = conj(Vh[r][c]) for c <= N/2, V[r][c] = Vh[(N-r)%N][N-c] beyond. cuFFT R2C moves
+// half the bytes of the C2C transform, and phase_rotate (an image-sized pass) is applied to the four taps
+// of every sample instead — the same float arithmetic per tap (src/functions.cu:2491-2517), 4 Z
+// sincospif instead of M N.
+__device__ __forceinline__ float2 gvm_fetch_half(const float2* __restrict__ Vh, int row, int col, int N,
+                                                 double upix, double vpix) {
+  const int NH = N / 2 + 1;
+  float2 g;
+  if (col <= N / 2) {
+    g = __ldg(&Vh[(long)row * NH + col]);
+    g.y = -g.y;
+  } else {
+    g = __ldg(&Vh[(long)(row ? N - row : 0) * NH + (N - col)]);
+  }
+  float u, v;
+  if (col < N / 2) u = upix * col; else u = upix * (col - N);
+  if (row < N / 2) v = vpix * row; else v = vpix * (row - N);
+  const float phase = -2.0f * (u + v);
+  float s, c;
+  sincospif(phase, &s, &c);
+  return make_float2(g.x * c - g.y * s, g.x * s + g.y * c);  // cuCmulf, as k_phase_rotate
+}
+
+template <bool kKeepVm, int kMode>
 __global__ void __launch_bounds__(kVisThreads) k_degrid_chi2(
     const float2* __restrict__ V, const uint32_t* __restrict__ cell,
     const float2* __restrict__ frac, const float2* __restrict__ Vo, const float* __restrict__ w,
@@ -175,6 +206,7 @@ __global__ void __launch_bounds__(kVisThreads) k_degrid_chi2(
   __shared__ float s_sum[kVisThreads / 32];
   __shared__ float s_max[kVisThreads / 32];
   __shared__ bool s_last;
+  constexpr bool kConv = kMode == kGridConv;
   __shared__ float s_tab[kConv ? GVM_MAX_CKERNEL : 1];
   if (kConv) {
     for (int t = threadIdx.x; t < cv.km * cv.kn; t += blockDim.x) s_tab[t] = cv.table[t];
@@ -210,10 +242,18 @@ __global__ void __launch_bounds__(kVisThreads) k_degrid_chi2(
       const int i1 = (int)(c & 0xFFFFu), j1 = (int)(c >> 16);
       const int i2 = (i1 + 1 == N) ? 0 : i1 + 1;
       const int j2 = (j1 + 1 == N) ? 0 : j1 + 1;
-      const float2 v11 = __ldg(&V[(long)N * j1 + i1]);
-      const float2 v12 = __ldg(&V[(long)N * j2 + i1]);
-      const float2 v21 = __ldg(&V[(long)N * j1 + i2]);
-      const float2 v22 = __ldg(&V[(long)N * j2 + i2]);
+      float2 v11, v12, v21, v22;
+      if (kMode == kGridHalf) {
+        v11 = gvm_fetch_half(V, j1, i1, N, cv.upix, cv.vpix);
+        v12 = gvm_fetch_half(V, j2, i1, N, cv.upix, cv.vpix);
+        v21 = gvm_fetch_half(V, j1, i2, N, cv.upix, cv.vpix);
+        v22 = gvm_fetch_half(V, j2, i2, N, cv.upix, cv.vpix);
+      } else {
+        v11 = __ldg(&V[(long)N * j1 + i1]);
+        v12 = __ldg(&V[(long)N * j2 + i1]);
+        v21 = __ldg(&V[(long)N * j1 + i2]);
+        v22 = __ldg(&V[(long)N * j2 + i2]);
+      }
       const float du = f.x, dv = f.y;
       const float w11 = (1.0f - du) * (1.0f - dv);
       const float w12 = (1.0f - du) * dv;
@@ -314,26 +354,45 @@ int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, 
   const gvm_config& g = e->cfg;
   const long MN = g.M * g.N;
   const int pix_blocks = (int)((MN + 255) / 256);
-  if (first)
-    k_image_prep<true><<<pix_blocks, 256, 0, e->stream>>>(
-        I_dev, e->noise, e->gcf, e->I_nu, g.N, g.M, g.noise_cut, g.minpix, g.eta, g.threshold,
-        flag_opt, c.d.freq, g.nu_0, g.fg_scale, c.d.antenna_diameter, c.d.pb_factor, c.d.pb_cutoff,
-        c.d.ref_xobs_pix, c.d.ref_yobs_pix, g.DELTAX, g.DELTAY, c.d.primary_beam);
-  else
-    k_image_prep<false><<<pix_blocks, 256, 0, e->stream>>>(
-        I_dev, e->noise, e->gcf, e->I_nu, g.N, g.M, g.noise_cut, g.minpix, g.eta, g.threshold,
-        flag_opt, c.d.freq, g.nu_0, g.fg_scale, c.d.antenna_diameter, c.d.pb_factor, c.d.pb_cutoff,
-        c.d.ref_xobs_pix, c.d.ref_yobs_pix, g.DELTAX, g.DELTAY, c.d.primary_beam);
-  GVM_LAUNCH(e);
-  if (cufftExecC2C(e->plan, reinterpret_cast<cufftComplex*>(e->I_nu),
-                   reinterpret_cast<cufftComplex*>(e->V), CUFFT_INVERSE) != CUFFT_SUCCESS) {
-    gvm_set_error("cufftExecC2C failed");
-    return 1;
+  // half-plane forward model (R2C + per-tap phase rotation) when the block has few samples per pixel
+  bool half = e->forward_mode == GVM_FORWARD_HALF || (e->forward_mode == GVM_FORWARD_AUTO && 4 * (long)c.Z <= MN);
+  if (e->degrid_table || (g.N & 1)) half = false;
+  if (half && !e->have_plan_r2c) {
+    if (cufftPlan2d(&e->plan_r2c, (int)g.N, (int)g.M, CUFFT_R2C) != CUFFT_SUCCESS) {
+      gvm_set_error("cufftPlan2d(R2C) failed");
+      return 1;
+    }
+    e->have_plan_r2c = true;
+    cufftSetStream(e->plan_r2c, e->stream);
   }
+  e->last_forward_half = half ? 1 : 0;
+#define GVM_PREP(CLIP, REAL)                                                                              \
+  k_image_prep<CLIP, REAL><<<pix_blocks, 256, 0, e->stream>>>(                                            \
+      I_dev, e->noise, e->gcf, e->I_nu, g.N, g.M, g.noise_cut, g.minpix, g.eta, g.threshold, flag_opt,    \
+      c.d.freq, g.nu_0, g.fg_scale, c.d.antenna_diameter, c.d.pb_factor, c.d.pb_cutoff, c.d.ref_xobs_pix, \
+      c.d.ref_yobs_pix, g.DELTAX, g.DELTAY, c.d.primary_beam)
+  if (first) { if (half) GVM_PREP(true, true); else GVM_PREP(true, false); }
+  else       { if (half) GVM_PREP(false, true); else GVM_PREP(false, false); }
+#undef GVM_PREP
   GVM_LAUNCH(e);
-  k_phase_rotate<<<pix_blocks, 256, 0, e->stream>>>(e->V, g.M, g.N, (double)c.d.phs_xobs_pix,
-                                                     (double)c.d.phs_yobs_pix);
-  GVM_LAUNCH(e);
+  if (half) {
+    if (cufftExecR2C(e->plan_r2c, reinterpret_cast<cufftReal*>(e->I_nu),
+                     reinterpret_cast<cufftComplex*>(e->V)) != CUFFT_SUCCESS) {
+      gvm_set_error("cufftExecR2C failed");
+      return 1;
+    }
+    GVM_LAUNCH(e);
+  } else {
+    if (cufftExecC2C(e->plan, reinterpret_cast<cufftComplex*>(e->I_nu),
+                     reinterpret_cast<cufftComplex*>(e->V), CUFFT_INVERSE) != CUFFT_SUCCESS) {
+      gvm_set_error("cufftExecC2C failed");
+      return 1;
+    }
+    GVM_LAUNCH(e);
+    k_phase_rotate<<<pix_blocks, 256, 0, e->stream>>>(e->V, g.M, g.N, (double)c.d.phs_xobs_pix,
+                                                       (double)c.d.phs_yobs_pix);
+    GVM_LAUNCH(e);
+  }
   long want = (c.Z + (long)kVisThreads * kVisPerThread - 1) / ((long)kVisThreads * kVisPerThread);
   int blocks = (int)(want < 1 ? 1 : (want > e->red_blocks ? e->red_blocks : want));
   double* partials = e->red_partials + (size_t)slot * e->red_blocks;
@@ -347,12 +406,15 @@ int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, 
       cv.deltau = 1.0 / (g.M * deltax); cv.deltav = 1.0 / (g.N * deltay);
       cv.km = e->degrid_m; cv.kn = e->degrid_n; cv.sx = e->degrid_sx; cv.sy = e->degrid_sy;
     }
-#define GVM_DEGRID(KEEP, CONV)                                                                     \
-  k_degrid_chi2<KEEP, CONV><<<blocks, kVisThreads, 0, e->stream>>>(                                \
+    cv.upix = (double)c.d.phs_xobs_pix / (double)g.M;
+    cv.vpix = (double)c.d.phs_yobs_pix / (double)g.N;
+#define GVM_DEGRID(KEEP, MODE)                                                                     \
+  k_degrid_chi2<KEEP, MODE><<<blocks, kVisThreads, 0, e->stream>>>(                                \
       e->V, c.cell, c.frac, c.Vo, c.w, c.Vr, KEEP ? c.Vm : nullptr, c.Z, (int)g.N, partials, pmax, \
       e->red_counter + slot, e->red_sum + slot, e->red_max + slot, cv)
-    if (e->degrid_table) { if (g.keep_vm) GVM_DEGRID(true, true); else GVM_DEGRID(false, true); }
-    else                 { if (g.keep_vm) GVM_DEGRID(true, false); else GVM_DEGRID(false, false); }
+    if (e->degrid_table) { if (g.keep_vm) GVM_DEGRID(true, kGridConv); else GVM_DEGRID(false, kGridConv); }
+    else if (half)       { if (g.keep_vm) GVM_DEGRID(true, kGridHalf); else GVM_DEGRID(false, kGridHalf); }
+    else                 { if (g.keep_vm) GVM_DEGRID(true, kGridFull); else GVM_DEGRID(false, kGridFull); }
 #undef GVM_DEGRID
     GVM_LAUNCH(e);
   }

@@ -61,6 +61,12 @@ struct gvm_engine {
   bool own_stream = false;
   cufftHandle plan = 0;
   bool have_plan = false;
+  cufftHandle plan_r2c = 0;       // half-plane forward model (forward.cu), created on first use
+  bool have_plan_r2c = false;
+  cufftHandle plan_c2r = 0;       // gridded gradient / error maps (grad_gridfft.cu), created on first use
+  bool have_plan_c2r = false;
+  int forward_mode = 0;           // GVM_FORWARD_*
+  int last_forward_half = 0;
   int sm_count = 148;
   // image-sized scratch
   float2* I_nu = nullptr;   // [MN] complex

@@ -178,6 +178,13 @@ class Engine:
         sx, sy = support if support is not None else (n // 2, m // 2)
         self._ck(self.lib.gvm_set_degrid_kernel(self.h, table.ctypes.data, m, n, int(sx), int(sy)))
 
+    def set_forward_mode(self, mode):
+        """0 auto, 1 full plane (C2C + phase_rotate, the reference's pipeline), 2 half plane (R2C + per-tap rotation)."""
+        self._ck(self.lib.gvm_set_forward_mode(self.h, mode))
+
+    def last_forward_mode(self):
+        return self.lib.gvm_last_forward_mode(self.h)
+
     def get_model_grid(self):
         out = np.empty((self.N, self.N, 2), np.float32)
         self._ck(self.lib.gvm_get_model_grid(self.h, out.ctypes.data))

@@ -53,6 +53,8 @@ SIGNATURES = {
     "gvm_set_gcf": (C.c_int, [_P, _P]),
     "gvm_set_degrid_kernel": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gvm_get_model_grid": (C.c_int, [_P, _P]),
+    "gvm_set_forward_mode": (C.c_int, [_P, C.c_int]),
+    "gvm_last_forward_mode": (C.c_int, [_P]),
     "gvm_add_channel": (C.c_int, [_P, C.POINTER(gvm_channel_desc), C.c_int64, _P, _P, _P, C.POINTER(C.c_int)]),
     "gvm_clear_channels": (C.c_int, [_P]),
     "gvm_num_channels": (C.c_int, [_P]),

@@ -112,6 +112,16 @@ int gvm_set_gcf(gvm_engine* e, const float* gcf_host);
  * gradient stays the exact DFT of the residuals (DChi2), as in the reference. */
 int gvm_set_degrid_kernel(gvm_engine* e, const float* table_host, int m, int n,
                           int support_x, int support_y);
+/* How gvm_chi2 transforms the image. FULL is the reference's pipeline: complex
+ * pre-FFT image, cuFFT C2C inverse (src/functions.cu:2165), phase_rotate over the
+ * whole grid (:2483). HALF uses that the pre-FFT image is real: cuFFT R2C onto the
+ * half plane (conjugated on read) and the phase rotation applied to the four
+ * bilinear taps of every sample — half the FFT bytes and no image-sized rotation
+ * pass; same float arithmetic per tap. AUTO picks HALF for blocks with
+ * 4 Z <= M N (gridded data). Not combined with gvm_set_degrid_kernel. */
+enum { GVM_FORWARD_AUTO = 0, GVM_FORWARD_FULL = 1, GVM_FORWARD_HALF = 2 };
+int gvm_set_forward_mode(gvm_engine* e, int mode);
+int gvm_last_forward_mode(gvm_engine* e);   /* GVM_FORWARD_FULL or GVM_FORWARD_HALF */
 /* The model grid of the LAST channel evaluated by gvm_chi2 (after phase_rotate):
  * [M][N] complex as interleaved floats, DC at [0,0] — device_V of varsPerGPU
  * (include/framework.cuh:49-55). For tests and diagnostics. */

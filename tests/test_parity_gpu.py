@@ -377,6 +377,7 @@ def test_gridded_gradient_as_fft_vs_direct_sum_and_oracle(oracle):
         g_fft = torch.zeros_like(I_dev)
         e.dchi2(I_dev, g_fft, flag_opt=0)
         assert e.last_grad_mode() == 4, "AUTO must pick the FFT path for gridded samples"
+        assert e.last_forward_mode() == (2 if 4 * len(wo) <= p.M * p.N else 1), "AUTO: half plane iff 4 Z <= M N"
         e.set_grad_mode(GRAD_SIMT)
         g_sum = torch.zeros_like(I_dev)
         e.dchi2(I_dev, g_sum, flag_opt=0)
@@ -552,3 +553,46 @@ def test_normalize_divides_by_the_block_size(small, oracle, mode):
     gg = g[0].cpu().numpy().reshape(-1)[pix]
     assert np.linalg.norm(gg - tot) / np.linalg.norm(tot) <= 2e-5
     e.chi2(I_dev)        # leave the shared engine in its default state
+
+
+def test_half_plane_forward_model_equals_the_full_plane_one(small, oracle):
+    """GVM_FORWARD_HALF (cuFFT R2C on the real pre-FFT image + phase rotation per bilinear tap) against
+    GVM_FORWARD_FULL (the reference's C2C + phase_rotate pipeline) and the oracle; AUTO keeps FULL here
+    (more samples than pixels / 4)."""
+    torch = _torch()
+    from gpuvmem_b200.engine import EngineError
+    p, e = small
+    I = _test_image(e)
+    try:
+        e.set_forward_mode(1)
+        I_full = torch.from_numpy(I).cuda()
+        c_full = e.chi2(I_full)
+        assert e.last_forward_mode() == 1
+        full = [e.get_vis(c, want=("Vm", "Vr", "w")) for c in range(p.nchan)]
+        e.set_forward_mode(2)
+        I_half = torch.from_numpy(I).cuda()
+        c_half = e.chi2(I_half)
+        assert e.last_forward_mode() == 2
+        assert torch.equal(I_full, I_half), "the clip side effect is the same"
+        assert abs(c_half - c_full) <= 2e-6 * c_full, (c_half, c_full)
+        for c in range(p.nchan):
+            h = e.get_vis(c, want=("Vm", "Vr", "w"))
+            scale = np.abs(full[c]["Vm"]).max()
+            assert np.array_equal(h["w"], full[c]["w"])
+            assert np.abs(h["Vm"] - full[c]["Vm"]).max() <= 3e-6 * scale
+        with pytest.raises(EngineError, match="half-plane"):
+            e.get_model_grid()
+        # gradient on the half-plane residuals, against the fp64 oracle
+        e.set_grad_mode(GRAD_UMMA)
+        g = torch.zeros_like(I_half)
+        e.dchi2(I_half, g, flag_opt=0)
+        pix = np.arange(0, p.N * p.N, 29)
+        want = _grad_oracle_sample(oracle, p, e, I_half.cpu().numpy(), pix, 0)
+        got = g[0].cpu().numpy().reshape(-1)[pix]
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 2e-5
+        e.set_forward_mode(0)
+        e.chi2(I_half)
+        assert e.last_forward_mode() == 1, "AUTO: 4 Z > M N keeps the full-plane pipeline"
+    finally:
+        e.set_forward_mode(0)
+        e.chi2(torch.from_numpy(I).cuda())
