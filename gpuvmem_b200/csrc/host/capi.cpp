@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../../include/gvm_host.h"
+#include "fits.hpp"
 #include "synthesizer.hpp"
 
 using namespace gpuvmem;
@@ -316,6 +317,40 @@ int gvmh_factory_has(const char* kind, const char* name) {
   if (k == "ObjectiveFunction") return Singleton<Factory<ObjectiveFunction, std::string>>::Instance().Has(id);
   return 0;
 }
+int gvmh_fits_read(const char* path, double* header16, float* data_out, int64_t cap) {
+  FitsImage img;
+  std::string err;
+  if (!fitsRead(path, data_out != nullptr, &img, &err)) { std::fprintf(stderr, "gvmh_fits_read: %s\n", err.c_str()); return 1; }
+  headerValues h;
+  const bool wcs = fitsHeaderValues(img, &h, &err);
+  if (header16) {
+    const double vals[16] = {(double)img.naxis1, (double)img.naxis2, (double)img.bitpix, wcs ? 1.0 : 0.0, h.DELTAX, h.DELTAY,
+                             h.ra, h.dec, h.crpix1, h.crpix2, h.beam_bmaj, h.beam_bmin, h.beam_bpa, (double)h.beam_noise,
+                             (double)h.equinox, (double)img.cards.size()};
+    for (int i = 0; i < 16; i++) header16[i] = vals[i];
+  }
+  if (data_out) {
+    if ((int64_t)img.data.size() > cap) return 2;
+    std::memcpy(data_out, img.data.data(), img.data.size() * sizeof(float));
+  }
+  return 0;
+}
+int gvmh_fits_write(const char* path, const float* data, int64_t naxis1, int64_t naxis2, const char* template_path,
+                    const char* bunit, int niter, const char* radesys, float equinox, double crval1, double crval2) {
+  FitsImage tmpl;
+  std::string err;
+  if (template_path && *template_path && !fitsRead(template_path, false, &tmpl, &err)) {
+    std::fprintf(stderr, "gvmh_fits_write: %s\n", err.c_str());
+    return 1;
+  }
+  if (!fitsWriteFloat(path, data, (long)naxis1, (long)naxis2, tmpl.cards, bunit ? bunit : "", niter,
+                      radesys ? radesys : "ICRS", equinox, crval1, crval2, &err)) {
+    std::fprintf(stderr, "gvmh_fits_write: %s\n", err.c_str());
+    return 1;
+  }
+  return 0;
+}
+
 int gvmh_parse_args(const char* args, char* json_out, size_t cap) {
   G() = Globals();
   std::vector<std::string> toks = splitArgs(args ? args : "");

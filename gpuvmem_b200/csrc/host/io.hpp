@@ -39,6 +39,8 @@ class Io {
   void setPath(const std::string& s) { path = s; }
   void setMN(long m, long n) { M = m; N = n; }
   void setRADec(double r, double d) { ra = r; dec = d; }
+  // pixel scale (degrees) and reference pixel, for image headers written without a template
+  void setPixelGrid(double dx, double dy, double cp1, double cp2) { cdelt1 = dx; cdelt2 = dy; crpix1 = cp1; crpix2 = cp2; }
   void setFrame(const std::string& s) { frame = s; }
   void setEquinox(float e) { equinox = e; }
   void setPrintImages(bool p) { print_images = p; }
@@ -53,7 +55,7 @@ class Io {
  protected:
   std::string input, output, path = "mem/", frame = "ICRS";
   long M = 0, N = 0;
-  double ra = 0, dec = 0;
+  double ra = 0, dec = 0, cdelt1 = 0, cdelt2 = 0, crpix1 = 0, crpix2 = 0;
   float equinox = 2000.0f, random_probability = 1.0f;
   bool print_images = false, apply_noise = false, store_model = false;
   int gridding = 0;

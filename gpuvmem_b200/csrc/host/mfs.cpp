@@ -247,6 +247,7 @@ void MFS::configure(int argc, char** argv) {
   g.crpix2 = header.crpix2;
   ioImageHandler->setMN(g.M, g.N);
   ioImageHandler->setRADec(g.ra, g.dec);
+  ioImageHandler->setPixelGrid(g.DELTAX, g.DELTAY, g.crpix1, g.crpix2);
   ioImageHandler->setFrame(header.radesys);
   ioImageHandler->setEquinox(header.equinox);
   if (header.beam_noise > 0.0f) setVisNoise(header.beam_noise);

@@ -44,6 +44,9 @@ SIGNATURES = {
     "gvmh_clear_run": (C.c_int, [_P]),
     "gvmh_set_lbfgs_k": (C.c_int, [_P, C.c_int]),
     "gvmh_write_outputs": (C.c_int, [_P]),
+    "gvmh_fits_read": (C.c_int, [C.c_char_p, _P, _P, C.c_int64]),
+    "gvmh_fits_write": (C.c_int, [C.c_char_p, _P, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p,
+                                  C.c_float, C.c_double, C.c_double]),
     "gvmh_error_image": (C.c_int, [_P, _P]),
     "gvmh_set_image": (C.c_int, [_P, _P]),
     "gvmh_get_image": (C.c_int, [_P, _P]),
@@ -270,6 +273,36 @@ def ckernel_gcf(name, m, n, M, N, dx, dy):
     g = np.zeros((M, N), np.float32)
     h.gvmh_ckernel_gcf(name.encode(), m, n, M, N, dx, dy, g.ctypes.data)
     return g
+
+
+FITS_HEADER_NAMES = ["naxis1", "naxis2", "bitpix", "has_wcs", "cdelt1", "cdelt2", "crval1", "crval2", "crpix1", "crpix2",
+                     "bmaj", "bmin", "bpa", "noise", "equinox", "ncards"]
+
+
+def fits_read(path, want_data=True):
+    """The host layer's FITS reader (csrc/host/fits.cpp): (header dict, data [naxis2][naxis1] float32 or None)."""
+    h = load_host_library()
+    hdr = np.zeros(16)
+    if h.gvmh_fits_read(path.encode(), hdr.ctypes.data, None, 0) != 0:
+        raise RuntimeError(f"cannot read {path} as FITS")
+    d = dict(zip(FITS_HEADER_NAMES, hdr.tolist()))
+    data = None
+    if want_data:
+        data = np.empty((int(d["naxis2"]), int(d["naxis1"])), np.float32)
+        if h.gvmh_fits_read(path.encode(), hdr.ctypes.data, data.ctypes.data, data.size) != 0:
+            raise RuntimeError(f"cannot read the image of {path}")
+    return d, data
+
+
+def fits_write(path, data, template=None, bunit="JY/PIXEL", niter=0, radesys="ICRS", equinox=2000.0, crval1=0.0,
+               crval2=0.0):
+    """The host layer's FITS writer (OCopyFITS semantics: template header copied, a few keys replaced)."""
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    rc = load_host_library().gvmh_fits_write(path.encode(), data.ctypes.data, data.shape[1], data.shape[0],
+                                             template.encode() if template else None, bunit.encode(), niter,
+                                             radesys.encode(), equinox, crval1, crval2)
+    if rc != 0:
+        raise RuntimeError(f"cannot write {path}")
 
 
 def factory_has(kind, name):

@@ -101,8 +101,16 @@ int gvmh_ckernel_table(const char* name, int m, int n, float sx, float sy, float
 /* CKernel::initializeGCF(M, N, dx, dy) image (M x N). */
 int gvmh_ckernel_gcf(const char* name, int m, int n, int M, int N, float dx, float dy, float* gcf);
 /* 1 if `name` is registered in the factory of `kind` ("Fi", "Optimizer", "CKernel",
- * "WeightingScheme", "Synthesizer", "Io", "ObjectiveFunction"). */
+ * "WeightingScheme", "Synthesizer", "Io", "ObjectiveFunction", "Error"). */
 int gvmh_factory_has(const char* kind, const char* name);
+/* The dependency-free FITS image reader/writer of the Io handlers (csrc/host/fits.hpp), for tests and
+ * Python callers. header16: naxis1, naxis2, bitpix, has_wcs, CDELT1, CDELT2, CRVAL1, CRVAL2, CRPIX1, CRPIX2,
+ * BMAJ, BMIN, BPA, NOISE (-1: absent), EQUINOX, number of header cards. data_out may be NULL. */
+int gvmh_fits_read(const char* path, double* header16, float* data_out, int64_t cap);
+/* OCopyFITS (src/MSFITSIO.cu:93-165): header of template_path (may be NULL) copied, BUNIT/NITER/NAXISn/
+ * RADESYS/EQUINOX/CRVALn replaced, BITPIX -32. */
+int gvmh_fits_write(const char* path, const float* data, int64_t naxis1, int64_t naxis2, const char* template_path,
+                    const char* bunit, int niter, const char* radesys, float equinox, double crval1, double crval2);
 /* getOptions on a command-line string; writes a JSON object of the parsed Vars. */
 int gvmh_parse_args(const char* args, char* json_out, size_t cap);
 /* linmin's bracketing + Brent search on a caller-supplied 1-D function (host logic test). */

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from gpuvmem_b200 import host, synth
+from gpuvmem_b200 import fits, host, synth
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -22,20 +22,27 @@ def test_command_line_reconstruction_with_error_maps(tmp_path):
     synth.write_gvms(p, gv)
     mem = str(tmp_path / "mem") + "/"
     os.makedirs(mem)
-    img = str(tmp_path / "image.f32")
-    args = ["-i", gv, "-m", gv, "-o", str(tmp_path / "out.gvmr"), "-O", img, "-p", mem, "-z", "0.001,0.2",
+    img = str(tmp_path / "image.fits")
+    # -m: a FITS model image whose header carries the astrometry (readFITSHeader, src/MSFITSIO.cu:262-325)
+    model = str(tmp_path / "mod_in.fits")
+    fits.write_fits(model, np.zeros((p.N, p.M), np.float32),
+                    {"CTYPE1": "RA---SIN", "CRVAL1": p.ra, "CDELT1": p.DELTAX, "CRPIX1": p.crpix1, "CTYPE2": "DEC--SIN",
+                     "CRVAL2": p.dec, "CDELT2": p.DELTAY, "CRPIX2": p.crpix2, "TELESCOP": p.telescope, "OBJECT": "synthetic"})
+    args = ["-i", gv, "-m", model, "-o", str(tmp_path / "out.gvmr"), "-O", img, "-p", mem, "-z", "0.001,0.2",
             "-Z", "0.01,0.0,0.001", "-t", "4", "-E", "-P"]
     r = subprocess.run([BIN] + args, capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, GVM_OPTIMIZER="CG-FRPRMN"))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "Calculating Error Images" in r.stdout
     N = p.N
-    out0 = np.fromfile(img, np.float32).reshape(N, N)
-    side = json.load(open(img + ".json"))
-    assert side["shape"] == [N, N] and side["bunit"] == "JY/PIXEL"
-    alpha = np.fromfile(mem + "alpha.fits", np.float32).reshape(N, N)
-    e0 = np.fromfile(mem + "error_Inu_0.fits", np.float32).reshape(N, N)
-    e1 = np.fromfile(mem + "error_alpha_0.fits", np.float32).reshape(N, N)
+    hdr, out0 = fits.read_fits(img)                      # written as FITS: the model's header copied (OCopyFITS)
+    out0 = out0.astype(np.float32)
+    assert hdr["NAXIS1"] == N and hdr["NAXIS2"] == N and hdr["BUNIT"] == "JY/PIXEL" and hdr["NITER"] == 4
+    assert hdr["CDELT1"] == p.DELTAX and hdr["CRPIX2"] == p.crpix2 and hdr["OBJECT"] == "synthetic"
+    assert abs(hdr["CRVAL1"] - p.ra) < 1e-9 and abs(hdr["CRVAL2"] - p.dec) < 1e-9
+    alpha = fits.read_fits(mem + "alpha.fits")[1].astype(np.float32)
+    e0 = fits.read_fits(mem + "error_Inu_0.fits")[1].astype(np.float32)
+    e1 = fits.read_fits(mem + "error_alpha_0.fits")[1].astype(np.float32)
     assert os.path.getsize(str(tmp_path / "out.gvmr")) > 8 + 12 + p.total_vis() * 20
 
     # the same run through the C entry points
@@ -71,8 +78,8 @@ def test_user_mask_and_radius_mask(tmp_path):
     base.close()
     mask = np.full((N, N), 1e30, np.float32)
     mask[40:90, 30:100] = 0.0
-    path = str(tmp_path / "mask.f32")
-    mask.tofile(path)
+    path = str(tmp_path / "mask.fits")
+    fits.write_fits(path, mask)                          # -U takes a FITS plane (read_data_float_FITS)
     s = host.Session(p, args=f"-z 0.001 -Z 0.01 -t 3 -U {path}")
     try:
         sc = s.scalars()
