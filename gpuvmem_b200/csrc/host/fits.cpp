@@ -39,7 +39,7 @@ std::string stringCard(const std::string& key, const std::string& value, const s
 }
 std::string numCard(const std::string& key, double v, const std::string& comment) {
   char num[40];
-  std::snprintf(num, sizeof(num), "%.15G", v);
+  std::snprintf(num, sizeof(num), "%.17G", v);   // 17 significant digits: doubles round-trip
   if (!std::strpbrk(num, ".EN")) std::strcat(num, ".");   // keep it a floating-point literal
   return makeCard(key, num, comment);
 }

@@ -16,7 +16,7 @@ def _card(key, value, comment=""):
     elif isinstance(value, (int, np.integer)):
         body = f"{key:<8}= {int(value):>20d}"
     else:
-        txt = f"{float(value):.15G}"
+        txt = f"{float(value):.17G}"
         if not any(ch in txt for ch in ".EN"):
             txt += "."
         body = f"{key:<8}= {txt:>20}"
