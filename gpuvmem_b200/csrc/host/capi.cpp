@@ -277,6 +277,15 @@ int gvmh_get_host_vis(gvmh_session* s, int chan, double* uvw_m, float* Vo, float
   if (w) std::memcpy(w, v.weight.data(), v.weight.size() * sizeof(float));
   return 0;
 }
+int gvmh_filter_gridding(gvmh_session* s, const char* ckernel, int ck_m, int ck_n) {
+  Filter* f = createObject<Filter, std::string>("Gridding");
+  CKernel* ck = ckernel && *ckernel ? makeCKernel(ckernel, ck_m, ck_n) : nullptr;
+  static_cast<Gridding*>(f)->setCKernel(ck);
+  f->applyCriteria(s->sy->getVisibilities());
+  delete f;
+  delete ck;
+  return 0;
+}
 const char* gvmh_exit_reason(gvmh_session* s) { return s->opt->getExitReason(); }
 int gvmh_history(gvmh_session* s, float* out, int cap) {
   const std::vector<float>& h = s->opt->getHistory();
@@ -312,6 +321,7 @@ int gvmh_factory_has(const char* kind, const char* name) {
   if (k == "CKernel") return Singleton<Factory<CKernel, std::string>>::Instance().Has(id);
   if (k == "WeightingScheme") return Singleton<Factory<WeightingScheme, std::string>>::Instance().Has(id);
   if (k == "Synthesizer") return Singleton<Factory<Synthesizer, std::string>>::Instance().Has(id);
+  if (k == "Filter") return Singleton<Factory<Filter, std::string>>::Instance().Has(id);
   if (k == "Error") return Singleton<Factory<Error, std::string>>::Instance().Has(id);
   if (k == "Io") return Singleton<Factory<Io, std::string>>::Instance().Has(id);
   if (k == "ObjectiveFunction") return Singleton<Factory<ObjectiveFunction, std::string>>::Instance().Has(id);

@@ -7,7 +7,7 @@
 
 namespace gpuvmem {
 
-struct Visibilities;   // the reference passes its (unused) Visibilities object through
+class Visibilities;   // visibilities.hpp; the reference passes its (unused) Visibilities object through
 
 class Error {
  public:

@@ -217,6 +217,9 @@ void MFS::configure(int argc, char** argv) {
     }
   }
   g.nMeasurementSets = (int)datasets.size();
+  if (!visibilities) visibilities = new Visibilities();      // src/mfs.cu:489-491
+  visibilities->setMSDataset(datasets);
+  visibilities->setNDatasets(g.nMeasurementSets);
   if (g.verbose_flag && !g.quiet) std::printf("Number of input datasets %d\n", g.nMeasurementSets);
 
   if (variables.initial_values == "NULL") {
@@ -488,6 +491,7 @@ void MFS::setDevice() {
   if (vis_noise <= 0.0) vis_noise = 0.5f * sqrtf(variance);
   der.beam_bmaj_deg = g.beam_bmaj; der.beam_bmin_deg = g.beam_bmin; der.beam_bpa_deg = g.beam_bpa;
   der.sum_weights = sum_weights; der.vis_noise = vis_noise; der.total_visibilities = total_visibilities;
+  if (visibilities) visibilities->setTotalVisibilities(total_visibilities);   // src/mfs.cu:553
 
   g.max_number_vis = 0;
   for (MSDataset& ds : datasets)
@@ -672,7 +676,7 @@ void MFS::writeImages() {
   if (g.print_errors) {
     if (!error) error = createObject<Error, std::string>("SecondDerivateError");
     if (!g.quiet) std::printf("Calculating Error Images\n");
-    error->calculateErrorImage(image, nullptr);
+    error->calculateErrorImage(image, visibilities);
     if (g.rank != 0) return;
     if (IoOrderError) {
       IoOrderError(image->getErrorImage(), ioImageHandler);
@@ -756,11 +760,65 @@ void MFS::unSetDevice() {
   functionPtr = nullptr;
 }
 
+
+// ---- Filter "Gridding" (src/gridding.cu) ------------------------------------------------------
+void gridDatasetsInPlace(std::vector<MSDataset>& datasets, CKernel* ckernel) {
+  Globals& g = G();
+  for (MSDataset& ds : datasets) {
+    int max = 0;
+    for (Field& f : ds.fields)
+      for (size_t i = 0; i < f.visibilities.size(); i++) {
+        long per_freq = 0;
+        for (size_t s = 0; s < f.visibilities[i].size(); s++) {
+          HVis& v = f.visibilities[i][s];
+          int64_t nout = 0;
+          GVM_CHECK(gvm_grid_block(g.firstgpu, g.M, g.N, g.deltau, g.deltav, f.nu[i], (int64_t)v.size(), v.uvw.data(),
+                                   v.Vo.data(), v.weight.data(), ckernel->getKernelPointer(), ckernel->getm(),
+                                   ckernel->getn(), ckernel->getSupportX(), ckernel->getSupportY(), nullptr, nullptr,
+                                   nullptr, &nout));
+          v.uvw.resize(3 * nout);
+          v.Vo.resize(2 * nout);
+          v.weight.resize(nout);
+          GVM_CHECK(gvm_grid_fetch(v.uvw.data(), v.Vo.data(), v.weight.data()));
+          v.Vm.assign(2 * nout, 0.0f);
+          v.Vr.assign(2 * nout, 0.0f);
+          if (i < f.numVisibilitiesPerFreqPerStoke.size() && s < f.numVisibilitiesPerFreqPerStoke[i].size())
+            f.numVisibilitiesPerFreqPerStoke[i][s] = (long)nout;
+          per_freq += (long)nout;
+          max = std::max<long>(max, (long)nout);
+        }
+        if (i < f.numVisibilitiesPerFreq.size()) f.numVisibilitiesPerFreq[i] = per_freq;
+      }
+    ds.data.max_number_visibilities_in_channel_and_stokes = max;
+  }
+  GVM_CHECK(gvm_grid_release());
+}
+
+void Gridding::setThreadsChecked(int t) {
+  if (t != 1 && t >= 1) threads = t;
+  else if (t != 1) std::printf("Number of threads set to 1\n");
+}
+
+void Gridding::applyCriteria(Visibilities* v) {
+  Globals& g = G();
+  if (g.deltau == 0.0 || g.deltav == 0.0) {
+    std::printf("ERROR: Gridding::applyCriteria needs the uv cell size (MFS::configure first)\n");
+    std::exit(-1);
+  }
+  PillBox2D fallback;
+  CKernel* ck = ckernel ? ckernel : &fallback;
+  ck->setSigmas(std::fabs(g.deltau), std::fabs(g.deltav));
+  ck->buildKernel();
+  gridDatasetsInPlace(v->getMSDataset(), ck);
+}
+
 namespace {
 Synthesizer* makeMFS() { return new MFS; }
 const bool kRegistered = registerCreationFunction<Synthesizer, std::string>("MFS", makeMFS);
 Error* makeSecondDerivateError() { return new SecondDerivateError; }
 const bool kRegisteredError = registerCreationFunction<Error, std::string>("SecondDerivateError", makeSecondDerivateError);
+Filter* makeGridding() { return new Gridding; }
+const bool kRegisteredGridding = registerCreationFunction<Filter, std::string>("Gridding", makeGridding);
 }  // namespace
 
 }  // namespace gpuvmem

@@ -11,6 +11,7 @@
 #include "image.hpp"
 #include "io.hpp"
 #include "optimizer.hpp"
+#include "visibilities.hpp"
 #include "weightingscheme.hpp"
 
 namespace gpuvmem {
@@ -52,6 +53,8 @@ class Synthesizer {
   virtual void writeResiduals() = 0;
 
   void setError(Error* e) { error = e; }
+  void setVisibilities(Visibilities* v) { visibilities = v; }
+  Visibilities* getVisibilities() { return visibilities; }
   void setOptimizator(Optimizer* min) { optimizer = min; }
   void setIoImageHandler(Io* h) { ioImageHandler = h; }
   void setIoVisibilitiesHandler(Io* h) { ioVisibilitiesHandler = h; }
@@ -81,6 +84,7 @@ class Synthesizer {
   Optimizer* optimizer = nullptr;
   CKernel* ckernel = nullptr;
   Error* error = nullptr;
+  Visibilities* visibilities = nullptr;
   Io* ioImageHandler = nullptr;
   Io* ioVisibilitiesHandler = nullptr;
   WeightingScheme* scheme = nullptr;

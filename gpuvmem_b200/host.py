@@ -48,6 +48,7 @@ SIGNATURES = {
     "gvmh_fits_write": (C.c_int, [C.c_char_p, _P, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p,
                                   C.c_float, C.c_double, C.c_double]),
     "gvmh_error_image": (C.c_int, [_P, _P]),
+    "gvmh_filter_gridding": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int]),
     "gvmh_set_image": (C.c_int, [_P, _P]),
     "gvmh_get_image": (C.c_int, [_P, _P]),
     "gvmh_set_iteration": (C.c_int, [_P, C.c_int]),
@@ -158,6 +159,10 @@ class Session:
 
     def write_outputs(self):
         self.h.gvmh_write_outputs(self.s)
+
+    def filter_gridding(self, ckernel="", ck_size=(0, 0)):
+        """Filter "Gridding" on the session's visibilities (host side, in place)."""
+        self.h.gvmh_filter_gridding(self.s, ckernel.encode(), ck_size[0], ck_size[1])
 
     def error_image(self):
         """Error "SecondDerivateError": (sigma I_nu0, sigma alpha) as [2][M][N]."""

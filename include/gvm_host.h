@@ -68,6 +68,10 @@ int gvmh_write_outputs(gvmh_session* s);   /* writeImages + writeResiduals */
  * src/functions.cu:4966-5040) on the session's image and the residuals of the last objective
  * evaluation; errors_host [2][M][N]: sigma(I_nu0), sigma(alpha). */
 int gvmh_error_image(gvmh_session* s, float* errors_host);
+/* Filter "Gridding" (src/gridding.cu:13-28): do_gridding over the session's Visibilities, in place, with
+ * the named CKernel (NULL/"": PillBox2D, the reference's default). The host-side samples change
+ * (gvmh_get_host_vis); the engine keeps what was uploaded. */
+int gvmh_filter_gridding(gvmh_session* s, const char* ckernel, int ck_m, int ck_n);
 
 /* ObjectiveFunction::calcFunction / calcGradient on the session's device image. */
 int gvmh_set_image(gvmh_session* s, const float* I_host);

@@ -104,3 +104,27 @@ def test_user_mask_and_radius_mask(tmp_path):
         assert np.array_equal(d, want)
     finally:
         s.close()
+
+
+def test_gridding_filter_equals_the_gridded_run():
+    """Filter "Gridding" (src/gridding.cu) applied to the Visibilities of an ungridded session gives the very
+    samples a `-g` session grids in MFS::configure (same kernel, natural weights): bit-identical."""
+    p = synth.make_problem(N=128, nvis=15000, nchan=2, freq0=1.0e11, bandwidth=2e9, seed=91, grid_fill=0.9)
+    host.set_quiet(True)
+    a = host.Session(p, args="-z 0.001 -Z 0.01 -t 2 -g 1", ckernel="Gaussian2D", ck_size=(7, 7))
+    try:
+        want = [a.host_vis(c) for c in range(p.nchan)]
+    finally:
+        a.close()
+    b = host.Session(p, args="-z 0.001 -Z 0.01 -t 2")
+    try:
+        before = [len(b.host_vis(c)[2]) for c in range(p.nchan)]
+        b.filter_gridding("Gaussian2D", (7, 7))
+        for c in range(p.nchan):
+            uvw, Vo, w = b.host_vis(c)
+            assert len(w) < before[c] and len(w) == len(want[c][2])
+            assert np.array_equal(uvw.view(np.uint64), want[c][0].view(np.uint64))
+            assert np.array_equal(Vo.view(np.uint32), want[c][1].view(np.uint32))
+            assert np.array_equal(w.view(np.uint32), want[c][2].view(np.uint32))
+    finally:
+        b.close()

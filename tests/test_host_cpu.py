@@ -33,7 +33,8 @@ def test_factory_keys_match_the_reference():
             "Fi": ["Chi2", "Entropy", "L1-Norm", "TotalVariation", "TotalSquaredVariation", "Laplacian", "Quadratic",
                    "GEntropy", "GL1Norm"],
             "CKernel": ["PillBox2D", "Gaussian2D", "GaussianSinc2D", "Sinc2D", "PSWF"],
-            "WeightingScheme": ["Natural", "Uniform", "Briggs", "Radial"], "Io": ["IoMS", "IoFITS"]}
+            "WeightingScheme": ["Natural", "Uniform", "Briggs", "Radial"], "Io": ["IoMS", "IoFITS"],
+            "Filter": ["Gridding"], "Error": ["SecondDerivateError"]}
     for kind, names in keys.items():
         for n in names:
             assert host.factory_has(kind, n), (kind, n)
