@@ -107,7 +107,8 @@ int gvm_create(const gvm_config* cfg, gvm_engine** out) {
 static void free_channel(GvmChannel& c) {
   cudaFree(c.uvw_l); cudaFree(c.cell); cudaFree(c.frac); cudaFree(c.Vo); cudaFree(c.w);
   cudaFree(c.Vr); cudaFree(c.Vm); cudaFree(c.du64); cudaFree(c.dv64); cudaFree(c.wz);
-  cudaFree(c.amp); cudaFree(c.gam);
+  cudaFree(c.amp); cudaFree(c.gam); cudaFree(c.atten);
+  c.atten = nullptr;
 }
 
 int gvm_destroy(gvm_engine* e) {
@@ -265,6 +266,7 @@ int gvm_clear_channels(gvm_engine* e) {
   GVM_CUDA(cudaStreamSynchronize(e->stream));
   for (auto& c : e->chans) free_channel(c);
   e->chans.clear();
+  e->atten_cache_bytes = 0;
   return 0;
 }
 

@@ -38,6 +38,7 @@ __global__ void k_wsum_finish(const double* __restrict__ partials, int n, double
 }
 
 struct ErrParams {
+  const float* atten;   // cached attenuation plane or null
   long N, M;
   float noise_cut, freq, nu_0, D, pb_factor, pb_cutoff, xobs, yobs;
   double DELTAX, DELTAY;
@@ -58,8 +59,9 @@ __global__ void __launch_bounds__(256) k_err_accumulate(float* __restrict__ err,
     return;
   }
   const int i = (int)(idx / p.N), j = (int)(idx % p.N);
-  const float atten = gvm_attenuation(i, j, p.D, p.pb_factor, p.pb_cutoff, p.freq, p.xobs, p.yobs,
-                                      p.DELTAX, p.DELTAY, p.primary_beam);
+  const float atten = p.atten ? p.atten[idx]
+                              : gvm_attenuation(i, j, p.D, p.pb_factor, p.pb_cutoff, p.freq, p.xobs, p.yobs,
+                                                p.DELTAX, p.DELTAY, p.primary_beam);
   const float sum_weights = (float)wsum[0];
   const float nudiv = p.freq / p.nu_0;
   const float I0 = I[idx], alpha = I[MN + idx];
@@ -118,6 +120,7 @@ extern "C" int gvm_error_maps(gvm_engine* e, const float* I_dev, int dist_mode, 
       if (gvm_dist_allreduce_f64(e, wsum, 1)) return 1;
     }
     ErrParams p;
+    p.atten = gvm_channel_atten(e, c);
     p.N = g.N; p.M = g.M; p.noise_cut = g.noise_cut; p.freq = c.d.freq; p.nu_0 = g.nu_0;
     p.D = c.d.antenna_diameter; p.pb_factor = c.d.pb_factor; p.pb_cutoff = c.d.pb_cutoff;
     p.xobs = c.d.ref_xobs_pix; p.yobs = c.d.ref_yobs_pix; p.DELTAX = g.DELTAX; p.DELTAY = g.DELTAY;

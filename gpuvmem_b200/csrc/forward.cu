@@ -94,10 +94,19 @@ __global__ void __launch_bounds__(256) k_prep_channel(
 // clip2IWNoise (src/functions.cu:2694-2719) fused with calculateInu (:3939-3966),
 // apply_beam2I (:2424-2444) and apply_GCF (:2468-2476). One thread per pixel.
 // kReal: the pre-FFT image is written as a real plane (half-plane forward model, see k_degrid_chi2).
+__global__ void __launch_bounds__(256) k_atten_image(float* __restrict__ out, long N, long M, float D,
+                                                     float pb_factor, float pb_cutoff, float nu, float xobs,
+                                                     float yobs, double DELTAX, double DELTAY, int primary_beam) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  out[idx] = gvm_attenuation((int)(idx / N), (int)(idx % N), D, pb_factor, pb_cutoff, nu, xobs, yobs, DELTAX,
+                             DELTAY, primary_beam);
+}
+
 template <bool kClip, bool kReal>
 __global__ void __launch_bounds__(256) k_image_prep(
     float* __restrict__ I, const float* __restrict__ noise, const float* __restrict__ gcf,
-    void* __restrict__ I_nu_out, long N, long M, float noise_cut, float minpix, float eta,
+    const float* __restrict__ atten_plane, void* __restrict__ I_nu_out, long N, long M, float noise_cut, float minpix, float eta,
     float threshold, int schedule, float nu, float nu_0, float fg_scale, float D, float pb_factor,
     float pb_cutoff, float xobs, float yobs, double DELTAX, double DELTAY, int primary_beam) {
   const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -120,8 +129,9 @@ __global__ void __launch_bounds__(256) k_image_prep(
   float v = I0 * powf(nudiv, alpha);
   const float floor_v = -1.0f * eta * minpix;
   if (v < floor_v) v = floor_v;
-  const float atten = gvm_attenuation(i, j, D, pb_factor, pb_cutoff, nu, xobs, yobs, DELTAX,
-                                      DELTAY, primary_beam);
+  const float atten = atten_plane ? atten_plane[idx]
+                                  : gvm_attenuation(i, j, D, pb_factor, pb_cutoff, nu, xobs, yobs, DELTAX,
+                                                    DELTAY, primary_beam);
   v = v * atten * fg_scale;
   if (gcf != nullptr) v = v * gcf[idx];
   if (kReal) reinterpret_cast<float*>(I_nu_out)[idx] = v;
@@ -349,6 +359,25 @@ int gvm_launch_prep_channel(gvm_engine* e, GvmChannel& c, const double* uvw_m_de
   return 0;
 }
 
+const float* gvm_channel_atten(gvm_engine* e, GvmChannel& c) {
+  if (c.atten) return c.atten;
+  static const size_t budget = [] {
+    const char* s = getenv("GVM_ATTEN_CACHE_MB");
+    return (size_t)(s ? atol(s) : 8192) << 20;
+  }();
+  const gvm_config& g = e->cfg;
+  const size_t bytes = (size_t)g.M * g.N * sizeof(float);
+  if (e->atten_cache_bytes + bytes > budget) return nullptr;
+  if (cudaMalloc(&c.atten, bytes) != cudaSuccess) { c.atten = nullptr; cudaGetLastError(); return nullptr; }
+  e->atten_cache_bytes += bytes;
+  const long MN = g.M * g.N;
+  k_atten_image<<<(int)((MN + 255) / 256), 256, 0, e->stream>>>(
+      c.atten, g.N, g.M, c.d.antenna_diameter, c.d.pb_factor, c.d.pb_cutoff, c.d.freq, c.d.ref_xobs_pix,
+      c.d.ref_yobs_pix, g.DELTAX, g.DELTAY, c.d.primary_beam);
+  GVM_LAUNCH(e);
+  return c.atten;
+}
+
 int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, int flag_opt,
                         int slot) {
   const gvm_config& g = e->cfg;
@@ -366,9 +395,10 @@ int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, 
     cufftSetStream(e->plan_r2c, e->stream);
   }
   e->last_forward_half = half ? 1 : 0;
+  const float* atten_plane = gvm_channel_atten(e, c);
 #define GVM_PREP(CLIP, REAL)                                                                              \
   k_image_prep<CLIP, REAL><<<pix_blocks, 256, 0, e->stream>>>(                                            \
-      I_dev, e->noise, e->gcf, e->I_nu, g.N, g.M, g.noise_cut, g.minpix, g.eta, g.threshold, flag_opt,    \
+      I_dev, e->noise, e->gcf, atten_plane, e->I_nu, g.N, g.M, g.noise_cut, g.minpix, g.eta, g.threshold, flag_opt,    \
       c.d.freq, g.nu_0, g.fg_scale, c.d.antenna_diameter, c.d.pb_factor, c.d.pb_cutoff, c.d.ref_xobs_pix, \
       c.d.ref_yobs_pix, g.DELTAX, g.DELTAY, c.d.primary_beam)
   if (first) { if (half) GVM_PREP(true, true); else GVM_PREP(true, false); }

@@ -53,6 +53,9 @@ struct GvmChannel {
   float max_abs_wz = 0.f;      // max |w| (wavelengths)
   long offgrid = -1;           // samples that are NOT the centre of a uv cell with w = 0 (0: gridded data)
   int slot = -1;               // reduction slot of the last forward pass
+  // attenuation(i, j) of this block's beam (src/functions.cu:2304-2333), cached on first use: the Airy
+  // beam costs a j1f per pixel and the reference re-evaluates it in every kernel of every evaluation
+  float* atten = nullptr;      // [MN] or null (cache budget exhausted: evaluated on the fly)
 };
 
 struct gvm_engine {
@@ -79,6 +82,7 @@ struct gvm_engine {
   float* dchi2 = nullptr;   // [MN] per-channel gradient before the chain rule
   float* grad_scratch = nullptr;  // [ksplit][MN] partial sums
   size_t grad_scratch_floats = 0;
+  size_t atten_cache_bytes = 0;   // attenuation planes held by the channels (budget: GVM_ATTEN_CACHE_MB, default 8192)
   float* pixtab = nullptr;  // [2][N] gA(x_j), gB(y_i) tables (w-term), rebuilt per channel
   // reductions
   double* red_partials = nullptr;  // per-block partials
@@ -181,6 +185,7 @@ __device__ inline float gvm_warp_max(float v) {
 // rule of DChi2_total_I_nu_0 (:4000-4024, flag_opt even) / DChi2_total_alpha (:3968-3998, odd),
 // accumulated into result. `d` is the raw sum over visibilities for an UNMASKED pixel.
 struct GvmFinishParams {
+  const float* atten;   // cached attenuation plane of the block, or null
   const float* gcf;
   const float* I;
   float* result;
@@ -194,8 +199,9 @@ struct GvmFinishParams {
 __device__ inline void gvm_finish_pixel(const GvmFinishParams& p, float d, long idx, int i, int j) {
   const long MN = p.M * p.N;
   if (p.raw) { p.dchi2_out[idx] = d; return; }
-  const float atten = gvm_attenuation(i, j, p.D, p.pb_factor, p.pb_cutoff, p.freq, p.xobs, p.yobs,
-                                      p.DELTAX, p.DELTAY, p.primary_beam);
+  const float atten = p.atten ? p.atten[idx]
+                              : gvm_attenuation(i, j, p.D, p.pb_factor, p.pb_cutoff, p.freq, p.xobs, p.yobs,
+                                                p.DELTAX, p.DELTAY, p.primary_beam);
   float scale_factor = p.fg_scale * atten;
   if (p.gcf) scale_factor = scale_factor * p.gcf[idx];
   d *= scale_factor;
@@ -218,6 +224,8 @@ GvmFinishParams gvm_finish_params(gvm_engine* e, const GvmChannel& c, const floa
 
 // ------------------------------------------------------------ kernel launchers
 // forward.cu
+// the block's cached attenuation plane (built on first use; null when over budget)
+const float* gvm_channel_atten(gvm_engine* e, GvmChannel& c);
 int gvm_launch_prep_channel(gvm_engine* e, GvmChannel& c, const double* uvw_m_dev,
                             const float2* Vo_dev, const float* w_dev);
 int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, int flag_opt,
