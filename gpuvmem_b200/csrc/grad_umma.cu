@@ -556,11 +556,10 @@ int gvm_grad_umma(gvm_engine* e, GvmChannel& c, const float* I_dev, int flag_opt
     gvm_set_error("gvm_grad_umma: the w-term exceeds 4 turns across the image; use the SIMT kernels");
     return 1;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!e->umma_attr_set) {   // per engine: the attribute belongs to the device the engine runs on
     GVM_CUDA(cudaFuncSetAttribute(k_grad_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     GVM_CUDA(cudaFuncSetAttribute(k_grad_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+    e->umma_attr_set = true;
   }
   if (e->plan_dirty)
     if (build_plan(e)) return 1;
