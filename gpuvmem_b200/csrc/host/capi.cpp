@@ -91,8 +91,9 @@ int gvmh_create(const gvmh_problem* p, const char* args, const char* optimizer, 
   Io* iofits = createObject<Io, std::string>("IoFITS");
 
   std::vector<MSDataset> ds(1);
-  fillDataset(&ds[0], p->telescope ? p->telescope : "ALMA", p->antenna_diameter, p->ra * 3.14159265358979323846 / 180.0,
-              p->dec * 3.14159265358979323846 / 180.0, p->nchan, p->freqs, p->Z, p->uvw_m, p->Vo, p->w);
+  const double fra = p->has_field_centre ? p->field_ra : p->ra, fdec = p->has_field_centre ? p->field_dec : p->dec;
+  fillDataset(&ds[0], p->telescope ? p->telescope : "ALMA", p->antenna_diameter, fra * 3.14159265358979323846 / 180.0,
+              fdec * 3.14159265358979323846 / 180.0, p->nchan, p->freqs, p->Z, p->uvw_m, p->Vo, p->w);
   ds[0].name = "memory";
   ds[0].oname = "NULL";
   headerValues h;

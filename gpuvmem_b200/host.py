@@ -29,7 +29,8 @@ class gvmh_problem(C.Structure):
     _fields_ = [("M", C.c_int64), ("N", C.c_int64), ("DELTAX", C.c_double), ("DELTAY", C.c_double),
                 ("ra", C.c_double), ("dec", C.c_double), ("crpix1", C.c_double), ("crpix2", C.c_double),
                 ("telescope", C.c_char_p), ("antenna_diameter", C.c_float), ("beam_noise", C.c_float),
-                ("nchan", C.c_int), ("freqs", _P), ("Z", _P), ("uvw_m", _P), ("Vo", _P), ("w", _P)]
+                ("nchan", C.c_int), ("freqs", _P), ("Z", _P), ("uvw_m", _P), ("Vo", _P), ("w", _P),
+                ("has_field_centre", C.c_int), ("field_ra", C.c_double), ("field_dec", C.c_double)]
 
 
 FN1D = C.CFUNCTYPE(C.c_float, C.c_float, _P)
@@ -121,7 +122,11 @@ class Session:
         k["w_p"] = (C.c_void_p * n)(*[a.ctypes.data for a in k["w"]])
         prob = gvmh_problem(p.M, p.N, p.DELTAX, p.DELTAY, p.ra, p.dec, p.crpix1, p.crpix2,
                             p.telescope.encode(), p.antenna_diameter, -1.0, n, k["freqs"].ctypes.data,
-                            k["Z"].ctypes.data, C.cast(k["uvw_p"], _P), C.cast(k["Vo_p"], _P), C.cast(k["w_p"], _P))
+                            k["Z"].ctypes.data, C.cast(k["uvw_p"], _P), C.cast(k["Vo_p"], _P), C.cast(k["w_p"], _P),
+                            0, 0.0, 0.0)
+        fc = getattr(p, "field_centre", None)     # (ra, dec) in degrees of the field when it is not the image centre
+        if fc is not None:
+            prob.has_field_centre, prob.field_ra, prob.field_dec = 1, float(fc[0]), float(fc[1])
         s = _P()
         rc = self.h.gvmh_create(C.byref(prob), args.encode(), optimizer.encode(), scheme.encode(), ckernel.encode(),
                                 ck_size[0], ck_size[1], (fi_spec or DEFAULT_FI_SPEC).encode(), rank, world,

@@ -39,6 +39,8 @@ typedef struct gvmh_problem {
   const double* const* uvw_m; /* [nchan] -> [Z][3] metres */
   const float* const* Vo;     /* [nchan] -> [Z][2] */
   const float* const* w;      /* [nchan] -> [Z] */
+  int has_field_centre;       /* 0: the field's phase/pointing centre is (ra, dec) */
+  double field_ra, field_dec; /* deg: Field::phs_ra/phs_dec = ref_ra/ref_dec when it is not the image centre */
 } gvmh_problem;
 
 /* Everything src/main.cu:147-212 does up to (not including) sy->run():

@@ -70,6 +70,8 @@ struct SynthProblem {
   std::vector<float> freqs;
   std::vector<SynthChannel> chans;
   double max_uv_m = 0.0;
+  bool has_field_centre = false;   // pointing / phase centre of the field when it is not the image centre
+  double field_ra = 0.0, field_dec = 0.0;   // degrees
 } g_prob;
 
 Synthesizer* g_sy = nullptr;
@@ -129,8 +131,8 @@ void fill_dataset(std::vector<MSAntenna>& antennas, std::vector<Field>& fields,
   fields.push_back(Field());
   Field& F = fields[0];
   F.id = 0;
-  F.ref_ra = F.phs_ra = g_prob.hdr.ra * (PI_D / 180.0);
-  F.ref_dec = F.phs_dec = g_prob.hdr.dec * (PI_D / 180.0);
+  F.ref_ra = F.phs_ra = (g_prob.has_field_centre ? g_prob.field_ra : g_prob.hdr.ra) * (PI_D / 180.0);
+  F.ref_dec = F.phs_dec = (g_prob.has_field_centre ? g_prob.field_dec : g_prob.hdr.dec) * (PI_D / 180.0);
   F.nu = g_prob.freqs;
   F.visibilities.resize(nchan, std::vector<HVis>(1, HVis()));
   F.device_visibilities.resize(nchan, std::vector<DVis>(1, DVis()));
@@ -249,6 +251,15 @@ int gvref_problem_begin(long m, long n, double cdelt1, double cdelt2,
   g_prob.dish = dish;
   g_prob.freqs.assign(freqs, freqs + nchan);
   g_prob.chans.assign(nchan, SynthChannel());
+  return 0;
+}
+
+/* The field's phase/pointing centre (degrees) when it differs from the image centre CRVAL1/2: the
+ * reference places it with direccos (src/mfs.cu:660-691). Call after gvref_problem_begin. */
+int gvref_set_field_centre(double ra_deg, double dec_deg) {
+  g_prob.has_field_centre = true;
+  g_prob.field_ra = ra_deg;
+  g_prob.field_dec = dec_deg;
   return 0;
 }
 

@@ -239,6 +239,8 @@ class GvRef:
         L.gvref_time_evals.argtypes = [C.c_int, C.c_int, C.c_int]
         L.gvref_run.argtypes = [_V, C.POINTER(C.c_float)]
         L.gvref_set_lbfgs_k.argtypes = [C.c_int]
+        if hasattr(L, "gvref_set_field_centre"):
+            L.gvref_set_field_centre.argtypes = [C.c_double, C.c_double]
         if hasattr(L, "gvref_cpu_last_seconds"):
             L.gvref_cpu_last_seconds.argtypes = [f64p]
         if hasattr(L, "gvref_degridding"):
@@ -253,6 +255,8 @@ class GvRef:
         self.lib.gvref_problem_begin(p.M, p.N, p.DELTAX, p.DELTAY, p.ra, p.dec, p.crpix1, p.crpix2,
                                      p.telescope.encode(), p.antenna_diameter, p.nchan,
                                      np.ascontiguousarray(p.freqs, np.float32))
+        if getattr(p, "field_centre", None) is not None:
+            self.lib.gvref_set_field_centre(float(p.field_centre[0]), float(p.field_centre[1]))
         for c in range(p.nchan):
             self.lib.gvref_problem_channel(c, len(p.w[c]), np.ascontiguousarray(p.uvw[c], np.float64),
                                            np.ascontiguousarray(p.Vo[c], np.float32),

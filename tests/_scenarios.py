@@ -24,9 +24,19 @@ SCENARIOS = {
     # MFS with a spectral-index threshold (-T sigma: alpha frozen where I0 < 5 T) and radial weighting, L-BFGS
     "lbfgs_mfs_threshold_radial": (dict(N=128, nvis=12000, nchan=3, freq0=1.0e11, bandwidth=6e9, seed=37, grid_fill=0.9),
                                    "-z 0.001,0.1 -Z 0.01,0.0,0.002 -T 0.001 -t 4", "CG-LBFGS", "Radial", "PillBox2D", (1, 1), 3),
+    # the field's phase / pointing centre is NOT the image centre: direccos -> phs_xobs_pix / ref_xobs_pix
+    # (src/mfs.cu:660-691) off the central pixel, phase_rotate and the beam follow it
+    "cg_offset_field": (dict(N=128, nvis=16000, nchan=1, freq0=2.3e11, seed=38, grid_fill=0.9),
+                        f"-z 0.001 -Z {LAMBDAS} -t 4", "CG-FRPRMN", "Natural", "PillBox2D", (1, 1), 0),
 }
+FIELD_OFFSET_PIX = {"cg_offset_field": (7.3, -4.6)}   # field centre relative to the image centre, in pixels
 REF_EXTRA = " -X 16 -Y 16 -V 256 -i synth.ms -o out.ms -m hdr.fits"
 
 
 def problem(name):
-    return synth.make_problem(**SCENARIOS[name][0])
+    p = synth.make_problem(**SCENARIOS[name][0])
+    if name in FIELD_OFFSET_PIX:
+        import math
+        dx, dy = FIELD_OFFSET_PIX[name]
+        p.field_centre = (p.ra + dx * p.DELTAX / math.cos(math.radians(p.dec)), p.dec + dy * p.DELTAY)
+    return p

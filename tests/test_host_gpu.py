@@ -20,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # rel-L2 tolerance on the final image (unmasked pixels) after the scenario's iterations
 FINAL_TOL = {"cg_natural": 2e-3, "lbfgs_natural": 2e-3, "cg_mfs_briggs": 2e-3, "cg_gridded_gaussian": 2e-3,
-             "cg_gridded_pswf": 2e-3, "cg_nopositivity_eta": 2e-3, "lbfgs_mfs_threshold_radial": 2e-3}
+             "cg_gridded_pswf": 2e-3, "cg_nopositivity_eta": 2e-3, "lbfgs_mfs_threshold_radial": 2e-3,
+             "cg_offset_field": 2e-3}
 
 
 def _rel(a, b):
@@ -63,6 +64,8 @@ def test_scenario_matches_reference(name, refdir):
         assert sc["deltau"] == ref["s_deltau"] and sc["deltav"] == ref["s_deltav"]
         assert np.float32(sc["xobs_pix"]) == np.float32(ref["s_xpix"]) and np.float32(sc["yobs_pix"]) == np.float32(ref["s_ypix"])
         assert np.float32(sc["nu_0"]) == np.float32(ref["s_nu_0"])
+        if name == "cg_offset_field":
+            assert abs(sc["xobs_pix"] - p.N / 2) > 3 and abs(sc["yobs_pix"] - p.N / 2) > 3, "the field must be off-centre"
         for mine, theirs, tol in (("vis_noise", "s_vis_noise", 1e-6), ("noise_jypix", "s_noise_jypix", 1e-5),
                                   ("fg_scale", "s_fg_scale", 1e-5), ("noise_cut", "s_noise_cut", 1e-5)):
             assert abs(sc[mine] - float(ref[theirs])) <= tol * abs(float(ref[theirs])), (mine, sc[mine], float(ref[theirs]))
