@@ -62,7 +62,7 @@ extern "C" {
 int gvmh_create(const gvmh_problem* p, const char* args, const char* optimizer, const char* scheme,
                 const char* ckernel, int ck_m, int ck_n, const char* fi_spec, int rank, int world,
                 const char* nccl_id, gvmh_session** out) {
-  if (!p || !out) return 1;
+  if (!out) return 1;   // p == NULL: the datasets and the header come from the -i / -m files named in `args`
   {  // library callers get an error code instead of the reference's print + exit when no B200 is present
     gvm_config probe;
     std::memset(&probe, 0, sizeof(probe));
@@ -90,16 +90,18 @@ int gvmh_create(const gvmh_problem* p, const char* args, const char* optimizer, 
   Io* ioms = createObject<Io, std::string>("IoMS");
   Io* iofits = createObject<Io, std::string>("IoFITS");
 
-  std::vector<MSDataset> ds(1);
-  const double fra = p->has_field_centre ? p->field_ra : p->ra, fdec = p->has_field_centre ? p->field_dec : p->dec;
-  fillDataset(&ds[0], p->telescope ? p->telescope : "ALMA", p->antenna_diameter, fra * 3.14159265358979323846 / 180.0,
-              fdec * 3.14159265358979323846 / 180.0, p->nchan, p->freqs, p->Z, p->uvw_m, p->Vo, p->w);
-  ds[0].name = "memory";
-  ds[0].oname = "NULL";
-  headerValues h;
-  h.M = p->M; h.N = p->N; h.DELTAX = p->DELTAX; h.DELTAY = p->DELTAY; h.ra = p->ra; h.dec = p->dec;
-  h.crpix1 = p->crpix1; h.crpix2 = p->crpix2; h.beam_noise = p->beam_noise;
-  s->mfs->adoptDatasets(std::move(ds), h);
+  if (p) {
+    std::vector<MSDataset> ds(1);
+    const double fra = p->has_field_centre ? p->field_ra : p->ra, fdec = p->has_field_centre ? p->field_dec : p->dec;
+    fillDataset(&ds[0], p->telescope ? p->telescope : "ALMA", p->antenna_diameter, fra * 3.14159265358979323846 / 180.0,
+                fdec * 3.14159265358979323846 / 180.0, p->nchan, p->freqs, p->Z, p->uvw_m, p->Vo, p->w);
+    ds[0].name = "memory";
+    ds[0].oname = "NULL";
+    headerValues h;
+    h.M = p->M; h.N = p->N; h.DELTAX = p->DELTAX; h.DELTAY = p->DELTAY; h.ra = p->ra; h.dec = p->dec;
+    h.crpix1 = p->crpix1; h.crpix2 = p->crpix2; h.beam_noise = p->beam_noise;
+    s->mfs->adoptDatasets(std::move(ds), h);
+  }
   s->mfs->setDistributed(rank, world, nccl_id ? std::string(nccl_id, GVM_DIST_ID_BYTES) : std::string());
   if (g_quiet_all) G().quiet = true;
 

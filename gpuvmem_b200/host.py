@@ -105,36 +105,45 @@ class Session:
 
     def __init__(self, problem, args="-z 0.001 -Z 0.0 -t 10", optimizer="CG-FRPRMN", scheme="Natural",
                  ckernel="PillBox2D", ck_size=(0, 0), fi_spec=None, rank=0, world=1, nccl_id=None,
-                 channels=None):
+                 channels=None, shape=None):
+        """``problem`` None: the datasets and the image header are read from the -i / -m files named in ``args``
+        (GVMS container, FITS model image); ``shape`` = (M, N) of that image is then required."""
         self.h = load_host_library()
         p = problem
-        chans = list(range(p.nchan)) if channels is None else list(channels)
-        self._keep = dict(
-            freqs=np.ascontiguousarray(p.freqs[chans], dtype=np.float32),
-            Z=np.array([len(p.w[c]) for c in chans], dtype=np.int64),
-            uvw=[np.ascontiguousarray(p.uvw[c], dtype=np.float64) for c in chans],
-            Vo=[np.ascontiguousarray(p.Vo[c], dtype=np.float32) for c in chans],
-            w=[np.ascontiguousarray(p.w[c], dtype=np.float32) for c in chans])
-        k = self._keep
-        n = len(chans)
-        k["uvw_p"] = (C.c_void_p * n)(*[a.ctypes.data for a in k["uvw"]])
-        k["Vo_p"] = (C.c_void_p * n)(*[a.ctypes.data for a in k["Vo"]])
-        k["w_p"] = (C.c_void_p * n)(*[a.ctypes.data for a in k["w"]])
-        prob = gvmh_problem(p.M, p.N, p.DELTAX, p.DELTAY, p.ra, p.dec, p.crpix1, p.crpix2,
-                            p.telescope.encode(), p.antenna_diameter, -1.0, n, k["freqs"].ctypes.data,
-                            k["Z"].ctypes.data, C.cast(k["uvw_p"], _P), C.cast(k["Vo_p"], _P), C.cast(k["w_p"], _P),
-                            0, 0.0, 0.0)
-        fc = getattr(p, "field_centre", None)     # (ra, dec) in degrees of the field when it is not the image centre
-        if fc is not None:
-            prob.has_field_centre, prob.field_ra, prob.field_dec = 1, float(fc[0]), float(fc[1])
+        if p is None:      # datasets and header come from the -i / -m files named in args
+            prob_ref = None
+        else:
+            chans = list(range(p.nchan)) if channels is None else list(channels)
+            self._keep = dict(
+                freqs=np.ascontiguousarray(p.freqs[chans], dtype=np.float32),
+                Z=np.array([len(p.w[c]) for c in chans], dtype=np.int64),
+                uvw=[np.ascontiguousarray(p.uvw[c], dtype=np.float64) for c in chans],
+                Vo=[np.ascontiguousarray(p.Vo[c], dtype=np.float32) for c in chans],
+                w=[np.ascontiguousarray(p.w[c], dtype=np.float32) for c in chans])
+            k = self._keep
+            n = len(chans)
+            k["uvw_p"] = (C.c_void_p * n)(*[a.ctypes.data for a in k["uvw"]])
+            k["Vo_p"] = (C.c_void_p * n)(*[a.ctypes.data for a in k["Vo"]])
+            k["w_p"] = (C.c_void_p * n)(*[a.ctypes.data for a in k["w"]])
+            prob = gvmh_problem(p.M, p.N, p.DELTAX, p.DELTAY, p.ra, p.dec, p.crpix1, p.crpix2,
+                                p.telescope.encode(), p.antenna_diameter, -1.0, n, k["freqs"].ctypes.data,
+                                k["Z"].ctypes.data, C.cast(k["uvw_p"], _P), C.cast(k["Vo_p"], _P), C.cast(k["w_p"], _P),
+                                0, 0.0, 0.0)
+            fc = getattr(p, "field_centre", None)     # (ra, dec) in degrees of the field when it is not the image centre
+            if fc is not None:
+                prob.has_field_centre, prob.field_ra, prob.field_dec = 1, float(fc[0]), float(fc[1])
+            prob_ref = C.byref(prob)
         s = _P()
-        rc = self.h.gvmh_create(C.byref(prob), args.encode(), optimizer.encode(), scheme.encode(), ckernel.encode(),
+        rc = self.h.gvmh_create(prob_ref, args.encode(), optimizer.encode(), scheme.encode(), ckernel.encode(),
                                 ck_size[0], ck_size[1], (fi_spec or DEFAULT_FI_SPEC).encode(), rank, world,
                                 nccl_id, C.byref(s))
         if rc != 0:
             raise RuntimeError("gvmh_create failed: " + _lib.load_library().gvm_last_error().decode())
         self.s = s
-        self.M, self.N = p.M, p.N
+        if p is not None:
+            self.M, self.N = p.M, p.N
+        else:
+            self.M, self.N = shape
         self.eng = _lib.load_library()
 
     # -- lifecycle ------------------------------------------------------------------------

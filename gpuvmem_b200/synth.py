@@ -137,26 +137,34 @@ def make_problem(N=512, nvis=1 << 20, nchan=1, freq0=2.3e11, bandwidth=0.0, seed
     return p
 
 
-def write_gvms(p: Problem, path):
+def write_gvms(p: Problem, path, fields=None, corr_types=(9,)):
     """Write the GVMS container the C++ host layer reads (``csrc/host/msdata.hpp``): the values
-    ``readMS`` + ``readFITSHeader`` would deliver, one field, one correlation (XX = 9)."""
+    ``readMS`` + ``readFITSHeader`` would deliver. Default: one field at the image centre, one
+    correlation (XX = 9). ``fields``: a list of Problems sharing ``p``'s header and frequencies, one per
+    mosaic field, each optionally carrying ``field_centre = (ra, dec)`` in degrees. ``corr_types``:
+    correlation codes (include/functions.cuh:25-59); every correlation after the first gets the
+    first one's samples with a different amplitude — only LL/RR/XX/YY may be used by the engine."""
     import struct
+    fields = [p] if fields is None else list(fields)
     with open(path, "wb") as f:
         f.write(b"GVMS0001")
         f.write(struct.pack("<qq", p.M, p.N))
         f.write(struct.pack("<6d", p.DELTAX, p.DELTAY, p.ra, p.dec, p.crpix1, p.crpix2))
         f.write(struct.pack("<ff", -1.0, p.antenna_diameter))
         f.write(p.telescope.encode()[:31].ljust(32, b"\0"))
-        f.write(struct.pack("<iii", 1, p.nchan, 1))
-        f.write(struct.pack("<i", 9))
-        ra, dec = np.deg2rad(p.ra), np.deg2rad(p.dec)
-        f.write(struct.pack("<4d", ra, dec, ra, dec))
-        f.write(np.asarray(p.freqs, dtype="<f4").tobytes())
-        for c in range(p.nchan):
-            f.write(struct.pack("<q", len(p.w[c])))
-            f.write(np.ascontiguousarray(p.uvw[c], dtype="<f8").tobytes())
-            f.write(np.ascontiguousarray(p.Vo[c], dtype="<f4").tobytes())
-            f.write(np.ascontiguousarray(p.w[c], dtype="<f4").tobytes())
+        f.write(struct.pack("<iii", len(fields), p.nchan, len(corr_types)))
+        f.write(struct.pack(f"<{len(corr_types)}i", *corr_types))
+        for q in fields:
+            fc = getattr(q, "field_centre", None) or (p.ra, p.dec)
+            ra, dec = np.deg2rad(fc[0]), np.deg2rad(fc[1])
+            f.write(struct.pack("<4d", ra, dec, ra, dec))
+            f.write(np.asarray(p.freqs, dtype="<f4").tobytes())
+            for c in range(p.nchan):
+                for s in range(len(corr_types)):
+                    f.write(struct.pack("<q", len(q.w[c])))
+                    f.write(np.ascontiguousarray(q.uvw[c], dtype="<f8").tobytes())
+                    f.write(np.ascontiguousarray(q.Vo[c] * (1.0 if s == 0 else -3.0 * s), dtype="<f4").tobytes())
+                    f.write(np.ascontiguousarray(q.w[c], dtype="<f4").tobytes())
 
 
 # BASELINE.json configs (SURVEY.md §8d). Sizes can be scaled down for tests.

@@ -43,6 +43,8 @@ typedef struct gvmh_problem {
   double field_ra, field_dec; /* deg: Field::phs_ra/phs_dec = ref_ra/ref_dec when it is not the image centre */
 } gvmh_problem;
 
+/* `problem` may be NULL: the visibilities and the image header are then read from the files named by
+ * -i / -m in `args` (GVMS container / FITS model image), as the command-line program does. */
 /* Everything src/main.cu:147-212 does up to (not including) sy->run():
  * factories -> MFS::configure(args) -> setDevice -> Fi terms -> ObjectiveFunction.
  *   args      the reference's command line as one string, e.g.

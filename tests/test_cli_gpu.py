@@ -128,3 +128,61 @@ def test_gridding_filter_equals_the_gridded_run():
             assert np.array_equal(w.view(np.uint32), want[c][2].view(np.uint32))
     finally:
         b.close()
+
+
+def test_mosaic_container_two_fields_and_an_unused_correlation(tmp_path):
+    """A GVMS container with two fields (one off the image centre) and two correlations (XX, XY) through the
+    file-reading path of the host layer (MFS::configure -> Io::read), against an engine assembled by hand:
+    only LL/RR/XX/YY blocks are used (src/functions.cu:4378-4381), every field keeps its own pointing / phase
+    centre from direccos (src/mfs.cu:660-691), the noise image adds the beams of all fields (:850-916)."""
+    import math
+    import torch
+    from gpuvmem_b200 import Engine
+    from gpuvmem_b200.engine import RPDEG_D, beam_model, direccos
+    kw = dict(N=128, nchan=2, freq0=1.0e11, bandwidth=2e9, grid_fill=0.9)
+    p = synth.make_problem(nvis=8000, seed=201, **kw)
+    q = synth.make_problem(nvis=6000, seed=202, **kw)
+    q.field_centre = (p.ra + 9.2 * p.DELTAX / math.cos(math.radians(p.dec)), p.dec - 6.1 * p.DELTAY)
+    path = str(tmp_path / "mosaic.gvms")
+    synth.write_gvms(p, path, fields=[p, q], corr_types=(9, 10))     # XX, XY
+    host.set_quiet(True)
+    s = host.Session(None, args=f"-i {path} -m {path} -o {tmp_path / 'out.gvmr'} -z 0.001,0.1 -Z 0.01 -t 3",
+                     shape=(p.M, p.N))
+    try:
+        sc = s.scalars()
+        assert int(sc["total_visibilities"]) == p.total_vis() + q.total_vis(), "the XY blocks must not count"
+        I = s.get_image()
+        s.set_iteration(0)
+        v, fi = s.calc_function()
+        g = s.calc_gradient(0)
+        pbf, pbc, pb = beam_model(p.telescope, p.antenna_diameter, float(p.freqs.min()))
+        e = Engine(p.M, p.N, p.DELTAX, p.DELTAY, sc["nu_0"], eta=-1.0, minpix=0.001, noise_cut=1e30, threshold=0.0,
+                   fg_scale=1.0)
+        try:
+            dx, dy = RPDEG_D * p.DELTAX, RPDEG_D * p.DELTAY
+            for fld in (p, q):
+                fc = getattr(fld, "field_centre", None) or (p.ra, p.dec)
+                l, m = direccos(math.radians(fc[0]), math.radians(fc[1]), math.radians(p.ra), math.radians(p.dec))
+                xp = float(np.float32(l / dx + float(np.float32(p.crpix1) - np.float32(1.0))))
+                yp = float(np.float32(m / dy + float(np.float32(p.crpix2) - np.float32(1.0))))
+                for c in range(p.nchan):
+                    e.add_channel(float(p.freqs[c]), fld.uvw[c], fld.Vo[c], fld.w[c], p.antenna_diameter, pbf, pbc, pb,
+                                  (xp, yp), (xp, yp))
+            assert e.num_channels() == 4
+            fg = e.build_noise_image(sc["noise_jypix"])
+            assert abs(fg - sc["fg_scale"]) <= 1e-6 * fg
+            e.set_scalars(fg, float(np.float32(10.0) * np.float32(fg)), 0.0)
+            I_dev = torch.from_numpy(I.copy()).cuda()
+            chi2 = e.chi2(I_dev)
+            assert abs(chi2 - fi[0]) <= 1e-6 * abs(chi2), (chi2, fi[0])
+            gd = torch.zeros_like(I_dev)
+            e.dchi2(I_dev, gd, flag_opt=0)
+            want = gd[0].cpu().numpy()
+            assert np.linalg.norm(g[0] - want) <= 1e-6 * np.linalg.norm(want)
+            assert abs(yp - p.N / 2) > 3, "the second field sits off the image centre"
+        finally:
+            e.close()
+        img, _ = s.run()                      # and the whole reconstruction runs on the mosaic
+        assert np.isfinite(img).all() and int(s.scalars()["iterations_done"]) == 3
+    finally:
+        s.close()
