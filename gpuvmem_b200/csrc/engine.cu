@@ -91,6 +91,9 @@ int gvm_create(const gvm_config* cfg, gvm_engine** out) {
   GVM_CUDA(cudaMalloc(&e->red_out, 8 * sizeof(double)));
   GVM_CUDA(cudaMemset(e->red_out, 0, 8 * sizeof(double)));
   GVM_CUDA(cudaMallocHost(&e->h_red, 8 * sizeof(double)));
+  GVM_CUDA(cudaMalloc(&e->obj_slots, 3 * GVM_OBJ_SLOTS * sizeof(double)));
+  GVM_CUDA(cudaMemset(e->obj_slots, 0, 3 * GVM_OBJ_SLOTS * sizeof(double)));
+  GVM_CUDA(cudaMallocHost(&e->h_slots, 3 * GVM_OBJ_SLOTS * sizeof(double)));
   GVM_CUDA(cudaMalloc(&e->tile_counter, 16 * sizeof(unsigned int)));
   GVM_CUDA(cudaMemset(e->tile_counter, 0, 16 * sizeof(unsigned int)));
   // cufftPlan2d(N, M, C2C): src/functions.cu:2149
@@ -123,7 +126,7 @@ int gvm_destroy(gvm_engine* e) {
   cudaFree(e->degrid_table);
   cudaFree(e->grad_scratch); cudaFree(e->pixtab); cudaFree(e->I_stage); cudaFree(e->grad_stage);
   cudaFree(e->red_partials); cudaFree(e->red_counter); cudaFree(e->red_sum); cudaFree(e->red_Z);
-  cudaFree(e->red_max); cudaFree(e->red_out); cudaFreeHost(e->h_red); cudaFree(e->tile_counter);
+  cudaFree(e->red_max); cudaFree(e->red_out); cudaFreeHost(e->h_red); cudaFree(e->obj_slots); cudaFreeHost(e->h_slots); cudaFree(e->tile_counter);
   cudaFree(e->row_ext); cudaFree(e->tile_list); cudaFree(e->band_tab);
   gvm_dist_release(e);
   cudaFree(e->dist_grad);

@@ -91,6 +91,8 @@ struct gvm_engine {
   float* red_max = nullptr;        // [slot] max_k w*max(|Vr.re|,|Vr.im|)  (fp16 scaling of the UMMA path)
   double* red_out = nullptr;       // [0] = 0.5*chi2 of the last gvm_chi2
   double* h_red = nullptr;         // pinned host mirror of red_out
+  double* obj_slots = nullptr;     // [GVM_OBJ_SLOTS][3] device results of gvm_*_to_slot (one sync per objective)
+  double* h_slots = nullptr;       // pinned host mirror
   long* red_Z = nullptr;           // [slot] visibilities per block (device)
   int red_blocks = 0;
   int red_slots = 0;

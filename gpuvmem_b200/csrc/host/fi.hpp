@@ -31,6 +31,12 @@ class Fi {
   virtual void setFgScale(float) {}
   virtual float getFgScale() { return 1.0f; }
   virtual float calculateSecondDerivate() { return 0.0f; }
+  // Single-synchronisation path of ObjectiveFunction::calcFunction (engine extension; plugins that do not
+  // override it are evaluated through calcFi as in the reference). enqueueFi launches the term's value
+  // asynchronously into result slot `slot` of the engine and returns true (false: not supported);
+  // finishFi is what calcFi does once the value is on the host.
+  virtual bool enqueueFi(float* p, int slot);
+  float finishFi(float value);
   // fi.cuh:58-89: penalizatorIndex -1 keeps the current factor; an index past the -Z list
   // disables the term (factor 0); a negative one is a configuration error (print + exit)
   virtual void configure(int penalizatorIndex, int imageIndex, int imageToAdd, bool normalize);
@@ -60,6 +66,9 @@ class Fi {
   // flag_opt % 2 == imageIndex gate of the gradients (:4666)
   float priorValue(int kind, float* p, const gvm_prior_params& pp);
   void priorGrad(int kind, float* p, const gvm_prior_params& pp);
+  // kind + parameters of a built-in prior (false: not a built-in prior)
+  virtual bool priorSpec(int* kind, gvm_prior_params* pp) { (void)kind; (void)pp; return false; }
+  bool enqueued_gate_closed = false;   // enqueueFi found the (iter > 0 && lambda) gate closed: the value is 0
 };
 
 class Chi2 : public Fi {
@@ -74,6 +83,7 @@ class Chi2 : public Fi {
   void setCKernel(CKernel* ck) override;
   void setFgScale(float s) override { fg_scale = s; }
   float getFgScale() override { return fg_scale; }
+  bool enqueueFi(float* p, int slot) override;
 
  private:
   float* result_dchi2 = nullptr;  // [image_count][M*N]
@@ -83,6 +93,7 @@ class Chi2 : public Fi {
 
 class Entropy : public Fi {
  public:
+  bool priorSpec(int* kind, gvm_prior_params* pp) override;
   Entropy() { name = "Entropy"; }
   explicit Entropy(float prior_value) : prior_value(prior_value) { name = "Entropy"; }
   Entropy(float prior_value, float eta) : prior_value(prior_value), eta(eta) { name = "Entropy"; }
@@ -99,6 +110,7 @@ class Entropy : public Fi {
 
 class L1norm : public Fi {
  public:
+  bool priorSpec(int* kind, gvm_prior_params* pp) override;
   L1norm() { name = "L1 Norm"; }
   explicit L1norm(float epsilon) : epsilon(epsilon) { name = "L1 Norm"; }
   float getEpsilon() const { return epsilon; }
@@ -112,6 +124,7 @@ class L1norm : public Fi {
 
 class TVariation : public Fi {
  public:
+  bool priorSpec(int* kind, gvm_prior_params* pp) override;
   TVariation() { name = "Total Variation"; }
   explicit TVariation(float epsilon) : epsilon(epsilon) { name = "Total Variation"; }
   float getEpsilon() const { return epsilon; }
@@ -126,6 +139,7 @@ class TVariation : public Fi {
 
 class TSqVariation : public Fi {
  public:
+  bool priorSpec(int* kind, gvm_prior_params* pp) override;
   TSqVariation() { name = "Total Squared Variation"; }
   float calcFi(float* p) override;
   void calcGi(float* p, float* xi) override;
@@ -133,6 +147,7 @@ class TSqVariation : public Fi {
 
 class Laplacian : public Fi {
  public:
+  bool priorSpec(int* kind, gvm_prior_params* pp) override;
   Laplacian() { name = "Laplacian"; }
   float calcFi(float* p) override;
   void calcGi(float* p, float* xi) override;
@@ -140,6 +155,7 @@ class Laplacian : public Fi {
 
 class QuadraticP : public Fi {
  public:
+  bool priorSpec(int* kind, gvm_prior_params* pp) override;
   QuadraticP() { name = "Quadratic"; }
   float calcFi(float* p) override;
   void calcGi(float* p, float* xi) override;
@@ -148,6 +164,7 @@ class QuadraticP : public Fi {
 // entropy / L1 against a prior IMAGE (device pointer, M*N floats, owned by the term)
 class GEntropy : public Fi {
  public:
+  bool priorSpec(int* kind, gvm_prior_params* pp) override;
   GEntropy() { name = "GEntropy"; }
   explicit GEntropy(float* prior) : prior(prior) { name = "GEntropy"; }
   GEntropy(float* prior, float normalization_factor) : prior(prior), normalization_factor(normalization_factor) { name = "GEntropy"; }
@@ -169,6 +186,7 @@ class GEntropy : public Fi {
 
 class GL1Norm : public Fi {
  public:
+  bool priorSpec(int* kind, gvm_prior_params* pp) override;
   GL1Norm() { name = "G L1-Norm"; }
   explicit GL1Norm(float* prior) : prior(prior) { name = "G L1-Norm"; }
   GL1Norm(float* prior, float epsilon_a, float epsilon_b) : prior(prior), epsilon_a(epsilon_a), epsilon_b(epsilon_b) { name = "G L1-Norm"; }

@@ -51,6 +51,19 @@ float Fi::priorValue(int kind, float* p, const gvm_prior_params& pp) {
   set_fivalue(v);
   return penalization_factor * v;
 }
+bool Fi::enqueueFi(float* p, int slot) {
+  int kind = 0;
+  gvm_prior_params pp;
+  if (!priorSpec(&kind, &pp)) return false;
+  enqueued_gate_closed = !(iteration > 0 && penalization_factor);
+  if (!enqueued_gate_closed) GVM_CHECK(gvm_prior_value_to_slot(G().engine, kind, p, imageIndex, &pp, slot));
+  return true;
+}
+float Fi::finishFi(float value) {
+  if (enqueued_gate_closed) value = 0.0f;
+  set_fivalue(value);
+  return penalization_factor * value;
+}
 void Fi::priorGrad(int kind, float* p, const gvm_prior_params& pp) {
   if (iteration > 0 && penalization_factor && G().flag_opt % 2 == imageIndex)
     GVM_CHECK(gvm_prior_grad(G().engine, kind, p, imageIndex, &pp, penalization_factor, device_DS));
@@ -82,6 +95,14 @@ float Chi2::calcFi(float* p) {
   set_fivalue(v);
   return penalization_factor * v;
 }
+bool Chi2::enqueueFi(float* p, int slot) {
+  Globals& g = G();
+  enqueued_gate_closed = false;
+  GVM_CHECK(gvm_set_scalars(g.engine, fg_scale, g.noise_cut, g.threshold));
+  GVM_CHECK(gvm_set_flag_opt(g.engine, g.flag_opt));
+  GVM_CHECK(gvm_chi2_to_slot(g.engine, p, normalize ? 1 : 0, slot));
+  return true;
+}
 void Chi2::calcGi(float* p, float*) {
   Globals& g = G();
   GVM_CHECK(gvm_dchi2(g.engine, p, g.flag_opt, normalize ? 1 : 0, result_dchi2));
@@ -108,22 +129,28 @@ gvm_prior_params params(float prior_value, float eta, float eps_a, float eps_b, 
 }
 }  // namespace
 
+bool Entropy::priorSpec(int* kind, gvm_prior_params* pp) { *kind = GVM_PRIOR_ENTROPY; *pp = params(prior_value, eta, 0, 0, nullptr); return true; }
 float Entropy::calcFi(float* p) { return priorValue(GVM_PRIOR_ENTROPY, p, params(prior_value, eta, 0, 0, nullptr)); }
 void Entropy::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_ENTROPY, p, params(prior_value, eta, 0, 0, nullptr)); }
 
+bool L1norm::priorSpec(int* kind, gvm_prior_params* pp) { *kind = GVM_PRIOR_L1; *pp = params(0, 0, epsilon, 0, nullptr); return true; }
 float L1norm::calcFi(float* p) { return priorValue(GVM_PRIOR_L1, p, params(0, 0, epsilon, 0, nullptr)); }
 void L1norm::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_L1, p, params(0, 0, epsilon, 0, nullptr)); }
 
+bool TVariation::priorSpec(int* kind, gvm_prior_params* pp) { *kind = GVM_PRIOR_TV; *pp = params(0, 0, epsilon, 0, nullptr); return true; }
 float TVariation::calcFi(float* p) { return priorValue(GVM_PRIOR_TV, p, params(0, 0, epsilon, 0, nullptr)); }
 void TVariation::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_TV, p, params(0, 0, epsilon, 0, nullptr)); }
 void TVariation::addToDphi(float* device_dphi) { GVM_CHECK(gvm_add_to_dphi(G().engine, device_dphi, device_DS, 0)); }
 
+bool TSqVariation::priorSpec(int* kind, gvm_prior_params* pp) { *kind = GVM_PRIOR_TSV; *pp = params(0, 0, 0, 0, nullptr); return true; }
 float TSqVariation::calcFi(float* p) { return priorValue(GVM_PRIOR_TSV, p, params(0, 0, 0, 0, nullptr)); }
 void TSqVariation::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_TSV, p, params(0, 0, 0, 0, nullptr)); }
 
+bool Laplacian::priorSpec(int* kind, gvm_prior_params* pp) { *kind = GVM_PRIOR_LAPLACIAN; *pp = params(0, 0, 0, 0, nullptr); return true; }
 float Laplacian::calcFi(float* p) { return priorValue(GVM_PRIOR_LAPLACIAN, p, params(0, 0, 0, 0, nullptr)); }
 void Laplacian::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_LAPLACIAN, p, params(0, 0, 0, 0, nullptr)); }
 
+bool QuadraticP::priorSpec(int* kind, gvm_prior_params* pp) { *kind = GVM_PRIOR_QUADRATIC; *pp = params(0, 0, 0, 0, nullptr); return true; }
 float QuadraticP::calcFi(float* p) { return priorValue(GVM_PRIOR_QUADRATIC, p, params(0, 0, 0, 0, nullptr)); }
 void QuadraticP::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_QUADRATIC, p, params(0, 0, 0, 0, nullptr)); }
 
@@ -142,6 +169,7 @@ GEntropy::GEntropy(const std::vector<float>& prior_host) : prior(uploadImage(pri
 GEntropy::~GEntropy() { if (G().engine) devFree(prior); }
 void GEntropy::setPrior(float* p) { devFree(prior); prior = p; }
 void GEntropy::normalizePrior() { scaleImage(prior, normalization_factor); }
+bool GEntropy::priorSpec(int* kind, gvm_prior_params* pp) { *kind = GVM_PRIOR_GENTROPY; *pp = params(0, eta, 0, 0, prior); return true; }
 float GEntropy::calcFi(float* p) { return priorValue(GVM_PRIOR_GENTROPY, p, params(0, eta, 0, 0, prior)); }
 void GEntropy::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_GENTROPY, p, params(0, eta, 0, 0, prior)); }
 
@@ -149,6 +177,7 @@ GL1Norm::GL1Norm(const std::vector<float>& prior_host) : prior(uploadImage(prior
 GL1Norm::~GL1Norm() { if (G().engine) devFree(prior); }
 void GL1Norm::setPrior(float* p) { devFree(prior); prior = p; }
 void GL1Norm::normalizePrior() { scaleImage(prior, normalization_factor); }
+bool GL1Norm::priorSpec(int* kind, gvm_prior_params* pp) { *kind = GVM_PRIOR_GL1; *pp = params(0, 0, epsilon_a, epsilon_b, prior); return true; }
 float GL1Norm::calcFi(float* p) { return priorValue(GVM_PRIOR_GL1, p, params(0, 0, epsilon_a, epsilon_b, prior)); }
 void GL1Norm::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_GL1, p, params(0, 0, epsilon_a, epsilon_b, prior)); }
 

@@ -1,12 +1,18 @@
 #include "objectivefunction.hpp"
 
 #include <chrono>
+#include <cstdlib>
 
 namespace gpuvmem {
 
 namespace {
 double nowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }  // namespace
+
+bool ObjectiveFunction::defaultSingleSync() {
+  const char* v = std::getenv("GVM_SINGLE_SYNC");
+  return !(v && *v == '0');
+}
 
 ObjectiveFunction::~ObjectiveFunction() {
   if (G().engine) devFree(dphi);
@@ -23,10 +29,26 @@ float ObjectiveFunction::calcFunction(float* p) {
   const double t0 = nowS();
   float value = 0.0f;
   size_t k = 0;
-  for (Fi* fi : fis) {
-    const float term = fi->calcFi(p);
-    fi_values[k++] = fi->get_fivalue();
-    value += term;
+  // Fast path: every term launches its value asynchronously into a result slot of the engine and ONE
+  // stream synchronisation brings them all back (the reference synchronises several times per term).
+  // Terms that do not support it (user plugins) switch the whole evaluation to the reference's loop.
+  bool fast = single_sync && fis.size() <= (size_t)GVM_OBJ_SLOTS;
+  size_t enq = 0;
+  for (; fast && enq < fis.size(); enq++) fast = fis[enq]->enqueueFi(p, (int)enq);
+  if (fast) {
+    double vals[GVM_OBJ_SLOTS];
+    GVM_CHECK(gvm_fetch_slots(G().engine, (int)fis.size(), vals));
+    for (Fi* fi : fis) {
+      const float term = fi->finishFi((float)vals[k]);
+      fi_values[k++] = fi->get_fivalue();
+      value += term;
+    }
+  } else {
+    for (Fi* fi : fis) {
+      const float term = fi->calcFi(p);
+      fi_values[k++] = fi->get_fivalue();
+      value += term;
+    }
   }
   n_function++;
   t_function += nowS() - t0;

@@ -36,6 +36,9 @@ class ObjectiveFunction {
   // host wall time spent inside calcFunction / calcGradient (the calls return after the GPU work)
   double functionSeconds() const { return t_function; }
   double gradientSeconds() const { return t_gradient; }
+  // one host synchronisation per calcFunction (Fi::enqueueFi) instead of one per term; on by default,
+  // GVM_SINGLE_SYNC=0 in the environment or setSingleSync(false) selects the reference's per-term loop
+  void setSingleSync(bool on) { single_sync = on; }
 
  private:
   std::vector<Fi*> fis;
@@ -47,6 +50,8 @@ class ObjectiveFunction {
   int image_count = 1;
   long n_function = 0, n_gradient = 0;
   double t_function = 0.0, t_gradient = 0.0;
+  bool single_sync = defaultSingleSync();
+  static bool defaultSingleSync();
 };
 
 }  // namespace gpuvmem

@@ -368,8 +368,9 @@ int fetch_red(gvm_engine* e, double* v3) {
 }
 
 template <int KIND>
-int launch_value(gvm_engine* e, const PriorArgs& a) {
+int launch_value(gvm_engine* e, const PriorArgs& a, double* out = nullptr) {
   RedBuf r = aux_red(e);
+  if (out) r.out = out;
   k_prior_value<KIND><<<red_grid(e, (long)a.N * a.N), kT, 0, e->stream>>>(a, r.partials, r.pmax, r.counter, r.out);
   return 0;
 }
@@ -405,27 +406,51 @@ int make_args(gvm_engine* e, int kind, const float* I_dev, int image_index,
 
 extern "C" {
 
-int gvm_prior_value(gvm_engine* e, int kind, const float* I_dev, int image_index,
-                    const gvm_prior_params* p, float* value_out) {
+static int prior_value_launch(gvm_engine* e, int kind, const float* I_dev, int image_index,
+                              const gvm_prior_params* p, double* out) {
   GVM_CUDA(cudaSetDevice(e->cfg.device));
   PriorArgs a;
   if (make_args(e, kind, I_dev, image_index, p, 1.0f, &a)) return 1;
   switch (kind) {
-    case GVM_PRIOR_ENTROPY: launch_value<GVM_PRIOR_ENTROPY>(e, a); break;
-    case GVM_PRIOR_L1: launch_value<GVM_PRIOR_L1>(e, a); break;
-    case GVM_PRIOR_TV: launch_value<GVM_PRIOR_TV>(e, a); break;
-    case GVM_PRIOR_TSV: launch_value<GVM_PRIOR_TSV>(e, a); break;
-    case GVM_PRIOR_LAPLACIAN: launch_value<GVM_PRIOR_LAPLACIAN>(e, a); break;
-    case GVM_PRIOR_QUADRATIC: launch_value<GVM_PRIOR_QUADRATIC>(e, a); break;
-    case GVM_PRIOR_GENTROPY: launch_value<GVM_PRIOR_GENTROPY>(e, a); break;
-    case GVM_PRIOR_GL1: launch_value<GVM_PRIOR_GL1>(e, a); break;
+    case GVM_PRIOR_ENTROPY: launch_value<GVM_PRIOR_ENTROPY>(e, a, out); break;
+    case GVM_PRIOR_L1: launch_value<GVM_PRIOR_L1>(e, a, out); break;
+    case GVM_PRIOR_TV: launch_value<GVM_PRIOR_TV>(e, a, out); break;
+    case GVM_PRIOR_TSV: launch_value<GVM_PRIOR_TSV>(e, a, out); break;
+    case GVM_PRIOR_LAPLACIAN: launch_value<GVM_PRIOR_LAPLACIAN>(e, a, out); break;
+    case GVM_PRIOR_QUADRATIC: launch_value<GVM_PRIOR_QUADRATIC>(e, a, out); break;
+    case GVM_PRIOR_GENTROPY: launch_value<GVM_PRIOR_GENTROPY>(e, a, out); break;
+    case GVM_PRIOR_GL1: launch_value<GVM_PRIOR_GL1>(e, a, out); break;
     default: gvm_set_error("gvm_prior_value: unknown kind %d", kind); return 1;
   }
   GVM_LAUNCH(e);
   GVM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gvm_prior_value(gvm_engine* e, int kind, const float* I_dev, int image_index,
+                    const gvm_prior_params* p, float* value_out) {
+  if (prior_value_launch(e, kind, I_dev, image_index, p, nullptr)) return 1;
   double v[3];
   if (fetch_red(e, v)) return 1;
   *value_out = (float)v[0];
+  return 0;
+}
+
+// ---- one host synchronisation for all terms of an objective evaluation ----
+int gvm_prior_value_to_slot(gvm_engine* e, int kind, const float* I_dev, int image_index,
+                            const gvm_prior_params* p, int slot) {
+  if (slot < 0 || slot >= GVM_OBJ_SLOTS) { gvm_set_error("gvm_prior_value_to_slot: slot %d out of range", slot); return 1; }
+  return prior_value_launch(e, kind, I_dev, image_index, p, e->obj_slots + 3 * slot);
+}
+int gvm_chi2_to_slot(gvm_engine* e, float* I_dev, int normalize, int slot) {
+  if (slot < 0 || slot >= GVM_OBJ_SLOTS) { gvm_set_error("gvm_chi2_to_slot: slot %d out of range", slot); return 1; }
+  return gvm_chi2_async(e, I_dev, normalize, e->obj_slots + 3 * slot);
+}
+int gvm_fetch_slots(gvm_engine* e, int n, double* values_out) {
+  if (n < 0 || n > GVM_OBJ_SLOTS) { gvm_set_error("gvm_fetch_slots: %d slots requested", n); return 1; }
+  GVM_CUDA(cudaMemcpyAsync(e->h_slots, e->obj_slots, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < n; i++) values_out[i] = e->h_slots[3 * i];
   return 0;
 }
 

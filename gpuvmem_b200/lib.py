@@ -66,6 +66,9 @@ SIGNATURES = {
     "gvm_error_maps": (C.c_int, [_P, _P, C.c_int, _P]),
     "gvm_eval_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(C.c_float), _P]),
     "gvm_prior_value": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(gvm_prior_params), C.POINTER(C.c_float)]),
+    "gvm_chi2_to_slot": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "gvm_prior_value_to_slot": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(gvm_prior_params), C.c_int]),
+    "gvm_fetch_slots": (C.c_int, [_P, C.c_int, _P]),
     "gvm_prior_grad": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(gvm_prior_params), C.c_float, _P]),
     "gvm_add_to_dphi": (C.c_int, [_P, _P, _P, C.c_int]),
     "gvm_vec_evaluate_xt": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int, C.c_int]),

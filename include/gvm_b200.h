@@ -206,6 +206,15 @@ typedef struct gvm_prior_params {
  * (e.g. :4643); the gate is the caller's (Fi adapter) business here. */
 int gvm_prior_value(gvm_engine* e, int kind, const float* I_dev, int image_index,
                     const gvm_prior_params* p, float* value_out);
+/* One host synchronisation for ALL terms of an objective evaluation (the reference synchronises, copies
+ * and frees inside every deviceReduce, i.e. several times per Fi): each term launches into a result slot
+ * of the engine, gvm_fetch_slots copies the first n slots back with a single stream synchronisation.
+ * gvm_chi2_to_slot = gvm_chi2 (same side effects), gvm_prior_value_to_slot = gvm_prior_value. */
+#define GVM_OBJ_SLOTS 16
+int gvm_chi2_to_slot(gvm_engine* e, float* I_dev, int normalize, int slot);
+int gvm_prior_value_to_slot(gvm_engine* e, int kind, const float* I_dev, int image_index,
+                            const gvm_prior_params* p, int slot);
+int gvm_fetch_slots(gvm_engine* e, int n, double* values_out);
 /* The gradient host functions: dgi_dev[M*N] = lambda * d(term)/dI, written (not
  * accumulated), like DS/DL1NormK/... write device_DS. */
 int gvm_prior_grad(gvm_engine* e, int kind, const float* I_dev, int image_index,

@@ -186,3 +186,34 @@ def test_mosaic_container_two_fields_and_an_unused_correlation(tmp_path):
         assert np.isfinite(img).all() and int(s.scalars()["iterations_done"]) == 3
     finally:
         s.close()
+
+
+def test_single_synchronisation_objective_equals_the_per_term_loop(monkeypatch):
+    """ObjectiveFunction::calcFunction's fast path (every Fi value launched into an engine slot, ONE stream
+    synchronisation) against the reference's per-term loop (GVM_SINGLE_SYNC=0): identical values, identical
+    reconstruction."""
+    from _ref_runner import probe_image
+    p = synth.make_problem(N=128, nvis=12000, nchan=2, freq0=1.0e11, bandwidth=4e9, seed=55, grid_fill=0.9)
+    host.set_quiet(True)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GVM_SINGLE_SYNC", mode)
+        s = host.Session(p, args="-z 0.001,0.1 -Z 0.01,0.005,0.002,0.001 -t 4")
+        try:
+            start = s.get_image()
+            s.set_image(probe_image(p.N, np.float32(0.001), 0.1))
+            s.set_iteration(0)
+            v0, fi0 = s.calc_function()            # priors gated off: their values are 0
+            s.set_iteration(1)
+            v1, fi1 = s.calc_function()
+            clipped = s.get_image()
+            s.set_image(start)
+            s.set_iteration(0)
+            img, _ = s.run()
+            out[mode] = (v0, fi0, v1, fi1, clipped, img, s.stats()["function_evals"])
+        finally:
+            s.close()
+    a, b = out["1"], out["0"]
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and not a[1][1:].any()
+    assert a[2] == b[2] and np.array_equal(a[3], b[3]) and a[3][1:].all()
+    assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5]) and a[6] == b[6]
