@@ -215,6 +215,156 @@ __global__ void __launch_bounds__(kThreads) k_grid_accumulate(
   out_V[cell] = make_float2(orr, oi);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tile-sequential gridding (default path). The uv grid is cut into kTile x kTile output tiles; every
+// Hermitian-doubled sample is listed under each tile its kernel footprint touches (1, 2 or 4 tiles), the
+// (tile, sample) pairs are stably radix-sorted by tile, and ONE WARP per tile replays its samples in
+// ascending sample order — the reference's loop order (src/functions.cu:1466-1505) — with the lanes
+// spread over the kernel taps and the four accumulators of the tile's cells in shared memory. A tap of
+// one sample touches a cell at most once, so lanes never collide inside a sample; __syncwarp() orders
+// consecutive samples. Per cell the sequence of fp32 operations is exactly the reference's, so the result
+// is bit-identical to the single-thread CPU code (and to k_grid_accumulate, kept as a cross-check).
+// The per-pair record (centre, weight, visibility) is gathered into sorted order first, so the replay
+// streams 16 B per pair with one coalesced load per 32 samples.
+constexpr int kTile = 16;
+
+__device__ __forceinline__ bool grid_centre(const double* __restrict__ uvw_m, long z, long Z, float freq,
+                                            double deltau, double deltav, long M, long N, int sx, int sy, int* j,
+                                            int* k) {
+  const long vi = (z < Z) ? z : z - Z;
+  double u = uvw_m[3 * vi], v = uvw_m[3 * vi + 1];
+  if (z >= Z) { u *= -1.0; v *= -1.0; }
+  u = gvm_metres_to_lambda(u, freq);
+  v = gvm_metres_to_lambda(v, freq);
+  const double gx = u / deltau, gy = v / deltav;
+  const double j_fp = gx + floor(N / 2.0) + 0.5, k_fp = gy + floor(M / 2.0) + 0.5;
+  *j = (int)j_fp;
+  *k = (int)k_fp;
+  return *j >= -sx && *j < N + sx && *k >= -sy && *k < M + sy;   // some tap reaches the grid
+}
+
+// pass 1: centre of every doubled sample (packed, offset by the support) and the number of tiles it touches
+__global__ void __launch_bounds__(256) k_tile_count(const double* __restrict__ uvw_m, long Z, float freq,
+                                                    double deltau, double deltav, long M, long N, int sx, int sy,
+                                                    uint32_t* __restrict__ cpos, int* __restrict__ cnt) {
+  const long z = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (z >= 2 * Z) return;
+  int j, k;
+  if (!grid_centre(uvw_m, z, Z, freq, deltau, deltav, M, N, sx, sy, &j, &k)) { cpos[z] = kNoCell; cnt[z] = 0; return; }
+  cpos[z] = ((uint32_t)(k + sy) << 16) | (uint32_t)(j + sx);
+  const int tx0 = max(j - sx, 0) / kTile, tx1 = min(j + sx, (int)N - 1) / kTile;
+  const int ty0 = max(k - sy, 0) / kTile, ty1 = min(k + sy, (int)M - 1) / kTile;
+  cnt[z] = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+}
+
+// pass 2: the (tile, sample) pairs at the offsets of the exclusive scan
+__global__ void __launch_bounds__(256) k_tile_emit(const uint32_t* __restrict__ cpos, const int* __restrict__ off,
+                                                   long n2, long M, long N, int sx, int sy, int ntx,
+                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const long z = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (z >= n2) return;
+  const uint32_t cp = cpos[z];
+  if (cp == kNoCell) return;
+  const int j = (int)(cp & 0xFFFFu) - sx, k = (int)(cp >> 16) - sy;
+  const int tx0 = max(j - sx, 0) / kTile, tx1 = min(j + sx, (int)N - 1) / kTile;
+  const int ty0 = max(k - sy, 0) / kTile, ty1 = min(k + sy, (int)M - 1) / kTile;
+  int o = off[z];
+  for (int ty = ty0; ty <= ty1; ty++)
+    for (int tx = tx0; tx <= tx1; tx++) {
+      keys[o] = (uint32_t)(ty * ntx + tx);
+      vals[o] = (uint32_t)z;
+      o++;
+    }
+}
+
+// pass 3 (after the stable sort by tile): first / one-past-last pair of every tile, and the 16-byte record
+// of every pair in sorted order: (centre, w, Vo.re, Vo.im) with the twin's visibility conjugated
+__global__ void __launch_bounds__(256) k_tile_gather(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                     long npairs, long Z, const uint32_t* __restrict__ cpos,
+                                                     const float2* __restrict__ Vo, const float* __restrict__ w,
+                                                     int* __restrict__ tstart, int* __restrict__ tend,
+                                                     float4* __restrict__ rec) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= npairs) return;
+  const uint32_t t = keys[i], z = vals[i];
+  if (i == 0 || keys[i - 1] != t) tstart[t] = (int)i;
+  if (i == npairs - 1 || keys[i + 1] != t) tend[t] = (int)(i + 1);
+  const long vi = (z < (uint32_t)Z) ? (long)z : (long)z - Z;
+  float2 vo = Vo[vi];
+  if (z >= (uint32_t)Z) vo.y *= -1.0f;
+  rec[i] = make_float4(__uint_as_float(cpos[z]), w[vi], vo.x, vo.y);
+}
+
+template <int kRounds>
+__global__ void __launch_bounds__(32) k_grid_tiles(const int* __restrict__ tstart, const int* __restrict__ tend,
+                                                   const float4* __restrict__ rec, const float* __restrict__ kernel,
+                                                   int ck_m, int ck_n, int sx, int sy, long M, long N, int ntx,
+                                                   float* __restrict__ out_w, float2* __restrict__ out_V) {
+  __shared__ float s_gw[kTile * kTile], s_gw2[kTile * kTile], s_gvr[kTile * kTile], s_gvi[kTile * kTile];
+  const int lane = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int ty = tile / ntx, tx = tile - ty * ntx;
+  const int k0 = ty * kTile, j0 = tx * kTile;
+  for (int c = lane; c < kTile * kTile; c += 32) { s_gw[c] = 0.f; s_gw2[c] = 0.f; s_gvr[c] = 0.f; s_gvi[c] = 0.f; }
+  // this lane's taps: offsets from the centre and kernel values (ck = NaN marks "no tap")
+  const int tw = 2 * sx + 1, taps = tw * (2 * sy + 1);
+  int dm[kRounds], dn[kRounds];
+  float ckv[kRounds], ck2v[kRounds];
+  bool on[kRounds];
+#pragma unroll
+  for (int r = 0; r < kRounds; r++) {
+    const int t = lane + 32 * r;
+    const int ki = t / tw, kj = t - ki * tw;
+    on[r] = t < taps && ki < ck_m && kj < ck_n;
+    dm[r] = ki - sy;
+    dn[r] = kj - sx;
+    ckv[r] = on[r] ? kernel[ck_n * ki + kj] : 0.f;
+    ck2v[r] = __fmul_rn(ckv[r], ckv[r]);
+  }
+  __syncwarp();
+  const int b = tstart[tile], e = tend[tile];
+  for (int base = b; base < e; base += 32) {
+    const int n = min(32, e - base);
+    float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < n) mine = __ldg(&rec[base + lane]);
+    for (int sidx = 0; sidx < n; sidx++) {
+      const uint32_t cp = __float_as_uint(__shfl_sync(0xffffffffu, mine.x, sidx));
+      const float wt = __shfl_sync(0xffffffffu, mine.y, sidx);
+      const float vr = __shfl_sync(0xffffffffu, mine.z, sidx);
+      const float vim = __shfl_sync(0xffffffffu, mine.w, sidx);
+      const int lj = (int)(cp & 0xFFFFu) - sx - j0, lk = (int)(cp >> 16) - sy - k0;   // centre relative to the tile
+      const float wr = __fmul_rn(wt, vr), wi = __fmul_rn(wt, vim);
+#pragma unroll
+      for (int r = 0; r < kRounds; r++) {
+        const int cj = lj + dn[r], ck_ = lk + dm[r];
+        if (on[r] && cj >= 0 && cj < kTile && ck_ >= 0 && ck_ < kTile && j0 + cj < N && k0 + ck_ < M) {
+          const int c = ck_ * kTile + cj;
+          s_gw[c] = __fadd_rn(s_gw[c], __fmul_rn(wt, ckv[r]));
+          s_gw2[c] = __fadd_rn(s_gw2[c], __fmul_rn(wt, ck2v[r]));
+          s_gvr[c] = __fadd_rn(s_gvr[c], __fmul_rn(wr, ckv[r]));
+          s_gvi[c] = __fadd_rn(s_gvi[c], __fmul_rn(wi, ckv[r]));
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // normalise (src/functions.cu:1537-1558) and write the tile
+  for (int c = lane; c < kTile * kTile; c += 32) {
+    const int ck_ = c / kTile, cj = c - ck_ * kTile;
+    if (j0 + cj >= N || k0 + ck_ >= M) continue;
+    const float gw = s_gw[c], gw2 = s_gw2[c];
+    float weight = 0.f, orr = 0.f, oi = 0.f;
+    if (gw2 != 0.0f && gw != 0.0f) {
+      weight = __fdiv_rn(__fmul_rn(gw, gw), gw2);
+      orr = __fdiv_rn(s_gvr[c], gw);
+      oi = __fdiv_rn(s_gvi[c], gw);
+    }
+    const long cell = (long)(k0 + ck_) * N + (j0 + cj);
+    out_w[cell] = weight;
+    out_V[cell] = make_float2(orr, oi);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_grid_flags(const float* __restrict__ wgt, long MN,
                                                     int* __restrict__ flags) {
   const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -275,6 +425,7 @@ thread_local GridResult g_grid_result;
 // block costs more than the kernels); gvm_grid_release() returns them
 struct GridWork {
   DevBuf uvw, Vo, w, ck, k0, k1, v0, v1, tmp, gw, gV, flags, pos, start;
+  DevBuf cpos, cnt, off, rec, tstart, tend;   // tile-sequential path
 };
 thread_local GridWork g_grid_work;
 
@@ -284,6 +435,69 @@ int sort_pairs(DevBuf& tmp, uint32_t* k_in, uint32_t* k_out, uint32_t* v_in, uin
   WG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit));
   if (tmp.ensure(bytes)) return 1;
   WG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit));
+  return 0;
+}
+
+// The tile-sequential accumulation (k_tile_* + k_grid_tiles): fills gw/gV like k_grid_accumulate does.
+// *done = false (nothing launched) when the problem does not fit its 16-bit centre packing / 31-bit pair count.
+int grid_tiles_path(GridWork& wk, long Z, float freq, double deltau, double deltav, long M, long N, int ck_m,
+                    int ck_n, int sx, int sy, bool* done) {
+  *done = false;
+  const long n2 = 2 * Z;
+  if (M + 2L * sy >= 65536 || N + 2L * sx >= 65536 || n2 > 400000000L) return 0;
+  const int ntx = (int)((N + kTile - 1) / kTile), nty = (int)((M + kTile - 1) / kTile);
+  const long ntiles = (long)ntx * nty;
+  long npairs = 0;
+  if (wk.tstart.ensure((size_t)ntiles * 4) || wk.tend.ensure((size_t)ntiles * 4)) return 1;
+  WG_CUDA(cudaMemset(wk.tstart.p, 0, (size_t)ntiles * 4));
+  WG_CUDA(cudaMemset(wk.tend.p, 0, (size_t)ntiles * 4));
+  if (n2 > 0) {
+    if (wk.cpos.ensure((size_t)n2 * 4) || wk.cnt.ensure((size_t)n2 * 4) || wk.off.ensure((size_t)n2 * 4)) return 1;
+    const int blocks = (int)((n2 + 255) / 256);
+    k_tile_count<<<blocks, 256>>>(wk.uvw.as<double>(), Z, freq, deltau, deltav, M, N, sx, sy, wk.cpos.as<uint32_t>(),
+                                  wk.cnt.as<int>());
+    WG_CUDA(cudaGetLastError());
+    size_t sb = 0;
+    WG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, wk.cnt.as<int>(), wk.off.as<int>(), (int)n2));
+    if (wk.tmp.ensure(sb)) return 1;
+    WG_CUDA(cub::DeviceScan::ExclusiveSum(wk.tmp.p, sb, wk.cnt.as<int>(), wk.off.as<int>(), (int)n2));
+    int last_off = 0, last_cnt = 0;
+    WG_CUDA(cudaMemcpy(&last_off, wk.off.as<int>() + (n2 - 1), 4, cudaMemcpyDeviceToHost));
+    WG_CUDA(cudaMemcpy(&last_cnt, wk.cnt.as<int>() + (n2 - 1), 4, cudaMemcpyDeviceToHost));
+    npairs = (long)last_off + last_cnt;
+    if (npairs > 0) {
+      if (wk.k0.ensure((size_t)npairs * 4) || wk.k1.ensure((size_t)npairs * 4) || wk.v0.ensure((size_t)npairs * 4) ||
+          wk.v1.ensure((size_t)npairs * 4) || wk.rec.ensure((size_t)npairs * 16))
+        return 1;
+      k_tile_emit<<<blocks, 256>>>(wk.cpos.as<uint32_t>(), wk.off.as<int>(), n2, M, N, sx, sy, ntx, wk.k0.as<uint32_t>(),
+                                   wk.v0.as<uint32_t>());
+      WG_CUDA(cudaGetLastError());
+      int bits = 1;
+      while ((1L << bits) < ntiles) bits++;
+      if (sort_pairs(wk.tmp, wk.k0.as<uint32_t>(), wk.k1.as<uint32_t>(), wk.v0.as<uint32_t>(), wk.v1.as<uint32_t>(), npairs,
+                     bits))
+        return 1;
+      k_tile_gather<<<(int)((npairs + 255) / 256), 256>>>(wk.k1.as<uint32_t>(), wk.v1.as<uint32_t>(), npairs, Z,
+                                                          wk.cpos.as<uint32_t>(), wk.Vo.as<float2>(), wk.w.as<float>(),
+                                                          wk.tstart.as<int>(), wk.tend.as<int>(), wk.rec.as<float4>());
+      WG_CUDA(cudaGetLastError());
+    }
+  }
+  const int taps = (2 * sx + 1) * (2 * sy + 1);
+  const int rounds = (taps + 31) / 32;
+#define GVM_GRID_TILES(R)                                                                                       \
+  k_grid_tiles<R><<<(unsigned)ntiles, 32>>>(wk.tstart.as<int>(), wk.tend.as<int>(), wk.rec.as<float4>(),         \
+                                            wk.ck.as<float>(), ck_m, ck_n, sx, sy, M, N, ntx, wk.gw.as<float>(), \
+                                            wk.gV.as<float2>())
+  if (rounds <= 1) GVM_GRID_TILES(1);
+  else if (rounds <= 2) GVM_GRID_TILES(2);
+  else if (rounds <= 3) GVM_GRID_TILES(3);
+  else if (rounds <= 4) GVM_GRID_TILES(4);
+  else if (rounds <= 6) GVM_GRID_TILES(6);
+  else GVM_GRID_TILES(10);
+#undef GVM_GRID_TILES
+  WG_CUDA(cudaGetLastError());
+  *done = true;
   return 0;
 }
 
@@ -452,58 +666,68 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
     WG_CUDA(cudaMemcpy(d_w.p, w, zz * 4, cudaMemcpyHostToDevice));
   }
   WG_CUDA(cudaMemcpy(d_ck.p, ckernel, (size_t)ck_m * ck_n * 4, cudaMemcpyHostToDevice));
-  if (n2 > 0) {
-    k_grid_centres<<<(int)((n2 + 255) / 256), 256>>>(d_uvw.as<double>(), (long)Z, freq, deltau, deltav, M, N,
-                                                     support_x, support_y, d_k0.as<uint32_t>(),
-                                                     d_v0.as<uint32_t>());
-    WG_CUDA(cudaGetLastError());
-    if (sort_pairs(d_tmp, d_k0.as<uint32_t>(), d_k1.as<uint32_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(), n2, 32))
-      return 1;
-  }
-  // start table over the extended grid (ext + 1 entries): histogram of the centre cells + exclusive scan
-  if (d_start.ensure((ext + 2) * 4)) return 1;
-  WG_CUDA(cudaMemset(d_start.p, 0, (ext + 2) * 4));
-  if (n2 > 0) {
-    k_cell_count<<<(int)((n2 + 255) / 256), 256>>>(d_k1.as<uint32_t>(), n2, d_start.as<int>());
-    WG_CUDA(cudaGetLastError());
-  }
+  // accumulation: tile-sequential replay by default, the per-cell k-way merge as fallback / cross-check
+  // (GVM_GRID_MERGE=1); both give the reference's summation order, i.e. bit-identical results
+  bool tiles_done = false;
   {
-    // the merge kernel packs a list's remaining count into 32 - kTapBits bits
-    size_t mb = 0;
-    int* d_maxc = d_flags.as<int>();     // free until k_grid_flags
-    WG_CUDA(cub::DeviceReduce::Max(nullptr, mb, d_start.as<int>(), d_maxc, (int)(ext + 1)));
-    if (d_tmp.ensure(mb)) return 1;
-    WG_CUDA(cub::DeviceReduce::Max(d_tmp.p, mb, d_start.as<int>(), d_maxc, (int)(ext + 1)));
-    int maxc = 0;
-    WG_CUDA(cudaMemcpy(&maxc, d_maxc, 4, cudaMemcpyDeviceToHost));
-    if (maxc >= (1 << (32 - kTapBits))) {
-      gvm_set_error("gvm_grid_block: %d samples fall into one uv cell (limit %d)", maxc, (1 << (32 - kTapBits)) - 1);
-      return 1;
+    const char* force_merge = getenv("GVM_GRID_MERGE");
+    if (!(force_merge && *force_merge == '1'))
+      if (grid_tiles_path(wk, (long)Z, freq, deltau, deltav, M, N, ck_m, ck_n, support_x, support_y, &tiles_done)) return 1;
+  }
+  if (!tiles_done) {
+    if (n2 > 0) {
+      k_grid_centres<<<(int)((n2 + 255) / 256), 256>>>(d_uvw.as<double>(), (long)Z, freq, deltau, deltav, M, N,
+                                                       support_x, support_y, d_k0.as<uint32_t>(),
+                                                       d_v0.as<uint32_t>());
+      WG_CUDA(cudaGetLastError());
+      if (sort_pairs(d_tmp, d_k0.as<uint32_t>(), d_k1.as<uint32_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(), n2, 32))
+        return 1;
     }
+    // start table over the extended grid (ext + 1 entries): histogram of the centre cells + exclusive scan
+    if (d_start.ensure((ext + 2) * 4)) return 1;
+    WG_CUDA(cudaMemset(d_start.p, 0, (ext + 2) * 4));
+    if (n2 > 0) {
+      k_cell_count<<<(int)((n2 + 255) / 256), 256>>>(d_k1.as<uint32_t>(), n2, d_start.as<int>());
+      WG_CUDA(cudaGetLastError());
+    }
+    {
+      // the merge kernel packs a list's remaining count into 32 - kTapBits bits
+      size_t mb = 0;
+      int* d_maxc = d_flags.as<int>();     // free until k_grid_flags
+      WG_CUDA(cub::DeviceReduce::Max(nullptr, mb, d_start.as<int>(), d_maxc, (int)(ext + 1)));
+      if (d_tmp.ensure(mb)) return 1;
+      WG_CUDA(cub::DeviceReduce::Max(d_tmp.p, mb, d_start.as<int>(), d_maxc, (int)(ext + 1)));
+      int maxc = 0;
+      WG_CUDA(cudaMemcpy(&maxc, d_maxc, 4, cudaMemcpyDeviceToHost));
+      if (maxc >= (1 << (32 - kTapBits))) {
+        gvm_set_error("gvm_grid_block: %d samples fall into one uv cell (limit %d)", maxc, (1 << (32 - kTapBits)) - 1);
+        return 1;
+      }
+    }
+    {
+      size_t sb = 0;
+      WG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, d_start.as<int>(), d_start.as<int>(), (int)(ext + 1)));
+      if (d_tmp.ensure(sb)) return 1;
+      WG_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, sb, d_start.as<int>(), d_start.as<int>(), (int)(ext + 1)));
+    }
+    {
+      // threads per CTA from the tap count: 12 bytes of shared state per (thread, tap)
+      const int taps = (2 * support_x + 1) * (2 * support_y + 1);
+  #define GVM_GRID_ACC(T)                                                                                      \
+    do {                                                                                                       \
+      const size_t smem = (size_t)taps * (T) * 3 * sizeof(uint32_t);                                           \
+      WG_CUDA(cudaFuncSetAttribute(k_grid_accumulate<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_grid_accumulate<T><<<(int)((MN + (T) - 1) / (T)), (T), smem>>>(                                        \
+          d_start.as<int>(), d_v1.as<uint32_t>(), n2, (long)Z, d_Vo.as<float2>(), d_w.as<float>(),             \
+          d_ck.as<float>(), ck_m, ck_n, support_x, support_y, M, N, taps, d_gw.as<float>(), d_gV.as<float2>()); \
+    } while (0)
+      if (taps <= 49) GVM_GRID_ACC(128);
+      else if (taps <= 121) GVM_GRID_ACC(64);
+      else GVM_GRID_ACC(32);
+  #undef GVM_GRID_ACC
+    }
+    WG_CUDA(cudaGetLastError());
   }
-  {
-    size_t sb = 0;
-    WG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, d_start.as<int>(), d_start.as<int>(), (int)(ext + 1)));
-    if (d_tmp.ensure(sb)) return 1;
-    WG_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, sb, d_start.as<int>(), d_start.as<int>(), (int)(ext + 1)));
-  }
-  {
-    // threads per CTA from the tap count: 12 bytes of shared state per (thread, tap)
-    const int taps = (2 * support_x + 1) * (2 * support_y + 1);
-#define GVM_GRID_ACC(T)                                                                                      \
-  do {                                                                                                       \
-    const size_t smem = (size_t)taps * (T) * 3 * sizeof(uint32_t);                                           \
-    WG_CUDA(cudaFuncSetAttribute(k_grid_accumulate<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_grid_accumulate<T><<<(int)((MN + (T) - 1) / (T)), (T), smem>>>(                                        \
-        d_start.as<int>(), d_v1.as<uint32_t>(), n2, (long)Z, d_Vo.as<float2>(), d_w.as<float>(),             \
-        d_ck.as<float>(), ck_m, ck_n, support_x, support_y, M, N, taps, d_gw.as<float>(), d_gV.as<float2>()); \
-  } while (0)
-    if (taps <= 49) GVM_GRID_ACC(128);
-    else if (taps <= 121) GVM_GRID_ACC(64);
-    else GVM_GRID_ACC(32);
-#undef GVM_GRID_ACC
-  }
-  WG_CUDA(cudaGetLastError());
   k_grid_flags<<<(int)((MN + 255) / 256), 256>>>(d_gw.as<float>(), (long)MN, d_flags.as<int>());
   size_t bytes = 0;
   WG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, d_flags.as<int>(), d_pos.as<int>(), (int)MN));
