@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(kThreads) k_grid_accumulate(
 // The per-pair record (centre, weight, visibility) is gathered into sorted order first, so the replay
 // streams 16 B per pair with one coalesced load per 32 samples.
 constexpr int kTile = 16;
+constexpr int kTileStride = kTile + 4;   // shared-memory row stride: taps of rows ki and ki + 2 no longer share banks
 
 __device__ __forceinline__ bool grid_centre(const double* __restrict__ uvw_m, long z, long Z, float freq,
                                             double deltau, double deltav, long M, long N, int sx, int sy, int* j,
@@ -300,12 +301,13 @@ __global__ void __launch_bounds__(32) k_grid_tiles(const int* __restrict__ tstar
                                                    const float4* __restrict__ rec, const float* __restrict__ kernel,
                                                    int ck_m, int ck_n, int sx, int sy, long M, long N, int ntx,
                                                    float* __restrict__ out_w, float2* __restrict__ out_V) {
-  __shared__ float s_gw[kTile * kTile], s_gw2[kTile * kTile], s_gvr[kTile * kTile], s_gvi[kTile * kTile];
+  __shared__ float s_gw[kTile * kTileStride], s_gw2[kTile * kTileStride], s_gvr[kTile * kTileStride],
+      s_gvi[kTile * kTileStride];
   const int lane = threadIdx.x;
   const int tile = blockIdx.x;
   const int ty = tile / ntx, tx = tile - ty * ntx;
   const int k0 = ty * kTile, j0 = tx * kTile;
-  for (int c = lane; c < kTile * kTile; c += 32) { s_gw[c] = 0.f; s_gw2[c] = 0.f; s_gvr[c] = 0.f; s_gvi[c] = 0.f; }
+  for (int c = lane; c < kTile * kTileStride; c += 32) { s_gw[c] = 0.f; s_gw2[c] = 0.f; s_gvr[c] = 0.f; s_gvi[c] = 0.f; }
   // this lane's taps: offsets from the centre and kernel values (ck = NaN marks "no tap")
   const int tw = 2 * sx + 1, taps = tw * (2 * sy + 1);
   int dm[kRounds], dn[kRounds];
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(32) k_grid_tiles(const int* __restrict__ tstar
       for (int r = 0; r < kRounds; r++) {
         const int cj = lj + dn[r], ck_ = lk + dm[r];
         if (on[r] && cj >= 0 && cj < kTile && ck_ >= 0 && ck_ < kTile && j0 + cj < N && k0 + ck_ < M) {
-          const int c = ck_ * kTile + cj;
+          const int c = ck_ * kTileStride + cj;
           s_gw[c] = __fadd_rn(s_gw[c], __fmul_rn(wt, ckv[r]));
           s_gw2[c] = __fadd_rn(s_gw2[c], __fmul_rn(wt, ck2v[r]));
           s_gvr[c] = __fadd_rn(s_gvr[c], __fmul_rn(wr, ckv[r]));
@@ -349,9 +351,10 @@ __global__ void __launch_bounds__(32) k_grid_tiles(const int* __restrict__ tstar
     }
   }
   // normalise (src/functions.cu:1537-1558) and write the tile
-  for (int c = lane; c < kTile * kTile; c += 32) {
-    const int ck_ = c / kTile, cj = c - ck_ * kTile;
+  for (int cc = lane; cc < kTile * kTile; cc += 32) {
+    const int ck_ = cc / kTile, cj = cc - ck_ * kTile;
     if (j0 + cj >= N || k0 + ck_ >= M) continue;
+    const int c = ck_ * kTileStride + cj;
     const float gw = s_gw[c], gw2 = s_gw2[c];
     float weight = 0.f, orr = 0.f, oi = 0.f;
     if (gw2 != 0.0f && gw != 0.0f) {
