@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kThreads) k_grid_accumulate(
 // The per-pair record (centre, weight, visibility) is gathered into sorted order first, so the replay
 // streams 16 B per pair with one coalesced load per 32 samples.
 constexpr int kTile = 16;
-constexpr int kTileStride = kTile + 4;   // shared-memory row stride: taps of rows ki and ki + 2 no longer share banks
+constexpr int kTileStride = kTile + 1;   // shared-memory row stride (in 16-byte cells): spreads the tap rows over the banks
 
 __device__ __forceinline__ bool grid_centre(const double* __restrict__ uvw_m, long z, long Z, float freq,
                                             double deltau, double deltav, long M, long N, int sx, int sy, int* j,
@@ -296,31 +296,43 @@ __global__ void __launch_bounds__(256) k_tile_gather(const uint32_t* __restrict_
   rec[i] = make_float4(__uint_as_float(cpos[z]), w[vi], vo.x, vo.y);
 }
 
+// tiles sorted by decreasing sample count: the long replays start first (longest-processing-time order)
+__global__ void __launch_bounds__(256) k_tile_order_keys(const int* __restrict__ tstart, const int* __restrict__ tend,
+                                                         long ntiles, uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ vals) {
+  const long t = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  keys[t] = 0x7FFFFFFFu - (uint32_t)(tend[t] - tstart[t]);
+  vals[t] = (uint32_t)t;
+}
+
 template <int kRounds>
-__global__ void __launch_bounds__(32) k_grid_tiles(const int* __restrict__ tstart, const int* __restrict__ tend,
-                                                   const float4* __restrict__ rec, const float* __restrict__ kernel,
-                                                   int ck_m, int ck_n, int sx, int sy, long M, long N, int ntx,
-                                                   float* __restrict__ out_w, float2* __restrict__ out_V) {
-  __shared__ float s_gw[kTile * kTileStride], s_gw2[kTile * kTileStride], s_gvr[kTile * kTileStride],
-      s_gvi[kTile * kTileStride];
+__global__ void __launch_bounds__(32) k_grid_tiles(const uint32_t* __restrict__ order, const int* __restrict__ tstart,
+                                                   const int* __restrict__ tend, const float4* __restrict__ rec,
+                                                   const float* __restrict__ kernel, int ck_m, int ck_n, int sx, int sy,
+                                                   long M, long N, int ntx, float* __restrict__ out_w,
+                                                   float2* __restrict__ out_V) {
+  // (gw, gw2, gvr, gvi) of every cell of the tile: one 16-byte shared-memory word per cell
+  __shared__ float4 s_acc[kTile * kTileStride];
   const int lane = threadIdx.x;
-  const int tile = blockIdx.x;
+  const int tile = (int)order[blockIdx.x];
   const int ty = tile / ntx, tx = tile - ty * ntx;
   const int k0 = ty * kTile, j0 = tx * kTile;
-  for (int c = lane; c < kTile * kTileStride; c += 32) { s_gw[c] = 0.f; s_gw2[c] = 0.f; s_gvr[c] = 0.f; s_gvi[c] = 0.f; }
-  // this lane's taps: offsets from the centre and kernel values (ck = NaN marks "no tap")
+  for (int c = lane; c < kTile * kTileStride; c += 32) s_acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // cells of the tile that lie on the grid (edge tiles): [0, lim_j) x [0, lim_k)
+  const unsigned lim_j = (unsigned)min((long)kTile, N - j0), lim_k = (unsigned)min((long)kTile, M - k0);
+  // this lane's taps: offsets from the centre and kernel values
   const int tw = 2 * sx + 1, taps = tw * (2 * sy + 1);
   int dm[kRounds], dn[kRounds];
   float ckv[kRounds], ck2v[kRounds];
-  bool on[kRounds];
 #pragma unroll
   for (int r = 0; r < kRounds; r++) {
     const int t = lane + 32 * r;
     const int ki = t / tw, kj = t - ki * tw;
-    on[r] = t < taps && ki < ck_m && kj < ck_n;
-    dm[r] = ki - sy;
+    const bool on = t < taps && ki < ck_m && kj < ck_n;
+    dm[r] = on ? ki - sy : -100000;     // an inactive tap lands outside every tile
     dn[r] = kj - sx;
-    ckv[r] = on[r] ? kernel[ck_n * ki + kj] : 0.f;
+    ckv[r] = on ? kernel[ck_n * ki + kj] : 0.f;
     ck2v[r] = __fmul_rn(ckv[r], ckv[r]);
   }
   __syncwarp();
@@ -338,13 +350,15 @@ __global__ void __launch_bounds__(32) k_grid_tiles(const int* __restrict__ tstar
       const float wr = __fmul_rn(wt, vr), wi = __fmul_rn(wt, vim);
 #pragma unroll
       for (int r = 0; r < kRounds; r++) {
-        const int cj = lj + dn[r], ck_ = lk + dm[r];
-        if (on[r] && cj >= 0 && cj < kTile && ck_ >= 0 && ck_ < kTile && j0 + cj < N && k0 + ck_ < M) {
-          const int c = ck_ * kTileStride + cj;
-          s_gw[c] = __fadd_rn(s_gw[c], __fmul_rn(wt, ckv[r]));
-          s_gw2[c] = __fadd_rn(s_gw2[c], __fmul_rn(wt, ck2v[r]));
-          s_gvr[c] = __fadd_rn(s_gvr[c], __fmul_rn(wr, ckv[r]));
-          s_gvi[c] = __fadd_rn(s_gvi[c], __fmul_rn(wi, ckv[r]));
+        const unsigned cj = (unsigned)(lj + dn[r]), ck_ = (unsigned)(lk + dm[r]);
+        if (cj < lim_j && ck_ < lim_k) {
+          float4* cell = &s_acc[ck_ * kTileStride + cj];
+          float4 a = *cell;
+          a.x = __fadd_rn(a.x, __fmul_rn(wt, ckv[r]));
+          a.y = __fadd_rn(a.y, __fmul_rn(wt, ck2v[r]));
+          a.z = __fadd_rn(a.z, __fmul_rn(wr, ckv[r]));
+          a.w = __fadd_rn(a.w, __fmul_rn(wi, ckv[r]));
+          *cell = a;
         }
       }
       __syncwarp();
@@ -352,15 +366,14 @@ __global__ void __launch_bounds__(32) k_grid_tiles(const int* __restrict__ tstar
   }
   // normalise (src/functions.cu:1537-1558) and write the tile
   for (int cc = lane; cc < kTile * kTile; cc += 32) {
-    const int ck_ = cc / kTile, cj = cc - ck_ * kTile;
-    if (j0 + cj >= N || k0 + ck_ >= M) continue;
-    const int c = ck_ * kTileStride + cj;
-    const float gw = s_gw[c], gw2 = s_gw2[c];
+    const unsigned ck_ = cc / kTile, cj = cc - ck_ * kTile;
+    if (cj >= lim_j || ck_ >= lim_k) continue;
+    const float4 a = s_acc[ck_ * kTileStride + cj];
     float weight = 0.f, orr = 0.f, oi = 0.f;
-    if (gw2 != 0.0f && gw != 0.0f) {
-      weight = __fdiv_rn(__fmul_rn(gw, gw), gw2);
-      orr = __fdiv_rn(s_gvr[c], gw);
-      oi = __fdiv_rn(s_gvi[c], gw);
+    if (a.y != 0.0f && a.x != 0.0f) {
+      weight = __fdiv_rn(__fmul_rn(a.x, a.x), a.y);
+      orr = __fdiv_rn(a.z, a.x);
+      oi = __fdiv_rn(a.w, a.x);
     }
     const long cell = (long)(k0 + ck_) * N + (j0 + cj);
     out_w[cell] = weight;
@@ -428,7 +441,7 @@ thread_local GridResult g_grid_result;
 // block costs more than the kernels); gvm_grid_release() returns them
 struct GridWork {
   DevBuf uvw, Vo, w, ck, k0, k1, v0, v1, tmp, gw, gV, flags, pos, start;
-  DevBuf cpos, cnt, off, rec, tstart, tend;   // tile-sequential path
+  DevBuf cpos, cnt, off, rec, tstart, tend, ord0, ord1, ordk0, ordk1;   // tile-sequential path
 };
 thread_local GridWork g_grid_work;
 
@@ -486,12 +499,22 @@ int grid_tiles_path(GridWork& wk, long Z, float freq, double deltau, double delt
       WG_CUDA(cudaGetLastError());
     }
   }
+  // replay order: tiles by decreasing sample count
+  if (wk.ord0.ensure((size_t)ntiles * 4) || wk.ord1.ensure((size_t)ntiles * 4) || wk.ordk0.ensure((size_t)ntiles * 4) ||
+      wk.ordk1.ensure((size_t)ntiles * 4))
+    return 1;
+  k_tile_order_keys<<<(int)((ntiles + 255) / 256), 256>>>(wk.tstart.as<int>(), wk.tend.as<int>(), ntiles,
+                                                          wk.ordk0.as<uint32_t>(), wk.ord0.as<uint32_t>());
+  WG_CUDA(cudaGetLastError());
+  if (sort_pairs(wk.tmp, wk.ordk0.as<uint32_t>(), wk.ordk1.as<uint32_t>(), wk.ord0.as<uint32_t>(), wk.ord1.as<uint32_t>(),
+                 ntiles, 31))
+    return 1;
   const int taps = (2 * sx + 1) * (2 * sy + 1);
   const int rounds = (taps + 31) / 32;
 #define GVM_GRID_TILES(R)                                                                                       \
-  k_grid_tiles<R><<<(unsigned)ntiles, 32>>>(wk.tstart.as<int>(), wk.tend.as<int>(), wk.rec.as<float4>(),         \
-                                            wk.ck.as<float>(), ck_m, ck_n, sx, sy, M, N, ntx, wk.gw.as<float>(), \
-                                            wk.gV.as<float2>())
+  k_grid_tiles<R><<<(unsigned)ntiles, 32>>>(wk.ord1.as<uint32_t>(), wk.tstart.as<int>(), wk.tend.as<int>(),      \
+                                            wk.rec.as<float4>(), wk.ck.as<float>(), ck_m, ck_n, sx, sy, M, N,    \
+                                            ntx, wk.gw.as<float>(), wk.gV.as<float2>())
   if (rounds <= 1) GVM_GRID_TILES(1);
   else if (rounds <= 2) GVM_GRID_TILES(2);
   else if (rounds <= 3) GVM_GRID_TILES(3);
