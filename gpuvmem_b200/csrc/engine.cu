@@ -249,9 +249,11 @@ int gvm_add_channel(gvm_engine* e, const gvm_channel_desc* desc, int64_t Z, cons
     GVM_CUDA(cudaMalloc(&d_uvw, z * 3 * sizeof(double)));
     GVM_CUDA(cudaMalloc(&d_vo, z * sizeof(float2)));
     GVM_CUDA(cudaMalloc(&d_w, z * sizeof(float)));
-    GVM_CUDA(cudaMemcpyAsync(d_uvw, uvw_m, z * 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    GVM_CUDA(cudaMemcpyAsync(d_vo, Vo, z * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
-    GVM_CUDA(cudaMemcpyAsync(d_w, w, z * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    if (gvm_fast_h2d(d_uvw, uvw_m, z * 3 * sizeof(double), e->stream) || gvm_fast_h2d(d_vo, Vo, z * sizeof(float2), e->stream) ||
+        gvm_fast_h2d(d_w, w, z * sizeof(float), e->stream)) {
+      cudaFree(d_uvw); cudaFree(d_vo); cudaFree(d_w);
+      return 1;
+    }
     int rc = gvm_launch_prep_channel(e, c, d_uvw, d_vo, d_w);
     cudaFree(d_uvw); cudaFree(d_vo); cudaFree(d_w);
     if (rc) return rc;
@@ -285,10 +287,10 @@ int gvm_get_vis(gvm_engine* e, int chan, double* uvw_lambda, int32_t* cell, floa
   GvmChannel& c = e->chans[chan];
   const size_t Z = (size_t)c.Z;
   GVM_CUDA(cudaStreamSynchronize(e->stream));
-  if (uvw_lambda) GVM_CUDA(cudaMemcpy(uvw_lambda, c.uvw_l, Z * 3 * sizeof(double), cudaMemcpyDeviceToHost));
-  if (Vo) GVM_CUDA(cudaMemcpy(Vo, c.Vo, Z * sizeof(float2), cudaMemcpyDeviceToHost));
-  if (Vr) GVM_CUDA(cudaMemcpy(Vr, c.Vr, Z * sizeof(float2), cudaMemcpyDeviceToHost));
-  if (w) GVM_CUDA(cudaMemcpy(w, c.w, Z * sizeof(float), cudaMemcpyDeviceToHost));
+  if (uvw_lambda && gvm_fast_d2h(uvw_lambda, c.uvw_l, Z * 3 * sizeof(double), e->stream)) return 1;
+  if (Vo && gvm_fast_d2h(Vo, c.Vo, Z * sizeof(float2), e->stream)) return 1;
+  if (Vr && gvm_fast_d2h(Vr, c.Vr, Z * sizeof(float2), e->stream)) return 1;
+  if (w && gvm_fast_d2h(w, c.w, Z * sizeof(float), e->stream)) return 1;
   if (Vm) {
     if (!c.Vm) { gvm_set_error("gvm_get_vis: Vm not kept (cfg.keep_vm = 0)"); return 1; }
     GVM_CUDA(cudaMemcpy(Vm, c.Vm, Z * sizeof(float2), cudaMemcpyDeviceToHost));
@@ -438,11 +440,10 @@ int gvm_dev_memset(gvm_engine* e, void* p, int value, size_t bytes) {
   return 0;
 }
 int gvm_dev_copy(gvm_engine* e, void* dst, const void* src, size_t bytes, int kind) {
-  const cudaMemcpyKind k = kind == GVM_COPY_H2D ? cudaMemcpyHostToDevice
-                           : kind == GVM_COPY_D2H ? cudaMemcpyDeviceToHost
-                                                  : cudaMemcpyDeviceToDevice;
-  GVM_CUDA(cudaMemcpyAsync(dst, src, bytes, k, e->stream));
-  if (kind != GVM_COPY_D2D) GVM_CUDA(cudaStreamSynchronize(e->stream));
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  if (kind == GVM_COPY_H2D) return gvm_fast_h2d(dst, src, bytes, e->stream);   // synchronous, pipelined for large pageable buffers
+  if (kind == GVM_COPY_D2H) return gvm_fast_d2h(dst, src, bytes, e->stream);
+  GVM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, e->stream));
   return 0;
 }
 

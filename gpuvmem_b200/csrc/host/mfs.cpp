@@ -395,7 +395,8 @@ void MFS::doGridding() {
     }
     ds.data.max_number_visibilities_in_channel_and_stokes = max;
   }
-  GVM_CHECK(gvm_grid_release());   // the gridding work buffers (several GB at C5) go back before the engine uploads
+  // the gridding work buffers stay allocated (a later block or run reuses them; cudaFree of tens of GB costs
+  // more than the gridding itself) and go back in MFS::unSetDevice
 }
 
 bool shardRange(int max_nfreq, int chan, size_t Z, int rank, int world, size_t* lo, size_t* hi) {
@@ -747,6 +748,7 @@ void MFS::unSetDevice() {
   Globals& g = G();
   hostProfileReport();
   if (!g.quiet) std::printf("Freeing device memory\n");
+  gvm_grid_release();
   if (g.engine) {
     devFree(device_Image);
     device_Image = nullptr;

@@ -454,6 +454,29 @@ int sort_pairs(DevBuf& tmp, uint32_t* k_in, uint32_t* k_out, uint32_t* v_in, uin
   return 0;
 }
 
+// GVM_GRID_TIMING=1: wall time of the phases of gvm_grid_block / gvm_weights on stderr (device-synchronised)
+struct PhaseTimer {
+  bool on;
+  double t0;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+  }
+  PhaseTimer() {
+    const char* v = getenv("GVM_GRID_TIMING");
+    on = v && *v == '1';
+    t0 = on ? now() : 0.0;
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const double t = now();
+    fprintf(stderr, "[gvm timing] %-28s %9.3f ms\n", what, 1e3 * (t - t0));
+    t0 = t;
+  }
+};
+
 // The tile-sequential accumulation (k_tile_* + k_grid_tiles): fills gw/gV like k_grid_accumulate does.
 // *done = false (nothing launched) when the problem does not fit its 16-bit centre packing / 31-bit pair count.
 int grid_tiles_path(GridWork& wk, long Z, float freq, double deltau, double deltav, long M, long N, int ck_m,
@@ -569,11 +592,11 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
       const long z = (long)Z[b];
       if (scheme == GVM_W_RADIAL && z > 0) {
         if (d_uvw.ensure((size_t)z * 24) || d_w.ensure((size_t)z * 4)) return 1;
-        WG_CUDA(cudaMemcpy(d_uvw.p, uvw_m[b], (size_t)z * 24, cudaMemcpyHostToDevice));
-        WG_CUDA(cudaMemcpy(d_w.p, w[b], (size_t)z * 4, cudaMemcpyHostToDevice));
+        if (gvm_fast_h2d(d_uvw.p, uvw_m[b], (size_t)z * 24, 0)) return 1;
+        if (gvm_fast_h2d(d_w.p, w[b], (size_t)z * 4, 0)) return 1;
         k_radial<<<(int)((z + 255) / 256), 256>>>(d_uvw.as<double>(), z, freqs[b], d_w.as<float>());
         WG_CUDA(cudaGetLastError());
-        WG_CUDA(cudaMemcpy(w[b], d_w.p, (size_t)z * 4, cudaMemcpyDeviceToHost));
+        if (gvm_fast_d2h(w[b], d_w.p, (size_t)z * 4, 0)) return 1;
       }
       if (use_taper) apply_taper_host(taper, scheme, z, uvw_m[b], freqs[b], w[b]);
     }
@@ -597,8 +620,8 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
 
   auto load_and_sort = [&](int b) -> int {
     const long z = (long)Z[b];
-    WG_CUDA(cudaMemcpy(d_uvw.p, uvw_m[b], (size_t)z * 24, cudaMemcpyHostToDevice));
-    WG_CUDA(cudaMemcpy(d_w.p, w[b], (size_t)z * 4, cudaMemcpyHostToDevice));
+    if (gvm_fast_h2d(d_uvw.p, uvw_m[b], (size_t)z * 24, 0)) return 1;
+    if (gvm_fast_h2d(d_w.p, w[b], (size_t)z * 4, 0)) return 1;
     k_weight_cells<<<(int)((z + 255) / 256), 256>>>(d_uvw.as<double>(), z, freqs[b], adu, adv, M, N,
                                                     d_k0.as<uint32_t>(), d_v0.as<uint32_t>());
     WG_CUDA(cudaGetLastError());
@@ -625,7 +648,7 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
       }
       // the first-pass grid is never cleared between blocks and the half-plane sum of squares is
       // taken after each one (src/briggsweightingscheme.cu:59-106)
-      WG_CUDA(cudaMemcpy(hgrid.data(), d_grid.p, MN * 4, cudaMemcpyDeviceToHost));
+      if (gvm_fast_d2h(hgrid.data(), d_grid.p, MN * 4, 0)) return 1;
       for (long m = 0; m < M; m++)
         for (long n = N / 2; n < N; n++) sum_g2 += hgrid[N * m + n] * hgrid[N * m + n];
     }
@@ -633,10 +656,12 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
     f_squared = (5.0f * powf(10.0f, -robust)) * (5.0f * powf(10.0f, -robust)) / avg;
     WG_CUDA(cudaMemset(d_grid.p, 0, MN * 4));
   }
+  // with a single block the first Briggs pass has left this block's sorted cells and weights on the device
+  const bool sorted_resident = scheme == GVM_W_BRIGGS && nblocks == 1;
   for (int b = 0; b < nblocks; b++) {
     const long z = (long)Z[b];
     if (z > 0) {
-      if (load_and_sort(b)) return 1;
+      if (!sorted_resident && load_and_sort(b)) return 1;
       const int blocks = (int)((z + 255) / 256);
       k_cell_accumulate<<<blocks, 256>>>(d_k1.as<uint32_t>(), d_v1.as<uint32_t>(), z, d_w.as<float>(),
                                          d_grid.as<float>());
@@ -644,7 +669,7 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
                                       scheme == GVM_W_BRIGGS, f_squared, d_w.as<float>());
       k_clear_cells<<<blocks, 256>>>(d_k1.as<uint32_t>(), z, d_grid.as<float>());
       WG_CUDA(cudaGetLastError());
-      WG_CUDA(cudaMemcpy(w[b], d_w.p, (size_t)z * 4, cudaMemcpyDeviceToHost));
+      if (gvm_fast_d2h(w[b], d_w.p, (size_t)z * 4, 0)) return 1;
     }
     if (use_taper) apply_taper_host(taper, scheme, z, uvw_m[b], freqs[b], w[b]);
   }
@@ -674,6 +699,7 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
   const size_t ext = (size_t)(M + 2 * support_y) * (size_t)(N + 2 * support_x);
   if (ext >= (size_t)kNoCell || n2 >= (long)0x7FFFFFFF) { gvm_set_error("gvm_grid_block: problem too large"); return 1; }
   *nout = 0;
+  PhaseTimer pt;
   GridWork& wk = g_grid_work;
   DevBuf &d_uvw = wk.uvw, &d_Vo = wk.Vo, &d_w = wk.w, &d_ck = wk.ck, &d_k0 = wk.k0, &d_k1 = wk.k1, &d_v0 = wk.v0,
          &d_v1 = wk.v1, &d_tmp = wk.tmp, &d_gw = wk.gw, &d_gV = wk.gV, &d_flags = wk.flags, &d_pos = wk.pos,
@@ -687,10 +713,10 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
       d_gw.ensure(MN * 4) || d_gV.ensure(MN * 8) || d_flags.ensure(MN * 4) || d_pos.ensure(MN * 4))
     return 1;
   if (Z > 0) {
-    WG_CUDA(cudaMemcpy(d_uvw.p, uvw_m, zz * 24, cudaMemcpyHostToDevice));
-    WG_CUDA(cudaMemcpy(d_Vo.p, Vo, zz * 8, cudaMemcpyHostToDevice));
-    WG_CUDA(cudaMemcpy(d_w.p, w, zz * 4, cudaMemcpyHostToDevice));
+  pt.mark("grid: device buffers");
+    if (gvm_fast_h2d(d_uvw.p, uvw_m, zz * 24, 0) || gvm_fast_h2d(d_Vo.p, Vo, zz * 8, 0) || gvm_fast_h2d(d_w.p, w, zz * 4, 0)) return 1;
   }
+  pt.mark("grid: upload");
   WG_CUDA(cudaMemcpy(d_ck.p, ckernel, (size_t)ck_m * ck_n * 4, cudaMemcpyHostToDevice));
   // accumulation: tile-sequential replay by default, the per-cell k-way merge as fallback / cross-check
   // (GVM_GRID_MERGE=1); both give the reference's summation order, i.e. bit-identical results
@@ -700,6 +726,7 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
     if (!(force_merge && *force_merge == '1'))
       if (grid_tiles_path(wk, (long)Z, freq, deltau, deltav, M, N, ck_m, ck_n, support_x, support_y, &tiles_done)) return 1;
   }
+  pt.mark("grid: tile replay");
   if (!tiles_done) {
     if (n2 > 0) {
       k_grid_centres<<<(int)((n2 + 255) / 256), 256>>>(d_uvw.as<double>(), (long)Z, freq, deltau, deltav, M, N,
@@ -755,6 +782,7 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
     WG_CUDA(cudaGetLastError());
   }
   k_grid_flags<<<(int)((MN + 255) / 256), 256>>>(d_gw.as<float>(), (long)MN, d_flags.as<int>());
+  pt.mark("grid: merge path / flags");
   size_t bytes = 0;
   WG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, d_flags.as<int>(), d_pos.as<int>(), (int)MN));
   if (d_tmp.ensure(bytes)) return 1;
@@ -771,6 +799,7 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
     WG_CUDA(cudaGetLastError());
     WG_CUDA(cudaDeviceSynchronize());
   }
+  pt.mark("grid: compact");
   res.count = count;
   *nout = count;
   // outputs may be omitted: the caller sizes its arrays from *nout and calls gvm_grid_fetch
@@ -787,9 +816,9 @@ int gvm_grid_fetch(double* uvw_out, float* Vo_out, float* w_out) {
   GridResult& res = g_grid_result;
   const size_t count = (size_t)res.count;
   if (count > 0) {
-    if (uvw_out) WG_CUDA(cudaMemcpy(uvw_out, res.uvw.p, count * 24, cudaMemcpyDeviceToHost));
-    if (Vo_out) WG_CUDA(cudaMemcpy(Vo_out, res.Vo.p, count * 8, cudaMemcpyDeviceToHost));
-    if (w_out) WG_CUDA(cudaMemcpy(w_out, res.w.p, count * 4, cudaMemcpyDeviceToHost));
+    if (uvw_out && gvm_fast_d2h(uvw_out, res.uvw.p, count * 24, 0)) return 1;
+    if (Vo_out && gvm_fast_d2h(Vo_out, res.Vo.p, count * 8, 0)) return 1;
+    if (w_out && gvm_fast_d2h(w_out, res.w.p, count * 4, 0)) return 1;
   }
   return 0;
 }
