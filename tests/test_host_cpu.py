@@ -230,3 +230,15 @@ def test_shard_plan_covers_every_visibility_exactly_once():
                 covered[lo:hi] += 1
             assert (covered == 1).all()
     assert host.shard_plan([5, 6], 1, 0) == [(0, 5), (0, 6)]
+
+
+def test_option_parser_is_reentrant():
+    """getOptions is called once per Synthesizer::configure; glibc's getopt keeps a pointer into the previous
+    argv unless it is fully re-initialised (optind = 0) — a trailing boolean flag used to poison the next parse."""
+    for _ in range(3):
+        a = host.parse_args("-z 0.001 -Z 0.01 -t 3 -M")
+        b = host.parse_args("-z 0.002,0.5 -Z 0.01,0.005 -t 6 -e -0.5 -x")
+        c = host.parse_args("-x -v -P")
+        assert a["ok"] and a["it_max"] == 3 and a["initial_values"] == "0.001"
+        assert b["ok"] and b["it_max"] == 6 and b["initial_values"] == "0.002,0.5" and b["eta"] == -0.5 and b["nopositivity"] == 1
+        assert c["ok"] and c["nopositivity"] == 1 and c["verbose"] == 1 and c["print_images"] == 1 and c["it_max"] == 500
