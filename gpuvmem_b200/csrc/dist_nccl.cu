@@ -23,7 +23,9 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*GetVersion)(int*) = nullptr;
 };
@@ -40,7 +42,9 @@ int load_nccl() {
   GVM_SYM(GetUniqueId, "ncclGetUniqueId")
   GVM_SYM(CommInitRank, "ncclCommInitRank")
   GVM_SYM(AllReduce, "ncclAllReduce")
+  GVM_SYM(Broadcast, "ncclBroadcast")
   GVM_SYM(CommDestroy, "ncclCommDestroy")
+  GVM_SYM(CommAbort, "ncclCommAbort")
   GVM_SYM(GetErrorString, "ncclGetErrorString")
   GVM_SYM(GetVersion, "ncclGetVersion")
 #undef GVM_SYM
@@ -58,17 +62,35 @@ int load_nccl() {
   } while (0)
 }  // namespace
 
+#define GVM_DIST_ALIVE(e) \
+  if (!(e)->nccl_comm) { gvm_set_error("gvm_dist: the communicator was aborted after a failure on this rank"); return 1; }
+
 int gvm_dist_allreduce_f32(gvm_engine* e, float* buf, size_t n) {
   if (e->world <= 1) return 0;
+  GVM_DIST_ALIVE(e)
   GVM_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat, ncclSum, (ncclComm_t)e->nccl_comm, e->stream));
   e->collectives++;
   return 0;
 }
 int gvm_dist_allreduce_f64(gvm_engine* e, double* buf, size_t n) {
   if (e->world <= 1) return 0;
+  GVM_DIST_ALIVE(e)
   GVM_NCCL(g_nccl.AllReduce(buf, buf, n, ncclDouble, ncclSum, (ncclComm_t)e->nccl_comm, e->stream));
   e->collectives++;
   return 0;
+}
+int gvm_dist_broadcast_f32(gvm_engine* e, float* buf, size_t n, int root) {
+  if (e->world <= 1) return 0;
+  GVM_DIST_ALIVE(e)
+  GVM_NCCL(g_nccl.Broadcast(buf, buf, n, ncclFloat, root, (ncclComm_t)e->nccl_comm, e->stream));
+  e->collectives++;
+  return 0;
+}
+void gvm_dist_abort_comm(gvm_engine* e) {
+  if (e->world <= 1 || !e->nccl_comm) return;
+  if (g_nccl.CommAbort) g_nccl.CommAbort((ncclComm_t)e->nccl_comm);
+  e->nccl_comm = nullptr;   // every later collective of this engine fails instead of touching a dead communicator
+  e->dist_aborted = true;
 }
 void gvm_dist_release(gvm_engine* e) {
   if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)e->nccl_comm);
@@ -107,6 +129,16 @@ int gvm_dist_init(gvm_engine* e, int rank, int world, const char* id, size_t byt
 int gvm_dist_rank(gvm_engine* e) { return e->rank; }
 int gvm_dist_world(gvm_engine* e) { return e->world; }
 int64_t gvm_dist_collectives(gvm_engine* e) { return e->collectives; }
+
+int gvm_dist_abort(gvm_engine* e) {
+  gvm_dist_abort_comm(e);
+  return 0;
+}
+
+int gvm_dist_broadcast(gvm_engine* e, float* buf_dev, int64_t n, int root) {
+  if (root < 0 || root >= e->world) { gvm_set_error("gvm_dist_broadcast: root %d of %d", root, e->world); return 1; }
+  return gvm_dist_broadcast_f32(e, buf_dev, (size_t)n, root);
+}
 
 /* In-place sum all-reduce of n floats on the engine stream (optimizer-level use). */
 int gvm_dist_allreduce(gvm_engine* e, float* buf_dev, int64_t n) {

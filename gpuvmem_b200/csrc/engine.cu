@@ -1,6 +1,6 @@
 // engine.cu — the C-ABI (include/gvm_b200.h): lifecycle, uploads, and the host
-// drivers of the hot path. The kernels live in forward.cu, grad_simt.cu,
-// grad_umma.cu, priors.cu, vecops.cu and weights_grid.cu.
+// drivers of the hot path. The kernels live in forward.cu, grad_simt.cu, grad_umma.cu,
+// grad_gridfft.cu, errormaps.cu, priors.cu (priors + optimizer vector ops) and weights_grid.cu.
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -36,6 +36,40 @@ extern "C" {
 const char* gvm_last_error(void) { return g_err; }
 int gvm_version(void) { return 100; }
 
+// (Re)allocate the per-block reduction state for `slots` blocks, keeping what the existing blocks left
+// there (Z, the sums and maxima of the last forward pass). Grows on demand in gvm_add_channel: large
+// mosaics / many-channel datasets have thousands of (field, channel, stokes) blocks.
+static int ensure_red_slots(gvm_engine* e, int slots) {
+  if (slots <= e->red_slots) return 0;
+  int n = e->red_slots > 0 ? e->red_slots : 1024;
+  while (n < slots) n *= 2;
+  const size_t rp = (size_t)n * e->red_blocks;
+  double* partials = nullptr; unsigned int* counter = nullptr; double* sum = nullptr; long* Zs = nullptr; float* mx = nullptr;
+  GVM_CUDA(cudaStreamSynchronize(e->stream));
+  GVM_CUDA(cudaMalloc(&partials, rp * (sizeof(double) + sizeof(float))));
+  GVM_CUDA(cudaMalloc(&counter, n * sizeof(unsigned int)));
+  GVM_CUDA(cudaMemset(counter, 0, n * sizeof(unsigned int)));
+  GVM_CUDA(cudaMalloc(&sum, n * sizeof(double)));
+  GVM_CUDA(cudaMemset(sum, 0, n * sizeof(double)));
+  GVM_CUDA(cudaMalloc(&Zs, n * sizeof(long)));
+  GVM_CUDA(cudaMemset(Zs, 0, n * sizeof(long)));
+  GVM_CUDA(cudaMalloc(&mx, 3 * (size_t)n * sizeof(float)));
+  GVM_CUDA(cudaMemset(mx, 0, 3 * (size_t)n * sizeof(float)));
+  if (e->red_slots > 0) {
+    const int o = e->red_slots;
+    GVM_CUDA(cudaMemcpy(sum, e->red_sum, o * sizeof(double), cudaMemcpyDeviceToDevice));
+    GVM_CUDA(cudaMemcpy(Zs, e->red_Z, o * sizeof(long), cudaMemcpyDeviceToDevice));
+    for (int k = 0; k < 3; k++)   // [max | inv_scale | spare] planes of `slots` floats each
+      GVM_CUDA(cudaMemcpy(mx + (size_t)k * n, e->red_max + (size_t)k * o, o * sizeof(float), cudaMemcpyDeviceToDevice));
+  }
+  cudaFree(e->red_partials); cudaFree(e->red_counter); cudaFree(e->red_sum); cudaFree(e->red_Z); cudaFree(e->red_max);
+  e->red_partials = partials; e->red_counter = counter; e->red_sum = sum; e->red_Z = Zs; e->red_max = mx;
+  e->red_slots = n;
+  return 0;
+}
+
+static int create_impl(gvm_engine* e, const gvm_config* cfg, const cudaDeviceProp& prop);
+
 int gvm_create(const gvm_config* cfg, gvm_engine** out) {
   if (!cfg || !out) { gvm_set_error("gvm_create: null argument"); return 1; }
   if (cfg->M != cfg->N || cfg->N <= 0) {
@@ -61,6 +95,15 @@ int gvm_create(const gvm_config* cfg, gvm_engine** out) {
   }
   gvm_engine* e = new gvm_engine();
   e->cfg = *cfg;
+  if (create_impl(e, cfg, prop)) {   // nothing leaks on a failed allocation: gvm_destroy frees what exists
+    gvm_destroy(e);
+    return 1;
+  }
+  *out = e;
+  return 0;
+}
+
+static int create_impl(gvm_engine* e, const gvm_config* cfg, const cudaDeviceProp& prop) {
   e->sm_count = prop.multiProcessorCount;
   // a BLOCKING stream: it orders itself against the legacy default stream, which is what the
   // reference's host code (and torch, by default) launches on — safe drop-in semantics
@@ -77,17 +120,8 @@ int gvm_create(const gvm_config* cfg, gvm_engine** out) {
   GVM_CUDA(cudaMalloc(&e->I_stage, 2 * MN * sizeof(float)));
   GVM_CUDA(cudaMalloc(&e->grad_stage, 2 * MN * sizeof(float)));
   e->red_blocks = e->sm_count * 8;
-  e->red_slots = 1024;
-  const size_t rp = (size_t)e->red_slots * e->red_blocks;
-  GVM_CUDA(cudaMalloc(&e->red_partials, rp * (sizeof(double) + sizeof(float))));
-  GVM_CUDA(cudaMalloc(&e->red_counter, e->red_slots * sizeof(unsigned int)));
-  GVM_CUDA(cudaMemset(e->red_counter, 0, e->red_slots * sizeof(unsigned int)));
-  GVM_CUDA(cudaMalloc(&e->red_sum, e->red_slots * sizeof(double)));
-  GVM_CUDA(cudaMemset(e->red_sum, 0, e->red_slots * sizeof(double)));
-  GVM_CUDA(cudaMalloc(&e->red_Z, e->red_slots * sizeof(long)));
-  GVM_CUDA(cudaMemset(e->red_Z, 0, e->red_slots * sizeof(long)));
-  GVM_CUDA(cudaMalloc(&e->red_max, 3 * e->red_slots * sizeof(float)));
-  GVM_CUDA(cudaMemset(e->red_max, 0, 3 * e->red_slots * sizeof(float)));
+  e->red_slots = 0;
+  if (ensure_red_slots(e, 1024)) return 1;
   GVM_CUDA(cudaMalloc(&e->red_out, 8 * sizeof(double)));
   GVM_CUDA(cudaMemset(e->red_out, 0, 8 * sizeof(double)));
   GVM_CUDA(cudaMallocHost(&e->h_red, 8 * sizeof(double)));
@@ -103,7 +137,6 @@ int gvm_create(const gvm_config* cfg, gvm_engine** out) {
   }
   e->have_plan = true;
   cufftSetStream(e->plan, e->stream);
-  *out = e;
   return 0;
 }
 
@@ -221,14 +254,7 @@ int gvm_get_model_grid(gvm_engine* e, float* V_host) {
   return 0;
 }
 
-int gvm_add_channel(gvm_engine* e, const gvm_channel_desc* desc, int64_t Z, const double* uvw_m,
-                    const float* Vo, const float* w, int* chan_out) {
-  if (!e || !desc || Z < 0) { gvm_set_error("gvm_add_channel: bad argument"); return 1; }
-  if ((int)e->chans.size() >= e->red_slots - 2) { gvm_set_error("gvm_add_channel: too many blocks"); return 1; }
-  GVM_CUDA(cudaSetDevice(e->cfg.device));
-  GvmChannel c;
-  c.d = *desc;
-  c.Z = Z;
+static int add_channel_impl(gvm_engine* e, GvmChannel& c, int64_t Z, const double* uvw_m, const float* Vo, const float* w) {
   const size_t z = (size_t)(Z > 0 ? Z : 1);
   GVM_CUDA(cudaMalloc(&c.uvw_l, z * 3 * sizeof(double)));
   GVM_CUDA(cudaMalloc(&c.cell, z * sizeof(uint32_t)));
@@ -246,23 +272,49 @@ int gvm_add_channel(gvm_engine* e, const gvm_channel_desc* desc, int64_t Z, cons
   GVM_CUDA(cudaMalloc(&c.wz, z * sizeof(float)));
   if (Z > 0) {
     double* d_uvw = nullptr; float2* d_vo = nullptr; float* d_w = nullptr;
-    GVM_CUDA(cudaMalloc(&d_uvw, z * 3 * sizeof(double)));
-    GVM_CUDA(cudaMalloc(&d_vo, z * sizeof(float2)));
-    GVM_CUDA(cudaMalloc(&d_w, z * sizeof(float)));
-    if (gvm_fast_h2d(d_uvw, uvw_m, z * 3 * sizeof(double), e->stream) || gvm_fast_h2d(d_vo, Vo, z * sizeof(float2), e->stream) ||
-        gvm_fast_h2d(d_w, w, z * sizeof(float), e->stream)) {
-      cudaFree(d_uvw); cudaFree(d_vo); cudaFree(d_w);
-      return 1;
-    }
-    int rc = gvm_launch_prep_channel(e, c, d_uvw, d_vo, d_w);
+    int rc = cudaMalloc(&d_uvw, z * 3 * sizeof(double)) != cudaSuccess || cudaMalloc(&d_vo, z * sizeof(float2)) != cudaSuccess ||
+             cudaMalloc(&d_w, z * sizeof(float)) != cudaSuccess;
+    if (rc) gvm_set_error("gvm_add_channel: out of device memory staging %ld visibilities", (long)Z);
+    rc = rc || gvm_fast_h2d(d_uvw, uvw_m, z * 3 * sizeof(double), e->stream) || gvm_fast_h2d(d_vo, Vo, z * sizeof(float2), e->stream) ||
+         gvm_fast_h2d(d_w, w, z * sizeof(float), e->stream) || gvm_launch_prep_channel(e, c, d_uvw, d_vo, d_w);
     cudaFree(d_uvw); cudaFree(d_vo); cudaFree(d_w);
-    if (rc) return rc;
+    if (rc) return 1;
+  }
+  return 0;
+}
+
+int gvm_add_channel(gvm_engine* e, const gvm_channel_desc* desc, int64_t Z, const double* uvw_m,
+                    const float* Vo, const float* w, int* chan_out) {
+  if (!e || !desc || Z < 0) { gvm_set_error("gvm_add_channel: bad argument"); return 1; }
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  // the last two reduction slots belong to the image-sized reductions (priors.cu aux_red)
+  if (ensure_red_slots(e, (int)e->chans.size() + 3)) return 1;
+  GvmChannel c;
+  c.d = *desc;
+  c.Z = Z;
+  c.Znorm = Z;
+  if (add_channel_impl(e, c, Z, uvw_m, Vo, w)) {
+    free_channel(c);     // a failed upload leaves nothing behind
+    return 1;
   }
   const int slot = (int)e->chans.size();
   long zl = (long)Z;
   GVM_CUDA(cudaMemcpy(e->red_Z + slot, &zl, sizeof(long), cudaMemcpyHostToDevice));
+  GVM_CUDA(cudaMemset(e->red_sum + slot, 0, sizeof(double)));   // a rank-empty block contributes 0, not a stale sum
   e->chans.push_back(c);
   if (chan_out) *chan_out = slot;
+  return 0;
+}
+
+int gvm_set_block_nvis(gvm_engine* e, int chan, int64_t Z_block) {
+  if (chan < 0 || chan >= (int)e->chans.size() || Z_block < e->chans[chan].Z) {
+    gvm_set_error("gvm_set_block_nvis: bad channel %d or block size %ld", chan, (long)Z_block);
+    return 1;
+  }
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  e->chans[chan].Znorm = Z_block;
+  long zl = (long)Z_block;
+  GVM_CUDA(cudaMemcpy(e->red_Z + chan, &zl, sizeof(long), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -307,7 +359,15 @@ int gvm_get_vis(gvm_engine* e, int chan, double* uvw_lambda, int32_t* cell, floa
 }
 
 // ------------------------------------------------------------------ hot path
+static int chi2_async_impl(gvm_engine* e, float* I_dev, int normalize, double* chi2_dev);
+// A failure on ONE rank before its collective must not leave the peers blocked in theirs: the failing
+// rank aborts the communicator (peers return an error from the pending all-reduce).
 int gvm_chi2_async(gvm_engine* e, float* I_dev, int normalize, double* chi2_dev) {
+  const int rc = chi2_async_impl(e, I_dev, normalize, chi2_dev);
+  if (rc && e->world > 1) gvm_dist_abort_comm(e);
+  return rc;
+}
+static int chi2_async_impl(gvm_engine* e, float* I_dev, int normalize, double* chi2_dev) {
   GVM_CUDA(cudaSetDevice(e->cfg.device));
   if (e->chans.empty()) { gvm_set_error("gvm_chi2: no visibility blocks uploaded"); return 1; }
   bool first = true;
@@ -352,8 +412,14 @@ static __global__ void k_add_inplace(float* __restrict__ dst, const float* __res
   if (idx < n) dst[idx] += src[idx];
 }
 
+static int dchi2_impl(gvm_engine* e, const float* I_dev, int flag_opt, int normalize, float* result_dchi2_dev);
 int gvm_dchi2(gvm_engine* e, const float* I_dev, int flag_opt, int normalize,
               float* result_dchi2_dev) {
+  const int rc = dchi2_impl(e, I_dev, flag_opt, normalize, result_dchi2_dev);
+  if (rc && e->world > 1) gvm_dist_abort_comm(e);
+  return rc;
+}
+static int dchi2_impl(gvm_engine* e, const float* I_dev, int flag_opt, int normalize, float* result_dchi2_dev) {
   GVM_CUDA(cudaSetDevice(e->cfg.device));
   e->flag_opt = flag_opt;
   e->ev_used = 0;

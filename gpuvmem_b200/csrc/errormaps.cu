@@ -81,7 +81,13 @@ __global__ void __launch_bounds__(256) k_err_reduction(float* __restrict__ err, 
 
 }  // namespace
 
+static int error_maps_impl(gvm_engine* e, const float* I_dev, int dist_mode, float* errors_dev);
 extern "C" int gvm_error_maps(gvm_engine* e, const float* I_dev, int dist_mode, float* errors_dev) {
+  const int rc = error_maps_impl(e, I_dev, dist_mode, errors_dev);
+  if (rc && e->world > 1) gvm_dist_abort_comm(e);   // peers must not wait for this rank's collectives
+  return rc;
+}
+static int error_maps_impl(gvm_engine* e, const float* I_dev, int dist_mode, float* errors_dev) {
   GVM_CUDA(cudaSetDevice(e->cfg.device));
   const gvm_config& g = e->cfg;
   const long MN = g.M * g.N;
@@ -92,32 +98,43 @@ extern "C" int gvm_error_maps(gvm_engine* e, const float* I_dev, int dist_mode, 
   e->ev_used = 0;
   for (size_t s = 0; s < e->chans.size(); s++) {
     GvmChannel& c = e->chans[s];
-    if (c.Z <= 0) continue;
-    if (c.slot < 0) { gvm_set_error("gvm_error_maps: call gvm_chi2 first (Vr comes from the forward pass)"); return 1; }
-    long want = (c.Z + 256L * 16 - 1) / (256L * 16);
-    const int blocks = (int)(want < 1 ? 1 : (want > e->red_blocks ? e->red_blocks : want));
-    k_wsum_partial<<<blocks, 256, 0, e->stream>>>(c.w, c.Z, e->red_partials);
-    GVM_LAUNCH(e);
-    k_wsum_finish<<<1, 32, 0, e->stream>>>(e->red_partials, blocks, wsum);
-    GVM_LAUNCH(e);
-    // raw DFT sum d[i,j] -> e->dchi2 through the gradient machinery
-    e->err_variant = 1;
-    int rc = 0;
-    const int mode = gvm_pick_grad_mode(e, c);
-    e->last_grad_mode = mode;
-    if (mode == GVM_GRAD_GRIDFFT) {
-      rc = gvm_grad_gridfft(e, c) || gvm_grad_finish(e, c, I_dev, 1, 0, 0, nullptr);
-    } else if (mode == GVM_GRAD_SIMT || mode == GVM_GRAD_SIMT_EXACT) {
-      int ksplit = 1;
-      rc = gvm_grad_simt(e, c, false, &ksplit) || gvm_grad_finish(e, c, I_dev, ksplit, 0, 0, nullptr);
-    } else {
-      rc = gvm_grad_umma(e, c, I_dev, 0, 0, nullptr);
-    }
-    e->err_variant = 0;
-    if (rc) return 1;
-    if (dist_mode == GVM_DIST_CHUNKS) {   // every rank holds a slice of THIS block: finish the sums first
+    // CHUNKS: every rank holds a slice of the same block and takes part in its two all-reduces, so "empty" is
+    // decided from the size of the WHOLE block (identical on all ranks); a rank whose slice is empty contributes zeros
+    const bool chunks = dist_mode == GVM_DIST_CHUNKS;
+    if ((chunks ? c.Znorm : c.Z) <= 0) continue;
+    if (c.Z <= 0) {
+      GVM_CUDA(cudaMemsetAsync(e->dchi2, 0, (size_t)MN * sizeof(float), e->stream));
+      GVM_CUDA(cudaMemsetAsync(wsum, 0, sizeof(double), e->stream));
       if (gvm_dist_allreduce_f32(e, e->dchi2, (size_t)MN)) return 1;
       if (gvm_dist_allreduce_f64(e, wsum, 1)) return 1;
+    }
+    if (c.Z > 0 && c.slot < 0) { gvm_set_error("gvm_error_maps: call gvm_chi2 first (Vr comes from the forward pass)"); return 1; }
+    if (c.Z > 0) {
+      long want = (c.Z + 256L * 16 - 1) / (256L * 16);
+      const int blocks = (int)(want < 1 ? 1 : (want > e->red_blocks ? e->red_blocks : want));
+      k_wsum_partial<<<blocks, 256, 0, e->stream>>>(c.w, c.Z, e->red_partials);
+      GVM_LAUNCH(e);
+      k_wsum_finish<<<1, 32, 0, e->stream>>>(e->red_partials, blocks, wsum);
+      GVM_LAUNCH(e);
+      // raw DFT sum d[i,j] -> e->dchi2 through the gradient machinery
+      e->err_variant = 1;
+      int rc = 0;
+      const int mode = gvm_pick_grad_mode(e, c);
+      e->last_grad_mode = mode;
+      if (mode == GVM_GRAD_GRIDFFT) {
+        rc = gvm_grad_gridfft(e, c) || gvm_grad_finish(e, c, I_dev, 1, 0, 0, nullptr);
+      } else if (mode == GVM_GRAD_SIMT || mode == GVM_GRAD_SIMT_EXACT) {
+        int ksplit = 1;
+        rc = gvm_grad_simt(e, c, false, &ksplit) || gvm_grad_finish(e, c, I_dev, ksplit, 0, 0, nullptr);
+      } else {
+        rc = gvm_grad_umma(e, c, I_dev, 0, 0, nullptr);
+      }
+      e->err_variant = 0;
+      if (rc) return 1;
+      if (dist_mode == GVM_DIST_CHUNKS) {   // every rank holds a slice of THIS block: finish the sums first
+        if (gvm_dist_allreduce_f32(e, e->dchi2, (size_t)MN)) return 1;
+        if (gvm_dist_allreduce_f64(e, wsum, 1)) return 1;
+      }
     }
     ErrParams p;
     p.atten = gvm_channel_atten(e, c);

@@ -339,7 +339,7 @@ GvmFinishParams gvm_finish_params(gvm_engine* e, const GvmChannel& c, const floa
   const gvm_config& g = e->cfg;
   GvmFinishParams p;
   p.atten = gvm_channel_atten(e, const_cast<GvmChannel&>(c)); p.gcf = e->gcf; p.I = I_dev; p.result = result_dev; p.dchi2_out = e->dchi2;
-  p.N = g.N; p.M = g.M; p.Z = (long)c.Z;
+  p.N = g.N; p.M = g.M; p.Z = (long)c.Znorm;
   p.fg_scale = g.fg_scale; p.D = c.d.antenna_diameter; p.pb_factor = c.d.pb_factor;
   p.pb_cutoff = c.d.pb_cutoff; p.freq = c.d.freq; p.xobs = c.d.ref_xobs_pix; p.yobs = c.d.ref_yobs_pix;
   p.nu_0 = g.nu_0; p.threshold = g.threshold; p.DELTAX = g.DELTAX; p.DELTAY = g.DELTAY;

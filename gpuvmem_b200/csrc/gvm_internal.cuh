@@ -33,7 +33,9 @@ void gvm_set_error(const char* fmt, ...);
 
 struct GvmChannel {
   gvm_channel_desc d;
-  int64_t Z = 0;
+  int64_t Z = 0;               // samples this rank holds
+  int64_t Znorm = 0;           // samples of the WHOLE block (numVisibilitiesPerFreqPerStoke): the `normalize` divisor;
+                               // differs from Z when the block is cut into visibility chunks over the ranks
   // SoA, device
   double* uvw_l = nullptr;     // [Z][3] wavelengths after the Hermitian fold (kept for readback / exact checks)
   uint32_t* cell = nullptr;    // i1 | j1 << 16, GVM_CELL_INVALID when outside the grid
@@ -117,6 +119,7 @@ struct gvm_engine {
   long plan_pixels = 0;            // output pixels the plan computes (algorithmic flops = 4 * this * Z)
   // multi-GPU (dist_nccl.cu): one process per GPU, NCCL communicator over NVLink
   void* nccl_comm = nullptr;
+  bool dist_aborted = false;
   int rank = 0, world = 1;
   float* dist_grad = nullptr;      // [2][MN] this rank's gradient contribution before the all-reduce
   int64_t collectives = 0;
@@ -252,6 +255,10 @@ double gvm_wterm_cross_bound(const gvm_engine* e, const GvmChannel& c);
 // dist_nccl.cu: in-place sum all-reduce on the engine stream (no-op when world == 1)
 int gvm_dist_allreduce_f32(gvm_engine* e, float* buf, size_t n);
 int gvm_dist_allreduce_f64(gvm_engine* e, double* buf, size_t n);
+int gvm_dist_broadcast_f32(gvm_engine* e, float* buf, size_t n, int root);
+// a rank that fails locally before a collective tears the communicator down so that its peers error out of
+// their pending collective instead of waiting for it forever
+void gvm_dist_abort_comm(gvm_engine* e);
 void gvm_dist_release(gvm_engine* e);
 // errormaps.cu needs the mode rule of gvm_dchi2
 int gvm_pick_grad_mode(gvm_engine* e, GvmChannel& c);

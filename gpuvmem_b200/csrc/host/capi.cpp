@@ -129,13 +129,15 @@ int gvmh_create(const gvmh_problem* p, const char* args, const char* optimizer, 
   std::string item;
   while (std::getline(is, item, ',')) {
     std::istringstream it(item);
-    std::string name, a, b, c;
+    std::string name, a, b, c, nrm;
     std::getline(it, name, ':');
     std::getline(it, a, ':');
     std::getline(it, b, ':');
     std::getline(it, c, ':');
+    std::getline(it, nrm, ':');   // optional 5th field: Fi::configure's `normalize`
     Fi* fi = createObject<Fi, std::string>(name);
-    fi->configure(a.empty() ? -1 : std::stoi(a), b.empty() ? 0 : std::stoi(b), c.empty() ? 0 : std::stoi(c), false);
+    fi->configure(a.empty() ? -1 : std::stoi(a), b.empty() ? 0 : std::stoi(b), c.empty() ? 0 : std::stoi(c),
+                  !nrm.empty() && std::stoi(nrm) != 0);
     if (name == "Entropy") fi->setPrior(0.001f);  // main.cu:177
     s->of->addFi(fi);
     s->terms.push_back(fi);
@@ -182,6 +184,20 @@ int gvmh_set_lbfgs_k(gvmh_session* s, int k) { s->opt->setK(k); return 0; }
 int gvmh_write_outputs(gvmh_session* s) {
   s->sy->writeImages();
   s->sy->writeResiduals();
+  return 0;
+}
+
+int gvmh_write_residuals(gvmh_session* s, float* nongridded_chi2) {
+  s->sy->writeResiduals();
+  if (nongridded_chi2) *nongridded_chi2 = s->mfs->getNonGriddedChi2();
+  return 0;
+}
+int gvmh_get_host_model(gvmh_session* s, int chan, float* Vm, float* Vr) {
+  Field& f = s->mfs->getDatasets()[0].fields[0];
+  if (chan < 0 || chan >= (int)f.visibilities.size()) return 1;
+  const HVis& v = f.visibilities[chan][0];
+  if (Vm) std::memcpy(Vm, v.Vm.data(), v.Vm.size() * sizeof(float));
+  if (Vr) std::memcpy(Vr, v.Vr.data(), v.Vr.size() * sizeof(float));
   return 0;
 }
 
@@ -239,10 +255,14 @@ int gvmh_eval_host(gvmh_session* s, const float* I_host, int iteration, float* v
   if (!s->image_stage) s->image_stage = devAllocFloats(imageFloats());
   Fi* chi2 = s->of->getFiByName("Chi2");
   if (chi2) chi2->setFgScale(s->sy->getFgScale());
-  devUpload(s->image_stage, I_host, imageFloats());
+  // Multi-rank: the image crosses PCIe ONCE (rank 0) and reaches the other replicas over NVLink
+  // (ncclBroadcast on the engine stream); the gradient, identical on every rank after the all-reduce,
+  // goes back to the host from rank 0 only. I_host / grad_host are not touched on the other ranks.
+  if (G().rank == 0) devUpload(s->image_stage, I_host, imageFloats());
+  if (G().world > 1) GVM_CHECK(gvm_dist_broadcast(G().engine, s->image_stage, (int64_t)imageFloats(), 0));
   const float v = s->of->calcFunction(s->image_stage);
   s->of->calcGradient(s->image_stage, s->xi, iteration);
-  devDownload(grad_host, s->xi, imageFloats());
+  if (G().rank == 0) devDownload(grad_host, s->xi, imageFloats());
   if (value) *value = v;
   return 0;
 }

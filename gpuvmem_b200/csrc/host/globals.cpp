@@ -15,6 +15,8 @@ Globals& G() {
 void gvmCheck(int rc, const char* what, const char* file, int line) {
   if (rc == 0) return;
   std::fprintf(stderr, "gpuvmem_b200 error at %s:%d: %s -> %s\n", file, line, what, gvm_last_error());
+  // one rank leaving must not strand the others inside a collective
+  if (G().engine && G().world > 1) gvm_dist_abort(G().engine);
   std::exit(-1);
 }
 

@@ -4,8 +4,13 @@
 // Input is the GVMS container (gpuvmem_b200/synth.py) instead of a Measurement Set + FITS.
 // Multi-GPU: start one process per GPU with RANK / WORLD_SIZE / LOCAL_RANK in the environment
 // (e.g. torchrun --no-python, or mpirun exporting them); rank 0 publishes the NCCL id through
-// the file named by GVM_RENDEZVOUS (default /tmp/gvm_nccl_<MASTER_PORT or 29500>.id).
+// a per-launch file (GVM_RENDEZVOUS, default /tmp/gvm_nccl_<uid>_<MASTER_PORT or 29500>_<launch nonce>.id)
+// that rank 0 removes as soon as the communicator exists.
+#include <fcntl.h>
 #include <unistd.h>
+
+#include <cctype>
+#include <cerrno>
 
 #include <cstdio>
 #include <cstdlib>
@@ -26,21 +31,42 @@ int envInt(const char* name, int fallback) {
   const char* v = std::getenv(name);
   return v && *v ? std::atoi(v) : fallback;
 }
+// The NCCL id travels through a file that belongs to THIS launch: its name carries a per-launch nonce
+// (GVM_RUN_ID, else TORCHELASTIC_RUN_ID, else the launcher's pid — every rank of one launch has the same
+// parent) and the uid, it is created exclusively with mode 0600 (no symlink games in a world-writable /tmp),
+// and rank 0 removes it once the communicator exists (rendezvousDone), so a later job never reads a stale id.
+std::string rendezvousPath() {
+  if (const char* named = std::getenv("GVM_RENDEZVOUS")) return named;
+  std::string nonce;
+  if (const char* v = std::getenv("GVM_RUN_ID")) nonce = v;
+  else if (const char* t = std::getenv("TORCHELASTIC_RUN_ID")) nonce = t;
+  else nonce = "ppid" + std::to_string((long)getppid());
+  for (char& ch : nonce)
+    if (!std::isalnum((unsigned char)ch) && ch != '-' && ch != '_') ch = '_';
+  return "/tmp/gvm_nccl_" + std::to_string((long)getuid()) + "_" + std::to_string(envInt("MASTER_PORT", 29500)) + "_" + nonce + ".id";
+}
 std::string rendezvous(int rank, int world) {
   if (world <= 1) return std::string();
-  const char* named = std::getenv("GVM_RENDEZVOUS");
-  const std::string path = named ? named : "/tmp/gvm_nccl_" + std::to_string(envInt("MASTER_PORT", 29500)) + ".id";
+  const std::string path = rendezvousPath();
   std::string id(GVM_DIST_ID_BYTES, '\0');
   if (rank == 0) {
     if (gvm_dist_unique_id(&id[0], id.size()) != 0) {
       std::printf("ERROR: %s\n", gvm_last_error());
       std::exit(-1);
     }
-    const std::string tmp = path + ".tmp";
-    std::FILE* fp = std::fopen(tmp.c_str(), "wb");
-    std::fwrite(id.data(), 1, id.size(), fp);
-    std::fclose(fp);
-    std::rename(tmp.c_str(), path.c_str());
+    const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    unlink(tmp.c_str());
+    const int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+    if (fd < 0) {
+      std::printf("ERROR: cannot create the rendezvous file %s (%s)\n", tmp.c_str(), std::strerror(errno));
+      std::exit(-1);
+    }
+    const ssize_t put = write(fd, id.data(), id.size());
+    if (close(fd) != 0 || put != (ssize_t)id.size() || std::rename(tmp.c_str(), path.c_str()) != 0) {
+      std::printf("ERROR: cannot publish the NCCL id in %s (%s)\n", path.c_str(), std::strerror(errno));
+      unlink(tmp.c_str());
+      std::exit(-1);
+    }
   } else {
     for (int tries = 0; tries < 600; tries++) {
       std::FILE* fp = std::fopen(path.c_str(), "rb");
@@ -55,6 +81,10 @@ std::string rendezvous(int rank, int world) {
     std::exit(-1);
   }
   return id;
+}
+// ncclCommInitRank is collective: when it has returned on rank 0 every rank has read the id
+void rendezvousDone(int rank, int world) {
+  if (world > 1 && rank == 0) unlink(rendezvousPath().c_str());
 }
 }  // namespace
 
@@ -86,6 +116,7 @@ int main(int argc, char** argv) {
   sy->configure(argc, argv);
   cg->setObjectiveFunction(of);
   sy->setDevice();
+  rendezvousDone(rank, world);
 
   Fi* chi2 = createObject<Fi, std::string>("Chi2");
   Fi* e = createObject<Fi, std::string>("Entropy");

@@ -438,6 +438,8 @@ void MFS::shardAndUpload() {
           int slot = -1;
           GVM_CHECK(gvm_add_channel(g.engine, &cd, (int64_t)(hi - lo), v.uvw.data() + 3 * lo, v.Vo.data() + 2 * lo,
                                     v.weight.data() + lo, &slot));
+          // -normalize divides by the size of the whole block, not of this rank's slice (src/functions.cu:4439-4441)
+          if (hi - lo != v.size()) GVM_CHECK(gvm_set_block_nvis(g.engine, slot, (int64_t)v.size()));
           f.engine_slot[i][s] = slot;
         }
     }
@@ -559,10 +561,26 @@ void MFS::setDevice() {
   // noise image -> fg_scale, noise_cut (src/mfs.cu:850-916)
   if (gvm_num_channels(g.engine) == 0) {
     std::printf("ERROR: rank %d holds no visibility block\n", g.rank);
+    gvm_dist_abort(g.engine);   // the peers must not wait in their first collective for a rank that is gone
     std::exit(-1);
   }
   float noise_min = 0.0f;
-  GVM_CHECK(gvm_build_noise_image(g.engine, g.noise_jypix, &noise_min));
+  // one attenuation^2 per (dataset, field), whatever was sharded to this rank (src/mfs.cu:870-888)
+  std::vector<gvm_channel_desc> beam_fields;
+  for (MSDataset& ds : datasets)
+    for (Field& f : ds.fields) {
+      gvm_channel_desc cd;
+      std::memset(&cd, 0, sizeof(cd));
+      cd.freq = g.nu_0;
+      cd.antenna_diameter = ds.antennas[0].antenna_diameter;
+      cd.pb_factor = ds.antennas[0].pb_factor;
+      cd.pb_cutoff = ds.antennas[0].pb_cutoff;
+      cd.primary_beam = ds.antennas[0].primary_beam;
+      cd.ref_xobs_pix = f.ref_xobs_pix; cd.ref_yobs_pix = f.ref_yobs_pix;
+      cd.phs_xobs_pix = f.phs_xobs_pix; cd.phs_yobs_pix = f.phs_yobs_pix;
+      beam_fields.push_back(cd);
+    }
+  GVM_CHECK(gvm_build_noise_image_fields(g.engine, g.noise_jypix, (int)beam_fields.size(), beam_fields.data(), &noise_min));
   fg_scale = noise_min;
   g.noise_cut = g.noise_cut * noise_min;
   GVM_CHECK(gvm_set_scalars(g.engine, fg_scale, g.noise_cut, g.threshold));
@@ -698,28 +716,32 @@ void SecondDerivateError::calculateErrorImage(Image* I, Visibilities*) {
   GVM_CHECK(gvm_error_maps(g.engine, I->getImage(), g.dist_kind, I->getErrorImage()));
 }
 
-// Residual / model write-back (src/mfs.cu:1115-1155): weights restored, and in gridded mode the
-// model is re-sampled at the ORIGINAL (u,v) with the bilinear degridder (what
-// getOriginalVisibilitiesBack + chi2 do, src/functions.cu:1844-2010).
+// Residual / model write-back (src/mfs.cu:1115-1155). Ungridded runs: the scheme's backup weights come
+// back (WeightingScheme::restoreWeights). Gridded runs: the ORIGINAL samples come back as
+// getOriginalVisibilitiesBack leaves them (src/functions.cu:1844-2010) — uvw and Vo of the input, and the
+// weights do_gridding backed up, i.e. the weights AFTER the weighting scheme (:1398-1409 overwrite the
+// scheme's own backup) — and one more Chi2::calcFi re-samples the model at the original (u,v) with the
+// bilinear degridder; the Chi2 term still carries the CKernel, so apply_GCF stays in that evaluation
+// (src/mfs.cu:989-992, src/functions.cu:4358). Then modelToHost (src/MSFITSIO.cu:1114-1138): Vm comes back and
+// is CONJUGATED where the host u > 0 (the device samples were folded by hermitianSymmetry, the host ones were
+// not), and the residual that goes to the file is host Vo - that Vm (writeMS, :1217).
 void MFS::writeResiduals() {
   Globals& g = G();
   if (!g.quiet) std::printf("Transferring residuals to host memory\n");
   Fi* chi2 = optimizer->getObjectiveFunction()->getFiByName("Chi2");
+  nongridded_chi2 = 0.0f;
   if (gridding && !ungridded.empty()) {
     datasets = std::move(ungridded);   // the originals come back (no copy); a second call finds them in place
     ungridded.clear();
-    scheme->restoreWeights(datasets);
     GVM_CHECK(gvm_clear_channels(g.engine));
-    GVM_CHECK(gvm_set_gcf(g.engine, nullptr));
     shardAndUpload();
     if (chi2) {
-      const float res = chi2->calcFi(image->getImage());
-      if (!g.quiet) std::printf("Non-gridded chi2 after de-gridding using bilinear interpolation %f\n", res);
+      nongridded_chi2 = chi2->calcFi(image->getImage());
+      if (!g.quiet) std::printf("Non-gridded chi2 after de-gridding using bilinear interpolation %f\n", nongridded_chi2);
     }
-  } else {
+  } else if (!gridding) {
     scheme->restoreWeights(datasets);
   }
-  // modelToHost (src/MSFITSIO.cu:1114-1138): Vm, Vr of the blocks this rank holds
   for (MSDataset& ds : datasets)
     for (Field& f : ds.fields)
       for (size_t i = 0; i < f.visibilities.size(); i++)
@@ -732,7 +754,12 @@ void MFS::writeResiduals() {
           if (g.world > 1 && Z != v.size()) lo = v.size() * (size_t)g.rank / g.world;
           v.Vm.assign(2 * v.size(), 0.0f);
           v.Vr.assign(2 * v.size(), 0.0f);
-          GVM_CHECK(gvm_get_vis(g.engine, slot, nullptr, nullptr, nullptr, v.Vm.data() + 2 * lo, v.Vr.data() + 2 * lo, nullptr));
+          GVM_CHECK(gvm_get_vis(g.engine, slot, nullptr, nullptr, nullptr, v.Vm.data() + 2 * lo, nullptr, nullptr));
+          for (size_t k = lo; k < lo + Z; k++) {
+            if (v.uvw[3 * k] > 0.0) v.Vm[2 * k + 1] = -v.Vm[2 * k + 1];
+            v.Vr[2 * k] = v.Vo[2 * k] - v.Vm[2 * k];
+            v.Vr[2 * k + 1] = v.Vo[2 * k + 1] - v.Vm[2 * k + 1];
+          }
         }
   if (msoutput != "NULL") {
     const std::vector<std::string> outs = countAndSeparateStrings(msoutput, ",");

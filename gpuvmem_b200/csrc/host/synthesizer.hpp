@@ -114,6 +114,7 @@ class MFS : public Synthesizer {
   // one process per GPU: this process's rank / world size and the NCCL id from rank 0
   void setDistributed(int rank, int world, const std::string& nccl_id);
   std::vector<MSDataset>& getDatasets() { return datasets; }
+  float getNonGriddedChi2() const { return nongridded_chi2; }
   // scalars derived in configure/setDevice (parity tests compare them with the reference's)
   struct Derived {
     double beam_bmaj_deg = 0, beam_bmin_deg = 0, beam_bpa_deg = 0, deltau = 0, deltav = 0;
@@ -130,6 +131,7 @@ class MFS : public Synthesizer {
   void doGridding();
   Vars variables;
   std::vector<MSDataset> datasets;
+  float nongridded_chi2 = 0.0f;       // the "Non-gridded chi2" of the last writeResiduals (gridded runs)
   std::vector<MSDataset> ungridded;   // originals kept when -g replaces them (residual write-back)
   headerValues header;
   bool adopted = false;

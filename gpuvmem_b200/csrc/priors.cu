@@ -484,15 +484,8 @@ int gvm_add_to_dphi(gvm_engine* e, float* dphi_dev, const float* dgi_dev, int in
 }
 
 int gvm_build_noise_image(gvm_engine* e, float noise_jypix, float* fg_scale_out) {
-  GVM_CUDA(cudaSetDevice(e->cfg.device));
-  const gvm_config& g = e->cfg;
-  const long MN = g.M * g.N;
-  const int blocks = (int)((MN + kT - 1) / kT);
   if (e->chans.empty()) { gvm_set_error("gvm_build_noise_image: add the visibility blocks first"); return 1; }
-  float* weight = nullptr;
-  GVM_CUDA(cudaMalloc(&weight, MN * sizeof(float)));
-  GVM_CUDA(cudaMemsetAsync(weight, 0, MN * sizeof(float), e->stream));
-  // one attenuation pattern per distinct field (pointing centre + beam model), at nu_0
+  // no field list given: one attenuation pattern per distinct (pointing centre, beam model) of the uploaded blocks
   std::vector<gvm_channel_desc> fields;
   for (auto& c : e->chans) {
     bool seen = false;
@@ -502,6 +495,20 @@ int gvm_build_noise_image(gvm_engine* e, float noise_jypix, float* fg_scale_out)
           f.pb_cutoff == c.d.pb_cutoff && f.primary_beam == c.d.primary_beam) seen = true;
     if (!seen) fields.push_back(c.d);
   }
+  return gvm_build_noise_image_fields(e, noise_jypix, (int)fields.size(), fields.data(), fg_scale_out);
+}
+
+int gvm_build_noise_image_fields(gvm_engine* e, float noise_jypix, int nfields, const gvm_channel_desc* fields_in,
+                                 float* fg_scale_out) {
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  const gvm_config& g = e->cfg;
+  const long MN = g.M * g.N;
+  const int blocks = (int)((MN + kT - 1) / kT);
+  if (nfields < 1 || !fields_in) { gvm_set_error("gvm_build_noise_image_fields: no fields"); return 1; }
+  const std::vector<gvm_channel_desc> fields(fields_in, fields_in + nfields);
+  float* weight = nullptr;
+  GVM_CUDA(cudaMalloc(&weight, MN * sizeof(float)));
+  GVM_CUDA(cudaMemsetAsync(weight, 0, MN * sizeof(float), e->stream));
   for (auto& f : fields) {
     k_weight_accum<<<blocks, kT, 0, e->stream>>>(weight, g.N, g.M, f.antenna_diameter, f.pb_factor,
                                                  f.pb_cutoff, g.nu_0, f.ref_xobs_pix, f.ref_yobs_pix,

@@ -45,6 +45,8 @@ SIGNATURES = {
     "gvmh_clear_run": (C.c_int, [_P]),
     "gvmh_set_lbfgs_k": (C.c_int, [_P, C.c_int]),
     "gvmh_write_outputs": (C.c_int, [_P]),
+    "gvmh_write_residuals": (C.c_int, [_P, _P]),
+    "gvmh_get_host_model": (C.c_int, [_P, C.c_int, _P, _P]),
     "gvmh_fits_read": (C.c_int, [C.c_char_p, _P, _P, C.c_int64]),
     "gvmh_fits_write": (C.c_int, [C.c_char_p, _P, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p,
                                   C.c_float, C.c_double, C.c_double]),
@@ -245,6 +247,20 @@ class Session:
         w = np.empty(n, np.float32)
         self.h.gvmh_get_host_vis(self.s, chan, uvw.ctypes.data, Vo.ctypes.data, w.ctypes.data)
         return uvw, Vo, w
+
+    def write_residuals(self):
+        """MFS::writeResiduals; returns (non-gridded 0.5*chi2 or 0, [per channel dict(uvw, Vo, w, Vm, Vr)])."""
+        v = C.c_float()
+        self.h.gvmh_write_residuals(self.s, C.byref(v))
+        out = []
+        c = 0
+        while self.h.gvmh_nvis(self.s, c) >= 0:
+            uvw, Vo, w = self.host_vis(c)
+            Vm = np.empty_like(Vo); Vr = np.empty_like(Vo)
+            self.h.gvmh_get_host_model(self.s, c, Vm.ctypes.data, Vr.ctypes.data)
+            out.append(dict(uvw=uvw, Vo=Vo, w=w, Vm=Vm, Vr=Vr))
+            c += 1
+        return v.value, out
 
     def exit_reason(self):
         return self.h.gvmh_exit_reason(self.s).decode()

@@ -49,6 +49,8 @@ SIGNATURES = {
     "gvm_set_flag_opt": (C.c_int, [_P, C.c_int]),
     "gvm_set_noise_image": (C.c_int, [_P, _P, C.c_int]),
     "gvm_build_noise_image": (C.c_int, [_P, C.c_float, C.POINTER(C.c_float)]),
+    "gvm_build_noise_image_fields": (C.c_int, [_P, C.c_float, C.c_int, _P, C.POINTER(C.c_float)]),
+    "gvm_set_block_nvis": (C.c_int, [_P, C.c_int, C.c_int64]),
     "gvm_get_noise_image": (C.c_int, [_P, _P]),
     "gvm_set_gcf": (C.c_int, [_P, _P]),
     "gvm_set_degrid_kernel": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -91,6 +93,8 @@ SIGNATURES = {
     "gvm_dist_world": (C.c_int, [_P]),
     "gvm_dist_allreduce": (C.c_int, [_P, _P, C.c_int64]),
     "gvm_dist_collectives": (C.c_int64, [_P]),
+    "gvm_dist_abort": (C.c_int, [_P]),
+    "gvm_dist_broadcast": (C.c_int, [_P, _P, C.c_int64, C.c_int]),
     "gvm_weights": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_int64, C.c_int64, C.c_double, C.c_double,
                               C.c_int, _P, _P, _P, _P, C.POINTER(gvm_taper)]),
     "gvm_grid_block": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_float,

@@ -95,6 +95,13 @@ int gvm_set_noise_image(gvm_engine* e, const float* noise, int src_is_device);
  * src/mfs.cu:850-916) from the channels already added; returns min(noise) =
  * fg_scale. Does NOT rescale noise_cut (the caller does, as src/mfs.cu:916). */
 int gvm_build_noise_image(gvm_engine* e, float noise_jypix, float* fg_scale_out);
+/* Same with the fields named explicitly: the reference adds attenuation^2 ONCE PER (dataset, field), in
+ * dataset-then-field order and without de-duplication (src/mfs.cu:870-888) — and the list must not depend on
+ * which blocks were sharded to this rank, or the replicas of a multi-rank job would mask different pixels.
+ * Only the beam / pointing members of each descriptor are read (freq is ignored: the pattern is taken at nu_0).
+ * gvm_build_noise_image derives the list from the uploaded blocks (one entry per distinct pointing + beam). */
+int gvm_build_noise_image_fields(gvm_engine* e, float noise_jypix, int nfields,
+                                 const gvm_channel_desc* fields, float* fg_scale_out);
 int gvm_get_noise_image(gvm_engine* e, float* noise_host);
 /* Gridding-correction image (CKernel::getGCFGPU, include/classes/ckernel.cuh:57);
  * NULL disables it (ip->getCKernel() == NULL, src/functions.cu:4358). */
@@ -137,6 +144,10 @@ int gvm_get_model_grid(gvm_engine* e, float* V_host);
 int gvm_add_channel(gvm_engine* e, const gvm_channel_desc* desc, int64_t Z,
                     const double* uvw_m, const float* Vo, const float* w,
                     int* chan_out);
+/* When `chan` holds only a slice of a (field, channel, stokes) block (visibility-chunk sharding over ranks),
+ * the size of the WHOLE block: chi2() and DChi2 normalise by numVisibilitiesPerFreqPerStoke of the block
+ * (src/functions.cu:4439-4441, :3785), not by the slice. Default: the uploaded Z. */
+int gvm_set_block_nvis(gvm_engine* e, int chan, int64_t Z_block);
 /* Drop every uploaded block (MFS::writeResiduals re-uploads the ungridded samples after a
  * gridded run, src/mfs.cu:1118-1139). */
 int gvm_clear_channels(gvm_engine* e);
@@ -283,7 +294,14 @@ int gvm_dist_init(gvm_engine* e, int rank, int world, const char* id, size_t byt
 int gvm_dist_rank(gvm_engine* e);
 int gvm_dist_world(gvm_engine* e);
 int gvm_dist_allreduce(gvm_engine* e, float* buf_dev, int64_t n);
+/* Broadcast n floats from `root` on the engine stream (the image replica of a multi-rank job: one rank
+ * uploads it, the others receive it over NVLink instead of each pulling it over PCIe). */
+int gvm_dist_broadcast(gvm_engine* e, float* buf_dev, int64_t n, int root);
 int64_t gvm_dist_collectives(gvm_engine* e);
+/* A rank that must bail out (a local failure) calls this first: the communicator is aborted, so the peers'
+ * pending collectives return an error instead of waiting forever. The engine does it itself when gvm_chi2,
+ * gvm_dchi2 or gvm_error_maps fail on a multi-rank engine. */
+int gvm_dist_abort(gvm_engine* e);
 
 /* ------------------------------------------------- weights and gridding ---
  * WeightingScheme::apply (src/{natural,uniform,briggs,radial}weightingscheme.cu)

@@ -51,7 +51,7 @@ typedef struct gvmh_problem {
  *             "-z 0.001 -Z 0.01,0.0,1e-4 -t 50 -R 0.0 -g 0 -v"
  *   optimizer "CG-FRPRMN" | "CG-LBFGS"; scheme "Natural"|"Uniform"|"Briggs"|"Radial";
  *   ckernel   "PillBox2D"|"Gaussian2D"|"Sinc2D"|"GaussianSinc2D"|"PSWF" with size ck_m x ck_n
- *   fi_spec   comma list of name:penalizatorIndex:imageIndex:imageToAdd, NULL = main.cu's
+ *   fi_spec   comma list of name:penalizatorIndex:imageIndex:imageToAdd[:normalize], NULL = main.cu's
  *             "Chi2:-1:0:0,Entropy:0:0:0,L1-Norm:1:0:0,TotalSquaredVariation:2:0:0,Laplacian:3:0:0"
  *   rank/world/nccl_id  one process per GPU; nccl_id from gvm_dist_unique_id on rank 0 */
 int gvmh_create(const gvmh_problem* p, const char* args, const char* optimizer, const char* scheme,
@@ -68,6 +68,13 @@ int gvmh_run(gvmh_session* s, float* image_out, double* optimize_seconds);
 int gvmh_clear_run(gvmh_session* s);
 int gvmh_set_lbfgs_k(gvmh_session* s, int k);
 int gvmh_write_outputs(gvmh_session* s);   /* writeImages + writeResiduals */
+/* MFS::writeResiduals alone (src/mfs.cu:1115-1155): weights restored / original samples brought back
+ * (getOriginalVisibilitiesBack, src/functions.cu:1844-2010) and re-evaluated, then modelToHost
+ * (src/MSFITSIO.cu:1114-1138). nongridded_chi2 (optional): the "Non-gridded chi2" of a gridded run, else 0.
+ * Afterwards gvmh_nvis / gvmh_get_host_vis describe the samples that go to the output file and
+ * gvmh_get_host_model returns their model Vm [Z][2] (conjugated back where u > 0) and residual Vo - Vm. */
+int gvmh_write_residuals(gvmh_session* s, float* nongridded_chi2);
+int gvmh_get_host_model(gvmh_session* s, int chan, float* Vm, float* Vr);
 /* Error "SecondDerivateError" (src/secondderivateerror.cu:6-10 -> calculateErrors,
  * src/functions.cu:4966-5040) on the session's image and the residuals of the last objective
  * evaluation; errors_host [2][M][N]: sigma(I_nu0), sigma(alpha). */
@@ -86,7 +93,9 @@ int gvmh_calc_function(gvmh_session* s, float* value, float* fi_values, int nfi)
 int gvmh_calc_gradient(gvmh_session* s, int iteration, float* grad_host /* [2][M][N] or NULL */);
 /* One objective + gradient evaluation, device resident (bench `value`) ... */
 int gvmh_eval_device(gvmh_session* s, int iteration, float* value);
-/* ... and end to end: pinned/pageable host image in, gradient + value out (bench `e2e`). */
+/* ... and end to end: pinned/pageable host image in, gradient + value out (bench `e2e`). With several ranks
+ * the image is uploaded by rank 0 and broadcast over NVLink, and only rank 0 receives the gradient
+ * (I_host / grad_host may be NULL elsewhere); the value is returned on every rank. */
 int gvmh_eval_host(gvmh_session* s, const float* I_host, int iteration, float* value, float* grad_host);
 
 gvm_engine* gvmh_engine(gvmh_session* s);

@@ -30,6 +30,9 @@
 #include "sinc2D.cuh"
 #include "pswf_12D.cuh"
 #include "imageProcessor.cuh"
+#include "totalvariation.cuh"
+#include "gl1norm.cuh"
+#include "gentropy.cuh"
 
 int num_gpus;  // defined in the reference's main.cu, which is not compiled here
 int gvref_tolerate_cuda_errors = 0;  // read by oracle/ref_shim/helper_cuda.h
@@ -172,8 +175,8 @@ __host__ void readMS(const char*, std::string, std::vector<MSAntenna>& antennas,
 __host__ void MScopy(const char*, const char*) {}
 __host__ void writeMS(const char*, const char*, std::vector<Field>, MSData,
                       float, bool, bool, bool) {}
-/* Semantics of src/MSFITSIO.cu:1114-1138: bring model visibilities and weights
- * back to the host vectors. */
+/* Semantics of src/MSFITSIO.cu:1114-1138: the model visibilities come back to the host vectors and are
+ * conjugated where the HOST u is positive (the device copy was folded by hermitianSymmetry). */
 __host__ void modelToHost(std::vector<Field>& fields, MSData data, int ngpus,
                           int first) {
   for (int f = 0; f < data.nfields; f++)
@@ -182,12 +185,11 @@ __host__ void modelToHost(std::vector<Field>& fields, MSData data, int ngpus,
       for (int s = 0; s < data.nstokes; s++) {
         long n = fields[f].numVisibilitiesPerFreqPerStoke[i][s];
         if (n <= 0) continue;
-        cudaMemcpy(fields[f].visibilities[i][s].Vm.data(),
-                   fields[f].device_visibilities[i][s].Vm,
+        HVis& h = fields[f].visibilities[i][s];
+        cudaMemcpy(h.Vm.data(), fields[f].device_visibilities[i][s].Vm,
                    sizeof(cufftComplex) * n, cudaMemcpyDeviceToHost);
-        cudaMemcpy(fields[f].visibilities[i][s].weight.data(),
-                   fields[f].device_visibilities[i][s].weight,
-                   sizeof(float) * n, cudaMemcpyDeviceToHost);
+        for (long j = 0; j < n; j++)
+          if (h.uvw[j].x > 0) h.Vm[j] = cuConjf(h.Vm[j]);
       }
     }
 }
@@ -606,6 +608,72 @@ int gvref_degridding(long Z, const double* uvw_lambda, const float* Vg, const fl
   cudaMemcpy(Vm_out, d_vm, sizeof(cufftComplex) * Z, cudaMemcpyDeviceToHost);
   cudaFree(d_uvw); cudaFree(d_vm); cudaFree(d_vg); cudaFree(d_k);
   return (int)err;
+}
+
+/* One Fi of the reference (factory name: "Entropy", "L1-Norm", "TotalVariation", "TotalSquaredVariation",
+ * "Laplacian", "Quadratic", "GEntropy", "GL1Norm") evaluated ON ITS OWN on a caller-supplied image
+ * [image_count][M][N]: Fi::configure(-1, image_index, image_index, false) (src/main.cu:185-197 pattern),
+ * penalization factor = lambda, then calcFi -> get_fivalue() and restartDGi + calcGi + addToDphi into a
+ * zeroed dphi [image_count][M][N] (what ObjectiveFunction::calcGradient does per term,
+ * include/classes/objectivefunction.cuh). prior_host: M*N floats for GEntropy / GL1Norm, else NULL.
+ * Needs gvref_init first (noise image, M, N, image_count). */
+int gvref_prior_eval(const char* name, const float* I_host, const float* prior_host, float lambda,
+                     float prior_value, float eta_v, float eps_a, float eps_b, int image_index, int iteration,
+                     float* value_out, float* dphi_out) {
+  Fi* f = createObject<Fi, std::string>(name);
+  if (!f) return -1;
+  f->configure(-1, image_index, image_index, false);
+  f->setPenalizationFactor(lambda);
+  f->setIteration(iteration);
+  std::string s(name);
+  float* d_prior = nullptr;
+  if (prior_host) {
+    cudaMalloc(&d_prior, sizeof(float) * M * N);
+    cudaMemcpy(d_prior, prior_host, sizeof(float) * M * N, cudaMemcpyHostToDevice);
+    f->setPrior(d_prior);   /* owned (and freed) by the Fi from here on */
+  }
+  if (s == "Entropy") { f->setPrior(prior_value); f->setEta(eta_v); }
+  if (s == "GEntropy") f->setEta(eta_v);
+  if (s == "TotalVariation") static_cast<TVariation*>(f)->setEpsilon(eps_a);
+  if (s == "GL1Norm") static_cast<GL1Norm*>(f)->setEpsilons(eps_a, eps_b);
+  float *d_I = nullptr, *d_phi = nullptr;
+  const size_t bytes = sizeof(float) * M * N * image_count;
+  cudaMalloc(&d_I, bytes);
+  cudaMalloc(&d_phi, bytes);
+  cudaMemcpy(d_I, I_host, bytes, cudaMemcpyHostToDevice);
+  cudaMemset(d_phi, 0, bytes);
+  f->calcFi(d_I);
+  if (value_out) *value_out = f->get_fivalue();
+  f->restartDGi();
+  f->calcGi(d_I, d_phi);
+  f->addToDphi(d_phi);
+  cudaError_t err = cudaDeviceSynchronize();
+  if (dphi_out) cudaMemcpy(dphi_out, d_phi, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_I);
+  cudaFree(d_phi);
+  return (int)err;
+}
+
+/* MFS::writeResiduals (src/mfs.cu:1115-1155): weights restored (or, in gridded mode, the original samples
+ * brought back by getOriginalVisibilitiesBack, src/functions.cu:1844-2010, and the model re-sampled at the
+ * original (u,v) by one more chi2()), then modelToHost. Returns through *nongridded_chi2 what that last
+ * Chi2::calcFi left in get_fivalue() (the "Non-gridded chi2" the reference prints). Fetch the result with
+ * gvref_nvis + gvref_get_host_model. */
+int gvref_write_residuals(float* nongridded_chi2) {
+  g_sy->writeResiduals();
+  if (nongridded_chi2) *nongridded_chi2 = g_fis[0]->get_fivalue();
+  return (int)cudaDeviceSynchronize();
+}
+/* Host arrays after modelToHost: Vm [Z][2], weight [Z], uvw in metres [Z][3], Vo [Z][2]. */
+int gvref_get_host_model(int chan, double* uvw_m, float* Vo, float* Vm, float* w) {
+  HVis& h = datasets[0].fields[0].visibilities[chan][0];
+  for (size_t k = 0; k < h.Vm.size(); k++) {
+    if (uvw_m) { uvw_m[3 * k] = h.uvw[k].x; uvw_m[3 * k + 1] = h.uvw[k].y; uvw_m[3 * k + 2] = h.uvw[k].z; }
+    if (Vo) { Vo[2 * k] = h.Vo[k].x; Vo[2 * k + 1] = h.Vo[k].y; }
+    if (Vm) { Vm[2 * k] = h.Vm[k].x; Vm[2 * k + 1] = h.Vm[k].y; }
+    if (w) w[k] = h.weight[k];
+  }
+  return 0;
 }
 
 int gvref_set_lbfgs_k(int k) { g_opt->setK(k); return 0; }

@@ -248,6 +248,12 @@ class GvRef:
         if hasattr(L, "gvref_error_image"):
             L.gvref_error_image.argtypes = [f32p]
         L.gvref_set_verbose.argtypes = [C.c_int]
+        if hasattr(L, "gvref_prior_eval"):
+            L.gvref_prior_eval.argtypes = [C.c_char_p, f32p, _V] + [C.c_float] * 5 + [C.c_int, C.c_int,
+                                                                                     C.POINTER(C.c_float), f32p]
+        if hasattr(L, "gvref_write_residuals"):
+            L.gvref_write_residuals.argtypes = [C.POINTER(C.c_float)]
+            L.gvref_get_host_model.argtypes = [C.c_int, _V, _V, _V, _V]
         self.problem = None
 
     def set_problem(self, p):
@@ -368,6 +374,33 @@ class GvRef:
         out = np.empty(2 * p.M * p.N, np.float32)
         self.lib.gvref_error_image(out)
         return out.reshape(2, p.M, p.N)
+
+    def prior_eval(self, name, I, lam, image_index=0, iteration=1, prior_image=None, prior_value=0.001, eta=-1.0,
+                   eps_a=1e-12, eps_b=1e-12):
+        """One Fi of the reference on its own: (get_fivalue(), dphi [2][M][N] after restartDGi + calcGi + addToDphi)."""
+        p = self.problem
+        val = C.c_float()
+        dphi = np.zeros(2 * p.M * p.N, np.float32)
+        pr = None if prior_image is None else np.ascontiguousarray(prior_image, np.float32)
+        rc = self.lib.gvref_prior_eval(name.encode(), np.ascontiguousarray(I.reshape(-1), np.float32),
+                                       None if pr is None else pr.ctypes.data, lam, prior_value, eta, eps_a, eps_b,
+                                       image_index, iteration, C.byref(val), dphi)
+        assert rc == 0, rc
+        return val.value, dphi.reshape(2, p.M, p.N)
+
+    def write_residuals(self):
+        """MFS::writeResiduals; returns (non-gridded 0.5*chi2 of the last Chi2::calcFi, [per channel dict])."""
+        v = C.c_float()
+        rc = self.lib.gvref_write_residuals(C.byref(v))
+        assert rc == 0, rc
+        out = []
+        for c in range(self.problem.nchan):
+            Z = self.lib.gvref_nvis(c)
+            uvw = np.empty((Z, 3)); Vo = np.empty((Z, 2), np.float32); Vm = np.empty((Z, 2), np.float32)
+            w = np.empty(Z, np.float32)
+            self.lib.gvref_get_host_model(c, uvw.ctypes.data, Vo.ctypes.data, Vm.ctypes.data, w.ctypes.data)
+            out.append(dict(uvw=uvw, Vo=Vo, Vm=Vm, w=w))
+        return v.value, out
 
     def time_evals(self, n, iteration=0, flag=0):
         return self.lib.gvref_time_evals(n, iteration, flag)

@@ -19,6 +19,7 @@ def main():
     from gpuvmem_b200 import dist as gdist
     from gpuvmem_b200 import host, synth
     nchan, out = int(sys.argv[1]), sys.argv[2]
+    normalize = len(sys.argv) > 3 and sys.argv[3] == "normalize"
     rank, world, local = gdist.init_from_env(0)
     torch.cuda.set_device(local)
     nccl_id = None
@@ -29,8 +30,10 @@ def main():
     p = synth.make_problem(N=128, nvis=15000, nchan=nchan, freq0=1.0e11, bandwidth=4e9 if nchan > 1 else 0.0,
                            seed=41, grid_fill=0.9)
     host.set_quiet(True)
+    # normalize: Chi2 configured with normalize = true (chi2 and its gradient divided by the block's visibility count)
+    fi_spec = "Chi2:-1:0:0:1,Entropy:0:0:0,L1-Norm:1:0:0,TotalSquaredVariation:2:0:0" if normalize else None
     s = host.Session(p, args=f"-z 0.001,0.1 -Z 0.01,0.005,0.002 -t 4 -G {local}", optimizer="CG-FRPRMN",
-                     rank=rank, world=world, nccl_id=nccl_id)
+                     fi_spec=fi_spec, rank=rank, world=world, nccl_id=nccl_id)
     start = s.get_image()
     s.set_image(probe_image(p.N, np.float32(0.001), 0.1))
     s.set_iteration(1)

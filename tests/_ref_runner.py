@@ -57,6 +57,12 @@ def main():
     res["final_image"], res["iterations"], res["run_ms"] = img, iters, ms
     v, fi = ref.calc_function(iteration=max(iters, 1))
     res["final_value"], res["final_fi"] = v, fi
+    # MFS::writeResiduals (src/mfs.cu:1115-1155) on the final image: what would go to the output Measurement Set
+    if hasattr(ref.lib, "gvref_write_residuals"):
+        wb_chi2, blocks = ref.write_residuals()
+        res["wb_chi2"] = np.float32(wb_chi2)
+        for c, b in enumerate(blocks):
+            res[f"wb_uvw{c}"], res[f"wb_Vo{c}"], res[f"wb_Vm{c}"], res[f"wb_w{c}"] = b["uvw"], b["Vo"], b["Vm"], b["w"]
     np.savez(out, **res)
     print("reference scenario", name, "iterations", iters, "value", v, "ms", ms)
 

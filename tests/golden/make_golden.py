@@ -5,6 +5,7 @@ Run on the GPU box (the reference's objective/gradient only exists as CUDA kerne
     gpurun -- 'python tests/golden/make_golden.py'      # writes gpurun_out/golden/ref_small.npz
     cp gpurun_out/golden/ref_small.npz tests/golden/
     gpurun -- 'python tests/golden/make_golden.py ext'  # ref_small_ext.npz: error maps + degriddingGPU
+    gpurun -- 'python tests/golden/make_golden.py priors'  # ref_small_priors.npz: every Fi kind on its own
 
 The inputs are NOT stored: tests rebuild them from the same seed with gpuvmem_b200.synth.
 tests/test_oracle_golden.py (CPU, no GPU needed) checks the C oracle against these vectors."""
@@ -45,6 +46,41 @@ def golden_grid(N, du, dv):
     for a, wdt, x, y in comps:
         g += a * np.exp(-(u * u + v * v) / (2 * (wdt * umax) ** 2)) * np.exp(-2j * np.pi * (u * x + v * y) / abs(du) / N * 8)
     return g.astype(np.complex64)
+
+
+PRIOR_GOLD = [("Entropy", 0), ("L1-Norm", 0), ("TotalVariation", 0), ("TotalSquaredVariation", 0), ("Laplacian", 0),
+              ("Quadratic", 0), ("GEntropy", 0), ("GL1Norm", 0), ("TotalVariation", 1), ("Quadratic", 1)]
+PRIOR_LAMBDA, PRIOR_EPS_B = 0.37, 1e-3
+
+
+def prior_inputs(kind, index, N):
+    """(image [2][N][N], prior image or None, epsilon_a) of one PRIOR_GOLD case."""
+    I = golden_image(N, np.float32(0.001))
+    if index == 1:
+        I[1] = np.abs(I[1]) + np.float32(0.01)
+    prior = (np.abs(I[index]) * 0.5 + 1e-4).astype(np.float32) if kind in ("GEntropy", "GL1Norm") else None
+    return I, prior, (1e-12 if kind in ("L1-Norm", "GL1Norm") else 1e-6)
+
+
+def main_priors():
+    """Third fixture (ref_small_priors.npz): value and gradient of EVERY Fi kind the reference registers, each
+    evaluated on its own by the reference build (gvref_prior_eval) — TV, Quadratic, GEntropy, GL1Norm are not
+    wired by main.cu, so ref_small.npz does not cover them."""
+    p = synth.make_problem(**PROBLEM)
+    ref = GvRef()
+    ref.set_problem(p)
+    ref.init(ARGS)
+    out = {"noise": ref.noise_image(), "noise_cut": np.float64(ref.scalars()["noise_cut"])}
+    for kind, index in PRIOR_GOLD:
+        I, prior, eps_a = prior_inputs(kind, index, p.N)
+        v, dphi = ref.prior_eval(kind, I, PRIOR_LAMBDA, image_index=index, iteration=1, prior_image=prior,
+                                 prior_value=0.001, eta=-1.0, eps_a=eps_a, eps_b=PRIOR_EPS_B)
+        out[f"value_{kind}_{index}"] = np.float32(v)
+        out[f"dphi_{kind}_{index}"] = dphi
+    d = os.path.join(ROOT, "gpurun_out", "golden")
+    os.makedirs(d, exist_ok=True)
+    np.savez_compressed(os.path.join(d, "ref_small_priors.npz"), **out)
+    print("wrote", os.path.join(d, "ref_small_priors.npz"), sorted(out))
 
 
 def main_ext():
@@ -101,4 +137,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main_ext() if len(sys.argv) > 1 and sys.argv[1] == "ext" else main()
+    {"ext": main_ext, "priors": main_priors}.get(sys.argv[1] if len(sys.argv) > 1 else "", main)()

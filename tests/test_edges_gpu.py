@@ -165,6 +165,21 @@ def test_full_size_c2_properties(oracle):
         half = 0.5 * float(np.sum(v["w"].astype(np.float64) * (v["Vr"].astype(np.float64) ** 2).sum(1)))
         assert abs(chi2 - half) <= 1e-6 * half, (chi2, half)
         assert e.chi2(I_dev) == chi2, "the forward pass is deterministic"
+        # the forward model itself at the benchmarked size: fp64 oracle (clip is already applied to I_dev; FFT of
+        # the 2048^2 model image, bilinear degridding of all 10 M samples) vs the engine's Vm, Vr and 0.5*chi2
+        Ic = I_dev.cpu().numpy()
+        prep = oracle.prep(p.uvw[0], p.Vo[0], p.w[0], float(p.freqs[0]), e.meta["deltau"], e.meta["deltav"], p.N)
+        assert np.array_equal(prep["uvw"].view(np.uint64), v["uvw"].view(np.uint64)), "fold + metres->lambda, 10 M samples"
+        assert np.array_equal(prep["w"].view(np.uint32), v["w"].view(np.uint32)), "off-grid weights"
+        Vre, Vim = oracle.model_grid(Ic, None, float(p.freqs[0]), e.meta, _cfg(p))
+        s_or, Vm_or, Vr_or = oracle.degrid_chi2(Vre, Vim, prep, p.N)
+        scale = float(np.abs(Vm_or).max())
+        on = v["w"] > 0
+        dvm = float(np.abs(v["Vm"][on] - Vm_or[on]).max()) / scale
+        print(f"\n[C2 full size] 0.5*chi2 engine {chi2:.8e} oracle {0.5 * s_or:.8e} (rel {abs(chi2 - 0.5 * s_or) / (0.5 * s_or):.2e}); "
+              f"max |Vm - Vm_oracle| / max |Vm| = {dvm:.2e} over {int(on.sum())} samples")
+        assert abs(chi2 - 0.5 * s_or) <= 1e-5 * 0.5 * s_or, (chi2, 0.5 * s_or)       # north-star tolerance on chi2
+        assert dvm <= 2e-5, dvm
         g = torch.zeros_like(I_dev)
         e.dchi2(I_dev, g, flag_opt=0)
         assert e.last_grad_mode() == GRAD_UMMA

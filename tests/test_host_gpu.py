@@ -125,5 +125,27 @@ def test_scenario_matches_reference(name, refdir):
             assert _rel(img[1][m], ref["final_image"][1][m]) <= 10 * FINAL_TOL[name]
         v2, fi2 = s.calc_function()
         assert abs(v2 - float(ref["final_value"])) <= 1e-3 * abs(float(ref["final_value"]))
+        # -- residual / model write-back (MFS::writeResiduals + modelToHost) on the REFERENCE's final image ----
+        if "wb_chi2" in ref.files:
+            s.set_image(ref["final_image"])
+            s.calc_function()
+            wb_chi2, blocks = s.write_residuals()
+            gridded = "-g" in args
+            assert len(blocks) == p.nchan
+            for c, b in enumerate(blocks):
+                # the samples that go to the file are the ORIGINAL ones (ungridded again after a gridded run)
+                assert np.array_equal(b["uvw"].view(np.uint64), ref[f"wb_uvw{c}"].view(np.uint64)), f"write-back uvw {c}"
+                assert np.array_equal(b["uvw"], np.ascontiguousarray(p.uvw[c], np.float64))
+                assert np.array_equal(b["Vo"].view(np.uint32), ref[f"wb_Vo{c}"].view(np.uint32)), f"write-back Vo {c}"
+                assert np.array_equal(b["w"].view(np.uint32), ref[f"wb_w{c}"].view(np.uint32)), f"write-back weights {c}"
+                rVm = ref[f"wb_Vm{c}"]
+                scale = float(np.abs(rVm).max())
+                assert scale > 0
+                assert np.abs(b["Vm"] - rVm).max() <= 2e-5 * scale, (c, np.abs(b["Vm"] - rVm).max() / scale)
+                assert np.abs(b["Vr"] - (ref[f"wb_Vo{c}"] - rVm)).max() <= 2e-5 * max(scale, float(np.abs(b["Vo"]).max()))
+            if gridded:
+                want = float(ref["wb_chi2"])
+                assert abs(wb_chi2 - want) <= 1e-5 * abs(want), ("non-gridded chi2", wb_chi2, want)
+                print(f"\n[{name}] write-back: non-gridded 0.5*chi2 {wb_chi2:.6e} (reference {want:.6e})")
     finally:
         s.close()

@@ -21,13 +21,13 @@ def _ngpu():
         return 0
 
 
-def _run(world, nchan, out, port):
+def _run(world, nchan, out, port, extra=()):
     worker = os.path.join(ROOT, "tests", "_mgpu_worker.py")
     if world == 1:
-        cmd = [sys.executable, worker, str(nchan), out]
+        cmd = [sys.executable, worker, str(nchan), out, *extra]
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-               "--master-addr", "127.0.0.1", "--master-port", str(port), worker, str(nchan), out]
+               "--master-addr", "127.0.0.1", "--master-port", str(port), worker, str(nchan), out, *extra]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return np.load(out)
@@ -61,3 +61,18 @@ def test_sharded_run_matches_single_gpu(tmp_path, nchan):
         assert np.median(np.abs(two["err"][1][both] - one["err"][1][both]) / one["err"][1][both]) <= 1e-4
     print(f"\n[nchan={nchan}] grad rel-L2 {_rel(two['grad'][0], one['grad'][0]):.2e}, final image rel-L2 "
           f"{_rel(two['image'][0], one['image'][0]):.2e}, collectives {int(two['collectives'])}")
+
+
+def test_normalized_chi2_with_visibility_chunks_matches_single_gpu(tmp_path):
+    """Chi2 with normalize = true on ONE channel cut into visibility chunks over 2 ranks: the divisor is the
+    block's numVisibilitiesPerFreqPerStoke (src/functions.cu:4439-4441, :3785), not the size of a rank's slice —
+    dividing the shards by their own size and summing would double chi2 against the priors."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    one = _run(1, 1, str(tmp_path / "one_norm.npz"), 0, extra=("normalize",))
+    two = _run(2, 1, str(tmp_path / "two_norm.npz"), 29547, extra=("normalize",))
+    assert int(two["world"]) == 2 and int(two["local_nvis"]) < int(one["local_nvis"])
+    assert abs(float(two["fi"][0]) - float(one["fi"][0])) <= 1e-5 * abs(float(one["fi"][0])), (two["fi"], one["fi"])
+    assert abs(float(two["value"]) - float(one["value"])) <= 1e-5 * abs(float(one["value"]))
+    assert _rel(two["grad"][0], one["grad"][0]) <= 1e-4
+    assert _rel(two["image"][0], one["image"][0]) <= 2e-3

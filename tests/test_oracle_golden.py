@@ -181,3 +181,35 @@ def test_degridding_kernel(gold, gold_ext, ctx, oracle):
     inner = (j - sx > 0) & (j + sx < N) & (k - sy > 0) & (k + sy < N)
     assert inner.sum() > 0.9 * len(j)
     assert np.abs(got[inner] - want[inner]).max() <= 2e-6 * np.abs(want).max()
+
+
+# ---- third fixture: every Fi kind on its own (tests/golden/make_golden.py priors)
+@pytest.fixture(scope="module")
+def gold_priors():
+    path = os.path.join(HERE, "golden", "ref_small_priors.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/ref_small_priors.npz not generated yet")
+    return np.load(path)
+
+
+def test_every_prior_kind(gold_priors, ctx, oracle):
+    """Value and gradient of Entropy, L1, TV, TSV, Laplacian, Quadratic, GEntropy, GL1Norm as the reference's own
+    Fi objects computed them (calcFi / restartDGi + calcGi + addToDphi), against the C restatement."""
+    from gpuvmem_b200.engine import PRIOR
+    from make_golden import PRIOR_EPS_B, PRIOR_GOLD, PRIOR_LAMBDA, prior_inputs
+    p, s, meta, cfg = ctx
+    noise, cut = gold_priors["noise"], float(gold_priors["noise_cut"])
+    for kind, index in PRIOR_GOLD:
+        I, prior, eps_a = prior_inputs(kind, index, p.N)
+        want_v = float(gold_priors[f"value_{kind}_{index}"])
+        dphi = gold_priors[f"dphi_{kind}_{index}"]
+        target = 0 if kind == "TotalVariation" else index      # TVariation::addToDphi: image 0 (src/totalvariation.cu:46)
+        assert not dphi[1 - target].any()
+        want_g = dphi[target]
+        okw = dict(G=0.001, eta=-1.0, eps=eps_a, eps_b=PRIOR_EPS_B, prior_image=prior)
+        v = oracle.prior_value(PRIOR[kind], I[index], noise, cut, **okw)
+        g = oracle.prior_grad(PRIOR[kind], I[index], noise, cut, PRIOR_LAMBDA, **okw)
+        assert abs(v - want_v) <= 2e-5 * abs(want_v), (kind, index, v, want_v)
+        rel = np.linalg.norm(g - want_g) / np.linalg.norm(want_g)
+        worst = np.abs(g - want_g).max() / np.abs(want_g).max()
+        assert rel <= 1e-5 and worst <= 1e-4, (kind, index, rel, worst)

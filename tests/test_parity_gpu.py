@@ -323,7 +323,7 @@ def test_weights_bit_exact_on_gpu(oracle, wprob, scheme, robust, taper):
 
 
 @pytest.mark.parametrize("name,m,n", [("PillBox2D", 1, 1), ("Gaussian2D", 7, 7), ("GaussianSinc2D", 7, 7),
-                                      ("PSWF", 9, 9)])
+                                      ("Sinc2D", 7, 7), ("PSWF", 9, 9)])
 def test_gridding_bit_exact_on_gpu(oracle, wprob, name, m, n):
     from gpuvmem_b200.engine import grid_block
     p = wprob

@@ -268,3 +268,56 @@ def test_conv_degridding_matches_reference_kernel(setup, oracle):
     ref.set_image(_image(e))
     want, _ = ref.calc_function(iteration=0)
     assert abs(e.chi2(I_dev) - want) <= 1e-5 * abs(want)
+
+
+# Every Fi kind the reference registers (factory names, src/*.cu registerCreationFunction), evaluated ON ITS OWN
+# by the reference build (gvref_prior_eval: Fi::configure + calcFi + restartDGi + calcGi + addToDphi) — TV,
+# Quadratic, GEntropy and GL1Norm are not wired by main.cu, so the objective-level tests above never reach them.
+PRIOR_CASES = [("Entropy", 0), ("L1-Norm", 0), ("TotalVariation", 0), ("TotalSquaredVariation", 0), ("Laplacian", 0),
+               ("Quadratic", 0), ("GEntropy", 0), ("GL1Norm", 0), ("TotalVariation", 1), ("Quadratic", 1), ("L1-Norm", 1)]
+# image the term's gradient is added to: TVariation::addToDphi always adds to image 0 (src/totalvariation.cu:46);
+# every other Fi uses imageToAdd
+ADDS_TO_IMAGE0 = ("TotalVariation",)
+
+
+@pytest.mark.parametrize("kind,index", PRIOR_CASES)
+def test_every_prior_kind_matches_reference(setup, oracle, kind, index):
+    p, e, ref, torch = setup
+    if not hasattr(ref.lib, "gvref_prior_eval"):
+        pytest.skip("oracle/_ref/libgvref.so predates gvref_prior_eval")
+    from gpuvmem_b200.engine import PRIOR
+    I = _image(e)
+    if index == 1:
+        I[1] = np.abs(I[1]) + np.float32(0.01)      # a positive plane (the terms take logs / square roots of it)
+    lam = 0.37
+    prior_img = (np.abs(I[index]) * 0.5 + 1e-4).astype(np.float32) if kind in ("GEntropy", "GL1Norm") else None
+    eps_a = 1e-12 if kind in ("L1-Norm", "GL1Norm") else 1e-6
+    eps_b = 1e-3
+    want_v, want_dphi = ref.prior_eval(kind, I, lam, image_index=index, iteration=1, prior_image=prior_img,
+                                       prior_value=0.001, eta=-1.0, eps_a=eps_a, eps_b=eps_b)
+    target = 0 if kind in ADDS_TO_IMAGE0 else index
+    assert not want_dphi[1 - target].any(), "the reference adds the gradient to one image only"
+    want_g = want_dphi[target]
+    noise = e.get_noise_image()
+    k = PRIOR[kind]
+    # the C oracle (what test_parity_gpu.py::test_priors holds the CUDA kernels to) against the reference
+    okw = dict(G=0.001, eta=-1.0, eps=eps_a, eps_b=eps_b, prior_image=prior_img)
+    ov = oracle.prior_value(k, I[index], noise, e.meta["noise_cut"], **okw)
+    og = oracle.prior_grad(k, I[index], noise, e.meta["noise_cut"], lam, **okw)
+    # the engine
+    I_dev = torch.from_numpy(I).cuda()
+    kw = dict(prior_value=0.001, eta=-1.0, epsilon=eps_a, epsilon_b=eps_b)
+    if prior_img is not None:
+        kw["prior_image"] = torch.from_numpy(prior_img).cuda()
+    gv = e.prior_value(kind, I_dev, index, **kw)
+    dgi = torch.empty(p.N, p.N, device="cuda")
+    e.prior_grad(kind, I_dev, dgi, lam, index, **kw)
+    gg = dgi.cpu().numpy()
+    scale = float(np.abs(want_g).max())
+    assert scale > 0 and np.isfinite(want_v)
+    for who, v, g in (("oracle", ov, og), ("engine", gv, gg)):
+        assert abs(v - want_v) <= 2e-5 * abs(want_v), (who, kind, index, v, want_v)
+        rel = np.linalg.norm(g - want_g) / np.linalg.norm(want_g)
+        worst = float(np.abs(g - want_g).max()) / scale
+        assert rel <= 1e-5 and worst <= 1e-4, (who, kind, index, rel, worst)
+        assert np.array_equal(g == 0, want_g == 0) or np.count_nonzero((g == 0) != (want_g == 0)) <= 2, (who, kind)
