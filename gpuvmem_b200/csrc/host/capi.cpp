@@ -201,6 +201,47 @@ int gvmh_get_host_model(gvmh_session* s, int chan, float* Vm, float* Vr) {
   return 0;
 }
 
+int gvmh_fi_eval(gvmh_session*, const char* name, const float* I_host, const float* prior_host, float lambda,
+                 float prior_value, float eta, float eps_a, float eps_b, int image_index, int iteration, int flag,
+                 float* value_out, float* dphi_out, float* prior_after_out) {
+  Globals& g = G();
+  Fi* f = createObject<Fi, std::string>(name);
+  if (!f) return 1;
+  const std::string n(name);
+  const size_t MN = (size_t)g.M * g.N;
+  const int saved_flag = g.flag_opt;
+  g.flag_opt = flag;
+  f->configure(-1, image_index, image_index, false);
+  f->setPenalizationFactor(lambda);
+  f->setIteration(iteration);
+  float* d_prior = nullptr;
+  if (prior_host) {
+    d_prior = devAllocFloats(MN);
+    devUpload(d_prior, prior_host, MN);
+    f->setPrior(d_prior);    // owned by the term from here on
+  }
+  if (n == "Entropy") { f->setPrior(prior_value); f->setEta(eta); }
+  if (n == "GEntropy") f->setEta(eta);
+  if (n == "TotalVariation") static_cast<TVariation*>(f)->setEpsilon(eps_a);
+  if (n == "L1-Norm") static_cast<L1norm*>(f)->setEpsilon(eps_a);
+  if (n == "GL1Norm") static_cast<GL1Norm*>(f)->setEpsilons(eps_a, eps_b);
+  float* d_I = devAllocFloats(imageFloats());
+  float* d_phi = devAllocFloats(imageFloats());
+  devUpload(d_I, I_host, imageFloats());
+  f->calcFi(d_I);
+  if (value_out) *value_out = f->get_fivalue();
+  f->restartDGi();
+  f->calcGi(d_I, d_phi);
+  f->addToDphi(d_phi);
+  if (dphi_out) devDownload(dphi_out, d_phi, imageFloats());
+  if (prior_after_out && d_prior) devDownload(prior_after_out, d_prior, MN);
+  devFree(d_I);
+  devFree(d_phi);
+  delete f;
+  g.flag_opt = saved_flag;
+  return 0;
+}
+
 int gvmh_error_image(gvmh_session* s, float* errors_host) {
   Error* est = createObject<Error, std::string>("SecondDerivateError");
   Image* img = s->sy->getImage();

@@ -179,7 +179,17 @@ void GL1Norm::setPrior(float* p) { devFree(prior); prior = p; }
 void GL1Norm::normalizePrior() { scaleImage(prior, normalization_factor); }
 bool GL1Norm::priorSpec(int* kind, gvm_prior_params* pp) { *kind = GVM_PRIOR_GL1; *pp = params(0, 0, epsilon_a, epsilon_b, prior); return true; }
 float GL1Norm::calcFi(float* p) { return priorValue(GVM_PRIOR_GL1, p, params(0, 0, epsilon_a, epsilon_b, prior)); }
-void GL1Norm::calcGi(float* p, float*) { priorGrad(GVM_PRIOR_GL1, p, params(0, 0, epsilon_a, epsilon_b, prior)); }
+// Reference quirk kept verbatim: GL1Norm::calcGi calls DGL1Norm(p, device_DS, this->prior, ...)
+// (src/gl1norm.cu:145-148) against the signature DGL1Norm(I, prior, dgi, ...) (src/functions.cu:4700-4709) — the two
+// image arguments are swapped. The kernel therefore reads the device_DS that restartDGi has just zeroed AS THE PRIOR
+// and writes the gradient INTO THE PRIOR IMAGE: device_DS stays zero, the term adds nothing to dphi, and every later
+// calcFi divides by the overwritten prior. Pinned against the reference build by
+// tests/test_parity_reference_gpu.py::test_host_fi_terms_match_reference.
+void GL1Norm::calcGi(float* p, float*) {
+  if (!(iteration > 0 && penalization_factor && G().flag_opt % 2 == imageIndex)) return;
+  const gvm_prior_params pp = params(0, 0, epsilon_a, epsilon_b, device_DS);
+  GVM_CHECK(gvm_prior_grad(G().engine, GVM_PRIOR_GL1, p, imageIndex, &pp, penalization_factor, prior));
+}
 
 namespace {
 Fi* makeChi2() { return new Chi2; }

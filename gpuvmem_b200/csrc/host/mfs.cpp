@@ -731,7 +731,16 @@ void MFS::writeResiduals() {
   Fi* chi2 = optimizer->getObjectiveFunction()->getFiByName("Chi2");
   nongridded_chi2 = 0.0f;
   if (gridding && !ungridded.empty()) {
-    datasets = std::move(ungridded);   // the originals come back (no copy); a second call finds them in place
+    // the originals come back (no copy); they take the pointing / phase-centre pixels setDevice derived for the
+    // gridded shells (the reference keeps ONE Field object per field, so its centres survive the swap)
+    for (size_t d = 0; d < ungridded.size() && d < datasets.size(); d++)
+      for (size_t f = 0; f < ungridded[d].fields.size() && f < datasets[d].fields.size(); f++) {
+        Field& dst = ungridded[d].fields[f];
+        const Field& src = datasets[d].fields[f];
+        dst.ref_xobs_pix = src.ref_xobs_pix; dst.ref_yobs_pix = src.ref_yobs_pix;
+        dst.phs_xobs_pix = src.phs_xobs_pix; dst.phs_yobs_pix = src.phs_yobs_pix;
+      }
+    datasets = std::move(ungridded);   // a second call finds them in place
     ungridded.clear();
     GVM_CHECK(gvm_clear_channels(g.engine));
     shardAndUpload();

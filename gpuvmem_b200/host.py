@@ -51,6 +51,7 @@ SIGNATURES = {
     "gvmh_fits_write": (C.c_int, [C.c_char_p, _P, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p,
                                   C.c_float, C.c_double, C.c_double]),
     "gvmh_error_image": (C.c_int, [_P, _P]),
+    "gvmh_fi_eval": (C.c_int, [_P, C.c_char_p, _P, _P] + [C.c_float] * 5 + [C.c_int] * 3 + [C.POINTER(C.c_float), _P, _P]),
     "gvmh_filter_gridding": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int]),
     "gvmh_set_image": (C.c_int, [_P, _P]),
     "gvmh_get_image": (C.c_int, [_P, _P]),
@@ -247,6 +248,22 @@ class Session:
         w = np.empty(n, np.float32)
         self.h.gvmh_get_host_vis(self.s, chan, uvw.ctypes.data, Vo.ctypes.data, w.ctypes.data)
         return uvw, Vo, w
+
+    def fi_eval(self, name, I, lam, image_index=0, iteration=1, prior_image=None, prior_value=0.001, eta=-1.0,
+                eps_a=1e-12, eps_b=1e-12, flag=None):
+        """One Fi term on its own through the host layer's classes: (value, dphi [2][M][N], prior image after calcGi)."""
+        N = I.shape[-1]
+        val = C.c_float()
+        dphi = np.zeros(I.size, np.float32)
+        Ic = np.ascontiguousarray(I.reshape(-1), np.float32)
+        pr = None if prior_image is None else np.ascontiguousarray(prior_image, np.float32)
+        after = None if pr is None else np.zeros(pr.size, np.float32)
+        rc = self.h.gvmh_fi_eval(self.s, name.encode(), Ic.ctypes.data, None if pr is None else pr.ctypes.data, lam,
+                                 prior_value, eta, eps_a, eps_b, image_index, iteration,
+                                 image_index if flag is None else flag, C.byref(val), dphi.ctypes.data,
+                                 None if after is None else after.ctypes.data)
+        assert rc == 0, rc
+        return val.value, dphi.reshape(I.shape), (None if after is None else after.reshape(N, N))
 
     def write_residuals(self):
         """MFS::writeResiduals; returns (non-gridded 0.5*chi2 or 0, [per channel dict(uvw, Vo, w, Vm, Vr)])."""

@@ -79,6 +79,15 @@ int gvmh_get_host_model(gvmh_session* s, int chan, float* Vm, float* Vr);
  * src/functions.cu:4966-5040) on the session's image and the residuals of the last objective
  * evaluation; errors_host [2][M][N]: sigma(I_nu0), sigma(alpha). */
 int gvmh_error_image(gvmh_session* s, float* errors_host);
+/* ONE Fi term of the factory ("Entropy", "L1-Norm", "TotalVariation", "TotalSquaredVariation", "Laplacian",
+ * "Quadratic", "GEntropy", "GL1Norm") on its own, the way ObjectiveFunction drives it (include/classes/
+ * objectivefunction.cuh; Fi::configure(-1, image_index, image_index, false), include/classes/fi.cuh:62-95):
+ * calcFi -> value_out = get_fivalue(); restartDGi + calcGi + addToDphi into a zeroed dphi_out [2][M][N].
+ * I_host [2][M][N]; prior_host M*N or NULL; flag = flag_opt; prior_after_out (optional, M*N): the term's prior image
+ * after calcGi (see GL1Norm::calcGi). The session provides the engine, mask and image size. */
+int gvmh_fi_eval(gvmh_session* s, const char* name, const float* I_host, const float* prior_host, float lambda,
+                 float prior_value, float eta, float eps_a, float eps_b, int image_index, int iteration, int flag,
+                 float* value_out, float* dphi_out, float* prior_after_out);
 /* Filter "Gridding" (src/gridding.cu:13-28): do_gridding over the session's Visibilities, in place, with
  * the named CKernel (NULL/"": PillBox2D, the reference's default). The host-side samples change
  * (gvmh_get_host_vis); the engine keeps what was uploaded. */

@@ -616,12 +616,17 @@ int gvref_degridding(long Z, const double* uvw_lambda, const float* Vg, const fl
  * penalization factor = lambda, then calcFi -> get_fivalue() and restartDGi + calcGi + addToDphi into a
  * zeroed dphi [image_count][M][N] (what ObjectiveFunction::calcGradient does per term,
  * include/classes/objectivefunction.cuh). prior_host: M*N floats for GEntropy / GL1Norm, else NULL.
- * Needs gvref_init first (noise image, M, N, image_count). */
+ * Needs gvref_init first (noise image, M, N, image_count).
+ * flag: the optimizers' flag_opt (the gradient hosts only act when flag_opt % 2 == imageIndex).
+ * prior_after_out (optional, M*N): the term's prior image AFTER calcGi — GL1Norm::calcGi passes its two image
+ * arguments to DGL1Norm in swapped order (src/gl1norm.cu:145-148 vs src/functions.cu:4700), so the reference
+ * writes that gradient into the prior image and adds zeros to dphi. */
 int gvref_prior_eval(const char* name, const float* I_host, const float* prior_host, float lambda,
                      float prior_value, float eta_v, float eps_a, float eps_b, int image_index, int iteration,
-                     float* value_out, float* dphi_out) {
+                     int flag, float* value_out, float* dphi_out, float* prior_after_out) {
   Fi* f = createObject<Fi, std::string>(name);
   if (!f) return -1;
+  flag_opt = flag;
   f->configure(-1, image_index, image_index, false);
   f->setPenalizationFactor(lambda);
   f->setIteration(iteration);
@@ -649,8 +654,10 @@ int gvref_prior_eval(const char* name, const float* I_host, const float* prior_h
   f->addToDphi(d_phi);
   cudaError_t err = cudaDeviceSynchronize();
   if (dphi_out) cudaMemcpy(dphi_out, d_phi, bytes, cudaMemcpyDeviceToHost);
+  if (prior_after_out && d_prior) cudaMemcpy(prior_after_out, d_prior, sizeof(float) * M * N, cudaMemcpyDeviceToHost);
   cudaFree(d_I);
   cudaFree(d_phi);
+  flag_opt = 0;
   return (int)err;
 }
 

@@ -249,8 +249,8 @@ class GvRef:
             L.gvref_error_image.argtypes = [f32p]
         L.gvref_set_verbose.argtypes = [C.c_int]
         if hasattr(L, "gvref_prior_eval"):
-            L.gvref_prior_eval.argtypes = [C.c_char_p, f32p, _V] + [C.c_float] * 5 + [C.c_int, C.c_int,
-                                                                                     C.POINTER(C.c_float), f32p]
+            L.gvref_prior_eval.argtypes = [C.c_char_p, f32p, _V] + [C.c_float] * 5 + [C.c_int, C.c_int, C.c_int,
+                                                                                     C.POINTER(C.c_float), f32p, _V]
         if hasattr(L, "gvref_write_residuals"):
             L.gvref_write_residuals.argtypes = [C.POINTER(C.c_float)]
             L.gvref_get_host_model.argtypes = [C.c_int, _V, _V, _V, _V]
@@ -376,17 +376,20 @@ class GvRef:
         return out.reshape(2, p.M, p.N)
 
     def prior_eval(self, name, I, lam, image_index=0, iteration=1, prior_image=None, prior_value=0.001, eta=-1.0,
-                   eps_a=1e-12, eps_b=1e-12):
-        """One Fi of the reference on its own: (get_fivalue(), dphi [2][M][N] after restartDGi + calcGi + addToDphi)."""
+                   eps_a=1e-12, eps_b=1e-12, flag=None):
+        """One Fi of the reference on its own: (get_fivalue(), dphi [2][M][N] after restartDGi + calcGi + addToDphi,
+        the term's prior image after calcGi or None). flag: flag_opt, default = image_index (gradient gate open)."""
         p = self.problem
         val = C.c_float()
         dphi = np.zeros(2 * p.M * p.N, np.float32)
         pr = None if prior_image is None else np.ascontiguousarray(prior_image, np.float32)
+        after = None if pr is None else np.zeros(p.M * p.N, np.float32)
         rc = self.lib.gvref_prior_eval(name.encode(), np.ascontiguousarray(I.reshape(-1), np.float32),
                                        None if pr is None else pr.ctypes.data, lam, prior_value, eta, eps_a, eps_b,
-                                       image_index, iteration, C.byref(val), dphi)
+                                       image_index, iteration, image_index if flag is None else flag, C.byref(val), dphi,
+                                       None if after is None else after.ctypes.data)
         assert rc == 0, rc
-        return val.value, dphi.reshape(2, p.M, p.N)
+        return val.value, dphi.reshape(2, p.M, p.N), (None if after is None else after.reshape(p.M, p.N))
 
     def write_residuals(self):
         """MFS::writeResiduals; returns (non-gridded 0.5*chi2 of the last Chi2::calcFi, [per channel dict])."""

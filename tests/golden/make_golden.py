@@ -73,10 +73,12 @@ def main_priors():
     out = {"noise": ref.noise_image(), "noise_cut": np.float64(ref.scalars()["noise_cut"])}
     for kind, index in PRIOR_GOLD:
         I, prior, eps_a = prior_inputs(kind, index, p.N)
-        v, dphi = ref.prior_eval(kind, I, PRIOR_LAMBDA, image_index=index, iteration=1, prior_image=prior,
-                                 prior_value=0.001, eta=-1.0, eps_a=eps_a, eps_b=PRIOR_EPS_B)
+        v, dphi, after = ref.prior_eval(kind, I, PRIOR_LAMBDA, image_index=index, iteration=1, prior_image=prior,
+                                        prior_value=0.001, eta=-1.0, eps_a=eps_a, eps_b=PRIOR_EPS_B)
         out[f"value_{kind}_{index}"] = np.float32(v)
         out[f"dphi_{kind}_{index}"] = dphi
+        if after is not None:
+            out[f"prior_after_{kind}_{index}"] = after
     d = os.path.join(ROOT, "gpurun_out", "golden")
     os.makedirs(d, exist_ok=True)
     np.savez_compressed(os.path.join(d, "ref_small_priors.npz"), **out)

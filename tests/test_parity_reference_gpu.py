@@ -275,49 +275,108 @@ def test_conv_degridding_matches_reference_kernel(setup, oracle):
 # Quadratic, GEntropy and GL1Norm are not wired by main.cu, so the objective-level tests above never reach them.
 PRIOR_CASES = [("Entropy", 0), ("L1-Norm", 0), ("TotalVariation", 0), ("TotalSquaredVariation", 0), ("Laplacian", 0),
                ("Quadratic", 0), ("GEntropy", 0), ("GL1Norm", 0), ("TotalVariation", 1), ("Quadratic", 1), ("L1-Norm", 1)]
-# image the term's gradient is added to: TVariation::addToDphi always adds to image 0 (src/totalvariation.cu:46);
-# every other Fi uses imageToAdd
-ADDS_TO_IMAGE0 = ("TotalVariation",)
+LAM, EPS_B = 0.37, 1e-3
+
+
+def _prior_case(e, kind, index):
+    I = _image(e)
+    if index == 1:
+        I[1] = np.abs(I[1]) + np.float32(0.01)      # a positive plane (the terms take logs / square roots of it)
+    prior_img = (np.abs(I[index]) * 0.5 + 1e-4).astype(np.float32) if kind in ("GEntropy", "GL1Norm") else None
+    eps_a = 1e-12 if kind in ("L1-Norm", "GL1Norm") else 1e-6
+    return I, prior_img, eps_a
+
+
+def _close(who, g, want_g, kind, index):
+    rel = np.linalg.norm(g - want_g) / np.linalg.norm(want_g)
+    worst = float(np.abs(g - want_g).max()) / float(np.abs(want_g).max())
+    assert rel <= 1e-5 and worst <= 1e-4, (who, kind, index, rel, worst)
+    assert np.count_nonzero((g == 0) != (want_g == 0)) <= 2, (who, kind, index)
 
 
 @pytest.mark.parametrize("kind,index", PRIOR_CASES)
 def test_every_prior_kind_matches_reference(setup, oracle, kind, index):
+    """Kernel level: gvm_prior_value / gvm_prior_grad and the C oracle's gvo_prior_* against the reference's Fi."""
     p, e, ref, torch = setup
     if not hasattr(ref.lib, "gvref_prior_eval"):
         pytest.skip("oracle/_ref/libgvref.so predates gvref_prior_eval")
     from gpuvmem_b200.engine import PRIOR
-    I = _image(e)
-    if index == 1:
-        I[1] = np.abs(I[1]) + np.float32(0.01)      # a positive plane (the terms take logs / square roots of it)
-    lam = 0.37
-    prior_img = (np.abs(I[index]) * 0.5 + 1e-4).astype(np.float32) if kind in ("GEntropy", "GL1Norm") else None
-    eps_a = 1e-12 if kind in ("L1-Norm", "GL1Norm") else 1e-6
-    eps_b = 1e-3
-    want_v, want_dphi = ref.prior_eval(kind, I, lam, image_index=index, iteration=1, prior_image=prior_img,
-                                       prior_value=0.001, eta=-1.0, eps_a=eps_a, eps_b=eps_b)
-    target = 0 if kind in ADDS_TO_IMAGE0 else index
+    I, prior_img, eps_a = _prior_case(e, kind, index)
+    want_v, want_dphi, prior_after = ref.prior_eval(kind, I, LAM, image_index=index, iteration=1, prior_image=prior_img,
+                                                    prior_value=0.001, eta=-1.0, eps_a=eps_a, eps_b=EPS_B)
+    # TVariation::addToDphi always adds to image 0 (src/totalvariation.cu:46); every other Fi uses imageToAdd
+    target = 0 if kind == "TotalVariation" else index
     assert not want_dphi[1 - target].any(), "the reference adds the gradient to one image only"
     want_g = want_dphi[target]
+    grad_prior = prior_img
+    if kind == "GL1Norm":
+        # reference quirk: GL1Norm::calcGi swaps DGL1Norm's image arguments (src/gl1norm.cu:145-148 vs
+        # src/functions.cu:4700): the gradient is computed against a ZERO prior (the freshly reset device_DS) and lands
+        # in the prior image; dphi receives nothing
+        assert not want_dphi.any()
+        assert not np.array_equal(prior_after, prior_img)
+        want_g, grad_prior = prior_after, np.zeros_like(prior_img)
+    else:
+        assert np.abs(want_g).max() > 0
+        if prior_img is not None:
+            assert np.array_equal(prior_after, prior_img)
+    assert np.isfinite(want_v)
     noise = e.get_noise_image()
     k = PRIOR[kind]
-    # the C oracle (what test_parity_gpu.py::test_priors holds the CUDA kernels to) against the reference
-    okw = dict(G=0.001, eta=-1.0, eps=eps_a, eps_b=eps_b, prior_image=prior_img)
-    ov = oracle.prior_value(k, I[index], noise, e.meta["noise_cut"], **okw)
-    og = oracle.prior_grad(k, I[index], noise, e.meta["noise_cut"], lam, **okw)
-    # the engine
+    okw = dict(G=0.001, eta=-1.0, eps=eps_a, eps_b=EPS_B)
+    ov = oracle.prior_value(k, I[index], noise, e.meta["noise_cut"], prior_image=prior_img, **okw)
+    og = oracle.prior_grad(k, I[index], noise, e.meta["noise_cut"], LAM, prior_image=grad_prior, **okw)
     I_dev = torch.from_numpy(I).cuda()
-    kw = dict(prior_value=0.001, eta=-1.0, epsilon=eps_a, epsilon_b=eps_b)
+    kw = dict(prior_value=0.001, eta=-1.0, epsilon=eps_a, epsilon_b=EPS_B)
+    vkw, gkw = dict(kw), dict(kw)
     if prior_img is not None:
-        kw["prior_image"] = torch.from_numpy(prior_img).cuda()
-    gv = e.prior_value(kind, I_dev, index, **kw)
+        vkw["prior_image"] = torch.from_numpy(prior_img).cuda()
+        gkw["prior_image"] = torch.from_numpy(grad_prior).cuda()
+    gv = e.prior_value(kind, I_dev, index, **vkw)
     dgi = torch.empty(p.N, p.N, device="cuda")
-    e.prior_grad(kind, I_dev, dgi, lam, index, **kw)
+    e.prior_grad(kind, I_dev, dgi, LAM, index, **gkw)
     gg = dgi.cpu().numpy()
-    scale = float(np.abs(want_g).max())
-    assert scale > 0 and np.isfinite(want_v)
     for who, v, g in (("oracle", ov, og), ("engine", gv, gg)):
         assert abs(v - want_v) <= 2e-5 * abs(want_v), (who, kind, index, v, want_v)
-        rel = np.linalg.norm(g - want_g) / np.linalg.norm(want_g)
-        worst = float(np.abs(g - want_g).max()) / scale
-        assert rel <= 1e-5 and worst <= 1e-4, (who, kind, index, rel, worst)
-        assert np.array_equal(g == 0, want_g == 0) or np.count_nonzero((g == 0) != (want_g == 0)) <= 2, (who, kind)
+        _close(who, g, want_g, kind, index)
+
+
+@pytest.fixture(scope="module")
+def session(setup):
+    from gpuvmem_b200 import host
+    p = setup[0]
+    host.set_quiet(True)
+    s = host.Session(p, args=ARGS.replace("-X 16 -Y 16 -V 256 ", "").replace(" -i synth.ms -o out.ms -m hdr.fits", ""))
+    yield s
+    s.close()
+
+
+@pytest.mark.parametrize("kind,index", PRIOR_CASES)
+def test_host_fi_terms_match_reference(setup, session, kind, index):
+    """Class level: the host layer's Fi adapters (calcFi, restartDGi, calcGi, addToDphi incl. the image each term adds
+    to, the flag_opt gate and GL1Norm's swapped-argument quirk) against the reference's Fi objects."""
+    p, e, ref, torch = setup
+    if not hasattr(ref.lib, "gvref_prior_eval"):
+        pytest.skip("oracle/_ref/libgvref.so predates gvref_prior_eval")
+    I, prior_img, eps_a = _prior_case(e, kind, index)
+    kw = dict(image_index=index, iteration=1, prior_image=prior_img, prior_value=0.001, eta=-1.0, eps_a=eps_a, eps_b=EPS_B)
+    want_v, want_dphi, want_after = ref.prior_eval(kind, I, LAM, **kw)
+    got_v, got_dphi, got_after = session.fi_eval(kind, I, LAM, **kw)
+    assert abs(got_v - want_v) <= 2e-5 * abs(want_v), (kind, index, got_v, want_v)
+    for img in range(2):
+        if want_dphi[img].any():
+            _close("host", got_dphi[img], want_dphi[img], kind, index)
+        else:
+            assert not got_dphi[img].any(), (kind, index, img)
+    if prior_img is not None:
+        if np.array_equal(want_after, prior_img):
+            assert np.array_equal(got_after, prior_img)
+        else:
+            _close("host prior-after", got_after, want_after, kind, index)
+    # gate closed: flag_opt % 2 != imageIndex -> no gradient at all; iteration 0 -> value 0 too
+    _, dphi_closed, _ = session.fi_eval(kind, I, LAM, **dict(kw, flag=1 - index))
+    _, ref_closed, _ = ref.prior_eval(kind, I, LAM, **dict(kw, flag=1 - index))
+    assert not dphi_closed.any() and not ref_closed.any()
+    v0, dphi0, _ = session.fi_eval(kind, I, LAM, **dict(kw, iteration=0))
+    r0, rdphi0, _ = ref.prior_eval(kind, I, LAM, **dict(kw, iteration=0))
+    assert v0 == 0.0 and r0 == 0.0 and not dphi0.any() and not rdphi0.any()
