@@ -141,7 +141,9 @@ static int create_impl(gvm_engine* e, const gvm_config* cfg, const cudaDevicePro
 }
 
 static void free_channel(GvmChannel& c) {
-  cudaFree(c.uvw_l); cudaFree(c.cell); cudaFree(c.frac); cudaFree(c.Vo); cudaFree(c.w);
+  cudaFree(c.uvw_l); cudaFree(c.cell); cudaFree(c.ccell); cudaFree(c.frac); cudaFree(c.Vo); cudaFree(c.w);
+  cudaFree(c.perm); cudaFree(c.items); cudaFree(c.block_first);
+  c.perm = nullptr; c.items = nullptr; c.block_first = nullptr;
   cudaFree(c.Vr); cudaFree(c.Vm); cudaFree(c.du64); cudaFree(c.dv64); cudaFree(c.wz);
   cudaFree(c.amp); cudaFree(c.gam); cudaFree(c.atten);
   c.atten = nullptr;
@@ -172,6 +174,7 @@ int gvm_destroy(gvm_engine* e) {
 }
 
 int gvm_set_stream(gvm_engine* e, void* s) {
+  e->epoch++;
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   e->own_stream = false;
   e->stream = (cudaStream_t)s;
@@ -200,6 +203,7 @@ int gvm_set_flag_opt(gvm_engine* e, int f) { e->flag_opt = f; return 0; }
 int gvm_set_noise_image(gvm_engine* e, const float* noise, int src_is_device) {
   const size_t MN = (size_t)e->cfg.M * e->cfg.N;
   e->plan_dirty = true;
+  e->epoch++;
   GVM_CUDA(cudaMemcpyAsync(e->noise, noise, MN * sizeof(float),
                            src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
   GVM_CUDA(cudaStreamSynchronize(e->stream));
@@ -213,6 +217,7 @@ int gvm_get_noise_image(gvm_engine* e, float* out) {
 }
 int gvm_set_gcf(gvm_engine* e, const float* gcf_host) {
   const size_t MN = (size_t)e->cfg.M * e->cfg.N;
+  e->epoch++;
   if (!gcf_host) { cudaFree(e->gcf); e->gcf = nullptr; return 0; }
   if (!e->gcf) GVM_CUDA(cudaMalloc(&e->gcf, MN * sizeof(float)));
   GVM_CUDA(cudaMemcpyAsync(e->gcf, gcf_host, MN * sizeof(float), cudaMemcpyHostToDevice, e->stream));
@@ -222,6 +227,7 @@ int gvm_set_gcf(gvm_engine* e, const float* gcf_host) {
 
 int gvm_set_degrid_kernel(gvm_engine* e, const float* table_host, int m, int n, int support_x, int support_y) {
   GVM_CUDA(cudaSetDevice(e->cfg.device));
+  e->epoch++;
   GVM_CUDA(cudaStreamSynchronize(e->stream));
   cudaFree(e->degrid_table);
   e->degrid_table = nullptr;
@@ -241,6 +247,7 @@ int gvm_set_degrid_kernel(gvm_engine* e, const float* table_host, int m, int n, 
 int gvm_set_forward_mode(gvm_engine* e, int mode) {
   if (mode < GVM_FORWARD_AUTO || mode > GVM_FORWARD_HALF) { gvm_set_error("gvm_set_forward_mode: unknown mode %d", mode); return 1; }
   e->forward_mode = mode;
+  e->epoch++;
   return 0;
 }
 int gvm_last_forward_mode(gvm_engine* e) { return e->last_forward_half ? GVM_FORWARD_HALF : GVM_FORWARD_FULL; }
@@ -256,11 +263,20 @@ int gvm_get_model_grid(gvm_engine* e, float* V_host) {
 
 static int add_channel_impl(gvm_engine* e, GvmChannel& c, int64_t Z, const double* uvw_m, const float* Vo, const float* w) {
   const size_t z = (size_t)(Z > 0 ? Z : 1);
+  // the streamed arrays carry 32 samples of slack: the tiled degridder's bulk copies start and end on 16-sample
+  // boundaries and may read (never use) up to that far past the last sample
+  const size_t zs = z + 32;
   GVM_CUDA(cudaMalloc(&c.uvw_l, z * 3 * sizeof(double)));
-  GVM_CUDA(cudaMalloc(&c.cell, z * sizeof(uint32_t)));
-  GVM_CUDA(cudaMalloc(&c.frac, z * sizeof(float2)));
-  GVM_CUDA(cudaMalloc(&c.Vo, z * sizeof(float2)));
-  GVM_CUDA(cudaMalloc(&c.w, z * sizeof(float)));
+  GVM_CUDA(cudaMalloc(&c.cell, zs * sizeof(uint32_t)));
+  GVM_CUDA(cudaMalloc(&c.ccell, zs * sizeof(uint32_t)));
+  GVM_CUDA(cudaMalloc(&c.frac, zs * sizeof(float2)));
+  GVM_CUDA(cudaMalloc(&c.Vo, zs * sizeof(float2)));
+  GVM_CUDA(cudaMalloc(&c.w, zs * sizeof(float)));
+  GVM_CUDA(cudaMemsetAsync(c.cell + (zs - 32 - (Z > 0 ? 0 : 1)), 0xFF, (32 + (Z > 0 ? 0 : 1)) * sizeof(uint32_t), e->stream));
+  GVM_CUDA(cudaMemsetAsync(c.ccell + (zs - 32 - (Z > 0 ? 0 : 1)), 0xFF, (32 + (Z > 0 ? 0 : 1)) * sizeof(uint32_t), e->stream));
+  GVM_CUDA(cudaMemsetAsync(c.frac + (zs - 32 - (Z > 0 ? 0 : 1)), 0, (32 + (Z > 0 ? 0 : 1)) * sizeof(float2), e->stream));
+  GVM_CUDA(cudaMemsetAsync(c.Vo + (zs - 32 - (Z > 0 ? 0 : 1)), 0, (32 + (Z > 0 ? 0 : 1)) * sizeof(float2), e->stream));
+  GVM_CUDA(cudaMemsetAsync(c.w + (zs - 32 - (Z > 0 ? 0 : 1)), 0, (32 + (Z > 0 ? 0 : 1)) * sizeof(float), e->stream));
   GVM_CUDA(cudaMalloc(&c.Vr, z * sizeof(float2)));
   GVM_CUDA(cudaMemset(c.Vr, 0, z * sizeof(float2)));
   if (e->cfg.keep_vm) {
@@ -287,6 +303,7 @@ int gvm_add_channel(gvm_engine* e, const gvm_channel_desc* desc, int64_t Z, cons
                     const float* Vo, const float* w, int* chan_out) {
   if (!e || !desc || Z < 0) { gvm_set_error("gvm_add_channel: bad argument"); return 1; }
   GVM_CUDA(cudaSetDevice(e->cfg.device));
+  e->epoch++;
   // the last two reduction slots belong to the image-sized reductions (priors.cu aux_red)
   if (ensure_red_slots(e, (int)e->chans.size() + 3)) return 1;
   GvmChannel c;
@@ -320,6 +337,7 @@ int gvm_set_block_nvis(gvm_engine* e, int chan, int64_t Z_block) {
 
 int gvm_clear_channels(gvm_engine* e) {
   GVM_CUDA(cudaSetDevice(e->cfg.device));
+  e->epoch++;
   GVM_CUDA(cudaStreamSynchronize(e->stream));
   for (auto& c : e->chans) free_channel(c);
   e->chans.clear();
@@ -338,24 +356,36 @@ int gvm_get_vis(gvm_engine* e, int chan, double* uvw_lambda, int32_t* cell, floa
   if (chan < 0 || chan >= (int)e->chans.size()) { gvm_set_error("gvm_get_vis: bad channel"); return 1; }
   GvmChannel& c = e->chans[chan];
   const size_t Z = (size_t)c.Z;
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
   GVM_CUDA(cudaStreamSynchronize(e->stream));
-  if (uvw_lambda && gvm_fast_d2h(uvw_lambda, c.uvw_l, Z * 3 * sizeof(double), e->stream)) return 1;
-  if (Vo && gvm_fast_d2h(Vo, c.Vo, Z * sizeof(float2), e->stream)) return 1;
-  if (Vr && gvm_fast_d2h(Vr, c.Vr, Z * sizeof(float2), e->stream)) return 1;
-  if (w && gvm_fast_d2h(w, c.w, Z * sizeof(float), e->stream)) return 1;
-  if (Vm) {
-    if (!c.Vm) { gvm_set_error("gvm_get_vis: Vm not kept (cfg.keep_vm = 0)"); return 1; }
-    GVM_CUDA(cudaMemcpy(Vm, c.Vm, Z * sizeof(float2), cudaMemcpyDeviceToHost));
-  }
-  if (cell) {
+  if (Z == 0) return 0;
+  if (Vm && !c.Vm) { gvm_set_error("gvm_get_vis: Vm not kept (cfg.keep_vm = 0)"); return 1; }
+  // the device arrays are in tile order (c.perm); the caller gets its own sample order back
+  void* tmp = nullptr;
+  if (c.perm) GVM_CUDA(cudaMalloc(&tmp, Z * sizeof(float2)));
+  auto fetch = [&](void* dst_host, const void* src_dev, int elem) -> int {
+    if (c.perm) {
+      if (gvm_unpermute(e, c, src_dev, tmp, elem)) return 1;
+      src_dev = tmp;
+    }
+    return gvm_fast_d2h(dst_host, src_dev, Z * (size_t)elem, e->stream);
+  };
+  int rc = 0;
+  if (uvw_lambda) rc = rc || gvm_fast_d2h(uvw_lambda, c.uvw_l, Z * 3 * sizeof(double), e->stream);
+  if (Vo) rc = rc || fetch(Vo, c.Vo, sizeof(float2));
+  if (Vr) rc = rc || fetch(Vr, c.Vr, sizeof(float2));
+  if (Vm) rc = rc || fetch(Vm, c.Vm, sizeof(float2));
+  if (w) rc = rc || fetch(w, c.w, sizeof(float));
+  if (cell && !rc) {
     std::vector<uint32_t> packed(Z);
-    GVM_CUDA(cudaMemcpy(packed.data(), c.cell, Z * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    for (size_t k = 0; k < Z; k++) {
+    rc = fetch(packed.data(), c.cell, sizeof(uint32_t));
+    for (size_t k = 0; k < Z && !rc; k++) {
       if (packed[k] == GVM_CELL_INVALID) { cell[2 * k] = -1; cell[2 * k + 1] = -1; }
       else { cell[2 * k] = (int32_t)(packed[k] & 0xFFFFu); cell[2 * k + 1] = (int32_t)(packed[k] >> 16); }
     }
   }
-  return 0;
+  cudaFree(tmp);
+  return rc;
 }
 
 // ------------------------------------------------------------------ hot path
@@ -510,6 +540,43 @@ int gvm_dev_copy(gvm_engine* e, void* dst, const void* src, size_t bytes, int ki
   if (kind == GVM_COPY_H2D) return gvm_fast_h2d(dst, src, bytes, e->stream);   // synchronous, pipelined for large pageable buffers
   if (kind == GVM_COPY_D2H) return gvm_fast_d2h(dst, src, bytes, e->stream);
   GVM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, e->stream));
+  return 0;
+}
+
+// --------------------------------------------------------------- CUDA graphs
+int64_t gvm_state_epoch(gvm_engine* e) { return e->epoch; }
+int gvm_graph_begin(gvm_engine* e) {
+  if (e->world > 1) { gvm_set_error("gvm_graph_begin: multi-rank engines are not captured (NCCL collectives inside)"); return 1; }
+  if (e->capturing) { gvm_set_error("gvm_graph_begin: already capturing"); return 1; }
+  GVM_CUDA(cudaSetDevice(e->cfg.device));
+  GVM_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+  e->capturing = true;
+  return 0;
+}
+int gvm_graph_end(gvm_engine* e, void** graph_exec_out) {
+  if (!e->capturing) { gvm_set_error("gvm_graph_end: no capture in progress"); return 1; }
+  e->capturing = false;
+  cudaGraph_t graph = nullptr;
+  cudaError_t err = cudaStreamEndCapture(e->stream, &graph);
+  if (err != cudaSuccess || !graph) {
+    gvm_set_error("gvm_graph_end: capture failed (%s): a captured call allocated or synchronised", cudaGetErrorString(err));
+    cudaGetLastError();
+    return 1;
+  }
+  cudaGraphExec_t exec = nullptr;
+  err = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (err != cudaSuccess) { gvm_set_error("gvm_graph_end: cudaGraphInstantiate -> %s", cudaGetErrorString(err)); return 1; }
+  *graph_exec_out = exec;
+  return 0;
+}
+int gvm_graph_launch(gvm_engine* e, void* graph_exec) {
+  GVM_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, e->stream));
+  GVM_LAUNCH(e);
+  return 0;
+}
+int gvm_graph_destroy(gvm_engine*, void* graph_exec) {
+  if (graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)graph_exec);
   return 0;
 }
 

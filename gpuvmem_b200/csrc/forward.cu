@@ -9,11 +9,19 @@
 //   k_image_prep     clip (first channel only) + I_nu + beam + GCF -> complex grid
 //   cuFFT            dense 2-D inverse C2C (the one library call the spec allows)
 //   k_phase_rotate   post-FFT modulation
-//   k_degrid_chi2    gather 4 taps + bilinear + residual + w|Vr|^2, block partials,
-//                    last block finishes the sum in fp64 in a fixed order
-// All streaming kernels are HBM-bound: 24 B read + 8 B written per visibility,
-// grid sized in multiples of the SM count, 128-bit loads where the layout allows.
+//   k_degrid_tiled   the degridder: samples are sorted by uv TILE at upload (32 x 32 cells; stable hand-written
+//                    radix sort, sort.cu), a block stages the tile of the model grid (+ halo) in shared memory
+//                    once and streams its samples' SoA arrays through a double-buffered shared-memory ring
+//                    filled by 1-D bulk asynchronous copies (cp.async.bulk + mbarrier, TMA without a tensor
+//                    map); taps are gathered from shared memory: bilinear vis_mod or the CKernel sum
+//   k_degrid_chi2    untiled fallback (grids that are not a multiple of the tile, the half-plane model of
+//                    gridded data whose samples are already in cell order): 4-tap gather from global memory
+//   both             + residual + w|Vr|^2, warp-shuffle block partials, last block finishes the sum in fp64
+//                    in a fixed order
+// All streaming kernels are HBM-bound: 24 B read + 8 B written per visibility (16 + 8 with a CKernel),
+// grids sized in multiples of the SM count.
 #include "gvm_internal.cuh"
+#include "gvm_ptx.cuh"
 
 namespace {
 
@@ -24,17 +32,20 @@ constexpr int kVisPerThread = 4;
 // Upload-time preprocessing. One thread per visibility.
 // hermitianSymmetry: src/functions.cu:2256-2273 (w is NOT negated there).
 // vis_mod static part: src/functions.cu:2569-2586, 2607.
+// Position in the device arrays: p. Sample it holds: k = perm ? perm[p] : p (tile-sorted upload). uvw_l stays
+// in the caller's order (read-back, fallback conv degridding); everything the kernels stream is in position order.
 __global__ void __launch_bounds__(256) k_prep_channel(
     const double* __restrict__ uvw_m, const float2* __restrict__ Vo_in,
-    const float* __restrict__ w_in, float freq, double deltau, double deltav, double dx_turn,
+    const float* __restrict__ w_in, const uint32_t* __restrict__ perm, float freq, double deltau, double deltav, double dx_turn,
     double dy_turn, long N, long Z, double* __restrict__ uvw_l, uint32_t* __restrict__ cell,
-    float2* __restrict__ frac, float2* __restrict__ Vo, float* __restrict__ w,
+    float2* __restrict__ frac, uint32_t* __restrict__ ccell, float2* __restrict__ Vo, float* __restrict__ w,
     uint64_t* __restrict__ du64, uint64_t* __restrict__ dv64, float* __restrict__ wz,
     float* __restrict__ max_abs_wz, unsigned long long* __restrict__ offgrid) {
-  long k = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long p = blockIdx.x * (long)blockDim.x + threadIdx.x;
   float my_wz = 0.f;
   bool off = false;
-  if (k < Z) {
+  if (p < Z) {
+    const long k = perm ? (long)perm[p] : p;
     double um = uvw_m[3 * k], vm = uvw_m[3 * k + 1], wm = uvw_m[3 * k + 2];
     float2 vo = Vo_in[k];
     if (um > 0.0) {
@@ -48,10 +59,15 @@ __global__ void __launch_bounds__(256) k_prep_channel(
     uvw_l[3 * k] = u;
     uvw_l[3 * k + 1] = v;
     uvw_l[3 * k + 2] = wl;
-    Vo[k] = vo;
+    Vo[p] = vo;
 
     double uv_x = u / deltau;
     double uv_y = v / deltav;
+    // centre cell of the convolutional degridder (degriddingGPU, src/functions.cu:2222-2223), CENTRED grid
+    // coordinates; kept for on-grid samples only (0xFFFFFFFF otherwise: the kernel falls back to uvw_l)
+    const int half = (int)(N / 2);
+    const int jc = (int)(uv_x + (double)half + 0.5);
+    const int kc = (int)(uv_y + (double)half + 0.5);
     if (uv_x < 0.0) uv_x += N;
     if (uv_y < 0.0) uv_y += N;
     const int i1 = __double2int_rd(uv_x);
@@ -60,23 +76,25 @@ __global__ void __launch_bounds__(256) k_prep_channel(
     const double dv = uv_y - j1;
     float wk = w_in[k];
     if (i1 >= 0 && i1 < N && j1 >= 0 && j1 < N) {
-      cell[k] = (uint32_t)i1 | ((uint32_t)j1 << 16);
-      frac[k] = make_float2((float)du, (float)dv);
+      cell[p] = (uint32_t)i1 | ((uint32_t)j1 << 16);
+      frac[p] = make_float2((float)du, (float)dv);
+      ccell[p] = (jc >= 0 && jc < 65536 && kc >= 0 && kc < 65536) ? ((uint32_t)jc | ((uint32_t)kc << 16)) : GVM_CELL_INVALID;
     } else {
-      cell[k] = GVM_CELL_INVALID;
-      frac[k] = make_float2(0.f, 0.f);
+      cell[p] = GVM_CELL_INVALID;
+      frac[p] = make_float2(0.f, 0.f);
+      ccell[p] = GVM_CELL_INVALID;
       wk = 0.0f;  // vis_mod: weight[i] = 0 for samples that fall off the grid
     }
-    w[k] = wk;
+    w[p] = wk;
 
     // phase increment per pixel step, as a 0.64 fixed-point fraction of a turn
     double tu = u * dx_turn;
     double tv = v * dy_turn;
     tu -= floor(tu);
     tv -= floor(tv);
-    du64[k] = __double2ull_rd(tu * 18446744073709551616.0);
-    dv64[k] = __double2ull_rd(tv * 18446744073709551616.0);
-    wz[k] = (float)wl;
+    du64[p] = __double2ull_rd(tu * 18446744073709551616.0);
+    dv64[p] = __double2ull_rd(tv * 18446744073709551616.0);
+    wz[p] = (float)wl;
     my_wz = fabsf((float)wl);
     // Is the sample the centre of a uv cell with w = 0 (output of do_gridding)? Then its phase
     // step per pixel is an integer multiple of 1/N turns and the DFT gradient is an FFT.
@@ -88,6 +106,57 @@ __global__ void __launch_bounds__(256) k_prep_channel(
   my_wz = gvm_warp_max(my_wz);
   if ((threadIdx.x & 31) == 0 && my_wz > 0.f)
     atomicMax(reinterpret_cast<int*>(max_abs_wz), __float_as_int(my_wz));  // non-negative floats order as ints
+}
+
+// ---------------------------------------------------------------------------
+// Tile-sorted upload. Key of a sample: the 32 x 32-cell tile of its vis_mod cell (same fp64 arithmetic as
+// k_prep_channel), or `ntiles` for samples that fall off the grid (they form the last bucket).
+constexpr int kTile = 32;            // cells per tile edge
+constexpr int kChunkV = 1024;        // samples per work item of the tiled degridder
+constexpr int kAlignV = 16;          // an item's streams are bulk-copied from a 16-sample boundary
+constexpr int kStageCap = kChunkV + kAlignV;   // samples a stage can hold
+
+__global__ void __launch_bounds__(256) k_tile_keys(const double* __restrict__ uvw_m, float freq, double deltau,
+                                                   double deltav, long N, long Z, int ntx, uint32_t ntiles,
+                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                   uint32_t* __restrict__ counts) {
+  const long k = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (k >= Z) return;
+  double um = uvw_m[3 * k], vm = uvw_m[3 * k + 1];
+  if (um > 0.0) { um *= -1.0; vm *= -1.0; }
+  double uv_x = gvm_metres_to_lambda(um, freq) / deltau;
+  double uv_y = gvm_metres_to_lambda(vm, freq) / deltav;
+  if (uv_x < 0.0) uv_x += N;
+  if (uv_y < 0.0) uv_y += N;
+  const int i1 = __double2int_rd(uv_x), j1 = __double2int_rd(uv_y);
+  uint32_t key = ntiles;
+  if (i1 >= 0 && i1 < N && j1 >= 0 && j1 < N) key = (uint32_t)(j1 / kTile) * (uint32_t)ntx + (uint32_t)(i1 / kTile);
+  keys[k] = key;
+  vals[k] = (uint32_t)k;
+  atomicAdd(&counts[key], 1u);
+}
+// counts -> number of work items (chunks of kChunkV samples) per bucket
+__global__ void __launch_bounds__(256) k_item_counts(const uint32_t* __restrict__ counts, uint32_t nbuckets,
+                                                     uint32_t* __restrict__ nitems) {
+  const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+  if (t < nbuckets) nitems[t] = (counts[t] + kChunkV - 1) / kChunkV;
+}
+// (bucket, first sample, samples) of every work item, in bucket order
+__global__ void __launch_bounds__(256) k_make_items(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ start,
+                                                    const uint32_t* __restrict__ item_start, uint32_t nbuckets,
+                                                    uint4* __restrict__ items) {
+  const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+  if (t >= nbuckets) return;
+  const uint32_t c = counts[t], s0 = start[t], i0 = item_start[t];
+  for (uint32_t k = 0, i = 0; k < c; k += kChunkV, i++)
+    items[i0 + i] = make_uint4(t, s0 + k, min(c - k, (uint32_t)kChunkV), 0u);
+}
+// out[perm[p]] = in[p]: back to the caller's sample order (gvm_get_vis)
+template <typename T>
+__global__ void __launch_bounds__(256) k_unpermute(const T* __restrict__ in, const uint32_t* __restrict__ perm, long Z,
+                                                   T* __restrict__ out) {
+  const long p = blockIdx.x * 256L + threadIdx.x;
+  if (p < Z) out[perm[p]] = in[p];
 }
 
 // ---------------------------------------------------------------------------
@@ -170,7 +239,8 @@ __global__ void __launch_bounds__(256) k_phase_rotate(float2* __restrict__ data,
 // grid is the full plane with DC at [0,0] (cuFFT output, no shift), so the same cell is read
 // directly at ((j - N/2) mod N, (k - M/2) mod N) — identical for the Hermitian grid of a real image.
 struct GvmConvDegrid {
-  const double* uvw_l;   // [Z][3] wavelengths (after the fold)
+  const double* uvw_l;   // [Z][3] wavelengths (after the fold), in the CALLER's sample order
+  const uint32_t* perm;  // position -> caller's sample index (tile-sorted upload) or null
   const float* table;    // [km][kn] kernel, device
   double deltau, deltav;
   int km, kn, sx, sy;
@@ -232,8 +302,9 @@ __global__ void __launch_bounds__(kVisThreads) k_degrid_chi2(
     float2 vm = make_float2(0.f, 0.f);
     if (kConv) {
       const int half = N / 2;
-      const int jc = (int)(cv.uvw_l[3 * k] / cv.deltau + (double)half + 0.5);
-      const int kc = (int)(cv.uvw_l[3 * k + 1] / cv.deltav + (double)half + 0.5);
+      const long ko = cv.perm ? (long)cv.perm[k] : k;
+      const int jc = (int)(cv.uvw_l[3 * ko] / cv.deltau + (double)half + 0.5);
+      const int kc = (int)(cv.uvw_l[3 * ko + 1] / cv.deltav + (double)half + 0.5);
       for (int m = -cv.sy; m <= cv.sy; m++) {
         const int sk = kc + m;
         if (sk < 0 || sk >= N) continue;
@@ -316,6 +387,198 @@ __global__ void __launch_bounds__(kVisThreads) k_degrid_chi2(
   }
 }
 
+// ---------------------------------------------------------------------------
+// The tiled degridder. Work item = (bucket, first position, count <= kChunkV) over the tile-sorted arrays; a block
+// owns a contiguous run of items, so consecutive items of one tile reuse the staged grid tile. Per item one thread
+// posts the bulk copies of the NEXT item's streams into the other stage (expect_tx on that stage's mbarrier) and the
+// block then consumes the current stage; copies start at the 16-sample boundary below the item so that every address
+// and size is a multiple of 16 bytes (the few foreign samples in front are skipped). Per-sample arithmetic is the
+// same as k_degrid_chi2's, tap for tap.
+struct TiledArgs {
+  const float2* V;
+  const uint32_t* cell;     // bilinear: i1 | j1 << 16
+  const uint32_t* ccell;    // CKernel: jc | kc << 16, centred grid coordinates
+  const float2* frac;
+  const float2* Vo;
+  const float* w;
+  float2* Vr;
+  float2* Vm;
+  const uint4* items;
+  const uint32_t* block_first;   // [blocks + 1] first item of every block (cost-balanced at upload)
+  int N, ntx;
+  uint32_t invalid_bucket;
+};
+
+template <bool kKeepVm, bool kConv>
+__global__ void __launch_bounds__(256) k_degrid_tiled(TiledArgs a, double* __restrict__ partials,
+                                                     float* __restrict__ partial_max, unsigned int* __restrict__ counter,
+                                                     double* __restrict__ out_sum, float* __restrict__ out_max,
+                                                     GvmConvDegrid cv) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ float s_sum[8], s_max[8];
+  __shared__ bool s_last;
+  __shared__ __align__(8) uint64_t s_bar[2];
+  // stage layout (per stage): idx u32[cap] | frac float2[cap] (bilinear only) | Vo float2[cap] | w float[cap]
+  constexpr int kStageBytes = kStageCap * (kConv ? 16 : 24);
+  const int lo_x = kConv ? cv.sx : 0, lo_y = kConv ? cv.sy : 0;
+  const int tw = kTile + (kConv ? 2 * cv.sx + 1 : 1), th = kTile + (kConv ? 2 * cv.sy + 1 : 1);
+  float2* s_tile = reinterpret_cast<float2*>(smem + 2 * kStageBytes);
+  float* s_tab = reinterpret_cast<float*>(s_tile + (size_t)tw * th);
+  auto stage_idx = [&](int st) { return reinterpret_cast<uint32_t*>(smem + st * kStageBytes); };
+  auto stage_frac = [&](int st) { return reinterpret_cast<float2*>(smem + st * kStageBytes + kStageCap * 4); };
+  auto stage_vo = [&](int st) { return reinterpret_cast<float2*>(smem + st * kStageBytes + kStageCap * (kConv ? 4 : 12)); };
+  auto stage_w = [&](int st) { return reinterpret_cast<float*>(smem + st * kStageBytes + kStageCap * (kConv ? 12 : 20)); };
+  const int tid = threadIdx.x;
+  const int N = a.N;
+  if (tid == 0) {
+    gvmptx::mbar_init(gvmptx::smem_addr(&s_bar[0]), 1);
+    gvmptx::mbar_init(gvmptx::smem_addr(&s_bar[1]), 1);
+    gvmptx::fence_barrier_init();
+  }
+  if (kConv)
+    for (int t = tid; t < cv.km * cv.kn; t += 256) s_tab[t] = cv.table[t];
+  __syncthreads();
+
+  const int it0 = (int)a.block_first[blockIdx.x], it1 = (int)a.block_first[blockIdx.x + 1];
+  auto post = [&](int it) {   // one thread: bulk copies of item `it` into stage (it - it0) & 1
+    const uint4 w = a.items[it];
+    const int st = (it - it0) & 1;
+    const uint32_t a0 = w.y & ~(uint32_t)(kAlignV - 1);
+    const uint32_t n = (w.y + w.z - a0 + kAlignV - 1) & ~(uint32_t)(kAlignV - 1);
+    const uint32_t bar = gvmptx::smem_addr(&s_bar[st]);
+    gvmptx::mbar_expect_tx(bar, n * (kConv ? 16u : 24u));
+    gvmptx::bulk_g2s(gvmptx::smem_addr(stage_idx(st)), (kConv ? a.ccell : a.cell) + a0, n * 4u, bar);
+    if (!kConv) gvmptx::bulk_g2s(gvmptx::smem_addr(stage_frac(st)), a.frac + a0, n * 8u, bar);
+    gvmptx::bulk_g2s(gvmptx::smem_addr(stage_vo(st)), a.Vo + a0, n * 8u, bar);
+    gvmptx::bulk_g2s(gvmptx::smem_addr(stage_w(st)), a.w + a0, n * 4u, bar);
+  };
+  if (tid == 0 && it0 < it1) post(it0);
+
+  float acc = 0.f, mx = 0.f;
+  uint32_t staged_bucket = 0xFFFFFFFFu;
+  int x0 = 0, y0 = 0;
+  for (int it = it0; it < it1; it++) {
+    const uint4 wi = a.items[it];
+    const int st = (it - it0) & 1;
+    // the other stage was consumed in the previous iteration (barrier at its end): refill it now
+    if (tid == 0 && it + 1 < it1) post(it + 1);
+    if (wi.x != staged_bucket && wi.x != a.invalid_bucket) {
+      // stage the grid tile (+ halo) of this bucket; rows and columns wrap (the grid is periodic: DC at [0,0])
+      x0 = (int)(wi.x % (uint32_t)a.ntx) * kTile;
+      y0 = (int)(wi.x / (uint32_t)a.ntx) * kTile;
+      for (int t = tid; t < tw * th; t += 256) {
+        const int lr = t / tw, lc = t - lr * tw;
+        int row = y0 - lo_y + lr, col = x0 - lo_x + lc;
+        row += row < 0 ? N : 0; row -= row >= N ? N : 0;
+        col += col < 0 ? N : 0; col -= col >= N ? N : 0;
+        s_tile[t] = __ldg(&a.V[(long)N * row + col]);
+      }
+      staged_bucket = wi.x;
+      __syncthreads();
+    }
+    gvmptx::mbar_wait(gvmptx::smem_addr(&s_bar[st]), (uint32_t)(((it - it0) >> 1) & 1));
+    const uint32_t skip = wi.y & (uint32_t)(kAlignV - 1);
+    const uint32_t* s_idx = stage_idx(st) + skip;
+    const float2* s_fr = stage_frac(st) + skip;
+    const float2* s_vo = stage_vo(st) + skip;
+    const float* s_w = stage_w(st) + skip;
+    for (uint32_t t = tid; t < wi.z; t += 256) {
+      const uint32_t c = s_idx[t];
+      const float2 vo = s_vo[t];
+      const float wk = s_w[t];
+      float2 vm = make_float2(0.f, 0.f);
+      if (kConv) {
+        const int half = N / 2;
+        int jc, kc;
+        if (c != GVM_CELL_INVALID) {
+          jc = (int)(c & 0xFFFFu); kc = (int)(c >> 16);
+        } else {   // off-grid sample: centre from the fp64 coordinates, taps from global memory below
+          const long ko = cv.perm ? (long)cv.perm[wi.y + t] : (long)(wi.y + t);
+          jc = (int)(cv.uvw_l[3 * ko] / cv.deltau + (double)half + 0.5);
+          kc = (int)(cv.uvw_l[3 * ko + 1] / cv.deltav + (double)half + 0.5);
+        }
+        const bool in_tile = wi.x != a.invalid_bucket && c != GVM_CELL_INVALID;
+        // centre in DC-origin coordinates relative to the staged tile
+        const int colc = jc - half;                                   // >= 0 for folded samples
+        const int rowc = kc >= half ? kc - half : kc + N - half;
+        int lr0 = rowc - y0; lr0 += lr0 < 0 ? N : 0;                  // rowc in {j1, j1 + 1 (mod N)}
+        const int lc0 = colc - x0 + lo_x, lrb = lr0 + lo_y;
+        for (int m = -cv.sy; m <= cv.sy; m++) {
+          const int sk = kc + m;
+          if (sk < 0 || sk >= N) continue;
+          for (int n = -cv.sx; n <= cv.sx; n++) {
+            const int sj = jc + n;
+            if (sj < 0 || sj >= N) continue;
+            const float kv = s_tab[cv.kn * (m + cv.sy) + (n + cv.sx)];
+            float2 g;
+            if (in_tile) {
+              g = s_tile[(lrb + m) * tw + (lc0 + n)];
+            } else {
+              const int row = sk >= half ? sk - half : sk + N - half;
+              const int col = sj >= half ? sj - half : sj + N - half;
+              g = __ldg(&a.V[(long)N * row + col]);
+            }
+            vm.x += kv * g.x;
+            vm.y += kv * g.y;
+          }
+        }
+      } else if (c != GVM_CELL_INVALID) {
+        const int li = (int)(c & 0xFFFFu) - x0, lj = (int)(c >> 16) - y0;
+        const float2 f = s_fr[t];
+        const float2 v11 = s_tile[lj * tw + li], v12 = s_tile[(lj + 1) * tw + li];
+        const float2 v21 = s_tile[lj * tw + li + 1], v22 = s_tile[(lj + 1) * tw + li + 1];
+        const float du = f.x, dv = f.y;
+        const float w11 = (1.0f - du) * (1.0f - dv);
+        const float w12 = (1.0f - du) * dv;
+        const float w21 = du * (1.0f - dv);
+        const float w22 = du * dv;
+        vm.x = w11 * v11.x + w12 * v12.x + w21 * v21.x + w22 * v22.x;
+        vm.y = w11 * v11.y + w12 * v12.y + w21 * v21.y + w22 * v22.y;
+      }
+      const float2 vr = make_float2(vo.x - vm.x, vo.y - vm.y);
+      a.Vr[wi.y + t] = vr;
+      if (kKeepVm) a.Vm[wi.y + t] = vm;
+      acc += wk * (vr.x * vr.x + vr.y * vr.y);
+      mx = fmaxf(mx, wk * fmaxf(fabsf(vr.x), fabsf(vr.y)));
+    }
+    __syncthreads();   // stage `st` and (if the next item changes bucket) the tile are free again
+  }
+  acc = gvm_warp_sum(acc);
+  mx = gvm_warp_max(mx);
+  const int warp = tid >> 5, lane = tid & 31;
+  if (lane == 0) { s_sum[warp] = acc; s_max[warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    float sa = lane < 8 ? s_sum[lane] : 0.f;
+    float sm = lane < 8 ? s_max[lane] : 0.f;
+    sa = gvm_warp_sum(sa);
+    sm = gvm_warp_max(sm);
+    if (lane == 0) {
+      partials[blockIdx.x] = (double)sa;
+      partial_max[blockIdx.x] = sm;
+      __threadfence();
+      s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (s_last && warp == 0) {   // fixed-order fp64 finish: deterministic for a given upload
+    __threadfence();
+    double t = 0.0;
+    float m = 0.f;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) {
+      t += partials[b];
+      m = fmaxf(m, partial_max[b]);
+    }
+    t = gvm_warp_sum_d(t);
+    m = gvm_warp_max(m);
+    if (lane == 0) {
+      *out_sum = t;
+      *out_max = m;
+      *counter = 0u;
+    }
+  }
+}
+
 // Combines the per-block sums the way chi2() does on the host
 // (src/functions.cu:4439-4453): float accumulation, optional /Z, 0.5f * total.
 __global__ void k_chi2_combine(const double* __restrict__ sums, const long* __restrict__ Zs,
@@ -334,19 +597,97 @@ __global__ void k_chi2_combine(const double* __restrict__ sums, const long* __re
 
 }  // namespace
 
+// Tile-sort plan of one block: the permutation (position -> caller's index), bucket sizes and the work items of
+// k_degrid_tiled. Nothing is sorted (perm stays null, every kernel sees the caller's order) when the grid is not
+// a multiple of the tile edge, for empty blocks, or with GVM_FORWARD_UNTILED=1.
+static int build_tile_plan(gvm_engine* e, GvmChannel& c, const double* uvw_m_dev, double deltau, double deltav) {
+  const long N = e->cfg.N;
+  static const bool disabled = [] { const char* s = getenv("GVM_FORWARD_UNTILED"); return s && *s == '1'; }();
+  if (disabled || N % kTile != 0 || c.Z <= 0 || c.Z >= ((int64_t)1 << 31)) return 0;
+  const int ntx = (int)(N / kTile);
+  const uint32_t ntiles = (uint32_t)ntx * (uint32_t)ntx, nb = ntiles + 1;   // + the off-grid bucket
+  const size_t Z = (size_t)c.Z;
+  uint32_t *keys = nullptr, *counts = nullptr;   // counts | start | nitems | item_start, nb + 1 words each
+  void* tmp = nullptr;
+  int rc = 1;
+  do {
+    if (cudaMalloc(&keys, Z * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&c.perm, Z * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&counts, 4 * (size_t)(nb + 1) * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&tmp, gvm_sort_temp_bytes(Z) + gvm_scan_temp_bytes(nb + 1)) != cudaSuccess) {
+      gvm_set_error("tile plan: out of device memory for %zu samples", Z);
+      break;
+    }
+    uint32_t *start = counts + (nb + 1), *nitems = start + (nb + 1), *item_start = nitems + (nb + 1);
+    if (cudaMemsetAsync(counts, 0, 4 * (size_t)(nb + 1) * sizeof(uint32_t), e->stream) != cudaSuccess) break;
+    k_tile_keys<<<(unsigned)((Z + 255) / 256), 256, 0, e->stream>>>(uvw_m_dev, c.d.freq, deltau, deltav, N, c.Z, ntx, ntiles,
+                                                                    keys, c.perm, counts);
+    GVM_LAUNCH(e);
+    int bits = 1;
+    while (((uint32_t)1 << bits) <= ntiles) bits++;
+    if (gvm_sort_pairs_u32(keys, c.perm, Z, bits, tmp, e->stream)) break;
+    if (cudaMemcpyAsync(start, counts, (nb + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream) != cudaSuccess) break;
+    if (gvm_exclusive_scan_u32(start, nb + 1, tmp, e->stream)) break;
+    k_item_counts<<<(nb + 255) / 256, 256, 0, e->stream>>>(counts, nb, nitems);
+    if (cudaMemcpyAsync(item_start, nitems, (nb + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream) != cudaSuccess) break;
+    if (gvm_exclusive_scan_u32(item_start, nb + 1, tmp, e->stream)) break;
+    uint32_t total = 0;
+    if (cudaMemcpyAsync(&total, item_start + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) break;
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) break;
+    if (cudaMalloc(&c.items, (size_t)(total ? total : 1) * sizeof(uint4)) != cudaSuccess) break;
+    k_make_items<<<(nb + 255) / 256, 256, 0, e->stream>>>(counts, start, item_start, nb, c.items);
+    GVM_LAUNCH(e);
+    // Contiguous runs of items per block, balanced by COST, not by count: an item moves 40 B per sample and, when
+    // it opens a new bucket, the 9 KB grid tile — sparse outer tiles are all tile, dense central ones all samples.
+    std::vector<uint4> h_items(total);
+    if (total && cudaMemcpyAsync(h_items.data(), c.items, (size_t)total * sizeof(uint4), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) break;
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) break;
+    int blocks = e->sm_count * 3;
+    if (blocks > (int)total) blocks = (int)total;
+    if (blocks > e->red_blocks) blocks = e->red_blocks;
+    if (blocks < 1) blocks = 1;
+    const double tile_cost = (double)(kTile + 1) * (kTile + 1) * sizeof(float2) + 2048.0;   // + fixed per-item overhead
+    double all = 0.0;
+    for (uint32_t i = 0; i < total; i++)
+      all += 40.0 * h_items[i].z + 512.0 + ((i == 0 || h_items[i].x != h_items[i - 1].x) ? tile_cost : 0.0);
+    std::vector<uint32_t> first((size_t)blocks + 1, total);
+    first[0] = 0;
+    double run = 0.0;
+    int b = 1;
+    for (uint32_t i = 0; i < total && b < blocks; i++) {
+      run += 40.0 * h_items[i].z + 512.0 + ((i == 0 || h_items[i].x != h_items[i - 1].x) ? tile_cost : 0.0);
+      while (b < blocks && run >= all * b / blocks) first[b++] = i + 1;
+    }
+    if (cudaMalloc(&c.block_first, ((size_t)blocks + 1) * sizeof(uint32_t)) != cudaSuccess) break;
+    if (cudaMemcpy(c.block_first, first.data(), ((size_t)blocks + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) break;
+    c.tiled_blocks = blocks;
+    c.nitems = (int)total;
+    c.ntx = ntx;
+    c.invalid_bucket = ntiles;
+    rc = 0;
+  } while (0);
+  if (rc && cudaPeekAtLastError() != cudaSuccess) gvm_set_error("tile plan: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaFree(keys); cudaFree(counts); cudaFree(tmp);
+  if (rc) {
+    cudaFree(c.perm); cudaFree(c.items); cudaFree(c.block_first);
+    c.perm = nullptr; c.items = nullptr; c.block_first = nullptr; c.nitems = 0;
+  }
+  return rc;
+}
+
 int gvm_launch_prep_channel(gvm_engine* e, GvmChannel& c, const double* uvw_m_dev,
                             const float2* Vo_dev, const float* w_dev) {
   const gvm_config& g = e->cfg;
   const double deltax = GVM_RPDEG_D * g.DELTAX, deltay = GVM_RPDEG_D * g.DELTAY;  // src/mfs.cu:493-496
   const double deltau = 1.0 / (g.M * deltax), deltav = 1.0 / (g.N * deltay);
+  if (build_tile_plan(e, c, uvw_m_dev, deltau, deltav)) return 1;
   float* d_max = nullptr;
   GVM_CUDA(cudaMalloc(&d_max, 16));
   GVM_CUDA(cudaMemsetAsync(d_max, 0, 16, e->stream));
   unsigned long long* d_off = reinterpret_cast<unsigned long long*>(d_max) + 1;
   const int blocks = (int)((c.Z + 255) / 256);
-  k_prep_channel<<<blocks, 256, 0, e->stream>>>(uvw_m_dev, Vo_dev, w_dev, c.d.freq, deltau, deltav,
+  k_prep_channel<<<blocks, 256, 0, e->stream>>>(uvw_m_dev, Vo_dev, w_dev, c.perm, c.d.freq, deltau, deltav,
                                                  g.DELTAX * GVM_RPDEG_D, g.DELTAY * GVM_RPDEG_D,
-                                                 g.N, c.Z, c.uvw_l, c.cell, c.frac, c.Vo, c.w,
+                                                 g.N, c.Z, c.uvw_l, c.cell, c.frac, c.ccell, c.Vo, c.w,
                                                  c.du64, c.dv64, c.wz, d_max, d_off);
   GVM_LAUNCH(e);
   GVM_CUDA(cudaGetLastError());
@@ -356,6 +697,19 @@ int gvm_launch_prep_channel(gvm_engine* e, GvmChannel& c, const double* uvw_m_de
   GVM_CUDA(cudaStreamSynchronize(e->stream));
   c.offgrid = (long)h_off;
   cudaFree(d_max);
+  return 0;
+}
+
+// dst_dev[caller's index] = src_dev[position] for the per-sample arrays a caller reads back (gvm_get_vis)
+int gvm_unpermute(gvm_engine* e, const GvmChannel& c, const void* src_dev, void* dst_dev, int elem_bytes) {
+  const unsigned blocks = (unsigned)((c.Z + 255) / 256);
+  if (elem_bytes == 4)
+    k_unpermute<uint32_t><<<blocks, 256, 0, e->stream>>>(static_cast<const uint32_t*>(src_dev), c.perm, c.Z, static_cast<uint32_t*>(dst_dev));
+  else if (elem_bytes == 8)
+    k_unpermute<uint2><<<blocks, 256, 0, e->stream>>>(static_cast<const uint2*>(src_dev), c.perm, c.Z, static_cast<uint2*>(dst_dev));
+  else { gvm_set_error("gvm_unpermute: element size %d", elem_bytes); return 1; }
+  GVM_LAUNCH(e);
+  GVM_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -423,8 +777,6 @@ int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, 
                                                        (double)c.d.phs_yobs_pix);
     GVM_LAUNCH(e);
   }
-  long want = (c.Z + (long)kVisThreads * kVisPerThread - 1) / ((long)kVisThreads * kVisPerThread);
-  int blocks = (int)(want < 1 ? 1 : (want > e->red_blocks ? e->red_blocks : want));
   double* partials = e->red_partials + (size_t)slot * e->red_blocks;
   float* pmax = reinterpret_cast<float*>(e->red_partials + (size_t)e->red_slots * e->red_blocks) +
                 (size_t)slot * e->red_blocks;
@@ -432,20 +784,45 @@ int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, 
     GvmConvDegrid cv = {};
     if (e->degrid_table) {
       const double deltax = GVM_RPDEG_D * g.DELTAX, deltay = GVM_RPDEG_D * g.DELTAY;
-      cv.uvw_l = c.uvw_l; cv.table = e->degrid_table;
+      cv.uvw_l = c.uvw_l; cv.perm = c.perm; cv.table = e->degrid_table;
       cv.deltau = 1.0 / (g.M * deltax); cv.deltav = 1.0 / (g.N * deltay);
       cv.km = e->degrid_m; cv.kn = e->degrid_n; cv.sx = e->degrid_sx; cv.sy = e->degrid_sy;
     }
     cv.upix = (double)c.d.phs_xobs_pix / (double)g.M;
     cv.vpix = (double)c.d.phs_yobs_pix / (double)g.N;
+    const bool conv = e->degrid_table != nullptr;
+    if (c.items && !half && (!conv || g.N <= 32768)) {
+      // tiled degridder: grid tile + streams in shared memory, one contiguous run of work items per block
+      const int tw = kTile + (conv ? 2 * cv.sx + 1 : 1), th = kTile + (conv ? 2 * cv.sy + 1 : 1);
+      const size_t smem = 2 * (size_t)kStageCap * (conv ? 16 : 24) + (size_t)tw * th * sizeof(float2) +
+                          (conv ? (size_t)cv.km * cv.kn * sizeof(float) : 0);
+      const int blocks = c.tiled_blocks;
+      TiledArgs a;
+      a.V = e->V; a.cell = c.cell; a.ccell = c.ccell; a.frac = c.frac; a.Vo = c.Vo; a.w = c.w; a.Vr = c.Vr;
+      a.Vm = g.keep_vm ? c.Vm : nullptr;
+      a.items = c.items; a.block_first = c.block_first;
+      a.N = (int)g.N; a.ntx = c.ntx; a.invalid_bucket = c.invalid_bucket;
+#define GVM_TILED(KEEP, CONV)                                                                                       \
+  do {                                                                                                              \
+    GVM_CUDA(cudaFuncSetAttribute(k_degrid_tiled<KEEP, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_degrid_tiled<KEEP, CONV><<<blocks, 256, smem, e->stream>>>(a, partials, pmax, e->red_counter + slot,          \
+                                                                e->red_sum + slot, e->red_max + slot, cv);         \
+  } while (0)
+      if (conv) { if (g.keep_vm) GVM_TILED(true, true); else GVM_TILED(false, true); }
+      else      { if (g.keep_vm) GVM_TILED(true, false); else GVM_TILED(false, false); }
+#undef GVM_TILED
+    } else {
+      long want = (c.Z + (long)kVisThreads * kVisPerThread - 1) / ((long)kVisThreads * kVisPerThread);
+      const int blocks = (int)(want < 1 ? 1 : (want > e->red_blocks ? e->red_blocks : want));
 #define GVM_DEGRID(KEEP, MODE)                                                                     \
   k_degrid_chi2<KEEP, MODE><<<blocks, kVisThreads, 0, e->stream>>>(                                \
       e->V, c.cell, c.frac, c.Vo, c.w, c.Vr, KEEP ? c.Vm : nullptr, c.Z, (int)g.N, partials, pmax, \
       e->red_counter + slot, e->red_sum + slot, e->red_max + slot, cv)
-    if (e->degrid_table) { if (g.keep_vm) GVM_DEGRID(true, kGridConv); else GVM_DEGRID(false, kGridConv); }
-    else if (half)       { if (g.keep_vm) GVM_DEGRID(true, kGridHalf); else GVM_DEGRID(false, kGridHalf); }
-    else                 { if (g.keep_vm) GVM_DEGRID(true, kGridFull); else GVM_DEGRID(false, kGridFull); }
+      if (conv)      { if (g.keep_vm) GVM_DEGRID(true, kGridConv); else GVM_DEGRID(false, kGridConv); }
+      else if (half) { if (g.keep_vm) GVM_DEGRID(true, kGridHalf); else GVM_DEGRID(false, kGridHalf); }
+      else           { if (g.keep_vm) GVM_DEGRID(true, kGridFull); else GVM_DEGRID(false, kGridFull); }
 #undef GVM_DEGRID
+    }
     GVM_LAUNCH(e);
   }
   c.slot = slot;

@@ -38,7 +38,15 @@ struct GvmChannel {
                                // differs from Z when the block is cut into visibility chunks over the ranks
   // SoA, device
   double* uvw_l = nullptr;     // [Z][3] wavelengths after the Hermitian fold (kept for readback / exact checks)
+  // tile-sorted upload (forward.cu): every per-sample array below except uvw_l is stored in TILE order; position p
+  // holds the caller's sample perm[p]. Null: the caller's order (grid not a multiple of the tile, empty block).
+  uint32_t* perm = nullptr;
+  uint4* items = nullptr;      // work items of k_degrid_tiled: (bucket, first position, count, -)
+  uint32_t* block_first = nullptr;   // [tiled_blocks + 1] first item of every block of the tiled degridder
+  int nitems = 0, ntx = 0, tiled_blocks = 0;
+  uint32_t invalid_bucket = 0;
   uint32_t* cell = nullptr;    // i1 | j1 << 16, GVM_CELL_INVALID when outside the grid
+  uint32_t* ccell = nullptr;   // CKernel degridding: centre cell jc | kc << 16 in centred grid coordinates
   float2* frac = nullptr;      // (du, dv) bilinear fractions
   float2* Vo = nullptr;
   float* w = nullptr;
@@ -104,6 +112,8 @@ struct gvm_engine {
   float* grad_stage = nullptr;  // [2][MN]
   std::vector<GvmChannel> chans;
   int64_t launches = 0;
+  int64_t epoch = 0;               // bumped by every call that invalidates captured graphs (gvm_state_epoch)
+  bool capturing = false;          // between gvm_graph_begin and gvm_graph_end
   // telemetry
   std::vector<cudaEvent_t> ev;
   int ev_used = 0;
@@ -237,6 +247,12 @@ int gvm_launch_prep_channel(gvm_engine* e, GvmChannel& c, const double* uvw_m_de
 int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, int flag_opt,
                         int slot);
 int gvm_reduce_finish(gvm_engine* e, int nslots, int normalize, double* out_dev);
+int gvm_unpermute(gvm_engine* e, const GvmChannel& c, const void* src_dev, void* dst_dev, int elem_bytes);
+// sort.cu: hand-written stable radix sort of (u32 key, u32 value) pairs and exclusive scan
+size_t gvm_sort_temp_bytes(size_t n);
+size_t gvm_scan_temp_bytes(size_t n);
+int gvm_sort_pairs_u32(uint32_t* keys, uint32_t* vals, size_t n, int key_bits, void* temp, cudaStream_t stream);
+int gvm_exclusive_scan_u32(uint32_t* data, size_t n, void* temp, cudaStream_t stream);
 // grad_simt.cu
 int gvm_grad_simt(gvm_engine* e, GvmChannel& c, bool exact, int* ksplit_out);
 // grad_umma.cu

@@ -36,6 +36,11 @@ class Fi {
   // asynchronously into result slot `slot` of the engine and returns true (false: not supported);
   // finishFi is what calcFi does once the value is on the host.
   virtual bool enqueueFi(float* p, int slot);
+  // Everything enqueueFi bakes into its launches besides the image pointer (kind, parameters, gate; Chi2: the
+  // scalars it hands to the engine): ObjectiveFunction replays a captured CUDA graph only while the keys match.
+  virtual uint64_t stateKey();
+  // the host-side part of enqueueFi, for evaluations that replay a captured graph instead of launching
+  virtual void noteEnqueued();
   float finishFi(float value);
   // fi.cuh:58-89: penalizatorIndex -1 keeps the current factor; an index past the -Z list
   // disables the term (factor 0); a negative one is a configuration error (print + exit)
@@ -84,6 +89,8 @@ class Chi2 : public Fi {
   void setFgScale(float s) override { fg_scale = s; }
   float getFgScale() override { return fg_scale; }
   bool enqueueFi(float* p, int slot) override;
+  uint64_t stateKey() override;
+  void noteEnqueued() override;
 
  private:
   float* result_dchi2 = nullptr;  // [image_count][M*N]

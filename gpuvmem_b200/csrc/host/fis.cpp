@@ -1,6 +1,7 @@
 // fis.cpp — Fi adapters over the C ABI (see fi.hpp).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "fi.hpp"
 
@@ -58,6 +59,37 @@ bool Fi::enqueueFi(float* p, int slot) {
   enqueued_gate_closed = !(iteration > 0 && penalization_factor);
   if (!enqueued_gate_closed) GVM_CHECK(gvm_prior_value_to_slot(G().engine, kind, p, imageIndex, &pp, slot));
   return true;
+}
+namespace {
+uint64_t mix(uint64_t h, const void* data, size_t n) {   // FNV-1a
+  const unsigned char* b = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+template <typename T> uint64_t mixv(uint64_t h, T v) { return mix(h, &v, sizeof(T)); }
+}  // namespace
+uint64_t Fi::stateKey() {
+  int kind = -1;
+  gvm_prior_params pp;
+  std::memset(&pp, 0, sizeof(pp));
+  priorSpec(&kind, &pp);
+  uint64_t h = mixv(1469598103934665603ull, kind);
+  h = mixv(h, pp.prior_value); h = mixv(h, pp.eta); h = mixv(h, pp.epsilon); h = mixv(h, pp.epsilon_b);
+  h = mixv(h, pp.prior_image_dev); h = mixv(h, imageIndex);
+  return mixv(h, (int)(iteration > 0 && penalization_factor));
+}
+uint64_t Chi2::stateKey() {
+  Globals& g = G();
+  uint64_t h = mixv(1469598103934665603ull, 0x43686932);
+  h = mixv(h, fg_scale); h = mixv(h, g.noise_cut); h = mixv(h, g.threshold); h = mixv(h, g.flag_opt);
+  return mixv(h, (int)normalize);
+}
+void Fi::noteEnqueued() { enqueued_gate_closed = !(iteration > 0 && penalization_factor); }
+void Chi2::noteEnqueued() {
+  Globals& g = G();
+  enqueued_gate_closed = false;
+  GVM_CHECK(gvm_set_scalars(g.engine, fg_scale, g.noise_cut, g.threshold));
+  GVM_CHECK(gvm_set_flag_opt(g.engine, g.flag_opt));
 }
 float Fi::finishFi(float value) {
   if (enqueued_gate_closed) value = 0.0f;

@@ -1,6 +1,7 @@
 #include "objectivefunction.hpp"
 
 #include <chrono>
+#include <cstdint>
 #include <cstdlib>
 
 namespace gpuvmem {
@@ -14,7 +15,19 @@ bool ObjectiveFunction::defaultSingleSync() {
   return !(v && *v == '0');
 }
 
+bool ObjectiveFunction::defaultGraphs() {
+  const char* v = std::getenv("GVM_GRAPHS");
+  return !(v && *v == '0');
+}
+
+void ObjectiveFunction::dropGraphs() {
+  for (GraphEntry& g : graph_cache)
+    if (g.exec && G().engine) gvm_graph_destroy(G().engine, g.exec);
+  graph_cache.clear();
+}
+
 ObjectiveFunction::~ObjectiveFunction() {
+  dropGraphs();
   if (G().engine) devFree(dphi);
 }
 
@@ -33,11 +46,66 @@ float ObjectiveFunction::calcFunction(float* p) {
   // stream synchronisation brings them all back (the reference synchronises several times per term).
   // Terms that do not support it (user plugins) switch the whole evaluation to the reference's loop.
   bool fast = single_sync && fis.size() <= (size_t)GVM_OBJ_SLOTS;
-  size_t enq = 0;
-  for (; fast && enq < fis.size(); enq++) fast = fis[enq]->enqueueFi(p, (int)enq);
+  // Graph path: an evaluation is identified by the image pointer, every term's state and the engine's epoch.
+  // First sight: plain launches (buffers that are created on first use appear). Second sight: the same launches
+  // are captured into a CUDA graph. From then on: one cudaGraphLaunch + one synchronisation per evaluation —
+  // the line search probes the same work buffer hundreds of times (src/f1dim.cu:49-80).
+  GraphEntry* entry = nullptr;
+  if (fast && graphs && G().world <= 1) {
+    uint64_t key = 1469598103934665603ull;
+    auto fold = [&key](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
+    fold((uint64_t)(uintptr_t)p);
+    fold((uint64_t)gvm_state_epoch(G().engine));
+    for (Fi* fi : fis) fold(fi->stateKey());
+    for (GraphEntry& g : graph_cache)
+      if (g.key == key) entry = &g;
+    if (!entry) {
+      if (graph_cache.size() >= 8) {   // evict the least recently used
+        size_t lru = 0;
+        for (size_t i = 1; i < graph_cache.size(); i++)
+          if (graph_cache[i].last_use < graph_cache[lru].last_use) lru = i;
+        if (graph_cache[lru].exec) gvm_graph_destroy(G().engine, graph_cache[lru].exec);
+        graph_cache.erase(graph_cache.begin() + lru);
+      }
+      graph_cache.push_back(GraphEntry());
+      entry = &graph_cache.back();
+      entry->key = key;
+    }
+    entry->seen++;
+    entry->last_use = n_function;
+  }
+  if (entry && entry->exec) {
+    for (Fi* fi : fis) fi->noteEnqueued();
+    GVM_CHECK(gvm_graph_launch(G().engine, entry->exec));
+    n_replays++;
+  } else {
+    const bool capture = entry && entry->seen == 2;
+    if (capture && gvm_graph_begin(G().engine) != 0) entry = nullptr;
+    size_t enq = 0;
+    for (; fast && enq < fis.size(); enq++) fast = fis[enq]->enqueueFi(p, (int)enq);
+    if (capture && entry) {
+      if (fast) GVM_CHECK(gvm_fetch_slots_enqueue(G().engine, (int)fis.size()));
+      void* exec = nullptr;
+      if (gvm_graph_end(G().engine, &exec) == 0 && fast) {
+        entry->exec = exec;
+        GVM_CHECK(gvm_graph_launch(G().engine, exec));   // the capture executed nothing
+      } else {
+        // not capturable (a term allocated or synchronised): stay on plain launches for this key
+        if (exec) gvm_graph_destroy(G().engine, exec);
+        entry->seen = 3;
+        if (fast) {
+          enq = 0;
+          for (; fast && enq < fis.size(); enq++) fast = fis[enq]->enqueueFi(p, (int)enq);
+          if (fast) GVM_CHECK(gvm_fetch_slots_enqueue(G().engine, (int)fis.size()));
+        }
+      }
+    } else if (fast) {
+      GVM_CHECK(gvm_fetch_slots_enqueue(G().engine, (int)fis.size()));
+    }
+  }
   if (fast) {
     double vals[GVM_OBJ_SLOTS];
-    GVM_CHECK(gvm_fetch_slots(G().engine, (int)fis.size(), vals));
+    GVM_CHECK(gvm_fetch_slots_wait(G().engine, (int)fis.size(), vals));
     for (Fi* fi : fis) {
       const float term = fi->finishFi((float)vals[k]);
       fi_values[k++] = fi->get_fivalue();

@@ -39,6 +39,10 @@ class ObjectiveFunction {
   // one host synchronisation per calcFunction (Fi::enqueueFi) instead of one per term; on by default,
   // GVM_SINGLE_SYNC=0 in the environment or setSingleSync(false) selects the reference's per-term loop
   void setSingleSync(bool on) { single_sync = on; }
+  // one CUDA graph per objective evaluation: the second evaluation with the same image pointer and term state is
+  // captured, later ones replay it with a single launch (GVM_GRAPHS=0 or setGraphs(false): plain launches)
+  void setGraphs(bool on) { graphs = on; }
+  long graphReplays() const { return n_replays; }
 
  private:
   std::vector<Fi*> fis;
@@ -52,6 +56,13 @@ class ObjectiveFunction {
   double t_function = 0.0, t_gradient = 0.0;
   bool single_sync = defaultSingleSync();
   static bool defaultSingleSync();
+  // captured objective evaluations, keyed by (image pointer, term states, engine epoch)
+  struct GraphEntry { uint64_t key = 0; void* exec = nullptr; int seen = 0; long last_use = 0; };
+  std::vector<GraphEntry> graph_cache;
+  bool graphs = defaultGraphs();
+  long n_replays = 0;
+  static bool defaultGraphs();
+  void dropGraphs();
 };
 
 }  // namespace gpuvmem

@@ -446,12 +446,19 @@ int gvm_chi2_to_slot(gvm_engine* e, float* I_dev, int normalize, int slot) {
   if (slot < 0 || slot >= GVM_OBJ_SLOTS) { gvm_set_error("gvm_chi2_to_slot: slot %d out of range", slot); return 1; }
   return gvm_chi2_async(e, I_dev, normalize, e->obj_slots + 3 * slot);
 }
-int gvm_fetch_slots(gvm_engine* e, int n, double* values_out) {
+int gvm_fetch_slots_enqueue(gvm_engine* e, int n) {
   if (n < 0 || n > GVM_OBJ_SLOTS) { gvm_set_error("gvm_fetch_slots: %d slots requested", n); return 1; }
   GVM_CUDA(cudaMemcpyAsync(e->h_slots, e->obj_slots, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  return 0;
+}
+int gvm_fetch_slots_wait(gvm_engine* e, int n, double* values_out) {
+  if (n < 0 || n > GVM_OBJ_SLOTS) { gvm_set_error("gvm_fetch_slots: %d slots requested", n); return 1; }
   GVM_CUDA(cudaStreamSynchronize(e->stream));
   for (int i = 0; i < n; i++) values_out[i] = e->h_slots[3 * i];
   return 0;
+}
+int gvm_fetch_slots(gvm_engine* e, int n, double* values_out) {
+  return gvm_fetch_slots_enqueue(e, n) || gvm_fetch_slots_wait(e, n, values_out);
 }
 
 int gvm_prior_grad(gvm_engine* e, int kind, const float* I_dev, int image_index,
@@ -522,6 +529,7 @@ int gvm_build_noise_image_fields(gvm_engine* e, float noise_jypix, int nfields, 
   if (fetch_red(e, v)) { cudaFree(weight); return 1; }
   const float max_weight = (float)v[2];
   e->plan_dirty = true;
+  e->epoch++;
   k_noise_image<<<blocks, kT, 0, e->stream>>>(e->noise, weight, MN, max_weight, noise_jypix);
   GVM_LAUNCH(e);
   float* d_min = nullptr;

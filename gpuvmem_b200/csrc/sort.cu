@@ -220,3 +220,26 @@ int gvm_sort_pairs_u32(uint32_t* keys, uint32_t* vals, size_t n, int key_bits, v
   }
   return 0;
 }
+
+// Test entry (include/gvm_b200.h): the sort on host arrays, in place.
+extern "C" int gvm_sort_pairs_host(int device, uint32_t* keys, uint32_t* vals, int64_t n, int key_bits) {
+  if (n < 0 || key_bits < 1 || key_bits > 32 || !keys || !vals) { gvm_set_error("gvm_sort_pairs_host: bad argument"); return 1; }
+  if (n == 0) return 0;
+  GVM_CUDA(cudaSetDevice(device));
+  uint32_t *dk = nullptr, *dv = nullptr;
+  void* tmp = nullptr;
+  int rc = 1;
+  do {
+    if (cudaMalloc(&dk, n * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&dv, n * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&tmp, gvm_sort_temp_bytes((size_t)n)) != cudaSuccess) { gvm_set_error("gvm_sort_pairs_host: out of device memory"); break; }
+    if (cudaMemcpy(dk, keys, n * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) break;
+    if (cudaMemcpy(dv, vals, n * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) break;
+    if (gvm_sort_pairs_u32(dk, dv, (size_t)n, key_bits, tmp, nullptr)) break;
+    if (cudaMemcpy(keys, dk, n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+    if (cudaMemcpy(vals, dv, n * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+    rc = 0;
+  } while (0);
+  if (rc && cudaPeekAtLastError() != cudaSuccess) gvm_set_error("gvm_sort_pairs_host: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaFree(dk); cudaFree(dv); cudaFree(tmp);
+  return rc;
+}

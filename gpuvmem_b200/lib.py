@@ -93,6 +93,14 @@ SIGNATURES = {
     "gvm_dist_world": (C.c_int, [_P]),
     "gvm_dist_allreduce": (C.c_int, [_P, _P, C.c_int64]),
     "gvm_dist_collectives": (C.c_int64, [_P]),
+    "gvm_fetch_slots_enqueue": (C.c_int, [_P, C.c_int]),
+    "gvm_fetch_slots_wait": (C.c_int, [_P, C.c_int, _P]),
+    "gvm_graph_begin": (C.c_int, [_P]),
+    "gvm_graph_end": (C.c_int, [_P, C.POINTER(_P)]),
+    "gvm_graph_launch": (C.c_int, [_P, _P]),
+    "gvm_graph_destroy": (C.c_int, [_P, _P]),
+    "gvm_state_epoch": (C.c_int64, [_P]),
+    "gvm_sort_pairs_host": (C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int]),
     "gvm_dist_abort": (C.c_int, [_P]),
     "gvm_dist_broadcast": (C.c_int, [_P, _P, C.c_int64, C.c_int]),
     "gvm_weights": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_int64, C.c_int64, C.c_double, C.c_double,

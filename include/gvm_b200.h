@@ -226,6 +226,24 @@ int gvm_chi2_to_slot(gvm_engine* e, float* I_dev, int normalize, int slot);
 int gvm_prior_value_to_slot(gvm_engine* e, int kind, const float* I_dev, int image_index,
                             const gvm_prior_params* p, int slot);
 int gvm_fetch_slots(gvm_engine* e, int n, double* values_out);
+/* The two halves of gvm_fetch_slots: enqueue the device->host copy of the first n slots on the engine stream
+ * (capturable), and wait for it + read the values. */
+int gvm_fetch_slots_enqueue(gvm_engine* e, int n);
+int gvm_fetch_slots_wait(gvm_engine* e, int n, double* values_out);
+
+/* One CUDA graph per objective evaluation (the reference launches ~10 kernels and synchronises several times per
+ * term in every line-search probe, src/f1dim.cu:49-80): everything the engine enqueues on its stream between
+ * gvm_graph_begin and gvm_graph_end — gvm_chi2_to_slot, gvm_prior_value_to_slot, gvm_fetch_slots_enqueue — is
+ * captured instead of executed and instantiated; gvm_graph_launch replays it with ONE launch. The captured calls
+ * must not allocate or synchronise: run the same sequence once un-captured first (beam planes, FFT plans are
+ * created on first use). A graph bakes in every argument (image pointer, scalars, flag_opt) and the engine's
+ * buffers: gvm_state_epoch changes whenever a call invalidates them (blocks added or cleared, noise image, GCF,
+ * degridding kernel, forward mode); compare it before replaying. Single-rank engines only. */
+int gvm_graph_begin(gvm_engine* e);
+int gvm_graph_end(gvm_engine* e, void** graph_exec_out);
+int gvm_graph_launch(gvm_engine* e, void* graph_exec);
+int gvm_graph_destroy(gvm_engine* e, void* graph_exec);
+int64_t gvm_state_epoch(gvm_engine* e);
 /* The gradient host functions: dgi_dev[M*N] = lambda * d(term)/dI, written (not
  * accumulated), like DS/DL1NormK/... write device_DS. */
 int gvm_prior_grad(gvm_engine* e, int kind, const float* I_dev, int image_index,
@@ -334,6 +352,11 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
 int gvm_grid_fetch(double* uvw_out, float* Vo_out, float* w_out);
 /* gvm_grid_block keeps its device work buffers between calls (this thread); this returns them. */
 int gvm_grid_release(void);
+
+/* The engine's own stable radix sort (csrc/sort.cu: the tile-sorted upload of gvm_add_channel and the gridding
+ * path order their samples with it instead of a library sort) on host arrays, in place: n (key, value) pairs by
+ * the low key_bits bits of the key, equal keys keep their input order. For tests. */
+int gvm_sort_pairs_host(int device, uint32_t* keys, uint32_t* vals, int64_t n, int key_bits);
 
 /* ------------------------------------------------------------- telemetry -- */
 /* Number of kernels (ours + cuFFT) launched by the engine since creation. */

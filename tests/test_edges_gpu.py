@@ -6,6 +6,10 @@ the 256-row tile — each against the fp64 oracle. BASELINE.json's full configur
 2048^2 x 10 M) through size-independent properties: Vm + Vr = Vo, chi2 = 1/2 sum w |Vr|^2 recomputed
 in fp64, determinism, accumulation, masked pixels exactly zero, and the tensor-core gradient
 against the fp64 oracle at sampled pixels over ALL 10 M visibilities."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -15,6 +19,7 @@ from gpuvmem_b200.engine import GRAD_SIMT, GRAD_SIMT_EXACT, GRAD_UMMA
 from test_parity_gpu import _cfg, _grad_oracle_sample, _test_image, _torch
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _rel(a, b):
@@ -256,3 +261,54 @@ def test_mosaic_blocks_with_their_own_pointing_and_phase_centres(oracle):
         assert _rel(g2[0].cpu().numpy().reshape(-1)[pix], grad) <= 3e-5
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("n,bits", [(1, 8), (31, 3), (4096, 8), (4097, 13), (1_000_003, 20), (3_000_000, 32)])
+def test_radix_sort_is_stable_and_sorted(n, bits):
+    """csrc/sort.cu: hand-written LSD radix sort used by the tile-sorted upload and the gridding path."""
+    from gpuvmem_b200 import lib
+    L = lib.load_library()
+    rng = np.random.default_rng(n)
+    keys = (rng.integers(0, 1 << min(bits, 31), n, dtype=np.uint64) if bits < 32
+            else rng.integers(0, 1 << 32, n, dtype=np.uint64)).astype(np.uint32)
+    if n > 1000:
+        keys[: n // 3] = keys[0]                       # long runs of equal keys
+    vals = np.arange(n, dtype=np.uint32)
+    k2, v2 = keys.copy(), vals.copy()
+    assert L.gvm_sort_pairs_host(0, k2.ctypes.data, v2.ctypes.data, n, bits) == 0, L.gvm_last_error()
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k2, keys[order])
+    assert np.array_equal(v2, vals[order]), "equal keys must keep their input order"
+
+
+def test_tile_sorted_upload_is_invisible_to_the_caller(oracle):
+    """gvm_add_channel stores the samples in uv-tile order; gvm_get_vis gives every array back in the caller's order,
+    and the tiled degridder (shared-memory grid tile + bulk-copied streams) equals the untiled kernel sample for sample."""
+    torch = _torch()
+    p = synth.make_problem(N=256, nvis=70001, nchan=1, seed=77, grid_fill=2.3)    # |u| / deltau > N for some samples: they fall off the grid
+    outs = []
+    for untiled in ("0", "1"):
+        os.environ["GVM_FORWARD_UNTILED"] = untiled
+        code = ("import os, sys, numpy as np, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+                "from gpuvmem_b200 import Engine, synth\n"
+                "from test_edges_gpu import _test_image\n"
+                "p = synth.make_problem(N=256, nvis=70001, nchan=1, seed=77, grid_fill=2.3)\n"
+                "e = Engine.from_problem(p, keep_vm=True)\n"
+                "I = torch.from_numpy(_test_image(e)).cuda(); chi2 = e.chi2(I)\n"
+                "v = e.get_vis(0, want=('uvw', 'cell', 'Vo', 'Vm', 'Vr', 'w'))\n"
+                "np.savez(sys.argv[1], chi2=chi2, **v); e.close()\n") % (ROOT, os.path.join(ROOT, "tests"))
+        out = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"gvm_tiled_{untiled}.npz")
+        r = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, GVM_FORWARD_UNTILED=untiled))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs.append(np.load(out))
+    os.environ.pop("GVM_FORWARD_UNTILED", None)
+    tiled, plain = outs
+    assert (plain["w"] == 0).sum() > 10, "no off-grid samples in the test problem"
+    for k in ("uvw", "cell", "Vo", "w", "Vm", "Vr"):
+        assert np.array_equal(tiled[k], plain[k]), k
+    assert abs(float(tiled["chi2"]) - float(plain["chi2"])) <= 2e-6 * float(plain["chi2"])   # same terms, other sum order
+    prep = oracle.prep(p.uvw[0], p.Vo[0], p.w[0], float(p.freqs[0]), 1.0 / (p.M * np.deg2rad(p.DELTAX)),
+                       1.0 / (p.N * np.deg2rad(p.DELTAY)), p.N)
+    assert np.array_equal(prep["uvw"].view(np.uint64), tiled["uvw"].view(np.uint64))
+    assert np.array_equal(prep["cell"], tiled["cell"]) or np.array_equal(prep["cell"][prep["w"] > 0], tiled["cell"][prep["w"] > 0])
