@@ -108,6 +108,9 @@ def make_workload(args):
         return synth.config_c3(scale=args.scale), "BASELINE.json configs[2]: MFS 64 channels x 1M visibilities, 2048x2048"
     if args.config == "c4":
         return synth.config_c4(scale=args.scale), "BASELINE.json configs[3]: VLBI-like 4096x4096, 50M visibilities"
+    if args.config == "c4l":
+        return synth.config_c4(scale=args.scale), ("BASELINE.json configs[3] read literally: VLBI-like 4096x4096, 50M UNGRIDDED visibilities, "
+                                                   "PSWF_12D 9x9 convolutional degridding in the forward model, exact DFT gradient")
     if args.config == "c5":
         return synth.config_c5(scale=args.scale), "BASELINE.json configs[4]: gridded mode, Briggs R=0, 8192x8192 grid, 200M visibilities"
     raise SystemExit(f"unknown --config {args.config}")
@@ -122,6 +125,9 @@ WORKLOAD_SETUP = {
     "c3": ("-z 0.001,0.0 -Z 0.01", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN", "Natural", "PillBox2D", (0, 0)),
     # PSWF_12D is a GRIDDING kernel in the reference (it only acts under -g; degriddingGPU is dead code)
     "c4": ("-z 0.001 -Z 0.01 -g 1", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN", "Natural", "PSWF", (9, 9)),
+    # C4 read literally: nothing is gridded; the PSWF table is the DEGRIDDING kernel of the forward model
+    # (gvmh_use_ckernel_degridding: degriddingGPU, src/functions.cu:2205-2254, + its GCF), gradient = tcgen05 DFT
+    "c4l": ("-z 0.001 -Z 0.01", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN", "Natural", "PSWF", (9, 9)),
     # gridded mode: Briggs R = 0 weights, convolutional gridding (-g), then the objective on the gridded samples
     "c5": ("-z 0.001 -Z 0.01 -g 1 -R 0.0", "Chi2:-1:0:0,Entropy:0:0:0", "CG-FRPRMN", "Briggs", "Gaussian2D", (7, 7)),
 }
@@ -203,7 +209,7 @@ def workload_config(name, problem, wl):
     cli, fi_spec, optimizer, scheme, ckernel, ck_size = WORKLOAD_SETUP[name]
     return {"workload": wl, "image": f"{problem.M}x{problem.N}", "visibilities": problem.total_vis(),
             "channels": problem.nchan, "terms": fi_spec, "cli": cli, "optimizer": optimizer, "weighting": scheme,
-            "ckernel": f"{ckernel} {ck_size[0]}x{ck_size[1]}" if "-g" in cli else None}
+            "ckernel": f"{ckernel} {ck_size[0]}x{ck_size[1]}" if ("-g" in cli or name == "c4l") else None}
 
 
 REF_RECON_HANDOFF = "/tmp/gvm_b200_reference_recon_{cfg}.npz"   # reference arm -> this arm, same box
@@ -397,6 +403,8 @@ def measure(ctx, name, scale, steps, warmup, recon_iters, grad_mode=0, lbfgs_k=1
                      nccl_id=ctx.nccl_id())
     if optimizer == "CG-LBFGS":
         s.set_lbfgs_k(lbfgs_k)
+    if name == "c4l":
+        s.use_ckernel_degridding(True)
     stream = torch.cuda.ExternalStream(s.eng.gvm_get_stream(s.engine_handle()), device=local)
     I_host = torch.from_numpy(s.get_image()).pin_memory()
     grad_host = torch.empty(2 * MN).pin_memory()

@@ -24,6 +24,10 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -43,6 +47,10 @@ int load_nccl() {
   GVM_SYM(CommInitRank, "ncclCommInitRank")
   GVM_SYM(AllReduce, "ncclAllReduce")
   GVM_SYM(Broadcast, "ncclBroadcast")
+  GVM_SYM(Send, "ncclSend")
+  GVM_SYM(Recv, "ncclRecv")
+  GVM_SYM(GroupStart, "ncclGroupStart")
+  GVM_SYM(GroupEnd, "ncclGroupEnd")
   GVM_SYM(CommDestroy, "ncclCommDestroy")
   GVM_SYM(CommAbort, "ncclCommAbort")
   GVM_SYM(GetErrorString, "ncclGetErrorString")
@@ -83,6 +91,44 @@ int gvm_dist_broadcast_f32(gvm_engine* e, float* buf, size_t n, int root) {
   if (e->world <= 1) return 0;
   GVM_DIST_ALIVE(e)
   GVM_NCCL(g_nccl.Broadcast(buf, buf, n, ncclFloat, root, (ncclComm_t)e->nccl_comm, e->stream));
+  e->collectives++;
+  return 0;
+}
+// point-to-point and byte-wise collectives of the distributed preprocessing (weights_grid.cu)
+int gvm_dist_send(gvm_engine* e, const void* buf, size_t bytes, int peer) {
+  GVM_DIST_ALIVE(e)
+  GVM_NCCL(g_nccl.Send(buf, bytes, ncclInt8, peer, (ncclComm_t)e->nccl_comm, e->stream));
+  return 0;
+}
+int gvm_dist_recv(gvm_engine* e, void* buf, size_t bytes, int peer) {
+  GVM_DIST_ALIVE(e)
+  GVM_NCCL(g_nccl.Recv(buf, bytes, ncclInt8, peer, (ncclComm_t)e->nccl_comm, e->stream));
+  return 0;
+}
+int gvm_dist_group_begin(gvm_engine* e) {
+  GVM_DIST_ALIVE(e)
+  GVM_NCCL(g_nccl.GroupStart());
+  return 0;
+}
+int gvm_dist_group_end(gvm_engine* e) {
+  GVM_DIST_ALIVE(e)
+  GVM_NCCL(g_nccl.GroupEnd());
+  e->collectives++;
+  return 0;
+}
+int gvm_dist_broadcast_bytes(gvm_engine* e, void* buf, size_t bytes, int root) {
+  if (e->world <= 1) return 0;
+  GVM_DIST_ALIVE(e)
+  GVM_NCCL(g_nccl.Broadcast(buf, buf, bytes, ncclInt8, root, (ncclComm_t)e->nccl_comm, e->stream));
+  e->collectives++;
+  return 0;
+}
+// element-wise max of unsigned words: with disjoint ownership (every word non-zero on at most one rank) this is an
+// exact bit-for-bit merge, which a floating-point sum is not (-0.0 + 0.0 = +0.0)
+int gvm_dist_allreduce_u32_max(gvm_engine* e, uint32_t* buf, size_t n) {
+  if (e->world <= 1) return 0;
+  GVM_DIST_ALIVE(e)
+  GVM_NCCL(g_nccl.AllReduce(buf, buf, n, ncclUint32, ncclMax, (ncclComm_t)e->nccl_comm, e->stream));
   e->collectives++;
   return 0;
 }

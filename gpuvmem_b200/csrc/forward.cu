@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(256) k_prep_channel(
 // Tile-sorted upload. Key of a sample: the 32 x 32-cell tile of its vis_mod cell (same fp64 arithmetic as
 // k_prep_channel), or `ntiles` for samples that fall off the grid (they form the last bucket).
 constexpr int kTile = 32;            // cells per tile edge
-constexpr int kChunkV = 1024;        // samples per work item of the tiled degridder
+constexpr int kChunkV = 384;         // samples per work item of the tiled degridder
+constexpr int kStages = 4;           // shared-memory stages: the streams of the next kStages - 1 items are in flight
 constexpr int kAlignV = 16;          // an item's streams are bulk-copied from a 16-sample boundary
 constexpr int kStageCap = kChunkV + kAlignV;   // samples a stage can hold
 
@@ -417,12 +418,13 @@ __global__ void __launch_bounds__(256) k_degrid_tiled(TiledArgs a, double* __res
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_sum[8], s_max[8];
   __shared__ bool s_last;
-  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ __align__(8) uint64_t s_bar[kStages];
   // stage layout (per stage): idx u32[cap] | frac float2[cap] (bilinear only) | Vo float2[cap] | w float[cap]
   constexpr int kStageBytes = kStageCap * (kConv ? 16 : 24);
+  constexpr int kTileRegs = kConv ? 1 : ((kTile + 1) * (kTile + 1) + 255) / 256;   // bilinear tile elements per thread
   const int lo_x = kConv ? cv.sx : 0, lo_y = kConv ? cv.sy : 0;
   const int tw = kTile + (kConv ? 2 * cv.sx + 1 : 1), th = kTile + (kConv ? 2 * cv.sy + 1 : 1);
-  float2* s_tile = reinterpret_cast<float2*>(smem + 2 * kStageBytes);
+  float2* s_tile = reinterpret_cast<float2*>(smem + kStages * kStageBytes);
   float* s_tab = reinterpret_cast<float*>(s_tile + (size_t)tw * th);
   auto stage_idx = [&](int st) { return reinterpret_cast<uint32_t*>(smem + st * kStageBytes); };
   auto stage_frac = [&](int st) { return reinterpret_cast<float2*>(smem + st * kStageBytes + kStageCap * 4); };
@@ -431,8 +433,7 @@ __global__ void __launch_bounds__(256) k_degrid_tiled(TiledArgs a, double* __res
   const int tid = threadIdx.x;
   const int N = a.N;
   if (tid == 0) {
-    gvmptx::mbar_init(gvmptx::smem_addr(&s_bar[0]), 1);
-    gvmptx::mbar_init(gvmptx::smem_addr(&s_bar[1]), 1);
+    for (int st = 0; st < kStages; st++) gvmptx::mbar_init(gvmptx::smem_addr(&s_bar[st]), 1);
     gvmptx::fence_barrier_init();
   }
   if (kConv)
@@ -440,9 +441,9 @@ __global__ void __launch_bounds__(256) k_degrid_tiled(TiledArgs a, double* __res
   __syncthreads();
 
   const int it0 = (int)a.block_first[blockIdx.x], it1 = (int)a.block_first[blockIdx.x + 1];
-  auto post = [&](int it) {   // one thread: bulk copies of item `it` into stage (it - it0) & 1
+  auto post = [&](int it) {   // one thread: bulk copies of item `it` into stage (it - it0) % kStages
     const uint4 w = a.items[it];
-    const int st = (it - it0) & 1;
+    const int st = (it - it0) % kStages;
     const uint32_t a0 = w.y & ~(uint32_t)(kAlignV - 1);
     const uint32_t n = (w.y + w.z - a0 + kAlignV - 1) & ~(uint32_t)(kAlignV - 1);
     const uint32_t bar = gvmptx::smem_addr(&s_bar[st]);
@@ -452,31 +453,47 @@ __global__ void __launch_bounds__(256) k_degrid_tiled(TiledArgs a, double* __res
     gvmptx::bulk_g2s(gvmptx::smem_addr(stage_vo(st)), a.Vo + a0, n * 8u, bar);
     gvmptx::bulk_g2s(gvmptx::smem_addr(stage_w(st)), a.w + a0, n * 4u, bar);
   };
-  if (tid == 0 && it0 < it1) post(it0);
+  if (tid == 0)
+    for (int it = it0; it < it1 && it < it0 + kStages - 1; it++) post(it);
+
+  // the grid tile (+ halo) of bucket b; rows and columns wrap (the grid is periodic: DC at [0,0])
+  auto tile_elem = [&](uint32_t b, int t) -> float2 {
+    const int bx = (int)(b % (uint32_t)a.ntx) * kTile, by = (int)(b / (uint32_t)a.ntx) * kTile;
+    const int lr = t / tw, lc = t - lr * tw;
+    int row = by - lo_y + lr, col = bx - lo_x + lc;
+    row += row < 0 ? N : 0; row -= row >= N ? N : 0;
+    col += col < 0 ? N : 0; col -= col >= N ? N : 0;
+    return __ldg(&a.V[(long)N * row + col]);
+  };
 
   float acc = 0.f, mx = 0.f;
   uint32_t staged_bucket = 0xFFFFFFFFu;
   int x0 = 0, y0 = 0;
+  uint4 wi = it0 < it1 ? a.items[it0] : make_uint4(0u, 0u, 0u, 0u);
   for (int it = it0; it < it1; it++) {
-    const uint4 wi = a.items[it];
-    const int st = (it - it0) & 1;
-    // the other stage was consumed in the previous iteration (barrier at its end): refill it now
-    if (tid == 0 && it + 1 < it1) post(it + 1);
-    if (wi.x != staged_bucket && wi.x != a.invalid_bucket) {
-      // stage the grid tile (+ halo) of this bucket; rows and columns wrap (the grid is periodic: DC at [0,0])
+    const int st = (it - it0) % kStages;
+    // the stage consumed in the previous iteration is free (barrier at its end): refill it kStages - 1 items ahead
+    if (tid == 0 && it + kStages - 1 < it1) post(it + kStages - 1);
+    const uint4 wn = it + 1 < it1 ? a.items[it + 1] : wi;
+    if (wi.x != staged_bucket && wi.x != a.invalid_bucket) {   // first item of the block (or after the off-grid bucket)
+      for (int t = tid; t < tw * th; t += 256) s_tile[t] = tile_elem(wi.x, t);
+      staged_bucket = wi.x;
       x0 = (int)(wi.x % (uint32_t)a.ntx) * kTile;
       y0 = (int)(wi.x / (uint32_t)a.ntx) * kTile;
-      for (int t = tid; t < tw * th; t += 256) {
-        const int lr = t / tw, lc = t - lr * tw;
-        int row = y0 - lo_y + lr, col = x0 - lo_x + lc;
-        row += row < 0 ? N : 0; row -= row >= N ? N : 0;
-        col += col < 0 ? N : 0; col -= col >= N ? N : 0;
-        s_tile[t] = __ldg(&a.V[(long)N * row + col]);
-      }
-      staged_bucket = wi.x;
       __syncthreads();
     }
-    gvmptx::mbar_wait(gvmptx::smem_addr(&s_bar[st]), (uint32_t)(((it - it0) >> 1) & 1));
+    // bilinear: the NEXT item's tile travels in registers while this item is computed (its latency hides behind the
+    // work below); it is written to shared memory after the barrier that ends this item
+    const bool next_tile = !kConv && wn.x != staged_bucket && wn.x != a.invalid_bucket && it + 1 < it1;
+    float2 tr[kTileRegs];
+    if (next_tile) {
+#pragma unroll
+      for (int r = 0; r < kTileRegs; r++) {
+        const int t = tid + 256 * r;
+        tr[r] = t < tw * th ? tile_elem(wn.x, t) : make_float2(0.f, 0.f);
+      }
+    }
+    gvmptx::mbar_wait(gvmptx::smem_addr(&s_bar[st]), (uint32_t)(((it - it0) / kStages) & 1));
     const uint32_t skip = wi.y & (uint32_t)(kAlignV - 1);
     const uint32_t* s_idx = stage_idx(st) + skip;
     const float2* s_fr = stage_frac(st) + skip;
@@ -542,6 +559,18 @@ __global__ void __launch_bounds__(256) k_degrid_tiled(TiledArgs a, double* __res
       mx = fmaxf(mx, wk * fmaxf(fabsf(vr.x), fabsf(vr.y)));
     }
     __syncthreads();   // stage `st` and (if the next item changes bucket) the tile are free again
+    if (next_tile) {
+#pragma unroll
+      for (int r = 0; r < kTileRegs; r++) {
+        const int t = tid + 256 * r;
+        if (t < tw * th) s_tile[t] = tr[r];
+      }
+      staged_bucket = wn.x;
+      x0 = (int)(wn.x % (uint32_t)a.ntx) * kTile;
+      y0 = (int)(wn.x / (uint32_t)a.ntx) * kTile;
+      __syncthreads();
+    }
+    wi = wn;
   }
   acc = gvm_warp_sum(acc);
   mx = gvm_warp_max(mx);
@@ -641,20 +670,23 @@ static int build_tile_plan(gvm_engine* e, GvmChannel& c, const double* uvw_m_dev
     std::vector<uint4> h_items(total);
     if (total && cudaMemcpyAsync(h_items.data(), c.items, (size_t)total * sizeof(uint4), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) break;
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) break;
-    int blocks = e->sm_count * 3;
+    int blocks = e->sm_count * 4;   // 4 stages x 9.4 KB + 8.5 KB tile = 47 KB: four blocks per SM
     if (blocks > (int)total) blocks = (int)total;
     if (blocks > e->red_blocks) blocks = e->red_blocks;
     if (blocks < 1) blocks = 1;
-    const double tile_cost = (double)(kTile + 1) * (kTile + 1) * sizeof(float2) + 2048.0;   // + fixed per-item overhead
+    // bytes-equivalent cost: streams, a fixed per-item overhead (barriers, mbarrier wait), the tile when the bucket changes
+    const double tile_cost = (double)(kTile + 1) * (kTile + 1) * sizeof(float2) + 4096.0;
+    auto cost = [&](uint32_t i) {
+      return 40.0 * h_items[i].z + 4096.0 + ((i == 0 || h_items[i].x != h_items[i - 1].x) ? tile_cost : 0.0);
+    };
     double all = 0.0;
-    for (uint32_t i = 0; i < total; i++)
-      all += 40.0 * h_items[i].z + 512.0 + ((i == 0 || h_items[i].x != h_items[i - 1].x) ? tile_cost : 0.0);
+    for (uint32_t i = 0; i < total; i++) all += cost(i);
     std::vector<uint32_t> first((size_t)blocks + 1, total);
     first[0] = 0;
     double run = 0.0;
     int b = 1;
     for (uint32_t i = 0; i < total && b < blocks; i++) {
-      run += 40.0 * h_items[i].z + 512.0 + ((i == 0 || h_items[i].x != h_items[i - 1].x) ? tile_cost : 0.0);
+      run += cost(i);
       while (b < blocks && run >= all * b / blocks) first[b++] = i + 1;
     }
     if (cudaMalloc(&c.block_first, ((size_t)blocks + 1) * sizeof(uint32_t)) != cudaSuccess) break;
@@ -794,7 +826,7 @@ int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, 
     if (c.items && !half && (!conv || g.N <= 32768)) {
       // tiled degridder: grid tile + streams in shared memory, one contiguous run of work items per block
       const int tw = kTile + (conv ? 2 * cv.sx + 1 : 1), th = kTile + (conv ? 2 * cv.sy + 1 : 1);
-      const size_t smem = 2 * (size_t)kStageCap * (conv ? 16 : 24) + (size_t)tw * th * sizeof(float2) +
+      const size_t smem = (size_t)kStages * kStageCap * (conv ? 16 : 24) + (size_t)tw * th * sizeof(float2) +
                           (conv ? (size_t)cv.km * cv.kn * sizeof(float) : 0);
       const int blocks = c.tiled_blocks;
       TiledArgs a;

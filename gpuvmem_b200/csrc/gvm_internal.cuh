@@ -141,6 +141,7 @@ struct gvm_engine {
   // 15-45 ms each on a loaded context, and the optimizers allocate work buffers per optimize() call
   std::map<void*, size_t> pool_live;          // pointer -> bytes of every block handed out
   std::multimap<size_t, void*> pool_free;     // bytes -> cached free blocks
+  std::vector<void*> pool_slabs;              // what cudaMalloc returned (blocks are carved out of these)
 };
 
 #define GVM_LAUNCH(e) ((e)->launches++)
@@ -272,6 +273,12 @@ double gvm_wterm_cross_bound(const gvm_engine* e, const GvmChannel& c);
 int gvm_dist_allreduce_f32(gvm_engine* e, float* buf, size_t n);
 int gvm_dist_allreduce_f64(gvm_engine* e, double* buf, size_t n);
 int gvm_dist_broadcast_f32(gvm_engine* e, float* buf, size_t n, int root);
+int gvm_dist_send(gvm_engine* e, const void* buf, size_t bytes, int peer);
+int gvm_dist_recv(gvm_engine* e, void* buf, size_t bytes, int peer);
+int gvm_dist_group_begin(gvm_engine* e);
+int gvm_dist_group_end(gvm_engine* e);
+int gvm_dist_broadcast_bytes(gvm_engine* e, void* buf, size_t bytes, int root);
+int gvm_dist_allreduce_u32_max(gvm_engine* e, uint32_t* buf, size_t n);
 // a rank that fails locally before a collective tears the communicator down so that its peers error out of
 // their pending collective instead of waiting for it forever
 void gvm_dist_abort_comm(gvm_engine* e);

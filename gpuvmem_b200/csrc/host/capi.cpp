@@ -187,6 +187,10 @@ int gvmh_write_outputs(gvmh_session* s) {
   return 0;
 }
 
+int gvmh_use_ckernel_degridding(gvmh_session* s, int on) {
+  s->mfs->useCKernelDegridding(on != 0);
+  return 0;
+}
 int gvmh_write_residuals(gvmh_session* s, float* nongridded_chi2) {
   s->sy->writeResiduals();
   if (nongridded_chi2) *nongridded_chi2 = s->mfs->getNonGriddedChi2();

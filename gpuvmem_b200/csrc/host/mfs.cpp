@@ -612,6 +612,22 @@ void MFS::setDevice() {
   der.setup_seconds = wallSeconds() - t_start;
 }
 
+void MFS::useCKernelDegridding(bool on) {
+  Globals& g = G();
+  if (!on || !ckernel) {
+    GVM_CHECK(gvm_set_degrid_kernel(g.engine, nullptr, 0, 0, 0, 0));
+    if (!gridding) GVM_CHECK(gvm_set_gcf(g.engine, nullptr));
+    return;
+  }
+  const double deltax = RPDEG_D * g.DELTAX, deltay = RPDEG_D * g.DELTAY;
+  ckernel->setSigmas(std::fabs(g.deltau), std::fabs(g.deltav));
+  ckernel->buildKernel();
+  ckernel->initializeGCF(g.M, g.N, std::fabs(deltax), std::fabs(deltay));
+  GVM_CHECK(gvm_set_degrid_kernel(g.engine, ckernel->getKernelPointer(), ckernel->getm(), ckernel->getn(),
+                                  ckernel->getSupportX(), ckernel->getSupportY()));
+  GVM_CHECK(gvm_set_gcf(g.engine, ckernel->getGCFCPUPointer()));
+}
+
 void MFS::clearRun() {
   Globals& g = G();
   devUpload(device_Image, host_I.data(), (size_t)g.M * g.N * g.image_count);

@@ -115,6 +115,10 @@ class MFS : public Synthesizer {
   void setDistributed(int rank, int world, const std::string& nccl_id);
   std::vector<MSDataset>& getDatasets() { return datasets; }
   float getNonGriddedChi2() const { return nongridded_chi2; }
+  // Forward-model option: the gridding kernel handed to setGriddingKernel is used as a
+  // convolutional DEGRIDDING kernel on the ungridded samples (degriddingGPU, src/functions.cu:2205-2254) with its
+  // gridding-correction image in front of the FFT, instead of the bilinear vis_mod. Call after setDevice.
+  void useCKernelDegridding(bool on);
   // scalars derived in configure/setDevice (parity tests compare them with the reference's)
   struct Derived {
     double beam_bmaj_deg = 0, beam_bmin_deg = 0, beam_bpa_deg = 0, deltau = 0, deltav = 0;

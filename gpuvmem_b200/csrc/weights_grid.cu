@@ -5,7 +5,7 @@
 // and do_gridding (src/functions.cu:1339-1653). Both accumulate fp32 sums sample by sample
 // (under `omp critical` / `omp atomic`), so the result depends on the order; the only
 // deterministic reference order is the single-thread one (ascending sample index). It is
-// reproduced exactly: samples are STABLY radix-sorted by grid cell (cub) and every cell is summed
+// reproduced exactly: samples are STABLY radix-sorted by grid cell (sort.cu, hand-written) and every cell is summed
 // sequentially in ascending sample order by one thread; all fp32 arithmetic uses explicit
 // round-to-nearest intrinsics so that nvcc cannot contract what gcc does not (the reference's
 // host code is compiled for baseline x86-64: separate multiply and add). Cell indices use the
@@ -17,8 +17,6 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
-
-#include <cub/cub.cuh>
 
 #include "gvm_internal.cuh"
 
@@ -440,18 +438,31 @@ thread_local GridResult g_grid_result;
 // work buffers of gvm_grid_block, kept between calls (a cudaMalloc/cudaFree pair of several GB per
 // block costs more than the kernels); gvm_grid_release() returns them
 struct GridWork {
-  DevBuf uvw, Vo, w, ck, k0, k1, v0, v1, tmp, gw, gV, flags, pos, start;
-  DevBuf cpos, cnt, off, rec, tstart, tend, ord0, ord1, ordk0, ordk1;   // tile-sequential path
+  DevBuf uvw, Vo, w, ck, k0, v0, tmp, gw, gV, flags, pos, start;
+  DevBuf cpos, cnt, off, rec, tstart, tend, ord0, ordk0;   // tile-sequential path
+  DevBuf sk, srec, rk, rrec, dk, dv;                        // distributed gridding: send / receive buffers
 };
 thread_local GridWork g_grid_work;
 
-int sort_pairs(DevBuf& tmp, uint32_t* k_in, uint32_t* k_out, uint32_t* v_in, uint32_t* v_out, long n,
-               int end_bit) {
-  size_t bytes = 0;
-  WG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit));
-  if (tmp.ensure(bytes)) return 1;
-  WG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit));
-  return 0;
+// stable in-place sort of (key, value) pairs by the low end_bit bits of the key (sort.cu)
+int sort_pairs(DevBuf& tmp, uint32_t* keys, uint32_t* vals, long n, int end_bit, cudaStream_t stream = nullptr) {
+  if (n <= 0) return 0;
+  if (tmp.ensure(gvm_sort_temp_bytes((size_t)n))) return 1;
+  return gvm_sort_pairs_u32(keys, vals, (size_t)n, end_bit, tmp.p, stream);
+}
+// out = exclusive prefix sum of in (n 32-bit counts; out may alias in)
+int exclusive_scan(DevBuf& tmp, const void* in, void* out, long n, cudaStream_t stream = nullptr) {
+  if (n <= 0) return 0;
+  if (tmp.ensure(gvm_scan_temp_bytes((size_t)n))) return 1;
+  if (out != in) WG_CUDA(cudaMemcpyAsync(out, in, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+  return gvm_exclusive_scan_u32(static_cast<uint32_t*>(out), (size_t)n, tmp.p, stream);
+}
+__global__ void __launch_bounds__(256) k_max_int(const int* __restrict__ v, long n, int* __restrict__ out) {
+  int m = 0;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < n; i += (long)gridDim.x * 256) m = max(m, v[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
 // GVM_GRID_TIMING=1: wall time of the phases of gvm_grid_block / gvm_weights on stderr (device-synchronised)
@@ -496,46 +507,35 @@ int grid_tiles_path(GridWork& wk, long Z, float freq, double deltau, double delt
     k_tile_count<<<blocks, 256>>>(wk.uvw.as<double>(), Z, freq, deltau, deltav, M, N, sx, sy, wk.cpos.as<uint32_t>(),
                                   wk.cnt.as<int>());
     WG_CUDA(cudaGetLastError());
-    size_t sb = 0;
-    WG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, wk.cnt.as<int>(), wk.off.as<int>(), (int)n2));
-    if (wk.tmp.ensure(sb)) return 1;
-    WG_CUDA(cub::DeviceScan::ExclusiveSum(wk.tmp.p, sb, wk.cnt.as<int>(), wk.off.as<int>(), (int)n2));
+    if (exclusive_scan(wk.tmp, wk.cnt.p, wk.off.p, n2)) return 1;
     int last_off = 0, last_cnt = 0;
     WG_CUDA(cudaMemcpy(&last_off, wk.off.as<int>() + (n2 - 1), 4, cudaMemcpyDeviceToHost));
     WG_CUDA(cudaMemcpy(&last_cnt, wk.cnt.as<int>() + (n2 - 1), 4, cudaMemcpyDeviceToHost));
     npairs = (long)last_off + last_cnt;
     if (npairs > 0) {
-      if (wk.k0.ensure((size_t)npairs * 4) || wk.k1.ensure((size_t)npairs * 4) || wk.v0.ensure((size_t)npairs * 4) ||
-          wk.v1.ensure((size_t)npairs * 4) || wk.rec.ensure((size_t)npairs * 16))
-        return 1;
+      if (wk.k0.ensure((size_t)npairs * 4) || wk.v0.ensure((size_t)npairs * 4) || wk.rec.ensure((size_t)npairs * 16)) return 1;
       k_tile_emit<<<blocks, 256>>>(wk.cpos.as<uint32_t>(), wk.off.as<int>(), n2, M, N, sx, sy, ntx, wk.k0.as<uint32_t>(),
                                    wk.v0.as<uint32_t>());
       WG_CUDA(cudaGetLastError());
       int bits = 1;
       while ((1L << bits) < ntiles) bits++;
-      if (sort_pairs(wk.tmp, wk.k0.as<uint32_t>(), wk.k1.as<uint32_t>(), wk.v0.as<uint32_t>(), wk.v1.as<uint32_t>(), npairs,
-                     bits))
-        return 1;
-      k_tile_gather<<<(int)((npairs + 255) / 256), 256>>>(wk.k1.as<uint32_t>(), wk.v1.as<uint32_t>(), npairs, Z,
+      if (sort_pairs(wk.tmp, wk.k0.as<uint32_t>(), wk.v0.as<uint32_t>(), npairs, bits)) return 1;
+      k_tile_gather<<<(int)((npairs + 255) / 256), 256>>>(wk.k0.as<uint32_t>(), wk.v0.as<uint32_t>(), npairs, Z,
                                                           wk.cpos.as<uint32_t>(), wk.Vo.as<float2>(), wk.w.as<float>(),
                                                           wk.tstart.as<int>(), wk.tend.as<int>(), wk.rec.as<float4>());
       WG_CUDA(cudaGetLastError());
     }
   }
   // replay order: tiles by decreasing sample count
-  if (wk.ord0.ensure((size_t)ntiles * 4) || wk.ord1.ensure((size_t)ntiles * 4) || wk.ordk0.ensure((size_t)ntiles * 4) ||
-      wk.ordk1.ensure((size_t)ntiles * 4))
-    return 1;
+  if (wk.ord0.ensure((size_t)ntiles * 4) || wk.ordk0.ensure((size_t)ntiles * 4)) return 1;
   k_tile_order_keys<<<(int)((ntiles + 255) / 256), 256>>>(wk.tstart.as<int>(), wk.tend.as<int>(), ntiles,
                                                           wk.ordk0.as<uint32_t>(), wk.ord0.as<uint32_t>());
   WG_CUDA(cudaGetLastError());
-  if (sort_pairs(wk.tmp, wk.ordk0.as<uint32_t>(), wk.ordk1.as<uint32_t>(), wk.ord0.as<uint32_t>(), wk.ord1.as<uint32_t>(),
-                 ntiles, 31))
-    return 1;
+  if (sort_pairs(wk.tmp, wk.ordk0.as<uint32_t>(), wk.ord0.as<uint32_t>(), ntiles, 31)) return 1;
   const int taps = (2 * sx + 1) * (2 * sy + 1);
   const int rounds = (taps + 31) / 32;
 #define GVM_GRID_TILES(R)                                                                                       \
-  k_grid_tiles<R><<<(unsigned)ntiles, 32>>>(wk.ord1.as<uint32_t>(), wk.tstart.as<int>(), wk.tend.as<int>(),      \
+  k_grid_tiles<R><<<(unsigned)ntiles, 32>>>(wk.ord0.as<uint32_t>(), wk.tstart.as<int>(), wk.tend.as<int>(),      \
                                             wk.rec.as<float4>(), wk.ck.as<float>(), ck_m, ck_n, sx, sy, M, N,    \
                                             ntx, wk.gw.as<float>(), wk.gV.as<float2>())
   if (rounds <= 1) GVM_GRID_TILES(1);
@@ -608,14 +608,14 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
   int end_bit = 1;
   while (end_bit < 32 && (1ull << end_bit) <= MN) end_bit++;
   end_bit = 32;  // the off-grid sentinel is all ones: sort on all 32 bits
-  DevBuf d_grid, d_uvw, d_w, d_k0, d_k1, d_v0, d_v1, d_tmp;
+  DevBuf d_grid, d_uvw, d_w, d_k0, d_v0, d_tmp;
   if (d_grid.ensure(MN * 4)) return 1;
   WG_CUDA(cudaMemset(d_grid.p, 0, MN * 4));
   long zmax = 1;
   for (int b = 0; b < nblocks; b++) zmax = Z[b] > zmax ? (long)Z[b] : zmax;
   if (zmax >= (long)0x7FFFFFFF) { gvm_set_error("gvm_weights: block too large"); return 1; }
   if (d_uvw.ensure((size_t)zmax * 24) || d_w.ensure((size_t)zmax * 4) || d_k0.ensure((size_t)zmax * 4) ||
-      d_k1.ensure((size_t)zmax * 4) || d_v0.ensure((size_t)zmax * 4) || d_v1.ensure((size_t)zmax * 4))
+      d_v0.ensure((size_t)zmax * 4))
     return 1;
 
   auto load_and_sort = [&](int b) -> int {
@@ -625,8 +625,7 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
     k_weight_cells<<<(int)((z + 255) / 256), 256>>>(d_uvw.as<double>(), z, freqs[b], adu, adv, M, N,
                                                     d_k0.as<uint32_t>(), d_v0.as<uint32_t>());
     WG_CUDA(cudaGetLastError());
-    return sort_pairs(d_tmp, d_k0.as<uint32_t>(), d_k1.as<uint32_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(), z,
-                      end_bit);
+    return sort_pairs(d_tmp, d_k0.as<uint32_t>(), d_v0.as<uint32_t>(), z, end_bit);
   };
 
   float f_squared = 0.0f;
@@ -642,7 +641,7 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
       const long z = (long)Z[b];
       if (z > 0) {
         if (load_and_sort(b)) return 1;
-        k_cell_accumulate<<<(int)((z + 255) / 256), 256>>>(d_k1.as<uint32_t>(), d_v1.as<uint32_t>(), z,
+        k_cell_accumulate<<<(int)((z + 255) / 256), 256>>>(d_k0.as<uint32_t>(), d_v0.as<uint32_t>(), z,
                                                            d_w.as<float>(), d_grid.as<float>());
         WG_CUDA(cudaGetLastError());
       }
@@ -663,11 +662,11 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
     if (z > 0) {
       if (!sorted_resident && load_and_sort(b)) return 1;
       const int blocks = (int)((z + 255) / 256);
-      k_cell_accumulate<<<blocks, 256>>>(d_k1.as<uint32_t>(), d_v1.as<uint32_t>(), z, d_w.as<float>(),
+      k_cell_accumulate<<<blocks, 256>>>(d_k0.as<uint32_t>(), d_v0.as<uint32_t>(), z, d_w.as<float>(),
                                          d_grid.as<float>());
-      k_weight_apply<<<blocks, 256>>>(d_k1.as<uint32_t>(), d_v1.as<uint32_t>(), z, d_grid.as<float>(),
+      k_weight_apply<<<blocks, 256>>>(d_k0.as<uint32_t>(), d_v0.as<uint32_t>(), z, d_grid.as<float>(),
                                       scheme == GVM_W_BRIGGS, f_squared, d_w.as<float>());
-      k_clear_cells<<<blocks, 256>>>(d_k1.as<uint32_t>(), z, d_grid.as<float>());
+      k_clear_cells<<<blocks, 256>>>(d_k0.as<uint32_t>(), z, d_grid.as<float>());
       WG_CUDA(cudaGetLastError());
       if (gvm_fast_d2h(w[b], d_w.p, (size_t)z * 4, 0)) return 1;
     }
@@ -701,16 +700,14 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
   *nout = 0;
   PhaseTimer pt;
   GridWork& wk = g_grid_work;
-  DevBuf &d_uvw = wk.uvw, &d_Vo = wk.Vo, &d_w = wk.w, &d_ck = wk.ck, &d_k0 = wk.k0, &d_k1 = wk.k1, &d_v0 = wk.v0,
-         &d_v1 = wk.v1, &d_tmp = wk.tmp, &d_gw = wk.gw, &d_gV = wk.gV, &d_flags = wk.flags, &d_pos = wk.pos,
-         &d_start = wk.start;
+  DevBuf &d_uvw = wk.uvw, &d_Vo = wk.Vo, &d_w = wk.w, &d_ck = wk.ck, &d_k0 = wk.k0, &d_v0 = wk.v0,
+         &d_tmp = wk.tmp, &d_gw = wk.gw, &d_gV = wk.gV, &d_flags = wk.flags, &d_pos = wk.pos, &d_start = wk.start;
   GridResult& res = g_grid_result;   // compacted output stays on the device until it is fetched
   DevBuf &d_uo = res.uvw, &d_Vout = res.Vo, &d_wo = res.w;
   res.count = 0;
   const size_t zz = (size_t)(Z > 0 ? Z : 1);
   if (d_uvw.ensure(zz * 24) || d_Vo.ensure(zz * 8) || d_w.ensure(zz * 4) || d_ck.ensure((size_t)ck_m * ck_n * 4) ||
-      d_k0.ensure(2 * zz * 4) || d_k1.ensure(2 * zz * 4) || d_v0.ensure(2 * zz * 4) || d_v1.ensure(2 * zz * 4) ||
-      d_gw.ensure(MN * 4) || d_gV.ensure(MN * 8) || d_flags.ensure(MN * 4) || d_pos.ensure(MN * 4))
+      d_k0.ensure(2 * zz * 4) || d_v0.ensure(2 * zz * 4) || d_gw.ensure(MN * 4) || d_gV.ensure(MN * 8) || d_flags.ensure(MN * 4) || d_pos.ensure(MN * 4))
     return 1;
   if (Z > 0) {
   pt.mark("grid: device buffers");
@@ -733,23 +730,20 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
                                                        support_x, support_y, d_k0.as<uint32_t>(),
                                                        d_v0.as<uint32_t>());
       WG_CUDA(cudaGetLastError());
-      if (sort_pairs(d_tmp, d_k0.as<uint32_t>(), d_k1.as<uint32_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(), n2, 32))
-        return 1;
+      if (sort_pairs(d_tmp, d_k0.as<uint32_t>(), d_v0.as<uint32_t>(), n2, 32)) return 1;
     }
     // start table over the extended grid (ext + 1 entries): histogram of the centre cells + exclusive scan
     if (d_start.ensure((ext + 2) * 4)) return 1;
     WG_CUDA(cudaMemset(d_start.p, 0, (ext + 2) * 4));
     if (n2 > 0) {
-      k_cell_count<<<(int)((n2 + 255) / 256), 256>>>(d_k1.as<uint32_t>(), n2, d_start.as<int>());
+      k_cell_count<<<(int)((n2 + 255) / 256), 256>>>(d_k0.as<uint32_t>(), n2, d_start.as<int>());
       WG_CUDA(cudaGetLastError());
     }
     {
       // the merge kernel packs a list's remaining count into 32 - kTapBits bits
-      size_t mb = 0;
       int* d_maxc = d_flags.as<int>();     // free until k_grid_flags
-      WG_CUDA(cub::DeviceReduce::Max(nullptr, mb, d_start.as<int>(), d_maxc, (int)(ext + 1)));
-      if (d_tmp.ensure(mb)) return 1;
-      WG_CUDA(cub::DeviceReduce::Max(d_tmp.p, mb, d_start.as<int>(), d_maxc, (int)(ext + 1)));
+      WG_CUDA(cudaMemset(d_maxc, 0, 4));
+      k_max_int<<<1024, 256>>>(d_start.as<int>(), (long)(ext + 1), d_maxc);
       int maxc = 0;
       WG_CUDA(cudaMemcpy(&maxc, d_maxc, 4, cudaMemcpyDeviceToHost));
       if (maxc >= (1 << (32 - kTapBits))) {
@@ -757,12 +751,7 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
         return 1;
       }
     }
-    {
-      size_t sb = 0;
-      WG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, d_start.as<int>(), d_start.as<int>(), (int)(ext + 1)));
-      if (d_tmp.ensure(sb)) return 1;
-      WG_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, sb, d_start.as<int>(), d_start.as<int>(), (int)(ext + 1)));
-    }
+    if (exclusive_scan(d_tmp, d_start.p, d_start.p, (long)(ext + 1))) return 1;
     {
       // threads per CTA from the tap count: 12 bytes of shared state per (thread, tap)
       const int taps = (2 * support_x + 1) * (2 * support_y + 1);
@@ -771,7 +760,7 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
       const size_t smem = (size_t)taps * (T) * 3 * sizeof(uint32_t);                                           \
       WG_CUDA(cudaFuncSetAttribute(k_grid_accumulate<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_grid_accumulate<T><<<(int)((MN + (T) - 1) / (T)), (T), smem>>>(                                        \
-          d_start.as<int>(), d_v1.as<uint32_t>(), n2, (long)Z, d_Vo.as<float2>(), d_w.as<float>(),             \
+          d_start.as<int>(), d_v0.as<uint32_t>(), n2, (long)Z, d_Vo.as<float2>(), d_w.as<float>(),             \
           d_ck.as<float>(), ck_m, ck_n, support_x, support_y, M, N, taps, d_gw.as<float>(), d_gV.as<float2>()); \
     } while (0)
       if (taps <= 49) GVM_GRID_ACC(128);
@@ -783,10 +772,7 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
   }
   k_grid_flags<<<(int)((MN + 255) / 256), 256>>>(d_gw.as<float>(), (long)MN, d_flags.as<int>());
   pt.mark("grid: merge path / flags");
-  size_t bytes = 0;
-  WG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, d_flags.as<int>(), d_pos.as<int>(), (int)MN));
-  if (d_tmp.ensure(bytes)) return 1;
-  WG_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, bytes, d_flags.as<int>(), d_pos.as<int>(), (int)MN));
+  if (exclusive_scan(d_tmp, d_flags.p, d_pos.p, (long)MN)) return 1;
   int last_pos = 0, last_flag = 0;
   WG_CUDA(cudaMemcpy(&last_pos, d_pos.as<int>() + (MN - 1), 4, cudaMemcpyDeviceToHost));
   WG_CUDA(cudaMemcpy(&last_flag, d_flags.as<int>() + (MN - 1), 4, cudaMemcpyDeviceToHost));

@@ -45,6 +45,7 @@ SIGNATURES = {
     "gvmh_clear_run": (C.c_int, [_P]),
     "gvmh_set_lbfgs_k": (C.c_int, [_P, C.c_int]),
     "gvmh_write_outputs": (C.c_int, [_P]),
+    "gvmh_use_ckernel_degridding": (C.c_int, [_P, C.c_int]),
     "gvmh_write_residuals": (C.c_int, [_P, _P]),
     "gvmh_get_host_model": (C.c_int, [_P, C.c_int, _P, _P]),
     "gvmh_fits_read": (C.c_int, [C.c_char_p, _P, _P, C.c_int64]),
@@ -264,6 +265,9 @@ class Session:
                                  None if after is None else after.ctypes.data)
         assert rc == 0, rc
         return val.value, dphi.reshape(I.shape), (None if after is None else after.reshape(N, N))
+
+    def use_ckernel_degridding(self, on=True):
+        self.h.gvmh_use_ckernel_degridding(self.s, int(on))
 
     def write_residuals(self):
         """MFS::writeResiduals; returns (non-gridded 0.5*chi2 or 0, [per channel dict(uvw, Vo, w, Vm, Vr)])."""

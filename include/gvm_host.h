@@ -68,6 +68,11 @@ int gvmh_run(gvmh_session* s, float* image_out, double* optimize_seconds);
 int gvmh_clear_run(gvmh_session* s);
 int gvmh_set_lbfgs_k(gvmh_session* s, int k);
 int gvmh_write_outputs(gvmh_session* s);   /* writeImages + writeResiduals */
+/* Forward-model option: use the session's CKernel (gvmh_create's ckernel / ck_m / ck_n) as a convolutional DEGRIDDING
+ * kernel on the ungridded samples — what the reference sketches in degriddingGPU (src/functions.cu:2205-2254) — with
+ * its gridding-correction image (apply_GCF, :2468) in front of the FFT; the gradient stays the exact DFT. on = 0
+ * restores the bilinear vis_mod. This is BASELINE config 4 read literally ("PSWF_12D degridding kernel"). */
+int gvmh_use_ckernel_degridding(gvmh_session* s, int on);
 /* MFS::writeResiduals alone (src/mfs.cu:1115-1155): weights restored / original samples brought back
  * (getOriginalVisibilitiesBack, src/functions.cu:1844-2010) and re-evaluated, then modelToHost
  * (src/MSFITSIO.cu:1114-1138). nongridded_chi2 (optional): the "Non-gridded chi2" of a gridded run, else 0.
