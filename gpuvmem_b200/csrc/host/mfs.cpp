@@ -321,6 +321,10 @@ void MFS::configure(int argc, char** argv) {
   der.deltau = g.deltau;
   der.deltav = g.deltav;
 
+  // The engine (per-GPU scratch, cuFFT plan, NCCL communicator) is created here rather than in setDevice: with
+  // several ranks the weighting and the gridding below are already distributed and need the communicator.
+  createEngine();
+
   if (!scheme) scheme = createObject<WeightingScheme, std::string>("Natural");
   if (gridding) scheme->setThreads(griddingThreads);
   scheme->configure(&g.robust_param);
@@ -376,10 +380,15 @@ void MFS::doGridding() {
           const HVis& in = sf.visibilities[i][s];
           HVis& v = f.visibilities[i][s];
           int64_t nout = 0;
-          GVM_CHECK(gvm_grid_block(g.firstgpu, g.M, g.N, g.deltau, g.deltav, f.nu[i], (int64_t)in.size(),
-                                   in.uvw.data(), in.Vo.data(), in.weight.data(), ckernel->getKernelPointer(),
-                                   ckernel->getm(), ckernel->getn(), ckernel->getSupportX(),
-                                   ckernel->getSupportY(), nullptr, nullptr, nullptr, &nout));
+          if (g.engine && g.world > 1)   // every rank grids a slice of the block; all end with the whole result
+            GVM_CHECK(gvm_grid_block_dist(g.engine, f.nu[i], (int64_t)in.size(), in.uvw.data(), in.Vo.data(),
+                                          in.weight.data(), ckernel->getKernelPointer(), ckernel->getm(), ckernel->getn(),
+                                          ckernel->getSupportX(), ckernel->getSupportY(), &nout));
+          else
+            GVM_CHECK(gvm_grid_block(g.firstgpu, g.M, g.N, g.deltau, g.deltav, f.nu[i], (int64_t)in.size(),
+                                     in.uvw.data(), in.Vo.data(), in.weight.data(), ckernel->getKernelPointer(),
+                                     ckernel->getm(), ckernel->getn(), ckernel->getSupportX(),
+                                     ckernel->getSupportY(), nullptr, nullptr, nullptr, &nout));
           v.uvw.resize(3 * nout);
           v.Vo.resize(2 * nout);
           v.weight.resize(nout);
@@ -443,6 +452,24 @@ void MFS::shardAndUpload() {
           f.engine_slot[i][s] = slot;
         }
     }
+}
+
+// gvm_create + gvm_dist_init, once (device-side part of MFS::setDevice, src/mfs.cu:530-560)
+void MFS::createEngine() {
+  Globals& g = G();
+  if (g.engine) return;
+  gvm_config cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.M = g.M; cfg.N = g.N; cfg.DELTAX = g.DELTAX; cfg.DELTAY = g.DELTAY;
+  cfg.nu_0 = g.nu_0; cfg.eta = g.eta; cfg.minpix = g.initial_values[0];
+  cfg.noise_cut = 1e30f; cfg.threshold = g.threshold; cfg.fg_scale = 1.0f;
+  cfg.device = g.firstgpu; cfg.grad_mode = variables.grad_mode;
+  cfg.keep_vm = 1;  // -o is mandatory in the reference: the model visibilities are always written back
+  if (gvm_create(&cfg, &g.engine) != 0) {
+    std::printf("ERROR: %s\n", gvm_last_error());
+    std::exit(-1);
+  }
+  if (g.world > 1) GVM_CHECK(gvm_dist_init(g.engine, g.rank, g.world, nccl_id.data(), nccl_id.size()));
 }
 
 void MFS::setDevice() {
@@ -528,19 +555,8 @@ void MFS::setDevice() {
       }
     }
 
-  // the engine: per-GPU scratch, cuFFT plan, visibility blocks (varsPerGPU + device_visibilities)
-  gvm_config cfg;
-  std::memset(&cfg, 0, sizeof(cfg));
-  cfg.M = g.M; cfg.N = g.N; cfg.DELTAX = g.DELTAX; cfg.DELTAY = g.DELTAY;
-  cfg.nu_0 = g.nu_0; cfg.eta = g.eta; cfg.minpix = g.initial_values[0];
-  cfg.noise_cut = 1e30f; cfg.threshold = g.threshold; cfg.fg_scale = 1.0f;
-  cfg.device = g.firstgpu; cfg.grad_mode = variables.grad_mode;
-  cfg.keep_vm = 1;  // -o is mandatory in the reference: the model visibilities are always written back
-  if (gvm_create(&cfg, &g.engine) != 0) {
-    std::printf("ERROR: %s\n", gvm_last_error());
-    std::exit(-1);
-  }
-  if (g.world > 1) GVM_CHECK(gvm_dist_init(g.engine, g.rank, g.world, nccl_id.data(), nccl_id.size()));
+  // the engine exists since configure(); the visibility blocks go up now (varsPerGPU + device_visibilities)
+  createEngine();
   shardAndUpload();
 
   // starting image (src/mfs.cu:742-750) and the Image object with its update rules (:798-811)

@@ -106,6 +106,7 @@ class MFS : public Synthesizer {
   void clearRun() override;
   void writeImages() override;
   void writeResiduals() override;
+  void createEngine();
   void unSetDevice() override;
   std::vector<std::string> countAndSeparateStrings(std::string long_str, std::string sep) override;
 

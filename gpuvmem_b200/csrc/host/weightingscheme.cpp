@@ -38,8 +38,14 @@ void WeightingScheme::applyOnGpu(int scheme, float robust, std::vector<MSDataset
     }
   gvm_taper taper;
   if (uvtaper) taper = uvtaper->abi();
-  GVM_CHECK(gvm_weights(g.firstgpu, scheme, robust, g.M, g.N, g.deltau, g.deltav, (int)Z.size(), Z.data(),
-                        uvw.data(), freqs.data(), w.data(), uvtaper ? &taper : nullptr));
+  // several ranks: every rank weighs a slice of every block, the cell sums travel down the ranks in sample order
+  // (bit-identical result, gvm_weights_dist); the engine and its communicator exist since MFS::configure
+  if (g.engine && g.world > 1)
+    GVM_CHECK(gvm_weights_dist(g.engine, scheme, robust, (int)Z.size(), Z.data(), uvw.data(), freqs.data(), w.data(),
+                               uvtaper ? &taper : nullptr));
+  else
+    GVM_CHECK(gvm_weights(g.firstgpu, scheme, robust, g.M, g.N, g.deltau, g.deltav, (int)Z.size(), Z.data(),
+                          uvw.data(), freqs.data(), w.data(), uvtaper ? &taper : nullptr));
   // backup_visibilities: the weights before the scheme, or the new ones with -W (modify_weights)
   size_t b = 0;
   for (auto& ds : d)

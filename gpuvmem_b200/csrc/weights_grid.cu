@@ -16,6 +16,7 @@
 // evaluated on the host: it calls libm's exp/cosf/sinf, which no device routine matches bit for bit.
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "gvm_internal.cuh"
@@ -379,6 +380,61 @@ __global__ void __launch_bounds__(32) k_grid_tiles(const uint32_t* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Distributed preprocessing (gvm_weights_dist / gvm_grid_block_dist): kernels of the exchange.
+// destination of every (tile, sample) pair: the tile's owner rank, originals before Hermitian twins
+__device__ __forceinline__ int tile_owner(uint32_t tile, int ntx, int world) {
+  const int ty = (int)(tile / (uint32_t)ntx), tx = (int)(tile - (uint32_t)ty * (uint32_t)ntx);
+  return (tx + ty) % world;   // neighbouring tiles (the dense centre of the uv plane) go to different ranks
+}
+__global__ void __launch_bounds__(256) k_pair_dest(const uint32_t* __restrict__ tile, const uint32_t* __restrict__ zl,
+                                                   long npairs, long nloc, int ntx, int world,
+                                                   uint32_t* __restrict__ dkey, uint32_t* __restrict__ didx) {
+  const long i = blockIdx.x * 256L + threadIdx.x;
+  if (i >= npairs) return;
+  const int half = zl[i] >= (uint32_t)nloc;
+  dkey[i] = (uint32_t)(half * world + tile_owner(tile[i], ntx, world));
+  didx[i] = (uint32_t)i;
+}
+// first pair of every destination in the destination-sorted list (entries of absent destinations stay at npairs)
+__global__ void __launch_bounds__(256) k_dest_starts(const uint32_t* __restrict__ dkey, long npairs,
+                                                     uint32_t* __restrict__ start) {
+  const long i = blockIdx.x * 256L + threadIdx.x;
+  if (i >= npairs) return;
+  if (i == 0 || dkey[i - 1] != dkey[i]) start[dkey[i]] = (uint32_t)i;
+}
+// send buffers in destination order: tile id and the 16-byte record (centre, w, Vo) of every pair
+__global__ void __launch_bounds__(256) k_pair_pack(const uint32_t* __restrict__ didx, const uint32_t* __restrict__ tile,
+                                                   const uint32_t* __restrict__ zl, long npairs, long nloc,
+                                                   const uint32_t* __restrict__ cpos, const float2* __restrict__ Vo,
+                                                   const float* __restrict__ w, uint32_t* __restrict__ skey,
+                                                   float4* __restrict__ srec) {
+  const long j = blockIdx.x * 256L + threadIdx.x;
+  if (j >= npairs) return;
+  const uint32_t i = didx[j], z = zl[i];
+  const long vi = z < (uint32_t)nloc ? (long)z : (long)z - nloc;
+  float2 vo = Vo[vi];
+  if (z >= (uint32_t)nloc) vo.y *= -1.0f;
+  skey[j] = tile[i];
+  srec[j] = make_float4(__uint_as_float(cpos[z]), w[vi], vo.x, vo.y);
+}
+__global__ void __launch_bounds__(256) k_iota(uint32_t* __restrict__ v, long n) {
+  const long i = blockIdx.x * 256L + threadIdx.x;
+  if (i < n) v[i] = (uint32_t)i;
+}
+// after the stable sort of the RECEIVED pairs by tile: records in replay order + first / last pair of every tile
+__global__ void __launch_bounds__(256) k_recv_gather(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ idx,
+                                                     long npairs, const float4* __restrict__ rrec,
+                                                     int* __restrict__ tstart, int* __restrict__ tend,
+                                                     float4* __restrict__ rec) {
+  const long i = blockIdx.x * 256L + threadIdx.x;
+  if (i >= npairs) return;
+  const uint32_t t = keys[i];
+  if (i == 0 || keys[i - 1] != t) tstart[t] = (int)i;
+  if (i == npairs - 1 || keys[i + 1] != t) tend[t] = (int)(i + 1);
+  rec[i] = rrec[idx[i]];
+}
+
 __global__ void __launch_bounds__(256) k_grid_flags(const float* __restrict__ wgt, long MN,
                                                     int* __restrict__ flags) {
   const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -488,6 +544,31 @@ struct PhaseTimer {
   }
 };
 
+// Replay of the sorted pair records tile by tile (wk.rec, wk.tstart, wk.tend -> wk.gw, wk.gV): tiles in decreasing
+// order of their sample count, one warp per tile.
+int tile_replay(GridWork& wk, long ntiles, int ntx, int ck_m, int ck_n, int sx, int sy, long M, long N, cudaStream_t stream) {
+  if (wk.ord0.ensure((size_t)ntiles * 4) || wk.ordk0.ensure((size_t)ntiles * 4)) return 1;
+  k_tile_order_keys<<<(int)((ntiles + 255) / 256), 256, 0, stream>>>(wk.tstart.as<int>(), wk.tend.as<int>(), ntiles,
+                                                                     wk.ordk0.as<uint32_t>(), wk.ord0.as<uint32_t>());
+  WG_CUDA(cudaGetLastError());
+  if (sort_pairs(wk.tmp, wk.ordk0.as<uint32_t>(), wk.ord0.as<uint32_t>(), ntiles, 31, stream)) return 1;
+  const int taps = (2 * sx + 1) * (2 * sy + 1);
+  const int rounds = (taps + 31) / 32;
+#define GVM_GRID_TILES(R)                                                                                                 \
+  k_grid_tiles<R><<<(unsigned)ntiles, 32, 0, stream>>>(wk.ord0.as<uint32_t>(), wk.tstart.as<int>(), wk.tend.as<int>(),    \
+                                                       wk.rec.as<float4>(), wk.ck.as<float>(), ck_m, ck_n, sx, sy, M, N,  \
+                                                       ntx, wk.gw.as<float>(), wk.gV.as<float2>())
+  if (rounds <= 1) GVM_GRID_TILES(1);
+  else if (rounds <= 2) GVM_GRID_TILES(2);
+  else if (rounds <= 3) GVM_GRID_TILES(3);
+  else if (rounds <= 4) GVM_GRID_TILES(4);
+  else if (rounds <= 6) GVM_GRID_TILES(6);
+  else GVM_GRID_TILES(10);
+#undef GVM_GRID_TILES
+  WG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // The tile-sequential accumulation (k_tile_* + k_grid_tiles): fills gw/gV like k_grid_accumulate does.
 // *done = false (nothing launched) when the problem does not fit its 16-bit centre packing / 31-bit pair count.
 int grid_tiles_path(GridWork& wk, long Z, float freq, double deltau, double deltav, long M, long N, int ck_m,
@@ -526,28 +607,21 @@ int grid_tiles_path(GridWork& wk, long Z, float freq, double deltau, double delt
       WG_CUDA(cudaGetLastError());
     }
   }
-  // replay order: tiles by decreasing sample count
-  if (wk.ord0.ensure((size_t)ntiles * 4) || wk.ordk0.ensure((size_t)ntiles * 4)) return 1;
-  k_tile_order_keys<<<(int)((ntiles + 255) / 256), 256>>>(wk.tstart.as<int>(), wk.tend.as<int>(), ntiles,
-                                                          wk.ordk0.as<uint32_t>(), wk.ord0.as<uint32_t>());
-  WG_CUDA(cudaGetLastError());
-  if (sort_pairs(wk.tmp, wk.ordk0.as<uint32_t>(), wk.ord0.as<uint32_t>(), ntiles, 31)) return 1;
-  const int taps = (2 * sx + 1) * (2 * sy + 1);
-  const int rounds = (taps + 31) / 32;
-#define GVM_GRID_TILES(R)                                                                                       \
-  k_grid_tiles<R><<<(unsigned)ntiles, 32>>>(wk.ord0.as<uint32_t>(), wk.tstart.as<int>(), wk.tend.as<int>(),      \
-                                            wk.rec.as<float4>(), wk.ck.as<float>(), ck_m, ck_n, sx, sy, M, N,    \
-                                            ntx, wk.gw.as<float>(), wk.gV.as<float2>())
-  if (rounds <= 1) GVM_GRID_TILES(1);
-  else if (rounds <= 2) GVM_GRID_TILES(2);
-  else if (rounds <= 3) GVM_GRID_TILES(3);
-  else if (rounds <= 4) GVM_GRID_TILES(4);
-  else if (rounds <= 6) GVM_GRID_TILES(6);
-  else GVM_GRID_TILES(10);
-#undef GVM_GRID_TILES
-  WG_CUDA(cudaGetLastError());
+  if (tile_replay(wk, ntiles, ntx, ck_m, ck_n, sx, sy, M, N, nullptr)) return 1;
   *done = true;
   return 0;
+}
+
+// std::accumulate(weights, 0.0f) per block, then summed over the blocks (src/briggsweightingscheme.cu:46-57)
+float briggs_sum_of_weights(int nblocks, const int64_t* Z, float* const* w) {
+  float sum_w = 0.0f;
+  for (int b = 0; b < nblocks; b++) {
+    float acc = 0.0f;
+    const float* wb = w[b];
+    for (long z = 0; z < (long)Z[b]; z++) acc += wb[z];
+    sum_w += acc;
+  }
+  return sum_w;
 }
 
 // UVTaper::getValue (include/classes/uvtaper.cuh:100-118), host libm, folded coordinates
@@ -631,11 +705,10 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
   float f_squared = 0.0f;
   if (scheme == GVM_W_BRIGGS) {
     float sum_w = 0.0f, sum_g2 = 0.0f;
-    for (int b = 0; b < nblocks; b++) {
-      float acc = 0.0f;
-      for (long z = 0; z < (long)Z[b]; z++) acc += w[b][z];   // std::accumulate(..., 0.0f)
-      sum_w += acc;
-    }
+    // the reference's sequential fp32 sum of all weights (src/briggsweightingscheme.cu:46-57) cannot be split
+    // without changing its rounding; it runs on a host thread next to the GPU's first pass
+    std::thread sum_thread([&] { sum_w = briggs_sum_of_weights(nblocks, Z, w); });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{sum_thread};
     std::vector<float> hgrid(MN);
     for (int b = 0; b < nblocks; b++) {
       const long z = (long)Z[b];
@@ -651,6 +724,7 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
       for (long m = 0; m < M; m++)
         for (long n = N / 2; n < N; n++) sum_g2 += hgrid[N * m + n] * hgrid[N * m + n];
     }
+    sum_thread.join();
     const float avg = sum_g2 / sum_w;
     f_squared = (5.0f * powf(10.0f, -robust)) * (5.0f * powf(10.0f, -robust)) / avg;
     WG_CUDA(cudaMemset(d_grid.p, 0, MN * 4));
@@ -806,6 +880,321 @@ int gvm_grid_fetch(double* uvw_out, float* Vo_out, float* w_out) {
     if (Vo_out && gvm_fast_d2h(Vo_out, res.Vo.p, count * 8, 0)) return 1;
     if (w_out && gvm_fast_d2h(w_out, res.w.p, count * 4, 0)) return 1;
   }
+  return 0;
+}
+
+// =============================================================================================
+// Multi-rank preprocessing. Every rank passes the SAME full host arrays; rank r uploads and processes only the
+// contiguous slice [Z r / W, Z (r + 1) / W) of every block, so uploads, cell indexing and sorting divide by W.
+// The results are bit-identical to the single-rank (and therefore to the reference's one-thread) results:
+//  * weights: the per-cell fp32 sums are sequential in ascending sample index; with contiguous slices that is
+//    "rank 0's samples, then rank 1's, ..." — the grid travels down the ranks (ncclSend / ncclRecv), every rank
+//    continues the sums of its predecessor (k_cell_accumulate starts from what the grid holds), and the last rank
+//    broadcasts the finished grid;
+//  * gridding: a (tile, sample) pair is owned by the rank that owns the tile; pairs are exchanged all-to-all in
+//    (originals | twins) x (source rank) order, which IS ascending doubled-sample order, so the stable sort by
+//    tile on the owner leaves every tile's samples in the reference's loop order (src/functions.cu:1418-1508);
+//    the tile results are merged with an unsigned max (every cell is non-zero on at most one rank: exact).
+static inline void slice_of(int64_t Z, int rank, int world, int64_t* lo, int64_t* hi) {
+  *lo = Z * rank / world;
+  *hi = Z * (rank + 1) / world;
+}
+
+int gvm_weights_dist(gvm_engine* e, int scheme, float robust, int nblocks, const int64_t* Z,
+                     const double* const* uvw_m, const float* freqs, float* const* w, const gvm_taper* taper) {
+  const gvm_config& g = e->cfg;
+  const double deltax = GVM_RPDEG_D * g.DELTAX, deltay = GVM_RPDEG_D * g.DELTAY;
+  const double deltau = 1.0 / (g.M * deltax), deltav = 1.0 / (g.N * deltay);
+  if (e->world <= 1 || scheme == GVM_W_NATURAL)
+    return gvm_weights(g.device, scheme, robust, g.M, g.N, deltau, deltav, nblocks, Z, uvw_m, freqs, w, taper);
+  if (scheme < GVM_W_NATURAL || scheme > GVM_W_RADIAL) { gvm_set_error("gvm_weights_dist: unknown scheme %d", scheme); return 1; }
+  if (scheme == GVM_W_BRIGGS && (robust < -2.0f || robust > 2.0f)) {
+    gvm_set_error("gvm_weights_dist: Briggs robust must be in [-2, 2] (src/briggsweightingscheme.cu:13-21)");
+    return 1;
+  }
+  const long M = g.M, N = g.N;
+  if (M * N >= (int64_t)kNoCell) { gvm_set_error("gvm_weights_dist: grid too large"); return 1; }
+  WG_CUDA(cudaSetDevice(g.device));
+  cudaStream_t st = e->stream;
+  const int rank = e->rank, world = e->world;
+  const bool use_taper = taper && taper->enabled;
+  const size_t MN = (size_t)(M * N);
+  const double adu = fabs(deltau), adv = fabs(deltav);
+  long zmax = 1, smax = 1;
+  for (int b = 0; b < nblocks; b++) {
+    zmax = Z[b] > zmax ? (long)Z[b] : zmax;
+    const long per = (long)(Z[b] / world) + 1;
+    smax = per > smax ? per : smax;
+  }
+  if (zmax >= (long)0x7FFFFFFF) { gvm_set_error("gvm_weights_dist: block too large"); return 1; }
+  DevBuf d_grid, d_uvw, d_w, d_k0, d_v0, d_tmp, d_wfull;
+  if (d_uvw.ensure((size_t)smax * 24) || d_w.ensure((size_t)smax * 4) || d_wfull.ensure((size_t)zmax * 4)) return 1;
+  if (scheme != GVM_W_RADIAL)
+    if (d_grid.ensure(MN * 4) || d_k0.ensure((size_t)smax * 4) || d_v0.ensure((size_t)smax * 4)) return 1;
+
+  // this rank's slice of block b on the device (+ its cells, sorted) ; returns the slice
+  auto load_slice = [&](int b, int64_t* lo, int64_t* hi, bool cells) -> int {
+    slice_of(Z[b], rank, world, lo, hi);
+    const long n = (long)(*hi - *lo);
+    if (n <= 0) return 0;
+    if (gvm_fast_h2d(d_uvw.p, uvw_m[b] + 3 * *lo, (size_t)n * 24, st)) return 1;
+    if (gvm_fast_h2d(d_w.p, w[b] + *lo, (size_t)n * 4, st)) return 1;
+    if (!cells) return 0;
+    k_weight_cells<<<(int)((n + 255) / 256), 256, 0, st>>>(d_uvw.as<double>(), n, freqs[b], adu, adv, M, N,
+                                                           d_k0.as<uint32_t>(), d_v0.as<uint32_t>());
+    WG_CUDA(cudaGetLastError());
+    return sort_pairs(d_tmp, d_k0.as<uint32_t>(), d_v0.as<uint32_t>(), n, 32, st);
+  };
+  // the grid of cell sums goes down the ranks: receive what the lower ranks summed, continue with this rank's
+  // samples, hand it on; the last rank holds the complete sums and broadcasts them
+  auto ring_accumulate = [&](long n) -> int {
+    if (rank > 0 && gvm_dist_recv(e, d_grid.p, MN * 4, rank - 1)) return 1;
+    if (n > 0) {
+      k_cell_accumulate<<<(int)((n + 255) / 256), 256, 0, st>>>(d_k0.as<uint32_t>(), d_v0.as<uint32_t>(), n,
+                                                                d_w.as<float>(), d_grid.as<float>());
+      WG_CUDA(cudaGetLastError());
+    }
+    if (rank < world - 1 && gvm_dist_send(e, d_grid.p, MN * 4, rank + 1)) return 1;
+    return gvm_dist_broadcast_bytes(e, d_grid.p, MN * 4, world - 1);
+  };
+  // every rank's slice of the new weights -> the whole block on every rank -> host
+  auto gather_weights = [&](int b, int64_t lo, int64_t hi) -> int {
+    if (hi > lo) WG_CUDA(cudaMemcpyAsync(d_wfull.as<float>() + lo, d_w.p, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToDevice, st));
+    if (gvm_dist_group_begin(e)) return 1;
+    for (int r = 0; r < world; r++) {
+      int64_t rlo, rhi;
+      slice_of(Z[b], r, world, &rlo, &rhi);
+      if (rhi > rlo && gvm_dist_broadcast_bytes(e, d_wfull.as<float>() + rlo, (size_t)(rhi - rlo) * 4, r)) return 1;
+    }
+    if (gvm_dist_group_end(e)) return 1;
+    return Z[b] > 0 ? gvm_fast_d2h(w[b], d_wfull.p, (size_t)Z[b] * 4, st) : 0;
+  };
+
+  if (scheme == GVM_W_RADIAL) {
+    for (int b = 0; b < nblocks; b++) {
+      int64_t lo, hi;
+      if (load_slice(b, &lo, &hi, false)) return 1;
+      if (hi > lo) {
+        k_radial<<<(int)((hi - lo + 255) / 256), 256, 0, st>>>(d_uvw.as<double>(), (long)(hi - lo), freqs[b], d_w.as<float>());
+        WG_CUDA(cudaGetLastError());
+      }
+      if (gather_weights(b, lo, hi)) return 1;
+      if (use_taper) apply_taper_host(taper, scheme, (long)Z[b], uvw_m[b], freqs[b], w[b]);
+    }
+    return 0;
+  }
+
+  float f_squared = 0.0f;
+  bool grid_resident = false;   // single block: the first Briggs pass leaves the finished sums (and the sorted slice) in place
+  if (scheme == GVM_W_BRIGGS) {
+    float sum_w = 0.0f, sum_g2 = 0.0f;
+    std::thread sum_thread([&] { sum_w = briggs_sum_of_weights(nblocks, Z, w); });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{sum_thread};
+    std::vector<float> hgrid(MN);
+    WG_CUDA(cudaMemsetAsync(d_grid.p, 0, MN * 4, st));
+    for (int b = 0; b < nblocks; b++) {
+      int64_t lo, hi;
+      if (load_slice(b, &lo, &hi, true)) return 1;
+      if (ring_accumulate((long)(hi - lo))) return 1;
+      // the first-pass grid is never cleared between blocks and the half-plane sum of squares is taken after
+      // each one (src/briggsweightingscheme.cu:59-106): every rank repeats that sequential host sum
+      if (gvm_fast_d2h(hgrid.data(), d_grid.p, MN * 4, st)) return 1;
+      for (long m = 0; m < M; m++)
+        for (long n = N / 2; n < N; n++) sum_g2 += hgrid[N * m + n] * hgrid[N * m + n];
+    }
+    sum_thread.join();
+    const float avg = sum_g2 / sum_w;
+    f_squared = (5.0f * powf(10.0f, -robust)) * (5.0f * powf(10.0f, -robust)) / avg;
+    grid_resident = nblocks == 1;
+    if (!grid_resident) WG_CUDA(cudaMemsetAsync(d_grid.p, 0, MN * 4, st));
+  } else {
+    WG_CUDA(cudaMemsetAsync(d_grid.p, 0, MN * 4, st));
+  }
+  for (int b = 0; b < nblocks; b++) {
+    int64_t lo, hi;
+    slice_of(Z[b], rank, world, &lo, &hi);
+    if (!grid_resident) {
+      if (load_slice(b, &lo, &hi, true)) return 1;
+      if (ring_accumulate((long)(hi - lo))) return 1;
+    }
+    const long n = (long)(hi - lo);
+    if (n > 0) {
+      k_weight_apply<<<(int)((n + 255) / 256), 256, 0, st>>>(d_k0.as<uint32_t>(), d_v0.as<uint32_t>(), n, d_grid.as<float>(),
+                                                             scheme == GVM_W_BRIGGS, f_squared, d_w.as<float>());
+      WG_CUDA(cudaGetLastError());
+    }
+    if (gather_weights(b, lo, hi)) return 1;
+    if (b + 1 < nblocks) WG_CUDA(cudaMemsetAsync(d_grid.p, 0, MN * 4, st));   // per-block sums in the second pass
+    if (use_taper) apply_taper_host(taper, scheme, (long)Z[b], uvw_m[b], freqs[b], w[b]);
+  }
+  WG_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_m, const float* Vo, const float* w,
+                        const float* ckernel, int ck_m, int ck_n, int support_x, int support_y, int64_t* nout) {
+  const gvm_config& g = e->cfg;
+  const double deltax = GVM_RPDEG_D * g.DELTAX, deltay = GVM_RPDEG_D * g.DELTAY;
+  const double deltau = 1.0 / (g.M * deltax), deltav = 1.0 / (g.N * deltay);
+  const long M = g.M, N = g.N;
+  const int sx = support_x, sy = support_y;
+  const bool fits = M + 2L * sy < 65536 && N + 2L * sx < 65536;   // 16-bit centre packing of the tile replay
+  if (e->world <= 1 || !fits)
+    return gvm_grid_block(g.device, M, N, deltau, deltav, freq, Z, uvw_m, Vo, w, ckernel, ck_m, ck_n, sx, sy, nullptr, nullptr,
+                          nullptr, nout);
+  if (!nout || Z < 0 || ck_m < 1 || ck_n < 1 || sx < 0 || sy < 0) { gvm_set_error("gvm_grid_block_dist: bad argument"); return 1; }
+  if ((2 * sx + 1) * (2 * sy + 1) > kMaxTaps) {
+    gvm_set_error("gvm_grid_block_dist: kernel support %d x %d exceeds %d taps", sx, sy, kMaxTaps);
+    return 1;
+  }
+  WG_CUDA(cudaSetDevice(g.device));
+  cudaStream_t st = e->stream;
+  const int rank = e->rank, world = e->world;
+  const size_t MN = (size_t)(M * N);
+  *nout = 0;
+  PhaseTimer pt;
+  GridWork& wk = g_grid_work;
+  GridResult& res = g_grid_result;
+  res.count = 0;
+  int64_t lo, hi;
+  slice_of(Z, rank, world, &lo, &hi);
+  const long nloc = (long)(hi - lo), n2 = 2 * nloc;
+  const size_t zz = (size_t)(nloc > 0 ? nloc : 1);
+  const int ntx = (int)((N + kTile - 1) / kTile), nty = (int)((M + kTile - 1) / kTile);
+  const long ntiles = (long)ntx * nty;
+  if (wk.uvw.ensure(zz * 24) || wk.Vo.ensure(zz * 8) || wk.w.ensure(zz * 4) || wk.ck.ensure((size_t)ck_m * ck_n * 4) ||
+      wk.gw.ensure(MN * 4) || wk.gV.ensure(MN * 8) || wk.flags.ensure(MN * 4) || wk.pos.ensure(MN * 4) ||
+      wk.tstart.ensure((size_t)ntiles * 4) || wk.tend.ensure((size_t)ntiles * 4) || wk.cpos.ensure(2 * zz * 4) ||
+      wk.cnt.ensure(2 * zz * 4 + ((size_t)2 * world + 1) * 4) || wk.off.ensure(2 * zz * 4))
+    return 1;
+  if (nloc > 0)
+    if (gvm_fast_h2d(wk.uvw.p, uvw_m + 3 * lo, zz * 24, st) || gvm_fast_h2d(wk.Vo.p, Vo + 2 * lo, zz * 8, st) ||
+        gvm_fast_h2d(wk.w.p, w + lo, zz * 4, st))
+      return 1;
+  WG_CUDA(cudaMemcpyAsync(wk.ck.p, ckernel, (size_t)ck_m * ck_n * 4, cudaMemcpyHostToDevice, st));
+  pt.mark("dist grid: upload of the slice");
+  // ---- local (tile, sample) pairs of the slice, in ascending local doubled index (originals, then twins)
+  long npairs = 0;
+  if (n2 > 0) {
+    const int blocks = (int)((n2 + 255) / 256);
+    k_tile_count<<<blocks, 256, 0, st>>>(wk.uvw.as<double>(), nloc, freq, deltau, deltav, M, N, sx, sy, wk.cpos.as<uint32_t>(),
+                                         wk.cnt.as<int>());
+    WG_CUDA(cudaGetLastError());
+    if (exclusive_scan(wk.tmp, wk.cnt.p, wk.off.p, n2, st)) return 1;
+    int last_off = 0, last_cnt = 0;
+    WG_CUDA(cudaMemcpyAsync(&last_off, wk.off.as<int>() + (n2 - 1), 4, cudaMemcpyDeviceToHost, st));
+    WG_CUDA(cudaMemcpyAsync(&last_cnt, wk.cnt.as<int>() + (n2 - 1), 4, cudaMemcpyDeviceToHost, st));
+    WG_CUDA(cudaStreamSynchronize(st));
+    npairs = (long)last_off + last_cnt;
+    if (npairs >= (long)0x7FFFFFFF) { gvm_set_error("gvm_grid_block_dist: too many (tile, sample) pairs on one rank"); return 1; }
+  }
+  const size_t np = (size_t)(npairs > 0 ? npairs : 1);
+  if (wk.k0.ensure(np * 4) || wk.v0.ensure(np * 4) || wk.dk.ensure(np * 4) || wk.dv.ensure(np * 4) || wk.sk.ensure(np * 4) ||
+      wk.srec.ensure(np * 16))
+    return 1;
+  std::vector<uint32_t> dstart((size_t)2 * world + 1, (uint32_t)npairs);
+  if (npairs > 0) {
+    const int blocks = (int)((n2 + 255) / 256), pb = (int)((npairs + 255) / 256);
+    k_tile_emit<<<blocks, 256, 0, st>>>(wk.cpos.as<uint32_t>(), wk.off.as<int>(), n2, M, N, sx, sy, ntx, wk.k0.as<uint32_t>(),
+                                        wk.v0.as<uint32_t>());
+    k_pair_dest<<<pb, 256, 0, st>>>(wk.k0.as<uint32_t>(), wk.v0.as<uint32_t>(), npairs, nloc, ntx, world, wk.dk.as<uint32_t>(),
+                                    wk.dv.as<uint32_t>());
+    WG_CUDA(cudaGetLastError());
+    int bits = 1;
+    while ((1 << bits) < 2 * world) bits++;
+    if (sort_pairs(wk.tmp, wk.dk.as<uint32_t>(), wk.dv.as<uint32_t>(), npairs, bits, st)) return 1;
+    uint32_t* d_start = wk.cnt.as<uint32_t>();    // free again: 2 W + 1 words
+    std::vector<uint32_t> init((size_t)2 * world + 1, (uint32_t)npairs);
+    WG_CUDA(cudaMemcpyAsync(d_start, init.data(), init.size() * 4, cudaMemcpyHostToDevice, st));
+    k_dest_starts<<<pb, 256, 0, st>>>(wk.dk.as<uint32_t>(), npairs, d_start);
+    k_pair_pack<<<pb, 256, 0, st>>>(wk.dv.as<uint32_t>(), wk.k0.as<uint32_t>(), wk.v0.as<uint32_t>(), npairs, nloc,
+                                    wk.cpos.as<uint32_t>(), wk.Vo.as<float2>(), wk.w.as<float>(), wk.sk.as<uint32_t>(),
+                                    wk.srec.as<float4>());
+    WG_CUDA(cudaGetLastError());
+    WG_CUDA(cudaMemcpyAsync(dstart.data(), d_start, dstart.size() * 4, cudaMemcpyDeviceToHost, st));
+    WG_CUDA(cudaStreamSynchronize(st));
+    for (int d = 2 * world - 1; d >= 0; d--)     // absent destinations: empty range in front of the next present one
+      if (dstart[d] > dstart[d + 1]) dstart[d] = dstart[d + 1];
+  }
+  pt.mark("dist grid: local pairs + destination sort");
+  // ---- counts of every (source, destination): counts[s][d], d = half * W + owner
+  std::vector<uint32_t> counts((size_t)world * 2 * world, 0u);
+  {
+    DevBuf d_counts;
+    if (d_counts.ensure(counts.size() * 4)) return 1;
+    std::vector<uint32_t> mine((size_t)2 * world);
+    for (int d = 0; d < 2 * world; d++) mine[d] = dstart[d + 1] - dstart[d];
+    WG_CUDA(cudaMemcpyAsync(d_counts.as<uint32_t>() + (size_t)rank * 2 * world, mine.data(), mine.size() * 4,
+                            cudaMemcpyHostToDevice, st));
+    if (gvm_dist_group_begin(e)) return 1;
+    for (int r = 0; r < world; r++)
+      if (gvm_dist_broadcast_bytes(e, d_counts.as<uint32_t>() + (size_t)r * 2 * world, (size_t)2 * world * 4, r)) return 1;
+    if (gvm_dist_group_end(e)) return 1;
+    WG_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, counts.size() * 4, cudaMemcpyDeviceToHost, st));
+    WG_CUDA(cudaStreamSynchronize(st));
+  }
+  // receive layout on this rank: (originals | twins) x (source rank) — ascending doubled-sample order
+  std::vector<size_t> roff((size_t)2 * world + 1, 0);
+  for (int h = 0; h < 2; h++)
+    for (int s_ = 0; s_ < world; s_++)
+      roff[(size_t)h * world + s_ + 1] = roff[(size_t)h * world + s_] + counts[(size_t)s_ * 2 * world + (size_t)h * world + rank];
+  const size_t nrecv = roff[(size_t)2 * world];
+  if (nrecv >= (size_t)0x7FFFFFFF) { gvm_set_error("gvm_grid_block_dist: too many pairs for one owner"); return 1; }
+  const size_t nr = nrecv > 0 ? nrecv : 1;
+  if (wk.rk.ensure(nr * 4) || wk.rrec.ensure(nr * 16) || wk.rec.ensure(nr * 16) || wk.dv.ensure(nr * 4)) return 1;
+  if (gvm_dist_group_begin(e)) return 1;
+  for (int peer = 0; peer < world; peer++)
+    for (int h = 0; h < 2; h++) {
+      const int d = h * world + peer;                                   // what this rank sends to `peer`
+      const size_t ns = (size_t)(dstart[d + 1] - dstart[d]);
+      const size_t nrv = roff[(size_t)h * world + peer + 1] - roff[(size_t)h * world + peer];   // what it receives from `peer`
+      if (ns > 0) {
+        if (gvm_dist_send(e, wk.sk.as<uint32_t>() + dstart[d], ns * 4, peer)) return 1;
+        if (gvm_dist_send(e, wk.srec.as<float4>() + dstart[d], ns * 16, peer)) return 1;
+      }
+      if (nrv > 0) {
+        if (gvm_dist_recv(e, wk.rk.as<uint32_t>() + roff[(size_t)h * world + peer], nrv * 4, peer)) return 1;
+        if (gvm_dist_recv(e, wk.rrec.as<float4>() + roff[(size_t)h * world + peer], nrv * 16, peer)) return 1;
+      }
+    }
+  if (gvm_dist_group_end(e)) return 1;
+  pt.mark("dist grid: all-to-all of the pairs");
+  // ---- owner side: stable sort by tile, records in replay order, replay
+  WG_CUDA(cudaMemsetAsync(wk.tstart.p, 0, (size_t)ntiles * 4, st));
+  WG_CUDA(cudaMemsetAsync(wk.tend.p, 0, (size_t)ntiles * 4, st));
+  if (nrecv > 0) {
+    const int rb = (int)((nrecv + 255) / 256);
+    k_iota<<<rb, 256, 0, st>>>(wk.dv.as<uint32_t>(), (long)nrecv);
+    int bits = 1;
+    while ((1L << bits) < ntiles) bits++;
+    if (sort_pairs(wk.tmp, wk.rk.as<uint32_t>(), wk.dv.as<uint32_t>(), (long)nrecv, bits, st)) return 1;
+    k_recv_gather<<<rb, 256, 0, st>>>(wk.rk.as<uint32_t>(), wk.dv.as<uint32_t>(), (long)nrecv, wk.rrec.as<float4>(),
+                                      wk.tstart.as<int>(), wk.tend.as<int>(), wk.rec.as<float4>());
+    WG_CUDA(cudaGetLastError());
+  }
+  if (tile_replay(wk, ntiles, ntx, ck_m, ck_n, sx, sy, M, N, st)) return 1;
+  pt.mark("dist grid: owner sort + tile replay");
+  // every cell was computed by its owner and is exactly zero elsewhere: merge the bit patterns
+  if (gvm_dist_allreduce_u32_max(e, wk.gw.as<uint32_t>(), MN)) return 1;
+  if (gvm_dist_allreduce_u32_max(e, wk.gV.as<uint32_t>(), 2 * MN)) return 1;
+  k_grid_flags<<<(int)((MN + 255) / 256), 256, 0, st>>>(wk.gw.as<float>(), (long)MN, wk.flags.as<int>());
+  if (exclusive_scan(wk.tmp, wk.flags.p, wk.pos.p, (long)MN, st)) return 1;
+  int last_pos = 0, last_flag = 0;
+  WG_CUDA(cudaMemcpyAsync(&last_pos, wk.pos.as<int>() + (MN - 1), 4, cudaMemcpyDeviceToHost, st));
+  WG_CUDA(cudaMemcpyAsync(&last_flag, wk.flags.as<int>() + (MN - 1), 4, cudaMemcpyDeviceToHost, st));
+  WG_CUDA(cudaStreamSynchronize(st));
+  const long count = (long)last_pos + last_flag;
+  if (count > 0) {
+    if (res.uvw.ensure((size_t)count * 24) || res.Vo.ensure((size_t)count * 8) || res.w.ensure((size_t)count * 4)) return 1;
+    k_grid_compact<<<(int)((MN + 255) / 256), 256, 0, st>>>(wk.gw.as<float>(), wk.gV.as<float2>(), wk.pos.as<int>(), M, N,
+                                                            deltau, deltav, gvm_freq_to_wavelength(freq),
+                                                            res.uvw.as<double>(), res.Vo.as<float2>(), res.w.as<float>());
+    WG_CUDA(cudaGetLastError());
+    WG_CUDA(cudaStreamSynchronize(st));
+  }
+  pt.mark("dist grid: merge + compact");
+  res.count = count;
+  *nout = count;
   return 0;
 }
 

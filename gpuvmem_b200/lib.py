@@ -100,6 +100,8 @@ SIGNATURES = {
     "gvm_graph_launch": (C.c_int, [_P, _P]),
     "gvm_graph_destroy": (C.c_int, [_P, _P]),
     "gvm_state_epoch": (C.c_int64, [_P]),
+    "gvm_weights_dist": (C.c_int, [_P, C.c_int, C.c_float, C.c_int, _P, _P, _P, _P, _P]),
+    "gvm_grid_block_dist": (C.c_int, [_P, C.c_float, C.c_int64, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "gvm_sort_pairs_host": (C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int]),
     "gvm_dist_abort": (C.c_int, [_P]),
     "gvm_dist_broadcast": (C.c_int, [_P, _P, C.c_int64, C.c_int]),

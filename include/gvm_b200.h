@@ -350,6 +350,17 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
 /* Two-phase use for large grids: call gvm_grid_block with the three output pointers NULL to get
  * *nout, size the host arrays, then fetch the gridded samples of that last call (same thread). */
 int gvm_grid_fetch(double* uvw_out, float* Vo_out, float* w_out);
+/* Multi-rank versions on an engine that went through gvm_dist_init (grid size and cell size are the engine's).
+ * EVERY rank passes the same full host arrays; rank r uploads and processes only the samples
+ * [Z r / W, Z (r + 1) / W) of every block, and every rank ends with the complete result: the new weights of all
+ * samples in w[b] / the gridded samples through gvm_grid_fetch. Bit-identical to gvm_weights / gvm_grid_block
+ * (DESIGN.md §6): the per-cell weight sums travel down the ranks in sample order, the (tile, sample) pairs of the
+ * gridding are exchanged all-to-all with the tile owners in ascending sample order. With world == 1 they are
+ * gvm_weights / gvm_grid_block. */
+int gvm_weights_dist(gvm_engine* e, int scheme, float robust, int nblocks, const int64_t* Z,
+                     const double* const* uvw_m, const float* freqs, float* const* w, const gvm_taper* taper);
+int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_m, const float* Vo, const float* w,
+                        const float* ckernel, int ck_m, int ck_n, int support_x, int support_y, int64_t* nout);
 /* gvm_grid_block keeps its device work buffers between calls (this thread); this returns them. */
 int gvm_grid_release(void);
 

@@ -19,7 +19,8 @@ def main():
     from gpuvmem_b200 import dist as gdist
     from gpuvmem_b200 import host, synth
     nchan, out = int(sys.argv[1]), sys.argv[2]
-    normalize = len(sys.argv) > 3 and sys.argv[3] == "normalize"
+    mode = sys.argv[3] if len(sys.argv) > 3 else ""
+    normalize = mode == "normalize"
     rank, world, local = gdist.init_from_env(0)
     torch.cuda.set_device(local)
     nccl_id = None
@@ -32,8 +33,21 @@ def main():
     host.set_quiet(True)
     # normalize: Chi2 configured with normalize = true (chi2 and its gradient divided by the block's visibility count)
     fi_spec = "Chi2:-1:0:0:1,Entropy:0:0:0,L1-Norm:1:0:0,TotalSquaredVariation:2:0:0" if normalize else None
-    s = host.Session(p, args=f"-z 0.001,0.1 -Z 0.01,0.005,0.002 -t 4 -G {local}", optimizer="CG-FRPRMN",
-                     fi_spec=fi_spec, rank=rank, world=world, nccl_id=nccl_id)
+    # gridded_*: weighting scheme + convolutional gridding (-g) are DISTRIBUTED over the ranks (gvm_weights_dist,
+    # gvm_grid_block_dist) and must reproduce the single-rank samples bit for bit
+    extra, scheme, ck, ck_size = "", "Natural", "PillBox2D", (0, 0)
+    if mode == "gridded_briggs":
+        extra, scheme, ck, ck_size = " -g 1 -R 0.0", "Briggs", "Gaussian2D", (7, 7)
+    elif mode == "gridded_uniform":
+        extra, scheme, ck, ck_size = " -g 1", "Uniform", "PSWF", (9, 9)
+    elif mode == "radial":
+        scheme = "Radial"
+    s = host.Session(p, args=f"-z 0.001,0.1 -Z 0.01,0.005,0.002 -t 4 -G {local}" + extra, optimizer="CG-FRPRMN",
+                     scheme=scheme, ckernel=ck, ck_size=ck_size, fi_spec=fi_spec, rank=rank, world=world, nccl_id=nccl_id)
+    vis = {}
+    for c in range(p.nchan):
+        u, V, wt = s.host_vis(c)
+        vis[f"uvw{c}"], vis[f"Vo{c}"], vis[f"w{c}"] = u, V, wt
     start = s.get_image()
     s.set_image(probe_image(p.N, np.float32(0.001), 0.1))
     s.set_iteration(1)
@@ -45,7 +59,7 @@ def main():
     img, sec = s.run()
     if rank == 0:
         np.savez(out, value=v, fi=fi, grad=g, image=img, err=err, local_nvis=s.local_nvis(), collectives=s.collectives(),
-                 world=world)
+                 world=world, **vis)
     s.close()
     if world > 1:
         dist.barrier()

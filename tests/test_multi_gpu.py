@@ -76,3 +76,22 @@ def test_normalized_chi2_with_visibility_chunks_matches_single_gpu(tmp_path):
     assert abs(float(two["value"]) - float(one["value"])) <= 1e-5 * abs(float(one["value"]))
     assert _rel(two["grad"][0], one["grad"][0]) <= 1e-4
     assert _rel(two["image"][0], one["image"][0]) <= 2e-3
+
+
+@pytest.mark.parametrize("mode,nchan", [("gridded_briggs", 1), ("gridded_briggs", 3), ("gridded_uniform", 1), ("radial", 2)])
+def test_distributed_weighting_and_gridding_are_bit_identical(tmp_path, mode, nchan):
+    """Weighting scheme (Briggs: two passes + the two order-dependent scalars; uniform; radial) and convolutional
+    gridding with every rank processing a slice of every block: the weighted / gridded samples that come out must
+    equal the single-rank ones bit for bit (which tests/test_host_gpu.py holds bit-equal to the reference's)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    one = _run(1, nchan, str(tmp_path / f"one_{mode}.npz"), 0, extra=(mode,))
+    two = _run(2, nchan, str(tmp_path / f"two_{mode}.npz"), 29560 + nchan, extra=(mode,))
+    assert int(two["world"]) == 2
+    for c in range(nchan):
+        assert len(two[f"w{c}"]) == len(one[f"w{c}"]) > 0, (c, len(two[f"w{c}"]), len(one[f"w{c}"]))
+        assert np.array_equal(two[f"w{c}"].view(np.uint32), one[f"w{c}"].view(np.uint32)), f"weights, channel {c}"
+        assert np.array_equal(two[f"uvw{c}"].view(np.uint64), one[f"uvw{c}"].view(np.uint64)), f"uvw, channel {c}"
+        assert np.array_equal(two[f"Vo{c}"].view(np.uint32), one[f"Vo{c}"].view(np.uint32)), f"Vo, channel {c}"
+    assert abs(float(two["value"]) - float(one["value"])) <= 1e-5 * abs(float(one["value"]))
+    assert _rel(two["grad"][0], one["grad"][0]) <= 1e-4
