@@ -533,7 +533,9 @@ def measure(ctx, name, scale, steps, warmup, recon_iters, grad_mode=0, lbfgs_k=1
         cfg = workload_config(name, problem, wl)
         engine = {"samples_in_objective": Zwork,
                   "api": "C++ host layer (ObjectiveFunction::calcFunction + calcGradient) over the C ABI",
-                  "sharding": (f"visibility chunks over {world} rank(s)" if problem.nchan < world or world == 1
+                  "sharding": ("replicated objective on the gridded samples (image-sized work does not shard); weighting + gridding "
+                               f"distributed over {world} ranks" if ("-g" in cli and world > 1) else
+                               f"visibility chunks over {world} rank(s)" if problem.nchan < world or world == 1
                                else f"channels over {world} rank(s) (i % world)"),
                   "l2": "inputs (>= 52 B/vis x Z) exceed the 126 MB L2; no flush needed", "grad_mode": mode}
         out = {"value": value, "ms_per_step": ms_step, "evals_per_s": 1e3 / ms_step,

@@ -74,14 +74,14 @@ int load_nccl() {
   if (!(e)->nccl_comm) { gvm_set_error("gvm_dist: the communicator was aborted after a failure on this rank"); return 1; }
 
 int gvm_dist_allreduce_f32(gvm_engine* e, float* buf, size_t n) {
-  if (e->world <= 1) return 0;
+  if (e->world <= 1 || e->replicated) return 0;
   GVM_DIST_ALIVE(e)
   GVM_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat, ncclSum, (ncclComm_t)e->nccl_comm, e->stream));
   e->collectives++;
   return 0;
 }
 int gvm_dist_allreduce_f64(gvm_engine* e, double* buf, size_t n) {
-  if (e->world <= 1) return 0;
+  if (e->world <= 1 || e->replicated) return 0;
   GVM_DIST_ALIVE(e)
   GVM_NCCL(g_nccl.AllReduce(buf, buf, n, ncclDouble, ncclSum, (ncclComm_t)e->nccl_comm, e->stream));
   e->collectives++;
@@ -175,6 +175,12 @@ int gvm_dist_init(gvm_engine* e, int rank, int world, const char* id, size_t byt
 int gvm_dist_rank(gvm_engine* e) { return e->rank; }
 int gvm_dist_world(gvm_engine* e) { return e->world; }
 int64_t gvm_dist_collectives(gvm_engine* e) { return e->collectives; }
+
+int gvm_dist_set_replicated(gvm_engine* e, int on) {
+  e->replicated = on != 0;
+  e->epoch++;
+  return 0;
+}
 
 int gvm_dist_abort(gvm_engine* e) {
   gvm_dist_abort_comm(e);

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <iterator>
 
 #include "gvm_internal.cuh"
 
@@ -454,7 +455,8 @@ static int dchi2_impl(gvm_engine* e, const float* I_dev, int flag_opt, int norma
   e->ev_used = 0;
   float* const caller_result = result_dchi2_dev;
   const size_t MN2 = 2 * (size_t)e->cfg.M * e->cfg.N;
-  if (e->world > 1) {
+  const bool reduce = e->world > 1 && !e->replicated;
+  if (reduce) {
     // this rank's shard accumulates into a private buffer; ONE all-reduce of the image-sized
     // gradient replaces the reference's serialised peer-to-peer accumulate (src/functions.cu:4534-4549)
     if (!e->dist_grad) GVM_CUDA(cudaMalloc(&e->dist_grad, MN2 * sizeof(float)));
@@ -478,7 +480,7 @@ static int dchi2_impl(gvm_engine* e, const float* I_dev, int flag_opt, int norma
       if (gvm_grad_finish(e, c, I_dev, ksplit, flag_opt, normalize, result_dchi2_dev)) return 1;
     }
   }
-  if (e->world > 1) {
+  if (reduce) {
     if (gvm_dist_allreduce_f32(e, e->dist_grad, MN2)) return 1;
     k_add_inplace<<<(int)((MN2 + 255) / 256), 256, 0, e->stream>>>(caller_result, e->dist_grad, (long)MN2);
     GVM_LAUNCH(e);
@@ -508,8 +510,10 @@ int gvm_dev_alloc(gvm_engine* e, size_t bytes, void** out) {
   GVM_CUDA(cudaSetDevice(e->cfg.device));
   const size_t want = ((bytes ? bytes : 4) + 255) & ~(size_t)255;
   void* p = nullptr;
-  auto hit = e->pool_free.find(want);       // exact-size reuse: the callers' sizes repeat
-  if (hit != e->pool_free.end()) {
+  // exact-size reuse (the callers' sizes repeat), most recently freed block first
+  auto hit = e->pool_free.upper_bound(want);
+  if (hit != e->pool_free.begin() && std::prev(hit)->first == want) {
+    --hit;
     p = hit->second;
     e->pool_free.erase(hit);
   } else {

@@ -92,7 +92,7 @@ static int error_maps_impl(gvm_engine* e, const float* I_dev, int dist_mode, flo
   const gvm_config& g = e->cfg;
   const long MN = g.M * g.N;
   const int pix_blocks = (int)((MN + 255) / 256);
-  if (e->world <= 1) dist_mode = GVM_DIST_NONE;
+  if (e->world <= 1 || e->replicated) dist_mode = GVM_DIST_NONE;
   GVM_CUDA(cudaMemsetAsync(errors_dev, 0, 2 * (size_t)MN * sizeof(float), e->stream));
   double* wsum = e->red_out + 1;
   e->ev_used = 0;

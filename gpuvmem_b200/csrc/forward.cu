@@ -173,39 +173,88 @@ __global__ void __launch_bounds__(256) k_atten_image(float* __restrict__ out, lo
                              DELTAY, primary_beam);
 }
 
-template <bool kClip, bool kReal>
-__global__ void __launch_bounds__(256) k_image_prep(
-    float* __restrict__ I, const float* __restrict__ noise, const float* __restrict__ gcf,
-    const float* __restrict__ atten_plane, void* __restrict__ I_nu_out, long N, long M, float noise_cut, float minpix, float eta,
-    float threshold, int schedule, float nu, float nu_0, float fg_scale, float D, float pb_factor,
-    float pb_cutoff, float xobs, float yobs, double DELTAX, double DELTAY, int primary_beam) {
-  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (idx >= M * N) return;
-  const int i = (int)(idx / N), j = (int)(idx % N);
-  float I0 = I[idx];
-  float alpha = I[M * N + idx];
+struct PrepArgs {
+  float* I;
+  const float* noise;
+  const float* gcf;
+  const float* atten_plane;
+  void* out;
+  long N, M;
+  float noise_cut, minpix, eta, threshold, nu, nu_0, fg_scale, D, pb_factor, pb_cutoff, xobs, yobs;
+  double DELTAX, DELTAY;
+  int schedule, primary_beam;
+};
+// one pixel of clip2IWNoise + calculateInu + apply_beam2I + apply_GCF; I0 / alpha are updated by the clip
+template <bool kClip>
+__device__ __forceinline__ float prep_pixel(const PrepArgs& a, long idx, float& I0, float& alpha, float noise,
+                                            float atten, float gcf, bool& touched) {
   if (kClip) {
-    if (noise[idx] > noise_cut) {
-      I0 = (eta > 0.0f) ? 0.0f : -1.0f * eta * minpix;
+    if (noise > a.noise_cut) {
+      I0 = (a.eta > 0.0f) ? 0.0f : -1.0f * a.eta * a.minpix;
       alpha = 0.0f;
-      I[idx] = I0;
-      I[M * N + idx] = alpha;
-    } else if (I0 < threshold && schedule > 0) {
+      touched = true;
+    } else if (I0 < a.threshold && a.schedule > 0) {
       alpha = 0.0f;
-      I[M * N + idx] = alpha;
+      touched = true;
     }
   }
-  const float nudiv = nu / nu_0;
+  const float nudiv = a.nu / a.nu_0;
   float v = I0 * powf(nudiv, alpha);
-  const float floor_v = -1.0f * eta * minpix;
+  const float floor_v = -1.0f * a.eta * a.minpix;
   if (v < floor_v) v = floor_v;
-  const float atten = atten_plane ? atten_plane[idx]
-                                  : gvm_attenuation(i, j, D, pb_factor, pb_cutoff, nu, xobs, yobs, DELTAX,
-                                                    DELTAY, primary_beam);
-  v = v * atten * fg_scale;
-  if (gcf != nullptr) v = v * gcf[idx];
-  if (kReal) reinterpret_cast<float*>(I_nu_out)[idx] = v;
-  else reinterpret_cast<float2*>(I_nu_out)[idx] = make_float2(v, 0.0f);
+  v = v * atten * a.fg_scale;
+  if (a.gcf != nullptr) v = v * gcf;
+  return v;
+}
+__device__ __forceinline__ float prep_atten(const PrepArgs& a, long idx) {
+  return gvm_attenuation((int)(idx / a.N), (int)(idx % a.N), a.D, a.pb_factor, a.pb_cutoff, a.nu, a.xobs, a.yobs, a.DELTAX,
+                         a.DELTAY, a.primary_beam);
+}
+
+// scalar version: any image size / alignment
+template <bool kClip, bool kReal>
+__global__ void __launch_bounds__(256) k_image_prep(PrepArgs a) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long MN = a.M * a.N;
+  if (idx >= MN) return;
+  float I0 = a.I[idx], alpha = a.I[MN + idx];
+  bool touched = false;
+  const float atten = a.atten_plane ? a.atten_plane[idx] : prep_atten(a, idx);
+  const float v = prep_pixel<kClip>(a, idx, I0, alpha, kClip ? a.noise[idx] : 0.f, atten, a.gcf ? a.gcf[idx] : 1.f, touched);
+  if (kClip && touched) { a.I[idx] = I0; a.I[MN + idx] = alpha; }
+  if (kReal) reinterpret_cast<float*>(a.out)[idx] = v;
+  else reinterpret_cast<float2*>(a.out)[idx] = make_float2(v, 0.0f);
+}
+// four pixels per thread, 128-bit loads and stores (M N a multiple of 4, planes 16-byte aligned)
+template <bool kClip, bool kReal>
+__global__ void __launch_bounds__(256) k_image_prep4(PrepArgs a) {
+  const long q = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long MN = a.M * a.N, idx = 4 * q;
+  if (idx >= MN) return;
+  float4 I0 = reinterpret_cast<const float4*>(a.I)[q];
+  float4 al = reinterpret_cast<const float4*>(a.I + MN)[q];
+  float4 nz = make_float4(0.f, 0.f, 0.f, 0.f), at, gc = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (kClip) nz = __ldg(reinterpret_cast<const float4*>(a.noise) + q);
+  if (a.atten_plane) at = __ldg(reinterpret_cast<const float4*>(a.atten_plane) + q);
+  else at = make_float4(prep_atten(a, idx), prep_atten(a, idx + 1), prep_atten(a, idx + 2), prep_atten(a, idx + 3));
+  if (a.gcf) gc = __ldg(reinterpret_cast<const float4*>(a.gcf) + q);
+  bool touched = false;
+  float4 v;
+  v.x = prep_pixel<kClip>(a, idx, I0.x, al.x, nz.x, at.x, gc.x, touched);
+  v.y = prep_pixel<kClip>(a, idx + 1, I0.y, al.y, nz.y, at.y, gc.y, touched);
+  v.z = prep_pixel<kClip>(a, idx + 2, I0.z, al.z, nz.z, at.z, gc.z, touched);
+  v.w = prep_pixel<kClip>(a, idx + 3, I0.w, al.w, nz.w, at.w, gc.w, touched);
+  if (kClip && touched) {
+    reinterpret_cast<float4*>(a.I)[q] = I0;
+    reinterpret_cast<float4*>(a.I + MN)[q] = al;
+  }
+  if (kReal) {
+    reinterpret_cast<float4*>(a.out)[q] = v;
+  } else {
+    float4* o = reinterpret_cast<float4*>(a.out) + 2 * q;
+    o[0] = make_float4(v.x, 0.0f, v.y, 0.0f);
+    o[1] = make_float4(v.z, 0.0f, v.w, 0.0f);
+  }
 }
 
 // phase_rotate: src/functions.cu:2483-2518.
@@ -782,11 +831,19 @@ int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, 
   }
   e->last_forward_half = half ? 1 : 0;
   const float* atten_plane = gvm_channel_atten(e, c);
-#define GVM_PREP(CLIP, REAL)                                                                              \
-  k_image_prep<CLIP, REAL><<<pix_blocks, 256, 0, e->stream>>>(                                            \
-      I_dev, e->noise, e->gcf, atten_plane, e->I_nu, g.N, g.M, g.noise_cut, g.minpix, g.eta, g.threshold, flag_opt,    \
-      c.d.freq, g.nu_0, g.fg_scale, c.d.antenna_diameter, c.d.pb_factor, c.d.pb_cutoff, c.d.ref_xobs_pix, \
-      c.d.ref_yobs_pix, g.DELTAX, g.DELTAY, c.d.primary_beam)
+  PrepArgs pa;
+  pa.I = I_dev; pa.noise = e->noise; pa.gcf = e->gcf; pa.atten_plane = atten_plane; pa.out = e->I_nu;
+  pa.N = g.N; pa.M = g.M; pa.noise_cut = g.noise_cut; pa.minpix = g.minpix; pa.eta = g.eta; pa.threshold = g.threshold;
+  pa.nu = c.d.freq; pa.nu_0 = g.nu_0; pa.fg_scale = g.fg_scale; pa.D = c.d.antenna_diameter; pa.pb_factor = c.d.pb_factor;
+  pa.pb_cutoff = c.d.pb_cutoff; pa.xobs = c.d.ref_xobs_pix; pa.yobs = c.d.ref_yobs_pix; pa.DELTAX = g.DELTAX;
+  pa.DELTAY = g.DELTAY; pa.schedule = flag_opt; pa.primary_beam = c.d.primary_beam;
+  const bool vec4 = MN % 4 == 0 && ((uintptr_t)I_dev & 15) == 0;   // engine-owned planes come from cudaMalloc
+  const int prep_blocks = vec4 ? (int)((MN / 4 + 255) / 256) : pix_blocks;
+#define GVM_PREP(CLIP, REAL)                                                          \
+  do {                                                                                \
+    if (vec4) k_image_prep4<CLIP, REAL><<<prep_blocks, 256, 0, e->stream>>>(pa);     \
+    else k_image_prep<CLIP, REAL><<<prep_blocks, 256, 0, e->stream>>>(pa);           \
+  } while (0)
   if (first) { if (half) GVM_PREP(true, true); else GVM_PREP(true, false); }
   else       { if (half) GVM_PREP(false, true); else GVM_PREP(false, false); }
 #undef GVM_PREP

@@ -130,6 +130,7 @@ struct gvm_engine {
   // multi-GPU (dist_nccl.cu): one process per GPU, NCCL communicator over NVLink
   void* nccl_comm = nullptr;
   bool dist_aborted = false;
+  bool replicated = false;         // every rank holds ALL blocks (gridded data): sums are complete locally, no all-reduce
   int rank = 0, world = 1;
   float* dist_grad = nullptr;      // [2][MN] this rank's gradient contribution before the all-reduce
   int64_t collectives = 0;

@@ -41,6 +41,14 @@ class Fi {
   virtual uint64_t stateKey();
   // the host-side part of enqueueFi, for evaluations that replay a captured graph instead of launching
   virtual void noteEnqueued();
+  // Fused gradient step (ObjectiveFunction::calcGradient's fast path): restartDGi + calcGi + addToDphi of this term
+  // applied straight to `dphi` (already zeroed) without the per-term device_DS / result buffers. Returns false when
+  // the term does not support it (user plugins): the evaluation then takes the reference's loop. `first`: the term
+  // is the first of the objective function (Chi2 REPLACES dphi with its gradient, src/chi2.cu:60-70 — that equals
+  // accumulating into the zeroed dphi only when nothing was added before).
+  virtual bool gradInto(float* p, float* dphi, bool first);
+  // image the term's gradient is added to (TVariation: always 0, src/totalvariation.cu:46)
+  virtual int dphiImage() const { return imageToAdd; }
   float finishFi(float value);
   // fi.cuh:58-89: penalizatorIndex -1 keeps the current factor; an index past the -Z list
   // disables the term (factor 0); a negative one is a configuration error (print + exit)
@@ -91,6 +99,7 @@ class Chi2 : public Fi {
   bool enqueueFi(float* p, int slot) override;
   uint64_t stateKey() override;
   void noteEnqueued() override;
+  bool gradInto(float* p, float* dphi, bool first) override;
 
  private:
   float* result_dchi2 = nullptr;  // [image_count][M*N]
@@ -134,6 +143,7 @@ class TVariation : public Fi {
   bool priorSpec(int* kind, gvm_prior_params* pp) override;
   TVariation() { name = "Total Variation"; }
   explicit TVariation(float epsilon) : epsilon(epsilon) { name = "Total Variation"; }
+  int dphiImage() const override { return 0; }
   float getEpsilon() const { return epsilon; }
   void setEpsilon(float e) { epsilon = e; }
   float calcFi(float* p) override;
@@ -208,6 +218,7 @@ class GL1Norm : public Fi {
   void normalizePrior();
   float calcFi(float* p) override;
   void calcGi(float* p, float* xi) override;
+  bool gradInto(float* p, float* dphi, bool first) override;
 
  private:
   float* prior = nullptr;

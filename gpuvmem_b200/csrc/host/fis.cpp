@@ -84,6 +84,26 @@ uint64_t Chi2::stateKey() {
   h = mixv(h, fg_scale); h = mixv(h, g.noise_cut); h = mixv(h, g.threshold); h = mixv(h, g.flag_opt);
   return mixv(h, (int)normalize);
 }
+bool Fi::gradInto(float* p, float* dphi, bool) {
+  int kind = 0;
+  gvm_prior_params pp;
+  if (!priorSpec(&kind, &pp)) return false;
+  if (iteration > 0 && penalization_factor && G().flag_opt % 2 == imageIndex)
+    GVM_CHECK(gvm_prior_grad_add(G().engine, kind, p, imageIndex, &pp, penalization_factor, dphi, dphiImage()));
+  return true;
+}
+bool Chi2::gradInto(float* p, float* dphi, bool first) {
+  if (!first) return false;   // the overwrite of src/chi2.cu:60-70 would discard what earlier terms added
+  Globals& g = G();
+  GVM_CHECK(gvm_dchi2(g.engine, p, g.flag_opt, normalize ? 1 : 0, dphi));
+  return true;
+}
+// the swapped-argument quirk (see calcGi): the gradient lands in the prior image, dphi receives nothing
+bool GL1Norm::gradInto(float* p, float*, bool) {
+  restartDGi();
+  calcGi(p, nullptr);
+  return true;
+}
 void Fi::noteEnqueued() { enqueued_gate_closed = !(iteration > 0 && penalization_factor); }
 void Chi2::noteEnqueued() {
   Globals& g = G();

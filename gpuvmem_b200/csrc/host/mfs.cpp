@@ -404,6 +404,7 @@ void MFS::doGridding() {
     }
     ds.data.max_number_visibilities_in_channel_and_stokes = max;
   }
+  datasets_are_gridded = true;
   // the gridding work buffers stay allocated (a later block or run reuses them; cudaFree of tens of GB costs
   // more than the gridding itself) and go back in MFS::unSetDevice
 }
@@ -411,7 +412,7 @@ void MFS::doGridding() {
 bool shardRange(int max_nfreq, int chan, size_t Z, int rank, int world, size_t* lo, size_t* hi) {
   *lo = 0;
   *hi = Z;
-  if (world <= 1) return true;
+  if (world <= 1 || max_nfreq < 0) return true;   // max_nfreq < 0: replicated (every rank holds everything)
   if (max_nfreq >= world) return chan % world == rank;  // whole channels, the reference's rule
   *lo = Z * (size_t)rank / world;                         // contiguous visibility chunks
   *hi = Z * (size_t)(rank + 1) / world;
@@ -427,6 +428,13 @@ void MFS::shardAndUpload() {
   int max_nfreq = 1;
   for (MSDataset& ds : datasets) max_nfreq = std::max(max_nfreq, ds.data.total_frequencies);
   g.dist_kind = g.world <= 1 ? GVM_DIST_NONE : (max_nfreq >= g.world ? GVM_DIST_BLOCKS : GVM_DIST_CHUNKS);
+  // Gridded samples (-g) are few (at most one per uv cell) and their objective is image-sized work — FFTs and image
+  // kernels that do not shard: every rank keeps all of them and evaluates the objective itself, without the
+  // all-reduce of the [2][M][N] gradient (which alone costs more than the evaluation). The weighting and the
+  // gridding before it ARE distributed (gvm_weights_dist, gvm_grid_block_dist).
+  const bool replicated = g.world > 1 && gridding && datasets_are_gridded;
+  if (g.world > 1) GVM_CHECK(gvm_dist_set_replicated(g.engine, replicated ? 1 : 0));
+  if (replicated) { g.dist_kind = GVM_DIST_NONE; max_nfreq = -1; }
   for (MSDataset& ds : datasets)
     for (Field& f : ds.fields) {
       f.engine_slot.assign(f.visibilities.size(), std::vector<int>(ds.data.nstokes, -1));
@@ -774,6 +782,7 @@ void MFS::writeResiduals() {
       }
     datasets = std::move(ungridded);   // a second call finds them in place
     ungridded.clear();
+    datasets_are_gridded = false;      // the originals shard over the ranks again (chunks / channels)
     GVM_CHECK(gvm_clear_channels(g.engine));
     shardAndUpload();
     if (chi2) {

@@ -42,6 +42,9 @@ class ObjectiveFunction {
   // one CUDA graph per objective evaluation: the second evaluation with the same image pointer and term state is
   // captured, later ones replay it with a single launch (GVM_GRAPHS=0 or setGraphs(false): plain launches)
   void setGraphs(bool on) { graphs = on; }
+  // gradient terms written straight into xi (Fi::gradInto); GVM_FUSED_GRADIENT=0 or setFusedGradient(false): the
+  // reference's restartDGi / calcGi / addToDphi loop
+  void setFusedGradient(bool on) { fused_gradient = on; }
   long graphReplays() const { return n_replays; }
 
  private:
@@ -62,6 +65,8 @@ class ObjectiveFunction {
   bool graphs = defaultGraphs();
   long n_replays = 0;
   static bool defaultGraphs();
+  bool fused_gradient = defaultFusedGradient();
+  static bool defaultFusedGradient();
   void dropGraphs();
 };
 

@@ -136,6 +136,7 @@ class MFS : public Synthesizer {
   void doGridding();
   Vars variables;
   std::vector<MSDataset> datasets;
+  bool datasets_are_gridded = false;  // `datasets` currently holds the output of doGridding
   float nongridded_chi2 = 0.0f;       // the "Non-gridded chi2" of the last writeResiduals (gridded runs)
   std::vector<MSDataset> ungridded;   // originals kept when -g replaces them (residual write-back)
   headerValues header;

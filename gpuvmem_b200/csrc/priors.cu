@@ -183,18 +183,26 @@ __device__ __forceinline__ void block_reduce_finish(float s0, float s1, float mx
 template <int KIND>
 __global__ void __launch_bounds__(kT) k_prior_value(PriorArgs a, double* partials, float* pmax,
                                                     unsigned int* counter, double* out) {
-  const long MN = (long)a.N * a.N;
+  // rows over the blocks, columns over the threads: (i, j) without a 64-bit division per pixel, four independent
+  // coalesced loads in flight per thread
   float s = 0.f;
-  for (long idx = blockIdx.x * (long)kT + threadIdx.x; idx < MN; idx += (long)gridDim.x * kT)
-    s += prior_value_at<KIND>(a, (int)(idx / a.N), (int)(idx % a.N));
+  for (int i = blockIdx.x; i < a.N; i += gridDim.x) {
+#pragma unroll 4
+    for (int j = threadIdx.x; j < a.N; j += kT) s += prior_value_at<KIND>(a, i, j);
+  }
   block_reduce_finish(s, 0.f, 0.f, partials, pmax, counter, out);
 }
 
-template <int KIND>
+// kAdd: dgi += lambda * g in the same pass (DS written by the gradient kernel and then added by AddToDPhi in the
+// reference, src/functions.cu:3890 — the same fp32 value is added, without the round trip through device_DS).
+// 2-D launch (x: column, y: row): no 64-bit division per pixel.
+template <int KIND, bool kAdd>
 __global__ void __launch_bounds__(kT) k_prior_grad(PriorArgs a, float* __restrict__ dgi) {
-  const long MN = (long)a.N * a.N;
-  const long idx = blockIdx.x * (long)kT + threadIdx.x;
-  if (idx < MN) dgi[idx] = prior_grad_at<KIND>(a, (int)(idx / a.N), (int)(idx % a.N));
+  const int j = blockIdx.x * kT + threadIdx.x, i = blockIdx.y;
+  if (j >= a.N) return;
+  const long idx = (long)a.N * i + j;
+  const float g = prior_grad_at<KIND>(a, i, j);
+  dgi[idx] = kAdd ? __fadd_rn(dgi[idx], g) : g;   // never contracted with the lambda product: same value as DS + AddToDPhi
 }
 
 __global__ void __launch_bounds__(kT) k_add_to_dphi(float* __restrict__ dphi,
@@ -371,13 +379,15 @@ template <int KIND>
 int launch_value(gvm_engine* e, const PriorArgs& a, double* out = nullptr) {
   RedBuf r = aux_red(e);
   if (out) r.out = out;
-  k_prior_value<KIND><<<red_grid(e, (long)a.N * a.N), kT, 0, e->stream>>>(a, r.partials, r.pmax, r.counter, r.out);
+  const int blocks = a.N < e->red_blocks ? a.N : e->red_blocks;
+  k_prior_value<KIND><<<blocks, kT, 0, e->stream>>>(a, r.partials, r.pmax, r.counter, r.out);
   return 0;
 }
 template <int KIND>
-int launch_grad(gvm_engine* e, const PriorArgs& a, float* dgi) {
-  const long MN = (long)a.N * a.N;
-  k_prior_grad<KIND><<<(int)((MN + kT - 1) / kT), kT, 0, e->stream>>>(a, dgi);
+int launch_grad(gvm_engine* e, const PriorArgs& a, float* dgi, bool add) {
+  const dim3 grid((unsigned)((a.N + kT - 1) / kT), (unsigned)a.N);
+  if (add) k_prior_grad<KIND, true><<<grid, kT, 0, e->stream>>>(a, dgi);
+  else k_prior_grad<KIND, false><<<grid, kT, 0, e->stream>>>(a, dgi);
   return 0;
 }
 
@@ -461,25 +471,38 @@ int gvm_fetch_slots(gvm_engine* e, int n, double* values_out) {
   return gvm_fetch_slots_enqueue(e, n) || gvm_fetch_slots_wait(e, n, values_out);
 }
 
-int gvm_prior_grad(gvm_engine* e, int kind, const float* I_dev, int image_index,
-                   const gvm_prior_params* p, float lambda, float* dgi_dev) {
+static int prior_grad_launch(gvm_engine* e, int kind, const float* I_dev, int image_index,
+                             const gvm_prior_params* p, float lambda, float* out_dev, bool add) {
   GVM_CUDA(cudaSetDevice(e->cfg.device));
   PriorArgs a;
   if (make_args(e, kind, I_dev, image_index, p, lambda, &a)) return 1;
   switch (kind) {
-    case GVM_PRIOR_ENTROPY: launch_grad<GVM_PRIOR_ENTROPY>(e, a, dgi_dev); break;
-    case GVM_PRIOR_L1: launch_grad<GVM_PRIOR_L1>(e, a, dgi_dev); break;
-    case GVM_PRIOR_TV: launch_grad<GVM_PRIOR_TV>(e, a, dgi_dev); break;
-    case GVM_PRIOR_TSV: launch_grad<GVM_PRIOR_TSV>(e, a, dgi_dev); break;
-    case GVM_PRIOR_LAPLACIAN: launch_grad<GVM_PRIOR_LAPLACIAN>(e, a, dgi_dev); break;
-    case GVM_PRIOR_QUADRATIC: launch_grad<GVM_PRIOR_QUADRATIC>(e, a, dgi_dev); break;
-    case GVM_PRIOR_GENTROPY: launch_grad<GVM_PRIOR_GENTROPY>(e, a, dgi_dev); break;
-    case GVM_PRIOR_GL1: launch_grad<GVM_PRIOR_GL1>(e, a, dgi_dev); break;
+    case GVM_PRIOR_ENTROPY: launch_grad<GVM_PRIOR_ENTROPY>(e, a, out_dev, add); break;
+    case GVM_PRIOR_L1: launch_grad<GVM_PRIOR_L1>(e, a, out_dev, add); break;
+    case GVM_PRIOR_TV: launch_grad<GVM_PRIOR_TV>(e, a, out_dev, add); break;
+    case GVM_PRIOR_TSV: launch_grad<GVM_PRIOR_TSV>(e, a, out_dev, add); break;
+    case GVM_PRIOR_LAPLACIAN: launch_grad<GVM_PRIOR_LAPLACIAN>(e, a, out_dev, add); break;
+    case GVM_PRIOR_QUADRATIC: launch_grad<GVM_PRIOR_QUADRATIC>(e, a, out_dev, add); break;
+    case GVM_PRIOR_GENTROPY: launch_grad<GVM_PRIOR_GENTROPY>(e, a, out_dev, add); break;
+    case GVM_PRIOR_GL1: launch_grad<GVM_PRIOR_GL1>(e, a, out_dev, add); break;
     default: gvm_set_error("gvm_prior_grad: unknown kind %d", kind); return 1;
   }
   GVM_LAUNCH(e);
   GVM_CUDA(cudaGetLastError());
   return 0;
+}
+
+int gvm_prior_grad(gvm_engine* e, int kind, const float* I_dev, int image_index,
+                   const gvm_prior_params* p, float lambda, float* dgi_dev) {
+  return prior_grad_launch(e, kind, I_dev, image_index, p, lambda, dgi_dev, false);
+}
+
+int gvm_prior_grad_add(gvm_engine* e, int kind, const float* I_dev, int image_index, const gvm_prior_params* p,
+                       float lambda, float* dphi_dev, int image_to_add) {
+  if (image_to_add < 0 || image_to_add > 1) { gvm_set_error("gvm_prior_grad_add: image %d out of range", image_to_add); return 1; }
+  const long MN = (long)e->cfg.M * e->cfg.N;
+  if (dphi_dev + MN * image_to_add == I_dev + MN * image_index) { gvm_set_error("gvm_prior_grad_add: dphi aliases the image"); return 1; }
+  return prior_grad_launch(e, kind, I_dev, image_index, p, lambda, dphi_dev + MN * image_to_add, true);
 }
 
 int gvm_add_to_dphi(gvm_engine* e, float* dphi_dev, const float* dgi_dev, int index) {

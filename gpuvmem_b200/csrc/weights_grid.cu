@@ -920,6 +920,7 @@ int gvm_weights_dist(gvm_engine* e, int scheme, float robust, int nblocks, const
   const bool use_taper = taper && taper->enabled;
   const size_t MN = (size_t)(M * N);
   const double adu = fabs(deltau), adv = fabs(deltav);
+  PhaseTimer pt;
   long zmax = 1, smax = 1;
   for (int b = 0; b < nblocks; b++) {
     zmax = Z[b] > zmax ? (long)Z[b] : zmax;
@@ -995,14 +996,18 @@ int gvm_weights_dist(gvm_engine* e, int scheme, float robust, int nblocks, const
     for (int b = 0; b < nblocks; b++) {
       int64_t lo, hi;
       if (load_slice(b, &lo, &hi, true)) return 1;
+      pt.mark("dist weights: slice upload + cells + sort");
       if (ring_accumulate((long)(hi - lo))) return 1;
+      pt.mark("dist weights: ring accumulate + broadcast");
       // the first-pass grid is never cleared between blocks and the half-plane sum of squares is taken after
       // each one (src/briggsweightingscheme.cu:59-106): every rank repeats that sequential host sum
       if (gvm_fast_d2h(hgrid.data(), d_grid.p, MN * 4, st)) return 1;
       for (long m = 0; m < M; m++)
         for (long n = N / 2; n < N; n++) sum_g2 += hgrid[N * m + n] * hgrid[N * m + n];
     }
+    pt.mark("dist weights: grid to host + half-plane sum of squares");
     sum_thread.join();
+    pt.mark("dist weights: wait for the host sum of weights");
     const float avg = sum_g2 / sum_w;
     f_squared = (5.0f * powf(10.0f, -robust)) * (5.0f * powf(10.0f, -robust)) / avg;
     grid_resident = nblocks == 1;
@@ -1024,6 +1029,7 @@ int gvm_weights_dist(gvm_engine* e, int scheme, float robust, int nblocks, const
       WG_CUDA(cudaGetLastError());
     }
     if (gather_weights(b, lo, hi)) return 1;
+    pt.mark("dist weights: apply + all-gather + weights to host");
     if (b + 1 < nblocks) WG_CUDA(cudaMemsetAsync(d_grid.p, 0, MN * 4, st));   // per-block sums in the second pass
     if (use_taper) apply_taper_host(taper, scheme, (long)Z[b], uvw_m[b], freqs[b], w[b]);
   }

@@ -102,8 +102,10 @@ SIGNATURES = {
     "gvm_state_epoch": (C.c_int64, [_P]),
     "gvm_weights_dist": (C.c_int, [_P, C.c_int, C.c_float, C.c_int, _P, _P, _P, _P, _P]),
     "gvm_grid_block_dist": (C.c_int, [_P, C.c_float, C.c_int64, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "gvm_prior_grad_add": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_float, _P, C.c_int]),
     "gvm_sort_pairs_host": (C.c_int, [C.c_int, _P, _P, C.c_int64, C.c_int]),
     "gvm_dist_abort": (C.c_int, [_P]),
+    "gvm_dist_set_replicated": (C.c_int, [_P, C.c_int]),
     "gvm_dist_broadcast": (C.c_int, [_P, _P, C.c_int64, C.c_int]),
     "gvm_weights": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_int64, C.c_int64, C.c_double, C.c_double,
                               C.c_int, _P, _P, _P, _P, C.POINTER(gvm_taper)]),

@@ -248,6 +248,11 @@ int64_t gvm_state_epoch(gvm_engine* e);
  * accumulated), like DS/DL1NormK/... write device_DS. */
 int gvm_prior_grad(gvm_engine* e, int kind, const float* I_dev, int image_index,
                    const gvm_prior_params* p, float lambda, float* dgi_dev);
+/* The two steps above in one pass: dphi[image_to_add] += lambda * d(term)/dI without the round trip through a
+ * per-term device_DS buffer (the gradient kernel + AddToDPhi pair of every prior, src/functions.cu:3890) — the same
+ * fp32 value is added, so the result is bit-identical. dphi_dev: [2][M][N]. */
+int gvm_prior_grad_add(gvm_engine* e, int kind, const float* I_dev, int image_index, const gvm_prior_params* p,
+                       float lambda, float* dphi_dev, int image_to_add);
 /* linkAddToDPhi / AddToDPhi (src/functions.cu:4560/3890): dphi[index] += dgi. */
 int gvm_add_to_dphi(gvm_engine* e, float* dphi_dev, const float* dgi_dev, int index);
 
@@ -311,6 +316,12 @@ int gvm_dist_unique_id(char* id_out, size_t bytes);
 int gvm_dist_init(gvm_engine* e, int rank, int world, const char* id, size_t bytes);
 int gvm_dist_rank(gvm_engine* e);
 int gvm_dist_world(gvm_engine* e);
+/* Replicated mode: every rank holds ALL visibility blocks and computes the complete chi2 / gradient itself, so
+ * gvm_chi2, gvm_dchi2 and gvm_error_maps skip their all-reduces. For gridded data (-g): the evaluation is then
+ * image-sized work (FFTs, image kernels) that does not shard, while the all-reduce of the [2][M][N] gradient would
+ * cost more than the few samples it saves; only the preprocessing (gvm_weights_dist / gvm_grid_block_dist) is
+ * distributed. Identical inputs give identical results on every rank. */
+int gvm_dist_set_replicated(gvm_engine* e, int on);
 int gvm_dist_allreduce(gvm_engine* e, float* buf_dev, int64_t n);
 /* Broadcast n floats from `root` on the engine stream (the image replica of a multi-rank job: one rank
  * uploads it, the others receive it over NVLink instead of each pulling it over PCIe). */

@@ -217,3 +217,43 @@ def test_single_synchronisation_objective_equals_the_per_term_loop(monkeypatch):
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and not a[1][1:].any()
     assert a[2] == b[2] and np.array_equal(a[3], b[3]) and a[3][1:].all()
     assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5]) and a[6] == b[6]
+
+
+@pytest.mark.parametrize("fi_spec", [None, "Chi2:-1:0:0,TotalVariation:0:0:0,Quadratic:1:0:0,L1-Norm:2:1:1",
+                                     "Entropy:0:0:0,Chi2:-1:0:0"])
+def test_fused_gradient_and_graph_replay_equal_the_reference_loop(monkeypatch, fi_spec):
+    """ObjectiveFunction's fast paths against the reference's loops, bit for bit: (a) calcGradient with every term
+    writing straight into xi (Fi::gradInto: chi2 accumulated in place, priors added by gvm_prior_grad_add) vs
+    restartDGi / calcGi / addToDphi through per-term buffers (GVM_FUSED_GRADIENT=0); (b) calcFunction replaying a
+    captured CUDA graph vs plain launches (GVM_GRAPHS=0). The third spec puts a prior BEFORE Chi2: Chi2's addToDphi
+    overwrites dphi (src/chi2.cu:60-70), so the fused path must step aside and the result still be the loop's."""
+    from _ref_runner import probe_image
+    p = synth.make_problem(N=128, nvis=12000, nchan=2, freq0=1.0e11, bandwidth=4e9, seed=56, grid_fill=0.9)
+    host.set_quiet(True)
+    out = {}
+    for mode in ("fast", "loop"):
+        monkeypatch.setenv("GVM_FUSED_GRADIENT", "1" if mode == "fast" else "0")
+        monkeypatch.setenv("GVM_GRAPHS", "1" if mode == "fast" else "0")
+        s = host.Session(p, args="-z 0.001,0.1 -Z 0.01,0.005,0.002,0.001 -t 4", fi_spec=fi_spec)
+        try:
+            start = s.get_image()
+            s.set_image(probe_image(p.N, np.float32(0.001), 0.1))
+            s.set_iteration(1)
+            vals = [s.calc_function() for _ in range(4)]       # 1st plain, 2nd captured, 3rd and 4th replayed
+            g0 = s.calc_gradient(1)
+            s.set_flag(1)
+            g1 = s.calc_gradient(1)
+            s.set_flag(0)
+            s.set_image(start)
+            s.set_iteration(0)
+            img, _ = s.run()
+            out[mode] = (vals, g0, g1, img)
+        finally:
+            s.close()
+    a, b = out["fast"], out["loop"]
+    for (va, fa), (vb, fb) in zip(a[0], b[0]):
+        assert va == vb and np.array_equal(fa, fb)
+    assert a[0][0][0] == a[0][3][0], "replaying the graph must reproduce the plain evaluation"
+    assert np.array_equal(a[1], b[1]) and a[1][0].any()
+    assert np.array_equal(a[2], b[2])
+    assert np.array_equal(a[3], b[3])

@@ -462,7 +462,7 @@ def test_lbfgs_vector_ops_and_device_pool(small):
     assert L.gvm_dev_copy(h, a, host, 4096, 0) == 0
     assert L.gvm_dev_free(h, a) == 0
     assert L.gvm_dev_alloc(h, 4096, C.byref(b)) == 0
-    assert b.value == a.value
+    assert b.value == a.value, "the most recently freed block of that size is handed out again"
     back = (C.c_float * 1024)()
     assert L.gvm_dev_copy(h, back, b, 4096, 1) == 0
     assert not any(back)
