@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "gvm_internal.cuh"
@@ -169,6 +170,25 @@ int gvm_dist_init(gvm_engine* e, int rank, int world, const char* id, size_t byt
   e->nccl_comm = comm;
   e->rank = rank;
   e->world = world;
+  // NCCL connects lazily: the first use of every transport (ring / tree of the collectives, every point-to-point
+  // pair) costs hundreds of milliseconds. Pay that here, once, with messages large enough to bring up all channels,
+  // instead of inside the first weighting / gridding / gradient of the run (GVM_NCCL_WARMUP=0 skips it).
+  const char* wu = getenv("GVM_NCCL_WARMUP");
+  if (!(wu && *wu == '0')) {
+    const size_t n = (size_t)8 << 20;   // 32 MB of floats per message
+    float* buf = nullptr;
+    GVM_CUDA(cudaMalloc(&buf, (size_t)(world + 1) * n * sizeof(float)));
+    GVM_CUDA(cudaMemsetAsync(buf, 0, (size_t)(world + 1) * n * sizeof(float), e->stream));
+    int rc = gvm_dist_allreduce_f32(e, buf, n) || gvm_dist_allreduce_u32_max(e, reinterpret_cast<uint32_t*>(buf), n) ||
+             gvm_dist_broadcast_bytes(e, buf, n * sizeof(float), 0) || gvm_dist_group_begin(e);
+    for (int peer = 0; peer < world && !rc; peer++)
+      rc = gvm_dist_send(e, buf, n * sizeof(float), peer) || gvm_dist_recv(e, buf + (size_t)(peer + 1) * n, n * sizeof(float), peer);
+    rc = rc || gvm_dist_group_end(e);
+    if (!rc && cudaStreamSynchronize(e->stream) != cudaSuccess) { gvm_set_error("gvm_dist_init: warm-up failed"); rc = 1; }
+    cudaFree(buf);
+    e->collectives = 0;
+    if (rc) return 1;
+  }
   return 0;
 }
 

@@ -485,6 +485,27 @@ struct DevBuf {
   template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// One cudaMalloc instead of a dozen: cudaMalloc / cudaFree cost 10-45 ms EACH on this platform (more than most of
+// the kernels here), so the work buffers of a call are carved out of a per-thread arena that only ever grows and is
+// kept between calls (gvm_grid_release returns it).
+struct Arena {
+  DevBuf buf;
+  size_t used = 0;
+  static size_t round(size_t n) { return (n + 511) & ~(size_t)511; }
+  int reserve(size_t total) { used = 0; return buf.ensure(total + 512); }
+  template <class T> T* take(size_t count) {
+    T* p = reinterpret_cast<T*>(static_cast<char*>(buf.p) + used);
+    used += round(count * sizeof(T));
+    return used <= buf.bytes ? p : nullptr;
+  }
+};
+thread_local Arena g_arena_a, g_arena_b, g_arena_c;
+// a carved buffer with DevBuf's accessors
+struct Raw {
+  void* p;
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
+
 // result of the last gvm_grid_block of this thread (device resident until fetched)
 struct GridResult {
   DevBuf uvw, Vo, w;
@@ -544,20 +565,18 @@ struct PhaseTimer {
   }
 };
 
-// Replay of the sorted pair records tile by tile (wk.rec, wk.tstart, wk.tend -> wk.gw, wk.gV): tiles in decreasing
-// order of their sample count, one warp per tile.
-int tile_replay(GridWork& wk, long ntiles, int ntx, int ck_m, int ck_n, int sx, int sy, long M, long N, cudaStream_t stream) {
-  if (wk.ord0.ensure((size_t)ntiles * 4) || wk.ordk0.ensure((size_t)ntiles * 4)) return 1;
-  k_tile_order_keys<<<(int)((ntiles + 255) / 256), 256, 0, stream>>>(wk.tstart.as<int>(), wk.tend.as<int>(), ntiles,
-                                                                     wk.ordk0.as<uint32_t>(), wk.ord0.as<uint32_t>());
+// Replay of the sorted pair records tile by tile (rec, tstart, tend -> gw, gV): tiles in decreasing order of their
+// sample count, one warp per tile. ordk / ord: ntiles words each; sort_tmp: gvm_sort_temp_bytes(ntiles).
+int tile_replay_raw(uint32_t* ordk, uint32_t* ord, void* sort_tmp, const int* tstart, const int* tend, const float4* rec,
+                    const float* ck, float* gw, float2* gV, long ntiles, int ntx, int ck_m, int ck_n, int sx, int sy,
+                    long M, long N, cudaStream_t stream) {
+  k_tile_order_keys<<<(int)((ntiles + 255) / 256), 256, 0, stream>>>(tstart, tend, ntiles, ordk, ord);
   WG_CUDA(cudaGetLastError());
-  if (sort_pairs(wk.tmp, wk.ordk0.as<uint32_t>(), wk.ord0.as<uint32_t>(), ntiles, 31, stream)) return 1;
+  if (gvm_sort_pairs_u32(ordk, ord, (size_t)ntiles, 31, sort_tmp, stream)) return 1;
   const int taps = (2 * sx + 1) * (2 * sy + 1);
   const int rounds = (taps + 31) / 32;
-#define GVM_GRID_TILES(R)                                                                                                 \
-  k_grid_tiles<R><<<(unsigned)ntiles, 32, 0, stream>>>(wk.ord0.as<uint32_t>(), wk.tstart.as<int>(), wk.tend.as<int>(),    \
-                                                       wk.rec.as<float4>(), wk.ck.as<float>(), ck_m, ck_n, sx, sy, M, N,  \
-                                                       ntx, wk.gw.as<float>(), wk.gV.as<float2>())
+#define GVM_GRID_TILES(R) \
+  k_grid_tiles<R><<<(unsigned)ntiles, 32, 0, stream>>>(ord, tstart, tend, rec, ck, ck_m, ck_n, sx, sy, M, N, ntx, gw, gV)
   if (rounds <= 1) GVM_GRID_TILES(1);
   else if (rounds <= 2) GVM_GRID_TILES(2);
   else if (rounds <= 3) GVM_GRID_TILES(3);
@@ -567,6 +586,14 @@ int tile_replay(GridWork& wk, long ntiles, int ntx, int ck_m, int ck_n, int sx, 
 #undef GVM_GRID_TILES
   WG_CUDA(cudaGetLastError());
   return 0;
+}
+int tile_replay(GridWork& wk, long ntiles, int ntx, int ck_m, int ck_n, int sx, int sy, long M, long N, cudaStream_t stream) {
+  if (wk.ord0.ensure((size_t)ntiles * 4) || wk.ordk0.ensure((size_t)ntiles * 4) ||
+      wk.tmp.ensure(gvm_sort_temp_bytes((size_t)ntiles)))
+    return 1;
+  return tile_replay_raw(wk.ordk0.as<uint32_t>(), wk.ord0.as<uint32_t>(), wk.tmp.p, wk.tstart.as<int>(), wk.tend.as<int>(),
+                         wk.rec.as<float4>(), wk.ck.as<float>(), wk.gw.as<float>(), wk.gV.as<float2>(), ntiles, ntx, ck_m,
+                         ck_n, sx, sy, M, N, stream);
 }
 
 // The tile-sequential accumulation (k_tile_* + k_grid_tiles): fills gw/gV like k_grid_accumulate does.
@@ -682,15 +709,16 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
   int end_bit = 1;
   while (end_bit < 32 && (1ull << end_bit) <= MN) end_bit++;
   end_bit = 32;  // the off-grid sentinel is all ones: sort on all 32 bits
-  DevBuf d_grid, d_uvw, d_w, d_k0, d_v0, d_tmp;
-  if (d_grid.ensure(MN * 4)) return 1;
-  WG_CUDA(cudaMemset(d_grid.p, 0, MN * 4));
   long zmax = 1;
   for (int b = 0; b < nblocks; b++) zmax = Z[b] > zmax ? (long)Z[b] : zmax;
   if (zmax >= (long)0x7FFFFFFF) { gvm_set_error("gvm_weights: block too large"); return 1; }
-  if (d_uvw.ensure((size_t)zmax * 24) || d_w.ensure((size_t)zmax * 4) || d_k0.ensure((size_t)zmax * 4) ||
-      d_v0.ensure((size_t)zmax * 4))
-    return 1;
+  Arena& A = g_arena_a;   // one allocation for everything (kept between calls)
+  if (A.reserve(MN * 4 + (size_t)zmax * (24 + 4 + 4 + 4) + gvm_sort_temp_bytes((size_t)zmax) + 8 * 512)) return 1;
+  Raw d_grid{A.take<float>(MN)}, d_uvw{A.take<double>((size_t)zmax * 3)}, d_w{A.take<float>((size_t)zmax)},
+      d_k0{A.take<uint32_t>((size_t)zmax)}, d_v0{A.take<uint32_t>((size_t)zmax)};
+  void* d_tmp = A.take<char>(gvm_sort_temp_bytes((size_t)zmax));
+  if (!d_tmp) { gvm_set_error("gvm_weights: arena too small"); return 1; }
+  WG_CUDA(cudaMemset(d_grid.p, 0, MN * 4));
 
   auto load_and_sort = [&](int b) -> int {
     const long z = (long)Z[b];
@@ -699,7 +727,7 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
     k_weight_cells<<<(int)((z + 255) / 256), 256>>>(d_uvw.as<double>(), z, freqs[b], adu, adv, M, N,
                                                     d_k0.as<uint32_t>(), d_v0.as<uint32_t>());
     WG_CUDA(cudaGetLastError());
-    return sort_pairs(d_tmp, d_k0.as<uint32_t>(), d_v0.as<uint32_t>(), z, end_bit);
+    return z > 0 ? gvm_sort_pairs_u32(d_k0.as<uint32_t>(), d_v0.as<uint32_t>(), (size_t)z, end_bit, d_tmp, nullptr) : 0;
   };
 
   float f_squared = 0.0f;
@@ -869,6 +897,7 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
 
 int gvm_grid_release(void) {
   g_grid_work = GridWork();
+  g_arena_a = Arena(); g_arena_b = Arena(); g_arena_c = Arena();
   return 0;
 }
 
@@ -928,10 +957,12 @@ int gvm_weights_dist(gvm_engine* e, int scheme, float robust, int nblocks, const
     smax = per > smax ? per : smax;
   }
   if (zmax >= (long)0x7FFFFFFF) { gvm_set_error("gvm_weights_dist: block too large"); return 1; }
-  DevBuf d_grid, d_uvw, d_w, d_k0, d_v0, d_tmp, d_wfull;
-  if (d_uvw.ensure((size_t)smax * 24) || d_w.ensure((size_t)smax * 4) || d_wfull.ensure((size_t)zmax * 4)) return 1;
-  if (scheme != GVM_W_RADIAL)
-    if (d_grid.ensure(MN * 4) || d_k0.ensure((size_t)smax * 4) || d_v0.ensure((size_t)smax * 4)) return 1;
+  Arena& A = g_arena_a;   // one allocation for everything (kept between calls)
+  if (A.reserve(MN * 4 + (size_t)smax * (24 + 4 + 4 + 4) + (size_t)zmax * 4 + gvm_sort_temp_bytes((size_t)smax) + 8 * 512)) return 1;
+  Raw d_grid{A.take<float>(MN)}, d_uvw{A.take<double>((size_t)smax * 3)}, d_w{A.take<float>((size_t)smax)},
+      d_k0{A.take<uint32_t>((size_t)smax)}, d_v0{A.take<uint32_t>((size_t)smax)}, d_wfull{A.take<float>((size_t)zmax)};
+  void* d_tmp = A.take<char>(gvm_sort_temp_bytes((size_t)smax));
+  if (!d_tmp) { gvm_set_error("gvm_weights_dist: arena too small"); return 1; }
 
   // this rank's slice of block b on the device (+ its cells, sorted) ; returns the slice
   auto load_slice = [&](int b, int64_t* lo, int64_t* hi, bool cells) -> int {
@@ -944,7 +975,7 @@ int gvm_weights_dist(gvm_engine* e, int scheme, float robust, int nblocks, const
     k_weight_cells<<<(int)((n + 255) / 256), 256, 0, st>>>(d_uvw.as<double>(), n, freqs[b], adu, adv, M, N,
                                                            d_k0.as<uint32_t>(), d_v0.as<uint32_t>());
     WG_CUDA(cudaGetLastError());
-    return sort_pairs(d_tmp, d_k0.as<uint32_t>(), d_v0.as<uint32_t>(), n, 32, st);
+    return gvm_sort_pairs_u32(d_k0.as<uint32_t>(), d_v0.as<uint32_t>(), (size_t)n, 32, d_tmp, st);
   };
   // the grid of cell sums goes down the ranks: receive what the lower ranks summed, continue with this rank's
   // samples, hand it on; the last rank holds the complete sums and broadcasts them
@@ -1059,7 +1090,6 @@ int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_
   const size_t MN = (size_t)(M * N);
   *nout = 0;
   PhaseTimer pt;
-  GridWork& wk = g_grid_work;
   GridResult& res = g_grid_result;
   res.count = 0;
   int64_t lo, hi;
@@ -1068,54 +1098,84 @@ int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_
   const size_t zz = (size_t)(nloc > 0 ? nloc : 1);
   const int ntx = (int)((N + kTile - 1) / kTile), nty = (int)((M + kTile - 1) / kTile);
   const long ntiles = (long)ntx * nty;
-  if (wk.uvw.ensure(zz * 24) || wk.Vo.ensure(zz * 8) || wk.w.ensure(zz * 4) || wk.ck.ensure((size_t)ck_m * ck_n * 4) ||
-      wk.gw.ensure(MN * 4) || wk.gV.ensure(MN * 8) || wk.flags.ensure(MN * 4) || wk.pos.ensure(MN * 4) ||
-      wk.tstart.ensure((size_t)ntiles * 4) || wk.tend.ensure((size_t)ntiles * 4) || wk.cpos.ensure(2 * zz * 4) ||
-      wk.cnt.ensure(2 * zz * 4 + ((size_t)2 * world + 1) * 4) || wk.off.ensure(2 * zz * 4))
-    return 1;
+  // ---- arena A: the slice, the grids, per-tile and per-sample tables (three arenas per call instead of ~20 cudaMallocs)
+  const size_t scan_n2 = gvm_scan_temp_bytes(2 * zz), scan_mn = gvm_scan_temp_bytes(MN), sort_tiles = gvm_sort_temp_bytes((size_t)ntiles);
+  size_t tmpA = scan_n2 > scan_mn ? scan_n2 : scan_mn;
+  tmpA = tmpA > sort_tiles ? tmpA : sort_tiles;
+  Arena& A = g_arena_a;
+  {
+    const size_t r = 512;
+    const size_t total = zz * 24 + zz * 8 + zz * 4 + (size_t)ck_m * ck_n * 4 + MN * 4 + MN * 8 + MN * 4 + MN * 4 +
+                         4 * (size_t)ntiles * 4 + 3 * (2 * zz * 4) + ((size_t)2 * world + 1) * 4 +
+                         (size_t)world * 2 * world * 4 + tmpA + 24 * r;
+    if (A.reserve(total)) return 1;
+  }
+  double* d_uvw = A.take<double>(zz * 3);
+  float2* d_Vo = A.take<float2>(zz);
+  float* d_w = A.take<float>(zz);
+  float* d_ck = A.take<float>((size_t)ck_m * ck_n);
+  float* d_gw = A.take<float>(MN);
+  float2* d_gV = A.take<float2>(MN);
+  int* d_flags = A.take<int>(MN);
+  int* d_pos = A.take<int>(MN);
+  int* d_tstart = A.take<int>((size_t)ntiles);
+  int* d_tend = A.take<int>((size_t)ntiles);
+  uint32_t* d_ordk = A.take<uint32_t>((size_t)ntiles);
+  uint32_t* d_ord = A.take<uint32_t>((size_t)ntiles);
+  uint32_t* d_cpos = A.take<uint32_t>(2 * zz);
+  int* d_cnt = A.take<int>(2 * zz);
+  int* d_off = A.take<int>(2 * zz);
+  uint32_t* d_start = A.take<uint32_t>((size_t)2 * world + 1);
+  uint32_t* d_counts = A.take<uint32_t>((size_t)world * 2 * world);
+  void* d_tmpA = A.take<char>(tmpA);
+  if (!d_tmpA) { gvm_set_error("gvm_grid_block_dist: arena A too small"); return 1; }
+  pt.mark("dist grid: arena A");
   if (nloc > 0)
-    if (gvm_fast_h2d(wk.uvw.p, uvw_m + 3 * lo, zz * 24, st) || gvm_fast_h2d(wk.Vo.p, Vo + 2 * lo, zz * 8, st) ||
-        gvm_fast_h2d(wk.w.p, w + lo, zz * 4, st))
+    if (gvm_fast_h2d(d_uvw, uvw_m + 3 * lo, zz * 24, st) || gvm_fast_h2d(d_Vo, Vo + 2 * lo, zz * 8, st) ||
+        gvm_fast_h2d(d_w, w + lo, zz * 4, st))
       return 1;
-  WG_CUDA(cudaMemcpyAsync(wk.ck.p, ckernel, (size_t)ck_m * ck_n * 4, cudaMemcpyHostToDevice, st));
+  WG_CUDA(cudaMemcpyAsync(d_ck, ckernel, (size_t)ck_m * ck_n * 4, cudaMemcpyHostToDevice, st));
   pt.mark("dist grid: upload of the slice");
   // ---- local (tile, sample) pairs of the slice, in ascending local doubled index (originals, then twins)
   long npairs = 0;
   if (n2 > 0) {
     const int blocks = (int)((n2 + 255) / 256);
-    k_tile_count<<<blocks, 256, 0, st>>>(wk.uvw.as<double>(), nloc, freq, deltau, deltav, M, N, sx, sy, wk.cpos.as<uint32_t>(),
-                                         wk.cnt.as<int>());
+    k_tile_count<<<blocks, 256, 0, st>>>(d_uvw, nloc, freq, deltau, deltav, M, N, sx, sy, d_cpos, d_cnt);
     WG_CUDA(cudaGetLastError());
-    if (exclusive_scan(wk.tmp, wk.cnt.p, wk.off.p, n2, st)) return 1;
+    WG_CUDA(cudaMemcpyAsync(d_off, d_cnt, (size_t)n2 * 4, cudaMemcpyDeviceToDevice, st));
+    if (gvm_exclusive_scan_u32(reinterpret_cast<uint32_t*>(d_off), (size_t)n2, d_tmpA, st)) return 1;
     int last_off = 0, last_cnt = 0;
-    WG_CUDA(cudaMemcpyAsync(&last_off, wk.off.as<int>() + (n2 - 1), 4, cudaMemcpyDeviceToHost, st));
-    WG_CUDA(cudaMemcpyAsync(&last_cnt, wk.cnt.as<int>() + (n2 - 1), 4, cudaMemcpyDeviceToHost, st));
+    WG_CUDA(cudaMemcpyAsync(&last_off, d_off + (n2 - 1), 4, cudaMemcpyDeviceToHost, st));
+    WG_CUDA(cudaMemcpyAsync(&last_cnt, d_cnt + (n2 - 1), 4, cudaMemcpyDeviceToHost, st));
     WG_CUDA(cudaStreamSynchronize(st));
     npairs = (long)last_off + last_cnt;
     if (npairs >= (long)0x7FFFFFFF) { gvm_set_error("gvm_grid_block_dist: too many (tile, sample) pairs on one rank"); return 1; }
   }
+  // ---- arena B: the pairs of this rank (tile id, sample, destination) and the send buffers
   const size_t np = (size_t)(npairs > 0 ? npairs : 1);
-  if (wk.k0.ensure(np * 4) || wk.v0.ensure(np * 4) || wk.dk.ensure(np * 4) || wk.dv.ensure(np * 4) || wk.sk.ensure(np * 4) ||
-      wk.srec.ensure(np * 16))
-    return 1;
+  Arena& B = g_arena_b;
+  if (B.reserve(np * (4 * 5 + 16) + gvm_sort_temp_bytes(np) + 16 * 512)) return 1;
+  uint32_t* d_pk = B.take<uint32_t>(np);     // tile id of the pair
+  uint32_t* d_pz = B.take<uint32_t>(np);     // local doubled sample index
+  uint32_t* d_dk = B.take<uint32_t>(np);     // destination key
+  uint32_t* d_dv = B.take<uint32_t>(np);     // pair index, sorted by destination
+  uint32_t* d_sk = B.take<uint32_t>(np);     // send: tile ids in destination order
+  float4* d_srec = B.take<float4>(np);       // send: records in destination order
+  void* d_tmpB = B.take<char>(gvm_sort_temp_bytes(np));
+  if (!d_tmpB) { gvm_set_error("gvm_grid_block_dist: arena B too small"); return 1; }
   std::vector<uint32_t> dstart((size_t)2 * world + 1, (uint32_t)npairs);
   if (npairs > 0) {
     const int blocks = (int)((n2 + 255) / 256), pb = (int)((npairs + 255) / 256);
-    k_tile_emit<<<blocks, 256, 0, st>>>(wk.cpos.as<uint32_t>(), wk.off.as<int>(), n2, M, N, sx, sy, ntx, wk.k0.as<uint32_t>(),
-                                        wk.v0.as<uint32_t>());
-    k_pair_dest<<<pb, 256, 0, st>>>(wk.k0.as<uint32_t>(), wk.v0.as<uint32_t>(), npairs, nloc, ntx, world, wk.dk.as<uint32_t>(),
-                                    wk.dv.as<uint32_t>());
+    k_tile_emit<<<blocks, 256, 0, st>>>(d_cpos, d_off, n2, M, N, sx, sy, ntx, d_pk, d_pz);
+    k_pair_dest<<<pb, 256, 0, st>>>(d_pk, d_pz, npairs, nloc, ntx, world, d_dk, d_dv);
     WG_CUDA(cudaGetLastError());
     int bits = 1;
     while ((1 << bits) < 2 * world) bits++;
-    if (sort_pairs(wk.tmp, wk.dk.as<uint32_t>(), wk.dv.as<uint32_t>(), npairs, bits, st)) return 1;
-    uint32_t* d_start = wk.cnt.as<uint32_t>();    // free again: 2 W + 1 words
+    if (gvm_sort_pairs_u32(d_dk, d_dv, (size_t)npairs, bits, d_tmpB, st)) return 1;
     std::vector<uint32_t> init((size_t)2 * world + 1, (uint32_t)npairs);
     WG_CUDA(cudaMemcpyAsync(d_start, init.data(), init.size() * 4, cudaMemcpyHostToDevice, st));
-    k_dest_starts<<<pb, 256, 0, st>>>(wk.dk.as<uint32_t>(), npairs, d_start);
-    k_pair_pack<<<pb, 256, 0, st>>>(wk.dv.as<uint32_t>(), wk.k0.as<uint32_t>(), wk.v0.as<uint32_t>(), npairs, nloc,
-                                    wk.cpos.as<uint32_t>(), wk.Vo.as<float2>(), wk.w.as<float>(), wk.sk.as<uint32_t>(),
-                                    wk.srec.as<float4>());
+    k_dest_starts<<<pb, 256, 0, st>>>(d_dk, npairs, d_start);
+    k_pair_pack<<<pb, 256, 0, st>>>(d_dv, d_pk, d_pz, npairs, nloc, d_cpos, d_Vo, d_w, d_sk, d_srec);
     WG_CUDA(cudaGetLastError());
     WG_CUDA(cudaMemcpyAsync(dstart.data(), d_start, dstart.size() * 4, cudaMemcpyDeviceToHost, st));
     WG_CUDA(cudaStreamSynchronize(st));
@@ -1126,17 +1186,14 @@ int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_
   // ---- counts of every (source, destination): counts[s][d], d = half * W + owner
   std::vector<uint32_t> counts((size_t)world * 2 * world, 0u);
   {
-    DevBuf d_counts;
-    if (d_counts.ensure(counts.size() * 4)) return 1;
     std::vector<uint32_t> mine((size_t)2 * world);
     for (int d = 0; d < 2 * world; d++) mine[d] = dstart[d + 1] - dstart[d];
-    WG_CUDA(cudaMemcpyAsync(d_counts.as<uint32_t>() + (size_t)rank * 2 * world, mine.data(), mine.size() * 4,
-                            cudaMemcpyHostToDevice, st));
+    WG_CUDA(cudaMemcpyAsync(d_counts + (size_t)rank * 2 * world, mine.data(), mine.size() * 4, cudaMemcpyHostToDevice, st));
     if (gvm_dist_group_begin(e)) return 1;
     for (int r = 0; r < world; r++)
-      if (gvm_dist_broadcast_bytes(e, d_counts.as<uint32_t>() + (size_t)r * 2 * world, (size_t)2 * world * 4, r)) return 1;
+      if (gvm_dist_broadcast_bytes(e, d_counts + (size_t)r * 2 * world, (size_t)2 * world * 4, r)) return 1;
     if (gvm_dist_group_end(e)) return 1;
-    WG_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, counts.size() * 4, cudaMemcpyDeviceToHost, st));
+    WG_CUDA(cudaMemcpyAsync(counts.data(), d_counts, counts.size() * 4, cudaMemcpyDeviceToHost, st));
     WG_CUDA(cudaStreamSynchronize(st));
   }
   // receive layout on this rank: (originals | twins) x (source rank) — ascending doubled-sample order
@@ -1146,8 +1203,16 @@ int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_
       roff[(size_t)h * world + s_ + 1] = roff[(size_t)h * world + s_] + counts[(size_t)s_ * 2 * world + (size_t)h * world + rank];
   const size_t nrecv = roff[(size_t)2 * world];
   if (nrecv >= (size_t)0x7FFFFFFF) { gvm_set_error("gvm_grid_block_dist: too many pairs for one owner"); return 1; }
+  // ---- arena C: what this rank receives as a tile owner
   const size_t nr = nrecv > 0 ? nrecv : 1;
-  if (wk.rk.ensure(nr * 4) || wk.rrec.ensure(nr * 16) || wk.rec.ensure(nr * 16) || wk.dv.ensure(nr * 4)) return 1;
+  Arena& Cc = g_arena_c;
+  if (Cc.reserve(nr * (4 + 16 + 16 + 4) + gvm_sort_temp_bytes(nr) + 8 * 512)) return 1;
+  uint32_t* d_rk = Cc.take<uint32_t>(nr);
+  float4* d_rrec = Cc.take<float4>(nr);
+  float4* d_rec = Cc.take<float4>(nr);
+  uint32_t* d_ridx = Cc.take<uint32_t>(nr);
+  void* d_tmpC = Cc.take<char>(gvm_sort_temp_bytes(nr));
+  if (!d_tmpC) { gvm_set_error("gvm_grid_block_dist: arena C too small"); return 1; }
   if (gvm_dist_group_begin(e)) return 1;
   for (int peer = 0; peer < world; peer++)
     for (int h = 0; h < 2; h++) {
@@ -1155,46 +1220,47 @@ int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_
       const size_t ns = (size_t)(dstart[d + 1] - dstart[d]);
       const size_t nrv = roff[(size_t)h * world + peer + 1] - roff[(size_t)h * world + peer];   // what it receives from `peer`
       if (ns > 0) {
-        if (gvm_dist_send(e, wk.sk.as<uint32_t>() + dstart[d], ns * 4, peer)) return 1;
-        if (gvm_dist_send(e, wk.srec.as<float4>() + dstart[d], ns * 16, peer)) return 1;
+        if (gvm_dist_send(e, d_sk + dstart[d], ns * 4, peer)) return 1;
+        if (gvm_dist_send(e, d_srec + dstart[d], ns * 16, peer)) return 1;
       }
       if (nrv > 0) {
-        if (gvm_dist_recv(e, wk.rk.as<uint32_t>() + roff[(size_t)h * world + peer], nrv * 4, peer)) return 1;
-        if (gvm_dist_recv(e, wk.rrec.as<float4>() + roff[(size_t)h * world + peer], nrv * 16, peer)) return 1;
+        if (gvm_dist_recv(e, d_rk + roff[(size_t)h * world + peer], nrv * 4, peer)) return 1;
+        if (gvm_dist_recv(e, d_rrec + roff[(size_t)h * world + peer], nrv * 16, peer)) return 1;
       }
     }
   if (gvm_dist_group_end(e)) return 1;
   pt.mark("dist grid: all-to-all of the pairs");
   // ---- owner side: stable sort by tile, records in replay order, replay
-  WG_CUDA(cudaMemsetAsync(wk.tstart.p, 0, (size_t)ntiles * 4, st));
-  WG_CUDA(cudaMemsetAsync(wk.tend.p, 0, (size_t)ntiles * 4, st));
+  WG_CUDA(cudaMemsetAsync(d_tstart, 0, (size_t)ntiles * 4, st));
+  WG_CUDA(cudaMemsetAsync(d_tend, 0, (size_t)ntiles * 4, st));
   if (nrecv > 0) {
     const int rb = (int)((nrecv + 255) / 256);
-    k_iota<<<rb, 256, 0, st>>>(wk.dv.as<uint32_t>(), (long)nrecv);
+    k_iota<<<rb, 256, 0, st>>>(d_ridx, (long)nrecv);
     int bits = 1;
     while ((1L << bits) < ntiles) bits++;
-    if (sort_pairs(wk.tmp, wk.rk.as<uint32_t>(), wk.dv.as<uint32_t>(), (long)nrecv, bits, st)) return 1;
-    k_recv_gather<<<rb, 256, 0, st>>>(wk.rk.as<uint32_t>(), wk.dv.as<uint32_t>(), (long)nrecv, wk.rrec.as<float4>(),
-                                      wk.tstart.as<int>(), wk.tend.as<int>(), wk.rec.as<float4>());
+    if (gvm_sort_pairs_u32(d_rk, d_ridx, nrecv, bits, d_tmpC, st)) return 1;
+    k_recv_gather<<<rb, 256, 0, st>>>(d_rk, d_ridx, (long)nrecv, d_rrec, d_tstart, d_tend, d_rec);
     WG_CUDA(cudaGetLastError());
   }
-  if (tile_replay(wk, ntiles, ntx, ck_m, ck_n, sx, sy, M, N, st)) return 1;
+  if (tile_replay_raw(d_ordk, d_ord, d_tmpA, d_tstart, d_tend, d_rec, d_ck, d_gw, d_gV, ntiles, ntx, ck_m, ck_n, sx, sy, M, N, st))
+    return 1;
   pt.mark("dist grid: owner sort + tile replay");
   // every cell was computed by its owner and is exactly zero elsewhere: merge the bit patterns
-  if (gvm_dist_allreduce_u32_max(e, wk.gw.as<uint32_t>(), MN)) return 1;
-  if (gvm_dist_allreduce_u32_max(e, wk.gV.as<uint32_t>(), 2 * MN)) return 1;
-  k_grid_flags<<<(int)((MN + 255) / 256), 256, 0, st>>>(wk.gw.as<float>(), (long)MN, wk.flags.as<int>());
-  if (exclusive_scan(wk.tmp, wk.flags.p, wk.pos.p, (long)MN, st)) return 1;
+  if (gvm_dist_allreduce_u32_max(e, reinterpret_cast<uint32_t*>(d_gw), MN)) return 1;
+  if (gvm_dist_allreduce_u32_max(e, reinterpret_cast<uint32_t*>(d_gV), 2 * MN)) return 1;
+  k_grid_flags<<<(int)((MN + 255) / 256), 256, 0, st>>>(d_gw, (long)MN, d_flags);
+  WG_CUDA(cudaMemcpyAsync(d_pos, d_flags, MN * 4, cudaMemcpyDeviceToDevice, st));
+  if (gvm_exclusive_scan_u32(reinterpret_cast<uint32_t*>(d_pos), MN, d_tmpA, st)) return 1;
   int last_pos = 0, last_flag = 0;
-  WG_CUDA(cudaMemcpyAsync(&last_pos, wk.pos.as<int>() + (MN - 1), 4, cudaMemcpyDeviceToHost, st));
-  WG_CUDA(cudaMemcpyAsync(&last_flag, wk.flags.as<int>() + (MN - 1), 4, cudaMemcpyDeviceToHost, st));
+  WG_CUDA(cudaMemcpyAsync(&last_pos, d_pos + (MN - 1), 4, cudaMemcpyDeviceToHost, st));
+  WG_CUDA(cudaMemcpyAsync(&last_flag, d_flags + (MN - 1), 4, cudaMemcpyDeviceToHost, st));
   WG_CUDA(cudaStreamSynchronize(st));
   const long count = (long)last_pos + last_flag;
   if (count > 0) {
     if (res.uvw.ensure((size_t)count * 24) || res.Vo.ensure((size_t)count * 8) || res.w.ensure((size_t)count * 4)) return 1;
-    k_grid_compact<<<(int)((MN + 255) / 256), 256, 0, st>>>(wk.gw.as<float>(), wk.gV.as<float2>(), wk.pos.as<int>(), M, N,
-                                                            deltau, deltav, gvm_freq_to_wavelength(freq),
-                                                            res.uvw.as<double>(), res.Vo.as<float2>(), res.w.as<float>());
+    k_grid_compact<<<(int)((MN + 255) / 256), 256, 0, st>>>(d_gw, d_gV, d_pos, M, N, deltau, deltav,
+                                                            gvm_freq_to_wavelength(freq), res.uvw.as<double>(),
+                                                            res.Vo.as<float2>(), res.w.as<float>());
     WG_CUDA(cudaGetLastError());
     WG_CUDA(cudaStreamSynchronize(st));
   }
