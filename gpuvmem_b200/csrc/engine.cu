@@ -138,6 +138,7 @@ static int create_impl(gvm_engine* e, const gvm_config* cfg, const cudaDevicePro
   }
   e->have_plan = true;
   cufftSetStream(e->plan, e->stream);
+  gvm_hostcopy_warm();
   return 0;
 }
 

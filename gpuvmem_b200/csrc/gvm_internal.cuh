@@ -289,5 +289,6 @@ int gvm_pick_grad_mode(gvm_engine* e, GvmChannel& c);
 // hostcopy.cu: pipelined copies between pageable host memory and the device (synchronous)
 int gvm_fast_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t stream);
 int gvm_fast_d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t stream);
+void gvm_hostcopy_warm();
 void gvm_ev_begin(gvm_engine* e);
 void gvm_ev_end(gvm_engine* e);

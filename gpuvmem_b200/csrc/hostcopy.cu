@@ -128,3 +128,7 @@ int gvm_fast_d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t
   }
   return 0;
 }
+
+// The pinned ring costs ~0.1 s to create (cudaMallocHost); gvm_create does it once so that the first large upload of
+// this thread (weighting, gridding, gvm_add_channel) does not pay for it.
+void gvm_hostcopy_warm() { g_ring.ensure(); }

@@ -277,24 +277,6 @@ __global__ void __launch_bounds__(256) k_tile_emit(const uint32_t* __restrict__ 
     }
 }
 
-// pass 3 (after the stable sort by tile): first / one-past-last pair of every tile, and the 16-byte record
-// of every pair in sorted order: (centre, w, Vo.re, Vo.im) with the twin's visibility conjugated
-__global__ void __launch_bounds__(256) k_tile_gather(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                     long npairs, long Z, const uint32_t* __restrict__ cpos,
-                                                     const float2* __restrict__ Vo, const float* __restrict__ w,
-                                                     int* __restrict__ tstart, int* __restrict__ tend,
-                                                     float4* __restrict__ rec) {
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (i >= npairs) return;
-  const uint32_t t = keys[i], z = vals[i];
-  if (i == 0 || keys[i - 1] != t) tstart[t] = (int)i;
-  if (i == npairs - 1 || keys[i + 1] != t) tend[t] = (int)(i + 1);
-  const long vi = (z < (uint32_t)Z) ? (long)z : (long)z - Z;
-  float2 vo = Vo[vi];
-  if (z >= (uint32_t)Z) vo.y *= -1.0f;
-  rec[i] = make_float4(__uint_as_float(cpos[z]), w[vi], vo.x, vo.y);
-}
-
 // tiles sorted by decreasing sample count: the long replays start first (longest-processing-time order)
 __global__ void __launch_bounds__(256) k_tile_order_keys(const int* __restrict__ tstart, const int* __restrict__ tend,
                                                          long ntiles, uint32_t* __restrict__ keys,
@@ -499,7 +481,7 @@ struct Arena {
     return used <= buf.bytes ? p : nullptr;
   }
 };
-thread_local Arena g_arena_a, g_arena_b, g_arena_c;
+thread_local Arena g_arena_a, g_arena_b, g_arena_c, g_arena_r;
 // a carved buffer with DevBuf's accessors
 struct Raw {
   void* p;
@@ -508,16 +490,17 @@ struct Raw {
 
 // result of the last gvm_grid_block of this thread (device resident until fetched)
 struct GridResult {
-  DevBuf uvw, Vo, w;
+  DevBuf uvw, Vo, w;           // merge path (GVM_GRID_MERGE=1)
+  double* uvw_p = nullptr;     // where the compacted samples are: the buffers above or the result arena
+  float2* Vo_p = nullptr;
+  float* w_p = nullptr;
   long count = 0;
 };
 thread_local GridResult g_grid_result;
 // work buffers of gvm_grid_block, kept between calls (a cudaMalloc/cudaFree pair of several GB per
 // block costs more than the kernels); gvm_grid_release() returns them
 struct GridWork {
-  DevBuf uvw, Vo, w, ck, k0, v0, tmp, gw, gV, flags, pos, start;
-  DevBuf cpos, cnt, off, rec, tstart, tend, ord0, ordk0;   // tile-sequential path
-  DevBuf sk, srec, rk, rrec, dk, dv;                        // distributed gridding: send / receive buffers
+  DevBuf uvw, Vo, w, ck, k0, v0, tmp, gw, gV, flags, pos, start;   // merge path (the tile replay uses the arenas)
 };
 thread_local GridWork g_grid_work;
 
@@ -587,58 +570,6 @@ int tile_replay_raw(uint32_t* ordk, uint32_t* ord, void* sort_tmp, const int* ts
   WG_CUDA(cudaGetLastError());
   return 0;
 }
-int tile_replay(GridWork& wk, long ntiles, int ntx, int ck_m, int ck_n, int sx, int sy, long M, long N, cudaStream_t stream) {
-  if (wk.ord0.ensure((size_t)ntiles * 4) || wk.ordk0.ensure((size_t)ntiles * 4) ||
-      wk.tmp.ensure(gvm_sort_temp_bytes((size_t)ntiles)))
-    return 1;
-  return tile_replay_raw(wk.ordk0.as<uint32_t>(), wk.ord0.as<uint32_t>(), wk.tmp.p, wk.tstart.as<int>(), wk.tend.as<int>(),
-                         wk.rec.as<float4>(), wk.ck.as<float>(), wk.gw.as<float>(), wk.gV.as<float2>(), ntiles, ntx, ck_m,
-                         ck_n, sx, sy, M, N, stream);
-}
-
-// The tile-sequential accumulation (k_tile_* + k_grid_tiles): fills gw/gV like k_grid_accumulate does.
-// *done = false (nothing launched) when the problem does not fit its 16-bit centre packing / 31-bit pair count.
-int grid_tiles_path(GridWork& wk, long Z, float freq, double deltau, double deltav, long M, long N, int ck_m,
-                    int ck_n, int sx, int sy, bool* done) {
-  *done = false;
-  const long n2 = 2 * Z;
-  if (M + 2L * sy >= 65536 || N + 2L * sx >= 65536 || n2 > 400000000L) return 0;
-  const int ntx = (int)((N + kTile - 1) / kTile), nty = (int)((M + kTile - 1) / kTile);
-  const long ntiles = (long)ntx * nty;
-  long npairs = 0;
-  if (wk.tstart.ensure((size_t)ntiles * 4) || wk.tend.ensure((size_t)ntiles * 4)) return 1;
-  WG_CUDA(cudaMemset(wk.tstart.p, 0, (size_t)ntiles * 4));
-  WG_CUDA(cudaMemset(wk.tend.p, 0, (size_t)ntiles * 4));
-  if (n2 > 0) {
-    if (wk.cpos.ensure((size_t)n2 * 4) || wk.cnt.ensure((size_t)n2 * 4) || wk.off.ensure((size_t)n2 * 4)) return 1;
-    const int blocks = (int)((n2 + 255) / 256);
-    k_tile_count<<<blocks, 256>>>(wk.uvw.as<double>(), Z, freq, deltau, deltav, M, N, sx, sy, wk.cpos.as<uint32_t>(),
-                                  wk.cnt.as<int>());
-    WG_CUDA(cudaGetLastError());
-    if (exclusive_scan(wk.tmp, wk.cnt.p, wk.off.p, n2)) return 1;
-    int last_off = 0, last_cnt = 0;
-    WG_CUDA(cudaMemcpy(&last_off, wk.off.as<int>() + (n2 - 1), 4, cudaMemcpyDeviceToHost));
-    WG_CUDA(cudaMemcpy(&last_cnt, wk.cnt.as<int>() + (n2 - 1), 4, cudaMemcpyDeviceToHost));
-    npairs = (long)last_off + last_cnt;
-    if (npairs > 0) {
-      if (wk.k0.ensure((size_t)npairs * 4) || wk.v0.ensure((size_t)npairs * 4) || wk.rec.ensure((size_t)npairs * 16)) return 1;
-      k_tile_emit<<<blocks, 256>>>(wk.cpos.as<uint32_t>(), wk.off.as<int>(), n2, M, N, sx, sy, ntx, wk.k0.as<uint32_t>(),
-                                   wk.v0.as<uint32_t>());
-      WG_CUDA(cudaGetLastError());
-      int bits = 1;
-      while ((1L << bits) < ntiles) bits++;
-      if (sort_pairs(wk.tmp, wk.k0.as<uint32_t>(), wk.v0.as<uint32_t>(), npairs, bits)) return 1;
-      k_tile_gather<<<(int)((npairs + 255) / 256), 256>>>(wk.k0.as<uint32_t>(), wk.v0.as<uint32_t>(), npairs, Z,
-                                                          wk.cpos.as<uint32_t>(), wk.Vo.as<float2>(), wk.w.as<float>(),
-                                                          wk.tstart.as<int>(), wk.tend.as<int>(), wk.rec.as<float4>());
-      WG_CUDA(cudaGetLastError());
-    }
-  }
-  if (tile_replay(wk, ntiles, ntx, ck_m, ck_n, sx, sy, M, N, nullptr)) return 1;
-  *done = true;
-  return 0;
-}
-
 // std::accumulate(weights, 0.0f) per block, then summed over the blocks (src/briggsweightingscheme.cu:46-57)
 float briggs_sum_of_weights(int nblocks, const int64_t* Z, float* const* w) {
   float sum_w = 0.0f;
@@ -668,6 +599,10 @@ void apply_taper_host(const gvm_taper* t, int scheme, long Z, const double* uvw_
 }  // namespace
 
 extern "C" {
+
+static int grid_block_core(gvm_engine* e, int device, cudaStream_t st, long M, long N, double deltau, double deltav, float freq,
+                           int64_t Z, const double* uvw_m, const float* Vo, const float* w, const float* ckernel, int ck_m,
+                           int ck_n, int sx, int sy, int64_t* nout);
 
 int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, double deltau, double deltav,
                 int nblocks, const int64_t* Z, const double* const* uvw_m, const float* freqs,
@@ -800,6 +735,20 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
   const size_t ext = (size_t)(M + 2 * support_y) * (size_t)(N + 2 * support_x);
   if (ext >= (size_t)kNoCell || n2 >= (long)0x7FFFFFFF) { gvm_set_error("gvm_grid_block: problem too large"); return 1; }
   *nout = 0;
+  {
+    // default: the tile-sequential replay (the same code as the multi-rank path, with one rank); the per-cell k-way
+    // merge below is the fallback for grids beyond the 16-bit centre packing and the cross-check (GVM_GRID_MERGE=1);
+    // both give the reference's summation order, i.e. bit-identical results
+    const char* force_merge = getenv("GVM_GRID_MERGE");
+    const bool fits = M + 2L * support_y < 65536 && N + 2L * support_x < 65536 && n2 <= 400000000L;
+    if (fits && !(force_merge && *force_merge == '1')) {
+      if (grid_block_core(nullptr, device, nullptr, M, N, deltau, deltav, freq, Z, uvw_m, Vo, w, ckernel, ck_m, ck_n, support_x,
+                          support_y, nout))
+        return 1;
+      if (uvw_out || Vo_out || w_out) return gvm_grid_fetch(uvw_out, Vo_out, w_out);
+      return 0;
+    }
+  }
   PhaseTimer pt;
   GridWork& wk = g_grid_work;
   DevBuf &d_uvw = wk.uvw, &d_Vo = wk.Vo, &d_w = wk.w, &d_ck = wk.ck, &d_k0 = wk.k0, &d_v0 = wk.v0,
@@ -817,16 +766,7 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
   }
   pt.mark("grid: upload");
   WG_CUDA(cudaMemcpy(d_ck.p, ckernel, (size_t)ck_m * ck_n * 4, cudaMemcpyHostToDevice));
-  // accumulation: tile-sequential replay by default, the per-cell k-way merge as fallback / cross-check
-  // (GVM_GRID_MERGE=1); both give the reference's summation order, i.e. bit-identical results
-  bool tiles_done = false;
   {
-    const char* force_merge = getenv("GVM_GRID_MERGE");
-    if (!(force_merge && *force_merge == '1'))
-      if (grid_tiles_path(wk, (long)Z, freq, deltau, deltav, M, N, ck_m, ck_n, support_x, support_y, &tiles_done)) return 1;
-  }
-  pt.mark("grid: tile replay");
-  if (!tiles_done) {
     if (n2 > 0) {
       k_grid_centres<<<(int)((n2 + 255) / 256), 256>>>(d_uvw.as<double>(), (long)Z, freq, deltau, deltav, M, N,
                                                        support_x, support_y, d_k0.as<uint32_t>(),
@@ -888,6 +828,7 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
     WG_CUDA(cudaDeviceSynchronize());
   }
   pt.mark("grid: compact");
+  res.uvw_p = d_uo.as<double>(); res.Vo_p = d_Vout.as<float2>(); res.w_p = d_wo.as<float>();
   res.count = count;
   *nout = count;
   // outputs may be omitted: the caller sizes its arrays from *nout and calls gvm_grid_fetch
@@ -897,7 +838,8 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
 
 int gvm_grid_release(void) {
   g_grid_work = GridWork();
-  g_arena_a = Arena(); g_arena_b = Arena(); g_arena_c = Arena();
+  g_arena_a = Arena(); g_arena_b = Arena(); g_arena_c = Arena(); g_arena_r = Arena();
+  g_grid_result = GridResult();
   return 0;
 }
 
@@ -905,9 +847,9 @@ int gvm_grid_fetch(double* uvw_out, float* Vo_out, float* w_out) {
   GridResult& res = g_grid_result;
   const size_t count = (size_t)res.count;
   if (count > 0) {
-    if (uvw_out && gvm_fast_d2h(uvw_out, res.uvw.p, count * 24, 0)) return 1;
-    if (Vo_out && gvm_fast_d2h(Vo_out, res.Vo.p, count * 8, 0)) return 1;
-    if (w_out && gvm_fast_d2h(w_out, res.w.p, count * 4, 0)) return 1;
+    if (uvw_out && gvm_fast_d2h(uvw_out, res.uvw_p, count * 24, 0)) return 1;
+    if (Vo_out && gvm_fast_d2h(Vo_out, res.Vo_p, count * 8, 0)) return 1;
+    if (w_out && gvm_fast_d2h(w_out, res.w_p, count * 4, 0)) return 1;
   }
   return 0;
 }
@@ -1068,25 +1010,12 @@ int gvm_weights_dist(gvm_engine* e, int scheme, float robust, int nblocks, const
   return 0;
 }
 
-int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_m, const float* Vo, const float* w,
-                        const float* ckernel, int ck_m, int ck_n, int support_x, int support_y, int64_t* nout) {
-  const gvm_config& g = e->cfg;
-  const double deltax = GVM_RPDEG_D * g.DELTAX, deltay = GVM_RPDEG_D * g.DELTAY;
-  const double deltau = 1.0 / (g.M * deltax), deltav = 1.0 / (g.N * deltay);
-  const long M = g.M, N = g.N;
-  const int sx = support_x, sy = support_y;
-  const bool fits = M + 2L * sy < 65536 && N + 2L * sx < 65536;   // 16-bit centre packing of the tile replay
-  if (e->world <= 1 || !fits)
-    return gvm_grid_block(g.device, M, N, deltau, deltav, freq, Z, uvw_m, Vo, w, ckernel, ck_m, ck_n, sx, sy, nullptr, nullptr,
-                          nullptr, nout);
-  if (!nout || Z < 0 || ck_m < 1 || ck_n < 1 || sx < 0 || sy < 0) { gvm_set_error("gvm_grid_block_dist: bad argument"); return 1; }
-  if ((2 * sx + 1) * (2 * sy + 1) > kMaxTaps) {
-    gvm_set_error("gvm_grid_block_dist: kernel support %d x %d exceeds %d taps", sx, sy, kMaxTaps);
-    return 1;
-  }
-  WG_CUDA(cudaSetDevice(g.device));
-  cudaStream_t st = e->stream;
-  const int rank = e->rank, world = e->world;
+// The tile-replay gridding of one block on `world` ranks (e == nullptr: one rank, default stream, no collectives).
+static int grid_block_core(gvm_engine* e, int device, cudaStream_t st, long M, long N, double deltau, double deltav, float freq,
+                           int64_t Z, const double* uvw_m, const float* Vo, const float* w, const float* ckernel, int ck_m,
+                           int ck_n, int sx, int sy, int64_t* nout) {
+  const int rank = e ? e->rank : 0, world = e ? e->world : 1;
+  WG_CUDA(cudaSetDevice(device));
   const size_t MN = (size_t)(M * N);
   *nout = 0;
   PhaseTimer pt;
@@ -1188,13 +1117,17 @@ int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_
   {
     std::vector<uint32_t> mine((size_t)2 * world);
     for (int d = 0; d < 2 * world; d++) mine[d] = dstart[d + 1] - dstart[d];
-    WG_CUDA(cudaMemcpyAsync(d_counts + (size_t)rank * 2 * world, mine.data(), mine.size() * 4, cudaMemcpyHostToDevice, st));
-    if (gvm_dist_group_begin(e)) return 1;
-    for (int r = 0; r < world; r++)
-      if (gvm_dist_broadcast_bytes(e, d_counts + (size_t)r * 2 * world, (size_t)2 * world * 4, r)) return 1;
-    if (gvm_dist_group_end(e)) return 1;
-    WG_CUDA(cudaMemcpyAsync(counts.data(), d_counts, counts.size() * 4, cudaMemcpyDeviceToHost, st));
-    WG_CUDA(cudaStreamSynchronize(st));
+    if (world > 1) {
+      WG_CUDA(cudaMemcpyAsync(d_counts + (size_t)rank * 2 * world, mine.data(), mine.size() * 4, cudaMemcpyHostToDevice, st));
+      if (gvm_dist_group_begin(e)) return 1;
+      for (int r = 0; r < world; r++)
+        if (gvm_dist_broadcast_bytes(e, d_counts + (size_t)r * 2 * world, (size_t)2 * world * 4, r)) return 1;
+      if (gvm_dist_group_end(e)) return 1;
+      WG_CUDA(cudaMemcpyAsync(counts.data(), d_counts, counts.size() * 4, cudaMemcpyDeviceToHost, st));
+      WG_CUDA(cudaStreamSynchronize(st));
+    } else {
+      counts = mine;
+    }
   }
   // receive layout on this rank: (originals | twins) x (source rank) — ascending doubled-sample order
   std::vector<size_t> roff((size_t)2 * world + 1, 0);
@@ -1213,12 +1146,19 @@ int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_
   uint32_t* d_ridx = Cc.take<uint32_t>(nr);
   void* d_tmpC = Cc.take<char>(gvm_sort_temp_bytes(nr));
   if (!d_tmpC) { gvm_set_error("gvm_grid_block_dist: arena C too small"); return 1; }
-  if (gvm_dist_group_begin(e)) return 1;
+  if (world > 1 && gvm_dist_group_begin(e)) return 1;
   for (int peer = 0; peer < world; peer++)
     for (int h = 0; h < 2; h++) {
       const int d = h * world + peer;                                   // what this rank sends to `peer`
       const size_t ns = (size_t)(dstart[d + 1] - dstart[d]);
       const size_t nrv = roff[(size_t)h * world + peer + 1] - roff[(size_t)h * world + peer];   // what it receives from `peer`
+      if (peer == rank) {   // this rank's own tiles: a device copy
+        if (ns > 0) {
+          WG_CUDA(cudaMemcpyAsync(d_rk + roff[(size_t)h * world + peer], d_sk + dstart[d], ns * 4, cudaMemcpyDeviceToDevice, st));
+          WG_CUDA(cudaMemcpyAsync(d_rrec + roff[(size_t)h * world + peer], d_srec + dstart[d], ns * 16, cudaMemcpyDeviceToDevice, st));
+        }
+        continue;
+      }
       if (ns > 0) {
         if (gvm_dist_send(e, d_sk + dstart[d], ns * 4, peer)) return 1;
         if (gvm_dist_send(e, d_srec + dstart[d], ns * 16, peer)) return 1;
@@ -1228,7 +1168,7 @@ int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_
         if (gvm_dist_recv(e, d_rrec + roff[(size_t)h * world + peer], nrv * 16, peer)) return 1;
       }
     }
-  if (gvm_dist_group_end(e)) return 1;
+  if (world > 1 && gvm_dist_group_end(e)) return 1;
   pt.mark("dist grid: all-to-all of the pairs");
   // ---- owner side: stable sort by tile, records in replay order, replay
   WG_CUDA(cudaMemsetAsync(d_tstart, 0, (size_t)ntiles * 4, st));
@@ -1246,8 +1186,10 @@ int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_
     return 1;
   pt.mark("dist grid: owner sort + tile replay");
   // every cell was computed by its owner and is exactly zero elsewhere: merge the bit patterns
-  if (gvm_dist_allreduce_u32_max(e, reinterpret_cast<uint32_t*>(d_gw), MN)) return 1;
-  if (gvm_dist_allreduce_u32_max(e, reinterpret_cast<uint32_t*>(d_gV), 2 * MN)) return 1;
+  if (world > 1) {
+    if (gvm_dist_allreduce_u32_max(e, reinterpret_cast<uint32_t*>(d_gw), MN)) return 1;
+    if (gvm_dist_allreduce_u32_max(e, reinterpret_cast<uint32_t*>(d_gV), 2 * MN)) return 1;
+  }
   k_grid_flags<<<(int)((MN + 255) / 256), 256, 0, st>>>(d_gw, (long)MN, d_flags);
   WG_CUDA(cudaMemcpyAsync(d_pos, d_flags, MN * 4, cudaMemcpyDeviceToDevice, st));
   if (gvm_exclusive_scan_u32(reinterpret_cast<uint32_t*>(d_pos), MN, d_tmpA, st)) return 1;
@@ -1257,10 +1199,13 @@ int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_
   WG_CUDA(cudaStreamSynchronize(st));
   const long count = (long)last_pos + last_flag;
   if (count > 0) {
-    if (res.uvw.ensure((size_t)count * 24) || res.Vo.ensure((size_t)count * 8) || res.w.ensure((size_t)count * 4)) return 1;
+    Arena& R = g_arena_r;   // the compacted result stays there until gvm_grid_fetch
+    if (R.reserve((size_t)count * 36 + 4 * 512)) return 1;
+    res.uvw_p = R.take<double>((size_t)count * 3);
+    res.Vo_p = R.take<float2>((size_t)count);
+    res.w_p = R.take<float>((size_t)count);
     k_grid_compact<<<(int)((MN + 255) / 256), 256, 0, st>>>(d_gw, d_gV, d_pos, M, N, deltau, deltav,
-                                                            gvm_freq_to_wavelength(freq), res.uvw.as<double>(),
-                                                            res.Vo.as<float2>(), res.w.as<float>());
+                                                            gvm_freq_to_wavelength(freq), res.uvw_p, res.Vo_p, res.w_p);
     WG_CUDA(cudaGetLastError());
     WG_CUDA(cudaStreamSynchronize(st));
   }
@@ -1268,6 +1213,25 @@ int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_
   res.count = count;
   *nout = count;
   return 0;
+}
+
+int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_m, const float* Vo, const float* w,
+                        const float* ckernel, int ck_m, int ck_n, int support_x, int support_y, int64_t* nout) {
+  const gvm_config& g = e->cfg;
+  const double deltax = GVM_RPDEG_D * g.DELTAX, deltay = GVM_RPDEG_D * g.DELTAY;
+  const double deltau = 1.0 / (g.M * deltax), deltav = 1.0 / (g.N * deltay);
+  const long M = g.M, N = g.N;
+  const bool fits = M + 2L * support_y < 65536 && N + 2L * support_x < 65536;   // 16-bit centre packing of the tile replay
+  if (e->world <= 1 || !fits)
+    return gvm_grid_block(g.device, M, N, deltau, deltav, freq, Z, uvw_m, Vo, w, ckernel, ck_m, ck_n, support_x, support_y,
+                          nullptr, nullptr, nullptr, nout);
+  if (!nout || Z < 0 || ck_m < 1 || ck_n < 1 || support_x < 0 || support_y < 0) { gvm_set_error("gvm_grid_block_dist: bad argument"); return 1; }
+  if ((2 * support_x + 1) * (2 * support_y + 1) > kMaxTaps) {
+    gvm_set_error("gvm_grid_block_dist: kernel support %d x %d exceeds %d taps", support_x, support_y, kMaxTaps);
+    return 1;
+  }
+  return grid_block_core(e, g.device, e->stream, M, N, deltau, deltav, freq, Z, uvw_m, Vo, w, ckernel, ck_m, ck_n, support_x,
+                         support_y, nout);
 }
 
 }  // extern "C"
