@@ -284,9 +284,13 @@ static int add_channel_impl(gvm_engine* e, GvmChannel& c, int64_t Z, const doubl
     GVM_CUDA(cudaMalloc(&c.Vm, z * sizeof(float2)));
     GVM_CUDA(cudaMemset(c.Vm, 0, z * sizeof(float2)));
   }
-  GVM_CUDA(cudaMalloc(&c.du64, z * sizeof(uint64_t)));
-  GVM_CUDA(cudaMalloc(&c.dv64, z * sizeof(uint64_t)));
-  GVM_CUDA(cudaMalloc(&c.wz, z * sizeof(float)));
+  // + 8 elements: the gradient kernel's bulk copies round a ragged tail up to 4 visibilities
+  GVM_CUDA(cudaMalloc(&c.du64, (z + 8) * sizeof(uint64_t)));
+  GVM_CUDA(cudaMalloc(&c.dv64, (z + 8) * sizeof(uint64_t)));
+  GVM_CUDA(cudaMalloc(&c.wz, (z + 8) * sizeof(float)));
+  GVM_CUDA(cudaMemsetAsync(c.du64 + z, 0, 8 * sizeof(uint64_t), e->stream));
+  GVM_CUDA(cudaMemsetAsync(c.dv64 + z, 0, 8 * sizeof(uint64_t), e->stream));
+  GVM_CUDA(cudaMemsetAsync(c.wz + z, 0, 8 * sizeof(float), e->stream));
   if (Z > 0) {
     double* d_uvw = nullptr; float2* d_vo = nullptr; float* d_w = nullptr;
     int rc = cudaMalloc(&d_uvw, z * 3 * sizeof(double)) != cudaSuccess || cudaMalloc(&d_vo, z * sizeof(float2)) != cudaSuccess ||

@@ -61,9 +61,13 @@ constexpr int REC_BYTES = NVS * KV * 16;
 constexpr int OFF_RECA = NSTAGE * STAGE_BYTES;
 constexpr int OFF_RECB = OFF_RECA + REC_BYTES;
 constexpr int OFF_BAR = OFF_RECB + REC_BYTES;
-constexpr int NBAR = 2 * NSTAGE + 2 * NVS + 2;
+constexpr int VBATCH = 256;                 // visibilities per bulk-copied batch of the five input streams
+constexpr int VRING = 2;
+constexpr int VB_BYTES = VBATCH * 28;       // du64 | dv64 (8 B) | wz | amp | gam (4 B)
+constexpr int NBAR = 2 * NSTAGE + 2 * NVS + 2 + VRING;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+constexpr int OFF_VIN = (OFF_TMEM + 16 + 127) & ~127;
+constexpr int SMEM_BYTES = OFF_VIN + VRING * VB_BYTES + 1024;
 constexpr int GEN_WARPS = 12;
 constexpr int NTHREADS = 18 * 32;
 constexpr uint32_t TMEM_COLS = 512;
@@ -239,6 +243,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
   auto BAR_VIS_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + NVS + s); };
   const uint32_t BAR_ACC_FULL = bar0 + 8u * (2 * NSTAGE + 2 * NVS);
   const uint32_t BAR_ACC_EMPTY = BAR_ACC_FULL + 8u;
+  auto BAR_VIN = [&](int s) { return BAR_ACC_EMPTY + 8u + 8u * s; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -266,6 +271,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
     }
     mbar_init(BAR_ACC_FULL, 1);
     mbar_init(BAR_ACC_EMPTY, 8);                  // 4 epilogue warps x 2 CTAs (used in the leader)
+    for (int s = 0; s < VRING; s++) mbar_init(BAR_VIN(s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 17) {
@@ -359,24 +365,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
     }
   } else if (warp == 16) {
     // ================================================= record producer (lane = visibility)
+    // The five per-visibility input streams are STAGED BY BULK ASYNCHRONOUS COPIES (cp.async.bulk + mbarrier, TMA
+    // without a tensor map): batches of VBATCH visibilities in a 2-deep shared-memory ring, the next batch in flight
+    // while this warp turns the current one into records. Batches start on multiples of KV = 32 visibilities (128 /
+    // 256-byte aligned); a ragged tail is rounded up to 4 visibilities (the arrays carry 8 elements of slack).
     const int ic = i0 + 64, jc = jb + (span >> 1);
+    const long nvis = kend - kbeg;
+    const int nbatch = (int)((nvis + VBATCH - 1) / VBATCH);
+    auto post_batch = [&](int b) {
+      const long k0 = kbeg + (long)b * VBATCH;
+      long n = kend - k0 < VBATCH ? kend - k0 : VBATCH;
+      n = (n + 3) & ~3L;
+      const uint32_t dst = sbase + OFF_VIN + (uint32_t)(b % VRING) * VB_BYTES, bar = BAR_VIN(b % VRING);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(n * (kUseW ? 28 : 24))) : "memory");
+      auto cp = [&](uint32_t off, const void* src, uint32_t bytes) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + off), "l"(src), "r"(bytes), "r"(bar) : "memory");
+      };
+      cp(0, du64 + k0, (uint32_t)n * 8);
+      cp(VBATCH * 8, dv64 + k0, (uint32_t)n * 8);
+      if (kUseW) cp(VBATCH * 16, wz + k0, (uint32_t)n * 4);
+      cp(VBATCH * 20, amp + k0, (uint32_t)n * 4);
+      cp(VBATCH * 24, gam + k0, (uint32_t)n * 4);
+    };
+    if (lane == 0 && nbatch > 0) post_batch(0);
     for (int it = 0; it < nst; it++) {
       const int vs = it % NVS;
+      const int b = it / (VBATCH / KV), within = (it % (VBATCH / KV)) * KV + lane;
+      if (it % (VBATCH / KV) == 0) {
+        // the other ring slot was consumed by the previous batch (program order of this warp): refill it, then wait for ours
+        __syncwarp();
+        if (lane == 0 && b + 1 < nbatch) post_batch(b + 1);
+        mbar_wait(BAR_VIN(b % VRING), (uint32_t)((b / VRING) & 1));
+      }
       mbar_wait(BAR_VIS_EMPTY(vs), (uint32_t)(((it / NVS) & 1) ^ 1));
       const long k = kbeg + (long)it * KV + lane;
       uint4 ra = make_uint4(0u, 0u, 0x3F800000u, 0u), rb = make_uint4(0u, 0u, 0u, 0u);
       if (k < kend) {
-        const uint64_t du = __ldg(&du64[k]), dv = __ldg(&dv64[k]);
-        const float wzk = kUseW ? __ldg(&wz[k]) : 0.f;
+        const uint8_t* vin = sgen + OFF_VIN + (b % VRING) * VB_BYTES;
+        const uint64_t du = reinterpret_cast<const uint64_t*>(vin)[within];
+        const uint64_t dv = reinterpret_cast<const uint64_t*>(vin + VBATCH * 8)[within];
+        const float wzk = kUseW ? reinterpret_cast<const float*>(vin + VBATCH * 16)[within] : 0.f;
         // A: +phase of v_k y_i ; B: arg(Vr_k) - phase of u_k x_j (and -w for the w-term).
         // The per-row increment is ROUNDED to 32 bits: |dr| <= 192 rows => <= 2.3e-8 turns.
         ra.x = (uint32_t)((dv * (uint64_t)(int64_t)(ic - y0)) >> 32);
         ra.y = (uint32_t)((dv + 0x80000000ull) >> 32);
         ra.w = __float_as_uint(wzk);
         const uint32_t pu = (uint32_t)((du * (uint64_t)(int64_t)(jc - x0)) >> 32);
-        rb.x = __ldg(&gam[k]) - pu;
+        rb.x = reinterpret_cast<const uint32_t*>(vin + VBATCH * 24)[within] - pu;
         rb.y = 0u - (uint32_t)((du + 0x80000000ull) >> 32);
-        rb.z = __float_as_uint(__ldg(&amp[k]));
+        rb.z = reinterpret_cast<const uint32_t*>(vin + VBATCH * 20)[within];
         rb.w = __float_as_uint(-wzk);
       }
       *reinterpret_cast<uint4*>(sgen + OFF_RECA + (vs * KV + lane) * 16) = ra;
@@ -567,8 +605,10 @@ int gvm_grad_umma(gvm_engine* e, GvmChannel& c, const float* I_dev, int flag_opt
   if (ntiles == 0) return 0;      // every pixel is masked: the gradient is exactly zero
   if (!c.amp) {
     const size_t z = (size_t)(c.Z > 0 ? c.Z : 1);
-    GVM_CUDA(cudaMalloc(&c.amp, z * sizeof(float)));
-    GVM_CUDA(cudaMalloc(&c.gam, z * sizeof(uint32_t)));
+    GVM_CUDA(cudaMalloc(&c.amp, (z + 8) * sizeof(float)));
+    GVM_CUDA(cudaMalloc(&c.gam, (z + 8) * sizeof(uint32_t)));
+    GVM_CUDA(cudaMemsetAsync(c.amp + z, 0, 8 * sizeof(float), e->stream));
+    GVM_CUDA(cudaMemsetAsync(c.gam + z, 0, 8 * sizeof(uint32_t), e->stream));
   }
   float* inv_scale = e->red_max + e->red_slots + c.slot;
   k_grad_coeff<<<(int)((c.Z + 255) / 256), 256, 0, e->stream>>>(c.Vr, c.w, c.Z, e->red_max + c.slot,

@@ -32,6 +32,25 @@ struct PriorArgs {
 
 __device__ __forceinline__ float approx_abs(float v, float eps) { return sqrtf(v * v + eps); }
 
+// the four kinds that only look at the pixel itself (and the prior image): shared by the scalar and the 4-wide kernels
+template <int KIND> struct IsPointwise {
+  static constexpr bool value = KIND == GVM_PRIOR_ENTROPY || KIND == GVM_PRIOR_GENTROPY || KIND == GVM_PRIOR_L1 || KIND == GVM_PRIOR_GL1;
+};
+template <int KIND>
+__device__ __forceinline__ float pw_value(const PriorArgs& a, float c, float pr) {
+  if (KIND == GVM_PRIOR_ENTROPY) return c * logf((c / a.G) + (a.eta + 1.0f));
+  if (KIND == GVM_PRIOR_GENTROPY) return c * logf((c / pr) + (a.eta + 1.0f));
+  if (KIND == GVM_PRIOR_L1) return approx_abs(c, a.eps);
+  return approx_abs(c, a.eps) / (approx_abs(pr, a.eps) + a.eps_b);   // GL1
+}
+template <int KIND>
+__device__ __forceinline__ float pw_grad(const PriorArgs& a, float c, float pr) {
+  if (KIND == GVM_PRIOR_ENTROPY) return logf((c / a.G) + (a.eta + 1.0f)) + 1.0f / (1.0f + (((a.eta + 1.0f) * a.G) / c));
+  if (KIND == GVM_PRIOR_GENTROPY) return logf((c / pr) + (a.eta + 1.0f)) + 1.0f / (1.0f + (((a.eta + 1.0f) * pr) / c));
+  if (KIND == GVM_PRIOR_L1) return c / approx_abs(c, a.eps);
+  return c / (approx_abs(c, a.eps) * (approx_abs(pr, a.eps) + a.eps_b));   // GL1
+}
+
 template <int KIND>
 __device__ __forceinline__ float prior_value_at(const PriorArgs& a, int i, int j) {
   const int N = a.N;
@@ -39,11 +58,8 @@ __device__ __forceinline__ float prior_value_at(const PriorArgs& a, int i, int j
   const float* I = a.I;
   if (!(a.noise[idx] < a.noise_cut)) return 0.0f;
   const float c = I[idx];
-  if (KIND == GVM_PRIOR_ENTROPY) return c * logf((c / a.G) + (a.eta + 1.0f));
-  if (KIND == GVM_PRIOR_GENTROPY) return c * logf((c / a.prior_image[idx]) + (a.eta + 1.0f));
-  if (KIND == GVM_PRIOR_L1) return approx_abs(c, a.eps);
-  if (KIND == GVM_PRIOR_GL1)
-    return approx_abs(c, a.eps) / (approx_abs(a.prior_image[idx], a.eps) + a.eps_b);
+  if (IsPointwise<KIND>::value)
+    return pw_value<KIND>(a, c, (KIND == GVM_PRIOR_GENTROPY || KIND == GVM_PRIOR_GL1) ? a.prior_image[idx] : 0.f);
   if (KIND == GVM_PRIOR_TV) {
     if (i < N - 1 && j < N - 1) {
       const float r = I[idx + 1], d = I[idx + N];
@@ -87,16 +103,8 @@ __device__ __forceinline__ float prior_grad_at(const PriorArgs& a, int i, int j)
   float g = 0.0f;
   if (a.noise[idx] < a.noise_cut) {
     const float c = I[idx];
-    if (KIND == GVM_PRIOR_ENTROPY) {
-      const float G = a.G;
-      g = logf((c / G) + (a.eta + 1.0f)) + 1.0f / (1.0f + (((a.eta + 1.0f) * G) / c));
-    } else if (KIND == GVM_PRIOR_GENTROPY) {
-      const float G = a.prior_image[idx];
-      g = logf((c / G) + (a.eta + 1.0f)) + 1.0f / (1.0f + (((a.eta + 1.0f) * G) / c));
-    } else if (KIND == GVM_PRIOR_L1) {
-      g = c / approx_abs(c, a.eps);
-    } else if (KIND == GVM_PRIOR_GL1) {
-      g = c / (approx_abs(c, a.eps) * (approx_abs(a.prior_image[idx], a.eps) + a.eps_b));
+    if (IsPointwise<KIND>::value) {
+      g = pw_grad<KIND>(a, c, (KIND == GVM_PRIOR_GENTROPY || KIND == GVM_PRIOR_GL1) ? a.prior_image[idx] : 0.f);
     } else if (KIND == GVM_PRIOR_TV) {
       if ((i > 0 && i < N - 1) && (j > 0 && j < N - 1)) {
         const float d = I[idx + N], u = I[idx - N], r = I[idx + 1], l = I[idx - 1];
@@ -375,16 +383,84 @@ int fetch_red(gvm_engine* e, double* v3) {
   return 0;
 }
 
+// 4-wide versions for the pointwise kinds (N a multiple of 4, planes 16-byte aligned): 128-bit loads of the mask, the
+// image, the prior image and (kAdd) dphi; same per-pixel arithmetic (pw_value / pw_grad)
+template <int KIND>
+__global__ void __launch_bounds__(kT) k_prior_value4(PriorArgs a, double* partials, float* pmax, unsigned int* counter,
+                                                     double* out) {
+  const long nq = (long)a.N * a.N / 4;
+  constexpr bool kPrior = KIND == GVM_PRIOR_GENTROPY || KIND == GVM_PRIOR_GL1;
+  float s = 0.f;
+#pragma unroll 2
+  for (long q = blockIdx.x * (long)kT + threadIdx.x; q < nq; q += (long)gridDim.x * kT) {
+    const float4 nz = __ldg(reinterpret_cast<const float4*>(a.noise) + q);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(a.I) + q);
+    float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kPrior) pr = __ldg(reinterpret_cast<const float4*>(a.prior_image) + q);
+    // same order as the scalar kernel's per-thread sum would be irrelevant: the partial sums differ anyway by layout
+    if (nz.x < a.noise_cut) s += pw_value<KIND>(a, c.x, pr.x);
+    if (nz.y < a.noise_cut) s += pw_value<KIND>(a, c.y, pr.y);
+    if (nz.z < a.noise_cut) s += pw_value<KIND>(a, c.z, pr.z);
+    if (nz.w < a.noise_cut) s += pw_value<KIND>(a, c.w, pr.w);
+  }
+  block_reduce_finish(s, 0.f, 0.f, partials, pmax, counter, out);
+}
+template <int KIND, bool kAdd>
+__global__ void __launch_bounds__(kT) k_prior_grad4(PriorArgs a, float* __restrict__ dgi) {
+  const long q = blockIdx.x * (long)kT + threadIdx.x;
+  if (4 * q >= (long)a.N * a.N) return;
+  constexpr bool kPrior = KIND == GVM_PRIOR_GENTROPY || KIND == GVM_PRIOR_GL1;
+  const float4 nz = __ldg(reinterpret_cast<const float4*>(a.noise) + q);
+  const bool u0 = nz.x < a.noise_cut, u1 = nz.y < a.noise_cut, u2 = nz.z < a.noise_cut, u3 = nz.w < a.noise_cut;
+  float4* dp = reinterpret_cast<float4*>(dgi) + q;
+  if (!(u0 || u1 || u2 || u3)) {          // masked quad: the gradient is +0 * lambda; adding it changes nothing but -0
+    if (!kAdd) *dp = make_float4(0.0f * a.lambda, 0.0f * a.lambda, 0.0f * a.lambda, 0.0f * a.lambda);
+    else {
+      float4 r = *dp;
+      const float z = 0.0f * a.lambda;
+      r.x = __fadd_rn(r.x, z); r.y = __fadd_rn(r.y, z); r.z = __fadd_rn(r.z, z); r.w = __fadd_rn(r.w, z);
+      *dp = r;
+    }
+    return;
+  }
+  const float4 c = __ldg(reinterpret_cast<const float4*>(a.I) + q);
+  float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kPrior) pr = __ldg(reinterpret_cast<const float4*>(a.prior_image) + q);
+  float4 g;
+  g.x = (u0 ? pw_grad<KIND>(a, c.x, pr.x) : 0.0f) * a.lambda;
+  g.y = (u1 ? pw_grad<KIND>(a, c.y, pr.y) : 0.0f) * a.lambda;
+  g.z = (u2 ? pw_grad<KIND>(a, c.z, pr.z) : 0.0f) * a.lambda;
+  g.w = (u3 ? pw_grad<KIND>(a, c.w, pr.w) : 0.0f) * a.lambda;
+  if (kAdd) {
+    const float4 r = *dp;
+    g.x = __fadd_rn(r.x, g.x); g.y = __fadd_rn(r.y, g.y); g.z = __fadd_rn(r.z, g.z); g.w = __fadd_rn(r.w, g.w);
+  }
+  *dp = g;
+}
+inline bool prior_vec4_ok(const PriorArgs& a, const void* out) {
+  return a.N % 4 == 0 && (((uintptr_t)a.I | (uintptr_t)a.noise | (uintptr_t)a.prior_image | (uintptr_t)out) & 15) == 0;
+}
+
 template <int KIND>
 int launch_value(gvm_engine* e, const PriorArgs& a, double* out = nullptr) {
   RedBuf r = aux_red(e);
   if (out) r.out = out;
+  if (IsPointwise<KIND>::value && prior_vec4_ok(a, nullptr)) {
+    k_prior_value4<KIND><<<red_grid(e, (long)a.N * a.N / 4), kT, 0, e->stream>>>(a, r.partials, r.pmax, r.counter, r.out);
+    return 0;
+  }
   const int blocks = a.N < e->red_blocks ? a.N : e->red_blocks;
   k_prior_value<KIND><<<blocks, kT, 0, e->stream>>>(a, r.partials, r.pmax, r.counter, r.out);
   return 0;
 }
 template <int KIND>
 int launch_grad(gvm_engine* e, const PriorArgs& a, float* dgi, bool add) {
+  if (IsPointwise<KIND>::value && prior_vec4_ok(a, dgi)) {
+    const unsigned blocks = (unsigned)(((long)a.N * a.N / 4 + kT - 1) / kT);
+    if (add) k_prior_grad4<KIND, true><<<blocks, kT, 0, e->stream>>>(a, dgi);
+    else k_prior_grad4<KIND, false><<<blocks, kT, 0, e->stream>>>(a, dgi);
+    return 0;
+  }
   const dim3 grid((unsigned)((a.N + kT - 1) / kT), (unsigned)a.N);
   if (add) k_prior_grad<KIND, true><<<grid, kT, 0, e->stream>>>(a, dgi);
   else k_prior_grad<KIND, false><<<grid, kT, 0, e->stream>>>(a, dgi);
