@@ -501,15 +501,21 @@ def measure(ctx, name, scale, steps, warmup, recon_iters, grad_mode=0, lbfgs_k=1
         ach = flops / (kern_ms / 1e3) / 1e12 if kern_ms > 0 else None
         peak = pk["tflops_sustained"]
         st_all = s.stats()
-        roof = {"bound": "tensor", "kernel": {1: "k_grad_umma (tcgen05 cta_group::2, fp16x3)", 2: "k_grad_sep (CUDA cores fp32)",
+        fp16x3 = os.environ.get("GVM_UMMA_SPLIT", "") == "fp16x3"
+        umma_name = ("k_grad_umma (tcgen05 cta_group::2, three fp16 products)" if fp16x3 else
+                     "k_grad_umma (tcgen05 cta_group::2, fp16 product + two 8-bit-float correction products)")
+        umma_note = ("the fp16x3 split issues 3 fp16 MMAs per useful product, so frac <= 1/3 by construction" if fp16x3 else
+                     "per useful product the kernel issues one fp16 MMA and one E4M3/E5M2 MMA of twice the K (both corrections), "
+                     "i.e. 2 fp16-MMA times, so frac <= 1/2 by construction")
+        roof = {"bound": "tensor", "kernel": {1: umma_name, 2: "k_grad_sep (CUDA cores fp32)",
                                               3: "k_grad_exact (CUDA cores)"}.get(mode, str(mode)),
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
                 "traffic": None, "share_of_step": kern_ms / ms_step if ms_step > 0 else None,
                 "plan": {"tiles": ntiles, "pixels_computed": npx, "pixels_image": MN},
                 "note": f"algorithmic flops 4*P*Z per step on this rank = {flops:.3e}, P = pixels of the tiles that cover the "
                         f"unmasked part of the image (masked pixels are skipped, as DChi2 does); {kern_n} launch(es) per step "
-                        f"(one per channel), {kern_ms:.2f} ms in total; peak = bf16/fp16 dense ({pk['source']}, sustained); the "
-                        "fp16x3 split issues 3 MMAs per useful product, so frac <= 1/3 by construction"}
+                        f"(one per channel), {kern_ms:.2f} ms in total; peak = bf16/fp16 dense ({pk['source']}, sustained); "
+                        + umma_note}
         if mode == 4:
             # gridded samples: scatter (28 B/sample in + 8 B RMW) + memset of the half plane (4 B/px) + cuFFT C2R
             # (two passes: 4 B/px in + ~8 B/px intermediate r/w + 4 B/px real out) — HBM-bound
@@ -522,12 +528,12 @@ def measure(ctx, name, scale, steps, warmup, recon_iters, grad_mode=0, lbfgs_k=1
                             f"peak = measured HBM copy bandwidth ({pk['source']})"}
         if mode == 1 and name == "c2" and scale == 1.0 and world == 1:
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this exact workload,
-            # from the committed ncu --set full capture (profiles/r1b_traffic.json)
+            # from the committed ncu --set full capture (profiles/r2d_traffic.json; r1b_traffic.json for the fp16x3 split)
             try:
-                tr = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json" if fp16x3 else "r2d_traffic.json")))
                 roof["traffic"] = next(iter(tr.values()))["dram_bytes_total"]
                 roof["traffic_note"] = ("bytes per launch (ncu); algorithmic minimum 28 B x Z per tile pass x 32 tiles, "
-                                        "served from L2: the kernel is tensor-bound, DRAM at 0.02 % of peak")
+                                        "served from L2, + the split-K scratch slices (340 MB written once); DRAM at 0.03 % of peak")
             except Exception:
                 pass
         cfg = workload_config(name, problem, wl)

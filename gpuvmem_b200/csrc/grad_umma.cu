@@ -44,8 +44,11 @@
 #include <climits>
 #include <algorithm>
 #include <cstdlib>
+#include <string>
+#include <type_traits>
 
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include "gvm_internal.cuh"
 
@@ -68,8 +71,9 @@ constexpr int NBAR = 2 * NSTAGE + 2 * NVS + 2 + VRING;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int OFF_VIN = (OFF_TMEM + 16 + 127) & ~127;
 constexpr int SMEM_BYTES = OFF_VIN + VRING * VB_BYTES + 1024;
-constexpr int GEN_WARPS = 12;
-constexpr int NTHREADS = 18 * 32;
+// kSplit generator warps share a row: 12 * kSplit generator warps, each thread fills 32 / kSplit visibilities of a stage
+__host__ __device__ constexpr int gen_warps(int split) { return 12 * split; }
+__host__ __device__ constexpr int nthreads(int split) { return (gen_warps(split) + 6) * 32; }
 constexpr uint32_t TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -98,25 +102,34 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The suspend-time hint lets a waiting warp sleep until the phase completes (or the hint expires) instead of polling:
+// the four epilogue warps wait for 64 stages at a time and their polls took 12 % of the issue slots of the generators
+// (ncu source view, profiles/r2d_k_grad_umma_mixed_ncu_summary.txt).
+// Operand hand-over to the tensor core of the pair: the generic-proxy stores were made visible to the async proxy by
+// fence.proxy.async; the arrive itself needs no cluster-scope release (which costs MEMBAR.ALL.GPU + ERRBAR per warp and
+// stage) — the consumer is tcgen05.mma reading shared memory through the async proxy, not a generic load.
+__device__ __forceinline__ void mbar_arrive_operands(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
   }
 }
-// wait with cluster-scope acquire: the arrivals come from both CTAs of the pair
+// wait with cluster-scope acquire: the arrivals come from both CTAs of the pair (accumulator hand-over)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
   }
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -140,6 +153,15 @@ __device__ __forceinline__ void tc_mma_pair_f16(uint32_t d_tmem, uint64_t a_desc
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// same accumulator, E4M3 operands (K = 32 per instruction): the correction products of the mixed split
+__device__ __forceinline__ void tc_mma_pair_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -201,6 +223,29 @@ __device__ __forceinline__ void split2(float c, float s, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// Mixed split (kMixed): x = hi + lo with hi = rn16(x) as before, but the two correction products are formed from 8-bit
+// float operands at twice the fp16 tensor rate. The amplitude w|Vr| 2^e (< 2^14.5) rides on the A rows, the B rows are
+// unit phasors, and the second block of every operand holds 128 one-byte K elements per row:
+//   A rows: [ e4m3(lo) x 64 | e5m2(hi) x 64 ]      B rows: [ e4m3(hi) x 64 | e5m2(lo) x 64 ]
+// so bytes 0-63 contract to Al Bh (E4M3 x E4M3: |Al| <= 8, |Bh| <= 1) and bytes 64-127 to Ah Bl (E5M2 x E5M2: the five
+// exponent bits take |Ah| < 2^14.5 and |Bl| <= 2^-12 as they are) — no scaling instruction in the generators. Each
+// correction is ~2^-12 of its term and is kept to 2^-4 / 2^-3: 1.3e-5 rms of the term (scripts/diag/umma_fp8mix.cu and
+// the numpy model in DESIGN.md §3.3; the third fp16 product kept it at 1e-7 — both are at or below the 1.2e-5 of the phases).
+template <bool kIsA>
+__device__ __forceinline__ void split_mixed(float c, float s, uint32_t& hi, uint32_t& first8, uint32_t& second8) {
+  const __half2 h = __floats2half2_rn(c, s);
+  const float2 hf = __half22float2(h);
+  const float2 lo = make_float2(c - hf.x, s - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  if (kIsA) {
+    first8 = __nv_cvt_float2_to_fp8x2(lo, __NV_SATFINITE, __NV_E4M3);
+    second8 = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(h), __NV_SATFINITE, __NV_E5M2);
+  } else {
+    first8 = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(h), __NV_SATFINITE, __NV_E4M3);
+    second8 = __nv_cvt_float2_to_fp8x2(lo, __NV_SATFINITE, __NV_E5M2);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Per evaluation, per visibility: amplitude and phase of w_k Vr_k, scaled by an exact
 // power of two so that the largest amplitude sits near 2^14 (fp16 max is 65504).
@@ -226,8 +271,8 @@ __global__ void __launch_bounds__(256) k_grad_coeff(const float2* __restrict__ V
 }
 
 // ---------------------------------------------------------------------------
-template <bool kUseW>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_umma(
+template <bool kUseW, bool kMixed, int kSplit>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(nthreads(kSplit), 1) k_grad_umma(
     const uint64_t* __restrict__ du64, const uint64_t* __restrict__ dv64,
     const float* __restrict__ wz, const float* __restrict__ amp, const uint32_t* __restrict__ gam,
     const float* __restrict__ gA, const float* __restrict__ gB, const int4* __restrict__ tile_list,
@@ -246,6 +291,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
   auto BAR_VIN = [&](int s) { return BAR_ACC_EMPTY + 8u + 8u * s; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
 
+  constexpr int GEN_WARPS = gen_warps(kSplit);
+  constexpr int W_EPI = GEN_WARPS, W_PROD = GEN_WARPS + 4, W_MMA = GEN_WARPS + 5;   // W_EPI % 4 == 0: TMEM lane quadrants
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
   const int tile = blockIdx.x >> 1;
@@ -274,7 +321,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
     for (int s = 0; s < VRING; s++) mbar_init(BAR_VIN(s), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 17) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      sbase + OFF_TMEM), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -287,7 +334,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
 
   if (warp < GEN_WARPS) {
     // ================================================= operand generators (one row per thread)
-    const int grp = warp >> 2;               // 0: A rows, 1: B block 0, 2: B block 1
+    const int grp = (warp >> 2) % 3;         // 0: A rows, 1: B block 0, 2: B block 1
+    const int part = warp / 12;              // which 32 / kSplit visibilities of a stage this thread fills
     const int r = tid & 127;
     const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
     const uint32_t swz = (uint32_t)(r & 7);
@@ -308,31 +356,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
       mbar_wait(BAR_OP_EMPTY(s), (uint32_t)(((it / NSTAGE) & 1) ^ 1));
       const uint32_t hi_row = sbase + (uint32_t)s * STAGE_BYTES + blk_hi, lo_row = hi_row + BLK_BYTES;
       const uint32_t recs = rec0 + (uint32_t)vs * (KV * 16);
+      if (!kMixed) {
 #pragma unroll 2
-      for (int kq = 0; kq < (active ? KV / 4 : 0); kq++) {
-        uint32_t hi[4], lo[4];
+        for (int kq = part * (KV / 4 / kSplit); kq < (active ? (part + 1) * (KV / 4 / kSplit) : 0); kq++) {
+          uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-          const uint4 rec = ld_shared_v4(recs + (uint32_t)(kq * 4 + kk) * 16);
-          float a = phase_to_angle(rec.x + (uint32_t)dr * rec.y);
-          if (kUseW) a = fmaf(__uint_as_float(rec.w), g2, a);
-          const float am = __uint_as_float(rec.z);          // 1 for A rows
-          split2(am * __cosf(a), am * __sinf(a), hi[kk], lo[kk]);
+          for (int kk = 0; kk < 4; kk++) {
+            const uint4 rec = ld_shared_v4(recs + (uint32_t)(kq * 4 + kk) * 16);
+            float a = phase_to_angle(rec.x + (uint32_t)dr * rec.y);
+            if (kUseW) a = fmaf(__uint_as_float(rec.w), g2, a);
+            const float am = __uint_as_float(rec.z);          // w|Vr| 2^e on the A rows, 1 on the B rows
+            split2(am * __cosf(a), am * __sinf(a), hi[kk], lo[kk]);
+          }
+          const uint32_t off = ((uint32_t)kq ^ swz) << 4;
+          st_shared_v4(hi_row + off, hi[0], hi[1], hi[2], hi[3]);
+          st_shared_v4(lo_row + off, lo[0], lo[1], lo[2], lo[3]);
         }
-        const uint32_t off = ((uint32_t)kq ^ swz) << 4;
-        st_shared_v4(hi_row + off, hi[0], hi[1], hi[2], hi[3]);
-        st_shared_v4(lo_row + off, lo[0], lo[1], lo[2], lo[3]);
+      } else {
+        // eight visibilities per pass: two 16-byte chunks of the fp16 row, one chunk in each half of the byte row
+        auto pass = [&](auto is_a) {
+          constexpr bool kIsA = decltype(is_a)::value;
+#pragma unroll
+          for (int k8 = part * (KV / 8 / kSplit); k8 < (active ? (part + 1) * (KV / 8 / kSplit) : 0); k8++) {
+            uint32_t hi[8], f8[8], s8[8];
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++) {
+              const uint4 rec = ld_shared_v4(recs + (uint32_t)(k8 * 8 + kk) * 16);
+              float a = phase_to_angle(rec.x + (uint32_t)dr * rec.y);
+              if (kUseW) a = fmaf(__uint_as_float(rec.w), g2, a);
+              float c = __cosf(a), sn = __sinf(a);
+              if (kIsA) { const float am = __uint_as_float(rec.z); c *= am; sn *= am; }
+              split_mixed<kIsA>(c, sn, hi[kk], f8[kk], s8[kk]);
+            }
+            st_shared_v4(hi_row + (((uint32_t)(2 * k8) ^ swz) << 4), hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(hi_row + (((uint32_t)(2 * k8 + 1) ^ swz) << 4), hi[4], hi[5], hi[6], hi[7]);
+            st_shared_v4(lo_row + (((uint32_t)k8 ^ swz) << 4), f8[0] | (f8[1] << 16), f8[2] | (f8[3] << 16),
+                         f8[4] | (f8[5] << 16), f8[6] | (f8[7] << 16));
+            st_shared_v4(lo_row + (((uint32_t)(4 + k8) ^ swz) << 4), s8[0] | (s8[1] << 16), s8[2] | (s8[3] << 16),
+                         s8[4] | (s8[5] << 16), s8[6] | (s8[7] << 16));
+          }
+        };
+        if (grp == 0) pass(std::true_type{}); else pass(std::false_type{});
       }
       fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive_remote(full_remote0 + 8u * s);
+        mbar_arrive_operands(full_remote0 + 8u * s);
         mbar_arrive(BAR_VIS_EMPTY(vs));
       }
     }
-  } else if (warp < 16) {
+  } else if (warp < W_PROD) {
     // ================================================= epilogue: TMEM -> split-K scratch slice
-    const int q = warp - 12;
+    const int q = warp - W_EPI;
     const int nchunks = (nst + chunk_stages - 1) / chunk_stages;
     // compact scratch: [K slice][tile][256 rows][2 x 256 columns]
     float* orow = scratch + (((size_t)ks * ntiles + tile) * TILE_I + (128 * rank + 32 * q + lane)) * TILE_J;
@@ -363,7 +438,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(acc_empty_remote);
     }
-  } else if (warp == 16) {
+  } else if (warp == W_PROD) {
     // ================================================= record producer (lane = visibility)
     // The five per-visibility input streams are STAGED BY BULK ASYNCHRONOUS COPIES (cp.async.bulk + mbarrier, TMA
     // without a tensor map): batches of VBATCH visibilities in a 2-deep shared-memory ring, the next batch in flight
@@ -400,7 +475,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
       }
       mbar_wait(BAR_VIS_EMPTY(vs), (uint32_t)(((it / NVS) & 1) ^ 1));
       const long k = kbeg + (long)it * KV + lane;
-      uint4 ra = make_uint4(0u, 0u, 0x3F800000u, 0u), rb = make_uint4(0u, 0u, 0u, 0u);
+      uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = make_uint4(0u, 0u, 0x3F800000u, 0u);   // padding: amplitude 0
       if (k < kend) {
         const uint8_t* vin = sgen + OFF_VIN + (b % VRING) * VB_BYTES;
         const uint64_t du = reinterpret_cast<const uint64_t*>(vin)[within];
@@ -410,11 +485,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
         // The per-row increment is ROUNDED to 32 bits: |dr| <= 192 rows => <= 2.3e-8 turns.
         ra.x = (uint32_t)((dv * (uint64_t)(int64_t)(ic - y0)) >> 32);
         ra.y = (uint32_t)((dv + 0x80000000ull) >> 32);
+        ra.z = reinterpret_cast<const uint32_t*>(vin + VBATCH * 20)[within];
         ra.w = __float_as_uint(wzk);
         const uint32_t pu = (uint32_t)((du * (uint64_t)(int64_t)(jc - x0)) >> 32);
         rb.x = reinterpret_cast<const uint32_t*>(vin + VBATCH * 24)[within] - pu;
         rb.y = 0u - (uint32_t)((du + 0x80000000ull) >> 32);
-        rb.z = reinterpret_cast<const uint32_t*>(vin + VBATCH * 20)[within];
         rb.w = __float_as_uint(-wzk);
       }
       *reinterpret_cast<uint4*>(sgen + OFF_RECA + (vs * KV + lane) * 16) = ra;
@@ -423,7 +498,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
     }
   } else if (rank == 0 && lane == 0) {
     // ================================================= MMA issuer (one thread of the leader CTA)
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(nbw >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(nbw >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // formats 0: F16 / E4M3
+    const uint32_t idesc_e5m2 = idesc | (1u << 7) | (1u << 10);
     for (int it = 0; it < nst; it++) {
       const int s = it % NSTAGE;
       const int cpos = it % chunk_stages;
@@ -431,7 +507,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
         mbar_wait_cluster(BAR_ACC_EMPTY, (uint32_t)(((it / chunk_stages) & 1) ^ 1));
         tc_fence_after();
       }
-      mbar_wait_cluster(BAR_OP_FULL(s), (uint32_t)((it / NSTAGE) & 1));
+      mbar_wait(BAR_OP_FULL(s), (uint32_t)((it / NSTAGE) & 1));
       tc_fence_after();
       const uint32_t st0 = sbase + (uint32_t)s * STAGE_BYTES;
       const uint32_t a_hi = st0, a_lo = st0 + BLK_BYTES;
@@ -444,8 +520,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
           const uint32_t ko = (uint32_t)kstep * 32;
           tc_mma_pair_f16(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_hi + ko), idesc,
                           (cpos > 0 || kstep > 0) ? 1u : 0u);
-          tc_mma_pair_f16(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), idesc, 1u);
-          tc_mma_pair_f16(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), idesc, 1u);
+          if (!kMixed) {
+            tc_mma_pair_f16(d, umma_desc_sw128(a_hi + ko), umma_desc_sw128(b_lo + ko), idesc, 1u);
+            tc_mma_pair_f16(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_hi + ko), idesc, 1u);
+          }
+        }
+        if (kMixed) {
+#pragma unroll
+          for (int kstep = 0; kstep < 4; kstep++) {   // 4 x (K = 32 bytes): Al Bh (E4M3) over bytes 0-63, Ah Bl (E5M2) over 64-127
+            const uint32_t ko = (uint32_t)kstep * 32;
+            tc_mma_pair_f8(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_lo + ko), kstep < 2 ? idesc : idesc_e5m2, 1u);
+          }
         }
       }
       tc_commit_pair(BAR_OP_EMPTY(s));                 // stage reusable (both CTAs) once retired
@@ -456,7 +541,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_grad_
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();          // the peer's TMEM / smem / barriers stay alive until both are done
-  if (warp == 17) {
+  if (warp == W_MMA) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
@@ -594,11 +679,12 @@ int gvm_grad_umma(gvm_engine* e, GvmChannel& c, const float* I_dev, int flag_opt
     gvm_set_error("gvm_grad_umma: the w-term exceeds 4 turns across the image; use the SIMT kernels");
     return 1;
   }
-  if (!e->umma_attr_set) {   // per engine: the attribute belongs to the device the engine runs on
-    GVM_CUDA(cudaFuncSetAttribute(k_grad_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    GVM_CUDA(cudaFuncSetAttribute(k_grad_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    e->umma_attr_set = true;
-  }
+  // GVM_UMMA_SPLIT=fp16x3 selects the three-product fp16 split (round 1); default: fp16 + two E4M3 correction products.
+  // GVM_UMMA_GENSPLIT=1|2: generator warps per operand row (12 or 24 generator warps per CTA).
+  bool mixed = true;
+  if (const char* s = getenv("GVM_UMMA_SPLIT")) mixed = std::string(s) != "fp16x3";
+  int gensplit = 1;
+  if (const char* s = getenv("GVM_UMMA_GENSPLIT")) gensplit = atoi(s) == 2 ? 2 : 1;
   if (e->plan_dirty)
     if (build_plan(e)) return 1;
   const int ntiles = e->plan_ntiles;
@@ -649,14 +735,24 @@ int gvm_grad_umma(gvm_engine* e, GvmChannel& c, const float* I_dev, int flag_opt
   const int x0 = (int)c.d.phs_xobs_pix, y0 = (int)c.d.phs_yobs_pix;
   dim3 grid(2 * ntiles, ksplit);
   gvm_ev_begin(e);
-  if (use_w)
-    k_grad_umma<true><<<grid, NTHREADS, SMEM_BYTES, e->stream>>>(
-        c.du64, c.dv64, c.wz, c.amp, c.gam, e->pixtab, e->pixtab + N, e->tile_list, ntiles, c.Z, N,
-        x0, y0, klen, (int)(chunk / KV), e->grad_scratch);
-  else
-    k_grad_umma<false><<<grid, NTHREADS, SMEM_BYTES, e->stream>>>(
-        c.du64, c.dv64, c.wz, c.amp, c.gam, e->pixtab, e->pixtab + N, e->tile_list, ntiles, c.Z, N,
-        x0, y0, klen, (int)(chunk / KV), e->grad_scratch);
+  int launch_rc = 0;
+  auto launch = [&](auto kern, int threads, unsigned bit) {
+    // per engine (the attribute belongs to its device): opt in to the dynamic shared memory of this instantiation
+    if (!(e->umma_attr_set & bit)) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { launch_rc = 1; return; }
+      e->umma_attr_set |= bit;
+    }
+    kern<<<grid, threads, SMEM_BYTES, e->stream>>>(c.du64, c.dv64, c.wz, c.amp, c.gam, e->pixtab, e->pixtab + N, e->tile_list,
+                                                   ntiles, c.Z, N, x0, y0, klen, (int)(chunk / KV), e->grad_scratch);
+  };
+  auto pick = [&](auto usew, auto mix) {
+    constexpr bool W = decltype(usew)::value, M = decltype(mix)::value;
+    constexpr unsigned bit = 1u << (4 * W + 2 * M);
+    if (gensplit == 2) launch(k_grad_umma<W, M, 2>, nthreads(2), bit << 1); else launch(k_grad_umma<W, M, 1>, nthreads(1), bit);
+  };
+  if (use_w) { if (mixed) pick(std::true_type{}, std::true_type{}); else pick(std::true_type{}, std::false_type{}); }
+  else { if (mixed) pick(std::false_type{}, std::true_type{}); else pick(std::false_type{}, std::false_type{}); }
+  if (launch_rc) { gvm_set_error("gvm_grad_umma: cudaFuncSetAttribute failed"); return 1; }
   gvm_ev_end(e);
   GVM_LAUNCH(e);
   GVM_CUDA(cudaGetLastError());

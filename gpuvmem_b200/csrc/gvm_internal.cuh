@@ -120,7 +120,7 @@ struct gvm_engine {
   int last_grad_mode = 0;
   unsigned int* tile_counter = nullptr;
   // tensor-core gradient: tile plan over the unmasked part of the image (grad_umma.cu)
-  bool umma_attr_set = false;      // dynamic shared-memory opt-in of k_grad_umma done on this engine's device
+  unsigned umma_attr_set = 0;      // dynamic shared-memory opt-in of the k_grad_umma instantiations (bit mask) done on this engine's device
   bool plan_dirty = true;          // noise image / noise_cut changed since the last plan
   int2* row_ext = nullptr;         // [N] (first, last) unmasked column of every row (device)
   int4* tile_list = nullptr;       // [ntiles] (i0, j0, block width, 0)   (device)

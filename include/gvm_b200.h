@@ -33,7 +33,7 @@ enum { GVM_BEAM_AIRYDISK = 0, GVM_BEAM_GAUSSIAN = 1 }; /* include/MSFITSIO.cuh:5
  * w-term bound holds, else SIMT_EXACT. */
 enum {
   GVM_GRAD_AUTO = 0,
-  GVM_GRAD_UMMA = 1,       /* tcgen05 / TMEM, fp16x3 error-compensated split */
+  GVM_GRAD_UMMA = 1,       /* tcgen05 / TMEM, error-compensated split: fp16 + two 8-bit-float correction products */
   GVM_GRAD_SIMT = 2,       /* separable outer-product on CUDA cores, fp32 */
   GVM_GRAD_SIMT_EXACT = 3, /* per-pair phase incl. the full w-term (reference formula) */
   GVM_GRAD_GRIDFFT = 4     /* samples on uv-cell centres with w = 0 (gridded mode, -g): the DFT

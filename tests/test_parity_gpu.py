@@ -138,7 +138,9 @@ def test_gradient_vs_fp64_oracle(small, oracle, mode, flag_opt):
     other = g[1 - flag_opt % 2]
     assert not other.any(), "only image flag_opt%2 receives the chi2 gradient"
     err = np.linalg.norm(got - want) / np.linalg.norm(want)
-    assert err <= 2e-5, (mode, flag_opt, err)
+    # north-star tolerance: 1e-4. The tensor-core path keeps its two correction products to 8-bit floats (1.3e-5 rms
+    # per term); the spectral-index gradient sums channels of both signs and shows it amplified (3.3e-5 here)
+    assert err <= (5e-5 if mode == GRAD_UMMA else 2e-5), (mode, flag_opt, err)
     masked = e.get_noise_image().reshape(-1)[pix] >= e.meta["noise_cut"]
     assert (got[masked] == 0).all()
 
@@ -264,13 +266,23 @@ def test_wterm_exact_vs_separable_wide_field(oracle):
     e.close()
 
 
-@pytest.mark.parametrize("wterm", [True, False])
-def test_umma_multitile_vs_simt_and_oracle(oracle, wterm):
+@pytest.mark.parametrize("wterm,split,gensplit,outliers", [
+    (True, "mixed", 2, False), (False, "mixed", 2, False), (True, "mixed", 1, False),
+    (True, "fp16x3", 2, False), (False, "fp16x3", 1, False), (True, "mixed", 2, True)])
+def test_umma_multitile_vs_simt_and_oracle(oracle, wterm, split, gensplit, outliers, monkeypatch):
     """Tensor-core gradient on a multi-tile image (2 x 4 tiles of 128 x 256 pixels... N = 384
     leaves ragged tiles on both axes), several TMEM chunks and split-K slices: every pixel
-    against the CUDA-core separable kernel, sampled pixels against the fp64 oracle."""
+    against the CUDA-core separable kernel, sampled pixels against the fp64 oracle. Both operand
+    splits (fp16 + two 8-bit-float correction products, the default; three fp16 products) and both
+    generator layouts; `outliers` spreads the weights over six decades (the 8-bit corrections see
+    amplitudes far below the largest one)."""
     torch = _torch()
+    monkeypatch.setenv("GVM_UMMA_SPLIT", split)
+    monkeypatch.setenv("GVM_UMMA_GENSPLIT", str(gensplit))
     p = synth.make_problem(N=384, nvis=70001, nchan=1, seed=17, wterm=wterm)
+    if outliers:
+        rng = np.random.default_rng(5)
+        p.w[0] = (p.w[0] * np.exp(rng.normal(0.0, 3.0, p.w[0].shape))).astype(np.float32)
     e = Engine.from_problem(p, grad_mode=GRAD_UMMA)
     I = _test_image(e)
     I_dev = torch.from_numpy(I).cuda()
@@ -289,7 +301,7 @@ def test_umma_multitile_vs_simt_and_oracle(oracle, wterm):
     want = _grad_oracle_sample(oracle, p, e, I_dev.cpu().numpy(), pix, 0)
     got = a.reshape(-1)[pix]
     err64 = np.linalg.norm(got - want) / np.linalg.norm(want)
-    print(f"\n[umma] wterm={wterm} rel-L2 vs SIMT={err:.3e} vs fp64 oracle={err64:.3e}")
+    print(f"\n[umma] wterm={wterm} split={split} gensplit={gensplit} outliers={outliers} rel-L2 vs SIMT={err:.3e} vs fp64 oracle={err64:.3e}")
     assert err64 <= 4e-5, err64
     e.close()
 
