@@ -10,12 +10,14 @@
 //   B_k(j) = w_k |Vr_k| exp(i (arg Vr_k - 2 pi (u_k x_j + w_k gA(x_j))))  ("B", N = j)
 // Neither operand can be materialised (B alone is N x 2Z), so K-blocks of both are
 // GENERATED into shared memory by CUDA-core warps — fixed-point phases (exact integer
-// wrap), MUFU sin/cos, error-compensated split of every fp32 value x into fp16
-// hi = rn(x), lo = rn(x - hi) — and consumed by tcgen05.mma (kind::f16, fp32 accumulate
-// in TMEM) as three products  Ah*Bh + Ah*Bl + Al*Bh  (the dropped Al*Bl is 2^-24
-// relative). fp16x3 carries the same 11+11 mantissa bits as a 3xTF32 split at twice
-// the tensor rate and half the shared-memory bytes; the exponent range is handled by
-// an exact power-of-two scale of B taken from max_k w|Vr| (reduced in the forward pass).
+// wrap), MUFU sin/cos, error-compensated split of every fp32 value x into hi = rn16(x)
+// and lo = x - hi — and consumed by tcgen05.mma with fp32 accumulation in TMEM:
+//   mixed split (default):  Ah*Bh as kind::f16, and the two corrections Al*Bh + Ah*Bl as
+//     ONE kind::f8f6f4 contraction over 8-bit-float copies (see split_mixed) on the same
+//     accumulator — 2 fp16-MMA times per useful product;
+//   fp16x3 (GVM_UMMA_SPLIT=fp16x3, round 1):  Ah*Bh + Ah*Bl + Al*Bh, all kind::f16.
+// The dropped Al*Bl is 2^-24 relative. The exponent range is handled by an exact
+// power-of-two scale of the amplitudes taken from max_k w|Vr| (reduced in the forward pass).
 //
 // Tile plan. DChi2 returns early for masked pixels (noise >= noise_cut, :3723-3726), so
 // only the unmasked part of the image is covered: 256-row bands starting at the first
@@ -27,13 +29,13 @@
 // half the shared-memory operand reads per output of a single-CTA 128 x 256 kernel, which
 // is what keeps the tensor pipe busy when every operand byte is computed, not loaded
 // (per SM and visibility at nbw = 256: tensor 96 clk, generation ~50 clk of issue slots,
-// shared memory 48 + 24 + 12 wavefronts).
+// shared memory 48 + 24 + 12 wavefronts; with the mixed split the tensor time is 64 clk).
 //
 // Warp roles per CTA (576 threads): 0-11 operand generators (one row per thread: A,
 // B block 0, B block 1), 12-15 epilogue (tcgen05.ld -> st/red.global into the split-K
-// scratch slice of this tile), 16 record producer (coalesced loads of the visibility
-// arrays, per-tile phase bases -> 16-byte records broadcast to the rows), 17 MMA issuer
-// (leader CTA only) + TMEM owner.
+// scratch slice of this tile), 16 record producer (bulk asynchronous copies of the
+// visibility arrays, per-tile phase bases -> 16-byte records broadcast to the rows), 17 MMA
+// issuer (leader CTA only) + TMEM owner.
 // Cross-CTA protocol: every generator warp of BOTH CTAs arrives (cluster scope) on the
 // LEADER's operand-full barrier; the leader's tcgen05.commit multicasts the stage-free
 // and accumulator-full arrivals to both CTAs; both epilogues arrive on the leader's
