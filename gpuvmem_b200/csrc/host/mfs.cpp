@@ -330,6 +330,16 @@ void MFS::configure(int argc, char** argv) {
   scheme->configure(&g.robust_param);
   scheme->setModifyWeights(g.modify_weights);
   double t0 = wallSeconds();
+  if (gridding) {
+    // weighting and gridding share one device work arena (this thread): size it once for the largest block, so that
+    // the gridding does not free and re-allocate what the weighting allocated (counted as weighting time)
+    int64_t zmax = 0;
+    for (auto& ds : datasets)
+      for (auto& f : ds.fields)
+        for (auto& chan : f.visibilities)
+          for (auto& v : chan) zmax = std::max<int64_t>(zmax, (int64_t)v.size());
+    GVM_CHECK(gvm_grid_reserve(g.firstgpu, g.M, g.N, zmax, g.world > 1 ? g.world : 1));
+  }
   scheme->apply(datasets);
   der.weighting_seconds = wallSeconds() - t0;
 

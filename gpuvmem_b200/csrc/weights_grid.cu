@@ -482,6 +482,14 @@ struct Arena {
   }
 };
 thread_local Arena g_arena_a, g_arena_b, g_arena_c, g_arena_r;
+// arena A of one tile-replay gridding call: the slice (zz samples), the grids, per-tile and per-sample tables
+size_t grid_arena_a_bytes(size_t zz, size_t MN, long ntiles, int world, size_t ck_elems) {
+  const size_t scan_n2 = gvm_scan_temp_bytes(2 * zz), scan_mn = gvm_scan_temp_bytes(MN), sort_tiles = gvm_sort_temp_bytes((size_t)ntiles);
+  size_t tmpA = scan_n2 > scan_mn ? scan_n2 : scan_mn;
+  tmpA = tmpA > sort_tiles ? tmpA : sort_tiles;
+  return zz * 24 + zz * 8 + zz * 4 + ck_elems * 4 + MN * 4 + MN * 8 + MN * 4 + MN * 4 + 4 * (size_t)ntiles * 4 + 3 * (2 * zz * 4) +
+         ((size_t)2 * world + 1) * 4 + (size_t)world * 2 * world * 4 + tmpA + 24 * 512;
+}
 // a carved buffer with DevBuf's accessors
 struct Raw {
   void* p;
@@ -582,6 +590,60 @@ float briggs_sum_of_weights(int nblocks, const int64_t* Z, float* const* w) {
   return sum_w;
 }
 
+
+// Briggs' second order-dependent scalar: sum over m, n in [N/2, N) of grid^2 as ONE sequential fp32 sum
+// (src/briggsweightingscheme.cu:96-106). Adding the +0.0 of an empty cell leaves a non-negative fp32 sum unchanged, so
+// only the cells whose square is non-zero matter, in the same order: they are compacted on the device in row-major
+// half-plane order (flags -> exclusive scan -> scatter) and the host adds the few that remain — instead of copying the
+// whole grid back (268 MB at 8192^2) and walking 33 M cells.
+__global__ void __launch_bounds__(256) k_half_flags(const float* __restrict__ grid, long M, long N, long nh,
+                                                    uint32_t* __restrict__ flags) {
+  const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (c >= M * nh) return;
+  const long m = c / nh, n = N / 2 + c % nh;
+  const float v = grid[N * m + n];
+  flags[c] = (v * v != 0.0f) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) k_half_compact(const float* __restrict__ grid, long M, long N, long nh,
+                                                      const uint32_t* __restrict__ pos, float* __restrict__ out) {
+  const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (c >= M * nh) return;
+  const long m = c / nh, n = N / 2 + c % nh;
+  const float v = grid[N * m + n];
+  if (v * v != 0.0f) out[pos[c]] = v;
+}
+inline size_t half_plane_scratch_bytes(long M, long N) {
+  const size_t nhalf = (size_t)M * (size_t)(N - N / 2);
+  return 2 * ((nhalf * 4 + 511) & ~(size_t)511) + gvm_scan_temp_bytes(nhalf) + 512;
+}
+// sum_g2 += the half plane's squares, in the reference's order; scratch: half_plane_scratch_bytes(M, N) device bytes
+int half_plane_sum_sq(const float* d_grid, long M, long N, void* scratch, cudaStream_t st, float* sum_g2) {
+  const long nh = N - N / 2;
+  const size_t nhalf = (size_t)M * (size_t)nh;
+  if (nhalf == 0) return 0;
+  const size_t plane = (nhalf * 4 + 511) & ~(size_t)511;
+  uint32_t* pos = static_cast<uint32_t*>(scratch);
+  float* vals = reinterpret_cast<float*>(static_cast<char*>(scratch) + plane);
+  void* scan_tmp = static_cast<char*>(scratch) + 2 * plane;
+  const int blocks = (int)((nhalf + 255) / 256);
+  k_half_flags<<<blocks, 256, 0, st>>>(d_grid, M, N, nh, pos);
+  uint32_t last_flag = 0, last_pos = 0;
+  WG_CUDA(cudaMemcpyAsync(&last_flag, pos + (nhalf - 1), 4, cudaMemcpyDeviceToHost, st));
+  if (gvm_exclusive_scan_u32(pos, nhalf, scan_tmp, st)) return 1;
+  WG_CUDA(cudaMemcpyAsync(&last_pos, pos + (nhalf - 1), 4, cudaMemcpyDeviceToHost, st));
+  k_half_compact<<<blocks, 256, 0, st>>>(d_grid, M, N, nh, pos, vals);
+  WG_CUDA(cudaGetLastError());
+  WG_CUDA(cudaStreamSynchronize(st));
+  const size_t count = (size_t)last_pos + last_flag;
+  if (count == 0) return 0;
+  std::vector<float> h(count);
+  if (gvm_fast_d2h(h.data(), vals, count * 4, st)) return 1;
+  float acc = *sum_g2;
+  for (size_t i = 0; i < count; i++) acc += h[i] * h[i];
+  *sum_g2 = acc;
+  return 0;
+}
+
 // UVTaper::getValue (include/classes/uvtaper.cuh:100-118), host libm, folded coordinates
 void apply_taper_host(const gvm_taper* t, int scheme, long Z, const double* uvw_m, float freq, float* w) {
   const float cb = cosf(t->bpa), sb = sinf(t->bpa), s2 = sinf(2.0f * t->bpa);
@@ -647,10 +709,14 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
   long zmax = 1;
   for (int b = 0; b < nblocks; b++) zmax = Z[b] > zmax ? (long)Z[b] : zmax;
   if (zmax >= (long)0x7FFFFFFF) { gvm_set_error("gvm_weights: block too large"); return 1; }
+  PhaseTimer pt;
   Arena& A = g_arena_a;   // one allocation for everything (kept between calls)
-  if (A.reserve(MN * 4 + (size_t)zmax * (24 + 4 + 4 + 4) + gvm_sort_temp_bytes((size_t)zmax) + 8 * 512)) return 1;
+  const size_t half_bytes = scheme == GVM_W_BRIGGS ? half_plane_scratch_bytes(M, N) : 0;
+  if (A.reserve(MN * 4 + (size_t)zmax * (24 + 4 + 4 + 4) + gvm_sort_temp_bytes((size_t)zmax) + half_bytes + 8 * 512)) return 1;
+  pt.mark("weights: arena");
   Raw d_grid{A.take<float>(MN)}, d_uvw{A.take<double>((size_t)zmax * 3)}, d_w{A.take<float>((size_t)zmax)},
       d_k0{A.take<uint32_t>((size_t)zmax)}, d_v0{A.take<uint32_t>((size_t)zmax)};
+  void* d_half = A.take<char>(half_bytes);
   void* d_tmp = A.take<char>(gvm_sort_temp_bytes((size_t)zmax));
   if (!d_tmp) { gvm_set_error("gvm_weights: arena too small"); return 1; }
   WG_CUDA(cudaMemset(d_grid.p, 0, MN * 4));
@@ -672,7 +738,6 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
     // without changing its rounding; it runs on a host thread next to the GPU's first pass
     std::thread sum_thread([&] { sum_w = briggs_sum_of_weights(nblocks, Z, w); });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{sum_thread};
-    std::vector<float> hgrid(MN);
     for (int b = 0; b < nblocks; b++) {
       const long z = (long)Z[b];
       if (z > 0) {
@@ -683,11 +748,12 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
       }
       // the first-pass grid is never cleared between blocks and the half-plane sum of squares is
       // taken after each one (src/briggsweightingscheme.cu:59-106)
-      if (gvm_fast_d2h(hgrid.data(), d_grid.p, MN * 4, 0)) return 1;
-      for (long m = 0; m < M; m++)
-        for (long n = N / 2; n < N; n++) sum_g2 += hgrid[N * m + n] * hgrid[N * m + n];
+      pt.mark("weights: upload + cells + sort + cell sums");
+      if (half_plane_sum_sq(d_grid.as<float>(), M, N, d_half, 0, &sum_g2)) return 1;
+      pt.mark("weights: half-plane sum of squares");
     }
     sum_thread.join();
+    pt.mark("weights: wait for the host sum of weights");
     const float avg = sum_g2 / sum_w;
     f_squared = (5.0f * powf(10.0f, -robust)) * (5.0f * powf(10.0f, -robust)) / avg;
     WG_CUDA(cudaMemset(d_grid.p, 0, MN * 4));
@@ -706,6 +772,7 @@ int gvm_weights(int device, int scheme, float robust, int64_t M, int64_t N, doub
       k_clear_cells<<<blocks, 256>>>(d_k0.as<uint32_t>(), z, d_grid.as<float>());
       WG_CUDA(cudaGetLastError());
       if (gvm_fast_d2h(w[b], d_w.p, (size_t)z * 4, 0)) return 1;
+      pt.mark("weights: second pass + weights to host");
     }
     if (use_taper) apply_taper_host(taper, scheme, z, uvw_m[b], freqs[b], w[b]);
   }
@@ -836,6 +903,22 @@ int gvm_grid_block(int device, int64_t M, int64_t N, double deltau, double delta
   return 0;
 }
 
+int gvm_grid_reserve(int device, int64_t M, int64_t N, int64_t Zmax, int world) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    gvm_set_error("gvm_grid_reserve: no CUDA device %d (no CPU fallback)", device);
+    return 1;
+  }
+  if (M < 1 || N < 1 || Zmax < 0 || world < 1) { gvm_set_error("gvm_grid_reserve: bad argument"); return 1; }
+  WG_CUDA(cudaSetDevice(device));
+  const size_t MN = (size_t)(M * N);
+  const size_t zz = (size_t)(Zmax / world + 1);
+  const long ntiles = (long)((N + kTile - 1) / kTile) * (long)((M + kTile - 1) / kTile);
+  const size_t grid = grid_arena_a_bytes(zz, MN, ntiles, world, (size_t)kMaxTaps);
+  const size_t weights = MN * 4 + zz * (24 + 4 + 4 + 4) + (size_t)Zmax * 4 + gvm_sort_temp_bytes(zz) + half_plane_scratch_bytes(M, N) + 8 * 512;
+  return g_arena_a.reserve(grid > weights ? grid : weights);
+}
+
 int gvm_grid_release(void) {
   g_grid_work = GridWork();
   g_arena_a = Arena(); g_arena_b = Arena(); g_arena_c = Arena(); g_arena_r = Arena();
@@ -900,9 +983,11 @@ int gvm_weights_dist(gvm_engine* e, int scheme, float robust, int nblocks, const
   }
   if (zmax >= (long)0x7FFFFFFF) { gvm_set_error("gvm_weights_dist: block too large"); return 1; }
   Arena& A = g_arena_a;   // one allocation for everything (kept between calls)
-  if (A.reserve(MN * 4 + (size_t)smax * (24 + 4 + 4 + 4) + (size_t)zmax * 4 + gvm_sort_temp_bytes((size_t)smax) + 8 * 512)) return 1;
+  const size_t half_bytes = scheme == GVM_W_BRIGGS ? half_plane_scratch_bytes(M, N) : 0;
+  if (A.reserve(MN * 4 + (size_t)smax * (24 + 4 + 4 + 4) + (size_t)zmax * 4 + gvm_sort_temp_bytes((size_t)smax) + half_bytes + 8 * 512)) return 1;
   Raw d_grid{A.take<float>(MN)}, d_uvw{A.take<double>((size_t)smax * 3)}, d_w{A.take<float>((size_t)smax)},
       d_k0{A.take<uint32_t>((size_t)smax)}, d_v0{A.take<uint32_t>((size_t)smax)}, d_wfull{A.take<float>((size_t)zmax)};
+  void* d_half = A.take<char>(half_bytes);
   void* d_tmp = A.take<char>(gvm_sort_temp_bytes((size_t)smax));
   if (!d_tmp) { gvm_set_error("gvm_weights_dist: arena too small"); return 1; }
 
@@ -964,7 +1049,6 @@ int gvm_weights_dist(gvm_engine* e, int scheme, float robust, int nblocks, const
     float sum_w = 0.0f, sum_g2 = 0.0f;
     std::thread sum_thread([&] { sum_w = briggs_sum_of_weights(nblocks, Z, w); });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{sum_thread};
-    std::vector<float> hgrid(MN);
     WG_CUDA(cudaMemsetAsync(d_grid.p, 0, MN * 4, st));
     for (int b = 0; b < nblocks; b++) {
       int64_t lo, hi;
@@ -974,11 +1058,9 @@ int gvm_weights_dist(gvm_engine* e, int scheme, float robust, int nblocks, const
       pt.mark("dist weights: ring accumulate + broadcast");
       // the first-pass grid is never cleared between blocks and the half-plane sum of squares is taken after
       // each one (src/briggsweightingscheme.cu:59-106): every rank repeats that sequential host sum
-      if (gvm_fast_d2h(hgrid.data(), d_grid.p, MN * 4, st)) return 1;
-      for (long m = 0; m < M; m++)
-        for (long n = N / 2; n < N; n++) sum_g2 += hgrid[N * m + n] * hgrid[N * m + n];
+      if (half_plane_sum_sq(d_grid.as<float>(), M, N, d_half, st, &sum_g2)) return 1;
     }
-    pt.mark("dist weights: grid to host + half-plane sum of squares");
+    pt.mark("dist weights: half-plane sum of squares (non-zero cells, compacted)");
     sum_thread.join();
     pt.mark("dist weights: wait for the host sum of weights");
     const float avg = sum_g2 / sum_w;
@@ -1032,13 +1114,7 @@ static int grid_block_core(gvm_engine* e, int device, cudaStream_t st, long M, l
   size_t tmpA = scan_n2 > scan_mn ? scan_n2 : scan_mn;
   tmpA = tmpA > sort_tiles ? tmpA : sort_tiles;
   Arena& A = g_arena_a;
-  {
-    const size_t r = 512;
-    const size_t total = zz * 24 + zz * 8 + zz * 4 + (size_t)ck_m * ck_n * 4 + MN * 4 + MN * 8 + MN * 4 + MN * 4 +
-                         4 * (size_t)ntiles * 4 + 3 * (2 * zz * 4) + ((size_t)2 * world + 1) * 4 +
-                         (size_t)world * 2 * world * 4 + tmpA + 24 * r;
-    if (A.reserve(total)) return 1;
-  }
+  if (A.reserve(grid_arena_a_bytes(zz, MN, ntiles, world, (size_t)ck_m * ck_n))) return 1;
   double* d_uvw = A.take<double>(zz * 3);
   float2* d_Vo = A.take<float2>(zz);
   float* d_w = A.take<float>(zz);

@@ -114,6 +114,7 @@ SIGNATURES = {
                                  _P, _P, _P, C.POINTER(C.c_int64)]),
     "gvm_grid_fetch": (C.c_int, [_P, _P, _P]),
     "gvm_grid_release": (C.c_int, []),
+    "gvm_grid_reserve": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
     "gvm_launch_count": (C.c_int64, [_P]),
     "gvm_last_grad_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "gvm_last_grad_mode": (C.c_int, [_P]),

@@ -374,6 +374,11 @@ int gvm_grid_block_dist(gvm_engine* e, float freq, int64_t Z, const double* uvw_
                         const float* ckernel, int ck_m, int ck_n, int support_x, int support_y, int64_t* nout);
 /* gvm_grid_block keeps its device work buffers between calls (this thread); this returns them. */
 int gvm_grid_release(void);
+/* Optional: size that work arena once, before the first gvm_weights* / gvm_grid_block* call of this thread, for blocks
+ * of up to Zmax samples on `world` ranks — otherwise weighting allocates it for its own (smaller) need and gridding
+ * frees and re-allocates it (a cudaMalloc of several GB costs 0.1-0.5 s here). The reference allocates its gridding
+ * buffers per call on the host (src/functions.cu:1339-1416). */
+int gvm_grid_reserve(int device, int64_t M, int64_t N, int64_t Zmax, int world);
 
 /* The engine's own stable radix sort (csrc/sort.cu: the tile-sorted upload of gvm_add_channel and the gridding
  * path order their samples with it instead of a library sort) on host arrays, in place: n (key, value) pairs by
