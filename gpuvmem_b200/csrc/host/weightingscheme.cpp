@@ -20,7 +20,6 @@ void WeightingScheme::applyOnGpu(int scheme, float robust, std::vector<MSDataset
   std::vector<const double*> uvw;
   std::vector<float> freqs;
   std::vector<float*> w;
-  std::vector<std::vector<float>> before;
   for (auto& ds : d)
     for (auto& f : ds.fields) {
       f.backup_visibilities.resize(f.visibilities.size());
@@ -32,7 +31,8 @@ void WeightingScheme::applyOnGpu(int scheme, float robust, std::vector<MSDataset
           uvw.push_back(v.uvw.data());
           freqs.push_back(f.nu[i]);
           w.push_back(v.weight.data());
-          before.push_back(v.weight);
+          // backup_visibilities: the weights before the scheme (one copy, taken now), or the new ones with -W
+          if (!modify_weights) f.backup_visibilities[i][s].weight = v.weight;
         }
       }
     }
@@ -46,13 +46,12 @@ void WeightingScheme::applyOnGpu(int scheme, float robust, std::vector<MSDataset
   else
     GVM_CHECK(gvm_weights(g.firstgpu, scheme, robust, g.M, g.N, g.deltau, g.deltav, (int)Z.size(), Z.data(),
                           uvw.data(), freqs.data(), w.data(), uvtaper ? &taper : nullptr));
-  // backup_visibilities: the weights before the scheme, or the new ones with -W (modify_weights)
-  size_t b = 0;
-  for (auto& ds : d)
-    for (auto& f : ds.fields)
-      for (size_t i = 0; i < f.visibilities.size(); i++)
-        for (size_t s = 0; s < f.visibilities[i].size(); s++, b++)
-          f.backup_visibilities[i][s].weight = modify_weights ? f.visibilities[i][s].weight : before[b];
+  if (modify_weights)
+    for (auto& ds : d)
+      for (auto& f : ds.fields)
+        for (size_t i = 0; i < f.visibilities.size(); i++)
+          for (size_t s = 0; s < f.visibilities[i].size(); s++)
+            f.backup_visibilities[i][s].weight = f.visibilities[i][s].weight;
 }
 
 void BriggsWeightingScheme::setRobustParam(float r) {
