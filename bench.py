@@ -576,7 +576,7 @@ def measure(ctx, name, scale, steps, warmup, recon_iters, grad_mode=0, lbfgs_k=1
 
 # the other named shapes of BASELINE.json, measured in the same process after the headline workload so that
 # the driver's BENCH/SCALE records carry them at every GPU count: (config, scale, steps, recon iterations)
-SIDE_CONFIGS = [("c1", 1.0, 20, 50), ("c3", 1.0, 3, 0), ("c5", 0.25, 10, 10)]
+SIDE_CONFIGS = [("c1", 1.0, 20, 50), ("c3", 1.0, 3, 0), ("c4l", 0.1, 2, 0), ("c5", 0.25, 10, 10)]
 
 
 def main():
@@ -596,7 +596,7 @@ def main():
     ap.add_argument("--full-eval-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--recon-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-configs", action="store_true", help="headline workload only (skip the C1/C3/C5 side measurements)")
+    ap.add_argument("--no-configs", action="store_true", help="headline workload only (skip the C1/C3/C4/C5 side measurements)")
     ap.add_argument("--recon-iters", type=int, default=10, help="optimizer iterations of the full-reconstruction leg (0: skip)")
     ap.add_argument("--lbfgs-k", type=int, default=10)
     args = ap.parse_args()
