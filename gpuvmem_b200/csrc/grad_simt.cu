@@ -243,25 +243,14 @@ __global__ void __launch_bounds__(256) k_grad_finish(const float* __restrict__ s
 // gvm_finish_pixel's.
 __global__ void __launch_bounds__(256) k_grad_finish4(const float* __restrict__ scratch, int ksplit,
                                                       const float* __restrict__ noise, float noise_cut, GvmFinishParams p) {
-  const long q = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  const long MN = p.M * p.N;
-  if (4 * q >= MN) return;
-  const float4 nz = __ldg(reinterpret_cast<const float4*>(noise) + q);
-  const bool m0 = nz.x >= noise_cut, m1 = nz.y >= noise_cut, m2 = nz.z >= noise_cut, m3 = nz.w >= noise_cut;
-  if (m0 && m1 && m2 && m3) return;
-  float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < ksplit; s++) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(scratch + (size_t)s * MN) + q);
-    d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
-  }
-  const float4 at = __ldg(reinterpret_cast<const float4*>(p.atten) + q);
-  float4 gc = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (p.gcf) gc = __ldg(reinterpret_cast<const float4*>(p.gcf) + q);
-  const float4 I0 = __ldg(reinterpret_cast<const float4*>(p.I) + q);
-  const float4 al = __ldg(reinterpret_cast<const float4*>(p.I + MN) + q);
+  const long MN = p.M * p.N, nq = MN / 4;
+  // two quads per thread, both mask loads in flight before anything depends on them
+  const long q0 = 2 * (blockIdx.x * (long)blockDim.x + threadIdx.x);
+  if (q0 >= nq) return;
+  const bool two = q0 + 1 < nq;
+  const float4 nz0 = __ldg(reinterpret_cast<const float4*>(noise) + q0);
+  const float4 nz1 = two ? __ldg(reinterpret_cast<const float4*>(noise) + q0 + 1) : make_float4(noise_cut, noise_cut, noise_cut, noise_cut);
   const bool odd = p.flag_opt % 2 != 0;
-  float4* rp = reinterpret_cast<float4*>(p.result + (odd ? MN : 0)) + q;
-  float4 r = *rp;
   const float nudiv = p.freq / p.nu_0;
   const float lognu = logf(nudiv);
   auto one = [&](float dv, float atten, float g, float i0, float alpha, float res, bool masked) -> float {
@@ -276,11 +265,29 @@ __global__ void __launch_bounds__(256) k_grad_finish4(const float* __restrict__ 
     const float dalpha = i0 * dI * p.fg_scale * lognu;
     return i0 > p.threshold ? res + dchi2 * dalpha : res;
   };
-  r.x = one(d.x, at.x, gc.x, I0.x, al.x, r.x, m0);
-  r.y = one(d.y, at.y, gc.y, I0.y, al.y, r.y, m1);
-  r.z = one(d.z, at.z, gc.z, I0.z, al.z, r.z, m2);
-  r.w = one(d.w, at.w, gc.w, I0.w, al.w, r.w, m3);
-  *rp = r;
+  auto quad = [&](long q, const float4& nz) {
+    const bool m0 = nz.x >= noise_cut, m1 = nz.y >= noise_cut, m2 = nz.z >= noise_cut, m3 = nz.w >= noise_cut;
+    if (m0 && m1 && m2 && m3) return;
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < ksplit; s++) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(scratch + (size_t)s * MN) + q);
+      d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+    }
+    const float4 at = __ldg(reinterpret_cast<const float4*>(p.atten) + q);
+    float4 gc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.gcf) gc = __ldg(reinterpret_cast<const float4*>(p.gcf) + q);
+    const float4 I0 = __ldg(reinterpret_cast<const float4*>(p.I) + q);
+    const float4 al = __ldg(reinterpret_cast<const float4*>(p.I + MN) + q);
+    float4* rp = reinterpret_cast<float4*>(p.result + (odd ? MN : 0)) + q;
+    float4 r = *rp;
+    r.x = one(d.x, at.x, gc.x, I0.x, al.x, r.x, m0);
+    r.y = one(d.y, at.y, gc.y, I0.y, al.y, r.y, m1);
+    r.z = one(d.z, at.z, gc.z, I0.z, al.z, r.z, m2);
+    r.w = one(d.w, at.w, gc.w, I0.w, al.w, r.w, m3);
+    *rp = r;
+  };
+  quad(q0, nz0);
+  if (two) quad(q0 + 1, nz1);
 }
 
 }  // namespace
@@ -400,7 +407,7 @@ int gvm_grad_finish(gvm_engine* e, GvmChannel& c, const float* I_dev, int ksplit
   const GvmFinishParams fp = gvm_finish_params(e, c, I_dev, flag_opt, normalize, result_dev);
   const bool vec4 = !fp.raw && fp.atten && MN % 4 == 0 && (((uintptr_t)I_dev | (uintptr_t)result_dev) & 15) == 0;
   if (vec4)
-    k_grad_finish4<<<(int)((MN / 4 + 255) / 256), 256, 0, e->stream>>>(e->grad_scratch, ksplit, e->noise, e->cfg.noise_cut, fp);
+    k_grad_finish4<<<(int)((MN / 8 + 255) / 256), 256, 0, e->stream>>>(e->grad_scratch, ksplit, e->noise, e->cfg.noise_cut, fp);
   else
     k_grad_finish<<<(int)((MN + 255) / 256), 256, 0, e->stream>>>(e->grad_scratch, ksplit, e->noise, e->cfg.noise_cut, fp);
   GVM_LAUNCH(e);

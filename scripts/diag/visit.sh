@@ -1,8 +1,9 @@
-bash scripts/gpu_run.sh "tests:weights or gridding or gridded or host or cli"
-GVM_GRID_TIMING=1 python bench.py --config c5 --scale 0.25 --steps 5 --warmup 3 --no-cpu-baseline --no-configs --recon-iters 0 > gpurun_out/c5q_timing.json 2> gpurun_out/c5q_timing.err
-grep "gvm timing" gpurun_out/c5q_timing.err | head -60
+SECONDS=0
+python bench.py > gpurun_out/bench_default_.json 2> gpurun_out/bench_default_.err
+echo "default bench wall seconds: $SECONDS"
 python - <<PY
 import json
-d=json.loads(open("gpurun_out/c5q_timing.json").read().strip().splitlines()[-1])
-print(d["ms_per_step"], d["preprocessing"], d["check"])
+d=json.loads(open("gpurun_out/bench_default_.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d["clocks"])
+for k,v in d["configs"].items(): print(k, v.get("value"), v.get("ms_per_step"), v.get("roofline",{}).get("frac"), v.get("error"))
 PY
