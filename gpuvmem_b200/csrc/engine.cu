@@ -110,6 +110,9 @@ static int create_impl(gvm_engine* e, const gvm_config* cfg, const cudaDevicePro
   // reference's host code (and torch, by default) launches on — safe drop-in semantics
   GVM_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamDefault));
   e->own_stream = true;
+  GVM_CUDA(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  GVM_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  GVM_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   const size_t MN = (size_t)cfg->M * cfg->N;
   GVM_CUDA(cudaMalloc(&e->I_nu, MN * sizeof(float2)));
   GVM_CUDA(cudaMalloc(&e->V, MN * sizeof(float2)));
@@ -170,6 +173,9 @@ int gvm_destroy(gvm_engine* e) {
   for (void* slab : e->pool_slabs) cudaFree(slab);   // blocks (live or cached) are carved out of the slabs
   for (auto ev : e->ev) cudaEventDestroy(ev);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   delete e;
   return 0;
 }
@@ -569,11 +575,15 @@ int gvm_graph_begin(gvm_engine* e) {
   GVM_CUDA(cudaSetDevice(e->cfg.device));
   GVM_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
   e->capturing = true;
+  e->fork_valid = false;
+  e->join_pending = false;
   return 0;
 }
 int gvm_graph_end(gvm_engine* e, void** graph_exec_out) {
   if (!e->capturing) { gvm_set_error("gvm_graph_end: no capture in progress"); return 1; }
+  gvm_join_branch(e);          // a forked prior-value branch must be back on the origin stream
   e->capturing = false;
+  e->fork_valid = false;
   cudaGraph_t graph = nullptr;
   cudaError_t err = cudaStreamEndCapture(e->stream, &graph);
   if (err != cudaSuccess || !graph) {

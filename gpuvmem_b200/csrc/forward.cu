@@ -848,6 +848,10 @@ int gvm_forward_channel(gvm_engine* e, GvmChannel& c, float* I_dev, bool first, 
   else       { if (half) GVM_PREP(false, true); else GVM_PREP(false, false); }
 #undef GVM_PREP
   GVM_LAUNCH(e);
+  if (first && e->capturing && e->ev_fork) {   // fork point of the captured evaluation (see gvm_prior_value_to_slot)
+    GVM_CUDA(cudaEventRecord(e->ev_fork, e->stream));
+    e->fork_valid = true;
+  }
   if (half) {
     if (cufftExecR2C(e->plan_r2c, reinterpret_cast<cufftReal*>(e->I_nu),
                      reinterpret_cast<cufftComplex*>(e->V)) != CUFFT_SUCCESS) {

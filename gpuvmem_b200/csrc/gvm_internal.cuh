@@ -114,6 +114,11 @@ struct gvm_engine {
   int64_t launches = 0;
   int64_t epoch = 0;               // bumped by every call that invalidates captured graphs (gvm_state_epoch)
   bool capturing = false;          // between gvm_graph_begin and gvm_graph_end
+  // inside a capture the prior values run on a forked branch of the graph: they only need the image as the first
+  // channel's preparation pass left it (clip2IWNoise), not the FFT / degridding chain behind it
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool fork_valid = false, join_pending = false;
   // telemetry
   std::vector<cudaEvent_t> ev;
   int ev_used = 0;
@@ -273,6 +278,7 @@ double gvm_wterm_cross_bound(const gvm_engine* e, const GvmChannel& c);
 // dist_nccl.cu: in-place sum all-reduce on the engine stream (no-op when world == 1)
 int gvm_dist_allreduce_f32(gvm_engine* e, float* buf, size_t n);
 int gvm_dist_allreduce_f64(gvm_engine* e, double* buf, size_t n);
+int gvm_join_branch(gvm_engine* e);   // priors.cu: the forked prior-value branch of a captured evaluation rejoins e->stream
 int gvm_dist_broadcast_f32(gvm_engine* e, float* buf, size_t n, int root);
 int gvm_dist_send(gvm_engine* e, const void* buf, size_t bytes, int peer);
 int gvm_dist_recv(gvm_engine* e, void* buf, size_t bytes, int peer);

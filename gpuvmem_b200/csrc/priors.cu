@@ -490,6 +490,15 @@ int make_args(gvm_engine* e, int kind, const float* I_dev, int image_index,
 
 }  // namespace
 
+// the forked branch joins the main stream (before the slots are copied back / the capture ends)
+int gvm_join_branch(gvm_engine* e) {
+  if (e->join_pending) {
+    GVM_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+    e->join_pending = false;
+  }
+  return 0;
+}
+
 extern "C" {
 
 static int prior_value_launch(gvm_engine* e, int kind, const float* I_dev, int image_index,
@@ -526,14 +535,28 @@ int gvm_prior_value(gvm_engine* e, int kind, const float* I_dev, int image_index
 int gvm_prior_value_to_slot(gvm_engine* e, int kind, const float* I_dev, int image_index,
                             const gvm_prior_params* p, int slot) {
   if (slot < 0 || slot >= GVM_OBJ_SLOTS) { gvm_set_error("gvm_prior_value_to_slot: slot %d out of range", slot); return 1; }
+  if (e->capturing && e->fork_valid) {
+    // captured evaluation: a branch that starts behind the image preparation of chi2 and joins before the slots are read
+    GVM_CUDA(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+    cudaStream_t main_stream = e->stream;
+    e->stream = e->stream2;
+    const int rc = prior_value_launch(e, kind, I_dev, image_index, p, e->obj_slots + 3 * slot);
+    e->stream = main_stream;
+    if (rc) return rc;
+    GVM_CUDA(cudaEventRecord(e->ev_join, e->stream2));
+    e->join_pending = true;
+    return 0;
+  }
   return prior_value_launch(e, kind, I_dev, image_index, p, e->obj_slots + 3 * slot);
 }
+
 int gvm_chi2_to_slot(gvm_engine* e, float* I_dev, int normalize, int slot) {
   if (slot < 0 || slot >= GVM_OBJ_SLOTS) { gvm_set_error("gvm_chi2_to_slot: slot %d out of range", slot); return 1; }
   return gvm_chi2_async(e, I_dev, normalize, e->obj_slots + 3 * slot);
 }
 int gvm_fetch_slots_enqueue(gvm_engine* e, int n) {
   if (n < 0 || n > GVM_OBJ_SLOTS) { gvm_set_error("gvm_fetch_slots: %d slots requested", n); return 1; }
+  if (gvm_join_branch(e)) return 1;
   GVM_CUDA(cudaMemcpyAsync(e->h_slots, e->obj_slots, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   return 0;
 }
