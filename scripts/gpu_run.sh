@@ -11,6 +11,8 @@
 #   ncu:<kernel regex>[:cfg[:skip]]   one ncu --set full capture of that kernel
 #   multi:N        test_multi_gpu + torchrun bench at N ranks (use with gpurun --gpus N)
 #   sanitizer      compute-sanitizer memcheck over the small parity tests
+#   diag:<name>[:args]   build scripts/diag/<name>.cu for sm_100a on the box and run it (umma_arith, umma_fp8mix, mufu_err,
+#                  cluster_occupancy) -> gpurun_out/diag_<name>.txt
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/gpus.txt 2>&1
 for stage in "$@"; do
@@ -56,6 +58,11 @@ for stage in "$@"; do
       timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py tests/test_edges_gpu.py -m gpu -q -x \
         -k "not full_size" > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"
       tail -n 5 gpurun_out/sanitizer_memcheck.log ;;
+    diag)
+      IFS=: read -r prog pargs <<< "$arg"
+      nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/diag_$prog scripts/diag/$prog.cu > gpurun_out/diag_$prog.txt 2>&1 &&
+        timeout 300 /tmp/diag_$prog $pargs >> gpurun_out/diag_$prog.txt 2>&1; echo "diag $prog rc=$?"
+      tail -n 25 gpurun_out/diag_$prog.txt ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
