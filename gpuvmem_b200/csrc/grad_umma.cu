@@ -228,11 +228,14 @@ __device__ __forceinline__ void split2(float c, float s, uint32_t& hi, uint32_t&
 // Mixed split (kMixed): x = hi + lo with hi = rn16(x) as before, but the two correction products are formed from 8-bit
 // float operands at twice the fp16 tensor rate. The amplitude w|Vr| 2^e (< 2^14.5) rides on the A rows, the B rows are
 // unit phasors, and the second block of every operand holds 128 one-byte K elements per row:
-//   A rows: [ e4m3(lo) x 64 | e5m2(hi) x 64 ]      B rows: [ e4m3(hi) x 64 | e5m2(lo) x 64 ]
-// so bytes 0-63 contract to Al Bh (E4M3 x E4M3: |Al| <= 8, |Bh| <= 1) and bytes 64-127 to Ah Bl (E5M2 x E5M2: the five
-// exponent bits take |Ah| < 2^14.5 and |Bl| <= 2^-12 as they are) — no scaling instruction in the generators. Each
-// correction is ~2^-12 of its term and is kept to 2^-4 / 2^-3: 1.3e-5 rms of the term (scripts/diag/umma_fp8mix.cu and
-// the numpy model in DESIGN.md §3.3; the third fp16 product kept it at 1e-7 — both are at or below the 1.2e-5 of the phases).
+//   A rows: [ e5m2(lo) x 64 | e5m2(hi) x 64 ]      B rows: [ e4m3(hi) x 64 | e5m2(lo) x 64 ]
+// so bytes 0-63 contract to Al Bh (E5M2 x E4M3) and bytes 64-127 to Ah Bl (E5M2 x E5M2). Everything that carries the
+// amplitude, or is 2^-12 of something, is E5M2: its five exponent bits take |Ah| < 2^14.5, |Bl| <= 2^-12 and |Al| from 8
+// down to 2^-16 as they are — no scaling instruction in the generators, and visibilities 2^15 times weaker than the
+// strongest one (which sets the fp16 scale) still get their correction (with E4M3 for Al a population 2^12 below the
+// maximum lost it: 1.9e-4 on that population in the numpy model). Each correction is ~2^-12 of its term and is kept to
+// 2^-3 / 2^-4: 1.4e-5 rms of the term (scripts/diag/umma_fp8mix.cu; the third fp16 product kept it at
+// 1e-7 — both are at or below the 1.2e-5 of the phases).
 template <bool kIsA>
 __device__ __forceinline__ void split_mixed(float c, float s, uint32_t& hi, uint32_t& first8, uint32_t& second8) {
   const __half2 h = __floats2half2_rn(c, s);
@@ -240,7 +243,7 @@ __device__ __forceinline__ void split_mixed(float c, float s, uint32_t& hi, uint
   const float2 lo = make_float2(c - hf.x, s - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   if (kIsA) {
-    first8 = __nv_cvt_float2_to_fp8x2(lo, __NV_SATFINITE, __NV_E4M3);
+    first8 = __nv_cvt_float2_to_fp8x2(lo, __NV_SATFINITE, __NV_E5M2);
     second8 = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(h), __NV_SATFINITE, __NV_E5M2);
   } else {
     first8 = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(h), __NV_SATFINITE, __NV_E4M3);
@@ -501,7 +504,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(nthreads(kSplit), 1)
   } else if (rank == 0 && lane == 0) {
     // ================================================= MMA issuer (one thread of the leader CTA)
     const uint32_t idesc = (1u << 4) | ((uint32_t)(nbw >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // formats 0: F16 / E4M3
-    const uint32_t idesc_e5m2 = idesc | (1u << 7) | (1u << 10);
+    const uint32_t idesc_albh = idesc | (1u << 7);                 // A E5M2 (bits 7-9 = 1), B E4M3
+    const uint32_t idesc_ahbl = idesc | (1u << 7) | (1u << 10);    // A E5M2, B E5M2 (bits 10-12 = 1)
     for (int it = 0; it < nst; it++) {
       const int s = it % NSTAGE;
       const int cpos = it % chunk_stages;
@@ -529,9 +533,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(nthreads(kSplit), 1)
         }
         if (kMixed) {
 #pragma unroll
-          for (int kstep = 0; kstep < 4; kstep++) {   // 4 x (K = 32 bytes): Al Bh (E4M3) over bytes 0-63, Ah Bl (E5M2) over 64-127
+          for (int kstep = 0; kstep < 4; kstep++) {   // 4 x (K = 32 bytes): Al Bh (E5M2 x E4M3) over bytes 0-63, Ah Bl (E5M2 x E5M2) over 64-127
             const uint32_t ko = (uint32_t)kstep * 32;
-            tc_mma_pair_f8(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_lo + ko), kstep < 2 ? idesc : idesc_e5m2, 1u);
+            tc_mma_pair_f8(d, umma_desc_sw128(a_lo + ko), umma_desc_sw128(b_lo + ko), kstep < 2 ? idesc_albh : idesc_ahbl, 1u);
           }
         }
       }

@@ -268,19 +268,24 @@ def test_wterm_exact_vs_separable_wide_field(oracle):
 
 @pytest.mark.parametrize("wterm,split,gensplit,outliers", [
     (True, "mixed", 2, False), (False, "mixed", 2, False), (True, "mixed", 1, False),
-    (True, "fp16x3", 2, False), (False, "fp16x3", 1, False), (True, "mixed", 2, True)])
+    (True, "fp16x3", 2, False), (False, "fp16x3", 1, False), (True, "mixed", 2, True), (True, "mixed", 1, "one")])
 def test_umma_multitile_vs_simt_and_oracle(oracle, wterm, split, gensplit, outliers, monkeypatch):
     """Tensor-core gradient on a multi-tile image (2 x 4 tiles of 128 x 256 pixels... N = 384
     leaves ragged tiles on both axes), several TMEM chunks and split-K slices: every pixel
     against the CUDA-core separable kernel, sampled pixels against the fp64 oracle. Both operand
     splits (fp16 + two 8-bit-float correction products, the default; three fp16 products) and both
     generator layouts; `outliers` spreads the weights over six decades (the 8-bit corrections see
-    amplitudes far below the largest one)."""
+    amplitudes far below the largest one); "one" gives a single visibility 8192 times the weight of all
+    others: it sets the fp16 scale and the whole remaining population sits 2^13 below it (exercises the
+    underflow / saturation handling of the 8-bit operands; at this Z the outlier dominates the gradient, so
+    the accuracy of the weak population in that regime is pinned by the numpy model of DESIGN.md §3.3)."""
     torch = _torch()
     monkeypatch.setenv("GVM_UMMA_SPLIT", split)
     monkeypatch.setenv("GVM_UMMA_GENSPLIT", str(gensplit))
     p = synth.make_problem(N=384, nvis=70001, nchan=1, seed=17, wterm=wterm)
-    if outliers:
+    if outliers == "one":
+        p.w[0][12345] *= 8192.0
+    elif outliers:
         rng = np.random.default_rng(5)
         p.w[0] = (p.w[0] * np.exp(rng.normal(0.0, 3.0, p.w[0].shape))).astype(np.float32)
     e = Engine.from_problem(p, grad_mode=GRAD_UMMA)
