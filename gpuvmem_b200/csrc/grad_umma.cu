@@ -166,9 +166,11 @@ __device__ __forceinline__ void tc_mma_pair_f8(uint32_t d_tmem, uint64_t a_desc,
       "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+// 16 TMEM lanes x 64 columns: thread t holds, for j = 0..7, lanes t/4 (v[4j], v[4j+1]) and t/4 + 8 (v[4j+2], v[4j+3]),
+// columns 8j + 2 (t % 4) + {0, 1} — four neighbouring threads cover one 32-byte sector of a row
+__device__ __forceinline__ void tc_ld_16x256b_x8(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -192,13 +194,11 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
-__device__ __forceinline__ void st_global_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void st_global_v2(float* p, float a, float b) {
+  asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
-// fire-and-forget fp32 add in L2: no load latency in the epilogue; each address is only ever
-// touched by one thread of one CTA, so the result does not depend on scheduling
-__device__ __forceinline__ void red_global_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void red_global_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
@@ -414,28 +414,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(nthreads(kSplit), 1)
     // ================================================= epilogue: TMEM -> split-K scratch slice
     const int q = warp - W_EPI;
     const int nchunks = (nst + chunk_stages - 1) / chunk_stages;
-    // compact scratch: [K slice][tile][256 rows][2 x 256 columns]
-    float* orow = scratch + (((size_t)ks * ntiles + tile) * TILE_I + (128 * rank + 32 * q + lane)) * TILE_J;
-    const int ncb = (nbw + 31) >> 5;
     const uint32_t acc_empty_remote = mapa_rank(BAR_ACC_EMPTY, 0);
+    // 16x256b TMEM loads: four neighbouring threads hold one 32-byte sector of an output row, so every st / red
+    // instruction of the warp touches 8 full sectors (the 32x32b shape gave 32 half-used ones: 1.3 % of the step).
+    // The adds are fire-and-forget fp32 reductions in L2 and each address is only ever touched by one thread of one
+    // CTA, so the result does not depend on scheduling. They are the cost of draining (20 ms of a C2 step, element-
+    // bound in L2; the TMEM reads are free).
+    float* tile_base = scratch + ((size_t)ks * ntiles + tile) * TILE_I * TILE_J;   // compact scratch: [K slice][tile][256 rows][2 x 256 columns]
+    const int n64 = (nbw + 63) >> 6;
     for (int c = 0; c < nchunks; c++) {
       mbar_wait(BAR_ACC_FULL, (uint32_t)(c & 1));
       tc_fence_after();
 #pragma unroll 1
-      for (int cbi = 0; cbi < 2 * ncb; cbi++) {
-        const int nb = cbi >= ncb, cb = cbi - nb * ncb;
-        const int col = nb * 256 + cb * 32;
+      for (int b = 0; b < 4 * n64; b++) {
+        const int hh = b & 1, cbn = b >> 1;          // lane half of the quadrant, 64-column block
+        const int nb = cbn >= n64, cb = cbn - nb * n64;
+        const int col = nb * 256 + cb * 64;
         uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)col, v);
+        tc_ld_16x256b_x8(tmem_base + ((uint32_t)(32 * q + 16 * hh) << 16) + (uint32_t)col, v);
         tc_wait_ld();
+        float* pa = tile_base + (size_t)(128 * rank + 32 * q + 16 * hh + (lane >> 2)) * TILE_J + col + 2 * (lane & 3);
+        float* pb = pa + 8 * TILE_J;
 #pragma unroll
-        for (int g = 0; g < 8; g++) {
-          if (cb * 32 + g * 4 < nbw) {   // nbw % 4 == 0
-            float* p = orow + col + g * 4;
-            const float a0 = __uint_as_float(v[4 * g]), a1 = __uint_as_float(v[4 * g + 1]),
-                        a2 = __uint_as_float(v[4 * g + 2]), a3 = __uint_as_float(v[4 * g + 3]);
-            if (c == 0) st_global_v4(p, a0, a1, a2, a3);
-            else red_global_v4(p, a0, a1, a2, a3);
+        for (int j = 0; j < 8; j++) {
+          if (cb * 64 + 8 * j < nbw) {   // nbw % 16 == 0
+            const float a0 = __uint_as_float(v[4 * j]), a1 = __uint_as_float(v[4 * j + 1]),
+                        b0 = __uint_as_float(v[4 * j + 2]), b1 = __uint_as_float(v[4 * j + 3]);
+            if (c == 0) { st_global_v2(pa + 8 * j, a0, a1); st_global_v2(pb + 8 * j, b0, b1); }
+            else { red_global_v2(pa + 8 * j, a0, a1); red_global_v2(pb + 8 * j, b0, b1); }
           }
         }
       }
