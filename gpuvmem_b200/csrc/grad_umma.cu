@@ -41,8 +41,9 @@
 // and accumulator-full arrivals to both CTAs; both epilogues arrive on the leader's
 // accumulator-empty barrier. The accumulator is drained every `chunk` visibilities:
 // TMEM accumulation is fp32 with round-toward-zero per instruction (measured,
-// scripts/diag/umma_arith.cu), so the bias grows linearly with the chunk length
-// (6e-9 relative per visibility): 2048 keeps the gradient at ~1e-5 of the fp64 truth.
+// scripts/diag/umma_arith.cu), a shrink that grows linearly with the chunk length
+// (6e-9 relative per visibility); the epilogue gives the expected loss back, which leaves
+// the gradient of a coherent sky at 1-4e-6 of the fp64 truth at chunk = 4096.
 #include <climits>
 #include <algorithm>
 #include <cstdlib>
@@ -425,6 +426,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(nthreads(kSplit), 1)
     for (int c = 0; c < nchunks; c++) {
       mbar_wait(BAR_ACC_FULL, (uint32_t)(c & 1));
       tc_fence_after();
+      // Expected truncation loss of this chunk, given back: every tcgen05.mma adds its K-sum to the accumulator with
+      // round-toward-zero (scripts/diag/umma_arith.cu), i.e. loses on average half an ulp of |acc| = 0.5 * 2^-23 * E[1/m]
+      // = 4.2e-8 of |acc| per instruction (mantissa m in [1, 2)); for an accumulator that grows from 0 over n
+      // instructions that is a shrink by n * 2.1e-8. Measured without the correction: 1.17e-5 at n = 512, 1.56e-5 at
+      // n = 768, linear in the chunk length; the factor that minimises the error against the fp64 oracle is 1.9e-8
+      // (scripts/diag/noise_like_gradient.py, coherent sky) to 2.3e-8 (C2) per instruction. With it the gradient of a
+      // coherent sky is at 3-6e-6 of the oracle at chunk = 4096 instead of 2.3e-5 (what remains is the pixel-to-pixel
+      // spread of the loss); a random-walk accumulator (noise-like residuals) keeps 0.58 of the shrink as rms error
+      // after the correction, 1.15 without.
+      const int stages_here = min(chunk_stages, nst - c * chunk_stages);
+      const float unshrink = 1.0f + 2.1e-8f * (float)(stages_here * (kMixed ? 8 : 12));
 #pragma unroll 1
       for (int b = 0; b < 4 * n64; b++) {
         const int hh = b & 1, cbn = b >> 1;          // lane half of the quadrant, 64-column block
@@ -438,8 +450,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(nthreads(kSplit), 1)
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           if (cb * 64 + 8 * j < nbw) {   // nbw % 16 == 0
-            const float a0 = __uint_as_float(v[4 * j]), a1 = __uint_as_float(v[4 * j + 1]),
-                        b0 = __uint_as_float(v[4 * j + 2]), b1 = __uint_as_float(v[4 * j + 3]);
+            const float a0 = unshrink * __uint_as_float(v[4 * j]), a1 = unshrink * __uint_as_float(v[4 * j + 1]),
+                        b0 = unshrink * __uint_as_float(v[4 * j + 2]), b1 = unshrink * __uint_as_float(v[4 * j + 3]);
             if (c == 0) { st_global_v2(pa + 8 * j, a0, a1); st_global_v2(pb + 8 * j, b0, b1); }
             else { red_global_v2(pa + 8 * j, a0, a1); red_global_v2(pb + 8 * j, b0, b1); }
           }
@@ -716,8 +728,9 @@ int gvm_grad_umma(gvm_engine* e, GvmChannel& c, const float* I_dev, int flag_opt
   if (use_w)
     if (gvm_build_pixtab(e, c)) return 1;
 
-  // visibilities per TMEM accumulation chunk (bounds the round-toward-zero bias, see header)
-  long chunk = 2048;
+  // visibilities per TMEM accumulation chunk (bounds what is left of the round-toward-zero bias after the epilogue's
+  // correction; every drain costs 512 KB of L2 reductions per CTA pair: 2048 -> 4096 is 3.8 % of a C2 step)
+  long chunk = 4096;
   if (const char* s = getenv("GVM_UMMA_CHUNK")) chunk = atol(s);
   chunk = (chunk / KV) * KV;
   if (chunk < KV) chunk = KV;
