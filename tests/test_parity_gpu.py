@@ -301,13 +301,15 @@ def test_umma_multitile_vs_simt_and_oracle(oracle, wterm, split, gensplit, outli
     e.synchronize()
     a, b = g_t.cpu().numpy()[0], g_s.cpu().numpy()[0]
     err = np.linalg.norm(a - b) / np.linalg.norm(b)
-    assert err <= 4e-5, err
+    assert err <= 2e-5, err
     pix = np.arange(0, p.N * p.N, 211)
     want = _grad_oracle_sample(oracle, p, e, I_dev.cpu().numpy(), pix, 0)
     got = a.reshape(-1)[pix]
     err64 = np.linalg.norm(got - want) / np.linalg.norm(want)
     print(f"\n[umma] wterm={wterm} split={split} gensplit={gensplit} outliers={outliers} rel-L2 vs SIMT={err:.3e} vs fp64 oracle={err64:.3e}")
-    assert err64 <= 4e-5, err64
+    # measured: 3-4e-6 (the epilogue gives the expected truncation loss of the TMEM accumulation back), 1.2-1.4e-5 with
+    # weights spread over many decades
+    assert err64 <= (2e-5 if outliers else 8e-6), err64
     e.close()
 
 
