@@ -206,7 +206,7 @@ def test_full_size_c2_properties(oracle):
         got = g[0].cpu().numpy().reshape(-1)[pix]
         err = _rel(got, truth)
         print(f"\n[C2 full size] gradient rel-L2 vs fp64 oracle over 10 M visibilities at {len(pix)} pixels: {err:.3e}")
-        assert err <= 1e-4, err          # north-star tolerance; measured ~1e-5
+        assert err <= 2e-5, err          # north-star tolerance 1e-4; measured 5.7e-6 (1.2e-5 before the truncation correction)
     finally:
         e.close()
 
