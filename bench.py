@@ -528,9 +528,9 @@ def measure(ctx, name, scale, steps, warmup, recon_iters, grad_mode=0, lbfgs_k=1
                             f"peak = measured HBM copy bandwidth ({pk['source']})"}
         if mode == 1 and name == "c2" and scale == 1.0 and world == 1:
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this exact workload,
-            # from the committed ncu --set full capture (profiles/r2d_traffic.json; r1b_traffic.json for the fp16x3 split)
+            # from the committed ncu --set full capture (profiles/r2f_traffic.json; r1b_traffic.json for the fp16x3 split)
             try:
-                tr = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json" if fp16x3 else "r2d_traffic.json")))
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json" if fp16x3 else "r2f_traffic.json")))
                 roof["traffic"] = next(iter(tr.values()))["dram_bytes_total"]
                 roof["traffic_note"] = ("bytes per launch (ncu); algorithmic minimum 28 B x Z per tile pass x 32 tiles, "
                                         "served from L2, + the split-K scratch slices (340 MB written once); DRAM at 0.03 % of peak")
