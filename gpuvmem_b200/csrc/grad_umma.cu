@@ -107,7 +107,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 }
 // The suspend-time hint lets a waiting warp sleep until the phase completes (or the hint expires) instead of polling:
 // the four epilogue warps wait for 64 stages at a time and their polls took 12 % of the issue slots of the generators
-// (ncu source view, profiles/r2d_k_grad_umma_mixed_ncu_summary.txt).
+// (ncu source view, profiles/r2d_k_grad_umma_mixed_c2_ncu_full_summary.txt).
 // Operand hand-over to the tensor core of the pair: the generic-proxy stores were made visible to the async proxy by
 // fence.proxy.async; the arrive itself needs no cluster-scope release (which costs MEMBAR.ALL.GPU + ERRBAR per warp and
 // stage) — the consumer is tcgen05.mma reading shared memory through the async proxy, not a generic load.
