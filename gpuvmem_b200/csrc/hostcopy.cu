@@ -6,6 +6,8 @@
 // copy is a pipeline over a ring of pinned 32 MB buffers: worker threads fill a buffer from the
 // caller's memory in parallel while the DMA engine drains the previous ones at PCIe speed.
 // Small copies (< 8 MB) go through plain cudaMemcpy.
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -47,8 +49,13 @@ int copy_threads() {
     const char* s = getenv("GVM_COPY_THREADS");
     int v = s ? atoi(s) : 0;
     if (v <= 0) {
+      // measured on a 16-core B200 host, 1.8 GB from pageable memory: 6 threads 73 ms, 10 threads 62 ms, 14 threads 57 ms
       const unsigned hc = std::thread::hardware_concurrency();
-      v = hc >= 16 ? 6 : (hc >= 8 ? 4 : 2);
+      v = hc >= 16 ? 10 : (hc >= 8 ? 4 : 2);
+      // one process per GPU: share the cores with the other ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
+      const char* lws = getenv("LOCAL_WORLD_SIZE");
+      const int ranks = lws ? atoi(lws) : 1;
+      if (ranks > 1 && hc > 0) v = std::max(2, std::min(v, (int)hc / ranks));
     }
     return v > 16 ? 16 : v;
   }();
