@@ -16,6 +16,7 @@
 // evaluated on the host: it calls libm's exp/cosf/sinf, which no device routine matches bit for bit.
 #include <cmath>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -226,7 +227,6 @@ __global__ void __launch_bounds__(kThreads) k_grid_accumulate(
 // The per-pair record (centre, weight, visibility) is gathered into sorted order first, so the replay
 // streams 16 B per pair with one coalesced load per 32 samples.
 constexpr int kTile = 16;
-constexpr int kTileStride = kTile + 1;   // shared-memory row stride (in 16-byte cells): spreads the tap rows over the banks
 
 __device__ __forceinline__ bool grid_centre(const double* __restrict__ uvw_m, long z, long Z, float freq,
                                             double deltau, double deltav, long M, long N, int sx, int sy, int* j,
@@ -287,79 +287,67 @@ __global__ void __launch_bounds__(256) k_tile_order_keys(const int* __restrict__
   vals[t] = (uint32_t)t;
 }
 
-template <int kRounds>
-__global__ void __launch_bounds__(32) k_grid_tiles(const uint32_t* __restrict__ order, const int* __restrict__ tstart,
-                                                   const int* __restrict__ tend, const float4* __restrict__ rec,
-                                                   const float* __restrict__ kernel, int ck_m, int ck_n, int sx, int sy,
-                                                   long M, long N, int ntx, float* __restrict__ out_w,
-                                                   float2* __restrict__ out_V) {
-  // (gw, gw2, gvr, gvi) of every cell of the tile: one 16-byte shared-memory word per cell
-  __shared__ float4 s_acc[kTile * kTileStride];
-  const int lane = threadIdx.x;
+// Tile-sequential replay with one THREAD PER CELL (256 threads per 16 x 16 tile): every thread walks the tile's records
+// (sorted by tile, ascending sample index inside a tile) and adds the tap that lands on its cell, accumulators in
+// registers. Per cell the fp32 operation sequence is exactly the reference's loop (src/functions.cu:1418-1508: ascending
+// sample index, the same products), so the result is bit-identical to it. Round 1 ran one WARP per tile with the lanes
+// over the taps and the accumulators in shared memory (bit-identical as well): a dense tile (44 k samples against a mean
+// of 755 at C5) was serialised on that warp and lanes idled on taps outside the tile; 38 -> 28 ms at C5 / 4.
+__global__ void __launch_bounds__(kTile * kTile) k_grid_tiles_cells(
+    const uint32_t* __restrict__ order, const int* __restrict__ tstart, const int* __restrict__ tend,
+    const float4* __restrict__ rec, const float* __restrict__ kernel, int ck_m, int ck_n, int sx, int sy, long M, long N,
+    int ntx, float* __restrict__ out_w, float2* __restrict__ out_V) {
+  __shared__ float4 s_rec[kTile * kTile];
+  __shared__ float s_ck[kMaxTaps];
+  const int tid = threadIdx.x;
   const int tile = (int)order[blockIdx.x];
+  const int b = tstart[tile], e = tend[tile];
   const int ty = tile / ntx, tx = tile - ty * ntx;
   const int k0 = ty * kTile, j0 = tx * kTile;
-  for (int c = lane; c < kTile * kTileStride; c += 32) s_acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-  // cells of the tile that lie on the grid (edge tiles): [0, lim_j) x [0, lim_k)
-  const unsigned lim_j = (unsigned)min((long)kTile, N - j0), lim_k = (unsigned)min((long)kTile, M - k0);
-  // this lane's taps: offsets from the centre and kernel values
-  const int tw = 2 * sx + 1, taps = tw * (2 * sy + 1);
-  int dm[kRounds], dn[kRounds];
-  float ckv[kRounds], ck2v[kRounds];
-#pragma unroll
-  for (int r = 0; r < kRounds; r++) {
-    const int t = lane + 32 * r;
-    const int ki = t / tw, kj = t - ki * tw;
-    const bool on = t < taps && ki < ck_m && kj < ck_n;
-    dm[r] = on ? ki - sy : -100000;     // an inactive tap lands outside every tile
-    dn[r] = kj - sx;
-    ckv[r] = on ? kernel[ck_n * ki + kj] : 0.f;
-    ck2v[r] = __fmul_rn(ckv[r], ckv[r]);
+  const int ck_ = tid / kTile, cj = tid - ck_ * kTile;
+  const bool on_grid = (long)(j0 + cj) < N && (long)(k0 + ck_) < M;
+  const long cell = (long)(k0 + ck_) * N + (j0 + cj);
+  if (b >= e) {                       // empty tile: the grids are not cleared beforehand
+    if (on_grid) { out_w[cell] = 0.f; out_V[cell] = make_float2(0.f, 0.f); }
+    return;
   }
-  __syncwarp();
-  const int b = tstart[tile], e = tend[tile];
-  for (int base = b; base < e; base += 32) {
-    const int n = min(32, e - base);
-    float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < n) mine = __ldg(&rec[base + lane]);
-    for (int sidx = 0; sidx < n; sidx++) {
-      const uint32_t cp = __float_as_uint(__shfl_sync(0xffffffffu, mine.x, sidx));
-      const float wt = __shfl_sync(0xffffffffu, mine.y, sidx);
-      const float vr = __shfl_sync(0xffffffffu, mine.z, sidx);
-      const float vim = __shfl_sync(0xffffffffu, mine.w, sidx);
-      const int lj = (int)(cp & 0xFFFFu) - sx - j0, lk = (int)(cp >> 16) - sy - k0;   // centre relative to the tile
-      const float wr = __fmul_rn(wt, vr), wi = __fmul_rn(wt, vim);
-#pragma unroll
-      for (int r = 0; r < kRounds; r++) {
-        const unsigned cj = (unsigned)(lj + dn[r]), ck_ = (unsigned)(lk + dm[r]);
-        if (cj < lim_j && ck_ < lim_k) {
-          float4* cell = &s_acc[ck_ * kTileStride + cj];
-          float4 a = *cell;
-          a.x = __fadd_rn(a.x, __fmul_rn(wt, ckv[r]));
-          a.y = __fadd_rn(a.y, __fmul_rn(wt, ck2v[r]));
-          a.z = __fadd_rn(a.z, __fmul_rn(wr, ckv[r]));
-          a.w = __fadd_rn(a.w, __fmul_rn(wi, ckv[r]));
-          *cell = a;
-        }
+  // the taps that exist: rows ki < min(2 sy + 1, ck_m), columns kj < min(2 sx + 1, ck_n) of the table (<= kMaxTaps)
+  const unsigned tw = (unsigned)min(2 * sx + 1, ck_n), th = (unsigned)min(2 * sy + 1, ck_m);
+  for (int t = tid; t < (int)(tw * th); t += kTile * kTile) s_ck[t] = kernel[ck_n * (t / (int)tw) + t % (int)tw];
+  // tap (ki, kj) of a record centred at (lk, lj) lands on this cell when ki = ck_ - lk + sy, kj = cj - lj + sx
+  const int cjb = cj + j0 + 2 * sx, ckb = ck_ + k0 + 2 * sy;
+  float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+  for (int base = b; base < e; base += kTile * kTile) {
+    const int n = min(kTile * kTile, e - base);
+    __syncthreads();
+    if (tid < n) s_rec[tid] = __ldg(&rec[base + tid]);
+    __syncthreads();
+    if (!on_grid) continue;
+#pragma unroll 4
+    for (int i = 0; i < n; i++) {
+      const float4 r = s_rec[i];
+      const uint32_t cp = __float_as_uint(r.x);
+      const unsigned kj = (unsigned)(cjb - (int)(cp & 0xFFFFu)), ki = (unsigned)(ckb - (int)(cp >> 16));
+      if (kj < tw && ki < th) {
+        const float ckv = s_ck[tw * ki + kj];
+        const float wt = r.y;
+        ax = __fadd_rn(ax, __fmul_rn(wt, ckv));
+        ay = __fadd_rn(ay, __fmul_rn(wt, __fmul_rn(ckv, ckv)));
+        az = __fadd_rn(az, __fmul_rn(__fmul_rn(wt, r.z), ckv));
+        aw = __fadd_rn(aw, __fmul_rn(__fmul_rn(wt, r.w), ckv));
       }
-      __syncwarp();
     }
   }
-  // normalise (src/functions.cu:1537-1558) and write the tile
-  for (int cc = lane; cc < kTile * kTile; cc += 32) {
-    const unsigned ck_ = cc / kTile, cj = cc - ck_ * kTile;
-    if (cj >= lim_j || ck_ >= lim_k) continue;
-    const float4 a = s_acc[ck_ * kTileStride + cj];
-    float weight = 0.f, orr = 0.f, oi = 0.f;
-    if (a.y != 0.0f && a.x != 0.0f) {
-      weight = __fdiv_rn(__fmul_rn(a.x, a.x), a.y);
-      orr = __fdiv_rn(a.z, a.x);
-      oi = __fdiv_rn(a.w, a.x);
-    }
-    const long cell = (long)(k0 + ck_) * N + (j0 + cj);
-    out_w[cell] = weight;
-    out_V[cell] = make_float2(orr, oi);
+  if (!on_grid) return;
+  // normalise (src/functions.cu:1537-1558) and write the cell
+  float weight = 0.f, orr = 0.f, oi = 0.f;
+  if (ay != 0.0f && ax != 0.0f) {
+    weight = __fdiv_rn(__fmul_rn(ax, ax), ay);
+    orr = __fdiv_rn(az, ax);
+    oi = __fdiv_rn(aw, ax);
   }
+  out_w[cell] = weight;
+  out_V[cell] = make_float2(orr, oi);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -557,24 +545,14 @@ struct PhaseTimer {
 };
 
 // Replay of the sorted pair records tile by tile (rec, tstart, tend -> gw, gV): tiles in decreasing order of their
-// sample count, one warp per tile. ordk / ord: ntiles words each; sort_tmp: gvm_sort_temp_bytes(ntiles).
+// sample count, one block of 256 threads (one per cell) per tile. ordk / ord: ntiles words each; sort_tmp: gvm_sort_temp_bytes(ntiles).
 int tile_replay_raw(uint32_t* ordk, uint32_t* ord, void* sort_tmp, const int* tstart, const int* tend, const float4* rec,
                     const float* ck, float* gw, float2* gV, long ntiles, int ntx, int ck_m, int ck_n, int sx, int sy,
                     long M, long N, cudaStream_t stream) {
   k_tile_order_keys<<<(int)((ntiles + 255) / 256), 256, 0, stream>>>(tstart, tend, ntiles, ordk, ord);
   WG_CUDA(cudaGetLastError());
   if (gvm_sort_pairs_u32(ordk, ord, (size_t)ntiles, 31, sort_tmp, stream)) return 1;
-  const int taps = (2 * sx + 1) * (2 * sy + 1);
-  const int rounds = (taps + 31) / 32;
-#define GVM_GRID_TILES(R) \
-  k_grid_tiles<R><<<(unsigned)ntiles, 32, 0, stream>>>(ord, tstart, tend, rec, ck, ck_m, ck_n, sx, sy, M, N, ntx, gw, gV)
-  if (rounds <= 1) GVM_GRID_TILES(1);
-  else if (rounds <= 2) GVM_GRID_TILES(2);
-  else if (rounds <= 3) GVM_GRID_TILES(3);
-  else if (rounds <= 4) GVM_GRID_TILES(4);
-  else if (rounds <= 6) GVM_GRID_TILES(6);
-  else GVM_GRID_TILES(10);
-#undef GVM_GRID_TILES
+  k_grid_tiles_cells<<<(unsigned)ntiles, kTile * kTile, 0, stream>>>(ord, tstart, tend, rec, ck, ck_m, ck_n, sx, sy, M, N, ntx, gw, gV);
   WG_CUDA(cudaGetLastError());
   return 0;
 }
