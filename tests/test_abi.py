@@ -35,6 +35,17 @@ def test_no_cpu_fallback():
         Engine(64, 64, -1e-5, 1e-5, 1e11)
 
 
+def test_preprocessing_entry_points_refuse_to_run_without_a_gpu():
+    """gvm_grid_reserve / gvm_weights (non-natural schemes) / gvm_grid_block fail loudly on a CPU-only box."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gpuvmem_b200 import lib
+    so = lib.load_library()
+    assert so.gvm_grid_reserve(0, 64, 64, 1000, 1) != 0
+    assert b"no CPU fallback" in so.gvm_last_error()
+
+
 def test_product_never_touches_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "gpuvmem_b200")):
         if "build" in dirpath:
