@@ -235,7 +235,7 @@ __device__ __forceinline__ void split2(float c, float s, uint32_t& hi, uint32_t&
 // down to 2^-16 as they are — no scaling instruction in the generators, and visibilities 2^15 times weaker than the
 // strongest one (which sets the fp16 scale) still get their correction (with E4M3 for Al a population 2^12 below the
 // maximum lost it: 1.9e-4 on that population in the numpy model). Each correction is ~2^-12 of its term and is kept to
-// 2^-3 / 2^-4: 1.4e-5 rms of the term (scripts/diag/umma_fp8mix.cu; the third fp16 product kept it at
+// 2^-3 / 2^-4: 1.4e-5 rms of the term (scripts/diag/mixed_split_model.py; the third fp16 product kept it at
 // 1e-7 — both are at or below the 1.2e-5 of the phases).
 template <bool kIsA>
 __device__ __forceinline__ void split_mixed(float c, float s, uint32_t& hi, uint32_t& first8, uint32_t& second8) {
